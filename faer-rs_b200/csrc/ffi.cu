@@ -1,0 +1,192 @@
+// extern "C" boundary: the symbols declared in include/faer_b200.h.
+// Each entry point mirrors the faer-ffi function of the same name (faer-ffi/src/lib.rs, cited per function in the
+// header): same argument order and meaning, by-value PODs, synchronous on return, abort() on precondition
+// violations. Host buffers are staged; device buffers are used in place.
+#include "../../include/faer_b200.h"
+#include "runtime.cuh"
+
+#include <atomic>
+#include <cstring>
+
+using namespace fb;
+
+namespace {
+
+std::atomic<int> g_par_tag{FaerV0_24_ParTag_Rayon};
+std::atomic<size_t> g_par_threads{0};
+
+inline size_t scalar_elem_f64() { return sizeof(double); }
+
+struct Mat {
+  StagedMat s;
+  Mat(FaerV0_24_MatRef m, cudaStream_t st)
+      : s(m.ptr, (i64)m.nrows, (i64)m.ncols, (i64)m.row_stride, (i64)m.col_stride, sizeof(double), true, false, st) {}
+  Mat(FaerV0_24_MatMut m, bool copy_in, cudaStream_t st)
+      : s(m.ptr, (i64)m.nrows, (i64)m.ncols, (i64)m.row_stride, (i64)m.col_stride, sizeof(double), copy_in, true, st) {}
+};
+
+inline double read_scalar_f64(const FaerV0_24_Scalar* p) {
+  FB_ASSERT(p != nullptr, "null scalar pointer");
+  double v;
+  if (is_device_pointer(p)) {
+    FB_CUDA_CHECK(cudaMemcpy(&v, p, sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    memcpy(&v, p, sizeof(double));
+  }
+  return v;
+}
+
+void finish_all(cudaStream_t st, std::initializer_list<StagedMat*> mats) {
+  // the compute must be complete before input mirrors return to the pool; calls are synchronous anyway
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (auto* m : mats) m->finish();
+}
+
+void solve_tri(FaerV0_24_MatRef T, FaerV0_24_MatMut rhs, bool lower, bool unit) {
+  require_device();
+  cudaStream_t st = current_stream();
+  FB_ASSERT(T.nrows == T.ncols && rhs.nrows == T.ncols, "triangular solve shape mismatch");
+  Mat t(T, st);
+  Mat r(rhs, true, st);
+  if (lower)
+    solve_lower_triangular_in_place_f64(st, t.s.view<const double>(), unit, r.s.view<double>());
+  else
+    solve_upper_triangular_in_place_f64(st, t.s.view<const double>(), unit, r.s.view<double>());
+  finish_all(st, {&t.s, &r.s});
+}
+
+}  // namespace
+
+extern "C" {
+
+void libfaer_v0_23_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
+                              const FaerV0_24_Scalar* alpha, FaerV0_24_Par par) {
+  (void)par;
+  require_device();
+  FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
+  cudaStream_t st = current_stream();
+  const double a = read_scalar_f64(alpha);
+  Mat c(C, accum == FaerV0_24_Accum_Add, st);
+  Mat lhs(A, st), rhs(B, st);
+  gemm_f64(st, c.s.view<double>(), RECT, accum == FaerV0_24_Accum_Add ? 1 : 0, lhs.s.view<const double>(), RECT,
+           rhs.s.view<const double>(), RECT, a);
+  finish_all(st, {&c.s, &lhs.s, &rhs.s});
+}
+
+void libfaer_v0_23_matmul_triangular_f64(FaerV0_24_MatMut C, FaerV0_24_Block C_block, FaerV0_24_Accum accum,
+                                         FaerV0_24_MatRef A, FaerV0_24_Block A_block, FaerV0_24_MatRef B,
+                                         FaerV0_24_Block B_block, const FaerV0_24_Scalar* alpha, FaerV0_24_Par par) {
+  (void)par;
+  require_device();
+  FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
+  cudaStream_t st = current_stream();
+  const double a = read_scalar_f64(alpha);
+  const bool copy_in = accum == FaerV0_24_Accum_Add || C_block != FaerV0_24_Block_Rectangular;
+  Mat c(C, copy_in, st);
+  Mat lhs(A, st), rhs(B, st);
+  gemm_f64(st, c.s.view<double>(), (int)C_block, accum == FaerV0_24_Accum_Add ? 1 : 0, lhs.s.view<const double>(),
+           (int)A_block, rhs.s.view<const double>(), (int)B_block, a);
+  finish_all(st, {&c.s, &lhs.s, &rhs.s});
+}
+
+void libfaer_v0_23_solve_triangular_lower_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs,
+                                                       FaerV0_24_Par par) {
+  (void)L_conj; (void)par;  // conjugation is the identity for real scalars
+  solve_tri(L, rhs, true, false);
+}
+void libfaer_v0_23_solve_triangular_upper_in_place_f64(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs,
+                                                       FaerV0_24_Par par) {
+  (void)U_conj; (void)par;
+  solve_tri(U, rhs, false, false);
+}
+void libfaer_v0_23_solve_unit_triangular_lower_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj,
+                                                            FaerV0_24_MatMut rhs, FaerV0_24_Par par) {
+  (void)L_conj; (void)par;
+  solve_tri(L, rhs, true, true);
+}
+void libfaer_v0_23_solve_unit_triangular_upper_in_place_f64(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj,
+                                                            FaerV0_24_MatMut rhs, FaerV0_24_Par par) {
+  (void)U_conj; (void)par;
+  solve_tri(U, rhs, false, true);
+}
+
+// ---- LLT ----
+FaerV0_24_LltParams libfaer_v0_23_LltParams_f64(void) {
+  // reference defaults: faer/src/linalg/cholesky/ldlt/factor.rs:705-714
+  return FaerV0_24_LltParams{64, 128};
+}
+
+FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_f64(size_t dim, FaerV0_24_Par par,
+                                                               FaerV0_24_LltParams params) {
+  (void)par; (void)params;
+  // reference: temp_mat_scratch::<T>(dim, 1) (llt/factor.rs:58-66). The GPU path keeps its (tiny) workspace in
+  // the internal device pool, but reports the reference's requirement so callers allocate identically.
+  return FaerV0_24_Layout{dim * sizeof(double), 64};
+}
+
+FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_LltRegularization regularization,
+                                                          FaerV0_24_Par par, FaerV0_24_MemAlloc mem,
+                                                          FaerV0_24_LltParams params) {
+  (void)par; (void)mem;
+  require_device();
+  FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
+  cudaStream_t st = current_stream();
+  double delta = 0.0, eps = 0.0;
+  if (regularization.dynamic_regularization_delta)
+    delta = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_delta);
+  if (regularization.dynamic_regularization_epsilon)
+    eps = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_epsilon);
+  Mat a(A, true, st);
+  LltResult r = llt_cholesky_in_place_f64(st, a.s.view<double>(), delta, eps,
+                                          LltParams{params.recursion_threshold, params.block_size});
+  finish_all(st, {&a.s});
+  FaerV0_24_LltStatus out;
+  memset(&out, 0, sizeof(out));
+  if (r.ok) {
+    out.tag = FaerV0_24_LltStatus_Ok;
+    out.ok.dynamic_regularization_count = r.dynamic_regularization_count;
+  } else {
+    out.tag = FaerV0_24_LltStatus_NonPositivePivot;
+    out.non_positive_pivot.index = r.non_positive_pivot_index;
+  }
+  return out;
+}
+
+// ---- global par / alloc ----
+FaerV0_24_Par libfaer_v0_23_get_global_par(void) {
+  FaerV0_24_Par p;
+  p.tag = (FaerV0_24_ParTag)g_par_tag.load();
+  p.nthreads = g_par_threads.load();
+  return p;
+}
+void libfaer_v0_23_set_global_par(FaerV0_24_Par par) {
+  g_par_tag.store((int)par.tag);
+  g_par_threads.store(par.nthreads);
+}
+void* libfaer_v0_23_alloc(size_t size, size_t align) {
+  // reference: std::alloc::alloc(Layout::from_size_align(size, align)) (faer-ffi/src/lib.rs:2537-2552)
+  if (align < sizeof(void*)) align = sizeof(void*);
+  void* p = nullptr;
+  if (posix_memalign(&p, align, size ? size : 1) != 0) return nullptr;
+  return p;
+}
+void libfaer_v0_23_dealloc(void* ptr, size_t size, size_t align) {
+  (void)size; (void)align;
+  free(ptr);
+}
+
+// ---- extensions ----
+int faer_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+void faer_b200_set_stream(void* cuda_stream) { set_current_stream((cudaStream_t)cuda_stream); }
+unsigned long long faer_b200_launch_count(void) { return g_launch_count; }
+void faer_b200_release_workspace(void) { ws_release_all(); }
+const char* faer_b200_version(void) { return "faer_b200 0.1 (faer-ffi v0_23 ABI subset, sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+// f64 GEMM / structured GEMM kernel, see gemm_f64.cuh for the reference semantics it implements.
+//
+// Design (B200, sm_100a):
+//   * math: mma.sync.m8n8k4.f64 -> DMMA.8x8x4 (the only f64 tensor op sm_100a has; tcgen05 has no f64 kind).
+//     64 f64 FMA/clk/SM => a 128x128x16 CTA k-step is 4096 clk of tensor work, so one __syncthreads per
+//     k-step and a 4-stage cp.async ring keep the DMMA pipe fed with large slack on smem/L2/HBM bandwidth.
+//   * operands staged with cp.async (16 B vectors when the view is aligned, 8 B otherwise => any stride,
+//     any sign) into padded shared tiles; pad of 4 doubles makes every fragment load (8 rows x 4 k of
+//     8-byte words per half-warp) hit 16 distinct 8-byte banks.
+//   * structure handling: triangular inputs are masked in shared memory after the tile lands (only tiles
+//     that intersect the diagonal pay the extra pass), fully-masked k-ranges are skipped, triangular dst
+//     tiles above/below the diagonal exit immediately and diagonal tiles mask the store.
+#include "gemm_f64.cuh"
+
+namespace fb {
+
+namespace {
+
+template <int WARPS_M_, int WARPS_N_, int WMI_, int WNI_, int BK_, int STAGES_>
+struct TileCfg {
+  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, WMI = WMI_, WNI = WNI_, BK = BK_, STAGES = STAGES_;
+  static constexpr int BM = WARPS_M * WMI * 8;
+  static constexpr int BN = WARPS_N * WNI * 8;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+};
+
+// One operand tile: `ROWS` indices along the non-contracted dim (mn) x BK along k.
+// KMAJOR: smem[mn][k] (ld = BK+4) else smem[k][mn] (ld = ROWS+4).
+template <int ROWS, int BK, bool KMAJOR>
+struct OpTile {
+  static constexpr int LD = KMAJOR ? BK + 4 : ROWS + 4;
+  static constexpr int SIZE = KMAJOR ? ROWS * LD : BK * LD;
+  __device__ static __forceinline__ int idx(int mn, int kk) { return KMAJOR ? mn * LD + kk : kk * LD + mn; }
+};
+
+// Global -> shared copy of one operand tile. Element (mn, kk) lives at g + (mn0+mn)*s_mn + (k0+kk)*s_k.
+template <int ROWS, int BK, bool KMAJOR, bool VEC, int THREADS>
+__device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ g, i64 s_mn, i64 s_k,
+                                          int mn0, int k0, int MN, int K, int tid) {
+  using T = OpTile<ROWS, BK, KMAJOR>;
+  if constexpr (VEC) {
+    constexpr int CHUNKS = ROWS * BK / 2;
+    static_assert(CHUNKS % THREADS == 0, "tile/threads mismatch");
+#pragma unroll
+    for (int it = 0; it < CHUNKS / THREADS; ++it) {
+      int c = it * THREADS + tid;
+      int mn, kk, nvalid;
+      const double* src;
+      if constexpr (KMAJOR) {
+        mn = c / (BK / 2);
+        kk = (c % (BK / 2)) * 2;
+        int rem = K - (k0 + kk);
+        nvalid = (mn0 + mn < MN) ? (rem < 0 ? 0 : (rem > 2 ? 2 : rem)) : 0;
+        src = g + (i64)(mn0 + mn) * s_mn + (i64)(k0 + kk);
+      } else {
+        kk = c / (ROWS / 2);
+        mn = (c % (ROWS / 2)) * 2;
+        int rem = MN - (mn0 + mn);
+        nvalid = (k0 + kk < K) ? (rem < 0 ? 0 : (rem > 2 ? 2 : rem)) : 0;
+        src = g + (i64)(mn0 + mn) + (i64)(k0 + kk) * s_k;
+      }
+      if (nvalid == 0) src = g;
+      cp_async_16(s + T::idx(mn, kk), src, nvalid * 8);
+    }
+  } else {
+    constexpr int ELEMS = ROWS * BK;
+    static_assert(ELEMS % THREADS == 0, "tile/threads mismatch");
+#pragma unroll
+    for (int it = 0; it < ELEMS / THREADS; ++it) {
+      int e = it * THREADS + tid;
+      int mn, kk;
+      if constexpr (KMAJOR) {
+        mn = e / BK;
+        kk = e % BK;
+      } else {
+        kk = e / ROWS;
+        mn = e % ROWS;
+      }
+      bool ok = (mn0 + mn < MN) && (k0 + kk < K);
+      const double* src = ok ? g + (i64)(mn0 + mn) * s_mn + (i64)(k0 + kk) * s_k : g;
+      cp_async_8(s + T::idx(mn, kk), src, ok ? 8 : 0);
+    }
+  }
+}
+
+// rel > 0 : kept side of a lower-triangular operand; rel == 0 : diagonal.
+// lhs (m x k): row = mn, col = k  -> rel_lower = mn - k
+// rhs (k x n): row = k,  col = mn -> rel_lower = k - mn
+template <int ROWS, int BK, bool KMAJOR, int THREADS>
+__device__ __forceinline__ void fixup_tile(double* s, int structure, bool is_rhs, int mn0, int k0, int tid) {
+  using T = OpTile<ROWS, BK, KMAJOR>;
+  const bool lower = is_lower(structure);
+  const double diagval = is_unit(structure) ? 1.0 : 0.0;
+  const bool keepdiag = !(is_unit(structure) || is_strict(structure));
+  for (int e = tid; e < ROWS * BK; e += THREADS) {
+    int mn = e % ROWS, kk = e / ROWS;
+    int rel = is_rhs ? (k0 + kk) - (mn0 + mn) : (mn0 + mn) - (k0 + kk);
+    if (!lower) rel = -rel;
+    if (rel < 0)
+      s[T::idx(mn, kk)] = 0.0;
+    else if (rel == 0 && !keepdiag)
+      s[T::idx(mn, kk)] = diagval;
+  }
+}
+
+// does the (mn0..mn0+ROWS) x (k0..k0+BK) tile of a structured operand need masking?
+__device__ __forceinline__ bool tile_needs_fixup(int structure, bool is_rhs, int mn0, int rows, int k0, int bk) {
+  if (structure == RECT) return false;
+  // min/max of rel_lower over the tile
+  int lo, hi;
+  if (!is_rhs) {
+    lo = mn0 - (k0 + bk - 1);
+    hi = (mn0 + rows - 1) - k0;
+  } else {
+    lo = k0 - (mn0 + rows - 1);
+    hi = (k0 + bk - 1) - mn0;
+  }
+  if (!is_lower(structure)) {
+    int t = lo;
+    lo = -hi;
+    hi = -t;
+  }
+  (void)hi;
+  // entirely strictly inside the kept region <=> lo > 0
+  return lo <= 0;
+}
+
+template <class Cfg, bool AK, bool BNM, bool VEC>
+__global__ void __launch_bounds__(Cfg::THREADS) gemm_f64_kernel(const GemmF64Params p) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
+  constexpr int WMI = Cfg::WMI, WNI = Cfg::WNI;
+  using TA = OpTile<BM, BK, AK>;
+  using TB = OpTile<BN, BK, !BNM>;  // rhs: K-major when b_rs == 1
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * TA::SIZE;
+
+  // ---- tile coordinates (grouped rasterisation for L2 reuse) ----
+  constexpr int GROUP = 8;
+  int bid = blockIdx.x;
+  int width = GROUP * p.tiles_n;
+  int group_id = bid / width;
+  int first_m = group_id * GROUP;
+  int gsize = min(p.tiles_m - first_m, GROUP);
+  int tm = first_m + (bid % width) % gsize;
+  int tn = (bid % width) / gsize;
+  const int m0 = tm * BM, n0 = tn * BN;
+
+  // ---- dst structure: skip tiles with nothing to write ----
+  const int cs_ = p.c_struct;
+  if (is_lower(cs_)) {
+    if (m0 + BM - 1 < n0) return;
+  } else if (is_upper(cs_)) {
+    if (n0 + BN - 1 < m0) return;
+  }
+
+  // ---- contracted range after structure pruning ----
+  int k_begin = 0, k_end = p.k;
+  if (is_lower(p.a_struct)) k_end = min(k_end, m0 + BM);
+  if (is_upper(p.a_struct)) k_begin = max(k_begin, m0);
+  if (is_lower(p.b_struct)) k_begin = max(k_begin, n0);
+  if (is_upper(p.b_struct)) k_end = min(k_end, n0 + BN);
+  k_begin = (k_begin / BK) * BK;
+  const int nkt = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % Cfg::WARPS_M) * (WMI * 8);
+  const int wn0 = (warp / Cfg::WARPS_M) * (WNI * 8);
+
+  double acc[WMI][WNI][2];
+#pragma unroll
+  for (int i = 0; i < WMI; ++i)
+#pragma unroll
+    for (int j = 0; j < WNI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto load_stage = [&](int stage, int kt) {
+    const int k0 = k_begin + kt * BK;
+    load_tile<BM, BK, AK, VEC, THREADS>(As + stage * TA::SIZE, p.A, p.a_rs, p.a_cs, m0, k0, p.m, p.k, tid);
+    load_tile<BN, BK, !BNM, VEC, THREADS>(Bs + stage * TB::SIZE, p.B, p.b_cs, p.b_rs, n0, k0, p.n, p.k, tid);
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nkt) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int stage = kt % STAGES;
+    double* a_s = As + stage * TA::SIZE;
+    double* b_s = Bs + stage * TB::SIZE;
+    {
+      const int k0 = k_begin + kt * BK;
+      const bool fa = tile_needs_fixup(p.a_struct, false, m0, BM, k0, BK);
+      const bool fb_ = tile_needs_fixup(p.b_struct, true, n0, BN, k0, BK);
+      if (fa || fb_) {
+        if (fa) fixup_tile<BM, BK, AK, THREADS>(a_s, p.a_struct, false, m0, k0, tid);
+        if (fb_) fixup_tile<BN, BK, !BNM, THREADS>(b_s, p.b_struct, true, n0, k0, tid);
+        __syncthreads();
+      }
+    }
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < nkt) load_stage(nk % STAGES, nk);
+      cp_async_commit();
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double a[WMI], b[WNI];
+#pragma unroll
+      for (int i = 0; i < WMI; ++i) a[i] = a_s[TA::idx(wm0 + i * 8 + g, kk + t)];
+#pragma unroll
+      for (int j = 0; j < WNI; ++j) b[j] = b_s[TB::idx(wn0 + j * 8 + g, kk + t)];
+#pragma unroll
+      for (int i = 0; i < WMI; ++i)
+#pragma unroll
+        for (int j = 0; j < WNI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: dst = [dst +] alpha * acc, masked by dst structure ----
+  const bool c_low = is_lower(cs_), c_up = is_upper(cs_);
+  const bool c_nodiag = is_strict(cs_) || is_unit(cs_);
+  const double alpha = p.alpha;
+  const bool add = p.accum != 0;
+#pragma unroll
+  for (int i = 0; i < WMI; ++i) {
+    const int row = m0 + wm0 + i * 8 + g;
+    if (row >= p.m) continue;
+#pragma unroll
+    for (int j = 0; j < WNI; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = n0 + wn0 + j * 8 + 2 * t + e;
+        if (col >= p.n) continue;
+        if (c_low && (row < col || (row == col && c_nodiag))) continue;
+        if (c_up && (row > col || (row == col && c_nodiag))) continue;
+        double* cp = p.C + (i64)row * p.c_rs + (i64)col * p.c_cs;
+        double v = alpha * acc[i][j][e];
+        if (add) v += *cp;
+        *cp = v;
+      }
+    }
+  }
+}
+
+using CfgL = TileCfg<2, 4, 8, 4, 16, 4>;  // 128 x 128 x 16, 256 threads
+using CfgS = TileCfg<2, 2, 4, 4, 16, 4>;  // 64 x 64 x 16, 128 threads
+
+template <class Cfg, bool AK, bool BNM>
+constexpr size_t smem_bytes() {
+  return sizeof(double) * Cfg::STAGES * (OpTile<Cfg::BM, Cfg::BK, AK>::SIZE + OpTile<Cfg::BN, Cfg::BK, !BNM>::SIZE);
+}
+
+template <class Cfg, bool AK, bool BNM, bool VEC>
+void launch_cfg(cudaStream_t stream, GemmF64Params& p) {
+  p.tiles_m = (p.m + Cfg::BM - 1) / Cfg::BM;
+  p.tiles_n = (p.n + Cfg::BN - 1) / Cfg::BN;
+  constexpr size_t smem = smem_bytes<Cfg, AK, BNM>();
+  static bool configured = false;
+  if (!configured) {
+    FB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<Cfg, AK, BNM, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    configured = true;
+  }
+  long long tiles = (long long)p.tiles_m * p.tiles_n;
+  gemm_f64_kernel<Cfg, AK, BNM, VEC><<<(unsigned)tiles, Cfg::THREADS, smem, stream>>>(p);
+  FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+}
+
+template <bool AK, bool BNM, bool VEC>
+void launch_layout(cudaStream_t stream, GemmF64Params& p) {
+  long long tiles_l = (long long)((p.m + 127) / 128) * ((p.n + 127) / 128);
+  if (is_lower(p.c_struct) || is_upper(p.c_struct)) tiles_l = tiles_l / 2 + 1;
+  if (tiles_l >= 2 * 148)
+    launch_cfg<CfgL, AK, BNM, VEC>(stream, p);
+  else
+    launch_cfg<CfgS, AK, BNM, VEC>(stream, p);
+}
+
+inline int transpose_struct(int s) {
+  switch (s) {
+    case TRI_LOWER: return TRI_UPPER;
+    case TRI_UPPER: return TRI_LOWER;
+    case STRICT_LOWER: return STRICT_UPPER;
+    case STRICT_UPPER: return STRICT_LOWER;
+    case UNIT_LOWER: return UNIT_UPPER;
+    case UNIT_UPPER: return UNIT_LOWER;
+    default: return RECT;
+  }
+}
+
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+}  // namespace
+
+void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, int lhs_struct, VCD rhs, int rhs_struct,
+              double alpha) {
+  FB_ASSERT(dst.nrows == lhs.nrows && dst.ncols == rhs.ncols && lhs.ncols == rhs.nrows, "matmul shape mismatch");
+  if (dst_struct != RECT) FB_ASSERT(dst.nrows == dst.ncols, "triangular dst must be square");
+  if (lhs_struct != RECT) FB_ASSERT(lhs.nrows == lhs.ncols, "triangular lhs must be square");
+  if (rhs_struct != RECT) FB_ASSERT(rhs.nrows == rhs.ncols, "triangular rhs must be square");
+  if (dst.nrows == 0 || dst.ncols == 0) return;
+  if (lhs.ncols == 0 && accum != 0) return;
+  FB_ASSERT(dst.nrows < (1ll << 31) && dst.ncols < (1ll << 31) && lhs.ncols < (1ll << 31), "dimension too large");
+
+  // Prefer a unit row stride on dst: C^T = B^T A^T.
+  if (dst.rs != 1 && dst.cs == 1) {
+    VD d2 = dst.t();
+    VCD l2 = rhs.t(), r2 = lhs.t();
+    int ls = transpose_struct(rhs_struct), rs_ = transpose_struct(lhs_struct);
+    dst = d2; lhs = l2; rhs = r2;
+    dst_struct = transpose_struct(dst_struct);
+    lhs_struct = ls; rhs_struct = rs_;
+  }
+
+  GemmF64Params p;
+  p.m = (int)dst.nrows; p.n = (int)dst.ncols; p.k = (int)lhs.ncols;
+  p.A = lhs.ptr; p.a_rs = lhs.rs; p.a_cs = lhs.cs; p.a_struct = lhs_struct;
+  p.B = rhs.ptr; p.b_rs = rhs.rs; p.b_cs = rhs.cs; p.b_struct = rhs_struct;
+  p.C = dst.ptr; p.c_rs = dst.rs; p.c_cs = dst.cs; p.c_struct = dst_struct;
+  p.alpha = alpha; p.accum = accum;
+
+  // operand layouts
+  bool a_unit_m = (lhs.rs == 1) || lhs.nrows == 1;
+  bool a_unit_k = (lhs.cs == 1) || lhs.ncols == 1;
+  bool AK = !a_unit_m && a_unit_k;  // k contiguous
+  bool a_vec = AK ? (lhs.cs == 1 && (lhs.rs % 2 == 0)) : (lhs.rs == 1 && (lhs.cs % 2 == 0));
+  a_vec = a_vec && aligned16(lhs.ptr);
+  bool b_unit_k = (rhs.rs == 1) || rhs.nrows == 1;
+  bool b_unit_n = (rhs.cs == 1) || rhs.ncols == 1;
+  bool BNM = !b_unit_k && b_unit_n;  // n contiguous
+  bool b_vec = BNM ? (rhs.cs == 1 && (rhs.rs % 2 == 0)) : (rhs.rs == 1 && (rhs.cs % 2 == 0));
+  b_vec = b_vec && aligned16(rhs.ptr);
+  bool VEC = a_vec && b_vec;
+
+#define FB_DISPATCH(ak, bnm, vec)                                   \
+  if (AK == ak && BNM == bnm && VEC == vec) {                       \
+    launch_layout<ak, bnm, vec>(stream, p);                         \
+    return;                                                         \
+  }
+  FB_DISPATCH(false, false, true)
+  FB_DISPATCH(false, true, true)
+  FB_DISPATCH(true, false, true)
+  FB_DISPATCH(true, true, true)
+  FB_DISPATCH(false, false, false)
+  FB_DISPATCH(false, true, false)
+  FB_DISPATCH(true, false, false)
+  FB_DISPATCH(true, true, false)
+#undef FB_DISPATCH
+}
+
+}  // namespace fb

@@ -1,0 +1,44 @@
+// Host-side mirror of faer::linalg for f64 (the functions SURVEY.md §8a puts on the hot path).
+// Names, argument meaning and error behaviour follow the Rust surface; every function launches on `stream`
+// and operates on DEVICE views (the C ABI in ffi.cu stages host buffers).
+#pragma once
+#include "common.cuh"
+#include "gemm_f64.cuh"
+
+namespace fb {
+
+// ---- triangular_solve (reference: faer/src/linalg/triangular_solve.rs:220-419) ----
+void solve_lower_triangular_in_place_f64(cudaStream_t stream, VCD tril, bool unit, VD rhs);
+void solve_upper_triangular_in_place_f64(cudaStream_t stream, VCD triu, bool unit, VD rhs);
+
+// ---- cholesky::llt::factor (reference: faer/src/linalg/cholesky/llt/factor.rs:68-97) ----
+struct LltParams {
+  size_t recursion_threshold;  // faer default 64  (ldlt/factor.rs:705-714); GPU path: leaf lives in one CTA
+  size_t block_size;           // faer default 128
+};
+struct LltResult {
+  bool ok;
+  size_t dynamic_regularization_count;  // valid if ok
+  size_t non_positive_pivot_index;      // valid if !ok
+};
+// In-place lower Cholesky of the lower triangle of A (strict upper triangle untouched).
+// `reg_delta`/`reg_eps`: dynamic regularisation (active iff both > 0), reference llt/factor.rs:85-87.
+LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, LltParams params);
+
+// ---- lu::partial_pivoting::factor (reference: faer/src/linalg/lu/partial_pivoting/factor.rs:234-295) ----
+struct PartialPivLuParams {
+  size_t recursion_threshold;  // faer default 16
+  size_t block_size;           // faer default 64 (unused by the reference's recursive code)
+  size_t par_threshold;
+};
+// In-place P A = L U. perm_fwd / perm_inv: DEVICE arrays of nrows indices (u32 if idx_bytes==4 else u64).
+// Returns the transposition count.
+size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, void* perm_inv, int idx_bytes,
+                                   PartialPivLuParams params);
+
+// ---- device workspace (grow-only pool, one per process) ----
+void* ws_alloc(size_t bytes);  // 256-byte aligned device memory, cached across calls
+void ws_free(void* p);
+void ws_release_all();
+
+}  // namespace fb

@@ -1,0 +1,184 @@
+// Process-wide runtime state: stream, launch counter, device workspace pool, host<->device staging.
+#include "runtime.cuh"
+
+#include <mutex>
+#include <vector>
+
+namespace fb {
+
+unsigned long long g_launch_count = 0;
+
+namespace {
+cudaStream_t g_stream = nullptr;
+std::mutex g_pool_mutex;
+struct PoolBlock {
+  void* ptr;
+  size_t bytes;
+  bool in_use;
+};
+std::vector<PoolBlock> g_pool;
+bool g_checked_device = false;
+}  // namespace
+
+cudaStream_t current_stream() { return g_stream; }
+void set_current_stream(cudaStream_t s) { g_stream = s; }
+
+void require_device() {
+  if (g_checked_device) return;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    fprintf(stderr,
+            "faer_b200: no CUDA device available (%s). This backend has no CPU fallback; refusing to compute.\n",
+            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    abort();
+  }
+  g_checked_device = true;
+}
+
+void* ws_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 256;
+  bytes = (bytes + 255) & ~(size_t)255;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  int best = -1;
+  for (int i = 0; i < (int)g_pool.size(); ++i) {
+    if (!g_pool[i].in_use && g_pool[i].bytes >= bytes) {
+      if (best < 0 || g_pool[i].bytes < g_pool[best].bytes) best = i;
+    }
+  }
+  if (best >= 0 && g_pool[best].bytes <= 2 * bytes + (1 << 20)) {
+    g_pool[best].in_use = true;
+    return g_pool[best].ptr;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    // drop cached free blocks and retry once
+    for (auto it = g_pool.begin(); it != g_pool.end();) {
+      if (!it->in_use) {
+        cudaFree(it->ptr);
+        it = g_pool.erase(it);
+      } else {
+        ++it;
+      }
+    }
+    (void)cudaGetLastError();
+    FB_CUDA_CHECK(cudaMalloc(&p, bytes));
+  }
+  g_pool.push_back(PoolBlock{p, bytes, true});
+  return p;
+}
+
+void ws_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (auto& b : g_pool)
+    if (b.ptr == p) {
+      b.in_use = false;
+      return;
+    }
+  FB_ASSERT(false, "ws_free of unknown pointer");
+}
+
+void ws_release_all() {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (auto it = g_pool.begin(); it != g_pool.end();) {
+    if (!it->in_use) {
+      cudaFree(it->ptr);
+      it = g_pool.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+bool is_device_pointer(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// ---- staging -------------------------------------------------------------------------------------
+StagedMat::StagedMat(const void* host_or_dev, i64 nrows, i64 ncols, i64 rs, i64 cs, size_t elem, bool copy_in,
+                     bool copy_out, cudaStream_t stream)
+    : orig_((void*)host_or_dev), nrows_(nrows), ncols_(ncols), rs_(rs), cs_(cs), elem_(elem), copy_out_(copy_out),
+      stream_(stream) {
+  dev_ptr_ = orig_;
+  dev_rs_ = rs;
+  dev_cs_ = cs;
+  if (nrows == 0 || ncols == 0 || is_device_pointer(host_or_dev)) {
+    staged_ = false;
+    return;
+  }
+  staged_ = true;
+  char* base = (char*)orig_;
+  if (rs == 1 && cs >= nrows) {
+    mode_ = 1;  // column-major rectangle
+    i64 ld = (nrows + 1) & ~(i64)1;
+    buf_ = ws_alloc((size_t)ld * ncols * elem);
+    dev_ptr_ = buf_;
+    dev_rs_ = 1;
+    dev_cs_ = ld;
+    if (copy_in)
+      FB_CUDA_CHECK(cudaMemcpy2DAsync(buf_, (size_t)ld * elem, base, (size_t)cs * elem, (size_t)nrows * elem,
+                                      (size_t)ncols, cudaMemcpyHostToDevice, stream));
+  } else if (cs == 1 && rs >= ncols) {
+    mode_ = 2;  // row-major rectangle
+    i64 ld = (ncols + 1) & ~(i64)1;
+    buf_ = ws_alloc((size_t)ld * nrows * elem);
+    dev_ptr_ = buf_;
+    dev_rs_ = ld;
+    dev_cs_ = 1;
+    if (copy_in)
+      FB_CUDA_CHECK(cudaMemcpy2DAsync(buf_, (size_t)ld * elem, base, (size_t)rs * elem, (size_t)ncols * elem,
+                                      (size_t)nrows, cudaMemcpyHostToDevice, stream));
+  } else {
+    mode_ = 3;  // arbitrary strides: mirror the spanned address range (always copied in, so that the
+                // untouched gaps are written back unchanged)
+    i64 lo = 0, hi = 0;
+    i64 r = (nrows - 1) * rs, c = (ncols - 1) * cs;
+    if (r < 0) lo += r; else hi += r;
+    if (c < 0) lo += c; else hi += c;
+    span_lo_ = lo;
+    span_elems_ = hi - lo + 1;
+    buf_ = ws_alloc((size_t)span_elems_ * elem);
+    FB_CUDA_CHECK(cudaMemcpyAsync(buf_, base + lo * (i64)elem, (size_t)span_elems_ * elem, cudaMemcpyHostToDevice,
+                                  stream));
+    dev_ptr_ = (char*)buf_ - lo * (i64)elem;
+  }
+}
+
+void StagedMat::finish() {
+  if (!staged_ || done_) return;
+  done_ = true;
+  char* base = (char*)orig_;
+  if (copy_out_) {
+    if (mode_ == 1)
+      FB_CUDA_CHECK(cudaMemcpy2DAsync(base, (size_t)cs_ * elem_, buf_, (size_t)dev_cs_ * elem_, (size_t)nrows_ * elem_,
+                                      (size_t)ncols_, cudaMemcpyDeviceToHost, stream_));
+    else if (mode_ == 2)
+      FB_CUDA_CHECK(cudaMemcpy2DAsync(base, (size_t)rs_ * elem_, buf_, (size_t)dev_rs_ * elem_, (size_t)ncols_ * elem_,
+                                      (size_t)nrows_, cudaMemcpyDeviceToHost, stream_));
+    else
+      FB_CUDA_CHECK(cudaMemcpyAsync(base + span_lo_ * (i64)elem_, buf_, (size_t)span_elems_ * elem_,
+                                    cudaMemcpyDeviceToHost, stream_));
+    FB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+  ws_free(buf_);
+  buf_ = nullptr;
+}
+
+StagedMat::~StagedMat() {
+  if (staged_ && !done_) {
+    // not finished explicitly: release without copying back
+    FB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    ws_free(buf_);
+  }
+}
+
+}  // namespace fb

@@ -1,0 +1,125 @@
+// G3: in-place triangular solve  rhs <- op(T)^-1 rhs  (f64).
+//
+// Reference semantics: faer/src/linalg/triangular_solve.rs:220-419 (public entry points),
+// 420-576 (recursive split: solve top, rhs_bot -= T_bot_left * rhs_top, solve bottom),
+// 200-211 (`block_size` split rule), 577-604 (upper = lower on reversed views),
+// 16-198 (leaves: reciprocal of the diagonal, then multiply).
+//
+// B200 mapping: the recursion stays on the host (it is O(n/32) launches); every off-diagonal update is a
+// DMMA GEMM launch (gemm_f64); the <=32-wide diagonal leaves run as one thread per right-hand-side column
+// with the rhs tile staged through shared memory so global accesses are coalesced for either rhs layout.
+#include "linalg_f64.cuh"
+
+namespace fb {
+
+namespace {
+
+constexpr int LEAF = 32;       // diagonal leaf size
+constexpr int LEAF_COLS = 128; // rhs columns per CTA (= threads)
+
+// Solve T x = b for every column of the (n x ncols) rhs tile, n <= LEAF. T lower triangular (n x n).
+__global__ void __launch_bounds__(LEAF_COLS) trsm_leaf_lower_kernel(const double* __restrict__ T, i64 t_rs, i64 t_cs,
+                                                                     int n, int unit, double* __restrict__ R, i64 r_rs,
+                                                                     i64 r_cs, i64 ncols) {
+  __shared__ double Ts[LEAF][LEAF + 1];
+  __shared__ double Rs[LEAF][LEAF_COLS + 1];
+  __shared__ double Tinv[LEAF];
+  const int tid = threadIdx.x;
+  const i64 c0 = (i64)blockIdx.x * LEAF_COLS;
+  const int nc = (int)min((i64)LEAF_COLS, ncols - c0);
+
+  for (int e = tid; e < n * n; e += LEAF_COLS) {
+    int i = e % n, j = e / n;
+    Ts[i][j] = (j <= i) ? T[i * t_rs + j * t_cs] : 0.0;
+  }
+  // stage rhs tile; iterate so that the unit-stride direction is the fast one
+  const bool row_fast = (r_rs == 1 || r_rs == -1);
+  if (row_fast) {
+    for (int e = tid; e < n * nc; e += LEAF_COLS) {
+      int i = e % n, c = e / n;
+      Rs[i][c] = R[i * r_rs + (c0 + c) * r_cs];
+    }
+  } else {
+    for (int e = tid; e < n * nc; e += LEAF_COLS) {
+      int c = e % nc, i = e / nc;
+      Rs[i][c] = R[i * r_rs + (c0 + c) * r_cs];
+    }
+  }
+  __syncthreads();
+  if (tid < n) Tinv[tid] = unit ? 1.0 : 1.0 / Ts[tid][tid];
+  __syncthreads();
+
+  if (tid < nc) {
+    double x[LEAF];
+#pragma unroll
+    for (int i = 0; i < LEAF; ++i) {
+      if (i < n) {
+        double s = Rs[i][tid];
+#pragma unroll
+        for (int k = 0; k < LEAF; ++k)
+          if (k < i) s = fma(-Ts[i][k], x[k], s);
+        x[i] = s * Tinv[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LEAF; ++i)
+      if (i < n) Rs[i][tid] = x[i];
+  }
+  __syncthreads();
+  if (row_fast) {
+    for (int e = tid; e < n * nc; e += LEAF_COLS) {
+      int i = e % n, c = e / n;
+      R[i * r_rs + (c0 + c) * r_cs] = Rs[i][c];
+    }
+  } else {
+    for (int e = tid; e < n * nc; e += LEAF_COLS) {
+      int c = e % nc, i = e / nc;
+      R[i * r_rs + (c0 + c) * r_cs] = Rs[i][c];
+    }
+  }
+}
+
+// faer's split rule (reference: triangular_solve.rs:200-211)
+inline i64 split_size(i64 n) {
+  i64 base_rem = n / 2;
+  i64 sub;
+  if (n >= 32) sub = (base_rem + 15) / 16 * 16;
+  else if (n >= 16) sub = (base_rem + 7) / 8 * 8;
+  else if (n >= 8) sub = (base_rem + 3) / 4 * 4;
+  else sub = base_rem;
+  return n - sub;
+}
+
+void solve_lower_rec(cudaStream_t stream, VCD T, bool unit, VD rhs) {
+  const i64 n = T.nrows;
+  if (n == 0 || rhs.ncols == 0) return;
+  if (n <= LEAF) {
+    unsigned blocks = (unsigned)((rhs.ncols + LEAF_COLS - 1) / LEAF_COLS);
+    trsm_leaf_lower_kernel<<<blocks, LEAF_COLS, 0, stream>>>(T.ptr, T.rs, T.cs, (int)n, unit ? 1 : 0, rhs.ptr, rhs.rs,
+                                                              rhs.cs, rhs.ncols);
+    FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+    return;
+  }
+  const i64 bs = split_size(n);
+  VCD T00 = T.sub(0, 0, bs, bs), T10 = T.sub(bs, 0, n - bs, bs), T11 = T.sub(bs, bs, n - bs, n - bs);
+  VD top = rhs.sub(0, 0, bs, rhs.ncols), bot = rhs.sub(bs, 0, n - bs, rhs.ncols);
+  solve_lower_rec(stream, T00, unit, top);
+  gemm_f64(stream, bot, 1, T10, cv(top), -1.0);
+  solve_lower_rec(stream, T11, unit, bot);
+}
+
+}  // namespace
+
+void solve_lower_triangular_in_place_f64(cudaStream_t stream, VCD tril, bool unit, VD rhs) {
+  FB_ASSERT(tril.nrows == tril.ncols && rhs.nrows == tril.ncols, "triangular solve shape mismatch");
+  solve_lower_rec(stream, tril, unit, rhs);
+}
+
+void solve_upper_triangular_in_place_f64(cudaStream_t stream, VCD triu, bool unit, VD rhs) {
+  FB_ASSERT(triu.nrows == triu.ncols && rhs.nrows == triu.ncols, "triangular solve shape mismatch");
+  if (triu.nrows == 0 || rhs.ncols == 0) return;
+  solve_lower_rec(stream, triu.rev_rows_cols(), unit, rhs.rev_rows());
+}
+
+}  // namespace fb

@@ -1,0 +1,150 @@
+"""Host-side mirror of faer::linalg for the hot path, over the C ABI (capi.py).
+
+Function names, argument order and error behaviour follow the reference's Rust surface so the parity tests
+read like faer's own tests:
+  matmul::matmul                      faer/src/linalg/matmul/mod.rs:1617-1660
+  matmul::triangular::matmul          faer/src/linalg/matmul/triangular.rs:1193-1245
+  triangular_solve::solve_*_in_place  faer/src/linalg/triangular_solve.rs:220-419
+  cholesky::llt::factor::cholesky_in_place   faer/src/linalg/cholesky/llt/factor.rs:68-97
+  lu::partial_pivoting::factor::lu_in_place  faer/src/linalg/lu/partial_pivoting/factor.rs:234-295
+Arguments are numpy arrays (host, staged by the library) or torch CUDA tensors (device, in place).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import (ACCUM_ADD, ACCUM_REPLACE, BLOCK_LOWER, BLOCK_RECT, BLOCK_STRICT_LOWER, BLOCK_STRICT_UPPER,  # noqa: F401
+                   BLOCK_UNIT_LOWER, BLOCK_UNIT_UPPER, BLOCK_UPPER, CONJ_NO, CONJ_YES)
+
+
+class Accum:
+    Replace = ACCUM_REPLACE
+    Add = ACCUM_ADD
+
+
+class BlockStructure:
+    Rectangular = BLOCK_RECT
+    TriangularLower = BLOCK_LOWER
+    TriangularUpper = BLOCK_UPPER
+    StrictTriangularLower = BLOCK_STRICT_LOWER
+    StrictTriangularUpper = BLOCK_STRICT_UPPER
+    UnitTriangularLower = BLOCK_UNIT_LOWER
+    UnitTriangularUpper = BLOCK_UNIT_UPPER
+
+
+def _check_f64(*xs):
+    for x in xs:
+        if capi._is_torch(x):
+            import torch
+            assert x.dtype == torch.float64, "f64 entry point needs float64 tensors"
+        else:
+            assert x.dtype == np.float64, "f64 entry point needs float64 arrays"
+
+
+def matmul(dst, accum: int, lhs, rhs, alpha: float, par=None) -> None:
+    """dst = [dst +] alpha * lhs * rhs  (Accum.Replace never reads dst)."""
+    _check_f64(dst, lhs, rhs)
+    lib = capi.load()
+    lib.libfaer_v0_23_matmul_f64(capi.mat_mut(dst), accum, capi.mat_ref(lhs), capi.mat_ref(rhs),
+                                 capi._scalar_f64(alpha), par or capi.par_default())
+
+
+def matmul_triangular(dst, dst_structure: int, accum: int, lhs, lhs_structure: int, rhs, rhs_structure: int,
+                      alpha: float, par=None) -> None:
+    _check_f64(dst, lhs, rhs)
+    lib = capi.load()
+    lib.libfaer_v0_23_matmul_triangular_f64(capi.mat_mut(dst), dst_structure, accum, capi.mat_ref(lhs), lhs_structure,
+                                            capi.mat_ref(rhs), rhs_structure, capi._scalar_f64(alpha),
+                                            par or capi.par_default())
+
+
+def _solve(name, tri, rhs, conj, par):
+    _check_f64(tri, rhs)
+    lib = capi.load()
+    getattr(lib, f"libfaer_v0_23_{name}_in_place_f64")(capi.mat_ref(tri), conj, capi.mat_mut(rhs),
+                                                       par or capi.par_default())
+
+
+def solve_lower_triangular_in_place(tril, rhs, conj: int = CONJ_NO, par=None) -> None:
+    _solve("solve_triangular_lower", tril, rhs, conj, par)
+
+
+def solve_upper_triangular_in_place(triu, rhs, conj: int = CONJ_NO, par=None) -> None:
+    _solve("solve_triangular_upper", triu, rhs, conj, par)
+
+
+def solve_unit_lower_triangular_in_place(tril, rhs, conj: int = CONJ_NO, par=None) -> None:
+    _solve("solve_unit_triangular_lower", tril, rhs, conj, par)
+
+
+def solve_unit_upper_triangular_in_place(triu, rhs, conj: int = CONJ_NO, par=None) -> None:
+    _solve("solve_unit_triangular_upper", triu, rhs, conj, par)
+
+
+# ---- LLT ------------------------------------------------------------------------------------------
+@dataclass
+class LltInfo:
+    dynamic_regularization_count: int
+
+
+class LltError(Exception):
+    """NonPositivePivot { index } (faer/src/linalg/cholesky/llt/factor.rs:21-24)."""
+
+    def __init__(self, index: int):
+        super().__init__(f"NonPositivePivot {{ index: {index} }}")
+        self.index = index
+
+
+def llt_params_default():
+    return capi.load().libfaer_v0_23_LltParams_f64()
+
+
+def cholesky_in_place(A, regularization=(0.0, 0.0), par=None, params=None) -> LltInfo:
+    """In-place LLT of the lower triangle of A. regularization = (delta, epsilon). Raises LltError."""
+    _check_f64(A)
+    lib = capi.load()
+    params = params or lib.libfaer_v0_23_LltParams_f64()
+    par = par or capi.par_default()
+    n = A.shape[0]
+    lay = lib.libfaer_v0_23_llt_factor_in_place_scratch_f64(n, par, params)
+    scratch = np.empty(lay.len_bytes + lay.align_bytes, dtype=np.uint8)
+    delta = C.c_double(float(regularization[0]))
+    eps = C.c_double(float(regularization[1]))
+    reg = capi.LltRegularization(C.cast(C.pointer(delta), C.c_void_p), C.cast(C.pointer(eps), C.c_void_p))
+    st = lib.libfaer_v0_23_llt_factor_in_place_f64(capi.mat_mut(A), reg, par,
+                                                   capi.MemAlloc(scratch.ctypes.data, scratch.size), params)
+    if st.tag == 0:
+        return LltInfo(int(st.value))
+    if st.tag == 1:
+        raise LltError(int(st.value))
+    raise RuntimeError("LltStatus::Unknown")
+
+
+# ---- partial-pivoting LU ---------------------------------------------------------------------------
+@dataclass
+class PartialPivLuInfo:
+    transposition_count: int
+
+
+def lu_in_place(A, perm, perm_inv, par=None, params=None) -> PartialPivLuInfo:
+    """In-place P A = L U. `perm`/`perm_inv`: uint32/uint64 arrays (numpy) or int32/int64 CUDA tensors of
+    length nrows; (P A)[i, :] = A[perm[i], :]."""
+    _check_f64(A)
+    lib = capi.load()
+    params = params or lib.libfaer_v0_23_PartialPivLuParams_f64()
+    par = par or capi.par_default()
+    isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
+    it = {4: "u32", 8: "u64"}[isz]
+    m, n = A.shape
+    lay = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_{it}_f64")(m, n, par, params)
+    scratch = np.empty(lay.len_bytes + lay.align_bytes, dtype=np.uint8)
+    st = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_{it}_f64")(
+        capi.mat_mut(A), capi.slice_mut(perm), capi.slice_mut(perm_inv), par,
+        capi.MemAlloc(scratch.ctypes.data, scratch.size), params)
+    if st.tag != 0:
+        raise RuntimeError("PartialPivLuStatus::Unknown")
+    return PartialPivLuInfo(int(st.value))

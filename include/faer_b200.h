@@ -1,0 +1,160 @@
+/*
+ * faer_b200.h — C ABI of the B200-native dense backend (libfaer_b200.so).
+ *
+ * Drop-in for the hot-path subset of faer-ffi's generated header: same include guard, same POD layouts,
+ * same symbol grammar `libfaer_v0_23_<fn>[_u32|_u64]_<dtype>` as /root/reference/faer-ffi/faer.h, so a C/C++
+ * caller of faer-ffi compiles and links against this library unchanged for the entry points below.
+ * Each declaration cites the reference interface it replaces (faer-ffi/src/lib.rs:LINE = Rust body,
+ * faer-ffi/faer.h:LINE = generated C declaration).
+ *
+ * Pointer semantics (extension of the reference, which is CPU-only): every matrix/slice pointer may be
+ *   - a HOST pointer  : staged to the GPU and back inside the call (the reference-facing path), or
+ *   - a DEVICE pointer: operated on in place (no copies); mixed calls are allowed per argument.
+ * Calls are synchronous on return, like the reference. Precondition violations abort() with a message
+ * (the reference panics inside extern "C", i.e. aborts).
+ * There is NO CPU fallback: without a CUDA device every compute entry point aborts.
+ */
+#ifndef LIBFAER_V0_24
+#define LIBFAER_V0_24
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums: faer-ffi/src/lib.rs:59-97 ---- */
+typedef enum FaerV0_24_Accum { FaerV0_24_Accum_Replace, FaerV0_24_Accum_Add } FaerV0_24_Accum;
+typedef enum FaerV0_24_Conj { FaerV0_24_Conj_No, FaerV0_24_Conj_Yes } FaerV0_24_Conj;
+typedef enum FaerV0_24_ParTag { FaerV0_24_ParTag_Seq, FaerV0_24_ParTag_Rayon } FaerV0_24_ParTag;
+typedef enum FaerV0_24_Block {
+  FaerV0_24_Block_Rectangular,
+  FaerV0_24_Block_TriangularLower,
+  FaerV0_24_Block_TriangularUpper,
+  FaerV0_24_Block_StrictTriangularLower,
+  FaerV0_24_Block_StrictTriangularUpper,
+  FaerV0_24_Block_UnitTriangularLower,
+  FaerV0_24_Block_UnitTriangularUpper
+} FaerV0_24_Block;
+
+/* ---- opaque scalar tags: faer-ffi/src/lib.rs:56-58 ---- */
+typedef struct FaerV0_24_Scalar FaerV0_24_Scalar;
+typedef struct FaerV0_24_Real FaerV0_24_Real;
+
+/* ---- views: faer-ffi/src/lib.rs:12-58 (strides in ELEMENTS, any sign) ---- */
+typedef struct FaerV0_24_MatRef { const void *ptr; size_t nrows; size_t ncols; ptrdiff_t row_stride; ptrdiff_t col_stride; } FaerV0_24_MatRef;
+typedef struct FaerV0_24_MatMut { void *ptr; size_t nrows; size_t ncols; ptrdiff_t row_stride; ptrdiff_t col_stride; } FaerV0_24_MatMut;
+typedef struct FaerV0_24_VecRef { const void *ptr; size_t len; ptrdiff_t stride; } FaerV0_24_VecRef;
+typedef struct FaerV0_24_VecMut { void *ptr; size_t len; ptrdiff_t stride; } FaerV0_24_VecMut;
+typedef struct FaerV0_24_SliceRef { const void *ptr; size_t len; } FaerV0_24_SliceRef;
+typedef struct FaerV0_24_SliceMut { void *ptr; size_t len; } FaerV0_24_SliceMut;
+
+/* ---- Par / scratch protocol: faer-ffi/src/lib.rs:76-128 ---- */
+typedef struct FaerV0_24_Par { enum FaerV0_24_ParTag tag; size_t nthreads; } FaerV0_24_Par;
+typedef struct FaerV0_24_Layout { size_t len_bytes; size_t align_bytes; } FaerV0_24_Layout;
+typedef struct FaerV0_24_MemAlloc { void *ptr; size_t len_bytes; } FaerV0_24_MemAlloc;
+
+/* ---- params: faer-ffi/src/lib.rs:650-688 ---- */
+typedef struct FaerV0_24_LltParams { size_t recursion_threshold; size_t block_size; } FaerV0_24_LltParams;
+typedef struct FaerV0_24_PartialPivLuParams { size_t recursion_threshold; size_t block_size; size_t par_threshold; } FaerV0_24_PartialPivLuParams;
+typedef struct FaerV0_24_QrParams { size_t blocking_threshold; size_t par_threshold; } FaerV0_24_QrParams;
+
+/* ---- LLT regularisation: faer-ffi/src/lib.rs:794-817 ---- */
+typedef struct FaerV0_24_LltRegularization {
+  const FaerV0_24_Real *dynamic_regularization_delta;
+  const FaerV0_24_Real *dynamic_regularization_epsilon;
+} FaerV0_24_LltRegularization;
+
+/* ---- status unions: faer-ffi/src/lib.rs:552-629, C layout faer-ffi/faer.h:383-469 ---- */
+typedef enum FaerV0_24_LltStatus_Tag { FaerV0_24_LltStatus_Ok, FaerV0_24_LltStatus_NonPositivePivot, FaerV0_24_LltStatus_Unknown } FaerV0_24_LltStatus_Tag;
+typedef struct FaerV0_24_LltStatus_FaerV0_24_Ok_Body { size_t dynamic_regularization_count; } FaerV0_24_LltStatus_FaerV0_24_Ok_Body;
+typedef struct FaerV0_24_LltStatus_FaerV0_24_NonPositivePivot_Body { size_t index; } FaerV0_24_LltStatus_FaerV0_24_NonPositivePivot_Body;
+typedef struct FaerV0_24_LltStatus {
+  FaerV0_24_LltStatus_Tag tag;
+  union {
+    FaerV0_24_LltStatus_FaerV0_24_Ok_Body ok;
+    FaerV0_24_LltStatus_FaerV0_24_NonPositivePivot_Body non_positive_pivot;
+  };
+} FaerV0_24_LltStatus;
+
+typedef enum FaerV0_24_PartialPivLuStatus_Tag { FaerV0_24_PartialPivLuStatus_Ok, FaerV0_24_PartialPivLuStatus_Unknown } FaerV0_24_PartialPivLuStatus_Tag;
+typedef struct FaerV0_24_PartialPivLuStatus_FaerV0_24_Ok_Body { size_t transposition_count; } FaerV0_24_PartialPivLuStatus_FaerV0_24_Ok_Body;
+typedef struct FaerV0_24_PartialPivLuStatus {
+  FaerV0_24_PartialPivLuStatus_Tag tag;
+  union { FaerV0_24_PartialPivLuStatus_FaerV0_24_Ok_Body ok; };
+} FaerV0_24_PartialPivLuStatus;
+
+typedef enum FaerV0_24_QrStatus_Tag { FaerV0_24_QrStatus_Ok, FaerV0_24_QrStatus_Unknown } FaerV0_24_QrStatus_Tag;
+typedef struct FaerV0_24_QrStatus_FaerV0_24_Ok_Body { size_t rank; } FaerV0_24_QrStatus_FaerV0_24_Ok_Body;
+typedef struct FaerV0_24_QrStatus {
+  FaerV0_24_QrStatus_Tag tag;
+  union { FaerV0_24_QrStatus_FaerV0_24_Ok_Body ok; };
+} FaerV0_24_QrStatus;
+
+/* =====================================================================================================
+ * Hot-path entry points
+ * ===================================================================================================== */
+
+/* matmul: C = [C +] alpha * A * B.   faer-ffi/src/lib.rs:855-871, faer-ffi/faer.h:4252-4257 */
+void libfaer_v0_23_matmul_f64(struct FaerV0_24_MatMut C, enum FaerV0_24_Accum accum, struct FaerV0_24_MatRef A,
+                              struct FaerV0_24_MatRef B, const struct FaerV0_24_Scalar *alpha, struct FaerV0_24_Par par);
+
+/* matmul_triangular.   faer-ffi/src/lib.rs:872-894, faer-ffi/faer.h:4306-4314 */
+void libfaer_v0_23_matmul_triangular_f64(struct FaerV0_24_MatMut C, enum FaerV0_24_Block C_block,
+                                         enum FaerV0_24_Accum accum, struct FaerV0_24_MatRef A,
+                                         enum FaerV0_24_Block A_block, struct FaerV0_24_MatRef B,
+                                         enum FaerV0_24_Block B_block, const struct FaerV0_24_Scalar *alpha,
+                                         struct FaerV0_24_Par par);
+
+/* triangular solves, in place.   faer-ffi/src/lib.rs:896-937, faer-ffi/faer.h:6130-6143 */
+void libfaer_v0_23_solve_triangular_lower_in_place_f64(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj L_conj,
+                                                       struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_triangular_upper_in_place_f64(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj,
+                                                       struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_unit_triangular_lower_in_place_f64(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj L_conj,
+                                                            struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_unit_triangular_upper_in_place_f64(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj,
+                                                            struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+
+/* LLT.   params: faer-ffi/src/lib.rs:650-654 (+408-456), faer.h:636; scratch: lib.rs:984-995; factor: lib.rs:996-1010, faer.h:4036-4040 */
+struct FaerV0_24_LltParams libfaer_v0_23_LltParams_f64(void);
+struct FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_f64(size_t dim, struct FaerV0_24_Par par,
+                                                                      struct FaerV0_24_LltParams params);
+struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(struct FaerV0_24_MatMut A,
+                                                                 struct FaerV0_24_LltRegularization regularization,
+                                                                 struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem,
+                                                                 struct FaerV0_24_LltParams params);
+
+/* partial-pivoting LU.   params: lib.rs:679-684, faer.h:648; scratch: lib.rs:1952-1965; factor: lib.rs:1966-1983, faer.h:4456-4461 */
+struct FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f64(void);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32_f64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_f64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u32_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
+
+/* global parallelism + allocation helpers.   faer-ffi/src/lib.rs:2521-2569, faer.h:724, 2034, 3080, 6108 */
+struct FaerV0_24_Par libfaer_v0_23_get_global_par(void);
+void libfaer_v0_23_set_global_par(struct FaerV0_24_Par par);
+void *libfaer_v0_23_alloc(size_t size, size_t align);
+void libfaer_v0_23_dealloc(void *ptr, size_t size, size_t align);
+
+/* =====================================================================================================
+ * GPU-only extensions (not in faer.h; kept in a separate namespace so faer.h layouts stay identical)
+ * ===================================================================================================== */
+/* Number of CUDA devices visible (0 => every compute entry point aborts). */
+int faer_b200_device_count(void);
+/* Stream used by subsequent calls from this process (cudaStream_t passed as void*; NULL = default stream). */
+void faer_b200_set_stream(void *cuda_stream);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+unsigned long long faer_b200_launch_count(void);
+/* Free the cached device workspace. */
+void faer_b200_release_workspace(void);
+/* Version string. */
+const char *faer_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBFAER_V0_24 */
