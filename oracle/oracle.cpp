@@ -1,0 +1,370 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE. See oracle.hpp for the contract and the parity-pinning statement.
+#include "oracle.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace oracle {
+
+// ------------------------------------------------------------------------------------------------
+// matmul — schoolbook definition: acc = sum_k conj_a(a_ik) * conj_b(b_kj) accumulated in k order, then
+// dst = acc*alpha (Replace) or dst + acc*alpha (Add).
+// Reference: faer/src/linalg/matmul/mod.rs:1909-1947 (`matmul_with_conj_fallback`, the comparator the
+// reference's own test_matmul uses), 1505-1523 (generic path), 1190-1198 (M==0/N==0/K==0 edge cases),
+// 1580-1582 (Replace must not read dst).
+// The (i,j) loop is register-blocked for speed; each output element still sums in k order.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+void matmul(Mat<T> dst, bool add, Mat<const T> lhs, bool conj_lhs, Mat<const T> rhs, bool conj_rhs, T alpha) {
+  const i64 M = dst.m, N = dst.n, K = lhs.n;
+  if (M == 0 || N == 0) return;
+  if (K == 0) {
+    if (!add)
+      for (i64 j = 0; j < N; ++j)
+        for (i64 i = 0; i < M; ++i) dst(i, j) = T(0);
+    return;
+  }
+  constexpr int BI = 8, BJ = 4;
+  const i64 nbj = (N + BJ - 1) / BJ;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (i64 jb = 0; jb < nbj; ++jb) {
+    const i64 j0 = jb * BJ, nj = std::min<i64>(BJ, N - j0);
+    for (i64 i0 = 0; i0 < M; i0 += BI) {
+      const i64 ni = std::min<i64>(BI, M - i0);
+      T acc[BI][BJ];
+      for (int a = 0; a < BI; ++a)
+        for (int b = 0; b < BJ; ++b) acc[a][b] = T(0);
+      for (i64 k = 0; k < K; ++k) {
+        T bv[BJ];
+        for (i64 b = 0; b < nj; ++b) bv[b] = conj_if(conj_rhs, rhs(k, j0 + b));
+        for (i64 a = 0; a < ni; ++a) {
+          const T av = conj_if(conj_lhs, lhs(i0 + a, k));
+          for (i64 b = 0; b < nj; ++b) acc[a][b] = acc[a][b] + av * bv[b];
+        }
+      }
+      for (i64 b = 0; b < nj; ++b)
+        for (i64 a = 0; a < ni; ++a) {
+          T v = acc[a][b] * alpha;
+          if (add) v = dst(i0 + a, j0 + b) + v;
+          dst(i0 + a, j0 + b) = v;
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// triangular matmul. Reference: faer/src/linalg/matmul/triangular.rs:1193-1245, 1246-1495.
+// Semantics restated (Appendix A of SURVEY.md, test `test_triangular` matmul/mod.rs:2106-2266):
+//  * the half of a triangular INPUT excluded by its BlockStructure is never read as data: it is 0, and the
+//    diagonal is 0 (strict) / 1 (unit)  (triangular.rs:26-52, 130-156);
+//  * only the part of dst selected by its structure is written; strict/unit dst leaves the diagonal untouched.
+// ------------------------------------------------------------------------------------------------
+static inline bool s_lower(int s) { return s == TRI_LOWER || s == STRICT_LOWER || s == UNIT_LOWER; }
+static inline bool s_upper(int s) { return s == TRI_UPPER || s == STRICT_UPPER || s == UNIT_UPPER; }
+static inline bool s_nodiag(int s) { return s >= STRICT_LOWER; }
+
+template <class T>
+static inline T masked(const Mat<const T>& a, int s, i64 i, i64 j) {
+  if (s == RECT) return a(i, j);
+  if (i == j) {
+    if (s == UNIT_LOWER || s == UNIT_UPPER) return T(1);
+    if (s == STRICT_LOWER || s == STRICT_UPPER) return T(0);
+    return a(i, j);
+  }
+  const bool keep = s_lower(s) ? (i > j) : (i < j);
+  return keep ? a(i, j) : T(0);
+}
+
+template <class T>
+void matmul_triangular(Mat<T> dst, int dst_s, bool add, Mat<const T> lhs, int lhs_s, bool conj_lhs, Mat<const T> rhs,
+                       int rhs_s, bool conj_rhs, T alpha) {
+  const i64 M = dst.m, N = dst.n, K = lhs.n;
+  if (M == 0 || N == 0) return;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (i64 j = 0; j < N; ++j) {
+    for (i64 i = 0; i < M; ++i) {
+      if (dst_s != RECT) {
+        if (i == j && s_nodiag(dst_s)) continue;
+        if (i != j && (s_lower(dst_s) ? (i < j) : (i > j))) continue;
+      }
+      T acc = T(0);
+      i64 k0 = 0, k1 = K;
+      if (s_lower(lhs_s)) k1 = std::min(k1, i + 1);
+      if (s_upper(lhs_s)) k0 = std::max(k0, i);
+      if (s_lower(rhs_s)) k0 = std::max(k0, j);
+      if (s_upper(rhs_s)) k1 = std::min(k1, j + 1);
+      for (i64 k = k0; k < k1; ++k)
+        acc = acc + conj_if(conj_lhs, masked(lhs, lhs_s, i, k)) * conj_if(conj_rhs, masked(rhs, rhs_s, k, j));
+      T v = acc * alpha;
+      if (add) v = dst(i, j) + v;
+      dst(i, j) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// triangular solve. Reference: faer/src/linalg/triangular_solve.rs
+//   block_size 200-211, recursion_threshold 213-215 (= 4), recursive split 420-576 (top solve, GEMM update
+//   with alpha = -1, bottom solve; rhs split by columns when k > 64 && n <= 128 — independent columns, so
+//   the split does not change any value), leaves 16-198 (reciprocal of the diagonal, products pre-divided),
+//   upper = lower on reversed views 577-604.
+// ------------------------------------------------------------------------------------------------
+static inline i64 ts_block_size(i64 n) {
+  const i64 base_rem = n / 2;
+  i64 sub;
+  if (n >= 32) sub = (base_rem + 15) / 16 * 16;
+  else if (n >= 16) sub = (base_rem + 7) / 8 * 8;
+  else if (n >= 8) sub = (base_rem + 3) / 4 * 4;
+  else sub = base_rem;
+  return n - sub;
+}
+
+template <class T>
+static void solve_lower_leaf(Mat<const T> L, bool conj, bool unit, Mat<T> rhs) {
+  // triangular_solve.rs:16-198: y_i = y_i * (1/l_ii) + sum_{k<i} (-(l_ik) * (1/l_ii)) * y_k   (non-unit)
+  //                             y_i = y_i + sum_{k<i} (-(l_ik)) * y_k                        (unit)
+  const i64 n = L.m;
+  T inv[4], nl[4][4];
+  for (i64 i = 0; i < n; ++i) {
+    inv[i] = unit ? T(1) : conj_if(conj, T(1) / L(i, i));
+    for (i64 k = 0; k < i; ++k) nl[i][k] = unit ? conj_if(conj, -L(i, k)) : conj_if(conj, -L(i, k)) * inv[i];
+  }
+  for (i64 c = 0; c < rhs.n; ++c) {
+    T y[4];
+    for (i64 i = 0; i < n; ++i) {
+      T v = rhs(i, c);
+      if (!unit) v = v * inv[i];
+      for (i64 k = 0; k < i; ++k) v = v + nl[i][k] * y[k];
+      y[i] = v;
+    }
+    for (i64 i = 0; i < n; ++i) rhs(i, c) = y[i];
+  }
+}
+
+template <class T>
+static void solve_lower_rec(Mat<const T> L, bool conj, bool unit, Mat<T> rhs) {
+  const i64 n = L.m;
+  if (n == 0 || rhs.n == 0) return;
+  if (n <= 4) {
+    solve_lower_leaf(L, conj, unit, rhs);
+    return;
+  }
+  const i64 bs = ts_block_size(n);
+  Mat<const T> L00 = L.sub(0, 0, bs, bs), L10 = L.sub(bs, 0, n - bs, bs), L11 = L.sub(bs, bs, n - bs, n - bs);
+  Mat<T> top = rhs.sub(0, 0, bs, rhs.n), bot = rhs.sub(bs, 0, n - bs, rhs.n);
+  solve_lower_rec(L00, conj, unit, top);
+  matmul<T>(bot, true, L10, conj, Mat<const T>{top.p, top.m, top.n, top.rs, top.cs}, false, T(-1));
+  solve_lower_rec(L11, conj, unit, bot);
+}
+
+template <class T>
+void solve_lower(Mat<const T> tril, bool conj, bool unit, Mat<T> rhs) { solve_lower_rec(tril, conj, unit, rhs); }
+template <class T>
+void solve_upper(Mat<const T> triu, bool conj, bool unit, Mat<T> rhs) {
+  if (triu.m == 0 || rhs.n == 0) return;
+  solve_lower_rec(triu.rev_rows_cols(), conj, unit, rhs.rev_rows());
+}
+
+// ------------------------------------------------------------------------------------------------
+// LLT. Reference: faer/src/linalg/cholesky/llt/factor.rs:68-97 calls
+// ldlt::factor::cholesky_block_left_looking(is_llt = true) whose `if true ||` (ldlt/factor.rs:528) always
+// forwards to cholesky_recursion_right_looking (367-498):
+//   n <= recursion_threshold -> leaf (simd_cholesky 7-298; scalar statement 299-366)
+//   else bs = min(next_pow2(n)/2, block_size); for j in steps of bs:
+//        recurse on A00 with (recursion_threshold, block_size = bs)          405-419  -> Err(j + idx)
+//        conj(A00) X = A10^T  (solve_lower_triangular_in_place)                421-426
+//        A11(lower) += -1 * A10 * A10^H (triangular::matmul, dst lower)        435-446
+// Leaf (SIMD col-major path, 7-177): a_ij <- fma(-conj(a_jk), a_ik, a_ij) for k < j in k order; d = Re(a_jj);
+// regularise (122-144, sign = +1 for LLT); !(d > 0) -> Err(j); l = sqrt(d); l == 0 or non-finite -> Err(j);
+// the WHOLE column j, diagonal included, is multiplied by recip(l)   (161-175).
+// ------------------------------------------------------------------------------------------------
+static inline i64 next_pow2(i64 n) {
+  i64 p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+template <class R> static inline R fma_(R a, R b, R c) { return std::fma(a, b, c); }
+template <class R> static inline std::complex<R> fma_(std::complex<R> a, std::complex<R> b, std::complex<R> c) {
+  // complex mul_add as four real FMAs (pulp's c64 mul_add lowers to fmaddsub pairs): re = fma(ar,br, fma(-ai,bi,cr))
+  R re = std::fma(a.real(), b.real(), std::fma(-a.imag(), b.imag(), c.real()));
+  R im = std::fma(a.real(), b.imag(), std::fma(a.imag(), b.real(), c.imag()));
+  return std::complex<R>(re, im);
+}
+
+template <class T> static inline T neg_conj(T x) { return -x; }
+template <class R> static inline std::complex<R> neg_conj(std::complex<R> x) { return -std::conj(x); }
+template <class T> static inline T mul_real(T x, typename real_of<T>::type r) { return x * r; }
+template <class R> static inline std::complex<R> mul_real(std::complex<R> x, R r) {
+  return std::complex<R>(x.real() * r, x.imag() * r);
+}
+
+template <class T>
+static i64 llt_leaf(Mat<T> A, typename real_of<T>::type delta, typename real_of<T>::type eps, bool regularize,
+                    i64* count) {
+  typedef typename real_of<T>::type R;
+  const i64 n = A.m;
+  for (i64 j = 0; j < n; ++j) {
+    // a_ij <- fma(-conj(a_jk), a_ik, a_ij), k = 0..j-1 in order (ldlt/factor.rs:44-53)
+    for (i64 i = j; i < n; ++i) {
+      T a = A(i, j);
+      for (i64 k = 0; k < j; ++k) a = fma_(neg_conj(A(j, k)), A(i, k), a);
+      A(i, j) = a;
+    }
+    R diag = real_part(A(j, j));
+    if (regularize) {
+      // sign == +1 for LLT (ldlt/factor.rs:122-144)
+      const bool small_or_negative = diag <= eps;
+      if (small_or_negative) {
+        diag = delta;
+        *count += 1;
+      }
+    }
+    if (!(diag > R(0))) return j;             // 147-150
+    diag = std::sqrt(diag);
+    if (diag == R(0) || !std::isfinite(diag)) return j;  // 156-158
+    const R inv = R(1) / diag;                // recip, then multiply (161-175), diagonal included
+    for (i64 i = j; i < n; ++i) A(i, j) = mul_real(A(i, j), inv);
+  }
+  return -1;
+}
+
+template <class T>
+static i64 llt_rec(Mat<T> A, typename real_of<T>::type delta, typename real_of<T>::type eps, bool regularize,
+                   i64 recursion_threshold, i64 block_size, i64* count) {
+  const i64 n = A.n;
+  if (n <= recursion_threshold) return llt_leaf(A, delta, eps, regularize, count);
+  const i64 bs0 = std::min(next_pow2(n) / 2, block_size);
+  for (i64 j = 0; j < n;) {
+    const i64 bs = std::min(bs0, n - j);
+    Mat<T> A00 = A.sub(j, j, bs, bs);
+    const i64 fail = llt_rec(A00, delta, eps, regularize, recursion_threshold, bs, count);
+    if (fail >= 0) return j + fail;
+    const i64 rem = n - j - bs;
+    if (rem > 0) {
+      Mat<T> A10 = A.sub(j + bs, j, rem, bs);
+      Mat<T> A11 = A.sub(j + bs, j + bs, rem, rem);
+      Mat<const T> cA00{A00.p, A00.m, A00.n, A00.rs, A00.cs};
+      Mat<const T> cA10{A10.p, A10.m, A10.n, A10.rs, A10.cs};
+      solve_lower<T>(cA00, /*conj=*/true, /*unit=*/false, A10.t());
+      matmul_triangular<T>(A11, TRI_LOWER, true, cA10, RECT, false, cA10.t(), RECT, true, T(-1));
+    }
+    j += bs;
+  }
+  return -1;
+}
+
+template <class T>
+i64 llt_in_place(Mat<T> A, typename real_of<T>::type delta, typename real_of<T>::type eps, i64 recursion_threshold,
+                 i64 block_size, i64* reg_count) {
+  typedef typename real_of<T>::type R;
+  *reg_count = 0;
+  const bool regularize = delta > R(0) && eps > R(0);  // llt/factor.rs:85-87
+  return llt_rec(A, delta, eps, regularize, recursion_threshold, block_size, reg_count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LU with partial pivoting. Reference: faer/src/linalg/lu/partial_pivoting/factor.rs
+//   lu_in_place 234-295: perm <- identity; transpositions from the recursion; perm.swap(i, i + t_i) in order;
+//                        m < n tail: unit-lower solve of the right block; perm_inv[perm[i]] = i.
+//   lu_in_place_recursion 68-187: n <= recursion_threshold -> unblocked; bs = round_up(n/2, min(16, next_pow2(n/2)));
+//        recurse left (all rows, cols [0, bs) of the [start, end) window); A01 <- unit_lower(A00)^-1 A01;
+//        A11 -= A10 A01; recurse on rows bs.. for cols [bs, n); then apply ALL n transpositions of this level to
+//        the columns left of `start` and right of `end` of the current view (127-185).
+//   lu_in_place_unblocked 19-67: pivot = FIRST row attaining max abs1 (strict `>` from max = 0); the swap is applied
+//        to the whole row of the current view (46); multipliers via recip-then-multiply (50-53); rank-1 update with
+//        alpha = -1 through matmul (K = 1).
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static i64 lu_unblocked(Mat<T> A, i64 start, i64 end, i64* trans) {
+  const i64 m = A.m;
+  if (start == end) return 0;
+  i64 n_trans = 0;
+  for (i64 j = start; j < end; ++j) {
+    const i64 col = j, row = j - start;
+    i64 imax = row;
+    typename real_of<T>::type mx = 0;
+    for (i64 i = imax; i < m; ++i) {
+      const auto a = abs1(A(i, col));
+      if (a > mx) {
+        mx = a;
+        imax = i;
+      }
+    }
+    trans[row] = imax - row;
+    if (imax != row) {
+      for (i64 c = 0; c < A.n; ++c) std::swap(A(row, c), A(imax, c));  // swap_rows_idx over the whole view
+      n_trans += 1;
+    }
+    Mat<T> W = A.sub(0, start, m, end - start);
+    const T inv = T(1) / W(row, row);
+    for (i64 i = row + 1; i < m; ++i) W(i, row) = W(i, row) * inv;
+    // A11 += -1 * A10 * A01 (rank-1)
+    for (i64 c = row + 1; c < end - start; ++c) {
+      const T u = W(row, c);
+      for (i64 i = row + 1; i < m; ++i) W(i, c) = W(i, c) + (W(i, row) * u) * T(-1);
+    }
+  }
+  return n_trans;
+}
+
+static inline i64 next_multiple_of(i64 x, i64 m) { return (x + m - 1) / m * m; }
+
+template <class T>
+static i64 lu_rec(Mat<T> A, i64 start, i64 end, i64* trans, i64 recursion_threshold) {
+  const i64 m = A.m, ncols = A.n, n = end - start;
+  if (n <= recursion_threshold) return lu_unblocked(A, start, end, trans);
+  const i64 half = n / 2;
+  const i64 pow = std::min<i64>(16, next_pow2(half));
+  const i64 bs = next_multiple_of(half, pow);
+  i64 n_trans = 0;
+  Mat<T> W = A.sub(0, start, m, n);
+  n_trans += lu_rec(W, 0, bs, trans, recursion_threshold);
+  {
+    Mat<T> A00 = W.sub(0, 0, bs, bs), A01 = W.sub(0, bs, bs, n - bs), A10 = W.sub(bs, 0, m - bs, bs),
+           A11 = W.sub(bs, bs, m - bs, n - bs);
+    Mat<const T> cA00{A00.p, A00.m, A00.n, A00.rs, A00.cs}, cA10{A10.p, A10.m, A10.n, A10.rs, A10.cs},
+        cA01{A01.p, A01.m, A01.n, A01.rs, A01.cs};
+    solve_lower<T>(cA00, false, true, A01);
+    matmul<T>(A11, true, cA10, false, cA01, false, T(-1));
+    n_trans += lu_rec(W.sub(bs, 0, m - bs, n), bs, n, trans + bs, recursion_threshold);
+  }
+  // apply this level's transpositions to the columns outside [start, end)
+  auto swap_cols = [&](Mat<T> M) {
+    for (i64 c = 0; c < M.n; ++c)
+      for (i64 j = 0; j < n; ++j) std::swap(M(j, c), M(j + trans[j], c));
+  };
+  swap_cols(A.sub(0, 0, m, start));
+  swap_cols(A.sub(0, end, m, ncols - end));
+  return n_trans;
+}
+
+template <class T>
+i64 lu_in_place(Mat<T> A, i64* perm, i64* perm_inv, i64 recursion_threshold) {
+  const i64 m = A.m, n = A.n, size = std::min(m, n);
+  for (i64 i = 0; i < m; ++i) perm[i] = i;
+  std::vector<i64> trans((size_t)size, 0);
+  const i64 n_trans = lu_rec(A, 0, size, trans.data(), recursion_threshold);
+  for (i64 i = 0; i < size; ++i) std::swap(perm[i], perm[i + trans[i]]);
+  if (m < n) {
+    Mat<T> left = A.sub(0, 0, m, size), right = A.sub(0, size, m, n - size);
+    solve_lower<T>(Mat<const T>{left.p, left.m, left.n, left.rs, left.cs}, false, true, right);
+  }
+  for (i64 i = 0; i < m; ++i) perm_inv[perm[i]] = i;
+  return n_trans;
+}
+
+// explicit instantiations
+#define ORACLE_INST(T)                                                                                           \
+  template void matmul<T>(Mat<T>, bool, Mat<const T>, bool, Mat<const T>, bool, T);                              \
+  template void matmul_triangular<T>(Mat<T>, int, bool, Mat<const T>, int, bool, Mat<const T>, int, bool, T);    \
+  template void solve_lower<T>(Mat<const T>, bool, bool, Mat<T>);                                                \
+  template void solve_upper<T>(Mat<const T>, bool, bool, Mat<T>);                                                \
+  template i64 llt_in_place<T>(Mat<T>, real_of<T>::type, real_of<T>::type, i64, i64, i64*);                      \
+  template i64 lu_in_place<T>(Mat<T>, i64*, i64*, i64);
+ORACLE_INST(double)
+ORACLE_INST(float)
+ORACLE_INST(std::complex<double>)
+ORACLE_INST(std::complex<float>)
+
+}  // namespace oracle

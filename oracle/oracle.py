@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes binding of the CPU oracle (oracle/liboracle.so, built by oracle/Makefile). Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+The oracle restates the reference's algorithms (see oracle.hpp for file:line citations and for the
+"parity unpinned at the bit level, pinned at tolerance level" statement).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+_DT = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.complex64): 2, np.dtype(np.complex128): 3}
+RECT, TRI_LOWER, TRI_UPPER, STRICT_LOWER, STRICT_UPPER, UNIT_LOWER, UNIT_UPPER = range(7)
+
+
+class OMat(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("m", C.c_longlong), ("n", C.c_longlong), ("rs", C.c_longlong), ("cs", C.c_longlong)]
+
+
+_lib = None
+
+
+def build() -> None:
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    lib.oracle_num_threads.restype = C.c_int
+    lib.oracle_set_num_threads.argtypes = [C.c_int]
+    lib.oracle_matmul.argtypes = [C.c_int, OMat, C.c_int, OMat, C.c_int, OMat, C.c_int, C.c_void_p]
+    lib.oracle_matmul.restype = C.c_longlong
+    lib.oracle_matmul_triangular.argtypes = [C.c_int, OMat, C.c_int, C.c_int, OMat, C.c_int, C.c_int, OMat, C.c_int,
+                                             C.c_int, C.c_void_p]
+    lib.oracle_matmul_triangular.restype = C.c_longlong
+    lib.oracle_solve_triangular.argtypes = [C.c_int, C.c_int, C.c_int, OMat, C.c_int, OMat]
+    lib.oracle_solve_triangular.restype = C.c_longlong
+    lib.oracle_llt.argtypes = [C.c_int, OMat, C.c_double, C.c_double, C.c_longlong, C.c_longlong,
+                               C.POINTER(C.c_longlong)]
+    lib.oracle_llt.restype = C.c_longlong
+    lib.oracle_lu.argtypes = [C.c_int, OMat, C.c_void_p, C.c_void_p, C.c_longlong]
+    lib.oracle_lu.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def _om(a: np.ndarray) -> OMat:
+    assert a.ndim == 2
+    return OMat(a.ctypes.data, a.shape[0], a.shape[1], a.strides[0] // a.itemsize, a.strides[1] // a.itemsize)
+
+
+def _scalar(dtype, v):
+    return np.array([v], dtype=dtype)
+
+
+def num_threads() -> int:
+    return load().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    load().oracle_set_num_threads(int(n))
+
+
+def matmul(dst, add: bool, lhs, rhs, alpha, conj_lhs=False, conj_rhs=False) -> None:
+    """dst = [dst +] alpha * conj?(lhs) * conj?(rhs)   (matmul/mod.rs:1909-1947)"""
+    assert dst.shape == (lhs.shape[0], rhs.shape[1]) and lhs.shape[1] == rhs.shape[0]
+    assert dst.dtype == lhs.dtype == rhs.dtype
+    a = _scalar(dst.dtype, alpha)
+    r = load().oracle_matmul(_DT[dst.dtype], _om(dst), int(add), _om(lhs), int(conj_lhs), _om(rhs), int(conj_rhs),
+                             a.ctypes.data)
+    assert r == 0
+
+
+def matmul_triangular(dst, dst_s, add, lhs, lhs_s, rhs, rhs_s, alpha, conj_lhs=False, conj_rhs=False) -> None:
+    assert dst.shape == (lhs.shape[0], rhs.shape[1]) and lhs.shape[1] == rhs.shape[0]
+    a = _scalar(dst.dtype, alpha)
+    r = load().oracle_matmul_triangular(_DT[dst.dtype], _om(dst), dst_s, int(add), _om(lhs), lhs_s, int(conj_lhs),
+                                        _om(rhs), rhs_s, int(conj_rhs), a.ctypes.data)
+    assert r == 0
+
+
+def solve_triangular(tri, rhs, lower: bool, unit: bool, conj=False) -> None:
+    assert tri.shape[0] == tri.shape[1] == rhs.shape[0]
+    r = load().oracle_solve_triangular(_DT[rhs.dtype], int(lower), int(unit), _om(tri), int(conj), _om(rhs))
+    assert r == 0
+
+
+def llt(A, delta=0.0, eps=0.0, recursion_threshold=64, block_size=128):
+    """In-place LLT of the lower triangle. Returns (fail_index or -1, regularisation count)."""
+    assert A.shape[0] == A.shape[1]
+    cnt = C.c_longlong(0)
+    r = load().oracle_llt(_DT[A.dtype], _om(A), float(delta), float(eps), recursion_threshold, block_size, C.byref(cnt))
+    assert r != -100
+    return int(r), int(cnt.value)
+
+
+def lu(A, recursion_threshold=16):
+    """In-place P A = L U. Returns (perm, perm_inv, transposition_count); (P A)[i] = A[perm[i]]."""
+    m = A.shape[0]
+    perm = np.zeros(m, dtype=np.int64)
+    perm_inv = np.zeros(m, dtype=np.int64)
+    r = load().oracle_lu(_DT[A.dtype], _om(A), perm.ctypes.data, perm_inv.ctypes.data, recursion_threshold)
+    assert r != -100
+    return perm, perm_inv, int(r)

@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """CPU oracle (test infrastructure; builds oracle/liboracle.so on first use)."""
+    from oracle import oracle as orc
+    orc.load()
+    return orc
+
+
+@pytest.fixture(scope="session")
+def fb():
+    """The product: ctypes binding + host mirror over libfaer_b200.so (no CPU fallback)."""
+    import faer_b200
+    faer_b200.load()
+    return faer_b200
+
+
+@pytest.fixture(scope="session")
+def cuda_dev(fb):
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    assert fb.load().faer_b200_device_count() > 0
+    return torch.device("cuda:0")
