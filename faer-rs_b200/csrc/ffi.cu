@@ -152,6 +152,59 @@ FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(FaerV0_24_MatMut A, Fa
   return out;
 }
 
+// ---- partial-pivoting LU ----
+FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f64(void) {
+  // reference defaults: faer/src/linalg/lu/partial_pivoting/factor.rs:212-222
+  return FaerV0_24_PartialPivLuParams{16, 64, 128 * 128};
+}
+
+static FaerV0_24_Layout lu_scratch(size_t nrows, size_t ncols, size_t idx_bytes) {
+  // reference: StackReq::new::<I>(min(nrows, ncols)) (factor.rs:224-233)
+  size_t size = nrows < ncols ? nrows : ncols;
+  return FaerV0_24_Layout{size * idx_bytes, idx_bytes};
+}
+FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32_f64(size_t nrows, size_t ncols, FaerV0_24_Par par,
+                                                                              FaerV0_24_PartialPivLuParams params) {
+  (void)par; (void)params;
+  return lu_scratch(nrows, ncols, 4);
+}
+FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_f64(size_t nrows, size_t ncols, FaerV0_24_Par par,
+                                                                              FaerV0_24_PartialPivLuParams params) {
+  (void)par; (void)params;
+  return lu_scratch(nrows, ncols, 8);
+}
+
+static FaerV0_24_PartialPivLuStatus lu_entry(FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd,
+                                             FaerV0_24_PartialPivLuParams params, int idx_bytes) {
+  require_device();
+  cudaStream_t st = current_stream();
+  // NB: faer.hpp fills SliceMut.len with BYTES while the Rust side reads elements, so the
+  // permutation length is taken from A.nrows, never from `len`.
+  FB_ASSERT(A.nrows == 0 || (perm_fwd.ptr != nullptr && perm_bwd.ptr != nullptr), "null permutation slice");
+  Mat a(A, true, st);
+  size_t cnt = lu_partial_piv_in_place_f64(st, a.s.view<double>(), perm_fwd.ptr, perm_bwd.ptr, idx_bytes,
+                                           PartialPivLuParams{params.recursion_threshold, params.block_size,
+                                                              params.par_threshold});
+  finish_all(st, {&a.s});
+  FaerV0_24_PartialPivLuStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_PartialPivLuStatus_Ok;
+  out.ok.transposition_count = cnt;
+  return out;
+}
+FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u32_f64(
+    FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd, FaerV0_24_Par par, FaerV0_24_MemAlloc mem,
+    FaerV0_24_PartialPivLuParams params) {
+  (void)par; (void)mem;
+  return lu_entry(A, perm_fwd, perm_bwd, params, 4);
+}
+FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f64(
+    FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd, FaerV0_24_Par par, FaerV0_24_MemAlloc mem,
+    FaerV0_24_PartialPivLuParams params) {
+  (void)par; (void)mem;
+  return lu_entry(A, perm_fwd, perm_bwd, params, 8);
+}
+
 // ---- global par / alloc ----
 FaerV0_24_Par libfaer_v0_23_get_global_par(void) {
   FaerV0_24_Par p;

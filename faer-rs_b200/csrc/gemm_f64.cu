@@ -249,8 +249,20 @@ __global__ void __launch_bounds__(Cfg::THREADS) gemm_f64_kernel(const GemmF64Par
   }
 }
 
-using CfgL = TileCfg<2, 4, 8, 4, 16, 4>;  // 128 x 128 x 16, 256 threads
-using CfgS = TileCfg<2, 2, 4, 4, 16, 4>;  // 64 x 64 x 16, 128 threads
+using CfgL = TileCfg<2, 4, 8, 4, 16, 4>;   // 128 x 128 x 16, 256 threads, warp tile 64 x 32
+using CfgS = TileCfg<2, 2, 4, 4, 16, 4>;   // 64 x 64 x 16, 128 threads, warp tile 32 x 32
+using CfgL16 = TileCfg<4, 4, 4, 4, 16, 4>; // 128 x 128 x 16, 512 threads, warp tile 32 x 32
+using CfgL32 = TileCfg<2, 4, 8, 4, 32, 3>; // 128 x 128 x 32, 256 threads, 3 stages
+
+// development knob: FAER_B200_GEMM_CFG=1..4 forces one tile configuration (0/unset = heuristic)
+inline int forced_cfg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FAER_B200_GEMM_CFG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 
 template <class Cfg, bool AK, bool BNM>
 constexpr size_t smem_bytes() {
@@ -278,6 +290,13 @@ template <bool AK, bool BNM, bool VEC>
 void launch_layout(cudaStream_t stream, GemmF64Params& p) {
   long long tiles_l = (long long)((p.m + 127) / 128) * ((p.n + 127) / 128);
   if (is_lower(p.c_struct) || is_upper(p.c_struct)) tiles_l = tiles_l / 2 + 1;
+  switch (forced_cfg()) {
+    case 1: launch_cfg<CfgL, AK, BNM, VEC>(stream, p); return;
+    case 2: launch_cfg<CfgL16, AK, BNM, VEC>(stream, p); return;
+    case 3: launch_cfg<CfgL32, AK, BNM, VEC>(stream, p); return;
+    case 4: launch_cfg<CfgS, AK, BNM, VEC>(stream, p); return;
+    default: break;
+  }
   if (tiles_l >= 2 * 148)
     launch_cfg<CfgL, AK, BNM, VEC>(stream, p);
   else

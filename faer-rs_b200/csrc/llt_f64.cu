@@ -60,11 +60,12 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
     // (ldlt/factor.rs:161-175 scales the whole column, diagonal included, and `diag` is a local copy).
     for (int i = j + tid; i < n; i += POTF2_THREADS) A[i * rs + j * cs] = s[i * ld + j] * inv;
     // trailing update, lower part only: a_ic <- fma(-l_cj, l_ij, a_ic)
-    for (int e = tid; e < r * r; e += POTF2_THREADS) {
-      int i = j + 1 + e % r, c = j + 1 + e / r;
-      if (c <= i) {
-        double lij = s[i * ld + j] * inv;
-        double lcj = s[c * ld + j] * inv;
+    // (2-D thread map: 32 lanes along c, POTF2_THREADS/32 rows; no integer division in the hot loop)
+    (void)r;
+    for (int i = j + 1 + (tid >> 5); i < n; i += POTF2_THREADS / 32) {
+      const double lij = s[i * ld + j] * inv;
+      for (int c = j + 1 + (tid & 31); c <= i; c += 32) {
+        const double lcj = s[c * ld + j] * inv;
         s[i * ld + c] = fma(-lcj, lij, s[i * ld + c]);
       }
     }

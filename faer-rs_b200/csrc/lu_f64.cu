@@ -1,0 +1,517 @@
+// P2/P3 + driver: in-place LU with partial pivoting (f64).
+//
+// Reference: faer/src/linalg/lu/partial_pivoting/factor.rs
+//   lu_in_place 234-295, lu_in_place_recursion 68-187 (split bs = round_up(n/2, min(16, next_pow2(n/2))),
+//   recurse left, A01 <- unit_lower(A00)^-1 A01, A11 -= A10 A01, recurse right, then apply the level's
+//   transpositions to the columns outside the window), lu_in_place_unblocked 19-67 (pivot = FIRST row attaining
+//   max abs1 with strict `>` from 0; whole-row swap; multipliers by reciprocal-multiply; rank-1 update).
+//
+// B200 mapping (same recursion as the reference, so every GEMM is as large as the reference's):
+//   * the recursion runs on the host stream; TRSM = G3, trailing update = G1 (DMMA GEMM);
+//   * windows of <= 64 columns are factored by ONE cooperative kernel (`lu_panel_kernel`): the tall panel is
+//     sliced by rows across up to 148 CTAs, each slice lives in shared memory for the whole panel, and each
+//     column costs exactly one grid-wide barrier: every CTA publishes its best pivot candidate (value, row
+//     index, the candidate row itself) and the owner of the diagonal row publishes that row; after the barrier
+//     every CTA reduces the candidates redundantly (ties -> lowest row index, zeros/NaNs never selected, exactly
+//     the reference's scan), the two owners exchange rows in shared memory and everybody applies the rank-1
+//     update to its slice while tracking the next column's local arg-max (warp-shuffle reduction);
+//   * row interchanges outside the window (P3) are applied group-wise: a tiny planning kernel turns each group
+//     of 64 transpositions into a net gather list (<= 128 affected rows), and the apply kernel moves all
+//     affected rows of a 32-column strip through shared memory with independent loads (full memory-level
+//     parallelism instead of a dependent swap chain).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "linalg_f64.cuh"
+
+namespace fb {
+
+namespace {
+
+constexpr int PANEL_W = 64;         // max panel width handled by the cooperative kernel
+constexpr int PANEL_THREADS = 256;
+constexpr int SWAP_GROUP = 64;      // transpositions per plan group
+constexpr int SWAP_CW = 32;         // columns per CTA in the apply kernel
+constexpr int SWAP_THREADS = 256;
+
+struct Cand {
+  double val;
+  long long idx;
+};
+
+__device__ __forceinline__ bool cand_better(double v1, long long i1, double v2, long long i2) {
+  // reference scan: `if abs > max { max = abs; imax = i }` over ascending i  => largest value, lowest index
+  return v1 > v2 || (v1 == v2 && i1 < i2);
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1ull);
+    while (*((volatile unsigned long long*)bar) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Scratch layout (doubles): for parity p in {0,1}:
+//   cand_val[p][G], cand_idx[p][G] (as long long), cand_row[p][G][PANEL_W], diag_row[p][PANEL_W]
+struct PanelScratch {
+  double* cand_val;      // [2][G]
+  long long* cand_idx;   // [2][G]
+  double* cand_row;      // [2][G][PANEL_W]
+  double* diag_row;      // [2][PANEL_W]
+  unsigned long long* bar;
+};
+
+__global__ void __launch_bounds__(PANEL_THREADS) lu_panel_kernel(double* __restrict__ A, i64 rs, i64 cs, int m, int w,
+                                                                  int rows_per_cta, int* __restrict__ trans,
+                                                                  PanelScratch sc, unsigned long long bar_base,
+                                                                  int* __restrict__ plan_rows, int* __restrict__ plan_src,
+                                                                  int* __restrict__ plan_cnt) {
+  extern __shared__ double S[];  // [rows_per_cta][LD], LD odd => conflict-free row-per-thread access
+  const int LD = w | 1;
+  __shared__ double pr[PANEL_W];  // pivot row
+  __shared__ double dr[PANEL_W];  // old diagonal row
+  __shared__ double red_val[PANEL_THREADS / 32];
+  __shared__ long long red_idx[PANEL_THREADS / 32];
+  __shared__ long long s_piv;
+  __shared__ int s_wincta;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, bid = blockIdx.x;
+  const int r0 = bid * rows_per_cta;
+  const int nloc = max(0, min(rows_per_cta, m - r0));
+  const int ncol = min(w, m);  // columns to eliminate
+
+  // ---- load slice (coalesced along rows for column-major A) ----
+  for (int e = tid; e < nloc * w; e += PANEL_THREADS) {
+    int r = e % nloc, c = e / nloc;
+    S[r * LD + c] = A[(i64)(r0 + r) * rs + (i64)c * cs];
+  }
+  __syncthreads();
+
+  // local arg-max of column 0 over rows >= 0
+  double my_val = 0.0;
+  long long my_idx = -1;
+  for (int r = tid; r < nloc; r += PANEL_THREADS) {
+    double v = fabs(S[r * LD + 0]);
+    if (v > 0.0 && cand_better(v, r0 + r, my_val, my_idx < 0 ? (1ll << 62) : my_idx)) {
+      my_val = v;
+      my_idx = r0 + r;
+    }
+  }
+
+  unsigned long long nbar = 0;
+  for (int j = 0; j < ncol; ++j) {
+    const int par = j & 1;
+    // ---- (1) block-reduce the local candidate ----
+    {
+      double v = my_val;
+      long long ix = my_idx < 0 ? (1ll << 62) : my_idx;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+        if (cand_better(ov, oi, v, ix)) {
+          v = ov;
+          ix = oi;
+        }
+      }
+      if (lane == 0) {
+        red_val[warp] = v;
+        red_idx[warp] = ix;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        v = lane < PANEL_THREADS / 32 ? red_val[lane] : 0.0;
+        ix = lane < PANEL_THREADS / 32 ? red_idx[lane] : (1ll << 62);
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+          double ov = __shfl_xor_sync(0xffffffffu, v, off);
+          long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+          if (cand_better(ov, oi, v, ix)) {
+            v = ov;
+            ix = oi;
+          }
+        }
+        if (lane == 0) {
+          red_val[0] = v;
+          red_idx[0] = ix;
+        }
+      }
+      __syncthreads();
+    }
+    {
+      const double bv = red_val[0];
+      const long long bi = red_idx[0];
+      if (tid == 0) {
+        sc.cand_val[par * G + bid] = bv;
+        sc.cand_idx[par * G + bid] = bi;
+      }
+      if (bv > 0.0) {
+        const int lr = (int)(bi - r0);
+        for (int c = tid; c < w; c += PANEL_THREADS) sc.cand_row[((i64)par * G + bid) * PANEL_W + c] = S[lr * LD + c];
+      }
+      if (j >= r0 && j < r0 + nloc) {
+        const int lr = j - r0;
+        for (int c = tid; c < w; c += PANEL_THREADS) sc.diag_row[par * PANEL_W + c] = S[lr * LD + c];
+      }
+    }
+    ++nbar;
+    grid_barrier(sc.bar, bar_base + nbar * (unsigned long long)G);
+
+    // ---- (2) global winner (computed redundantly by every CTA) ----
+    if (warp == 0) {
+      double v = 0.0;
+      long long ix = (1ll << 62);
+      int wc = -1;
+      for (int b = lane; b < G; b += 32) {
+        double ov = __ldcg(&sc.cand_val[par * G + b]);
+        long long oi = __ldcg(&sc.cand_idx[par * G + b]);
+        if (ov > 0.0 && cand_better(ov, oi, v, ix)) {
+          v = ov;
+          ix = oi;
+          wc = b;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+        int oc = __shfl_xor_sync(0xffffffffu, wc, off);
+        if (cand_better(ov, oi, v, ix)) {
+          v = ov;
+          ix = oi;
+          wc = oc;
+        }
+      }
+      if (lane == 0) {
+        // an all-zero / all-NaN column keeps imax = row (reference factor.rs:35-44)
+        s_piv = (v > 0.0) ? ix : (long long)j;
+        s_wincta = (v > 0.0) ? wc : -1;
+      }
+    }
+    __syncthreads();
+    const int piv = (int)s_piv;
+    const int wincta = s_wincta;
+    for (int c = tid; c < w; c += PANEL_THREADS) {
+      const double d = __ldcg(&sc.diag_row[par * PANEL_W + c]);
+      dr[c] = d;
+      pr[c] = (piv != j) ? __ldcg(&sc.cand_row[((i64)par * G + wincta) * PANEL_W + c]) : d;
+    }
+    __syncthreads();
+    if (piv != j) {
+      if (piv >= r0 && piv < r0 + nloc)
+        for (int c = tid; c < w; c += PANEL_THREADS) S[(piv - r0) * LD + c] = dr[c];
+      if (j >= r0 && j < r0 + nloc)
+        for (int c = tid; c < w; c += PANEL_THREADS) S[(j - r0) * LD + c] = pr[c];
+    }
+    if (bid == 0 && tid == 0) trans[j] = piv - j;
+    __syncthreads();
+
+    // ---- (3) multipliers + rank-1 update of the slice; track next column's local arg-max ----
+    const double inv = 1.0 / pr[j];
+    my_val = 0.0;
+    my_idx = -1;
+    for (int r = tid; r < nloc; r += PANEL_THREADS) {
+      if (r0 + r > j) {
+        double* row = S + r * LD;
+        const double l = row[j] * inv;
+        row[j] = l;
+        for (int c = j + 1; c < w; ++c) row[c] = fma(-l, pr[c], row[c]);
+        if (j + 1 < w) {
+          const double v = fabs(row[j + 1]);
+          if (v > 0.0 && cand_better(v, r0 + r, my_val, my_idx < 0 ? (1ll << 62) : my_idx)) {
+            my_val = v;
+            my_idx = r0 + r;
+          }
+        }
+      }
+    }
+    // (the block reduction at the top of the next iteration starts with __syncthreads-protected smem)
+  }
+  __syncthreads();
+  // ---- store slice ----
+  for (int e = tid; e < nloc * w; e += PANEL_THREADS) {
+    int r = e % nloc, c = e / nloc;
+    A[(i64)(r0 + r) * rs + (i64)c * cs] = S[r * LD + c];
+  }
+  // ---- swap plan for this window (one group) so that the caller can permute the outside columns ----
+  if (plan_rows != nullptr && bid == 0) {
+    // all `trans` writes of this CTA are done (same thread 0 wrote them); build the net gather list
+    __syncthreads();
+    if (tid == 0) {
+      int ids[2 * PANEL_W], cur[2 * PANEL_W];
+      int cnt = 0;
+      for (int t = 0; t < ncol; ++t) {
+        const int a = t, b = t + trans[t];
+        if (a == b) continue;
+        int qa = -1, qb = -1;
+        for (int q = 0; q < cnt; ++q) {
+          if (ids[q] == a) qa = q;
+          if (ids[q] == b) qb = q;
+        }
+        if (qa < 0) { qa = cnt; ids[cnt] = a; cur[cnt] = a; ++cnt; }
+        if (qb < 0) { qb = cnt; ids[cnt] = b; cur[cnt] = b; ++cnt; }
+        const int tmp = cur[qa];
+        cur[qa] = cur[qb];
+        cur[qb] = tmp;
+      }
+      int out = 0;
+      for (int q = 0; q < cnt; ++q)
+        if (ids[q] != cur[q]) {
+          plan_rows[out] = ids[q];
+          plan_src[out] = cur[q];
+          ++out;
+        }
+      plan_cnt[0] = out;
+    }
+  }
+}
+
+// One thread per group of SWAP_GROUP transpositions: net effect as a gather list (dst row <- src row).
+__global__ void laswp_plan_kernel(const int* __restrict__ trans, int n, int* __restrict__ plan_rows,
+                                  int* __restrict__ plan_src, int* __restrict__ plan_cnt, int ngroups) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= ngroups) return;
+  int ids[2 * SWAP_GROUP], cur[2 * SWAP_GROUP];
+  int cnt = 0;
+  const int t0 = gi * SWAP_GROUP, t1 = min(n, t0 + SWAP_GROUP);
+  for (int t = t0; t < t1; ++t) {
+    const int a = t, b = t + trans[t];
+    if (a == b) continue;
+    int qa = -1, qb = -1;
+    for (int q = 0; q < cnt; ++q) {
+      if (ids[q] == a) qa = q;
+      if (ids[q] == b) qb = q;
+    }
+    if (qa < 0) { qa = cnt; ids[cnt] = a; cur[cnt] = a; ++cnt; }
+    if (qb < 0) { qb = cnt; ids[cnt] = b; cur[cnt] = b; ++cnt; }
+    const int tmp = cur[qa];
+    cur[qa] = cur[qb];
+    cur[qb] = tmp;
+  }
+  int out = 0;
+  for (int q = 0; q < cnt; ++q)
+    if (ids[q] != cur[q]) {
+      plan_rows[(i64)gi * 2 * SWAP_GROUP + out] = ids[q];
+      plan_src[(i64)gi * 2 * SWAP_GROUP + out] = cur[q];
+      ++out;
+    }
+  plan_cnt[gi] = out;
+}
+
+// Apply the gather lists of all groups (in order) to a strip of SWAP_CW columns per CTA.
+__global__ void __launch_bounds__(SWAP_THREADS) laswp_apply_kernel(double* __restrict__ A, i64 rs, i64 cs, i64 ncols,
+                                                                    const int* __restrict__ plan_rows,
+                                                                    const int* __restrict__ plan_src,
+                                                                    const int* __restrict__ plan_cnt, int ngroups) {
+  __shared__ double tile[2 * SWAP_GROUP][SWAP_CW + 1];
+  const i64 c0 = (i64)blockIdx.x * SWAP_CW;
+  const int nc = (int)min((i64)SWAP_CW, ncols - c0);
+  const int tid = threadIdx.x;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const int cnt = plan_cnt[gi];
+    if (cnt == 0) continue;
+    const int* rows = plan_rows + (i64)gi * 2 * SWAP_GROUP;
+    const int* src = plan_src + (i64)gi * 2 * SWAP_GROUP;
+    for (int e = tid; e < cnt * nc; e += SWAP_THREADS) {
+      const int q = e % cnt, c = e / cnt;
+      tile[q][c] = A[(i64)src[q] * rs + (c0 + c) * cs];
+    }
+    __syncthreads();
+    for (int e = tid; e < cnt * nc; e += SWAP_THREADS) {
+      const int q = e % cnt, c = e / cnt;
+      A[(i64)rows[q] * rs + (c0 + c) * cs] = tile[q][c];
+    }
+    __syncthreads();
+  }
+}
+
+inline i64 next_pow2(i64 n) {
+  i64 p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+struct LuCtx {
+  cudaStream_t st;
+  int num_sms;
+  int* d_trans;          // [size]
+  int* plan_rows;        // [ngroups_max][2*SWAP_GROUP]
+  int* plan_src;
+  int* plan_cnt;         // [ngroups_max]
+  PanelScratch sc;
+  unsigned long long bar_count;  // host mirror of the barrier counter
+  i64 recursion_threshold;       // reference's leaf width (<= it -> unblocked); GPU leaf = cooperative panel
+};
+
+constexpr i64 PANEL_SMEM_BUDGET = 200 * 1024;
+
+// widest window (<= PANEL_W) whose row slices (ceil(m / #CTAs) rows x (w|1) doubles) fit in shared memory
+int panel_width_for(const LuCtx& ctx, i64 m) {
+  const i64 rows = std::max<i64>(1, (m + ctx.num_sms - 1) / ctx.num_sms);
+  i64 w = PANEL_SMEM_BUDGET / (8 * rows) - 1;
+  if (w > PANEL_W) w = PANEL_W;
+  if (w >= 16) w = w / 16 * 16;
+  return (int)std::max<i64>(1, w);
+}
+
+void launch_panel(LuCtx& ctx, VD P, int* trans, bool want_plan) {
+  const int m = (int)P.nrows, w = (int)P.ncols;
+  int G = (int)std::min<i64>(ctx.num_sms, (m + 63) / 64);
+  if (G < 1) G = 1;
+  int rows_per_cta = (m + G - 1) / G;
+  size_t smem = (size_t)rows_per_cta * (size_t)(w | 1) * sizeof(double);
+  FB_ASSERT(smem <= 220 * 1024, "LU panel too tall for the shared-memory slices");
+  static size_t configured = 0;
+  if (smem > configured) {
+    FB_CUDA_CHECK(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = 220 * 1024;
+  }
+  double* Aptr = P.ptr;
+  i64 rs = P.rs, cs = P.cs;
+  int mm = m, ww = w;
+  unsigned long long base = ctx.bar_count;
+  int* pr = want_plan ? ctx.plan_rows : nullptr;
+  int* ps = ctx.plan_src;
+  int* pc = ctx.plan_cnt;
+  void* args[] = {&Aptr, &rs, &cs, &mm, &ww, &rows_per_cta, &trans, &ctx.sc, &base, &pr, &ps, &pc};
+  FB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(G), dim3(PANEL_THREADS), args, smem, ctx.st));
+  note_launch();
+  ctx.bar_count += (unsigned long long)std::min(w, m) * G;
+}
+
+void apply_plan(LuCtx& ctx, VD cols, int ngroups) {
+  if (cols.ncols == 0 || cols.nrows == 0) return;
+  unsigned blocks = (unsigned)((cols.ncols + SWAP_CW - 1) / SWAP_CW);
+  laswp_apply_kernel<<<blocks, SWAP_THREADS, 0, ctx.st>>>(cols.ptr, cols.rs, cols.cs, cols.ncols, ctx.plan_rows,
+                                                          ctx.plan_src, ctx.plan_cnt, ngroups);
+  FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+}
+
+// A: current view (all m rows, ncols columns); window [start, end); trans: device pointer for this window.
+void lu_rec(LuCtx& ctx, VD A, i64 start, i64 end, int* trans) {
+  const i64 m = A.nrows, ncols = A.ncols, n = end - start;
+  if (n == 0) return;
+  const bool has_outside = start > 0 || end < ncols;
+  if (n <= panel_width_for(ctx, m) || n == 1) {
+    launch_panel(ctx, A.sub(0, start, m, n), trans, has_outside);
+    if (has_outside) {
+      apply_plan(ctx, A.sub(0, 0, m, start), 1);
+      apply_plan(ctx, A.sub(0, end, m, ncols - end), 1);
+    }
+    return;
+  }
+  const i64 half = n / 2;
+  const i64 pw = std::min<i64>(16, next_pow2(half));
+  const i64 bs = (half + pw - 1) / pw * pw;
+  VD W = A.sub(0, start, m, n);
+  lu_rec(ctx, W, 0, bs, trans);
+  {
+    VD A00 = W.sub(0, 0, bs, bs), A01 = W.sub(0, bs, bs, n - bs), A10 = W.sub(bs, 0, m - bs, bs),
+       A11 = W.sub(bs, bs, m - bs, n - bs);
+    solve_lower_triangular_in_place_f64(ctx.st, cv(A00), true, A01);
+    gemm_f64(ctx.st, A11, 1, cv(A10), cv(A01), -1.0);
+    lu_rec(ctx, W.sub(bs, 0, m - bs, n), bs, n, trans + bs);
+  }
+  if (has_outside) {
+    const int ngroups = (int)((n + SWAP_GROUP - 1) / SWAP_GROUP);
+    laswp_plan_kernel<<<(ngroups + 63) / 64, 64, 0, ctx.st>>>(trans, (int)n, ctx.plan_rows, ctx.plan_src, ctx.plan_cnt,
+                                                              ngroups);
+    FB_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    apply_plan(ctx, A.sub(0, 0, m, start), ngroups);
+    apply_plan(ctx, A.sub(0, end, m, ncols - end), ngroups);
+  }
+}
+
+}  // namespace
+
+size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, void* perm_inv, int idx_bytes,
+                                   PartialPivLuParams params) {
+  const i64 m = A.nrows, n = A.ncols, size = std::min(m, n);
+  FB_ASSERT(idx_bytes == 4 || idx_bytes == 8, "index type must be u32 or u64");
+  FB_ASSERT(m < (1ll << 31) && n < (1ll << 31), "dimension too large");
+  std::vector<long long> perm((size_t)m), pinv((size_t)m);
+  for (i64 i = 0; i < m; ++i) perm[(size_t)i] = i;
+  size_t n_trans = 0;
+  if (size > 0) {
+    LuCtx ctx;
+    ctx.st = stream;
+    int dev = 0;
+    FB_CUDA_CHECK(cudaGetDevice(&dev));
+    FB_CUDA_CHECK(cudaDeviceGetAttribute(&ctx.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    ctx.recursion_threshold = (i64)params.recursion_threshold;
+    const int G = ctx.num_sms;
+    const i64 ngroups_max = (size + SWAP_GROUP - 1) / SWAP_GROUP + 1;
+    ctx.d_trans = (int*)ws_alloc((size_t)size * sizeof(int));
+    ctx.plan_rows = (int*)ws_alloc((size_t)ngroups_max * 2 * SWAP_GROUP * sizeof(int));
+    ctx.plan_src = (int*)ws_alloc((size_t)ngroups_max * 2 * SWAP_GROUP * sizeof(int));
+    ctx.plan_cnt = (int*)ws_alloc((size_t)ngroups_max * sizeof(int));
+    const size_t sc_bytes = (size_t)2 * G * 8 * 2 + (size_t)2 * G * PANEL_W * 8 + (size_t)2 * PANEL_W * 8 + 64;
+    char* scb = (char*)ws_alloc(sc_bytes);
+    ctx.sc.cand_val = (double*)scb;
+    ctx.sc.cand_idx = (long long*)(scb + (size_t)2 * G * 8);
+    ctx.sc.cand_row = (double*)(scb + (size_t)4 * G * 8);
+    ctx.sc.diag_row = (double*)(scb + (size_t)4 * G * 8 + (size_t)2 * G * PANEL_W * 8);
+    ctx.sc.bar = (unsigned long long*)(scb + (size_t)4 * G * 8 + (size_t)2 * G * PANEL_W * 8 + (size_t)2 * PANEL_W * 8);
+    FB_CUDA_CHECK(cudaMemsetAsync(ctx.sc.bar, 0, 8, stream));
+    ctx.bar_count = 0;
+
+    lu_rec(ctx, A, 0, size, ctx.d_trans);
+
+    std::vector<int> h_trans((size_t)size);
+    FB_CUDA_CHECK(cudaMemcpyAsync(h_trans.data(), ctx.d_trans, (size_t)size * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    FB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    // perm.swap(idx, idx + t)  (reference factor.rs:274-277)
+    for (i64 i = 0; i < size; ++i) {
+      const int t = h_trans[(size_t)i];
+      if (t != 0) {
+        std::swap(perm[(size_t)i], perm[(size_t)(i + t)]);
+        ++n_trans;
+      }
+    }
+    if (m < n) {
+      // reference factor.rs:278-285
+      solve_lower_triangular_in_place_f64(stream, cv(A.sub(0, 0, m, size)), true, A.sub(0, size, m, n - size));
+      FB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    ws_free(scb);
+    ws_free(ctx.plan_cnt);
+    ws_free(ctx.plan_src);
+    ws_free(ctx.plan_rows);
+    ws_free(ctx.d_trans);
+  }
+  for (i64 i = 0; i < m; ++i) pinv[(size_t)perm[(size_t)i]] = i;
+
+  // write the permutation arrays (host or device, u32 or u64)
+  auto put = [&](void* dst, const std::vector<long long>& v) {
+    if (m == 0) return;
+    std::vector<unsigned char> buf((size_t)m * idx_bytes);
+    for (i64 i = 0; i < m; ++i) {
+      if (idx_bytes == 4) ((uint32_t*)buf.data())[i] = (uint32_t)v[(size_t)i];
+      else ((uint64_t*)buf.data())[i] = (uint64_t)v[(size_t)i];
+    }
+    cudaPointerAttributes attr;
+    bool devp = false;
+    if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess)
+      devp = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    else
+      (void)cudaGetLastError();
+    if (devp)
+      FB_CUDA_CHECK(cudaMemcpy(dst, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+    else
+      memcpy(dst, buf.data(), buf.size());
+  };
+  put(perm_fwd, perm);
+  put(perm_inv, pinv);
+  return n_trans;
+}
+
+}  // namespace fb
