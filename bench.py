@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native faer hot path.
+
+Workload at N=1 (BASELINE.json configs[1]): f64 Cholesky LLT, n = 16384, synthetic SPD input
+A = G G^T + n I (G ~ N(0,1), the reference's bench generator, faer/examples/bench.rs:1513-1515), column-major,
+resident in HBM when the timed region starts. One "step" = restore the input (device copy of the 2.1 GB matrix;
+faer's own bench also times `copy_from_triangular_lower`, bench.rs:1531-1540) + one in-place factorisation through
+the C ABI `libfaer_v0_23_llt_factor_in_place_f64`.
+  value  = n^3/3 flop per factorisation x N ranks / max-over-ranks device time   [TFLOP/s]
+  e2e    = same metric through the same C-ABI call with HOST (pinned) buffers: H2D + factor + D2H inside the timed region
+N > 1: the LLT path does not shard in this round ("replicas only"): every rank factors its own matrix,
+no data-path collective; scaling = weak.
+
+--impl reference: times the CPU restatement of the reference's algorithm (oracle/, OpenMP over all host cores; faer
+itself needs a Rust toolchain that this image does not have) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "f64 GEMM & LU/LLT TFLOP/s at n=16384; % of B200 tensor-core peak"
+UNIT = "TFLOP/s"
+N_DEFAULT = 16384
+
+
+def llt_flops(n: int) -> float:
+    return n ** 3 / 3.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for (ts, line) in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (oracle = test infrastructure; this is one of the two places allowed to execute it)
+# ---------------------------------------------------------------------------------------------------
+def cpu_llt_sample(target_seconds: float = 15.0, n_cap: int = 8192):
+    """Time the CPU restatement of faer's LLT on all host cores on a bounded sample (same generator, smaller n)."""
+    from oracle import oracle as orc
+    orc.load()
+    cores = orc.num_threads()
+    rng = np.random.default_rng(0)
+
+    def run(n):
+        G = rng.standard_normal((n, n))
+        A = np.asfortranarray(G @ G.T + n * np.eye(n))
+        t = time.perf_counter()
+        fail, _ = orc.llt(A)
+        dt = time.perf_counter() - t
+        assert fail == -1
+        return dt
+
+    run(512)  # thread start-up
+    t_probe = run(2048)
+    rate = llt_flops(2048) / t_probe
+    n = int((target_seconds * rate * 3.0) ** (1.0 / 3.0)) // 256 * 256
+    n = max(2048, min(n_cap, n))
+    dt = run(n)
+    return {"value": llt_flops(n) / dt / 1e12, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle (C++/OpenMP restatement of faer's LLT, not faer itself: no Rust toolchain) LLT n={n}, "
+                      f"same generator as the GPU workload, {dt:.2f} s"}, n, dt
+
+
+def lapack_proxy(n: int):
+    """scipy/OpenBLAS dpotrf on all cores at the full size — a PROXY for an optimised CPU library, not faer."""
+    try:
+        import scipy.linalg as sla
+        rng = np.random.default_rng(0)
+        G = rng.standard_normal((n, n))
+        A = np.asfortranarray(G @ G.T + n * np.eye(n))
+        t = time.perf_counter()
+        sla.cholesky(A, lower=True, overwrite_a=True, check_finite=False)
+        dt = time.perf_counter() - t
+        return {"value": llt_flops(n) / dt / 1e12, "unit": UNIT, "what": f"scipy.linalg.cholesky (OpenBLAS) n={n}, {dt:.2f} s",
+                "cores": os.cpu_count()}
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "what": f"unavailable: {e}"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; faer cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    times = []
+    base, n, _ = cpu_llt_sample(target_seconds=6.0, n_cap=6144)
+    from oracle import oracle as orc
+    rng = np.random.default_rng(1)
+    for it in range(args.warmup + args.steps):
+        if it >= 1 and it < args.warmup:
+            continue  # one warm-up is enough for a CPU loop; keep the whole run within minutes
+        G = rng.standard_normal((n, n))
+        A = np.asfortranarray(G @ G.T + n * np.eye(n))
+        t = time.perf_counter()
+        orc.llt(A)
+        dt = time.perf_counter() - t
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = llt_flops(n) / (ms * 1e-3) / 1e12
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"f64 Cholesky LLT, bounded CPU sample n={n} of the n={args.n} workload (SPD = G G^T + n I)",
+                   "n": n, "n_full": args.n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": base["cores"], "kind": "port",
+                         "sample": f"oracle LLT n={n} per step (C++/OpenMP restatement; faer needs Rust, absent here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import faer_b200
+    from faer_b200 import linalg as la
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = faer_b200.load()
+    stream = torch.cuda.current_stream()
+    lib.faer_b200_set_stream(stream.cuda_stream)
+
+    n = args.n
+    torch.manual_seed(1234 + rank)
+    G = torch.randn((n, n), dtype=torch.float64, device=dev)
+    A0 = torch.addmm(n * torch.eye(n, dtype=torch.float64, device=dev), G, G.T).T  # symmetric, column-major view
+    del G
+    A = A0.clone(memory_format=torch.preserve_format)
+
+    def step():
+        A.copy_(A0)
+        la.cholesky_in_place(A)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = lib.faer_b200_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    launches = lib.faer_b200_launch_count() - launches0 + args.steps  # + the restore copies (torch kernels)
+    my_launches = lib.faer_b200_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = llt_flops(n) * world / (ms_per_step * 1e-3) / 1e12
+
+    # ---- correctness guard on the timed data (cheap probe): A0 x == L (L^T x) ----
+    L = torch.tril(A)
+    x = torch.randn((n, 2), dtype=torch.float64, device=dev)
+    resid = float((A0 @ x - L @ (L.T @ x)).abs().max()) / (float(A0.abs().max()) * n)
+    del L
+
+    # ---- roofline of the dominant kernel (the DMMA GEMM doing the trailing updates) ----
+    roof = None
+    if hasattr(lib, "faer_b200_profile_begin"):
+        import ctypes as C
+        lib.faer_b200_profile_begin()
+        step()
+        torch.cuda.synchronize()
+        flops = C.c_double(0); ms = C.c_double(0); cnt = C.c_ulonglong(0)
+        lib.faer_b200_profile_end(C.byref(flops), C.byref(ms), C.byref(cnt))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "profiles", "r01_f64_peaks.json")))
+        except Exception:
+            pass
+        peak = peaks.get("dmma_tflops_sustained", 36.9)
+        ach = flops.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        bf16 = None
+        try:
+            bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4 trailing updates)", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
+                "launches_per_step": int(cnt.value), "ms_in_kernel_per_step": ms.value,
+                "flops_in_kernel_per_step": flops.value,
+                "peak_source": "measured on this pool: DMMA.8x8x4 issue-bound peak, profiles/r01_f64_peaks.json "
+                               "(tcgen05 has no f64 kind; MEASURED_PEAKS.json only has bf16: "
+                               f"{bf16} TF/s sustained => frac_of_bf16 = {(ach / bf16) if (ach and bf16) else None})",
+                "how": "CUDA events around every launch of the kernel on the launching stream, one extra profiled step "
+                       "right after the timed region; achieved = sum(algorithmic flop per launch) / sum(duration)"}
+
+    # ---- e2e: same metric through the C ABI with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hA0 = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        hA0.copy_(A0.T)  # hA0 (row-major storage) == A0 column-major, A0 symmetric anyway
+        hA = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        hv = hA.numpy().T  # column-major view over pinned memory
+        reps = max(2, min(args.steps, 3))
+        hA.copy_(hA0); la.cholesky_in_place(hv)  # warm-up (pool allocation)
+        barrier()
+        ts = []
+        for _ in range(reps):
+            hA.copy_(hA0)
+            t0 = time.perf_counter()
+            la.cholesky_in_place(hv)  # H2D (2.1 GB) + factorisation + D2H (2.1 GB), synchronous
+            ts.append(time.perf_counter() - t0)
+        tt = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": llt_flops(n) * world / float(tt.item()) / 1e12, "unit": UNIT,
+               "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8, "ms_per_step": 1e3 * float(tt.item()),
+               "how": "libfaer_v0_23_llt_factor_in_place_f64 on a pinned HOST matrix (wall clock around the synchronous call)"}
+        del hA, hA0
+
+    cpu = None
+    proxy = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _, _ = cpu_llt_sample()
+        proxy = lapack_proxy(min(n, 8192))
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"f64 Cholesky LLT n={n} (BASELINE.json configs[1]); SPD = G G^T + n I; step = restore copy + factor",
+                       "n": n, "layout": "column-major", "per_rank": "independent replica (no data-path collective)" if world > 1 else "single GPU",
+                       "l2": "inputs (2.1 GB per matrix) exceed the 126 MB L2; no flush needed",
+                       "probe_residual": resid},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(my_launches),
+            "roofline": roof, "cpu_baseline": cpu, "cpu_lapack_proxy": proxy,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

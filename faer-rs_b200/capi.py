@@ -150,6 +150,10 @@ def load() -> C.CDLL:
     lib.faer_b200_launch_count.restype = C.c_ulonglong
     lib.faer_b200_release_workspace.argtypes = []
     lib.faer_b200_release_workspace.restype = None
+    lib.faer_b200_profile_begin.argtypes = []
+    lib.faer_b200_profile_begin.restype = None
+    lib.faer_b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    lib.faer_b200_profile_end.restype = None
     lib.faer_b200_version.argtypes = []
     lib.faer_b200_version.restype = C.c_char_p
     _lib = lib

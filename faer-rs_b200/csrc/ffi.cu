@@ -240,6 +240,8 @@ int faer_b200_device_count(void) {
 void faer_b200_set_stream(void* cuda_stream) { set_current_stream((cudaStream_t)cuda_stream); }
 unsigned long long faer_b200_launch_count(void) { return g_launch_count; }
 void faer_b200_release_workspace(void) { ws_release_all(); }
+void faer_b200_profile_begin(void) { profile_begin(); }
+void faer_b200_profile_end(double* flops, double* ms, unsigned long long* count) { profile_end(flops, ms, count); }
 const char* faer_b200_version(void) { return "faer_b200 0.1 (faer-ffi v0_23 ABI subset, sm_100a)"; }
 
 }  // extern "C"

@@ -11,6 +11,7 @@
 //     that intersect the diagonal pay the extra pass), fully-masked k-ranges are skipped, triangular dst
 //     tiles above/below the diagonal exit immediately and diagonal tiles mask the store.
 #include "gemm_f64.cuh"
+#include "runtime.cuh"
 
 namespace fb {
 
@@ -253,8 +254,11 @@ using CfgL = TileCfg<2, 4, 8, 4, 16, 4>;   // 128 x 128 x 16, 256 threads, warp 
 using CfgS = TileCfg<2, 2, 4, 4, 16, 4>;   // 64 x 64 x 16, 128 threads, warp tile 32 x 32
 using CfgL16 = TileCfg<4, 4, 4, 4, 16, 4>; // 128 x 128 x 16, 512 threads, warp tile 32 x 32
 using CfgL32 = TileCfg<2, 4, 8, 4, 32, 3>; // 128 x 128 x 32, 256 threads, 3 stages
+using CfgS3 = TileCfg<2, 2, 4, 4, 16, 3>;  // 64 x 64 x 16, 3 stages (57 KB => 3 CTAs/SM)
+using CfgS8 = TileCfg<2, 2, 4, 4, 8, 5>;   // 64 x 64 x 8, 5 stages (61 KB => 3 CTAs/SM)
+using CfgM = TileCfg<4, 2, 4, 4, 16, 3>;   // 128 x 64 x 16, 256 threads, 3 stages (92 KB => 2 CTAs/SM)
 
-// development knob: FAER_B200_GEMM_CFG=1..4 forces one tile configuration (0/unset = heuristic)
+// development knob: FAER_B200_GEMM_CFG=1..7 forces one tile configuration (0/unset = heuristic)
 inline int forced_cfg() {
   static int v = -1;
   if (v < 0) {
@@ -295,12 +299,15 @@ void launch_layout(cudaStream_t stream, GemmF64Params& p) {
     case 2: launch_cfg<CfgL16, AK, BNM, VEC>(stream, p); return;
     case 3: launch_cfg<CfgL32, AK, BNM, VEC>(stream, p); return;
     case 4: launch_cfg<CfgS, AK, BNM, VEC>(stream, p); return;
+    case 5: launch_cfg<CfgS3, AK, BNM, VEC>(stream, p); return;
+    case 6: launch_cfg<CfgS8, AK, BNM, VEC>(stream, p); return;
+    case 7: launch_cfg<CfgM, AK, BNM, VEC>(stream, p); return;
     default: break;
   }
-  if (tiles_l >= 2 * 148)
-    launch_cfg<CfgL, AK, BNM, VEC>(stream, p);
-  else
-    launch_cfg<CfgS, AK, BNM, VEC>(stream, p);
+  // measured on B200 (profiles/r01_gemm_cfg_sweep.log): the 64x64 tile with several CTAs per SM beats the
+  // 128x128 single-CTA tile at every size (prologue/epilogue of one CTA overlap another CTA's main loop)
+  (void)tiles_l;
+  launch_cfg<CfgS, AK, BNM, VEC>(stream, p);
 }
 
 inline int transpose_struct(int s) {
@@ -359,9 +366,17 @@ void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, i
   b_vec = b_vec && aligned16(rhs.ptr);
   bool VEC = a_vec && b_vec;
 
+  // algorithmic flop count of this launch (structured operands / dst count only their kept part)
+  double flops = 2.0 * (double)p.m * (double)p.n * (double)p.k;
+  if (dst_struct != RECT) flops *= ((double)p.m + 1.0) / (2.0 * (double)p.m);
+  if (lhs_struct != RECT) flops *= 0.5;
+  if (rhs_struct != RECT) flops *= 0.5;
+  const bool prof = profiling_enabled();
 #define FB_DISPATCH(ak, bnm, vec)                                   \
   if (AK == ak && BNM == bnm && VEC == vec) {                       \
+    if (prof) profile_record_start(stream);                         \
     launch_layout<ak, bnm, vec>(stream, p);                         \
+    if (prof) profile_record_stop(stream, flops);                   \
     return;                                                         \
   }
   FB_DISPATCH(false, false, true)

@@ -74,6 +74,40 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
   if (tid == 0 && count) info[1] += count;
 }
 
+struct LltCtx {
+  cudaStream_t stream;
+  int regularize;
+  double eps, delta;
+  long long* d_info;
+  i64 nb;  // leaf (diagonal block) size, <= POTF2_MAX
+};
+
+// Recursive blocked LLT. Same dataflow as the reference's right-looking recursion (factor A00, solve the panel,
+// update the trailing lower triangle, continue) but split in HALVES instead of fixed 128-wide steps, so that
+// almost all flops are DMMA GEMMs with a large contracted dimension (k = n/2, n/4, ...): the trailing matrix is
+// read/written O(log n) times instead of n/128 times. Leaves (<= nb) are the single-CTA potf2 kernel.
+void llt_rec(const LltCtx& ctx, VD A, i64 j0) {
+  const i64 n = A.nrows;
+  if (n <= ctx.nb) {
+    potf2_kernel<<<1, POTF2_THREADS, (size_t)n * (n + 1) * sizeof(double), ctx.stream>>>(
+        A.ptr, A.rs, A.cs, (int)n, j0, ctx.regularize, ctx.eps, ctx.delta, ctx.d_info);
+    FB_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    return;
+  }
+  // split at a multiple of the leaf size closest to n/2
+  i64 n1 = ((n / 2 + ctx.nb - 1) / ctx.nb) * ctx.nb;
+  if (n1 >= n) n1 = ((n - 1) / ctx.nb) * ctx.nb;
+  const i64 n2 = n - n1;
+  VD A11 = A.sub(0, 0, n1, n1), A21 = A.sub(n1, 0, n2, n1), A22 = A.sub(n1, n1, n2, n2);
+  llt_rec(ctx, A11, j0);
+  // conj(L11) X = A21^T   (reference ldlt/factor.rs:421-426)
+  solve_lower_triangular_in_place_f64(ctx.stream, cv(A11), false, A21.t());
+  // A22(lower) += -1 * A21 * A21^H   (reference ldlt/factor.rs:435-446)
+  gemm_f64(ctx.stream, A22, TRI_LOWER, 1, cv(A21), RECT, cv(A21).t(), RECT, -1.0);
+  llt_rec(ctx, A22, j0 + n1);
+}
+
 }  // namespace
 
 LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, LltParams params) {
@@ -96,23 +130,8 @@ LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta,
     configured = true;
   }
 
-  for (i64 j = 0; j < n; j += nb) {
-    const i64 jb = n - j < nb ? n - j : nb;
-    VD A00 = A.sub(j, j, jb, jb);
-    potf2_kernel<<<1, POTF2_THREADS, (size_t)jb * (jb + 1) * sizeof(double), stream>>>(
-        A00.ptr, A00.rs, A00.cs, (int)jb, j, regularize, reg_eps, reg_delta, d_info);
-    FB_CUDA_CHECK(cudaGetLastError());
-  note_launch();
-    const i64 rem = n - j - jb;
-    if (rem > 0) {
-      VD A10 = A.sub(j + jb, j, rem, jb);
-      VD A11 = A.sub(j + jb, j + jb, rem, rem);
-      // conj(L00) X = A10^T   (reference ldlt/factor.rs:421-426)
-      solve_lower_triangular_in_place_f64(stream, cv(A00), false, A10.t());
-      // A11(lower) += -1 * A10 * A10^H   (reference ldlt/factor.rs:435-446)
-      gemm_f64(stream, A11, TRI_LOWER, 1, cv(A10), RECT, cv(A10).t(), RECT, -1.0);
-    }
-  }
+  LltCtx ctx{stream, regularize, reg_eps, reg_delta, d_info, nb};
+  llt_rec(ctx, A, 0);
   FB_CUDA_CHECK(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, stream));
   FB_CUDA_CHECK(cudaStreamSynchronize(stream));
   ws_free(d_info);

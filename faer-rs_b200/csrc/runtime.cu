@@ -92,6 +92,50 @@ void ws_release_all() {
   }
 }
 
+namespace {
+bool g_prof = false;
+struct ProfRec { cudaEvent_t e0, e1; double flops; };
+std::vector<ProfRec> g_prof_recs;
+cudaEvent_t g_prof_pending = nullptr;
+}  // namespace
+bool profiling_enabled() { return g_prof; }
+void profile_begin() {
+  g_prof_recs.clear();
+  g_prof = true;
+}
+void profile_record_start(cudaStream_t st) {
+  if (!g_prof) return;
+  FB_CUDA_CHECK(cudaEventCreate(&g_prof_pending));
+  FB_CUDA_CHECK(cudaEventRecord(g_prof_pending, st));
+}
+void profile_record_stop(cudaStream_t st, double flops) {
+  if (!g_prof || !g_prof_pending) return;
+  ProfRec r;
+  r.e0 = g_prof_pending;
+  g_prof_pending = nullptr;
+  FB_CUDA_CHECK(cudaEventCreate(&r.e1));
+  FB_CUDA_CHECK(cudaEventRecord(r.e1, st));
+  r.flops = flops;
+  g_prof_recs.push_back(r);
+}
+void profile_end(double* flops, double* ms, unsigned long long* count) {
+  g_prof = false;
+  double f = 0, t = 0;
+  for (auto& r : g_prof_recs) {
+    FB_CUDA_CHECK(cudaEventSynchronize(r.e1));
+    float m = 0;
+    FB_CUDA_CHECK(cudaEventElapsedTime(&m, r.e0, r.e1));
+    t += m;
+    f += r.flops;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  *flops = f;
+  *ms = t;
+  *count = g_prof_recs.size();
+  g_prof_recs.clear();
+}
+
 bool is_device_pointer(const void* p) {
   if (!p) return false;
   cudaPointerAttributes attr;

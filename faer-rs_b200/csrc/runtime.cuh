@@ -11,6 +11,13 @@ void set_current_stream(cudaStream_t s);
 void require_device();
 bool is_device_pointer(const void* p);
 
+// Optional per-launch timing of the dominant kernel (bench.py roofline): CUDA events around each GEMM launch.
+bool profiling_enabled();
+void profile_begin();
+void profile_record_start(cudaStream_t st);
+void profile_record_stop(cudaStream_t st, double flops);
+void profile_end(double* flops, double* ms, unsigned long long* count);
+
 // A matrix argument of the C ABI. Device pointers are used in place; host pointers are mirrored in device
 // memory (H2D on construction if `copy_in`, D2H in finish() if `copy_out`).
 class StagedMat {

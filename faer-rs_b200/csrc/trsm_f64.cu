@@ -14,16 +14,19 @@ namespace fb {
 
 namespace {
 
-constexpr int LEAF = 32;       // diagonal leaf size
-constexpr int LEAF_COLS = 128; // rhs columns per CTA (= threads)
+constexpr int LEAF = 64;        // diagonal leaf size (x lives in registers: LEAF doubles per thread)
+constexpr int LEAF_COLS = 128;  // rhs columns per CTA (= threads)
 
 // Solve T x = b for every column of the (n x ncols) rhs tile, n <= LEAF. T lower triangular (n x n).
+// One thread per rhs column; T is broadcast from shared memory; the rhs tile is staged through shared memory so
+// that global accesses are coalesced for either rhs layout.
 __global__ void __launch_bounds__(LEAF_COLS) trsm_leaf_lower_kernel(const double* __restrict__ T, i64 t_rs, i64 t_cs,
                                                                      int n, int unit, double* __restrict__ R, i64 r_rs,
                                                                      i64 r_cs, i64 ncols) {
-  __shared__ double Ts[LEAF][LEAF + 1];
-  __shared__ double Rs[LEAF][LEAF_COLS + 1];
-  __shared__ double Tinv[LEAF];
+  extern __shared__ double sm[];
+  double(*Ts)[LEAF + 1] = reinterpret_cast<double(*)[LEAF + 1]>(sm);
+  double(*Rs)[LEAF_COLS + 1] = reinterpret_cast<double(*)[LEAF_COLS + 1]>(sm + LEAF * (LEAF + 1));
+  double* Tinv = sm + LEAF * (LEAF + 1) + LEAF * (LEAF_COLS + 1);
   const int tid = threadIdx.x;
   const i64 c0 = (i64)blockIdx.x * LEAF_COLS;
   const int nc = (int)min((i64)LEAF_COLS, ncols - c0);
@@ -54,11 +57,16 @@ __global__ void __launch_bounds__(LEAF_COLS) trsm_leaf_lower_kernel(const double
 #pragma unroll
     for (int i = 0; i < LEAF; ++i) {
       if (i < n) {
-        double s = Rs[i][tid];
+        // two interleaved partial sums halve the dependent-FMA chain
+        double s0 = Rs[i][tid], s1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < LEAF; ++k)
-          if (k < i) s = fma(-Ts[i][k], x[k], s);
-        x[i] = s * Tinv[i];
+        for (int k = 0; k + 1 < LEAF; k += 2)
+          if (k + 1 < i) {
+            s0 = fma(-Ts[i][k], x[k], s0);
+            s1 = fma(-Ts[i][k + 1], x[k + 1], s1);
+          }
+        if ((i & 1) && i >= 1) s0 = fma(-Ts[i][i - 1], x[i - 1], s0);
+        x[i] = (s0 + s1) * Tinv[i];
       }
     }
 #pragma unroll
@@ -79,6 +87,8 @@ __global__ void __launch_bounds__(LEAF_COLS) trsm_leaf_lower_kernel(const double
   }
 }
 
+constexpr size_t LEAF_SMEM = sizeof(double) * (LEAF * (LEAF + 1) + LEAF * (LEAF_COLS + 1) + LEAF);
+
 // faer's split rule (reference: triangular_solve.rs:200-211)
 inline i64 split_size(i64 n) {
   i64 base_rem = n / 2;
@@ -95,7 +105,13 @@ void solve_lower_rec(cudaStream_t stream, VCD T, bool unit, VD rhs) {
   if (n == 0 || rhs.ncols == 0) return;
   if (n <= LEAF) {
     unsigned blocks = (unsigned)((rhs.ncols + LEAF_COLS - 1) / LEAF_COLS);
-    trsm_leaf_lower_kernel<<<blocks, LEAF_COLS, 0, stream>>>(T.ptr, T.rs, T.cs, (int)n, unit ? 1 : 0, rhs.ptr, rhs.rs,
+    static bool configured = false;
+    if (!configured) {
+      FB_CUDA_CHECK(cudaFuncSetAttribute(trsm_leaf_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)LEAF_SMEM));
+      configured = true;
+    }
+    trsm_leaf_lower_kernel<<<blocks, LEAF_COLS, LEAF_SMEM, stream>>>(T.ptr, T.rs, T.cs, (int)n, unit ? 1 : 0, rhs.ptr, rhs.rs,
                                                               rhs.cs, rhs.ncols);
     FB_CUDA_CHECK(cudaGetLastError());
   note_launch();

@@ -151,6 +151,10 @@ void faer_b200_set_stream(void *cuda_stream);
 unsigned long long faer_b200_launch_count(void);
 /* Free the cached device workspace. */
 void faer_b200_release_workspace(void);
+/* Per-launch timing of the dominant kernel (the DMMA GEMM): between begin and end every GEMM launch is bracketed by
+ * CUDA events on the launching stream; end() returns the summed algorithmic flop, summed kernel ms and launch count. */
+void faer_b200_profile_begin(void);
+void faer_b200_profile_end(double *flops, double *ms, unsigned long long *count);
 /* Version string. */
 const char *faer_b200_version(void);
 
