@@ -7,36 +7,50 @@
 //     d = Re(a_jj); [regularise]; fail with Err(j) if !(d > 0); l_jj = sqrt(d); fail if l_jj == 0 or non-finite;
 //     column j (INCLUDING the diagonal entry) is multiplied by recip(l_jj).
 //
-// B200 mapping: right-looking blocked loop on the host stream; the diagonal block is factored by ONE CTA in
-// shared memory with a rank-1 right-looking sweep that performs exactly the reference's per-element FMA
-// chain (same k order, same reciprocal-multiply), the panel solve is G3 and the trailing update is the
-// lower-masked DMMA GEMM (G2). A device status word carries the first failing column / the
-// regularisation count and is read back once per factorisation.
+// B200 mapping: recursive blocked driver on the host stream; the <=128-wide diagonal block is factored by ONE
+// CTA whose 1024 threads hold the block in REGISTERS (thread (lane, warp) owns rows lane+32a, columns warp+32b):
+// each column step broadcasts the unscaled pivot column through a double-buffered shared vector (one
+// __syncthreads per column) and every thread applies the reference's per-element FMA chain (same k order, same
+// reciprocal-multiply, diagonal scaled too) to its 16 entries => bit-identical to the reference leaf recurrence.
+// The panel solve is G3 and the trailing update is the lower-masked DMMA GEMM (G2). A device status word carries
+// the first failing column / the regularisation count and is read back once per factorisation.
 #include "linalg_f64.cuh"
 
 namespace fb {
 
 namespace {
 
-constexpr int POTF2_THREADS = 512;
+constexpr int POTF2_THREADS = 1024;
 constexpr int POTF2_MAX = 128;
 
 // info[0]: first failing global column (or -1), info[1]: regularisation count
 __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict__ A, i64 rs, i64 cs, int n, i64 j0,
                                                                int regularize, double eps, double delta,
                                                                long long* __restrict__ info) {
-  extern __shared__ double s[];  // s[i * ld + c], c <= i
-  const int ld = n + 1;
-  const int tid = threadIdx.x;
+  __shared__ double colbuf[2][POTF2_MAX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (info[0] >= 0) return;  // an earlier block already failed (uniform across the CTA)
-  for (int e = tid; e < n * n; e += POTF2_THREADS) {
-    int i = e % n, c = e / n;
-    if (c <= i) s[i * ld + c] = A[i * rs + c * cs];
+
+  // thread-owned entries: rows i = lane + 32a, columns c = warp + 32b, kept iff c <= i < n
+  double a[4][4];
+#pragma unroll
+  for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) {
+      const int i = lane + 32 * ai, c = warp + 32 * bi;
+      a[ai][bi] = (i < n && c <= i) ? A[(i64)i * rs + (i64)c * cs] : 0.0;
+    }
+  // owners of column 0 (warp 0, b = 0) publish it
+  if (warp == 0) {
+#pragma unroll
+    for (int ai = 0; ai < 4; ++ai) colbuf[0][lane + 32 * ai] = a[ai][0];
   }
   __syncthreads();
+
   int count = 0;
   for (int j = 0; j < n; ++j) {
-    double d = s[j * ld + j];
+    const double* col = colbuf[j & 1];
+    double d = col[j];
     if (regularize) {
       // LLT: sign == +1 (reference ldlt/factor.rs:122-144)
       if (d <= eps) {
@@ -54,19 +68,41 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
       return;
     }
     const double inv = 1.0 / sd;
-    const int r = n - j - 1;
-    // column j of L goes straight to global memory; shared column j stays unscaled for this step's readers
+    const int jw = j & 31;
+    // column j of L goes to global memory (owners: warp jw).
     // NB: like the reference, the stored diagonal is (unregularised a_jj) * recip(l_jj)
     // (ldlt/factor.rs:161-175 scales the whole column, diagonal included, and `diag` is a local copy).
-    for (int i = j + tid; i < n; i += POTF2_THREADS) A[i * rs + j * cs] = s[i * ld + j] * inv;
-    // trailing update, lower part only: a_ic <- fma(-l_cj, l_ij, a_ic)
-    // (2-D thread map: 32 lanes along c, POTF2_THREADS/32 rows; no integer division in the hot loop)
-    (void)r;
-    for (int i = j + 1 + (tid >> 5); i < n; i += POTF2_THREADS / 32) {
-      const double lij = s[i * ld + j] * inv;
-      for (int c = j + 1 + (tid & 31); c <= i; c += 32) {
-        const double lcj = s[c * ld + j] * inv;
-        s[i * ld + c] = fma(-lcj, lij, s[i * ld + c]);
+    if (warp == jw) {
+#pragma unroll
+      for (int ai = 0; ai < 4; ++ai) {
+        const int i = lane + 32 * ai;
+        if (i >= j && i < n) A[(i64)i * rs + (i64)j * cs] = col[i] * inv;
+      }
+    }
+    // trailing update: a_ic <- fma(-l_cj, l_ij, a_ic) for j < c <= i
+    double li[4], lc[4];
+#pragma unroll
+    for (int ai = 0; ai < 4; ++ai) li[ai] = col[lane + 32 * ai] * inv;
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) lc[bi] = col[warp + 32 * bi] * inv;
+#pragma unroll
+    for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+      for (int bi = 0; bi < 4; ++bi) {
+        const int i = lane + 32 * ai, c = warp + 32 * bi;
+        if (c > j && c <= i && i < n) a[ai][bi] = fma(-lc[bi], li[ai], a[ai][bi]);
+      }
+    // owners of column j+1 publish it (unscaled) into the other buffer
+    if (j + 1 < n && warp == ((j + 1) & 31)) {
+      const int nb = (j + 1) >> 5;
+      double* nxt = colbuf[(j + 1) & 1];
+#pragma unroll
+      for (int ai = 0; ai < 4; ++ai) {
+        double v = 0.0;
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi)
+          if (bi == nb) v = a[ai][bi];
+        nxt[lane + 32 * ai] = v;
       }
     }
     __syncthreads();
@@ -89,8 +125,8 @@ struct LltCtx {
 void llt_rec(const LltCtx& ctx, VD A, i64 j0) {
   const i64 n = A.nrows;
   if (n <= ctx.nb) {
-    potf2_kernel<<<1, POTF2_THREADS, (size_t)n * (n + 1) * sizeof(double), ctx.stream>>>(
-        A.ptr, A.rs, A.cs, (int)n, j0, ctx.regularize, ctx.eps, ctx.delta, ctx.d_info);
+    potf2_kernel<<<1, POTF2_THREADS, 0, ctx.stream>>>(A.ptr, A.rs, A.cs, (int)n, j0, ctx.regularize, ctx.eps, ctx.delta,
+                                                      ctx.d_info);
     FB_CUDA_CHECK(cudaGetLastError());
     note_launch();
     return;
@@ -123,15 +159,9 @@ LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta,
   long long h_info[2] = {-1, 0};
   FB_CUDA_CHECK(cudaMemcpyAsync(d_info, h_info, sizeof(h_info), cudaMemcpyHostToDevice, stream));
 
-  static bool configured = false;
-  if (!configured) {
-    FB_CUDA_CHECK(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(POTF2_MAX * (POTF2_MAX + 1) * sizeof(double))));
-    configured = true;
-  }
-
   LltCtx ctx{stream, regularize, reg_eps, reg_delta, d_info, nb};
   llt_rec(ctx, A, 0);
+
   FB_CUDA_CHECK(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, stream));
   FB_CUDA_CHECK(cudaStreamSynchronize(stream));
   ws_free(d_info);

@@ -57,6 +57,62 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
   __syncthreads();
 }
 
+// Net effect of transpositions [t0, t1) (rows relative to the view) as a gather list (dst row <- src row), built
+// by ONE WARP. Slots 0..63 are the group's own rows t0..t0+63, pivot rows outside are appended (warp-parallel search).
+__device__ __forceinline__ void build_plan_warp(const int* trans, int t0, int t1, int* ids, int* cur,
+                                                int* __restrict__ out_rows, int* __restrict__ out_src,
+                                                int* __restrict__ out_cnt, int lane) {
+  for (int q = lane; q < 2 * SWAP_GROUP; q += 32) {
+    ids[q] = q < SWAP_GROUP ? t0 + q : -1;
+    cur[q] = q < SWAP_GROUP ? t0 + q : -1;
+  }
+  __syncwarp();
+  int cnt = SWAP_GROUP;
+  for (int t = t0; t < t1; ++t) {
+    const int a = t, b = t + __ldcg(trans + t);  // L2 read: may have been written earlier in this kernel
+    if (a == b) continue;  // uniform
+    const int qa = a - t0;
+    int qb;
+    if (b < t0 + SWAP_GROUP) {
+      qb = b - t0;
+    } else {
+      const int q1 = SWAP_GROUP + lane, q2 = SWAP_GROUP + 32 + lane;
+      const bool h1 = q1 < cnt && ids[q1] == b, h2 = q2 < cnt && ids[q2] == b;
+      const unsigned m1 = __ballot_sync(0xffffffffu, h1), m2 = __ballot_sync(0xffffffffu, h2);
+      if (m1) qb = SWAP_GROUP + __ffs(m1) - 1;
+      else if (m2) qb = SWAP_GROUP + 32 + __ffs(m2) - 1;
+      else {
+        qb = cnt;
+        if (lane == 0) {
+          ids[cnt] = b;
+          cur[cnt] = b;
+        }
+        ++cnt;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int tmp = cur[qa];
+      cur[qa] = cur[qb];
+      cur[qb] = tmp;
+    }
+    __syncwarp();
+  }
+  int out = 0;
+  for (int base = 0; base < cnt; base += 32) {
+    const int q = base + lane;
+    const bool mv = q < cnt && ids[q] != cur[q];
+    const unsigned m = __ballot_sync(0xffffffffu, mv);
+    if (mv) {
+      const int pos = out + __popc(m & ((1u << lane) - 1u));
+      out_rows[pos] = ids[q];
+      out_src[pos] = cur[q];
+    }
+    out += __popc(m);
+  }
+  if (lane == 0) *out_cnt = out;
+}
+
 // Scratch layout (doubles): for parity p in {0,1}:
 //   cand_val[p][G], cand_idx[p][G] (as long long), cand_row[p][G][PANEL_W], diag_row[p][PANEL_W]
 struct PanelScratch {
@@ -88,9 +144,12 @@ __global__ void __launch_bounds__(PANEL_THREADS) lu_panel_kernel(double* __restr
   const int ncol = min(w, m);  // columns to eliminate
 
   // ---- load slice (coalesced along rows for column-major A) ----
-  for (int e = tid; e < nloc * w; e += PANEL_THREADS) {
-    int r = e % nloc, c = e / nloc;
-    S[r * LD + c] = A[(i64)(r0 + r) * rs + (i64)c * cs];
+  // (each thread owns rows r = tid, tid+256, ...; the column loop is unrolled so 8 independent loads are in flight)
+  for (int r = tid; r < nloc; r += PANEL_THREADS) {
+    const double* src = A + (i64)(r0 + r) * rs;
+    double* dst = S + r * LD;
+#pragma unroll 8
+    for (int c = 0; c < w; ++c) dst[c] = src[(i64)c * cs];
   }
   __syncthreads();
 
@@ -236,73 +295,30 @@ __global__ void __launch_bounds__(PANEL_THREADS) lu_panel_kernel(double* __restr
   }
   __syncthreads();
   // ---- store slice ----
-  for (int e = tid; e < nloc * w; e += PANEL_THREADS) {
-    int r = e % nloc, c = e / nloc;
-    A[(i64)(r0 + r) * rs + (i64)c * cs] = S[r * LD + c];
+  for (int r = tid; r < nloc; r += PANEL_THREADS) {
+    double* dstg = A + (i64)(r0 + r) * rs;
+    const double* srcs = S + r * LD;
+#pragma unroll 8
+    for (int c = 0; c < w; ++c) dstg[(i64)c * cs] = srcs[c];
   }
   // ---- swap plan for this window (one group) so that the caller can permute the outside columns ----
   if (plan_rows != nullptr && bid == 0) {
-    // all `trans` writes of this CTA are done (same thread 0 wrote them); build the net gather list
-    __syncthreads();
-    if (tid == 0) {
-      int ids[2 * PANEL_W], cur[2 * PANEL_W];
-      int cnt = 0;
-      for (int t = 0; t < ncol; ++t) {
-        const int a = t, b = t + trans[t];
-        if (a == b) continue;
-        int qa = -1, qb = -1;
-        for (int q = 0; q < cnt; ++q) {
-          if (ids[q] == a) qa = q;
-          if (ids[q] == b) qb = q;
-        }
-        if (qa < 0) { qa = cnt; ids[cnt] = a; cur[cnt] = a; ++cnt; }
-        if (qb < 0) { qb = cnt; ids[cnt] = b; cur[cnt] = b; ++cnt; }
-        const int tmp = cur[qa];
-        cur[qa] = cur[qb];
-        cur[qb] = tmp;
-      }
-      int out = 0;
-      for (int q = 0; q < cnt; ++q)
-        if (ids[q] != cur[q]) {
-          plan_rows[out] = ids[q];
-          plan_src[out] = cur[q];
-          ++out;
-        }
-      plan_cnt[0] = out;
-    }
+    __shared__ int p_ids[2 * SWAP_GROUP], p_cur[2 * SWAP_GROUP];
+    __syncthreads();  // thread 0's `trans` writes (global) are ordered before the reads below
+    __threadfence_block();
+    if (warp == 0) build_plan_warp(trans, 0, ncol, p_ids, p_cur, plan_rows, plan_src, plan_cnt, lane);
   }
 }
 
-// One thread per group of SWAP_GROUP transpositions: net effect as a gather list (dst row <- src row).
-__global__ void laswp_plan_kernel(const int* __restrict__ trans, int n, int* __restrict__ plan_rows,
-                                  int* __restrict__ plan_src, int* __restrict__ plan_cnt, int ngroups) {
-  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32) laswp_plan_kernel(const int* __restrict__ trans, int n, int* __restrict__ plan_rows,
+                                                        int* __restrict__ plan_src, int* __restrict__ plan_cnt,
+                                                        int ngroups) {
+  __shared__ int ids[2 * SWAP_GROUP], cur[2 * SWAP_GROUP];
+  const int gi = blockIdx.x;
   if (gi >= ngroups) return;
-  int ids[2 * SWAP_GROUP], cur[2 * SWAP_GROUP];
-  int cnt = 0;
   const int t0 = gi * SWAP_GROUP, t1 = min(n, t0 + SWAP_GROUP);
-  for (int t = t0; t < t1; ++t) {
-    const int a = t, b = t + trans[t];
-    if (a == b) continue;
-    int qa = -1, qb = -1;
-    for (int q = 0; q < cnt; ++q) {
-      if (ids[q] == a) qa = q;
-      if (ids[q] == b) qb = q;
-    }
-    if (qa < 0) { qa = cnt; ids[cnt] = a; cur[cnt] = a; ++cnt; }
-    if (qb < 0) { qb = cnt; ids[cnt] = b; cur[cnt] = b; ++cnt; }
-    const int tmp = cur[qa];
-    cur[qa] = cur[qb];
-    cur[qb] = tmp;
-  }
-  int out = 0;
-  for (int q = 0; q < cnt; ++q)
-    if (ids[q] != cur[q]) {
-      plan_rows[(i64)gi * 2 * SWAP_GROUP + out] = ids[q];
-      plan_src[(i64)gi * 2 * SWAP_GROUP + out] = cur[q];
-      ++out;
-    }
-  plan_cnt[gi] = out;
+  build_plan_warp(trans, t0, t1, ids, cur, plan_rows + (i64)gi * 2 * SWAP_GROUP, plan_src + (i64)gi * 2 * SWAP_GROUP,
+                  plan_cnt + gi, threadIdx.x);
 }
 
 // Apply the gather lists of all groups (in order) to a strip of SWAP_CW columns per CTA.
@@ -314,19 +330,24 @@ __global__ void __launch_bounds__(SWAP_THREADS) laswp_apply_kernel(double* __res
   const i64 c0 = (i64)blockIdx.x * SWAP_CW;
   const int nc = (int)min((i64)SWAP_CW, ncols - c0);
   const int tid = threadIdx.x;
+  const int q = tid & (2 * SWAP_GROUP - 1), cb = tid >> 7;  // 256 threads = 128 rows x 2 column phases
   for (int gi = 0; gi < ngroups; ++gi) {
     const int cnt = plan_cnt[gi];
     if (cnt == 0) continue;
-    const int* rows = plan_rows + (i64)gi * 2 * SWAP_GROUP;
-    const int* src = plan_src + (i64)gi * 2 * SWAP_GROUP;
-    for (int e = tid; e < cnt * nc; e += SWAP_THREADS) {
-      const int q = e % cnt, c = e / cnt;
-      tile[q][c] = A[(i64)src[q] * rs + (c0 + c) * cs];
+    const bool act = q < cnt;
+    const i64 srow = act ? (i64)plan_src[(i64)gi * 2 * SWAP_GROUP + q] : 0;
+    const i64 drow = act ? (i64)plan_rows[(i64)gi * 2 * SWAP_GROUP + q] : 0;
+    // independent loads, unrolled => full memory-level parallelism
+#pragma unroll 8
+    for (int cc = 0; cc < SWAP_CW / 2; ++cc) {
+      const int c = cb + 2 * cc;
+      if (act && c < nc) tile[q][c] = A[srow * rs + (c0 + c) * cs];
     }
     __syncthreads();
-    for (int e = tid; e < cnt * nc; e += SWAP_THREADS) {
-      const int q = e % cnt, c = e / cnt;
-      A[(i64)rows[q] * rs + (c0 + c) * cs] = tile[q][c];
+#pragma unroll 8
+    for (int cc = 0; cc < SWAP_CW / 2; ++cc) {
+      const int c = cb + 2 * cc;
+      if (act && c < nc) A[drow * rs + (c0 + c) * cs] = tile[q][c];
     }
     __syncthreads();
   }
@@ -422,8 +443,7 @@ void lu_rec(LuCtx& ctx, VD A, i64 start, i64 end, int* trans) {
   }
   if (has_outside) {
     const int ngroups = (int)((n + SWAP_GROUP - 1) / SWAP_GROUP);
-    laswp_plan_kernel<<<(ngroups + 63) / 64, 64, 0, ctx.st>>>(trans, (int)n, ctx.plan_rows, ctx.plan_src, ctx.plan_cnt,
-                                                              ngroups);
+    laswp_plan_kernel<<<ngroups, 32, 0, ctx.st>>>(trans, (int)n, ctx.plan_rows, ctx.plan_src, ctx.plan_cnt, ngroups);
     FB_CUDA_CHECK(cudaGetLastError());
     note_launch();
     apply_plan(ctx, A.sub(0, 0, m, start), ngroups);

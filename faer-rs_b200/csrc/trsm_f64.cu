@@ -31,22 +31,31 @@ __global__ void __launch_bounds__(LEAF_COLS) trsm_leaf_lower_kernel(const double
   const i64 c0 = (i64)blockIdx.x * LEAF_COLS;
   const int nc = (int)min((i64)LEAF_COLS, ncols - c0);
 
-  for (int e = tid; e < n * n; e += LEAF_COLS) {
-    int i = e % n, j = e / n;
-    Ts[i][j] = (j <= i) ? T[i * t_rs + j * t_cs] : 0.0;
+  // Staging loops are written so that every thread issues several INDEPENDENT global loads back to back
+  // (fixed trip counts + predicates, unrolled): a dependent load-per-iteration loop is latency-bound.
+  {
+    const int i = tid & (LEAF - 1);
+#pragma unroll 8
+    for (int jj = 0; jj < LEAF / 2; ++jj) {
+      const int j = (tid >> 6) + 2 * jj;
+      double v = 0.0;
+      if (i < n && j <= i) v = T[i * t_rs + j * t_cs];
+      if (i < n && j < n) Ts[i][j] = v;
+    }
   }
-  // stage rhs tile; iterate so that the unit-stride direction is the fast one
   const bool row_fast = (r_rs == 1 || r_rs == -1);
   if (row_fast) {
-    for (int e = tid; e < n * nc; e += LEAF_COLS) {
-      int i = e % n, c = e / n;
-      Rs[i][c] = R[i * r_rs + (c0 + c) * r_cs];
+    const int i = tid & (LEAF - 1);
+#pragma unroll 8
+    for (int cc = 0; cc < LEAF_COLS / 2; ++cc) {
+      const int c = (tid >> 6) + 2 * cc;
+      if (i < n && c < nc) Rs[i][c] = R[i * r_rs + (c0 + c) * r_cs];
     }
   } else {
-    for (int e = tid; e < n * nc; e += LEAF_COLS) {
-      int c = e % nc, i = e / nc;
-      Rs[i][c] = R[i * r_rs + (c0 + c) * r_cs];
-    }
+    const int c = tid;
+#pragma unroll 8
+    for (int i = 0; i < LEAF; ++i)
+      if (i < n && c < nc) Rs[i][c] = R[i * r_rs + (c0 + c) * r_cs];
   }
   __syncthreads();
   if (tid < n) Tinv[tid] = unit ? 1.0 : 1.0 / Ts[tid][tid];
@@ -75,15 +84,17 @@ __global__ void __launch_bounds__(LEAF_COLS) trsm_leaf_lower_kernel(const double
   }
   __syncthreads();
   if (row_fast) {
-    for (int e = tid; e < n * nc; e += LEAF_COLS) {
-      int i = e % n, c = e / n;
-      R[i * r_rs + (c0 + c) * r_cs] = Rs[i][c];
+    const int i = tid & (LEAF - 1);
+#pragma unroll 8
+    for (int cc = 0; cc < LEAF_COLS / 2; ++cc) {
+      const int c = (tid >> 6) + 2 * cc;
+      if (i < n && c < nc) R[i * r_rs + (c0 + c) * r_cs] = Rs[i][c];
     }
   } else {
-    for (int e = tid; e < n * nc; e += LEAF_COLS) {
-      int c = e % nc, i = e / nc;
-      R[i * r_rs + (c0 + c) * r_cs] = Rs[i][c];
-    }
+    const int c = tid;
+#pragma unroll 8
+    for (int i = 0; i < LEAF; ++i)
+      if (i < n && c < nc) R[i * r_rs + (c0 + c) * r_cs] = Rs[i][c];
   }
 }
 

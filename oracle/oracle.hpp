@@ -71,4 +71,15 @@ i64 llt_in_place(Mat<T> A, typename real_of<T>::type delta, typename real_of<T>:
 template <class T>
 i64 lu_in_place(Mat<T> A, i64* perm, i64* perm_inv, i64 recursion_threshold);
 
+// ---- oracle_qr.cpp ----
+// norm_l2: faer/src/linalg/reductions/norm_l2.rs:6-172
+template <class T> typename real_of<T>::type norm_l2(const T* p, i64 n, i64 stride);
+// Householder QR without pivoting: faer/src/linalg/qr/no_pivoting/factor.rs:258-301; Q_coeff is block_size x min(m,n);
+// returns the numerical rank.
+template <class T> i64 qr_in_place(Mat<T> A, Mat<T> Q_coeff, i64 blocking_threshold);
+i64 qr_recommended_block_size(i64 nrows, i64 ncols);
+// block reflector application: faer/src/linalg/householder.rs:370-620
+template <class T>
+void apply_block_householder_on_the_left(Mat<const T> V, Mat<const T> Tf, bool conj_lhs, Mat<T> M, bool forward);
+
 }  // namespace oracle

@@ -52,6 +52,14 @@ def load() -> C.CDLL:
     lib.oracle_llt.restype = C.c_longlong
     lib.oracle_lu.argtypes = [C.c_int, OMat, C.c_void_p, C.c_void_p, C.c_longlong]
     lib.oracle_lu.restype = C.c_longlong
+    lib.oracle_qr.argtypes = [C.c_int, OMat, OMat, C.c_longlong]
+    lib.oracle_qr.restype = C.c_longlong
+    lib.oracle_qr_recommended_block_size.argtypes = [C.c_longlong, C.c_longlong]
+    lib.oracle_qr_recommended_block_size.restype = C.c_longlong
+    lib.oracle_apply_block_householder_left.argtypes = [C.c_int, OMat, OMat, C.c_int, OMat, C.c_int]
+    lib.oracle_apply_block_householder_left.restype = C.c_longlong
+    lib.oracle_norm_l2.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_longlong]
+    lib.oracle_norm_l2.restype = C.c_double
     _lib = lib
     return lib
 
@@ -114,3 +122,53 @@ def lu(A, recursion_threshold=16):
     r = load().oracle_lu(_DT[A.dtype], _om(A), perm.ctypes.data, perm_inv.ctypes.data, recursion_threshold)
     assert r != -100
     return perm, perm_inv, int(r)
+
+
+def qr_recommended_block_size(nrows: int, ncols: int) -> int:
+    """qr/no_pivoting/factor.rs:91-116"""
+    return int(load().oracle_qr_recommended_block_size(nrows, ncols))
+
+
+def qr(A, block_size=None, blocking_threshold=48 * 48):
+    """In-place Householder QR without pivoting (qr/no_pivoting/factor.rs:258-301).
+    Returns (Q_coeff [block_size x min(m,n)], rank). R is the upper triangle of A, V strictly below the diagonal."""
+    m, n = A.shape
+    bs = block_size or qr_recommended_block_size(m, n)
+    H = np.zeros((bs, min(m, n)), dtype=A.dtype, order="F")
+    r = load().oracle_qr(_DT[A.dtype], _om(A), _om(H), blocking_threshold)
+    assert r != -100
+    return H, int(r)
+
+
+def apply_block_householder_on_the_left(V, T, M, forward: bool, conj_lhs=False) -> None:
+    """M <- (I - V T^-1 V^H) M (forward=False) or (I - V T^-H V^H) M (forward=True)  (householder.rs:370-620)."""
+    r = load().oracle_apply_block_householder_left(_DT[M.dtype], _om(V), _om(T), int(conj_lhs), _om(M), int(forward))
+    assert r == 0
+
+
+def apply_q_transpose_sequence(QR, H, M, conj_lhs=True) -> None:
+    """apply_block_householder_sequence_transpose_on_the_left_in_place_with_conj (householder.rs:768-808): M <- Q^H M."""
+    bs, size = H.shape
+    j = 0
+    while j < size:
+        b = min(bs, size - j)
+        # transpose_on_the_left composes conj_lhs with Conj::Yes and uses forward = true (householder.rs:697-719)
+        apply_block_householder_on_the_left(QR[j:, j:j + b], H[:b, j:j + b], M[j:, :], True, conj_lhs=not conj_lhs)
+        j += b
+
+
+def apply_q_sequence(QR, H, M, conj_lhs=False) -> None:
+    """apply_block_householder_sequence_on_the_left_in_place_with_conj (householder.rs:724-765): M <- Q M."""
+    bs, size = H.shape
+    j = size
+    b = size % bs or bs
+    while j > 0:
+        jp = j - b
+        apply_block_householder_on_the_left(QR[jp:, jp:j], H[:j - jp, jp:j], M[jp:, :], False, conj_lhs=conj_lhs)
+        j = jp
+        b = bs
+
+
+def norm_l2(x) -> float:
+    x = np.ascontiguousarray(x).ravel()
+    return float(load().oracle_norm_l2(_DT[x.dtype], x.ctypes.data, x.size, 1))

@@ -65,4 +65,28 @@ long long oracle_lu(int dtype, OMat A, long long* perm, long long* perm_inv, lon
   return r;
 }
 
+// Householder QR (no pivoting). Q_coeff: block_size x min(m,n). returns the rank.
+long long oracle_qr(int dtype, OMat A, OMat Q_coeff, long long blocking_threshold) {
+  long long r = -100;
+  DISPATCH(dtype, r = qr_in_place<T>(mm<T>(A), mm<T>(Q_coeff), blocking_threshold));
+  return r;
+}
+long long oracle_qr_recommended_block_size(long long nrows, long long ncols) {
+  return qr_recommended_block_size(nrows, ncols);
+}
+// M <- (I - V T^-1 V^H) M (forward = 0) or (I - V T^-H V^H) M (forward = 1); conj_lhs conjugates V and T.
+long long oracle_apply_block_householder_left(int dtype, OMat V, OMat Tf, int conj_lhs, OMat M, int forward) {
+  DISPATCH(dtype, apply_block_householder_on_the_left<T>(mc<T>(V), mc<T>(Tf), conj_lhs != 0, mm<T>(M), forward != 0));
+  return 0;
+}
+double oracle_norm_l2(int dtype, const void* p, long long n, long long stride) {
+  switch (dtype) {
+    case 0: return norm_l2<float>((const float*)p, n, stride);
+    case 1: return norm_l2<double>((const double*)p, n, stride);
+    case 2: return norm_l2<std::complex<float>>((const std::complex<float>*)p, n, stride);
+    case 3: return norm_l2<std::complex<double>>((const std::complex<double>*)p, n, stride);
+  }
+  return -1.0;
+}
+
 }  // extern "C"
