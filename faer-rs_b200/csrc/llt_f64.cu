@@ -28,8 +28,12 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
                                                                int regularize, double eps, double delta,
                                                                long long* __restrict__ info) {
   __shared__ double colbuf[2][POTF2_MAX];
+  __shared__ double s_inv[2];
+  __shared__ int s_fail[2];
+  __shared__ int s_count;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (info[0] >= 0) return;  // an earlier block already failed (uniform across the CTA)
+  if (tid == 0) s_count = 0;
 
   // thread-owned entries: rows i = lane + 32a, columns c = warp + 32b, kept iff c <= i < n
   double a[4][4];
@@ -40,34 +44,46 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
       const int i = lane + 32 * ai, c = warp + 32 * bi;
       a[ai][bi] = (i < n && c <= i) ? A[(i64)i * rs + (i64)c * cs] : 0.0;
     }
+  __syncthreads();
+
+  // The thread that owns the diagonal entry of column jc does the (expensive, serial) pivot arithmetic ONCE:
+  // regularise, test, sqrt, reciprocal (reference ldlt/factor.rs:122-160) and publishes recip(l_jj) + a fail flag.
+  auto publish_pivot = [&](int jc, double d) {
+    int fail = 0;
+    if (regularize) {
+      // LLT: sign == +1
+      if (d <= eps) {
+        d = delta;
+        s_count += 1;  // single writer per column, ordered by the per-column barrier
+      }
+    }
+    double inv = 0.0;
+    if (!(d > 0.0)) {
+      fail = 1;
+    } else {
+      const double sd = sqrt(d);
+      if (sd == 0.0 || !isfinite(sd)) fail = 1;
+      else inv = 1.0 / sd;
+    }
+    s_inv[jc & 1] = inv;
+    s_fail[jc & 1] = fail;
+  };
+
   // owners of column 0 (warp 0, b = 0) publish it
   if (warp == 0) {
 #pragma unroll
     for (int ai = 0; ai < 4; ++ai) colbuf[0][lane + 32 * ai] = a[ai][0];
+    if (lane == 0) publish_pivot(0, a[0][0]);
   }
   __syncthreads();
 
-  int count = 0;
   for (int j = 0; j < n; ++j) {
     const double* col = colbuf[j & 1];
-    double d = col[j];
-    if (regularize) {
-      // LLT: sign == +1 (reference ldlt/factor.rs:122-144)
-      if (d <= eps) {
-        d = delta;
-        ++count;
-      }
-    }
-    if (!(d > 0.0)) {
+    if (s_fail[j & 1]) {
       if (tid == 0) info[0] = j0 + j;
       return;
     }
-    const double sd = sqrt(d);
-    if (sd == 0.0 || !isfinite(sd)) {
-      if (tid == 0) info[0] = j0 + j;
-      return;
-    }
-    const double inv = 1.0 / sd;
+    const double inv = s_inv[j & 1];
     const int jw = j & 31;
     // column j of L goes to global memory (owners: warp jw).
     // NB: like the reference, the stored diagonal is (unregularised a_jj) * recip(l_jj)
@@ -96,6 +112,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
     if (j + 1 < n && warp == ((j + 1) & 31)) {
       const int nb = (j + 1) >> 5;
       double* nxt = colbuf[(j + 1) & 1];
+      double diag = 0.0;
 #pragma unroll
       for (int ai = 0; ai < 4; ++ai) {
         double v = 0.0;
@@ -103,11 +120,13 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
         for (int bi = 0; bi < 4; ++bi)
           if (bi == nb) v = a[ai][bi];
         nxt[lane + 32 * ai] = v;
+        if (ai == nb) diag = v;
       }
+      if (lane == ((j + 1) & 31)) publish_pivot(j + 1, diag);
     }
     __syncthreads();
   }
-  if (tid == 0 && count) info[1] += count;
+  if (tid == 0 && s_count) info[1] += s_count;
 }
 
 struct LltCtx {

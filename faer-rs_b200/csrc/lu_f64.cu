@@ -228,13 +228,21 @@ __global__ void __launch_bounds__(PANEL_THREADS) lu_panel_kernel(double* __restr
       double v = 0.0;
       long long ix = (1ll << 62);
       int wc = -1;
-      for (int b = lane; b < G; b += 32) {
-        double ov = __ldcg(&sc.cand_val[par * G + b]);
-        long long oi = __ldcg(&sc.cand_idx[par * G + b]);
-        if (ov > 0.0 && cand_better(ov, oi, v, ix)) {
-          v = ov;
-          ix = oi;
-          wc = b;
+      // G <= 160: five predicated, independent (value, index) loads per lane, all in flight together
+      double ovs[5];
+      long long ois[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int b = lane + 32 * u;
+        ovs[u] = b < G ? __ldcg(&sc.cand_val[par * G + b]) : 0.0;
+        ois[u] = b < G ? __ldcg(&sc.cand_idx[par * G + b]) : (1ll << 62);
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        if (ovs[u] > 0.0 && cand_better(ovs[u], ois[u], v, ix)) {
+          v = ovs[u];
+          ix = ois[u];
+          wc = lane + 32 * u;
         }
       }
 #pragma unroll

@@ -5,9 +5,11 @@
 // 200-211 (`block_size` split rule), 577-604 (upper = lower on reversed views),
 // 16-198 (leaves: reciprocal of the diagonal, then multiply).
 //
-// B200 mapping: the recursion stays on the host (it is O(n/32) launches); every off-diagonal update is a
-// DMMA GEMM launch (gemm_f64); the <=32-wide diagonal leaves run as one thread per right-hand-side column
-// with the rhs tile staged through shared memory so global accesses are coalesced for either rhs layout.
+// B200 mapping: the recursion stays on the host (it is O(n/64) launches); every off-diagonal update is a
+// DMMA GEMM launch (gemm_f64); the <=64-wide diagonal leaves run as one thread per right-hand-side column:
+// the thread pulls its whole column (<=64 values) into REGISTERS with independent loads (all in flight at once;
+// coalesced across the warp when rhs columns are contiguous, full 128-B lines per thread when rhs rows are),
+// substitutes against T broadcast from shared memory with two interleaved FMA chains, and writes the column back.
 #include "linalg_f64.cuh"
 
 namespace fb {
@@ -17,88 +19,53 @@ namespace {
 constexpr int LEAF = 64;        // diagonal leaf size (x lives in registers: LEAF doubles per thread)
 constexpr int LEAF_COLS = 128;  // rhs columns per CTA (= threads)
 
-// Solve T x = b for every column of the (n x ncols) rhs tile, n <= LEAF. T lower triangular (n x n).
-// One thread per rhs column; T is broadcast from shared memory; the rhs tile is staged through shared memory so
-// that global accesses are coalesced for either rhs layout.
 __global__ void __launch_bounds__(LEAF_COLS) trsm_leaf_lower_kernel(const double* __restrict__ T, i64 t_rs, i64 t_cs,
                                                                      int n, int unit, double* __restrict__ R, i64 r_rs,
                                                                      i64 r_cs, i64 ncols) {
-  extern __shared__ double sm[];
-  double(*Ts)[LEAF + 1] = reinterpret_cast<double(*)[LEAF + 1]>(sm);
-  double(*Rs)[LEAF_COLS + 1] = reinterpret_cast<double(*)[LEAF_COLS + 1]>(sm + LEAF * (LEAF + 1));
-  double* Tinv = sm + LEAF * (LEAF + 1) + LEAF * (LEAF_COLS + 1);
+  __shared__ double Ts[LEAF][LEAF + 1];
+  __shared__ double Tinv[LEAF];
   const int tid = threadIdx.x;
-  const i64 c0 = (i64)blockIdx.x * LEAF_COLS;
-  const int nc = (int)min((i64)LEAF_COLS, ncols - c0);
+  const i64 c = (i64)blockIdx.x * LEAF_COLS + tid;
+  const bool active = c < ncols;
 
-  // Staging loops are written so that every thread issues several INDEPENDENT global loads back to back
-  // (fixed trip counts + predicates, unrolled): a dependent load-per-iteration loop is latency-bound.
+  // T tile: fixed trip count + predicates, unrolled => 16 independent loads per thread in flight
   {
     const int i = tid & (LEAF - 1);
-#pragma unroll 8
+#pragma unroll 16
     for (int jj = 0; jj < LEAF / 2; ++jj) {
       const int j = (tid >> 6) + 2 * jj;
       double v = 0.0;
       if (i < n && j <= i) v = T[i * t_rs + j * t_cs];
-      if (i < n && j < n) Ts[i][j] = v;
+      Ts[i][j] = v;
     }
   }
-  const bool row_fast = (r_rs == 1 || r_rs == -1);
-  if (row_fast) {
-    const int i = tid & (LEAF - 1);
-#pragma unroll 8
-    for (int cc = 0; cc < LEAF_COLS / 2; ++cc) {
-      const int c = (tid >> 6) + 2 * cc;
-      if (i < n && c < nc) Rs[i][c] = R[i * r_rs + (c0 + c) * r_cs];
-    }
-  } else {
-    const int c = tid;
-#pragma unroll 8
-    for (int i = 0; i < LEAF; ++i)
-      if (i < n && c < nc) Rs[i][c] = R[i * r_rs + (c0 + c) * r_cs];
-  }
+  // this thread's rhs column -> registers (independent loads)
+  double x[LEAF];
+  double* col = R + c * r_cs;
+#pragma unroll
+  for (int i = 0; i < LEAF; ++i) x[i] = (active && i < n) ? col[i * r_rs] : 0.0;
   __syncthreads();
-  if (tid < n) Tinv[tid] = unit ? 1.0 : 1.0 / Ts[tid][tid];
+  if (tid < LEAF) Tinv[tid] = (unit || tid >= n) ? 1.0 : 1.0 / Ts[tid][tid];
   __syncthreads();
 
-  if (tid < nc) {
-    double x[LEAF];
 #pragma unroll
-    for (int i = 0; i < LEAF; ++i) {
-      if (i < n) {
-        // two interleaved partial sums halve the dependent-FMA chain
-        double s0 = Rs[i][tid], s1 = 0.0;
+  for (int i = 0; i < LEAF; ++i) {
+    // two interleaved partial sums halve the dependent-FMA chain; rows >= n see T == 0 and are never stored
+    double s0 = x[i], s1 = 0.0;
 #pragma unroll
-        for (int k = 0; k + 1 < LEAF; k += 2)
-          if (k + 1 < i) {
-            s0 = fma(-Ts[i][k], x[k], s0);
-            s1 = fma(-Ts[i][k + 1], x[k + 1], s1);
-          }
-        if ((i & 1) && i >= 1) s0 = fma(-Ts[i][i - 1], x[i - 1], s0);
-        x[i] = (s0 + s1) * Tinv[i];
-      }
+    for (int k = 0; k + 1 < i; k += 2) {
+      s0 = fma(-Ts[i][k], x[k], s0);
+      s1 = fma(-Ts[i][k + 1], x[k + 1], s1);
     }
-#pragma unroll
-    for (int i = 0; i < LEAF; ++i)
-      if (i < n) Rs[i][tid] = x[i];
+    if (i & 1) s0 = fma(-Ts[i][i - 1], x[i - 1], s0);
+    x[i] = (s0 + s1) * Tinv[i];
   }
-  __syncthreads();
-  if (row_fast) {
-    const int i = tid & (LEAF - 1);
-#pragma unroll 8
-    for (int cc = 0; cc < LEAF_COLS / 2; ++cc) {
-      const int c = (tid >> 6) + 2 * cc;
-      if (i < n && c < nc) R[i * r_rs + (c0 + c) * r_cs] = Rs[i][c];
-    }
-  } else {
-    const int c = tid;
-#pragma unroll 8
+  if (active) {
+#pragma unroll
     for (int i = 0; i < LEAF; ++i)
-      if (i < n && c < nc) R[i * r_rs + (c0 + c) * r_cs] = Rs[i][c];
+      if (i < n) col[i * r_rs] = x[i];
   }
 }
-
-constexpr size_t LEAF_SMEM = sizeof(double) * (LEAF * (LEAF + 1) + LEAF * (LEAF_COLS + 1) + LEAF);
 
 // faer's split rule (reference: triangular_solve.rs:200-211)
 inline i64 split_size(i64 n) {
@@ -116,16 +83,10 @@ void solve_lower_rec(cudaStream_t stream, VCD T, bool unit, VD rhs) {
   if (n == 0 || rhs.ncols == 0) return;
   if (n <= LEAF) {
     unsigned blocks = (unsigned)((rhs.ncols + LEAF_COLS - 1) / LEAF_COLS);
-    static bool configured = false;
-    if (!configured) {
-      FB_CUDA_CHECK(cudaFuncSetAttribute(trsm_leaf_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)LEAF_SMEM));
-      configured = true;
-    }
-    trsm_leaf_lower_kernel<<<blocks, LEAF_COLS, LEAF_SMEM, stream>>>(T.ptr, T.rs, T.cs, (int)n, unit ? 1 : 0, rhs.ptr, rhs.rs,
+    trsm_leaf_lower_kernel<<<blocks, LEAF_COLS, 0, stream>>>(T.ptr, T.rs, T.cs, (int)n, unit ? 1 : 0, rhs.ptr, rhs.rs,
                                                               rhs.cs, rhs.ncols);
     FB_CUDA_CHECK(cudaGetLastError());
-  note_launch();
+    note_launch();
     return;
   }
   const i64 bs = split_size(n);
