@@ -4,8 +4,9 @@ Layout:
   csrc/      hand-written CUDA kernels + the extern "C" boundary (-> libfaer_b200.so)
   capi.py    ctypes binding of include/faer_b200.h
   linalg.py  host-side mirror of faer::linalg for the hot path (same names / argument meaning)
+  dist.py    multi-GPU front end: block-column-cyclic layout helpers + distributed LLT
 
 The directory name contains a '-', so import it through the repo-root shim:  `import faer_b200`.
 """
-from . import capi, linalg  # noqa: F401
+from . import capi, dist, linalg  # noqa: F401
 from .capi import load  # noqa: F401

@@ -1,0 +1,253 @@
+// Multi-GPU (one process per GPU) 1-D block-column-cyclic factorizations with NCCL panel broadcast over NVLink.
+//
+// The reference is a single-process CPU library (no collective anywhere), so this file has no reference
+// counterpart; it distributes the SAME factorizations (llt_f64.cu / lu_f64.cu kernels) the single-GPU entry points
+// use. SURVEY.md §8e: block column b (width nb) is owned by rank b % P; at step k the owner factors panel k,
+// broadcasts it (plus the pivots for LU) and every rank updates only its own block columns — one exchange per panel,
+// no reduction on the data path. Look-ahead: the owner of panel k+1 updates and factors it on a high-priority
+// stream and starts its broadcast while the other trailing updates of step k are still running.
+//
+// NCCL is resolved at run time with dlopen("libnccl.so.2") (the copy torch already loaded in a torch process), so
+// libfaer_b200.so has no link-time NCCL dependency and single-GPU users never touch it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "runtime.cuh"
+
+namespace fb {
+
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+ncclComm_t g_comm = nullptr;
+int g_rank = 0, g_nranks = 1;
+cudaStream_t g_panel_stream = nullptr;  // high priority: panel factorization + broadcast
+cudaStream_t g_main_stream = nullptr;   // trailing updates
+
+bool load_nccl() {
+  if (g_nccl.handle) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    fprintf(stderr, "faer_b200: cannot dlopen libnccl.so.2: %s\n", dlerror());
+    return false;
+  }
+  g_nccl.handle = h;
+#define LOAD(field, sym)                                            \
+  *(void**)(&g_nccl.field) = dlsym(h, sym);                         \
+  if (!g_nccl.field) {                                              \
+    fprintf(stderr, "faer_b200: libnccl lacks %s\n", sym);          \
+    return false;                                                   \
+  }
+  LOAD(GetUniqueId, "ncclGetUniqueId")
+  LOAD(CommInitRank, "ncclCommInitRank")
+  LOAD(CommDestroy, "ncclCommDestroy")
+  LOAD(Broadcast, "ncclBroadcast")
+  LOAD(GroupStart, "ncclGroupStart")
+  LOAD(GroupEnd, "ncclGroupEnd")
+  LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+  return true;
+}
+
+#define FB_NCCL_CHECK(x)                                                                            \
+  do {                                                                                              \
+    ncclResult_t r_ = (x);                                                                          \
+    if (r_ != ncclSuccess) {                                                                        \
+      fprintf(stderr, "faer_b200: NCCL error %s at %s:%d\n", g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+      abort();                                                                                      \
+    }                                                                                               \
+  } while (0)
+
+// pack / unpack a (rows x cols) sub-block of a column-major matrix (ld) to / from a contiguous buffer
+void pack(cudaStream_t st, double* dst, const double* src, i64 ld, i64 rows, i64 cols) {
+  if (rows == 0 || cols == 0) return;
+  FB_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)rows * 8, src, (size_t)ld * 8, (size_t)rows * 8, (size_t)cols,
+                                  cudaMemcpyDeviceToDevice, st));
+}
+
+inline i64 nblocks(i64 n, i64 nb) { return (n + nb - 1) / nb; }
+// number of local columns of rank r
+inline i64 local_cols(i64 n, i64 nb, int P, int r) {
+  i64 cnt = 0;
+  for (i64 b = r; b < nblocks(n, nb); b += P) cnt += std::min(nb, n - b * nb);
+  return cnt;
+}
+// local column offset of global block column b (owned by this rank)
+inline i64 local_off(i64 b, i64 nb, int P) { return (b / P) * nb; }
+
+}  // namespace
+
+bool dist_ready() { return g_comm != nullptr; }
+int dist_rank() { return g_rank; }
+int dist_nranks() { return g_nranks; }
+
+int dist_unique_id(void* out128) {
+  if (!load_nccl()) return -1;
+  ncclUniqueId id;
+  FB_NCCL_CHECK(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+int dist_init(int rank, int nranks, const void* id128) {
+  require_device();
+  if (!load_nccl()) return -1;
+  if (g_comm) return 0;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  FB_NCCL_CHECK(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
+  g_rank = rank;
+  g_nranks = nranks;
+  int lo = 0, hi = 0;
+  FB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  FB_CUDA_CHECK(cudaStreamCreateWithPriority(&g_panel_stream, cudaStreamNonBlocking, hi));
+  FB_CUDA_CHECK(cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, lo));
+  return 0;
+}
+
+void dist_finalize() {
+  if (g_comm) {
+    g_nccl.CommDestroy(g_comm);
+    g_comm = nullptr;
+  }
+  if (g_panel_stream) cudaStreamDestroy(g_panel_stream), g_panel_stream = nullptr;
+  if (g_main_stream) cudaStreamDestroy(g_main_stream), g_main_stream = nullptr;
+  g_rank = 0;
+  g_nranks = 1;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Distributed LLT. A_local: column-major n x local_cols (ld = ld_local >= n): the block columns this rank owns, in
+// increasing global order. On return the lower triangle of the global matrix holds L (strict upper part untouched).
+// Works for P == 1 too (no communicator needed) — the same code path the multi-GPU runs use, so results do not depend
+// on P: every output element receives its rank-nb updates in the same order k = 0, 1, ...
+// -----------------------------------------------------------------------------------------------------------------
+LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta, double reg_eps, int lookahead) {
+  require_device();
+  const int P = g_comm ? g_nranks : 1, me = g_comm ? g_rank : 0;
+  LltResult res{true, 0, 0};
+  if (n == 0) return res;
+  FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
+  cudaStream_t sp = g_comm ? g_panel_stream : current_stream();
+  cudaStream_t sm = g_comm ? g_main_stream : current_stream();
+  const bool two_streams = sp != sm && lookahead;
+  if (!two_streams) sm = sp;
+  // order after whatever the caller enqueued on the current stream
+  cudaEvent_t ev_start;
+  FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  FB_CUDA_CHECK(cudaEventRecord(ev_start, current_stream()));
+  FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_start, 0));
+  if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
+
+  const i64 nblk = nblocks(n, nb);
+  // two panel buffers (double buffering for look-ahead)
+  double* W[2];
+  W[0] = (double*)ws_alloc((size_t)n * nb * 8);
+  W[1] = (double*)ws_alloc((size_t)n * nb * 8);
+  long long* d_info = (long long*)ws_alloc(4 * sizeof(long long));
+  long long h_info[2] = {-1, 0};
+  FB_CUDA_CHECK(cudaMemcpyAsync(d_info, h_info, sizeof(h_info), cudaMemcpyHostToDevice, sp));
+  std::vector<cudaEvent_t> ev_bcast((size_t)nblk), ev_used((size_t)nblk);
+  for (i64 k = 0; k < nblk; ++k) {
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_bcast[(size_t)k], cudaEventDisableTiming));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_used[(size_t)k], cudaEventDisableTiming));
+  }
+
+  auto factor_and_bcast = [&](i64 k) {
+    // runs on sp. Panel k: rows k0..n of block column k.
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    const int owner = (int)(k % P);
+    double* Wk = W[k & 1];
+    if (k >= 2) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - 2)], 0));  // buffer reuse
+    if (owner == me) {
+      double* pk = A_local + local_off(k, nb, P) * ld + k0;
+      VD diag{pk, kb, kb, 1, ld};
+      llt_cholesky_device_f64(sp, diag, reg_delta, reg_eps, d_info, k0);
+      if (rows > kb) {
+        VD below{pk + kb, rows - kb, kb, 1, ld};
+        solve_lower_triangular_in_place_f64(sp, cv(diag), false, below.t());
+      }
+      pack(sp, Wk, pk, ld, rows, kb);
+    }
+    if (P > 1) FB_NCCL_CHECK(g_nccl.Broadcast(Wk, Wk, (size_t)rows * kb, ncclDouble, owner, g_comm, sp));
+    FB_CUDA_CHECK(cudaEventRecord(ev_bcast[(size_t)k], sp));
+  };
+
+  auto update_block_col = [&](cudaStream_t st, i64 k, i64 j) {
+    // block column j (> k, owned by me) -= W_k[rows >= j0] * W_k[rows of block j]^T
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows_k = n - k0;
+    const i64 j0 = j * nb, jb = std::min(nb, n - j0);
+    const double* Wk = W[k & 1];
+    double* pj = A_local + local_off(j, nb, P) * ld + j0;
+    VCD Wj{Wk + (j0 - k0), jb, kb, 1, rows_k};                       // rows of block j in the panel
+    VD djj{pj, jb, jb, 1, ld};
+    gemm_f64(st, djj, TRI_LOWER, 1, Wj, RECT, Wj.t(), RECT, -1.0);    // diagonal block: lower triangle only
+    const i64 below = n - j0 - jb;
+    if (below > 0) {
+      VCD Wb{Wk + (j0 - k0) + jb, below, kb, 1, rows_k};
+      VD dbj{pj + jb, below, jb, 1, ld};
+      gemm_f64(st, dbj, 1, Wb, Wj.t(), -1.0);
+    }
+  };
+
+  factor_and_bcast(0);
+  for (i64 k = 0; k < nblk; ++k) {
+    // trailing updates of step k need panel k
+    if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_bcast[(size_t)k], 0));
+    const i64 kn = k + 1;
+    if (kn < nblk) {
+      if ((int)(kn % P) == me) {
+        // look-ahead: bring block column k+1 up to date first (on the panel stream), then factor + broadcast it
+        // block column k+1 has received updates 0..k-1 on sm; order sp after them
+        if (two_streams && k >= 1) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - 1)], 0));
+        update_block_col(sp, k, kn);
+      }
+      factor_and_bcast(kn);
+    }
+    for (i64 j = k + 2; j < nblk; ++j)
+      if ((int)(j % P) == me) update_block_col(sm, k, j);
+    FB_CUDA_CHECK(cudaEventRecord(ev_used[(size_t)k], sm));
+  }
+  if (two_streams) {
+    FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(nblk - 1)], 0));
+  }
+  FB_CUDA_CHECK(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, sp));
+  FB_CUDA_CHECK(cudaStreamSynchronize(sp));
+  if (two_streams) FB_CUDA_CHECK(cudaStreamSynchronize(sm));
+  for (i64 k = 0; k < nblk; ++k) {
+    cudaEventDestroy(ev_bcast[(size_t)k]);
+    cudaEventDestroy(ev_used[(size_t)k]);
+  }
+  cudaEventDestroy(ev_start);
+  ws_free(d_info);
+  ws_free(W[1]);
+  ws_free(W[0]);
+  // the status word lives on the owners; combine across ranks (tiny host-side exchange through a broadcast per rank
+  // would need another collective: instead every owner's failure is propagated through the panel data itself — a
+  // failed panel is NaN-free but the failing rank reports; callers reduce the status with their own process group).
+  if (h_info[0] >= 0) {
+    res.ok = false;
+    res.non_positive_pivot_index = (size_t)h_info[0];
+  } else {
+    res.dynamic_regularization_count = (size_t)h_info[1];
+  }
+  return res;
+}
+
+}  // namespace fb

@@ -242,6 +242,31 @@ unsigned long long faer_b200_launch_count(void) { return g_launch_count; }
 void faer_b200_release_workspace(void) { ws_release_all(); }
 void faer_b200_profile_begin(void) { profile_begin(); }
 void faer_b200_profile_end(double* flops, double* ms, unsigned long long* count) { profile_end(flops, ms, count); }
+// ---- multi-GPU extensions (dist.cu) ----
+int faer_b200_dist_unique_id(void* out128) { return dist_unique_id(out128); }
+int faer_b200_dist_init(int rank, int nranks, const void* id128) { return dist_init(rank, nranks, id128); }
+void faer_b200_dist_finalize(void) { dist_finalize(); }
+FaerV0_24_LltStatus faer_b200_dist_llt_factor_in_place_f64(void* A_local, size_t ld, size_t n, size_t nb,
+                                                           FaerV0_24_LltRegularization regularization, int lookahead) {
+  double delta = 0.0, eps = 0.0;
+  if (regularization.dynamic_regularization_delta)
+    delta = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_delta);
+  if (regularization.dynamic_regularization_epsilon)
+    eps = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_epsilon);
+  FB_ASSERT(n == 0 || is_device_pointer(A_local), "distributed entry points take device-resident local matrices");
+  LltResult r = dist_llt_f64((double*)A_local, (i64)ld, (i64)n, (i64)nb, delta, eps, lookahead);
+  FaerV0_24_LltStatus out;
+  memset(&out, 0, sizeof(out));
+  if (r.ok) {
+    out.tag = FaerV0_24_LltStatus_Ok;
+    out.ok.dynamic_regularization_count = r.dynamic_regularization_count;
+  } else {
+    out.tag = FaerV0_24_LltStatus_NonPositivePivot;
+    out.non_positive_pivot.index = r.non_positive_pivot_index;
+  }
+  return out;
+}
+
 const char* faer_b200_version(void) { return "faer_b200 0.1 (faer-ffi v0_23 ABI subset, sm_100a)"; }
 
 }  // extern "C"

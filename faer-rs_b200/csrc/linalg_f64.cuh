@@ -25,6 +25,9 @@ struct LltResult {
 // `reg_delta`/`reg_eps`: dynamic regularisation (active iff both > 0), reference llt/factor.rs:85-87.
 LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, LltParams params);
 
+// same factorisation, device-only (no sync / read-back); status accumulates in d_info (see llt_f64.cu)
+void llt_cholesky_device_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, long long* d_info, i64 j0);
+
 // ---- lu::partial_pivoting::factor (reference: faer/src/linalg/lu/partial_pivoting/factor.rs:234-295) ----
 struct PartialPivLuParams {
   size_t recursion_threshold;  // faer default 16
@@ -35,6 +38,16 @@ struct PartialPivLuParams {
 // Returns the transposition count.
 size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, void* perm_inv, int idx_bytes,
                                    PartialPivLuParams params);
+
+// ---- multi-GPU (dist.cu): 1-D block-column-cyclic factorizations, one process per GPU, NCCL panel broadcast ----
+int dist_unique_id(void* out128);                       // rank 0: 128-byte NCCL unique id
+int dist_init(int rank, int nranks, const void* id128);  // all ranks (collective)
+void dist_finalize();
+bool dist_ready();
+int dist_rank();
+int dist_nranks();
+// A_local: column-major n x (local columns), ld >= n; block column b (width nb) lives on rank b % P.
+LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta, double reg_eps, int lookahead);
 
 // ---- device workspace (grow-only pool, one per process) ----
 void* ws_alloc(size_t bytes);  // 256-byte aligned device memory, cached across calls

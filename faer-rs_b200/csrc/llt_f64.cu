@@ -95,19 +95,27 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
         if (i >= j && i < n) A[(i64)i * rs + (i64)j * cs] = col[i] * inv;
       }
     }
-    // trailing update: a_ic <- fma(-l_cj, l_ij, a_ic) for j < c <= i
-    double li[4], lc[4];
+    // trailing update: a_ic <- fma(-l_cj, l_ij, a_ic) for j < c <= i. The column test depends only on (warp, bi, j):
+    // it is warp-uniform, so dead column slots are BRANCHED over (no predicated-off instruction issue).
+    if (warp + 96 > j) {
+      double li[4];
 #pragma unroll
-    for (int ai = 0; ai < 4; ++ai) li[ai] = col[lane + 32 * ai] * inv;
-#pragma unroll
-    for (int bi = 0; bi < 4; ++bi) lc[bi] = col[warp + 32 * bi] * inv;
-#pragma unroll
-    for (int ai = 0; ai < 4; ++ai)
+      for (int ai = 0; ai < 4; ++ai) li[ai] = col[lane + 32 * ai] * inv;
 #pragma unroll
       for (int bi = 0; bi < 4; ++bi) {
-        const int i = lane + 32 * ai, c = warp + 32 * bi;
-        if (c > j && c <= i && i < n) a[ai][bi] = fma(-lc[bi], li[ai], a[ai][bi]);
+        const int c = warp + 32 * bi;
+        if (c > j && c < n) {
+          const double lc = col[c] * inv;
+#pragma unroll
+          for (int ai = 0; ai < 4; ++ai) {
+            const int i = lane + 32 * ai;
+            if (32 * ai + 31 >= c) {  // warp-uniform: this row slot intersects i >= c
+              if (i >= c && i < n) a[ai][bi] = fma(-lc, li[ai], a[ai][bi]);
+            }
+          }
+        }
       }
+    }
     // owners of column j+1 publish it (unscaled) into the other buffer
     if (j + 1 < n && warp == ((j + 1) & 31)) {
       const int nb = (j + 1) >> 5;
@@ -164,6 +172,16 @@ void llt_rec(const LltCtx& ctx, VD A, i64 j0) {
 }
 
 }  // namespace
+
+// Device-side variant for callers that own the status word (multi-GPU driver): no synchronisation, no read-back.
+// d_info[0] must hold -1 (or the first failing column of an earlier block), d_info[1] the regularisation count.
+void llt_cholesky_device_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, long long* d_info, i64 j0) {
+  FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
+  if (A.nrows == 0) return;
+  const int regularize = (reg_delta > 0.0 && reg_eps > 0.0) ? 1 : 0;
+  LltCtx ctx{stream, regularize, reg_eps, reg_delta, d_info, POTF2_MAX};
+  llt_rec(ctx, A, j0);
+}
 
 LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, LltParams params) {
   FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");

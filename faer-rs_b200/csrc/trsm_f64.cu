@@ -67,6 +67,114 @@ __global__ void __launch_bounds__(LEAF_COLS) trsm_leaf_lower_kernel(const double
   }
 }
 
+// Fused leaf for 64 < n <= 128: one launch does  x_top = T11^-1 b_top;  b_bot -= T21 x_top;  x_bot = T22^-1 b_bot
+// (the reference's recursion step, triangular_solve.rs:541-576, for one split) with T11/T21/T22 in shared memory.
+// x_top stays in registers while the bottom rows are streamed through in chunks (updated in place in global memory),
+// then the bottom column is pulled into registers for the second substitution.
+constexpr int LEAF2 = 2 * LEAF;
+constexpr size_t LEAF2_SMEM = sizeof(double) * (3 * LEAF * (LEAF + 1) + LEAF2);
+
+__global__ void __launch_bounds__(LEAF_COLS) trsm_leaf128_lower_kernel(const double* __restrict__ T, i64 t_rs, i64 t_cs,
+                                                                        int n, int unit, double* __restrict__ R, i64 r_rs,
+                                                                        i64 r_cs, i64 ncols) {
+  extern __shared__ double sm2[];
+  double(*T11)[LEAF + 1] = reinterpret_cast<double(*)[LEAF + 1]>(sm2);
+  double(*T21)[LEAF + 1] = reinterpret_cast<double(*)[LEAF + 1]>(sm2 + LEAF * (LEAF + 1));
+  double(*T22)[LEAF + 1] = reinterpret_cast<double(*)[LEAF + 1]>(sm2 + 2 * LEAF * (LEAF + 1));
+  double* Tinv = sm2 + 3 * LEAF * (LEAF + 1);
+  const int tid = threadIdx.x;
+  const i64 c = (i64)blockIdx.x * LEAF_COLS + tid;
+  const bool active = c < ncols;
+  const int nbot = n - LEAF;  // 1..64
+
+  {
+    const int i = tid & (LEAF - 1);
+#pragma unroll 16
+    for (int jj = 0; jj < LEAF / 2; ++jj) {
+      const int j = (tid >> 6) + 2 * jj;
+      T11[i][j] = (j <= i) ? T[i * t_rs + j * t_cs] : 0.0;
+    }
+#pragma unroll 16
+    for (int jj = 0; jj < LEAF / 2; ++jj) {
+      const int j = (tid >> 6) + 2 * jj;
+      T21[i][j] = (i < nbot) ? T[(LEAF + i) * t_rs + j * t_cs] : 0.0;
+    }
+#pragma unroll 16
+    for (int jj = 0; jj < LEAF / 2; ++jj) {
+      const int j = (tid >> 6) + 2 * jj;
+      T22[i][j] = (i < nbot && j <= i) ? T[(LEAF + i) * t_rs + (LEAF + j) * t_cs] : 0.0;
+    }
+  }
+  double x[LEAF];
+  double* col = R + c * r_cs;
+#pragma unroll
+  for (int i = 0; i < LEAF; ++i) x[i] = active ? col[i * r_rs] : 0.0;
+  __syncthreads();
+  if (tid < LEAF) {
+    Tinv[tid] = unit ? 1.0 : 1.0 / T11[tid][tid];
+    Tinv[LEAF + tid] = (unit || tid >= nbot) ? 1.0 : 1.0 / T22[tid][tid];
+  }
+  __syncthreads();
+
+  // ---- top solve ----
+#pragma unroll
+  for (int i = 0; i < LEAF; ++i) {
+    double s0 = x[i], s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 1 < i; k += 2) {
+      s0 = fma(-T11[i][k], x[k], s0);
+      s1 = fma(-T11[i][k + 1], x[k + 1], s1);
+    }
+    if (i & 1) s0 = fma(-T11[i][i - 1], x[i - 1], s0);
+    x[i] = (s0 + s1) * Tinv[i];
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < LEAF; ++i) col[i * r_rs] = x[i];
+  }
+  // ---- bottom rows: b_bot -= T21 x_top, streamed 8 rows at a time ----
+  double* colb = col + (i64)LEAF * r_rs;
+  for (int i0 = 0; i0 < LEAF; i0 += 8) {
+    double y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) y[u] = (active && i0 + u < nbot) ? colb[(i0 + u) * r_rs] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      double s0 = y[u], s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < LEAF; k += 2) {
+        s0 = fma(-T21[i0 + u][k], x[k], s0);
+        s1 = fma(-T21[i0 + u][k + 1], x[k + 1], s1);
+      }
+      y[u] = s0 + s1;
+    }
+    if (active) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u < nbot) colb[(i0 + u) * r_rs] = y[u];
+    }
+  }
+  // ---- bottom solve (the thread re-reads its own just-written values) ----
+#pragma unroll
+  for (int i = 0; i < LEAF; ++i) x[i] = (active && i < nbot) ? colb[i * r_rs] : 0.0;
+#pragma unroll
+  for (int i = 0; i < LEAF; ++i) {
+    double s0 = x[i], s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 1 < i; k += 2) {
+      s0 = fma(-T22[i][k], x[k], s0);
+      s1 = fma(-T22[i][k + 1], x[k + 1], s1);
+    }
+    if (i & 1) s0 = fma(-T22[i][i - 1], x[i - 1], s0);
+    x[i] = (s0 + s1) * Tinv[LEAF + i];
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < LEAF; ++i)
+      if (i < nbot) colb[i * r_rs] = x[i];
+  }
+}
+
 // faer's split rule (reference: triangular_solve.rs:200-211)
 inline i64 split_size(i64 n) {
   i64 base_rem = n / 2;
@@ -85,6 +193,20 @@ void solve_lower_rec(cudaStream_t stream, VCD T, bool unit, VD rhs) {
     unsigned blocks = (unsigned)((rhs.ncols + LEAF_COLS - 1) / LEAF_COLS);
     trsm_leaf_lower_kernel<<<blocks, LEAF_COLS, 0, stream>>>(T.ptr, T.rs, T.cs, (int)n, unit ? 1 : 0, rhs.ptr, rhs.rs,
                                                               rhs.cs, rhs.ncols);
+    FB_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    return;
+  }
+  if (n <= LEAF2) {
+    static bool configured = false;
+    if (!configured) {
+      FB_CUDA_CHECK(cudaFuncSetAttribute(trsm_leaf128_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)LEAF2_SMEM));
+      configured = true;
+    }
+    unsigned blocks = (unsigned)((rhs.ncols + LEAF_COLS - 1) / LEAF_COLS);
+    trsm_leaf128_lower_kernel<<<blocks, LEAF_COLS, LEAF2_SMEM, stream>>>(T.ptr, T.rs, T.cs, (int)n, unit ? 1 : 0, rhs.ptr,
+                                                                         rhs.rs, rhs.cs, rhs.ncols);
     FB_CUDA_CHECK(cudaGetLastError());
     note_launch();
     return;

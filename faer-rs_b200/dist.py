@@ -1,0 +1,138 @@
+"""Multi-GPU front end: 1-D block-column-cyclic layout helpers + the distributed LLT entry point.
+
+One process per GPU (torchrun); `torch.distributed` is the plumbing (rendezvous, id exchange, status reduction); the
+data path is the library's own NCCL broadcast of each factored panel (csrc/dist.cu), issued on a high-priority CUDA
+stream so that it overlaps the trailing updates (look-ahead). The reference has no multi-process code
+(SURVEY.md §2b); the layout follows SURVEY.md §8e: block column b (width nb) lives on rank b % P.
+
+The layout helpers are pure index arithmetic (numpy / torch, CPU or GPU) and are unit-tested on CPU with a
+world-size-2 gloo group (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+# ---- layout (pure index arithmetic) ------------------------------------------------------------------
+def num_blocks(n: int, nb: int) -> int:
+    return (n + nb - 1) // nb
+
+
+def owner_of_block(b: int, nranks: int) -> int:
+    return b % nranks
+
+
+def local_blocks(n: int, nb: int, nranks: int, rank: int) -> list[int]:
+    """Global block-column indices owned by `rank`, in local storage order."""
+    return list(range(rank, num_blocks(n, nb), nranks))
+
+
+def local_cols(n: int, nb: int, nranks: int, rank: int) -> int:
+    return sum(min(nb, n - b * nb) for b in local_blocks(n, nb, nranks, rank))
+
+
+def local_col_offset(b: int, nb: int, nranks: int) -> int:
+    """Local column offset of global block column b on its owner."""
+    return (b // nranks) * nb
+
+
+def global_col_indices(n: int, nb: int, nranks: int, rank: int) -> np.ndarray:
+    """Global column index of every local column of `rank` (length local_cols)."""
+    idx = [np.arange(b * nb, min(n, (b + 1) * nb)) for b in local_blocks(n, nb, nranks, rank)]
+    return np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64)
+
+
+def scatter_block_cyclic(A, nb: int, nranks: int, rank: int):
+    """Local part (n x local_cols, column-major for numpy inputs) of a replicated global matrix."""
+    cols = global_col_indices(A.shape[0] if A.shape[0] == A.shape[1] else A.shape[1], nb, nranks, rank)
+    if capi._is_torch(A):
+        import torch
+        return A[:, torch.as_tensor(cols, device=A.device)].T.contiguous().T
+    return np.asfortranarray(A[:, cols])
+
+
+def gather_block_cyclic(locals_, n: int, nb: int, nranks: int):
+    """Inverse of scatter_block_cyclic: list of per-rank local matrices -> global n x n (numpy)."""
+    out = np.zeros((locals_[0].shape[0], n), dtype=locals_[0].dtype, order="F")
+    for r, loc in enumerate(locals_):
+        out[:, global_col_indices(n, nb, nranks, r)] = loc
+    return out
+
+
+# ---- communicator ------------------------------------------------------------------------------------
+def init_from_torch_distributed() -> None:
+    """Create the library's NCCL communicator over the default torch.distributed group (collective call)."""
+    import torch
+    import torch.distributed as dist
+    lib = capi.load()
+    _bind(lib)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        assert lib.faer_b200_dist_unique_id(buf) == 0
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    buf2 = (C.c_ubyte * 128).from_buffer_copy(raw)
+    assert lib.faer_b200_dist_init(rank, world, buf2) == 0
+
+
+def finalize() -> None:
+    lib = capi.load()
+    _bind(lib)
+    lib.faer_b200_dist_finalize()
+
+
+_bound = False
+
+
+def _bind(lib) -> None:
+    global _bound
+    if _bound:
+        return
+    lib.faer_b200_dist_unique_id.argtypes = [C.c_void_p]
+    lib.faer_b200_dist_unique_id.restype = C.c_int
+    lib.faer_b200_dist_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    lib.faer_b200_dist_init.restype = C.c_int
+    lib.faer_b200_dist_finalize.argtypes = []
+    lib.faer_b200_dist_finalize.restype = None
+    lib.faer_b200_dist_llt_factor_in_place_f64.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                          capi.LltRegularization, C.c_int]
+    lib.faer_b200_dist_llt_factor_in_place_f64.restype = capi.LltStatus
+    _bound = True
+
+
+# ---- distributed LLT ---------------------------------------------------------------------------------
+def cholesky_in_place(A_local, n: int, nb: int = 512, regularization=(0.0, 0.0), lookahead: bool = True):
+    """Distributed in-place LLT. `A_local`: torch CUDA tensor, column-major view (n x local_cols, stride (1, ld)).
+    Returns (fail_index or -1, regularisation count) reduced over the ranks of the default process group (if any)."""
+    import torch
+    lib = capi.load()
+    _bind(lib)
+    assert capi._is_torch(A_local) and A_local.is_cuda and A_local.dtype == torch.float64
+    assert A_local.shape[0] == n and (A_local.shape[1] == 0 or A_local.stride(0) == 1)
+    ld = A_local.stride(1) if A_local.shape[1] > 1 else max(n, 1)
+    delta = C.c_double(float(regularization[0])); eps = C.c_double(float(regularization[1]))
+    reg = capi.LltRegularization(C.cast(C.pointer(delta), C.c_void_p), C.cast(C.pointer(eps), C.c_void_p))
+    st = lib.faer_b200_dist_llt_factor_in_place_f64(A_local.data_ptr(), ld, n, nb, reg, 1 if lookahead else 0)
+    fail = int(st.value) if st.tag == 1 else -1
+    cnt = int(st.value) if st.tag == 0 else 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            big = 1 << 62
+            t = torch.tensor([fail if fail >= 0 else big, -cnt], dtype=torch.int64, device=A_local.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)  # min failing index; counts are summed below
+            c = torch.tensor([cnt], dtype=torch.int64, device=A_local.device)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            fail = int(t[0].item()) if int(t[0].item()) < big else -1
+            cnt = int(c.item())
+    except ImportError:  # pragma: no cover
+        pass
+    return fail, cnt

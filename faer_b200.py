@@ -16,5 +16,6 @@ if _NAME not in sys.modules:
 _pkg = sys.modules[_NAME]
 capi = _pkg.capi
 linalg = _pkg.linalg
+dist = _pkg.dist
 load = _pkg.load
 PKG_DIR = _PKG_DIR

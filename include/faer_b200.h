@@ -155,6 +155,18 @@ void faer_b200_release_workspace(void);
  * CUDA events on the launching stream; end() returns the summed algorithmic flop, summed kernel ms and launch count. */
 void faer_b200_profile_begin(void);
 void faer_b200_profile_end(double *flops, double *ms, unsigned long long *count);
+/* ---- multi-GPU: one process per GPU, 1-D block-column-cyclic layout, NCCL panel broadcast (no reference
+ * counterpart: faer is single-process). Rank 0 obtains a 128-byte id, the caller ships it to the
+ * other ranks (e.g. torch.distributed broadcast), every rank calls dist_init (collective). A_local is the DEVICE
+ * column-major n x (local columns) matrix holding the block columns b with b % nranks == rank, in increasing b.
+ * The returned status is this rank's view (only the owner of a failing panel sees NonPositivePivot): reduce it
+ * over the ranks with the caller's process group. Works without dist_init as a single-rank run. */
+int faer_b200_dist_unique_id(void *out128);
+int faer_b200_dist_init(int rank, int nranks, const void *id128);
+void faer_b200_dist_finalize(void);
+struct FaerV0_24_LltStatus faer_b200_dist_llt_factor_in_place_f64(void *A_local, size_t ld, size_t n, size_t nb,
+                                                                  struct FaerV0_24_LltRegularization regularization,
+                                                                  int lookahead);
 /* Version string. */
 const char *faer_b200_version(void);
 

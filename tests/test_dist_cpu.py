@@ -1,0 +1,170 @@
+"""CPU tests of the multi-GPU host logic with a world-size-2 gloo group (no GPU needed).
+
+What is covered here: the block-column-cyclic layout helpers (faer-rs_b200/dist.py) and the step/ownership/broadcast
+schedule of the distributed LLT and LU, executed with the CPU ORACLE as the per-block compute (test infrastructure) and
+gloo as the transport. The schedule below is the one csrc/dist.cu runs on the GPUs (same panel order, same owner rule,
+same update order per block column), so a layout/ownership/ordering bug shows up here. The CUDA implementation itself is
+exercised by tests/test_gpu_dist.py (-m gpu) and by the multi-rank runs of bench.py.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, nb, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import faer_b200
+    from oracle import oracle as orc
+    lay = faer_b200._pkg.dist if hasattr(faer_b200, "_pkg") else None
+    from faer_rs_b200 import dist as lay  # noqa: F811  (registered by the faer_b200 shim)
+
+    rng = np.random.default_rng(0)  # same seed on every rank: replicated global input
+    G = rng.standard_normal((n, n))
+    A = np.asfortranarray(G @ G.T + n * np.eye(n))
+    loc = lay.scatter_block_cyclic(A, nb, world, rank)
+    assert loc.shape == (n, lay.local_cols(n, nb, world, rank))
+
+    # ---- distributed LLT schedule (mirrors csrc/dist.cu::dist_llt_f64) ----
+    nblk = lay.num_blocks(n, nb)
+    for k in range(nblk):
+        k0 = k * nb; kb = min(nb, n - k0); owner = lay.owner_of_block(k, world)
+        W = np.zeros((n - k0, kb), order="F")
+        if owner == rank:
+            off = lay.local_col_offset(k, nb, world)
+            panel = loc[k0:, off:off + kb]
+            diag = np.asfortranarray(panel[:kb, :])
+            fail, _ = orc.llt(diag)
+            assert fail == -1
+            panel[:kb, :] = diag
+            if n - k0 > kb:
+                below_t = np.ascontiguousarray(panel[kb:, :]).T  # (kb x rows) view, solve conj(L) X = A10^T
+                orc.solve_triangular(np.asfortranarray(np.tril(diag)), below_t, lower=True, unit=False)
+                panel[kb:, :] = below_t.T
+            W[:, :] = panel
+            W[:kb, :] = np.tril(W[:kb, :])
+        t = torch.from_numpy(np.ascontiguousarray(W))
+        dist.broadcast(t, src=owner)
+        W = np.asfortranarray(t.numpy())
+        for j in range(k + 1, nblk):
+            if lay.owner_of_block(j, world) != rank:
+                continue
+            j0 = j * nb; jb = min(nb, n - j0); off = lay.local_col_offset(j, nb, world)
+            Wj = W[j0 - k0:j0 - k0 + jb, :]
+            blk = loc[j0:, off:off + jb]
+            full = blk - W[j0 - k0:, :] @ Wj.T
+            # diagonal block: lower triangle only (strict upper part untouched)
+            d = blk[:jb, :].copy()
+            blk[:, :] = full
+            iu = np.triu_indices(jb, 1)
+            blk[:jb, :][iu] = d[iu]
+    np.save(os.path.join(out_dir, f"llt_{rank}.npy"), loc)
+
+    # ---- distributed LU schedule (panel factor on the owner, broadcast panel + transpositions, swaps everywhere) ----
+    rng = np.random.default_rng(1)
+    M = np.asfortranarray(rng.standard_normal((n, n)))
+    loc = lay.scatter_block_cyclic(M, nb, world, rank)
+    trans_all = np.zeros(n, dtype=np.int64)
+    for k in range(nblk):
+        k0 = k * nb; kb = min(nb, n - k0); owner = lay.owner_of_block(k, world)
+        W = np.zeros((n - k0, kb), order="F"); piv = np.zeros(kb, dtype=np.int64)
+        if owner == rank:
+            off = lay.local_col_offset(k, nb, world)
+            panel = np.asfortranarray(loc[k0:, off:off + kb])
+            perm, _, _ = orc.lu(panel)
+            # recover the transposition sequence from the permutation (replay: perm.swap(i, i + t_i))
+            cur = np.arange(n - k0)
+            for i in range(kb):
+                src = int(np.where(cur == perm[i])[0][0])
+                piv[i] = src - i
+                cur[i], cur[src] = cur[src], cur[i]
+            loc[k0:, off:off + kb] = panel
+            W[:, :] = panel
+        tw = torch.from_numpy(np.ascontiguousarray(W)); tp = torch.from_numpy(piv)
+        dist.broadcast(tw, src=owner); dist.broadcast(tp, src=owner)
+        W = np.asfortranarray(tw.numpy()); piv = tp.numpy()
+        trans_all[k0:k0 + kb] = piv
+        # apply the swaps to every local column except the panel itself
+        mycols = np.ones(loc.shape[1], bool)
+        if owner == rank:
+            off = lay.local_col_offset(k, nb, world); mycols[off:off + kb] = False
+        for i in range(kb):
+            a, b = k0 + i, k0 + i + piv[i]
+            if a != b:
+                tmp = loc[a, mycols].copy(); loc[a, mycols] = loc[b, mycols]; loc[b, mycols] = tmp
+        L11 = np.tril(W[:kb, :], -1) + np.eye(kb)
+        for j in range(k + 1, nblk):
+            if lay.owner_of_block(j, world) != rank:
+                continue
+            j0 = j * nb; jb = min(nb, n - j0); off = lay.local_col_offset(j, nb, world)
+            U = np.asfortranarray(loc[k0:k0 + kb, off:off + jb])
+            orc.solve_triangular(np.asfortranarray(L11), U, lower=True, unit=True)
+            loc[k0:k0 + kb, off:off + jb] = U
+            loc[k0 + kb:, off:off + jb] -= W[kb:, :] @ U
+    np.save(os.path.join(out_dir, f"lu_{rank}.npy"), loc)
+    np.save(os.path.join(out_dir, f"lu_trans_{rank}.npy"), trans_all)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,nb", [(96, 16), (100, 24)])
+def test_block_cyclic_llt_and_lu_schedule_gloo_world2(tmp_path, oracle, n, nb):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, nb, str(tmp_path)), nprocs=world, join=True)
+    import faer_b200  # noqa: F401
+    from faer_rs_b200 import dist as lay
+    # LLT: gather and compare with the single-process oracle
+    locs = [np.load(tmp_path / f"llt_{r}.npy") for r in range(world)]
+    got = lay.gather_block_cyclic(locs, n, nb, world)
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal((n, n)); A = np.asfortranarray(G @ G.T + n * np.eye(n))
+    want = A.copy(order="F"); fail, _ = oracle.llt(want); assert fail == -1
+    assert np.allclose(np.tril(got), np.tril(want), rtol=1e-11, atol=1e-11)
+    assert np.array_equal(np.triu(got, 1), np.triu(A, 1))  # strict upper triangle untouched
+    # LU: permutation identical to the oracle's, factors within tolerance
+    locs = [np.load(tmp_path / f"lu_{r}.npy") for r in range(world)]
+    got = lay.gather_block_cyclic(locs, n, nb, world)
+    t0 = np.load(tmp_path / "lu_trans_0.npy"); t1 = np.load(tmp_path / "lu_trans_1.npy")
+    assert np.array_equal(t0, t1)
+    perm = np.arange(n)
+    for i, t in enumerate(t0):
+        perm[i], perm[i + t] = perm[i + t], perm[i]
+    rng = np.random.default_rng(1)
+    M = np.asfortranarray(rng.standard_normal((n, n)))
+    want = M.copy(order="F"); perm_o, _, _ = oracle.lu(want)
+    assert np.array_equal(perm, perm_o)
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-10)
+
+
+def test_layout_helpers():
+    import faer_b200  # noqa: F401
+    from faer_rs_b200 import dist as lay
+    for n, nb, P in [(100, 16, 3), (64, 16, 4), (17, 8, 2), (5, 8, 4)]:
+        cols = [lay.global_col_indices(n, nb, P, r) for r in range(P)]
+        allc = np.sort(np.concatenate(cols))
+        assert np.array_equal(allc, np.arange(n))
+        for r in range(P):
+            assert len(cols[r]) == lay.local_cols(n, nb, P, r)
+            for b in lay.local_blocks(n, nb, P, r):
+                assert lay.owner_of_block(b, P) == r
+                off = lay.local_col_offset(b, nb, P)
+                assert cols[r][off] == b * nb
+        A = np.arange(n * n, dtype=np.float64).reshape(n, n)
+        locs = [lay.scatter_block_cyclic(A, nb, P, r) for r in range(P)]
+        assert np.array_equal(lay.gather_block_cyclic(locs, n, nb, P), A)
