@@ -250,4 +250,134 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   return res;
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Distributed LU with partial pivoting (square n x n), same layout. Step k: the owner factors panel k (all rows
+// k0.., our recursive panel LU => pivots identical to the single-GPU path: the pivot search only ever looks at the
+// panel's own, fully updated columns), broadcasts the factored panel + its kb transpositions; every rank applies the
+// row swaps to ALL its other columns (left ones too: final L is fully permuted, LAPACK/faer convention), then
+// U_kj = L_kk^-1 A_kj and A_(k+1:, j) -= L_(k+1:, k) U_kj on its own block columns j > k.
+// -----------------------------------------------------------------------------------------------------------------
+size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, long long* perm_inv, int lookahead) {
+  require_device();
+  const int P = g_comm ? g_nranks : 1, me = g_comm ? g_rank : 0;
+  for (i64 i = 0; i < n; ++i) perm_fwd[i] = i;
+  size_t n_trans = 0;
+  if (n == 0) return 0;
+  FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
+  cudaStream_t sp = g_comm ? g_panel_stream : current_stream();
+  cudaStream_t sm = g_comm ? g_main_stream : current_stream();
+  const bool two_streams = sp != sm && lookahead;
+  if (!two_streams) sm = sp;
+  cudaEvent_t ev_start;
+  FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  FB_CUDA_CHECK(cudaEventRecord(ev_start, current_stream()));
+  FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_start, 0));
+  if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
+
+  const i64 nblk = nblocks(n, nb);
+  const i64 ncols_loc = local_cols(n, nb, P, me);
+  double* W[2];
+  W[0] = (double*)ws_alloc((size_t)n * nb * 8);
+  W[1] = (double*)ws_alloc((size_t)n * nb * 8);
+  int* d_trans = (int*)ws_alloc((size_t)n * sizeof(int));
+  LuWorkspace* wp = lu_ws_create(sp, nb);
+  LuWorkspace* wm = two_streams ? lu_ws_create(sm, nb) : wp;
+  std::vector<cudaEvent_t> ev_bcast((size_t)nblk), ev_used((size_t)nblk);
+  for (i64 k = 0; k < nblk; ++k) {
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_bcast[(size_t)k], cudaEventDisableTiming));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_used[(size_t)k], cudaEventDisableTiming));
+  }
+  // number of local columns that belong to blocks with index < b
+  auto cols_before = [&](i64 b) {
+    i64 cnt = 0;
+    for (i64 q = me; q < b && q < nblk; q += P) cnt += std::min(nb, n - q * nb);
+    return cnt;
+  };
+
+  auto factor_and_bcast = [&](i64 k) {
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    const int owner = (int)(k % P);
+    double* Wk = W[k & 1];
+    if (k >= 2) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - 2)], 0));
+    if (owner == me) {
+      double* pk = A_local + local_off(k, nb, P) * ld + k0;
+      VD panel{pk, rows, kb, 1, ld};
+      lu_factor_window_f64(wp, panel, 0, kb, d_trans + k0);
+      pack(sp, Wk, pk, ld, rows, kb);
+    }
+    if (P > 1) {
+      FB_NCCL_CHECK(g_nccl.GroupStart());
+      FB_NCCL_CHECK(g_nccl.Broadcast(Wk, Wk, (size_t)rows * kb, ncclDouble, owner, g_comm, sp));
+      FB_NCCL_CHECK(g_nccl.Broadcast(d_trans + k0, d_trans + k0, (size_t)kb, ncclInt32, owner, g_comm, sp));
+      FB_NCCL_CHECK(g_nccl.GroupEnd());
+    }
+    FB_CUDA_CHECK(cudaEventRecord(ev_bcast[(size_t)k], sp));
+  };
+
+  // swaps (+ TRSM/GEMM if `right`) of step k on the local column range [c0, c1)
+  auto update_cols = [&](LuWorkspace* w, cudaStream_t st, i64 k, i64 c0, i64 c1, bool right) {
+    if (c1 <= c0) return;
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    const double* Wk = W[k & 1];
+    VD cols{A_local + c0 * ld + k0, rows, c1 - c0, 1, ld};
+    lu_apply_transpositions_f64(w, cols, d_trans + k0, kb);
+    if (right) {
+      VCD L11{Wk, kb, kb, 1, rows};
+      VD top = cols.sub(0, 0, kb, c1 - c0);
+      solve_lower_triangular_in_place_f64(st, L11, true, top);
+      if (rows > kb) {
+        VCD L21{Wk + kb, rows - kb, kb, 1, rows};
+        gemm_f64(st, cols.sub(kb, 0, rows - kb, c1 - c0), 1, L21, cv(top), -1.0);
+      }
+    }
+  };
+
+  factor_and_bcast(0);
+  for (i64 k = 0; k < nblk; ++k) {
+    const i64 kb = std::min(nb, n - k * nb);
+    if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_bcast[(size_t)k], 0));
+    const i64 left_end = cols_before(k);                               // blocks < k
+    const i64 right_begin = left_end + (((int)(k % P) == me) ? kb : 0);  // skip the panel itself on its owner
+    i64 sm_right_begin = right_begin;
+    const i64 kn = k + 1;
+    if (kn < nblk) {
+      if ((int)(kn % P) == me) {
+        const i64 cb = cols_before(kn);
+        const i64 knb = std::min(nb, n - kn * nb);
+        if (two_streams && k >= 1) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - 1)], 0));
+        update_cols(wp, sp, k, cb, cb + knb, true);
+        sm_right_begin = cb + knb;  // block k+1 is my first block to the right of k
+      }
+      factor_and_bcast(kn);
+    }
+    update_cols(wm, sm, k, 0, left_end, false);
+    update_cols(wm, sm, k, sm_right_begin, ncols_loc, true);
+    FB_CUDA_CHECK(cudaEventRecord(ev_used[(size_t)k], sm));
+  }
+  if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(nblk - 1)], 0));
+  std::vector<int> h_trans((size_t)n);
+  FB_CUDA_CHECK(cudaMemcpyAsync(h_trans.data(), d_trans, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, sp));
+  FB_CUDA_CHECK(cudaStreamSynchronize(sp));
+  if (two_streams) FB_CUDA_CHECK(cudaStreamSynchronize(sm));
+  for (i64 i = 0; i < n; ++i) {
+    const int t = h_trans[(size_t)i];
+    if (t != 0) {
+      std::swap(perm_fwd[i], perm_fwd[i + t]);
+      ++n_trans;
+    }
+  }
+  for (i64 i = 0; i < n; ++i) perm_inv[perm_fwd[i]] = i;
+  for (i64 k = 0; k < nblk; ++k) {
+    cudaEventDestroy(ev_bcast[(size_t)k]);
+    cudaEventDestroy(ev_used[(size_t)k]);
+  }
+  cudaEventDestroy(ev_start);
+  if (wm != wp) lu_ws_destroy(wm);
+  lu_ws_destroy(wp);
+  ws_free(d_trans);
+  ws_free(W[1]);
+  ws_free(W[0]);
+  return n_trans;
+}
+
 }  // namespace fb

@@ -267,6 +267,12 @@ FaerV0_24_LltStatus faer_b200_dist_llt_factor_in_place_f64(void* A_local, size_t
   return out;
 }
 
+size_t faer_b200_dist_partial_piv_lu_factor_in_place_f64(void* A_local, size_t ld, size_t n, size_t nb, long long* perm_fwd,
+                                                         long long* perm_inv, int lookahead) {
+  FB_ASSERT(n == 0 || is_device_pointer(A_local), "distributed entry points take device-resident local matrices");
+  return dist_lu_f64((double*)A_local, (i64)ld, (i64)n, (i64)nb, perm_fwd, perm_inv, lookahead);
+}
+
 const char* faer_b200_version(void) { return "faer_b200 0.1 (faer-ffi v0_23 ABI subset, sm_100a)"; }
 
 }  // extern "C"

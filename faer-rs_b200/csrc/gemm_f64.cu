@@ -239,22 +239,40 @@ __global__ void __launch_bounds__(Cfg::THREADS) gemm_f64_kernel(const GemmF64Par
   const bool c_nodiag = is_strict(cs_) || is_unit(cs_);
   const double alpha = p.alpha;
   const bool add = p.accum != 0;
+  // Two passes per half of the warp tile: (1) issue ALL dst loads of the half as independent predicated loads
+  // (a load->add->store chain per element would expose the full memory latency 2*WMI*WNI times: measured ~20 us
+  // per 64x64 tile), (2) combine and store.
+  constexpr int HALF = WMI > 1 ? WMI / 2 : 1;
 #pragma unroll
-  for (int i = 0; i < WMI; ++i) {
-    const int row = m0 + wm0 + i * 8 + g;
-    if (row >= p.m) continue;
+  for (int ih = 0; ih < WMI; ih += HALF) {
+    double cv[HALF][WNI][2];
+    bool ok[HALF][WNI][2];
 #pragma unroll
-    for (int j = 0; j < WNI; ++j) {
+    for (int ii = 0; ii < HALF; ++ii) {
+      const int row = m0 + wm0 + (ih + ii) * 8 + g;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = n0 + wn0 + j * 8 + 2 * t + e;
-        if (col >= p.n) continue;
-        if (c_low && (row < col || (row == col && c_nodiag))) continue;
-        if (c_up && (row > col || (row == col && c_nodiag))) continue;
-        double* cp = p.C + (i64)row * p.c_rs + (i64)col * p.c_cs;
-        double v = alpha * acc[i][j][e];
-        if (add) v += *cp;
-        *cp = v;
+      for (int j = 0; j < WNI; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = n0 + wn0 + j * 8 + 2 * t + e;
+          bool v = row < p.m && col < p.n;
+          if (c_low && (row < col || (row == col && c_nodiag))) v = false;
+          if (c_up && (row > col || (row == col && c_nodiag))) v = false;
+          ok[ii][j][e] = v;
+          cv[ii][j][e] = (add && v) ? p.C[(i64)row * p.c_rs + (i64)col * p.c_cs] : 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < HALF; ++ii) {
+      const int row = m0 + wm0 + (ih + ii) * 8 + g;
+#pragma unroll
+      for (int j = 0; j < WNI; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = n0 + wn0 + j * 8 + 2 * t + e;
+          if (ok[ii][j][e]) p.C[(i64)row * p.c_rs + (i64)col * p.c_cs] = alpha * acc[ih + ii][j][e] + cv[ii][j][e];
+        }
       }
     }
   }
@@ -262,13 +280,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) gemm_f64_kernel(const GemmF64Par
 
 using CfgL = TileCfg<2, 4, 8, 4, 16, 4>;   // 128 x 128 x 16, 256 threads, warp tile 64 x 32
 using CfgS = TileCfg<2, 2, 4, 4, 16, 4>;   // 64 x 64 x 16, 128 threads, warp tile 32 x 32
-using CfgL16 = TileCfg<4, 4, 4, 4, 16, 4>; // 128 x 128 x 16, 512 threads, warp tile 32 x 32
-using CfgL32 = TileCfg<2, 4, 8, 4, 32, 3>; // 128 x 128 x 32, 256 threads, 3 stages
 using CfgS3 = TileCfg<2, 2, 4, 4, 16, 3>;  // 64 x 64 x 16, 3 stages (57 KB => 3 CTAs/SM)
-using CfgS8 = TileCfg<2, 2, 4, 4, 8, 5>;   // 64 x 64 x 8, 5 stages (61 KB => 3 CTAs/SM)
-using CfgM = TileCfg<4, 2, 4, 4, 16, 3>;   // 128 x 64 x 16, 256 threads, 3 stages (92 KB => 2 CTAs/SM)
-using CfgS84 = TileCfg<2, 2, 4, 4, 8, 4>;  // 64 x 64 x 8, 4 stages (49 KB => 4 CTAs/SM)
-using CfgZ3 = TileCfg<2, 2, 4, 4, 16, 3, true>;  // 64 x 64 x 16 swizzled, 3 stages (48 KB => 4 CTAs/SM)
 using CfgZ4 = TileCfg<2, 2, 4, 4, 16, 4, true>;  // 64 x 64 x 16 swizzled, 4 stages (64 KB => 3 CTAs/SM)
 
 // development knob: FAER_B200_GEMM_CFG=1..10 forces one tile configuration (0/unset = heuristic)
@@ -310,14 +322,8 @@ void launch_layout(cudaStream_t stream, GemmF64Params& p) {
   if (is_lower(p.c_struct) || is_upper(p.c_struct)) tiles_l = tiles_l / 2 + 1;
   switch (forced_cfg()) {
     case 1: launch_cfg<CfgL, AK, BNM, VEC>(stream, p); return;
-    case 2: launch_cfg<CfgL16, AK, BNM, VEC>(stream, p); return;
-    case 3: launch_cfg<CfgL32, AK, BNM, VEC>(stream, p); return;
     case 4: launch_cfg<CfgS, AK, BNM, VEC>(stream, p); return;
     case 5: launch_cfg<CfgS3, AK, BNM, VEC>(stream, p); return;
-    case 6: launch_cfg<CfgS8, AK, BNM, VEC>(stream, p); return;
-    case 7: launch_cfg<CfgM, AK, BNM, VEC>(stream, p); return;
-    case 8: launch_cfg<CfgS84, AK, BNM, VEC>(stream, p); return;
-    case 9: launch_cfg<CfgZ3, AK, BNM, VEC>(stream, p); return;
     case 10: launch_cfg<CfgZ4, AK, BNM, VEC>(stream, p); return;
     default: break;
   }

@@ -39,6 +39,13 @@ struct PartialPivLuParams {
 size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, void* perm_inv, int idx_bytes,
                                    PartialPivLuParams params);
 
+// workspace-based LU building blocks (used by dist.cu); all work is enqueued on the stream given at creation
+struct LuWorkspace;
+LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window);
+void lu_ws_destroy(LuWorkspace* w);
+void lu_factor_window_f64(LuWorkspace* w, VD A, i64 start, i64 end, int* d_trans);
+void lu_apply_transpositions_f64(LuWorkspace* w, VD cols, const int* d_trans, i64 n);
+
 // ---- multi-GPU (dist.cu): 1-D block-column-cyclic factorizations, one process per GPU, NCCL panel broadcast ----
 int dist_unique_id(void* out128);                       // rank 0: 128-byte NCCL unique id
 int dist_init(int rank, int nranks, const void* id128);  // all ranks (collective)
@@ -48,6 +55,8 @@ int dist_rank();
 int dist_nranks();
 // A_local: column-major n x (local columns), ld >= n; block column b (width nb) lives on rank b % P.
 LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta, double reg_eps, int lookahead);
+// Distributed P A = L U (square n x n). perm_fwd / perm_inv: HOST arrays of n int64 (identical on every rank).
+size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, long long* perm_inv, int lookahead);
 
 // ---- device workspace (grow-only pool, one per process) ----
 void* ws_alloc(size_t bytes);  // 256-byte aligned device memory, cached across calls

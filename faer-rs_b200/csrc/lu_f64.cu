@@ -542,4 +542,67 @@ size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, vo
   return n_trans;
 }
 
+// ---- workspace-based entry points used by the multi-GPU driver (dist.cu) --------------------------------------
+struct LuWorkspace {
+  LuCtx ctx;
+  char* scb;
+  i64 max_window;
+};
+
+LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window) {
+  LuWorkspace* w = new LuWorkspace();
+  LuCtx& ctx = w->ctx;
+  ctx.st = stream;
+  int dev = 0;
+  FB_CUDA_CHECK(cudaGetDevice(&dev));
+  FB_CUDA_CHECK(cudaDeviceGetAttribute(&ctx.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  ctx.recursion_threshold = 16;
+  const int G = ctx.num_sms;
+  w->max_window = max_window;
+  const i64 ngroups_max = (max_window + SWAP_GROUP - 1) / SWAP_GROUP + 1;
+  ctx.d_trans = nullptr;
+  ctx.plan_rows = (int*)ws_alloc((size_t)ngroups_max * 2 * SWAP_GROUP * sizeof(int));
+  ctx.plan_src = (int*)ws_alloc((size_t)ngroups_max * 2 * SWAP_GROUP * sizeof(int));
+  ctx.plan_cnt = (int*)ws_alloc((size_t)ngroups_max * sizeof(int));
+  const size_t sc_bytes = (size_t)2 * G * 8 * 2 + (size_t)2 * G * PANEL_W * 8 + (size_t)2 * PANEL_W * 8 + 64;
+  w->scb = (char*)ws_alloc(sc_bytes);
+  char* scb = w->scb;
+  ctx.sc.cand_val = (double*)scb;
+  ctx.sc.cand_idx = (long long*)(scb + (size_t)2 * G * 8);
+  ctx.sc.cand_row = (double*)(scb + (size_t)4 * G * 8);
+  ctx.sc.diag_row = (double*)(scb + (size_t)4 * G * 8 + (size_t)2 * G * PANEL_W * 8);
+  ctx.sc.bar = (unsigned long long*)(scb + (size_t)4 * G * 8 + (size_t)2 * G * PANEL_W * 8 + (size_t)2 * PANEL_W * 8);
+  FB_CUDA_CHECK(cudaMemsetAsync(ctx.sc.bar, 0, 8, stream));
+  ctx.bar_count = 0;
+  return w;
+}
+
+void lu_ws_destroy(LuWorkspace* w) {
+  if (!w) return;
+  ws_free(w->scb);
+  ws_free(w->ctx.plan_cnt);
+  ws_free(w->ctx.plan_src);
+  ws_free(w->ctx.plan_rows);
+  delete w;
+}
+
+// Factor the window [start, end) of the view A (all rows) on the workspace's stream; relative transpositions go to
+// d_trans (device, length end-start); the view's columns outside the window receive the row swaps.
+void lu_factor_window_f64(LuWorkspace* w, VD A, i64 start, i64 end, int* d_trans) {
+  FB_ASSERT(end - start <= w->max_window, "LU window larger than the workspace was sized for");
+  lu_rec(w->ctx, A, start, end, d_trans);
+}
+
+// Apply n transpositions (device array, relative to row 0 of `cols`) to every column of `cols`.
+void lu_apply_transpositions_f64(LuWorkspace* w, VD cols, const int* d_trans, i64 n) {
+  if (cols.ncols == 0 || n == 0) return;
+  FB_ASSERT(n <= w->max_window, "too many transpositions for this workspace");
+  LuCtx& ctx = w->ctx;
+  const int ngroups = (int)((n + SWAP_GROUP - 1) / SWAP_GROUP);
+  laswp_plan_kernel<<<ngroups, 32, 0, ctx.st>>>(d_trans, (int)n, ctx.plan_rows, ctx.plan_src, ctx.plan_cnt, ngroups);
+  FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  apply_plan(ctx, cols, ngroups);
+}
+
 }  // namespace fb

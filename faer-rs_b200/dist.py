@@ -105,6 +105,9 @@ def _bind(lib) -> None:
     lib.faer_b200_dist_llt_factor_in_place_f64.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                                           capi.LltRegularization, C.c_int]
     lib.faer_b200_dist_llt_factor_in_place_f64.restype = capi.LltStatus
+    lib.faer_b200_dist_partial_piv_lu_factor_in_place_f64.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                                      C.c_void_p, C.c_void_p, C.c_int]
+    lib.faer_b200_dist_partial_piv_lu_factor_in_place_f64.restype = C.c_size_t
     _bound = True
 
 
@@ -136,3 +139,19 @@ def cholesky_in_place(A_local, n: int, nb: int = 512, regularization=(0.0, 0.0),
     except ImportError:  # pragma: no cover
         pass
     return fail, cnt
+
+
+# ---- distributed LU -----------------------------------------------------------------------------------
+def lu_in_place(A_local, n: int, nb: int = 512, lookahead: bool = True):
+    """Distributed in-place P A = L U (square n x n). Returns (perm_fwd, perm_inv, transposition_count) as numpy int64
+    arrays (identical on every rank); (P A)[i, :] = A[perm_fwd[i], :]."""
+    import torch
+    lib = capi.load()
+    _bind(lib)
+    assert capi._is_torch(A_local) and A_local.is_cuda and A_local.dtype == torch.float64
+    assert A_local.shape[0] == n and (A_local.shape[1] == 0 or A_local.stride(0) == 1)
+    ld = A_local.stride(1) if A_local.shape[1] > 1 else max(n, 1)
+    perm = np.zeros(n, dtype=np.int64); pinv = np.zeros(n, dtype=np.int64)
+    cnt = lib.faer_b200_dist_partial_piv_lu_factor_in_place_f64(A_local.data_ptr(), ld, n, nb, perm.ctypes.data,
+                                                                pinv.ctypes.data, 1 if lookahead else 0)
+    return perm, pinv, int(cnt)

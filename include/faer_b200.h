@@ -167,6 +167,10 @@ void faer_b200_dist_finalize(void);
 struct FaerV0_24_LltStatus faer_b200_dist_llt_factor_in_place_f64(void *A_local, size_t ld, size_t n, size_t nb,
                                                                   struct FaerV0_24_LltRegularization regularization,
                                                                   int lookahead);
+/* Distributed P A = L U (square). perm_fwd / perm_inv: HOST int64[n], identical on every rank. Returns the
+ * transposition count. Pivots are identical to the single-GPU entry point's. */
+size_t faer_b200_dist_partial_piv_lu_factor_in_place_f64(void *A_local, size_t ld, size_t n, size_t nb,
+                                                         long long *perm_fwd, long long *perm_inv, int lookahead);
 /* Version string. */
 const char *faer_b200_version(void);
 
