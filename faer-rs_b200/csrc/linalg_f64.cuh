@@ -7,6 +7,10 @@
 
 namespace fb {
 
+// ---- c64 matmul on the f64 DMMA kernel (gemm_c64.cu); views in COMPLEX element units ----
+void gemm_c64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, int lhs_struct, bool conj_lhs, VCD rhs,
+              int rhs_struct, bool conj_rhs, double alpha_re, double alpha_im);
+
 // ---- triangular_solve (reference: faer/src/linalg/triangular_solve.rs:220-419) ----
 void solve_lower_triangular_in_place_f64(cudaStream_t stream, VCD tril, bool unit, VD rhs);
 void solve_upper_triangular_in_place_f64(cudaStream_t stream, VCD triu, bool unit, VD rhs);

@@ -45,18 +45,44 @@ def _check_f64(*xs):
             assert x.dtype == np.float64, "f64 entry point needs float64 arrays"
 
 
-def matmul(dst, accum: int, lhs, rhs, alpha: float, par=None) -> None:
-    """dst = [dst +] alpha * lhs * rhs  (Accum.Replace never reads dst)."""
-    _check_f64(dst, lhs, rhs)
+def _is_c64(x) -> bool:
+    if capi._is_torch(x):
+        import torch
+        return x.dtype == torch.complex128
+    return x.dtype == np.complex128
+
+
+def _scalar_c64(v):
+    buf = (C.c_double * 2)(complex(v).real, complex(v).imag)
+    return C.cast(buf, C.c_void_p), buf
+
+
+def matmul(dst, accum: int, lhs, rhs, alpha, par=None) -> None:
+    """dst = [dst +] alpha * lhs * rhs  (Accum.Replace never reads dst). f64 or c64 (complex128) operands."""
     lib = capi.load()
+    if _is_c64(dst):
+        assert _is_c64(lhs) and _is_c64(rhs)
+        p, keep = _scalar_c64(alpha)
+        lib.libfaer_v0_23_matmul_c64(capi.mat_mut(dst), accum, capi.mat_ref(lhs), capi.mat_ref(rhs), p,
+                                     par or capi.par_default())
+        del keep
+        return
+    _check_f64(dst, lhs, rhs)
     lib.libfaer_v0_23_matmul_f64(capi.mat_mut(dst), accum, capi.mat_ref(lhs), capi.mat_ref(rhs),
                                  capi._scalar_f64(alpha), par or capi.par_default())
 
 
 def matmul_triangular(dst, dst_structure: int, accum: int, lhs, lhs_structure: int, rhs, rhs_structure: int,
                       alpha: float, par=None) -> None:
-    _check_f64(dst, lhs, rhs)
     lib = capi.load()
+    if _is_c64(dst):
+        assert _is_c64(lhs) and _is_c64(rhs)
+        p, keep = _scalar_c64(alpha)
+        lib.libfaer_v0_23_matmul_triangular_c64(capi.mat_mut(dst), dst_structure, accum, capi.mat_ref(lhs), lhs_structure,
+                                                capi.mat_ref(rhs), rhs_structure, p, par or capi.par_default())
+        del keep
+        return
+    _check_f64(dst, lhs, rhs)
     lib.libfaer_v0_23_matmul_triangular_f64(capi.mat_mut(dst), dst_structure, accum, capi.mat_ref(lhs), lhs_structure,
                                             capi.mat_ref(rhs), rhs_structure, capi._scalar_f64(alpha),
                                             par or capi.par_default())

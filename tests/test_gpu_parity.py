@@ -305,3 +305,46 @@ def test_lu_half_size_property(fb, cuda_dev):
     growth = max(1.0, float(torch.triu(A).abs().max()) / float(A0.abs().max()))
     assert float(r.abs().max()) <= 128 * 8 * U * n * float(A0.abs().max()) * float(x.abs().max()) * growth
     assert float(torch.tril(A, -1).abs().max()) <= 1.0  # partial pivoting bounds the multipliers
+
+
+def test_c64_matmul_vs_oracle(fb, oracle, cuda_dev):
+    """c64 matmul / triangular matmul (4M formulation on the f64 DMMA kernel) vs the oracle: shapes of the reference's
+    test_matmul, complex alpha, all dst structures; tolerance = the forward bound of appendix B on |a||b|."""
+    import itertools
+    la = fb.linalg
+    rng = np.random.default_rng(21)
+
+    def crandn(shape, order):
+        return np.array(rng.standard_normal(shape) + 1j * rng.standard_normal(shape), order=order)
+
+    for (m, n, k) in [(1, 1, 1), (2, 2, 2), (17, 17, 17), (127, 129, 65), (128, 128, 128), (16, 1, 16), (4, 4, 0), (100, 63, 9)]:
+        for layout in [("F", "F", "F"), ("C", "F", "C"), ("F", "C", "F")]:
+            for add, alpha in [(False, 1.0), (True, -1.0), (True, 0.5 - 2.0j), (False, 1.5j)]:
+                A = crandn((m, k), layout[0]); B = crandn((k, n), layout[1]); C0 = crandn((m, n), layout[2])
+                want = C0.copy(order="K")
+                if not add:
+                    want[...] = np.nan
+                oracle.matmul(want, add, A, B, alpha)
+                got = C0.copy(order="K")
+                if not add:
+                    got[...] = np.nan
+                la.matmul(got, la.Accum.Add if add else la.Accum.Replace, A, B, alpha)
+                bound = 8 * abs(alpha) * max(k, 1) * (2 * U) * (np.abs(A) @ np.abs(B)) + 8 * U * np.abs(want) + 1e-300
+                assert np.all(np.abs(got - want) <= bound), (m, n, k, layout, add, alpha)
+    # structured: a few representative combos incl. unit diagonals (real part 1, imaginary part 0)
+    for ds, ls, rs in [(0, 5, 0), (1, 0, 0), (0, 0, 6), (6, 6, 5), (2, 1, 2), (3, 4, 0)]:
+        n = 70
+        A = crandn((n, n), "F"); B = crandn((n, n), "F"); C0 = crandn((n, n), "F")
+        want = C0.copy(order="F"); oracle.matmul_triangular(want, ds, True, A, ls, B, rs, 0.5 + 1j)
+        got = C0.copy(order="F"); la.matmul_triangular(got, ds, la.Accum.Add, A, ls, B, rs, 0.5 + 1j)
+        assert np.all(np.abs(got - want) <= 1e-10 * np.maximum(1.0, np.abs(want))), (ds, ls, rs)
+    # device-resident c64, n = 1024
+    import torch
+    n = 1024
+    A = crandn((n, n), "F"); B = crandn((n, n), "F")
+    dA = torch.from_numpy(np.ascontiguousarray(A.T)).to(cuda_dev).T
+    dB = torch.from_numpy(np.ascontiguousarray(B.T)).to(cuda_dev).T
+    dC = torch.empty((n, n), dtype=torch.complex128, device=cuda_dev).T
+    la.matmul(dC, la.Accum.Replace, dA, dB, 1.0)
+    ref = A @ B
+    assert np.all(np.abs(dC.cpu().numpy() - ref) <= 8 * n * (2 * U) * (np.abs(A) @ np.abs(B)))

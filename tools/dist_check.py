@@ -73,6 +73,50 @@ for la in (1, 0):
             best = min(best, float(t.item()))
     if rank == 0:
         print(f"[dist_check] world={world} n={n} nb={nb} lookahead={la}: {best:.2f} ms  {n**3/3/best/1e9:.2f} TFLOP/s aggregate", flush=True)
+# ---- distributed LU: P A = L U on probes, permutation identical on all ranks, timing ----
+del A, loc, loc0
+torch.manual_seed(1)
+M = torch.randn((n, n), dtype=torch.float64, device=dev)
+loc0 = M[:, cols].T.contiguous().T
+loc = loc0.clone(memory_format=torch.preserve_format)
+perm, pinv, nt = lay.lu_in_place(loc, n, nb=nb)
+tperm = torch.as_tensor(perm, device=dev)
+if world > 1:
+    t0 = tperm.clone(); dist.broadcast(t0, src=0)
+    assert torch.equal(t0, tperm), "permutation differs across ranks"
+    parts = [torch.empty_like(loc) for _ in range(world)]
+    dist.all_gather(parts, loc.contiguous())
+else:
+    parts = [loc]
+if rank == 0:
+    LU = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    for r in range(world):
+        LU[:, torch.as_tensor(lay.global_col_indices(n, nb, world, r), device=dev)] = parts[r]
+    x = torch.randn((n, 4), dtype=torch.float64, device=dev)
+    Ux = torch.triu(LU) @ x
+    r_ = M[tperm, :] @ x - (torch.tril(LU, -1) @ Ux + Ux)
+    growth = max(1.0, float(torch.triu(LU).abs().max()) / float(M.abs().max()))
+    resid = float(r_.abs().max()) / (float(M.abs().max()) * n * growth)
+    print(f"[dist_check] LU world={world} n={n} nb={nb}: probe residual {resid:.3e}, max|L| {float(torch.tril(LU, -1).abs().max()):.3f}, "
+          f"transpositions {nt}", flush=True)
+    assert resid < 1e-12
+    del LU
+for la in (1, 0):
+    best = 1e30
+    for it in range(3):
+        loc.copy_(loc0)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lay.lu_in_place(loc, n, nb=nb, lookahead=bool(la))
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it > 0:
+            best = min(best, float(t.item()))
+    if rank == 0:
+        print(f"[dist_check] LU world={world} n={n} nb={nb} lookahead={la}: {best:.2f} ms  {2*n**3/3/best/1e9:.2f} TFLOP/s aggregate", flush=True)
 if world > 1:
     faer_b200.dist.finalize()
     dist.destroy_process_group()
