@@ -8,8 +8,9 @@ faer's own bench also times `copy_from_triangular_lower`, bench.rs:1531-1540) + 
 the C ABI `libfaer_v0_23_llt_factor_in_place_f64`.
   value  = n^3/3 flop per factorisation x N ranks / max-over-ranks device time   [TFLOP/s]
   e2e    = same metric through the same C-ABI call with HOST (pinned) buffers: H2D + factor + D2H inside the timed region
-N > 1: the LLT path does not shard in this round ("replicas only"): every rank factors its own matrix,
-no data-path collective; scaling = weak.
+N > 1 (torchrun, one rank per GPU): ONE matrix is factored by all N GPUs — 1-D block-column-cyclic layout, NCCL broadcast of
+each factored panel with look-ahead (csrc/dist.cu); weak scaling: n = 16384 * N^(1/3) rounded to whole blocks, so the
+per-GPU flop stays at the N=1 value; value = n^3/3 / (max-over-ranks device time).
 
 --impl reference: times the CPU restatement of the reference's algorithm (oracle/, OpenMP over all host cores; faer
 itself needs a Rust toolchain that this image does not have) on a bounded sample of the same workload.
@@ -177,19 +178,32 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+DIST_NB = 1024
+
+
+def weak_n(world: int, nb: int = DIST_NB) -> int:
+    """Weak scaling: per-GPU flop (n^3 / 3 / N) held at the N=1 value => n ~ 16384 * N^(1/3), rounded to whole blocks."""
+    if world == 1:
+        return N_DEFAULT
+    return int(round(N_DEFAULT * world ** (1.0 / 3.0) / nb)) * nb
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--n", type=int, default=0, help="matrix dimension (default: 16384 at N=1, weak-scaled for N>1)")
+    ap.add_argument("--nb", type=int, default=DIST_NB, help="block-column width of the distributed layout (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
+        if not args.n:
+            args.n = N_DEFAULT
         return run_reference_arm(args)
 
     import torch
@@ -204,23 +218,43 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    lib = faer_b200.load()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    lib = faer_b200.load()
+        faer_b200.dist.init_from_torch_distributed()
+    lay = faer_b200.dist
     stream = torch.cuda.current_stream()
     lib.faer_b200_set_stream(stream.cuda_stream)
 
-    n = args.n
-    torch.manual_seed(1234 + rank)
+    nb = args.nb
+    n = args.n or weak_n(world, nb)
+    distributed = world > 1
+
+    # ---- synthetic SPD input: A = G G^T + n I (same G on every rank); each rank keeps its block columns ----
+    torch.manual_seed(1234)
     G = torch.randn((n, n), dtype=torch.float64, device=dev)
-    A0 = torch.addmm(n * torch.eye(n, dtype=torch.float64, device=dev), G, G.T).T  # symmetric, column-major view
+    if distributed:
+        gcols = torch.as_tensor(lay.global_col_indices(n, nb, world, rank), device=dev)
+        A0 = (G @ G[gcols, :].T)  # n x local_cols (row-major storage)
+        A0[gcols, torch.arange(gcols.numel(), device=dev)] += n
+        A0 = A0.T.contiguous().T  # column-major local matrix
+    else:
+        gcols = None
+        A0 = torch.addmm(n * torch.eye(n, dtype=torch.float64, device=dev), G, G.T).T  # symmetric, column-major view
     del G
     A = A0.clone(memory_format=torch.preserve_format)
 
+    def factor():
+        if distributed:
+            fail, _ = lay.cholesky_in_place(A, n, nb=nb)
+            assert fail == -1
+        else:
+            la.cholesky_in_place(A)
+
     def step():
         A.copy_(A0)
-        la.cholesky_in_place(A)
+        factor()
 
     def barrier():
         if world > 1:
@@ -243,7 +277,6 @@ def main():
     e1.record(stream)
     barrier()
     t_wall1 = time.time()
-    launches = lib.faer_b200_launch_count() - launches0 + args.steps  # + the restore copies (torch kernels)
     my_launches = lib.faer_b200_launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop(t_wall0, t_wall1)
@@ -252,72 +285,100 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = llt_flops(n) * world / (ms_per_step * 1e-3) / 1e12
+    # one factorisation of the (global) n x n matrix per step, whatever the number of ranks
+    value = llt_flops(n) / (ms_per_step * 1e-3) / 1e12
 
-    # ---- correctness guard on the timed data (cheap probe): A0 x == L (L^T x) ----
-    L = torch.tril(A)
+    # ---- correctness guard on the timed data (cheap probe): A x == L (L^T x), reduced over the ranks ----
+    torch.manual_seed(99)
     x = torch.randn((n, 2), dtype=torch.float64, device=dev)
-    resid = float((A0 @ x - L @ (L.T @ x)).abs().max()) / (float(A0.abs().max()) * n)
-    del L
+    if distributed:
+        rows = torch.arange(n, device=dev)
+        Lloc = torch.where(rows[:, None] >= gcols[None, :], A, torch.zeros((), dtype=torch.float64, device=dev))
+        lhs = A0 @ x[gcols, :]
+        rhs = Lloc @ (Lloc.T @ x)
+        amax = A0.abs().max().reshape(1)
+        dist.all_reduce(lhs); dist.all_reduce(rhs); dist.all_reduce(amax, op=dist.ReduceOp.MAX)
+        resid = float((lhs - rhs).abs().max()) / (float(amax.item()) * n)
+        del Lloc
+    else:
+        L = torch.tril(A)
+        resid = float((A0 @ x - L @ (L.T @ x)).abs().max()) / (float(A0.abs().max()) * n)
+        del L
 
-    # ---- roofline of the dominant kernel (the DMMA GEMM doing the trailing updates) ----
+    # ---- roofline of the dominant kernel (the DMMA GEMM doing the trailing updates), rank 0's view ----
     roof = None
-    if hasattr(lib, "faer_b200_profile_begin"):
-        import ctypes as C
-        lib.faer_b200_profile_begin()
-        step()
-        torch.cuda.synchronize()
-        flops = C.c_double(0); ms = C.c_double(0); cnt = C.c_ulonglong(0)
-        lib.faer_b200_profile_end(C.byref(flops), C.byref(ms), C.byref(cnt))
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "profiles", "r01_f64_peaks.json")))
-        except Exception:
-            pass
-        peak = peaks.get("dmma_tflops_sustained", 36.9)
-        ach = flops.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else None
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json"))).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        bf16 = None
-        try:
-            bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
-        except Exception:
-            pass
-        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4 trailing updates)", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
-                "launches_per_step": int(cnt.value), "ms_in_kernel_per_step": ms.value,
-                "flops_in_kernel_per_step": flops.value,
-                "peak_source": "measured on this pool: DMMA.8x8x4 issue-bound peak, profiles/r01_f64_peaks.json "
-                               "(tcgen05 has no f64 kind; MEASURED_PEAKS.json only has bf16: "
-                               f"{bf16} TF/s sustained => frac_of_bf16 = {(ach / bf16) if (ach and bf16) else None})",
-                "how": "CUDA events around every launch of the kernel on the launching stream, one extra profiled step "
-                       "right after the timed region; achieved = sum(algorithmic flop per launch) / sum(duration)"}
+    import ctypes as C
+    lib.faer_b200_profile_begin()
+    step()
+    barrier()
+    flops = C.c_double(0); ms = C.c_double(0); cnt = C.c_ulonglong(0)
+    lib.faer_b200_profile_end(C.byref(flops), C.byref(ms), C.byref(cnt))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "profiles", "r01_f64_peaks.json")))
+    except Exception:
+        pass
+    peak = peaks.get("dmma_tflops_sustained", 36.9)
+    ach = flops.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    bf16 = None
+    try:
+        bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
+    except Exception:
+        pass
+    roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4 trailing updates)", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
+            "launches_per_step": int(cnt.value), "ms_in_kernel_per_step": ms.value,
+            "flops_in_kernel_per_step": flops.value,
+            "peak_source": "measured on this pool: DMMA.8x8x4 issue-bound peak, profiles/r01_f64_peaks.json "
+                           "(tcgen05 has no f64 kind; MEASURED_PEAKS.json only has bf16: "
+                           f"{bf16} TF/s sustained => frac_of_bf16 = {(ach / bf16) if (ach and bf16) else None})",
+            "how": "CUDA events around every launch of the kernel on the launching stream(s), one extra profiled step "
+                   "right after the timed region (rank 0); achieved = sum(algorithmic flop per launch) / sum(duration)"}
 
-    # ---- e2e: same metric through the C ABI with HOST buffers (pinned), copies inside the timed region ----
+    # ---- e2e: same metric with HOST (pinned) buffers, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        hA0 = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
-        hA0.copy_(A0.T)  # hA0 (row-major storage) == A0 column-major, A0 symmetric anyway
-        hA = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
-        hv = hA.numpy().T  # column-major view over pinned memory
+        rows_, cols_ = A0.shape
+        hA0 = torch.empty((cols_, rows_), dtype=torch.float64, pin_memory=True)  # storage of the column-major matrix
+        hA0.copy_(A0.T)
+        hA = torch.empty((cols_, rows_), dtype=torch.float64, pin_memory=True)
         reps = max(2, min(args.steps, 3))
-        hA.copy_(hA0); la.cholesky_in_place(hv)  # warm-up (pool allocation)
-        barrier()
+        bytes_h2d = rows_ * cols_ * 8
+        if distributed:
+            dA = torch.empty((cols_, rows_), dtype=torch.float64, device=dev)
+
+            def e2e_call():
+                dA.copy_(hA, non_blocking=True)            # H2D of this rank's block columns
+                fail, _ = lay.cholesky_in_place(dA.T, n, nb=nb)
+                hA.copy_(dA, non_blocking=True)            # D2H of the factor
+                torch.cuda.synchronize()
+                assert fail == -1
+            how = "faer_b200.dist.cholesky_in_place on this rank's block columns, pinned host <-> device copies timed"
+        else:
+            hv = hA.numpy().T  # column-major view over pinned memory
+
+            def e2e_call():
+                la.cholesky_in_place(hv)  # H2D + factorisation + D2H inside the C-ABI call, synchronous
+            how = "libfaer_v0_23_llt_factor_in_place_f64 on a pinned HOST matrix (wall clock around the synchronous call)"
+        hA.copy_(hA0); e2e_call()  # warm-up (pool allocation)
         ts = []
         for _ in range(reps):
             hA.copy_(hA0)
+            barrier()
             t0 = time.perf_counter()
-            la.cholesky_in_place(hv)  # H2D (2.1 GB) + factorisation + D2H (2.1 GB), synchronous
+            e2e_call()
             ts.append(time.perf_counter() - t0)
         tt = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": llt_flops(n) * world / float(tt.item()) / 1e12, "unit": UNIT,
-               "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8, "ms_per_step": 1e3 * float(tt.item()),
-               "how": "libfaer_v0_23_llt_factor_in_place_f64 on a pinned HOST matrix (wall clock around the synchronous call)"}
+        e2e = {"value": llt_flops(n) / float(tt.item()) / 1e12, "unit": UNIT,
+               "h2d_bytes_per_step": bytes_h2d * world, "d2h_bytes_per_step": bytes_h2d * world,
+               "ms_per_step": 1e3 * float(tt.item()), "how": how}
         del hA, hA0
 
     cpu = None
@@ -327,19 +388,26 @@ def main():
         proxy = lapack_proxy(min(n, 8192))
 
     if rank == 0:
+        if distributed:
+            wl = (f"f64 Cholesky LLT, ONE n={n} matrix factored by {world} GPUs (1-D block-column-cyclic, nb={nb}, NCCL panel "
+                  f"broadcast + look-ahead); weak scaling of BASELINE.json configs[1] (n=16384 at N=1): n^3/(3N) flop per GPU held "
+                  "constant; SPD = G G^T + n I; step = restore copy + factor")
+        else:
+            wl = f"f64 Cholesky LLT n={n} (BASELINE.json configs[1]); SPD = G G^T + n I; step = restore copy + factor"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"f64 Cholesky LLT n={n} (BASELINE.json configs[1]); SPD = G G^T + n I; step = restore copy + factor",
-                       "n": n, "layout": "column-major", "per_rank": "independent replica (no data-path collective)" if world > 1 else "single GPU",
-                       "l2": "inputs (2.1 GB per matrix) exceed the 126 MB L2; no flush needed",
+            "config": {"workload": wl, "n": n, "layout": "column-major",
+                       "parallelism": f"block-column-cyclic x{world}" if distributed else "single GPU",
+                       "l2": f"inputs ({A0.numel() * 8 / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no flush needed",
                        "probe_residual": resid},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(my_launches),
             "roofline": roof, "cpu_baseline": cpu, "cpu_lapack_proxy": proxy,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        faer_b200.dist.finalize()
         dist.destroy_process_group()
     return 0
 

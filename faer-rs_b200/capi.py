@@ -139,6 +139,17 @@ def load() -> C.CDLL:
             f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_{it}_f64")
             f.argtypes = [MatMut, SliceMut, SliceMut, P, MemAlloc, PartialPivLuParams]
             f.restype = PartialPivLuStatus
+    lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.argtypes = [C.c_size_t, C.c_size_t, P]
+    lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.restype = Layout
+    lib.libfaer_v0_23_llt_solve_in_place_f64.argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]
+    lib.libfaer_v0_23_llt_solve_in_place_f64.restype = None
+    for it in ("u32", "u64"):
+        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_{it}_f64")
+        f.argtypes = [C.c_size_t, C.c_size_t, P]
+        f.restype = Layout
+        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_f64")
+        f.argtypes = [MatRef, MatRef, C.c_int, SliceMut, SliceMut, MatMut, P, MemAlloc]
+        f.restype = None
     lib.libfaer_v0_23_get_global_par.argtypes = []
     lib.libfaer_v0_23_get_global_par.restype = Par
     lib.libfaer_v0_23_set_global_par.argtypes = [Par]

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <vector>
 
 using namespace fb;
 
@@ -238,6 +239,68 @@ FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f6
     FaerV0_24_PartialPivLuParams params) {
   (void)par; (void)mem;
   return lu_entry(A, perm_fwd, perm_bwd, params, 8);
+}
+
+// ---- solves on top of the factors ----
+FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
+  (void)dim; (void)rhs_ncols; (void)par;
+  return FaerV0_24_Layout{0, 1};  // reference: StackReq::EMPTY (llt/solve.rs:3-10)
+}
+void libfaer_v0_23_llt_solve_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,
+                                          FaerV0_24_MemAlloc mem) {
+  (void)A_conj; (void)par; (void)mem;
+  require_device();
+  cudaStream_t st = current_stream();
+  FB_ASSERT(L.nrows == L.ncols && rhs.nrows == L.nrows, "LLT solve shape mismatch");
+  Mat l(L, st);
+  Mat r(rhs, true, st);
+  llt_solve_in_place_f64(st, l.s.view<const double>(), r.s.view<double>());
+  finish_all(st, {&l.s, &r.s});
+}
+
+static std::vector<long long> read_perm(const void* p, size_t n, int idx_bytes) {
+  std::vector<unsigned char> raw(n * (size_t)idx_bytes);
+  if (n) {
+    if (is_device_pointer(p)) FB_CUDA_CHECK(cudaMemcpy(raw.data(), p, raw.size(), cudaMemcpyDeviceToHost));
+    else memcpy(raw.data(), p, raw.size());
+  }
+  std::vector<long long> out(n);
+  for (size_t i = 0; i < n; ++i)
+    out[i] = idx_bytes == 4 ? (long long)((const uint32_t*)raw.data())[i] : (long long)((const uint64_t*)raw.data())[i];
+  return out;
+}
+static void lu_solve_entry(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_SliceRef perm_fwd, FaerV0_24_MatMut rhs,
+                           int idx_bytes) {
+  require_device();
+  cudaStream_t st = current_stream();
+  const size_t n = L.nrows;
+  FB_ASSERT(L.ncols == n && U.nrows == n && U.ncols == n && rhs.nrows == n, "LU solve shape mismatch");
+  std::vector<long long> perm = read_perm(perm_fwd.ptr, n, idx_bytes);  // length from L.nrows (see lu_entry note)
+  for (size_t i = 0; i < n; ++i) FB_ASSERT(perm[i] >= 0 && (size_t)perm[i] < n, "invalid permutation entry");
+  Mat l(L, st), u(U, st);
+  Mat r(rhs, true, st);
+  lu_solve_in_place_f64(st, l.s.view<const double>(), u.s.view<const double>(), perm.data(), r.s.view<double>());
+  finish_all(st, {&l.s, &u.s, &r.s});
+}
+FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u32_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
+  (void)par;
+  return FaerV0_24_Layout{dim * rhs_ncols * sizeof(double), 64};  // permute_rows_in_place_scratch (perm/mod.rs)
+}
+FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u64_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
+  (void)par;
+  return FaerV0_24_Layout{dim * rhs_ncols * sizeof(double), 64};
+}
+void libfaer_v0_23_partial_piv_lu_solve_in_place_u32_f64(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj,
+                                                         FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,
+                                                         FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
+  (void)A_conj; (void)perm_bwd; (void)par; (void)mem;
+  lu_solve_entry(L, U, perm_fwd, rhs, 4);
+}
+void libfaer_v0_23_partial_piv_lu_solve_in_place_u64_f64(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj,
+                                                         FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,
+                                                         FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
+  (void)A_conj; (void)perm_bwd; (void)par; (void)mem;
+  lu_solve_entry(L, U, perm_fwd, rhs, 8);
 }
 
 // ---- global par / alloc ----

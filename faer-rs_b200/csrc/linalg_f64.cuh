@@ -43,6 +43,11 @@ struct PartialPivLuParams {
 size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, void* perm_inv, int idx_bytes,
                                    PartialPivLuParams params);
 
+// ---- solves on top of the factors (solve_f64.cu; reference llt/solve.rs:12-35, lu/partial_pivoting/solve.rs:21-54) ----
+void permute_rows_in_place_f64(cudaStream_t stream, VD rhs, const long long* perm_fwd_host);
+void llt_solve_in_place_f64(cudaStream_t stream, VCD L, VD rhs);
+void lu_solve_in_place_f64(cudaStream_t stream, VCD L, VCD U, const long long* perm_fwd_host, VD rhs);
+
 // workspace-based LU building blocks (used by dist.cu); all work is enqueued on the stream given at creation
 struct LuWorkspace;
 LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window);

@@ -150,6 +150,26 @@ def cholesky_in_place(A, regularization=(0.0, 0.0), par=None, params=None) -> Ll
     raise RuntimeError("LltStatus::Unknown")
 
 
+def llt_solve_in_place(L, rhs, conj: int = CONJ_NO, par=None) -> None:
+    """cholesky::llt::solve::solve_in_place_with_conj (llt/solve.rs:12-35): rhs <- (L L^H)^-1 rhs."""
+    _check_f64(L, rhs)
+    lib = capi.load()
+    lib.libfaer_v0_23_llt_solve_in_place_f64(capi.mat_ref(L), conj, capi.mat_mut(rhs), par or capi.par_default(),
+                                             capi.MemAlloc(None, 0))
+
+
+def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None) -> None:
+    """lu::partial_pivoting::solve::solve_in_place_with_conj (lu/partial_pivoting/solve.rs:21-54):
+    rhs <- A^-1 rhs from the packed factors (L unit-lower below the diagonal, U on/above) and the row permutation."""
+    _check_f64(LU, rhs)
+    lib = capi.load()
+    isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
+    it = {4: "u32", 8: "u64"}[isz]
+    getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_f64")(
+        capi.mat_ref(LU), capi.mat_ref(LU), conj, capi.slice_mut(perm), capi.slice_mut(perm_inv), capi.mat_mut(rhs),
+        par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
 # ---- partial-pivoting LU ---------------------------------------------------------------------------
 @dataclass
 class PartialPivLuInfo:
