@@ -100,7 +100,10 @@ def cpu_llt_sample(target_seconds: float = 15.0, n_cap: int = 8192):
     """Time the CPU restatement of faer's LLT on all host cores on a bounded sample (same generator, smaller n)."""
     from oracle import oracle as orc
     orc.load()
-    cores = orc.num_threads()
+    # The restatement keeps faer's 128-wide recursion, i.e. thousands of small OpenMP regions: beyond ~32 threads the
+    # fork/join cost dominates (measured on the GPU box: 0.0007 TFLOP/s with 128 threads vs 0.017 with 64), so cap the team.
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    orc.set_num_threads(cores)
     rng = np.random.default_rng(0)
 
     def run(n):

@@ -92,6 +92,15 @@ inline i64 local_off(i64 b, i64 nb, int P) { return (b / P) * nb; }
 
 }  // namespace
 
+// the panel (high priority) / trailing-update (low priority) stream pair, also used for single-rank look-ahead
+static void ensure_streams() {
+  if (g_panel_stream) return;
+  int lo = 0, hi = 0;
+  FB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  FB_CUDA_CHECK(cudaStreamCreateWithPriority(&g_panel_stream, cudaStreamNonBlocking, hi));
+  FB_CUDA_CHECK(cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, lo));
+}
+
 bool dist_ready() { return g_comm != nullptr; }
 int dist_rank() { return g_rank; }
 int dist_nranks() { return g_nranks; }
@@ -114,10 +123,7 @@ int dist_init(int rank, int nranks, const void* id128) {
   FB_NCCL_CHECK(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
   g_rank = rank;
   g_nranks = nranks;
-  int lo = 0, hi = 0;
-  FB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  FB_CUDA_CHECK(cudaStreamCreateWithPriority(&g_panel_stream, cudaStreamNonBlocking, hi));
-  FB_CUDA_CHECK(cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, lo));
+  ensure_streams();
   return 0;
 }
 
@@ -144,8 +150,9 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   LltResult res{true, 0, 0};
   if (n == 0) return res;
   FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
-  cudaStream_t sp = g_comm ? g_panel_stream : current_stream();
-  cudaStream_t sm = g_comm ? g_main_stream : current_stream();
+  if (lookahead) ensure_streams();
+  cudaStream_t sp = lookahead ? g_panel_stream : current_stream();
+  cudaStream_t sm = lookahead ? g_main_stream : current_stream();
   const bool two_streams = sp != sm && lookahead;
   if (!two_streams) sm = sp;
   // order after whatever the caller enqueued on the current stream
@@ -264,8 +271,9 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
   size_t n_trans = 0;
   if (n == 0) return 0;
   FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
-  cudaStream_t sp = g_comm ? g_panel_stream : current_stream();
-  cudaStream_t sm = g_comm ? g_main_stream : current_stream();
+  if (lookahead) ensure_streams();
+  cudaStream_t sp = lookahead ? g_panel_stream : current_stream();
+  cudaStream_t sm = lookahead ? g_main_stream : current_stream();
   const bool two_streams = sp != sm && lookahead;
   if (!two_streams) sm = sp;
   cudaEvent_t ev_start;

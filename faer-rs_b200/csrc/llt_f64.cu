@@ -7,21 +7,26 @@
 //     d = Re(a_jj); [regularise]; fail with Err(j) if !(d > 0); l_jj = sqrt(d); fail if l_jj == 0 or non-finite;
 //     column j (INCLUDING the diagonal entry) is multiplied by recip(l_jj).
 //
-// B200 mapping: recursive blocked driver on the host stream; the <=128-wide diagonal block is factored by ONE
-// CTA whose 1024 threads hold the block in REGISTERS (thread (lane, warp) owns rows lane+32a, columns warp+32b):
-// each column step broadcasts the unscaled pivot column through a double-buffered shared vector (one
-// __syncthreads per column) and every thread applies the reference's per-element FMA chain (same k order, same
-// reciprocal-multiply, diagonal scaled too) to its 16 entries => bit-identical to the reference leaf recurrence.
-// The panel solve is G3 and the trailing update is the lower-masked DMMA GEMM (G2). A device status word carries
-// the first failing column / the regularisation count and is read back once per factorisation.
+// B200 mapping: recursive blocked driver on the host stream; the <=128-wide diagonal block is factored by ONE CTA:
+//   * 16 "update" warps hold the block in REGISTERS (thread (lane, w) owns rows lane+32a, columns w+16b) and apply the
+//     reference's per-element FMA chain (same k order, same reciprocal-multiply, diagonal scaled too) => bit-identical
+//     to the reference leaf recurrence;
+//   * 4 "pivot" warps keep a redundant copy of the diagonal (updated with the very same FMA sequence, so bit-identical)
+//     and do the serial pivot arithmetic (regularise, test, sqrt, reciprocal) of column j+1 WHILE the update warps are
+//     still applying column j — the sqrt+divide latency is off the update warps' critical path;
+//   * each column costs one __syncthreads; the unscaled pivot column travels through a double-buffered shared vector.
+// The panel solve is G3 and the trailing update is the lower-masked DMMA GEMM (G2). A device status word carries the
+// first failing column / the regularisation count and is read back once per factorisation.
 #include "linalg_f64.cuh"
 
 namespace fb {
 
 namespace {
 
-constexpr int POTF2_THREADS = 1024;
 constexpr int POTF2_MAX = 128;
+constexpr int POTF2_UPD_WARPS = 16;
+constexpr int POTF2_THREADS = POTF2_UPD_WARPS * 32 + POTF2_MAX;  // 512 update threads + 128 pivot threads
+constexpr int POTF2_CB = POTF2_MAX / POTF2_UPD_WARPS;           // column slots per update thread (8)
 
 // info[0]: first failing global column (or -1), info[1]: regularisation count
 __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict__ A, i64 rs, i64 cs, int n, i64 j0,
@@ -32,27 +37,32 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
   __shared__ int s_fail[2];
   __shared__ int s_count;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_upd = warp < POTF2_UPD_WARPS;
+  const int p = tid - POTF2_UPD_WARPS * 32;  // pivot-thread index (diagonal entry p) when !is_upd
   if (info[0] >= 0) return;  // an earlier block already failed (uniform across the CTA)
   if (tid == 0) s_count = 0;
 
-  // thread-owned entries: rows i = lane + 32a, columns c = warp + 32b, kept iff c <= i < n
-  double a[4][4];
+  // update threads: rows i = lane + 32a, columns c = warp + 16b, kept iff c <= i < n
+  double a[4][POTF2_CB];
+  double dp = 0.0;  // pivot threads: diagonal entry p
+  if (is_upd) {
 #pragma unroll
-  for (int ai = 0; ai < 4; ++ai)
+    for (int ai = 0; ai < 4; ++ai)
 #pragma unroll
-    for (int bi = 0; bi < 4; ++bi) {
-      const int i = lane + 32 * ai, c = warp + 32 * bi;
-      a[ai][bi] = (i < n && c <= i) ? A[(i64)i * rs + (i64)c * cs] : 0.0;
-    }
-  __syncthreads();
+      for (int bi = 0; bi < POTF2_CB; ++bi) {
+        const int i = lane + 32 * ai, c = warp + POTF2_UPD_WARPS * bi;
+        a[ai][bi] = (i < n && c <= i) ? A[(i64)i * rs + (i64)c * cs] : 0.0;
+      }
+  } else if (p < n) {
+    dp = A[(i64)p * rs + (i64)p * cs];
+  }
+  __syncthreads();  // s_count initialised
 
-  // The thread that owns the diagonal entry of column jc does the (expensive, serial) pivot arithmetic ONCE:
-  // regularise, test, sqrt, reciprocal (reference ldlt/factor.rs:122-160) and publishes recip(l_jj) + a fail flag.
+  // serial pivot arithmetic of column jc (reference ldlt/factor.rs:122-160), done by ONE pivot thread
   auto publish_pivot = [&](int jc, double d) {
     int fail = 0;
     if (regularize) {
-      // LLT: sign == +1
-      if (d <= eps) {
+      if (d <= eps) {  // LLT: sign == +1
         d = delta;
         s_count += 1;  // single writer per column, ordered by the per-column barrier
       }
@@ -69,11 +79,13 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
     s_fail[jc & 1] = fail;
   };
 
-  // owners of column 0 (warp 0, b = 0) publish it
-  if (warp == 0) {
+  if (is_upd) {
+    if (warp == 0) {
 #pragma unroll
-    for (int ai = 0; ai < 4; ++ai) colbuf[0][lane + 32 * ai] = a[ai][0];
-    if (lane == 0) publish_pivot(0, a[0][0]);
+      for (int ai = 0; ai < 4; ++ai) colbuf[0][lane + 32 * ai] = a[ai][0];
+    }
+  } else if (p == 0) {
+    publish_pivot(0, dp);
   }
   __syncthreads();
 
@@ -84,53 +96,60 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
       return;
     }
     const double inv = s_inv[j & 1];
-    const int jw = j & 31;
-    // column j of L goes to global memory (owners: warp jw).
-    // NB: like the reference, the stored diagonal is (unregularised a_jj) * recip(l_jj)
-    // (ldlt/factor.rs:161-175 scales the whole column, diagonal included, and `diag` is a local copy).
-    if (warp == jw) {
-#pragma unroll
-      for (int ai = 0; ai < 4; ++ai) {
-        const int i = lane + 32 * ai;
-        if (i >= j && i < n) A[(i64)i * rs + (i64)j * cs] = col[i] * inv;
+    if (!is_upd) {
+      // pivot group: keep the diagonal current with the SAME fma the update threads apply to a_pp, then start the
+      // next column's pivot arithmetic immediately
+      if (p > j && p < n) {
+        const double l = col[p] * inv;
+        dp = fma(-l, l, dp);
+        if (p == j + 1) publish_pivot(j + 1, dp);
       }
-    }
-    // trailing update: a_ic <- fma(-l_cj, l_ij, a_ic) for j < c <= i. The column test depends only on (warp, bi, j):
-    // it is warp-uniform, so dead column slots are BRANCHED over (no predicated-off instruction issue).
-    if (warp + 96 > j) {
-      double li[4];
+    } else {
+      const int jw = j & (POTF2_UPD_WARPS - 1);
+      // column j of L goes to global memory (owners: warp jw).
+      // NB: like the reference, the stored diagonal is (unregularised a_jj) * recip(l_jj)
+      // (ldlt/factor.rs:161-175 scales the whole column, diagonal included, and `diag` is a local copy).
+      if (warp == jw) {
 #pragma unroll
-      for (int ai = 0; ai < 4; ++ai) li[ai] = col[lane + 32 * ai] * inv;
+        for (int ai = 0; ai < 4; ++ai) {
+          const int i = lane + 32 * ai;
+          if (i >= j && i < n) A[(i64)i * rs + (i64)j * cs] = col[i] * inv;
+        }
+      }
+      // trailing update: a_ic <- fma(-l_cj, l_ij, a_ic) for j < c <= i. The column test depends only on
+      // (warp, bi, j): warp-uniform, so dead column slots are BRANCHED over (no predicated-off instruction issue).
+      if (warp + POTF2_UPD_WARPS * (POTF2_CB - 1) > j) {
+        double li[4];
 #pragma unroll
-      for (int bi = 0; bi < 4; ++bi) {
-        const int c = warp + 32 * bi;
-        if (c > j && c < n) {
-          const double lc = col[c] * inv;
+        for (int ai = 0; ai < 4; ++ai) li[ai] = col[lane + 32 * ai] * inv;
 #pragma unroll
-          for (int ai = 0; ai < 4; ++ai) {
-            const int i = lane + 32 * ai;
-            if (32 * ai + 31 >= c) {  // warp-uniform: this row slot intersects i >= c
-              if (i >= c && i < n) a[ai][bi] = fma(-lc, li[ai], a[ai][bi]);
+        for (int bi = 0; bi < POTF2_CB; ++bi) {
+          const int c = warp + POTF2_UPD_WARPS * bi;
+          if (c > j && c < n) {
+            const double lc = col[c] * inv;
+#pragma unroll
+            for (int ai = 0; ai < 4; ++ai) {
+              const int i = lane + 32 * ai;
+              if (32 * ai + 31 >= c) {  // warp-uniform: this row slot intersects i >= c
+                if (i >= c && i < n) a[ai][bi] = fma(-lc, li[ai], a[ai][bi]);
+              }
             }
           }
         }
       }
-    }
-    // owners of column j+1 publish it (unscaled) into the other buffer
-    if (j + 1 < n && warp == ((j + 1) & 31)) {
-      const int nb = (j + 1) >> 5;
-      double* nxt = colbuf[(j + 1) & 1];
-      double diag = 0.0;
+      // owners of column j+1 publish it (unscaled) into the other buffer
+      if (j + 1 < n && warp == ((j + 1) & (POTF2_UPD_WARPS - 1))) {
+        const int nbk = (j + 1) / POTF2_UPD_WARPS;
+        double* nxt = colbuf[(j + 1) & 1];
 #pragma unroll
-      for (int ai = 0; ai < 4; ++ai) {
-        double v = 0.0;
+        for (int ai = 0; ai < 4; ++ai) {
+          double v = 0.0;
 #pragma unroll
-        for (int bi = 0; bi < 4; ++bi)
-          if (bi == nb) v = a[ai][bi];
-        nxt[lane + 32 * ai] = v;
-        if (ai == nb) diag = v;
+          for (int bi = 0; bi < POTF2_CB; ++bi)
+            if (bi == nbk) v = a[ai][bi];
+          nxt[lane + 32 * ai] = v;
+        }
       }
-      if (lane == ((j + 1) & 31)) publish_pivot(j + 1, diag);
     }
     __syncthreads();
   }

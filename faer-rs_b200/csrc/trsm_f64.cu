@@ -197,7 +197,9 @@ void solve_lower_rec(cudaStream_t stream, VCD T, bool unit, VD rhs) {
     note_launch();
     return;
   }
-  if (n <= LEAF2) {
+  // The fused 65..128 leaf is kept for reference but disabled: its 8128 dependent FMAs per thread measured 71 us per
+  // launch (profiles/r01_llt16384_launches_v3.txt) against ~38 us for two 64-leaves + one small DMMA GEMM.
+  if (false && n <= LEAF2) {
     static bool configured = false;
     if (!configured) {
       FB_CUDA_CHECK(cudaFuncSetAttribute(trsm_leaf128_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
