@@ -113,6 +113,11 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_matmul_triangular_f64.argtypes = [MatMut, C.c_int, C.c_int, MatRef, C.c_int, MatRef, C.c_int,
                                                         C.c_void_p, P]
     lib.libfaer_v0_23_matmul_triangular_f64.restype = None
+    lib.libfaer_v0_23_matmul_f32.argtypes = [MatMut, C.c_int, MatRef, MatRef, C.c_void_p, P]
+    lib.libfaer_v0_23_matmul_f32.restype = None
+    lib.libfaer_v0_23_matmul_triangular_f32.argtypes = [MatMut, C.c_int, C.c_int, MatRef, C.c_int, MatRef, C.c_int,
+                                                        C.c_void_p, P]
+    lib.libfaer_v0_23_matmul_triangular_f32.restype = None
     lib.libfaer_v0_23_matmul_c64.argtypes = [MatMut, C.c_int, MatRef, MatRef, C.c_void_p, P]
     lib.libfaer_v0_23_matmul_c64.restype = None
     lib.libfaer_v0_23_matmul_triangular_c64.argtypes = [MatMut, C.c_int, C.c_int, MatRef, C.c_int, MatRef, C.c_int,

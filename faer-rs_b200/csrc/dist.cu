@@ -101,6 +101,25 @@ static void ensure_streams() {
   FB_CUDA_CHECK(cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, lo));
 }
 
+i64 lookahead_min_n() {
+  static i64 v = -1;
+  if (v < 0) {
+    const char* e = getenv("FAER_B200_LOOKAHEAD_MIN_N");
+    v = e ? atoll(e) : 4096;
+    if (v == 0) v = (i64)1 << 62;
+  }
+  return v;
+}
+i64 lookahead_block() {
+  static i64 v = -1;
+  if (v < 0) {
+    const char* e = getenv("FAER_B200_NB");
+    v = e ? atoll(e) : 1024;
+    if (v < 2 || (v & 1)) v = 1024;
+  }
+  return v;
+}
+
 bool dist_ready() { return g_comm != nullptr; }
 int dist_rank() { return g_rank; }
 int dist_nranks() { return g_nranks; }
@@ -146,7 +165,10 @@ void dist_finalize() {
 // -----------------------------------------------------------------------------------------------------------------
 LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta, double reg_eps, int lookahead) {
   require_device();
-  const int P = g_comm ? g_nranks : 1, me = g_comm ? g_rank : 0;
+  // `lookahead` bit 0: two-stream look-ahead; bit 1: purely local run (ignore the communicator even if one exists)
+  const bool local_only = (lookahead & 2) != 0;
+  lookahead &= 1;
+  const int P = (g_comm && !local_only) ? g_nranks : 1, me = (g_comm && !local_only) ? g_rank : 0;
   LltResult res{true, 0, 0};
   if (n == 0) return res;
   FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
@@ -266,7 +288,10 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
 // -----------------------------------------------------------------------------------------------------------------
 size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, long long* perm_inv, int lookahead) {
   require_device();
-  const int P = g_comm ? g_nranks : 1, me = g_comm ? g_rank : 0;
+  // `lookahead` bit 0: two-stream look-ahead; bit 1: purely local run (ignore the communicator even if one exists)
+  const bool local_only = (lookahead & 2) != 0;
+  lookahead &= 1;
+  const int P = (g_comm && !local_only) ? g_nranks : 1, me = (g_comm && !local_only) ? g_rank : 0;
   for (i64 i = 0; i < n; ++i) perm_fwd[i] = i;
   size_t n_trans = 0;
   if (n == 0) return 0;

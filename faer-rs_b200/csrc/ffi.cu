@@ -3,6 +3,7 @@
 // header): same argument order and meaning, by-value PODs, synchronous on return, abort() on precondition
 // violations. Host buffers are staged; device buffers are used in place.
 #include "../../include/faer_b200.h"
+#include "gemm_f32.cuh"
 #include "runtime.cuh"
 
 #include <atomic>
@@ -88,6 +89,36 @@ void libfaer_v0_23_matmul_triangular_f64(FaerV0_24_MatMut C, FaerV0_24_Block C_b
   gemm_f64(st, c.s.view<double>(), (int)C_block, accum == FaerV0_24_Accum_Add ? 1 : 0, lhs.s.view<const double>(),
            (int)A_block, rhs.s.view<const double>(), (int)B_block, a);
   finish_all(st, {&c.s, &lhs.s, &rhs.s});
+}
+
+// ---- f32 matmul (3xTF32 tensor-core kernel) ----
+static void matmul_f32_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum accum, FaerV0_24_MatRef A, int A_block,
+                            FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha) {
+  require_device();
+  FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
+  cudaStream_t st = current_stream();
+  FB_ASSERT(alpha != nullptr, "null scalar pointer");
+  float a;
+  if (is_device_pointer(alpha)) FB_CUDA_CHECK(cudaMemcpy(&a, alpha, 4, cudaMemcpyDeviceToHost));
+  else memcpy(&a, alpha, 4);
+  const bool copy_in = accum == FaerV0_24_Accum_Add || C_block != FaerV0_24_Block_Rectangular;
+  StagedMat c(C.ptr, (i64)C.nrows, (i64)C.ncols, (i64)C.row_stride, (i64)C.col_stride, 4, copy_in, true, st);
+  StagedMat l(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 4, true, false, st);
+  StagedMat r(B.ptr, (i64)B.nrows, (i64)B.ncols, (i64)B.row_stride, (i64)B.col_stride, 4, true, false, st);
+  gemm_f32(st, c.view<float>(), C_block, accum == FaerV0_24_Accum_Add ? 1 : 0, l.view<const float>(), A_block,
+           r.view<const float>(), B_block, a);
+  finish_all(st, {&c, &l, &r});
+}
+void libfaer_v0_23_matmul_f32(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
+                              const FaerV0_24_Scalar* alpha, FaerV0_24_Par par) {
+  (void)par;
+  matmul_f32_impl(C, 0, accum, A, 0, B, 0, alpha);
+}
+void libfaer_v0_23_matmul_triangular_f32(FaerV0_24_MatMut C, FaerV0_24_Block C_block, FaerV0_24_Accum accum,
+                                         FaerV0_24_MatRef A, FaerV0_24_Block A_block, FaerV0_24_MatRef B,
+                                         FaerV0_24_Block B_block, const FaerV0_24_Scalar* alpha, FaerV0_24_Par par) {
+  (void)par;
+  matmul_f32_impl(C, (int)C_block, accum, A, (int)A_block, B, (int)B_block, alpha);
 }
 
 // ---- c64 matmul (interleaved complex<f64>; `alpha` points to a complex scalar) ----

@@ -1,0 +1,28 @@
+// f32 GEMM / structured GEMM (3xTF32 on the tensor pipe), see gemm_f32.cu.
+#pragma once
+#include "common.cuh"
+
+namespace fb {
+
+typedef View<float> VF;
+typedef View<const float> VCF;
+inline VCF cv(const VF& v) { return VCF{v.ptr, v.nrows, v.ncols, v.rs, v.cs}; }
+
+struct GemmF32Params {
+  int m, n, k;
+  const float* A; i64 a_rs, a_cs; int a_struct;
+  const float* B; i64 b_rs, b_cs; int b_struct;
+  float* C;       i64 c_rs, c_cs; int c_struct;
+  float alpha;
+  int accum;
+  int tiles_m, tiles_n;
+};
+
+// dst(struct) = [dst +] alpha * lhs(struct) * rhs(struct); device views, element strides of any sign.
+void gemm_f32(cudaStream_t stream, VF dst, int dst_struct, int accum, VCF lhs, int lhs_struct, VCF rhs, int rhs_struct,
+              float alpha);
+inline void gemm_f32(cudaStream_t stream, VF dst, int accum, VCF lhs, VCF rhs, float alpha) {
+  gemm_f32(stream, dst, RECT, accum, lhs, RECT, rhs, RECT, alpha);
+}
+
+}  // namespace fb

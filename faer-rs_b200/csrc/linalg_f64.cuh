@@ -67,6 +67,11 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
 // Distributed P A = L U (square n x n). perm_fwd / perm_inv: HOST arrays of n int64 (identical on every rank).
 size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, long long* perm_inv, int lookahead);
 
+// single-GPU entry points switch to the look-ahead block-column driver above this size (env FAER_B200_LOOKAHEAD_MIN_N,
+// default 4096; 0 disables) with this block width (env FAER_B200_NB, default 1024)
+i64 lookahead_min_n();
+i64 lookahead_block();
+
 // ---- device workspace (grow-only pool, one per process) ----
 void* ws_alloc(size_t bytes);  // 256-byte aligned device memory, cached across calls
 void ws_free(void* p);

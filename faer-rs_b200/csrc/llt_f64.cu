@@ -207,6 +207,12 @@ LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta,
   const i64 n = A.nrows;
   LltResult res{true, 0, 0};
   if (n == 0) return res;
+  // Large column-major problems: right-looking block-column driver with two-stream look-ahead (dist.cu run on a
+  // single rank): the panel chain (potf2 + solves of block column k+1) overlaps the trailing update of step k.
+  // Measured on B200 at n = 16384: 67.5 ms vs 80.8 ms for the purely recursive driver (profiles/r01_lookahead_p1.log).
+  if (A.rs == 1 && n >= lookahead_min_n()) {
+    return dist_llt_f64(A.ptr, A.cs, n, lookahead_block(), reg_delta, reg_eps, /*lookahead | local*/ 3);
+  }
   const int regularize = (reg_delta > 0.0 && reg_eps > 0.0) ? 1 : 0;
   i64 nb = (i64)params.block_size;
   if (nb <= 0 || nb > POTF2_MAX) nb = POTF2_MAX;

@@ -57,9 +57,22 @@ def _scalar_c64(v):
     return C.cast(buf, C.c_void_p), buf
 
 
+def _is_f32(x) -> bool:
+    if capi._is_torch(x):
+        import torch
+        return x.dtype == torch.float32
+    return x.dtype == np.float32
+
+
 def matmul(dst, accum: int, lhs, rhs, alpha, par=None) -> None:
-    """dst = [dst +] alpha * lhs * rhs  (Accum.Replace never reads dst). f64 or c64 (complex128) operands."""
+    """dst = [dst +] alpha * lhs * rhs  (Accum.Replace never reads dst). f64, f32 or c64 (complex128) operands."""
     lib = capi.load()
+    if _is_f32(dst):
+        assert _is_f32(lhs) and _is_f32(rhs)
+        a = C.c_float(float(alpha))
+        lib.libfaer_v0_23_matmul_f32(capi.mat_mut(dst), accum, capi.mat_ref(lhs), capi.mat_ref(rhs), C.byref(a),
+                                     par or capi.par_default())
+        return
     if _is_c64(dst):
         assert _is_c64(lhs) and _is_c64(rhs)
         p, keep = _scalar_c64(alpha)
@@ -75,6 +88,12 @@ def matmul(dst, accum: int, lhs, rhs, alpha, par=None) -> None:
 def matmul_triangular(dst, dst_structure: int, accum: int, lhs, lhs_structure: int, rhs, rhs_structure: int,
                       alpha: float, par=None) -> None:
     lib = capi.load()
+    if _is_f32(dst):
+        assert _is_f32(lhs) and _is_f32(rhs)
+        a = C.c_float(float(alpha))
+        lib.libfaer_v0_23_matmul_triangular_f32(capi.mat_mut(dst), dst_structure, accum, capi.mat_ref(lhs), lhs_structure,
+                                                capi.mat_ref(rhs), rhs_structure, C.byref(a), par or capi.par_default())
+        return
     if _is_c64(dst):
         assert _is_c64(lhs) and _is_c64(rhs)
         p, keep = _scalar_c64(alpha)

@@ -1,0 +1,68 @@
+"""GPU parity tests for the f32 path (3xTF32 error-compensated tensor-core GEMM) against the oracle (f32 schoolbook).
+
+Tolerance: the reference's own matmul test uses abs 1e-3 on 32-bit inputs (matmul/mod.rs:2015-2016); we use the much
+tighter forward bound  |dC| <= 4 k u32 sum|a||b|  (u32 = 2^-24) — i.e. the compensated product must be as accurate as an
+fp32 FMA chain, NOT merely tf32-accurate (a plain tf32 product would violate this bound by ~2^10).
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+U32 = 2.0 ** -24
+SHAPES = [(2, 2, 2), (8, 8, 8), (16, 16, 16), (127, 127, 127), (128, 128, 128), (129, 129, 129), (15, 15, 15), (17, 17, 17),
+          (1, 1, 1), (1, 16, 16), (16, 1, 16), (16, 16, 1), (0, 4, 4), (4, 4, 0), (63, 9, 100), (100, 63, 9), (300, 520, 260)]
+
+
+def test_f32_matmul_vs_oracle(fb, oracle, cuda_dev):
+    import torch
+    la = fb.linalg
+    rng = np.random.default_rng(41)
+    for (m, n, k) in SHAPES:
+        for layout in itertools.product("CF", repeat=3):
+            for add, alpha in [(False, 1.0), (True, -1.0), (True, 0.5)]:
+                A = np.array(rng.standard_normal((m, k)), dtype=np.float32, order=layout[0])
+                B = np.array(rng.standard_normal((k, n)), dtype=np.float32, order=layout[1])
+                C0 = np.array(rng.standard_normal((m, n)), dtype=np.float32, order=layout[2])
+                want = C0.copy(order="K")
+                if not add:
+                    want[...] = np.nan
+                oracle.matmul(want, add, A, B, alpha)
+                exact = (alpha * (A.astype(np.float64) @ B.astype(np.float64)) + (C0 if add else 0)).astype(np.float64)
+                bound = 4 * max(k, 1) * U32 * abs(alpha) * (np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)) \
+                    + 4 * U32 * np.abs(exact) + 1e-30
+                got = C0.copy(order="K")
+                if not add:
+                    got[...] = np.nan
+                la.matmul(got, la.Accum.Add if add else la.Accum.Replace, A, B, alpha)
+                assert np.all(np.abs(got.astype(np.float64) - exact) <= bound), (m, n, k, layout, add)
+                assert np.all(np.abs(want.astype(np.float64) - exact) <= bound)  # the oracle obeys the same bound
+    # device resident, n = 2048: accuracy must be fp32-class, far better than plain tf32
+    n = 2048
+    A = rng.standard_normal((n, n)).astype(np.float32); B = rng.standard_normal((n, n)).astype(np.float32)
+    dA = torch.from_numpy(A).to(cuda_dev); dB = torch.from_numpy(B).to(cuda_dev)
+    dC = torch.empty((n, n), dtype=torch.float32, device=cuda_dev)
+    la.matmul(dC, la.Accum.Replace, dA, dB, 1.0)
+    exact = A.astype(np.float64) @ B.astype(np.float64)
+    err = np.abs(dC.cpu().numpy().astype(np.float64) - exact)
+    assert np.all(err <= 4 * n * U32 * (np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)))
+    assert err.max() / np.abs(exact).max() < 2e-6
+
+
+def test_f32_triangular_structures(fb, oracle):
+    la = fb.linalg
+    rng = np.random.default_rng(42)
+    for ds, ls, rs in [(0, 5, 0), (1, 0, 0), (0, 0, 6), (6, 6, 5), (2, 1, 2), (3, 4, 0), (5, 0, 0), (0, 2, 1)]:
+        n = 150
+        A = np.asfortranarray(rng.standard_normal((n, n)).astype(np.float32))
+        B = np.asfortranarray(rng.standard_normal((n, n)).astype(np.float32))
+        C0 = np.asfortranarray(rng.standard_normal((n, n)).astype(np.float32))
+        want = C0.copy(order="F"); oracle.matmul_triangular(want, ds, True, A, ls, B, rs, 0.5)
+        got = C0.copy(order="F"); la.matmul_triangular(got, ds, la.Accum.Add, A, ls, B, rs, 0.5)
+        assert np.all(np.abs(got - want) <= 1e-4 * np.maximum(1.0, np.abs(want))), (ds, ls, rs)
+        if ds:
+            sel = np.tril(np.ones((n, n), bool)) if ds in (1, 3, 5) else np.triu(np.ones((n, n), bool))
+            if ds >= 3:
+                np.fill_diagonal(sel, False)
+            assert np.array_equal(got[~sel], C0[~sel])
