@@ -114,8 +114,8 @@ i64 lookahead_block() {
   static i64 v = -1;
   if (v < 0) {
     const char* e = getenv("FAER_B200_NB");
-    v = e ? atoll(e) : 1024;
-    if (v < 2 || (v & 1)) v = 1024;
+    v = e ? atoll(e) : 0;  // 0 = caller's measured default (LLT 1024; LU 512 up to n = 20000, then 1024)
+    if (v < 0 || (v & 1)) v = 0;
   }
   return v;
 }

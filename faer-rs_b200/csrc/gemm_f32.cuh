@@ -25,4 +25,8 @@ inline void gemm_f32(cudaStream_t stream, VF dst, int accum, VCF lhs, VCF rhs, f
   gemm_f32(stream, dst, RECT, accum, lhs, RECT, rhs, RECT, alpha);
 }
 
+// f32 triangular solves (trsm.cu; same algorithm as the f64 ones)
+void solve_lower_triangular_in_place_f32(cudaStream_t stream, VCF tril, bool unit, VF rhs);
+void solve_upper_triangular_in_place_f32(cudaStream_t stream, VCF triu, bool unit, VF rhs);
+
 }  // namespace fb

@@ -171,6 +171,13 @@ __global__ void __launch_bounds__(Cfg::THREADS) gemm_f64_kernel(const GemmF64Par
   if (is_upper(p.a_struct)) k_begin = max(k_begin, m0);
   if (is_lower(p.b_struct)) k_begin = max(k_begin, n0);
   if (is_upper(p.b_struct)) k_end = min(k_end, n0 + BN);
+  double* __restrict__ Cout = p.C;
+  if (p.k_split_len > 0) {
+    const int kb = (int)blockIdx.y * p.k_split_len;
+    k_begin = max(k_begin, kb);
+    k_end = min(k_end, kb + p.k_split_len);
+    Cout += (i64)blockIdx.y * p.c_split_stride;
+  }
   k_begin = (k_begin / BK) * BK;
   const int nkt = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
 
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) gemm_f64_kernel(const GemmF64Par
           if (c_low && (row < col || (row == col && c_nodiag))) v = false;
           if (c_up && (row > col || (row == col && c_nodiag))) v = false;
           ok[ii][j][e] = v;
-          cv[ii][j][e] = (add && v) ? p.C[(i64)row * p.c_rs + (i64)col * p.c_cs] : 0.0;
+          cv[ii][j][e] = (add && v) ? Cout[(i64)row * p.c_rs + (i64)col * p.c_cs] : 0.0;
         }
       }
     }
@@ -271,7 +278,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) gemm_f64_kernel(const GemmF64Par
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = n0 + wn0 + j * 8 + 2 * t + e;
-          if (ok[ii][j][e]) p.C[(i64)row * p.c_rs + (i64)col * p.c_cs] = alpha * acc[ih + ii][j][e] + cv[ii][j][e];
+          if (ok[ii][j][e]) Cout[(i64)row * p.c_rs + (i64)col * p.c_cs] = alpha * acc[ih + ii][j][e] + cv[ii][j][e];
         }
       }
     }
@@ -311,7 +318,8 @@ void launch_cfg(cudaStream_t stream, GemmF64Params& p) {
     configured = true;
   }
   long long tiles = (long long)p.tiles_m * p.tiles_n;
-  gemm_f64_kernel<Cfg, AK, BNM, VEC><<<(unsigned)tiles, Cfg::THREADS, smem, stream>>>(p);
+  const unsigned splits = p.k_split_len > 0 ? (unsigned)((p.k + p.k_split_len - 1) / p.k_split_len) : 1u;
+  gemm_f64_kernel<Cfg, AK, BNM, VEC><<<dim3((unsigned)tiles, splits), Cfg::THREADS, smem, stream>>>(p);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
 }
@@ -347,6 +355,21 @@ inline int transpose_struct(int s) {
 
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+// dst(struct) = [dst +] alpha * sum_z W_z  (W_z: compact column-major m x n partial products, summed in z order)
+__global__ void splitk_reduce_kernel(double* __restrict__ C, i64 rs, i64 cs, int m, int n, int c_struct, int accum,
+                                     double alpha, const double* __restrict__ W, int splits) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)m * n) return;
+  const int row = (int)(e % m), col = (int)(e / m);
+  const bool nodiag = is_strict(c_struct) || is_unit(c_struct);
+  if (is_lower(c_struct) && (row < col || (row == col && nodiag))) return;
+  if (is_upper(c_struct) && (row > col || (row == col && nodiag))) return;
+  double s = 0.0;
+  for (int z = 0; z < splits; ++z) s += W[(long long)z * m * n + e];
+  double* cp = C + (i64)row * rs + (i64)col * cs;
+  *cp = accum ? (*cp + alpha * s) : alpha * s;
+}
+
 }  // namespace
 
 void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, int lhs_struct, VCD rhs, int rhs_struct,
@@ -375,6 +398,30 @@ void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, i
   p.B = rhs.ptr; p.b_rs = rhs.rs; p.b_cs = rhs.cs; p.b_struct = rhs_struct;
   p.C = dst.ptr; p.c_rs = dst.rs; p.c_cs = dst.cs; p.c_struct = dst_struct;
   p.alpha = alpha; p.accum = accum;
+  p.k_split_len = 0; p.c_split_stride = 0;
+
+  // split-K for tall-skinny products (few output tiles, long contraction): partial products go to workspace slices,
+  // then one deterministic reduce pass applies alpha / accum / the dst structure mask.
+  double* split_ws = nullptr;
+  int splits = 1;
+  {
+    const long long tiles = (long long)((p.m + 63) / 64) * ((p.n + 63) / 64);
+    if (tiles < 148 && p.k >= 4096 && lhs_struct == RECT && rhs_struct == RECT) {
+      splits = (int)std::min<long long>((148 * 3 + tiles - 1) / tiles, p.k / 1024);
+      if (splits >= 2) {
+        int len = (p.k + splits - 1) / splits;
+        len = (len + 63) / 64 * 64;
+        splits = (p.k + len - 1) / len;
+        split_ws = (double*)ws_alloc((size_t)splits * p.m * p.n * sizeof(double));
+        p.k_split_len = len;
+        p.c_split_stride = (i64)p.m * p.n;
+        p.C = split_ws; p.c_rs = 1; p.c_cs = p.m; p.c_struct = RECT;
+        p.alpha = 1.0; p.accum = 0;
+      } else {
+        splits = 1;
+      }
+    }
+  }
 
   // operand layouts
   bool a_unit_m = (lhs.rs == 1) || lhs.nrows == 1;
@@ -400,17 +447,30 @@ void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, i
     if (prof) profile_record_start(stream);                         \
     launch_layout<ak, bnm, vec>(stream, p);                         \
     if (prof) profile_record_stop(stream, flops);                   \
-    return;                                                         \
+    launched = true;                                                \
   }
+  bool launched = false;
   FB_DISPATCH(false, false, true)
-  FB_DISPATCH(false, true, true)
-  FB_DISPATCH(true, false, true)
-  FB_DISPATCH(true, true, true)
-  FB_DISPATCH(false, false, false)
-  FB_DISPATCH(false, true, false)
-  FB_DISPATCH(true, false, false)
-  FB_DISPATCH(true, true, false)
+  else FB_DISPATCH(false, true, true)
+  else FB_DISPATCH(true, false, true)
+  else FB_DISPATCH(true, true, true)
+  else FB_DISPATCH(false, false, false)
+  else FB_DISPATCH(false, true, false)
+  else FB_DISPATCH(true, false, false)
+  else FB_DISPATCH(true, true, false)
 #undef FB_DISPATCH
+  FB_ASSERT(launched, "no GEMM variant matched");
+  if (split_ws) {
+    const long long total = (long long)dst.nrows * dst.ncols;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dst.ptr, dst.rs, dst.cs, (int)dst.nrows,
+                                                                             (int)dst.ncols, dst_struct, accum, alpha,
+                                                                             split_ws, splits);
+    FB_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    // the pool is stream-agnostic: hand the slices back only once the reduce has consumed them
+    FB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    ws_free(split_ws);
+  }
 }
 
 }  // namespace fb

@@ -24,6 +24,10 @@ struct GemmF64Params {
   double alpha;
   int accum;  // 0 = Replace, 1 = Add
   int tiles_m, tiles_n;
+  // split-K (tall-skinny products, e.g. V^H V with k = 65536): blockIdx.y = z handles k in [z*len, (z+1)*len) and
+  // writes its partial product to C + z * c_split_stride; a reduce kernel combines the slices deterministically.
+  int k_split_len;       // 0 = no split; otherwise a multiple of the k-tile
+  i64 c_split_stride;    // elements between consecutive partial slices
 };
 
 // Launch on `stream`. All pointers are device pointers. Views use element strides of any sign.

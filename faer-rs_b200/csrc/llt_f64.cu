@@ -211,7 +211,10 @@ LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta,
   // single rank): the panel chain (potf2 + solves of block column k+1) overlaps the trailing update of step k.
   // Measured on B200 at n = 16384: 67.5 ms vs 80.8 ms for the purely recursive driver (profiles/r01_lookahead_p1.log).
   if (A.rs == 1 && n >= lookahead_min_n()) {
-    return dist_llt_f64(A.ptr, A.cs, n, lookahead_block(), reg_delta, reg_eps, /*lookahead | local*/ 3);
+    // block width: measured sweep at n = 16384 (profiles/r01_nb_sweep.log): 512 -> 76.7 ms, 768 -> 72.2, 1024 -> 67.3,
+    // 1536 -> 72.4, 2048 -> 72.7
+    const i64 nbl = lookahead_block() ? lookahead_block() : 1024;
+    return dist_llt_f64(A.ptr, A.cs, n, nbl, reg_delta, reg_eps, /*lookahead | local*/ 3);
   }
   const int regularize = (reg_delta > 0.0 && reg_eps > 0.0) ? 1 : 0;
   i64 nb = (i64)params.block_size;

@@ -473,7 +473,10 @@ size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, vo
   // single rank; same panel kernel => same pivots). Measured at n = 32768: 966 ms vs 1074 ms for the recursive driver.
   const bool use_lookahead = m == n && A.rs == 1 && n >= lookahead_min_n();
   if (use_lookahead) {
-    n_trans = dist_lu_f64(A.ptr, A.cs, n, lookahead_block(), perm.data(), pinv.data(), /*lookahead | local*/ 3);
+    // block width: measured (profiles/r01_nb_sweep.log) n = 16384: 512 -> 192 ms, 1024 -> 199, 2048 -> 211;
+    // n = 32768: 1024 -> 963 ms, 2048 -> 967
+    const i64 nbl = lookahead_block() ? lookahead_block() : (n <= 20000 ? 512 : 1024);
+    n_trans = dist_lu_f64(A.ptr, A.cs, n, nbl, perm.data(), pinv.data(), /*lookahead | local*/ 3);
   } else if (size > 0) {
     LuCtx ctx;
     ctx.st = stream;

@@ -31,7 +31,7 @@ def test_f32_matmul_vs_oracle(fb, oracle, cuda_dev):
                 oracle.matmul(want, add, A, B, alpha)
                 exact = (alpha * (A.astype(np.float64) @ B.astype(np.float64)) + (C0 if add else 0)).astype(np.float64)
                 bound = 4 * max(k, 1) * U32 * abs(alpha) * (np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)) \
-                    + 4 * U32 * np.abs(exact) + 1e-30
+                    + 4 * U32 * np.abs(exact) + (4 * U32 * np.abs(C0).astype(np.float64) if add else 0.0) + 1e-30
                 got = C0.copy(order="K")
                 if not add:
                     got[...] = np.nan
