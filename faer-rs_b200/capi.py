@@ -144,6 +144,25 @@ def load() -> C.CDLL:
             f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_{it}_f64")
             f.argtypes = [MatMut, SliceMut, SliceMut, P, MemAlloc, PartialPivLuParams]
             f.restype = PartialPivLuStatus
+    for suf in ("f64", "f32"):
+        getattr(lib, f"libfaer_v0_23_QrParams_{suf}").argtypes = []
+        getattr(lib, f"libfaer_v0_23_QrParams_{suf}").restype = QrParams
+        f = getattr(lib, f"libfaer_v0_23_qr_recommended_block_size_{suf}")
+        f.argtypes = [C.c_size_t, C.c_size_t]
+        f.restype = C.c_size_t
+        f = getattr(lib, f"libfaer_v0_23_qr_factor_in_place_scratch_{suf}")
+        f.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, P, QrParams]
+        f.restype = Layout
+        f = getattr(lib, f"libfaer_v0_23_qr_factor_in_place_{suf}")
+        f.argtypes = [MatMut, MatMut, P, MemAlloc, QrParams]
+        f.restype = QrStatus
+        for name in ("apply_householder_on_the_left", "apply_householder_transpose_on_the_left"):
+            f = getattr(lib, f"libfaer_v0_23_{name}_scratch_{suf}")
+            f.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t]
+            f.restype = Layout
+            f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
+            f.argtypes = [MatRef, MatRef, C.c_int, MatMut, P, MemAlloc]
+            f.restype = None
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.argtypes = [C.c_size_t, C.c_size_t, P]
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.restype = Layout
     lib.libfaer_v0_23_llt_solve_in_place_f64.argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]

@@ -5,6 +5,7 @@
 #include "../../include/faer_b200.h"
 #include "gemm_f32.cuh"
 #include "runtime.cuh"
+#include "tensor_ops.cuh"
 
 #include <atomic>
 #include <cstring>
@@ -57,6 +58,39 @@ void solve_tri(FaerV0_24_MatRef T, FaerV0_24_MatMut rhs, bool lower, bool unit) 
   finish_all(st, {&t.s, &r.s});
 }
 
+// ---- Householder QR (no pivoting) + block-Householder sequence application, f64 and f32 ----
+template <class T>
+FaerV0_24_QrStatus qr_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Q) {
+  require_device();
+  cudaStream_t st = current_stream();
+  const size_t size = A.nrows < A.ncols ? A.nrows : A.ncols;
+  FB_ASSERT(Q.nrows > 0 && Q.ncols == size, "Q_coeff must be block_size x min(nrows, ncols)");
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
+  StagedMat q(Q.ptr, (i64)Q.nrows, (i64)Q.ncols, (i64)Q.row_stride, (i64)Q.col_stride, sizeof(T), true, true, st);
+  // the reference leaves the strict lower part of each T block untouched and zero-fills nothing for full rank
+  const i64 rank = qr_in_place<T>(st, a.view<T>(), q.view<T>());
+  finish_all(st, {&a, &q});
+  FaerV0_24_QrStatus out;
+  memset(&out, 0, sizeof(out));
+  if (rank < 0) {
+    out.tag = FaerV0_24_QrStatus_Unknown;  // rank-deficient input: not handled by the GPU path yet (see qr.cu)
+  } else {
+    out.tag = FaerV0_24_QrStatus_Ok;
+    out.ok.rank = (size_t)rank;
+  }
+  return out;
+}
+template <class T>
+void householder_seq_entry(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, FaerV0_24_MatMut rhs, bool transpose) {
+  require_device();
+  cudaStream_t st = current_stream();
+  StagedMat b(basis.ptr, (i64)basis.nrows, (i64)basis.ncols, (i64)basis.row_stride, (i64)basis.col_stride, sizeof(T), true, false, st);
+  StagedMat f(factor.ptr, (i64)factor.nrows, (i64)factor.ncols, (i64)factor.row_stride, (i64)factor.col_stride, sizeof(T), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, sizeof(T), true, true, st);
+  if (transpose) apply_block_householder_sequence_transpose_on_the_left<T>(st, b.view<const T>(), f.view<const T>(), r.view<T>());
+  else apply_block_householder_sequence_on_the_left<T>(st, b.view<const T>(), f.view<const T>(), r.view<T>());
+  finish_all(st, {&b, &f, &r});
+}
 }  // namespace
 
 extern "C" {
@@ -271,6 +305,46 @@ FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f6
   (void)par; (void)mem;
   return lu_entry(A, perm_fwd, perm_bwd, params, 8);
 }
+
+// ---- Householder QR (no pivoting) + block-Householder sequence application, f64 and f32 (helpers above) ----
+#define FB_QR_FFI(SUF, T)                                                                                              \
+  FaerV0_24_QrParams libfaer_v0_23_QrParams_##SUF(void) { return FaerV0_24_QrParams{48 * 48, 192 * 256}; }             \
+  size_t libfaer_v0_23_qr_recommended_block_size_##SUF(size_t nrows, size_t ncols) {                                   \
+    return (size_t)qr_recommended_block_size((i64)nrows, (i64)ncols);                                                  \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_qr_factor_in_place_scratch_##SUF(size_t nrows, size_t ncols, size_t block_size,       \
+                                                                  FaerV0_24_Par par, FaerV0_24_QrParams params) {      \
+    (void)nrows; (void)par; (void)params;                                                                              \
+    return FaerV0_24_Layout{block_size * ncols * sizeof(T), 64}; /* temp_mat_scratch(block_size, ncols) */            \
+  }                                                                                                                    \
+  FaerV0_24_QrStatus libfaer_v0_23_qr_factor_in_place_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatMut Q_coeff, FaerV0_24_Par par, \
+                                                            FaerV0_24_MemAlloc mem, FaerV0_24_QrParams params) {       \
+    (void)par; (void)mem; (void)params;                                                                                \
+    return qr_entry<T>(A, Q_coeff);                                                                                    \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_left_scratch_##SUF(size_t dim, size_t block_size, size_t rhs_ncols) { \
+    (void)dim;                                                                                                         \
+    return FaerV0_24_Layout{block_size * rhs_ncols * sizeof(T), 64};                                                   \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_left_scratch_##SUF(size_t dim, size_t block_size,  \
+                                                                                        size_t rhs_ncols) {            \
+    (void)dim;                                                                                                         \
+    return FaerV0_24_Layout{block_size * rhs_ncols * sizeof(T), 64};                                                   \
+  }                                                                                                                    \
+  void libfaer_v0_23_apply_householder_on_the_left_##SUF(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, FaerV0_24_Conj conj, \
+                                                         FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) { \
+    (void)conj; (void)par; (void)mem;                                                                                  \
+    householder_seq_entry<T>(basis, factor, rhs, false);                                                               \
+  }                                                                                                                    \
+  void libfaer_v0_23_apply_householder_transpose_on_the_left_##SUF(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor,    \
+                                                                   FaerV0_24_Conj conj, FaerV0_24_MatMut rhs,          \
+                                                                   FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {        \
+    (void)conj; (void)par; (void)mem;                                                                                  \
+    householder_seq_entry<T>(basis, factor, rhs, true);                                                                \
+  }
+FB_QR_FFI(f64, double)
+FB_QR_FFI(f32, float)
+#undef FB_QR_FFI
 
 // ---- solves on top of the factors ----
 FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {

@@ -1,0 +1,363 @@
+// Householder QR without pivoting (f32 / f64): cooperative panel kernel + blocked driver.
+//
+// Reference: faer/src/linalg/qr/no_pivoting/factor.rs
+//   qr_in_place 258-301, qr_in_place_blocked 137-256 (panel -> T factor -> block apply to the trailing columns),
+//   qr_in_place_unblocked 11-86 (per column: make_householder, rank test, dot + axpy on the rest of the panel),
+//   householder::make_householder_imp (householder.rs:59-107): tail norm, beta = -sign(head) * norm stored in the
+//   head, v_tail = tail / (head + sign * norm), tau = (1 + (|tail| * |1/(head + sign*norm)|)^2) / 2, tau = +inf when
+//   the tail vanishes.
+//
+// B200 mapping. The reference recurses 256 -> 128 -> ... -> 1 with a GEMM-based T upgrade at every level; on the GPU
+// that is ~10^5 tiny launches, so the blocking is different while the mathematics (and the output format: V below the
+// diagonal, R above, Q_coeff = one block_size x block_size T block per block of columns, T = striu(V^H V) + diag(tau))
+// is the same:
+//   * a block of `block_size` columns is factored as sub-panels of <= 32 columns; each sub-panel is ONE cooperative
+//     kernel (`qr_panel_kernel`): the panel is sliced by rows over <= 148 CTAs and stays in shared memory; per column
+//     there is exactly one grid-wide exchange: every CTA publishes its partial tail norm (three scaled accumulators,
+//     as reductions/norm_l2.rs) and its partial dot products of the tail with the remaining panel columns, the owner
+//     of the diagonal row publishes that row; after the barrier every CTA reduces the partials in a fixed order
+//     (deterministic), forms (beta, tau, 1/(head+beta)) and the coefficients k_c = -(head_c + v^H a_c) / tau, and updates
+//     its slice (v in place, a_c += k_c v);
+//   * the sub-panel's T block and the block's full T are tall-skinny V^H V products (split-K DMMA / 3xTF32 GEMM);
+//   * reflector blocks are applied to the rest of the block and to the trailing matrix with the block-Householder
+//     GEMM composition (householder.cu).
+// Rank deficiency: the reference skips columns whose norm falls below eps*16*(m-row)*norm and compacts the reflectors
+// (factor.rs:52-83). The GPU path DETECTS that event (same test) and reports it (QrStatus::Unknown) instead of
+// continuing — full-rank inputs (row == col throughout) are handled completely.
+#include <algorithm>
+#include <limits>
+
+#include "runtime.cuh"
+#include "tensor_ops.cuh"
+
+namespace fb {
+
+namespace {
+
+constexpr int QR_PW = 32;        // sub-panel width (columns per cooperative launch)
+constexpr int QR_THREADS = 256;  // 8 row groups x 32 column lanes
+constexpr int QR_NV = QR_PW + 4; // published values per CTA and column: dots[PW], sml, med, big, above
+
+template <class T>
+struct QrScratch {
+  T* part;   // [2][G][QR_NV]
+  T* rowv;   // [2][QR_PW]
+  unsigned long long* bar;
+};
+
+__device__ __forceinline__ void qr_grid_barrier(unsigned long long* bar, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1ull);
+    while (*((volatile unsigned long long*)bar) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float t_hypot(float a, float b) { return hypotf(a, b); }
+__device__ __forceinline__ double t_hypot(double a, double b) { return hypot(a, b); }
+__device__ __forceinline__ float t_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double t_sqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float t_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ double t_abs(double a) { return fabs(a); }
+template <class T> struct TLim;
+template <> struct TLim<float> {
+  __device__ static float min_pos() { return 1.17549435e-38f; }
+  __device__ static float eps() { return 1.1920929e-7f; }
+  __device__ static float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct TLim<double> {
+  __device__ static double min_pos() { return 2.2250738585072014e-308; }
+  __device__ static double eps() { return 2.220446049250313e-16; }
+  __device__ static double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
+};
+__device__ __forceinline__ float t_ldcg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ double t_ldcg(const double* p) { return __ldcg(p); }
+
+// A: panel top-left (local row 0 = the diagonal row of panel column 0); mp rows, w <= QR_PW columns.
+// taus: pointer to the T-block diagonal entry of column 0, `tau_stride` elements between consecutive diagonal entries.
+// above2[c]: sum of squares of the w panel columns over the matrix rows ABOVE the panel (rank test only).
+// flag: set to 1 if a rank-deficient column is met.
+template <class T>
+__global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(T* __restrict__ A, i64 rs, i64 cs, int mp, int w,
+                                                               int rows_per_cta, T* __restrict__ taus, i64 tau_stride,
+                                                               QrScratch<T> sc, unsigned long long bar_base,
+                                                               const T* __restrict__ above2, long long rows_below0,
+                                                               int* __restrict__ flag) {
+  extern __shared__ unsigned char qr_smem_raw[];
+  T* S = reinterpret_cast<T*>(qr_smem_raw);  // [rows_per_cta][LD]
+  const int LD = w | 1;
+  __shared__ T red[QR_THREADS / 32][QR_NV];
+  __shared__ T tot[QR_NV];
+  __shared__ T rowj[QR_PW];
+  __shared__ T kc[QR_PW];
+
+  const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;  // lane = panel column, rg = row group
+  const int G = gridDim.x, bid = blockIdx.x;
+  const int r0 = bid * rows_per_cta;
+  const int nloc = max(0, min(rows_per_cta, mp - r0));
+  const int ncol = min(w, mp);
+
+  const T min_pos = TLim<T>::min_pos();
+  const T sml = t_sqrt(min_pos), big = t_sqrt(T(1) / min_pos);
+  const T eps = TLim<T>::eps();
+
+  for (int r = tid; r < nloc; r += QR_THREADS) {
+    const T* src = A + (i64)(r0 + r) * rs;
+    T* dst = S + r * LD;
+#pragma unroll 8
+    for (int c = 0; c < w; ++c) dst[c] = src[(i64)c * cs];
+  }
+  __syncthreads();
+
+  unsigned long long nbar = 0;
+  for (int j = 0; j < ncol; ++j) {
+    const int par = j & 1;
+    // ---- phase A: partial dots of the tail of column j with columns c > j, and partial norms ----
+    T acc = T(0), a_sml = T(0), a_big = T(0), a_above = T(0);
+    for (int r = rg; r < nloc; r += QR_THREADS / 32) {
+      const int il = r0 + r;
+      const T x = S[r * LD + j];
+      if (il > j) {
+        if (lane >= j && lane < w) acc = fma(x, S[r * LD + lane], acc);
+        if (lane == j) {
+          const T xs = x * sml, xb = x * big;
+          a_sml = fma(xs, xs, a_sml);
+          a_big = fma(xb, xb, a_big);
+        }
+      } else if (il < j && lane == j) {
+        a_above = fma(x, x, a_above);
+      }
+    }
+    red[rg][lane] = acc;  // lane == j carries the unscaled sum of squares ("med")
+    if (lane == j) {
+      red[rg][QR_PW + 0] = a_sml;
+      red[rg][QR_PW + 1] = a_big;
+      red[rg][QR_PW + 2] = a_above;
+    }
+    __syncthreads();
+    if (tid < QR_NV - 1) {
+      T s = T(0);
+#pragma unroll
+      for (int q = 0; q < QR_THREADS / 32; ++q) s += red[q][tid];
+      sc.part[((i64)par * G + bid) * QR_NV + tid] = s;
+    }
+    if (j >= r0 && j < r0 + nloc) {
+      if (tid < w) sc.rowv[par * QR_PW + tid] = S[(j - r0) * LD + tid];
+    }
+    ++nbar;
+    qr_grid_barrier(sc.bar, bar_base + nbar * (unsigned long long)G);
+
+    // ---- phase B: deterministic reduction over the CTAs (fixed order), then the reflector scalars ----
+    {
+      const int v = tid & 63, q = tid >> 6;  // 4 partial sums per value
+      T s = T(0);
+      if (v < QR_NV - 1)
+        for (int b = q; b < G; b += 4) s += t_ldcg(&sc.part[((i64)par * G + b) * QR_NV + v]);
+      __syncthreads();  // red[] reuse
+      if (v < QR_NV - 1) red[q][v] = s;
+      __syncthreads();
+      if (tid < QR_NV - 1) tot[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+      if (tid < w) rowj[tid] = t_ldcg(&sc.rowv[par * QR_PW + tid]);
+      __syncthreads();
+    }
+    // make_householder (householder.rs:59-107), evaluated redundantly by every thread
+    const T acc_med = tot[j], acc_sml = tot[QR_PW + 0], acc_big = tot[QR_PW + 1];
+    T tail_norm;
+    if (acc_sml >= T(1)) tail_norm = t_sqrt(acc_sml) * big;
+    else if (acc_med >= T(1)) tail_norm = t_sqrt(acc_med);
+    else tail_norm = t_sqrt(acc_big) * sml;
+    T head = rowj[j];
+    T head_norm = t_abs(head);
+    if (head_norm < min_pos) {
+      head = T(0);
+      head_norm = T(0);
+    }
+    T tau, inv = T(0), norm, new_head = head;
+    const bool no_tail = tail_norm < min_pos;
+    if (no_tail) {
+      tau = TLim<T>::inf();
+      norm = head_norm;
+    } else {
+      norm = t_hypot(head_norm, tail_norm);
+      const T sign = head_norm != T(0) ? head * (T(1) / head_norm) : T(1);
+      const T signed_norm = sign * norm;
+      inv = T(1) / (head + signed_norm);
+      new_head = -signed_norm;
+      const T tt = tail_norm * t_abs(inv);
+      tau = T(0.5) * (T(1) + tt * tt);
+    }
+    // rank test (factor.rs:52-64)
+    const T norm_above = t_sqrt(above2[j] + tot[QR_PW + 2]);
+    const T total = t_hypot(norm, norm_above);
+    const T threshold = eps * T((double)(rows_below0 - j) * 16.0) * total;
+    const T tau_inv = T(1) / tau;
+    bool apply = false;
+    if (tau_inv < min_pos) {
+      if (!(norm > T(0))) {
+        if (bid == 0 && tid == 0) *flag = 1;  // exactly zero column: the reference would not advance `row`
+      }
+    } else if (norm > threshold) {
+      apply = true;
+    } else {
+      if (bid == 0 && tid == 0) *flag = 1;    // numerically dependent column: reference skips it
+    }
+    if (bid == 0 && tid == 0) taus[(i64)j * tau_stride] = tau;
+    if (tid < w) {
+      // k_c = -(head_c + v^H a_c) / tau   (factor.rs:65-80)
+      const T dot = rowj[tid] + inv * tot[tid];
+      kc[tid] = (apply && tid > j) ? -(dot * tau_inv) : T(0);
+    }
+    __syncthreads();
+    // ---- phase C: write v (scaled tail), beta, and update the remaining panel columns ----
+    if (j >= r0 && j < r0 + nloc && rg == ((j - r0) & (QR_THREADS / 32 - 1))) {
+      T* row = S + (j - r0) * LD;
+      if (lane == j && !no_tail) row[j] = new_head;
+      else if (lane == j && no_tail && head_norm == T(0)) row[j] = T(0);
+      if (lane > j && lane < w) row[lane] += kc[lane];
+    }
+    if (!no_tail) {
+      for (int r = rg; r < nloc; r += QR_THREADS / 32) {
+        const int il = r0 + r;
+        if (il > j) {
+          const T vi = S[r * LD + j] * inv;
+          __syncwarp();
+          if (lane == j) S[r * LD + j] = vi;
+          else if (lane > j && lane < w) S[r * LD + lane] = fma(kc[lane], vi, S[r * LD + lane]);
+        }
+      }
+    }
+    // rows are owned by warps (row r -> warp r mod 8) in phases A and C alike; the next phase A needs no CTA barrier
+    // for S, and red/tot/rowj/kc are protected by the barriers of the next iteration
+    __syncthreads();
+  }
+  for (int r = tid; r < nloc; r += QR_THREADS) {
+    T* dstg = A + (i64)(r0 + r) * rs;
+    const T* srcs = S + r * LD;
+#pragma unroll 8
+    for (int c = 0; c < w; ++c) dstg[(i64)c * cs] = srcs[c];
+  }
+}
+
+// above2[c] = sum_{i < nrows} A[i, c]^2 for c < w  (one CTA per column; only feeds the rank test)
+template <class T>
+__global__ void __launch_bounds__(256) col_sumsq_kernel(const T* __restrict__ A, i64 rs, i64 cs, i64 nrows, T* out) {
+  __shared__ T red[256];
+  const T* col = A + (i64)blockIdx.x * cs;
+  T s = T(0);
+  for (i64 i = threadIdx.x; i < nrows; i += 256) {
+    const T x = col[i * rs];
+    s = fma(x, x, s);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
+}  // namespace
+
+i64 qr_recommended_block_size(i64 nrows, i64 ncols) {
+  // reference qr/no_pivoting/factor.rs:91-116
+  const i64 prod = nrows * ncols, size = std::min(nrows, ncols);
+  i64 bs;
+  if (prod > 8192ll * 8192) bs = 256;
+  else if (prod > 2048 * 2048) bs = 128;
+  else if (prod > 1024 * 1024) bs = 64;
+  else if (prod > 512 * 512) bs = 48;
+  else if (prod > 128 * 128) bs = 32;
+  else if (prod > 32 * 32) bs = 8;
+  else if (prod > 16 * 16) bs = 4;
+  else bs = 1;
+  return std::max<i64>(1, std::min(bs, size));
+}
+
+template <class T>
+i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
+  const i64 m = A.nrows, n = A.ncols, size = std::min(m, n), bs = H.nrows;
+  FB_ASSERT(bs > 0 && H.ncols == size, "Q_coeff must be block_size x min(nrows, ncols)");
+  if (size == 0) return 0;
+  FB_ASSERT(m < (1ll << 31) && n < (1ll << 31), "dimension too large");
+  int dev = 0, num_sms = 0;
+  FB_CUDA_CHECK(cudaGetDevice(&dev));
+  FB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int Gmax = num_sms;
+  // scratch
+  const size_t part_elems = (size_t)2 * Gmax * QR_NV, rowv_elems = (size_t)2 * QR_PW;
+  char* scb = (char*)ws_alloc((part_elems + rowv_elems + QR_PW) * sizeof(T) + 64);
+  QrScratch<T> sc;
+  sc.part = (T*)scb;
+  sc.rowv = sc.part + part_elems;
+  T* above2 = sc.rowv + rowv_elems;
+  sc.bar = (unsigned long long*)(((uintptr_t)(above2 + QR_PW) + 15) & ~(uintptr_t)15);
+  int* d_flag = (int*)ws_alloc(sizeof(int) * 4);
+  FB_CUDA_CHECK(cudaMemsetAsync(sc.bar, 0, 8, st));
+  FB_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  unsigned long long bar_count = 0;
+  static bool configured = false;
+  if (!configured) {
+    FB_CUDA_CHECK(cudaFuncSetAttribute(qr_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+
+  for (i64 j0 = 0; j0 < size; j0 += bs) {
+    const i64 jb = std::min(bs, size - j0);
+    for (i64 s0 = 0; s0 < jb; s0 += QR_PW) {
+      const i64 sw = std::min<i64>(QR_PW, jb - s0), c0 = j0 + s0;
+      const i64 mp = m - c0;
+      // sums of squares above the panel (rank test)
+      if (c0 > 0) {
+        col_sumsq_kernel<T><<<(unsigned)sw, 256, 0, st>>>(A.at(0, c0), A.rs, A.cs, c0, above2);
+        FB_CUDA_CHECK(cudaGetLastError());
+        note_launch();
+      } else {
+        FB_CUDA_CHECK(cudaMemsetAsync(above2, 0, QR_PW * sizeof(T), st));
+      }
+      int G = (int)std::min<i64>(Gmax, (mp + 63) / 64);
+      if (G < 1) G = 1;
+      int rows_per_cta = (int)((mp + G - 1) / G);
+      const size_t smem = (size_t)rows_per_cta * (size_t)((int)sw | 1) * sizeof(T);
+      FB_ASSERT(smem <= 200 * 1024, "QR panel too tall for the shared-memory slices");
+      T* Ap = A.at(c0, c0);
+      i64 rs = A.rs, cs = A.cs;
+      int mpi = (int)mp, wi = (int)sw;
+      T* taus = H.at(s0, c0);
+      i64 tau_stride = H.rs + H.cs;
+      unsigned long long base = bar_count;
+      const T* ab = above2;
+      long long rows_below0 = (long long)(m - c0);
+      void* args[] = {&Ap, &rs, &cs, &mpi, &wi, &rows_per_cta, &taus, &tau_stride, &sc, &base, &ab, &rows_below0, &d_flag};
+      FB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qr_panel_kernel<T>, dim3(G), dim3(QR_THREADS), args, smem, st));
+      note_launch();
+      bar_count += (unsigned long long)std::min<i64>(sw, mp) * G;
+      // T block of this sub-panel, then apply it to the rest of the block
+      View<const T> Vs = cview(A.sub(c0, c0, mp, sw));
+      View<T> Tss = H.sub(s0, c0, sw, sw);
+      householder_build_t<T>(st, Vs, Tss);
+      const i64 rest = j0 + jb - (c0 + sw);
+      if (rest > 0) apply_block_householder_on_the_left<T>(st, Vs, cview(Tss), A.sub(c0, c0 + sw, mp, rest), true);
+    }
+    // full T of the block (off-diagonal sub-blocks V_i^H V_j; the diagonal sub-blocks are recomputed identically)
+    View<const T> Vb = cview(A.sub(j0, j0, m - j0, jb));
+    View<T> Tb = H.sub(0, j0, jb, jb);
+    if (jb > QR_PW) householder_build_t<T>(st, Vb, Tb);
+    if (j0 + jb < n) apply_block_householder_on_the_left<T>(st, Vb, cview(Tb), A.sub(j0, j0 + jb, m - j0, n - (j0 + jb)), true);
+  }
+  int h_flag = 0;
+  FB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  ws_free(d_flag);
+  ws_free(scb);
+  return h_flag ? -1 : size;
+}
+
+template i64 qr_in_place<double>(cudaStream_t, View<double>, View<double>);
+template i64 qr_in_place<float>(cudaStream_t, View<float>, View<float>);
+
+}  // namespace fb

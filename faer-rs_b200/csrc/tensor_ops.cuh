@@ -1,0 +1,49 @@
+// Type-generic spellings (f32 / f64) of the tensor-core building blocks, so that the Householder / QR drivers are written
+// once. f64 -> DMMA GEMM (gemm_f64.cu), f32 -> 3xTF32 GEMM (gemm_f32.cu); triangular solves from trsm.cu.
+#pragma once
+#include "gemm_f32.cuh"
+#include "linalg_f64.cuh"
+
+namespace fb {
+
+inline void gemm(cudaStream_t st, VD dst, int ds, int accum, VCD lhs, int ls, VCD rhs, int rs, double alpha) {
+  gemm_f64(st, dst, ds, accum, lhs, ls, rhs, rs, alpha);
+}
+inline void gemm(cudaStream_t st, VF dst, int ds, int accum, VCF lhs, int ls, VCF rhs, int rs, float alpha) {
+  gemm_f32(st, dst, ds, accum, lhs, ls, rhs, rs, alpha);
+}
+inline void solve_lower(cudaStream_t st, VCD t, bool unit, VD rhs) { solve_lower_triangular_in_place_f64(st, t, unit, rhs); }
+inline void solve_lower(cudaStream_t st, VCF t, bool unit, VF rhs) { solve_lower_triangular_in_place_f32(st, t, unit, rhs); }
+inline void solve_upper(cudaStream_t st, VCD t, bool unit, VD rhs) { solve_upper_triangular_in_place_f64(st, t, unit, rhs); }
+inline void solve_upper(cudaStream_t st, VCF t, bool unit, VF rhs) { solve_upper_triangular_in_place_f32(st, t, unit, rhs); }
+
+template <class T>
+inline View<const T> cview(const View<T>& v) { return View<const T>{v.ptr, v.nrows, v.ncols, v.rs, v.cs}; }
+
+// ---- householder.cu ----
+// T(strict upper) <- V^H V for the N reflectors stored in V (m x N, implicit unit diagonal, R above it is ignored);
+// the diagonal of Tf (the taus) is left untouched.  Reference: householder.rs:132-272 (upgrade_householder_factor)
+template <class T>
+void householder_build_t(cudaStream_t st, View<const T> V, View<T> Tf);
+// M <- (I - V T^-1 V^H) M  (forward = false)   or   M <- (I - V T^-H V^H) M  (forward = true)
+// Reference: householder.rs:370-620 (apply_block_householder_on_the_left_in_place_generic)
+template <class T>
+void apply_block_householder_on_the_left(cudaStream_t st, View<const T> V, View<const T> Tf, View<T> M, bool forward);
+
+// sequences of block reflectors stored as (basis = V below the diagonal, factor = block_size x size T blocks)
+// Reference: householder.rs:724-808
+template <class T>
+void apply_block_householder_sequence_on_the_left(cudaStream_t st, View<const T> basis, View<const T> factor, View<T> M);
+template <class T>
+void apply_block_householder_sequence_transpose_on_the_left(cudaStream_t st, View<const T> basis, View<const T> factor,
+                                                            View<T> M);
+
+// ---- qr.cu ----
+// Householder QR without pivoting, reference qr/no_pivoting/factor.rs:258-301. H: block_size x min(m, n).
+// Returns the rank, or -1 if a rank-deficient column was met (full support of the reference's column-skipping logic is
+// not implemented on the GPU path yet; the caller reports QrStatus::Unknown instead of returning wrong factors).
+template <class T>
+i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H);
+i64 qr_recommended_block_size(i64 nrows, i64 ncols);
+
+}  // namespace fb

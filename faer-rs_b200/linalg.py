@@ -189,6 +189,49 @@ def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None) ->
         par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
+# ---- Householder QR (no pivoting) -----------------------------------------------------------------
+@dataclass
+class QrInfo:
+    rank: int
+
+
+def _suf(x) -> str:
+    return "f32" if _is_f32(x) else "f64"
+
+
+def qr_recommended_block_size(nrows: int, ncols: int) -> int:
+    """qr::no_pivoting::factor::recommended_block_size (qr/no_pivoting/factor.rs:91-116)."""
+    return int(capi.load().libfaer_v0_23_qr_recommended_block_size_f64(nrows, ncols))
+
+
+def qr_in_place(A, Q_coeff, par=None, params=None) -> QrInfo:
+    """qr::no_pivoting::factor::qr_in_place (qr/no_pivoting/factor.rs:258-301). Q_coeff: block_size x min(m, n).
+    f64 or f32. Raises RuntimeError on a rank-deficient input (not handled by the GPU path yet)."""
+    lib = capi.load()
+    suf = _suf(A)
+    assert _suf(Q_coeff) == suf
+    params = params or getattr(lib, f"libfaer_v0_23_QrParams_{suf}")()
+    st = getattr(lib, f"libfaer_v0_23_qr_factor_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(Q_coeff),
+                                                               par or capi.par_default(), capi.MemAlloc(None, 0), params)
+    if st.tag != 0:
+        raise RuntimeError("QrStatus::Unknown (rank-deficient input is not supported by the B200 QR path yet)")
+    return QrInfo(int(st.value))
+
+
+def apply_block_householder_sequence_on_the_left_in_place(basis, factor, rhs, conj: int = CONJ_NO, par=None) -> None:
+    """householder.rs:724-765: rhs <- Q rhs."""
+    lib = capi.load()
+    getattr(lib, f"libfaer_v0_23_apply_householder_on_the_left_{_suf(rhs)}")(
+        capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
+def apply_block_householder_sequence_transpose_on_the_left_in_place(basis, factor, rhs, conj: int = CONJ_YES, par=None) -> None:
+    """householder.rs:768-808: rhs <- Q^H rhs."""
+    lib = capi.load()
+    getattr(lib, f"libfaer_v0_23_apply_householder_transpose_on_the_left_{_suf(rhs)}")(
+        capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
 # ---- partial-pivoting LU ---------------------------------------------------------------------------
 @dataclass
 class PartialPivLuInfo:

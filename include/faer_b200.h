@@ -154,6 +154,29 @@ struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64
 struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u32_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
 struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
 
+/* Householder QR without pivoting + block-Householder sequence application, f64 and f32.
+ * params: faer-ffi/src/lib.rs:671-675, faer.h:670; recommended_block_size: lib.rs:1520-1527, faer.h:5718;
+ * scratch/factor: lib.rs:1528-1558, faer.h:5592-5602; apply_householder_*: lib.rs:1423-1518, faer.h:754-759.
+ * Q_coeff is block_size x min(nrows, ncols): one upper-triangular T block per block of columns (tau on the diagonal,
+ * faer's convention tau = (1 + |v_tail|^2)/2). Rank-deficient inputs return QrStatus_Unknown on this backend (the
+ * reference's column-skipping path is not implemented on the GPU yet). */
+struct FaerV0_24_QrParams libfaer_v0_23_QrParams_f64(void);
+struct FaerV0_24_QrParams libfaer_v0_23_QrParams_f32(void);
+size_t libfaer_v0_23_qr_recommended_block_size_f64(size_t nrows, size_t ncols);
+size_t libfaer_v0_23_qr_recommended_block_size_f32(size_t nrows, size_t ncols);
+struct FaerV0_24_Layout libfaer_v0_23_qr_factor_in_place_scratch_f64(size_t nrows, size_t ncols, size_t block_size, struct FaerV0_24_Par par, struct FaerV0_24_QrParams params);
+struct FaerV0_24_Layout libfaer_v0_23_qr_factor_in_place_scratch_f32(size_t nrows, size_t ncols, size_t block_size, struct FaerV0_24_Par par, struct FaerV0_24_QrParams params);
+struct FaerV0_24_QrStatus libfaer_v0_23_qr_factor_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut Q_coeff, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_QrParams params);
+struct FaerV0_24_QrStatus libfaer_v0_23_qr_factor_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut Q_coeff, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_QrParams params);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_left_scratch_f64(size_t dim, size_t block_size, size_t rhs_ncols);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_left_scratch_f32(size_t dim, size_t block_size, size_t rhs_ncols);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_left_scratch_f64(size_t dim, size_t block_size, size_t rhs_ncols);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_left_scratch_f32(size_t dim, size_t block_size, size_t rhs_ncols);
+void libfaer_v0_23_apply_householder_on_the_left_f64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_on_the_left_f32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_transpose_on_the_left_f64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_transpose_on_the_left_f32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+
 /* solves on top of the factors.   llt: faer-ffi/src/lib.rs:1012-1038, faer.h:4188, 4216;
  * LU: lib.rs:1985-2020, faer.h:4786, 4884. L and U are views of the factored matrix (L: unit-lower part, U: upper part). */
 struct FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_f64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
