@@ -149,6 +149,13 @@ __global__ void __launch_bounds__(F_THREADS) gemm_f32_kernel(const GemmF32Params
   if (is_upper(p.a_struct)) k_begin = max(k_begin, m0);
   if (is_lower(p.b_struct)) k_begin = max(k_begin, n0);
   if (is_upper(p.b_struct)) k_end = min(k_end, n0 + F_BN);
+  float* __restrict__ Cout = p.C;
+  if (p.k_split_len > 0) {
+    const int kb = (int)blockIdx.y * p.k_split_len;
+    k_begin = max(k_begin, kb);
+    k_end = min(k_end, kb + p.k_split_len);
+    Cout += (i64)blockIdx.y * p.c_split_stride;
+  }
   k_begin = (k_begin / F_BK) * F_BK;
   const int nkt = k_end > k_begin ? (k_end - k_begin + F_BK - 1) / F_BK : 0;
 
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(F_THREADS) gemm_f32_kernel(const GemmF32Params
         if (c_low && (row < col || (row == col && c_nodiag))) v = false;
         if (c_up && (row > col || (row == col && c_nodiag))) v = false;
         ok[j][e] = v;
-        cv[j][e] = (add && v) ? p.C[(i64)row * p.c_rs + (i64)col * p.c_cs] : 0.0f;
+        cv[j][e] = (add && v) ? Cout[(i64)row * p.c_rs + (i64)col * p.c_cs] : 0.0f;
       }
 #pragma unroll
     for (int j = 0; j < F_WNI; ++j)
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(F_THREADS) gemm_f32_kernel(const GemmF32Params
       for (int e = 0; e < 4; ++e) {
         const int row = m0 + wm0 + i * 16 + g + (e >= 2 ? 8 : 0);
         const int col = n0 + wn0 + j * 8 + 2 * t + (e & 1);
-        if (ok[j][e]) p.C[(i64)row * p.c_rs + (i64)col * p.c_cs] = alpha * acc[i][j][e] + cv[j][e];
+        if (ok[j][e]) Cout[(i64)row * p.c_rs + (i64)col * p.c_cs] = alpha * acc[i][j][e] + cv[j][e];
       }
   }
 }
@@ -271,7 +278,8 @@ void f_launch(cudaStream_t stream, GemmF32Params& p) {
     FB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f32_kernel<AK, BNM, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  gemm_f32_kernel<AK, BNM, VEC><<<(unsigned)((long long)p.tiles_m * p.tiles_n), F_THREADS, smem, stream>>>(p);
+  const unsigned splits = p.k_split_len > 0 ? (unsigned)((p.k + p.k_split_len - 1) / p.k_split_len) : 1u;
+  gemm_f32_kernel<AK, BNM, VEC><<<dim3((unsigned)((long long)p.tiles_m * p.tiles_n), splits), F_THREADS, smem, stream>>>(p);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
 }
@@ -288,6 +296,22 @@ inline int f_transpose_struct(int s) {
   }
 }
 inline bool f_aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+// dst(struct) = [dst +] alpha * sum_z W_z (partial products summed in z order, in double to keep fp32-level accuracy)
+__global__ void f_splitk_reduce_kernel(float* __restrict__ C, i64 rs, i64 cs, int m, int n, int c_struct, int accum,
+                                       float alpha, const float* __restrict__ W, int splits) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)m * n) return;
+  const int row = (int)(e % m), col = (int)(e / m);
+  const bool nodiag = is_strict(c_struct) || is_unit(c_struct);
+  if (is_lower(c_struct) && (row < col || (row == col && nodiag))) return;
+  if (is_upper(c_struct) && (row > col || (row == col && nodiag))) return;
+  double s = 0.0;
+  for (int z = 0; z < splits; ++z) s += (double)W[(long long)z * m * n + e];
+  float* cp = C + (i64)row * rs + (i64)col * cs;
+  const float v = alpha * (float)s;
+  *cp = accum ? (*cp + v) : v;
+}
 
 }  // namespace
 
@@ -314,6 +338,28 @@ void gemm_f32(cudaStream_t stream, VF dst, int dst_struct, int accum, VCF lhs, i
   p.B = rhs.ptr; p.b_rs = rhs.rs; p.b_cs = rhs.cs; p.b_struct = rhs_struct;
   p.C = dst.ptr; p.c_rs = dst.rs; p.c_cs = dst.cs; p.c_struct = dst_struct;
   p.alpha = alpha; p.accum = accum;
+  p.k_split_len = 0; p.c_split_stride = 0;
+  // split-K for tall-skinny products (see gemm_f64.cu)
+  float* split_ws = nullptr;
+  int splits = 1;
+  {
+    const long long tiles = (long long)((p.m + F_BM - 1) / F_BM) * ((p.n + F_BN - 1) / F_BN);
+    if (tiles < 148 && p.k >= 4096 && lhs_struct == RECT && rhs_struct == RECT) {
+      splits = (int)std::min<long long>((148 * 4 + tiles - 1) / tiles, p.k / 1024);
+      if (splits >= 2) {
+        int len = (p.k + splits - 1) / splits;
+        len = (len + 63) / 64 * 64;
+        splits = (p.k + len - 1) / len;
+        split_ws = (float*)ws_alloc((size_t)splits * p.m * p.n * sizeof(float));
+        p.k_split_len = len;
+        p.c_split_stride = (i64)p.m * p.n;
+        p.C = split_ws; p.c_rs = 1; p.c_cs = p.m; p.c_struct = RECT;
+        p.alpha = 1.0f; p.accum = 0;
+      } else {
+        splits = 1;
+      }
+    }
+  }
   const bool a_unit_m = (lhs.rs == 1) || lhs.nrows == 1;
   const bool a_unit_k = (lhs.cs == 1) || lhs.ncols == 1;
   const bool AK = !a_unit_m && a_unit_k;
@@ -335,17 +381,29 @@ void gemm_f32(cudaStream_t stream, VF dst, int dst_struct, int accum, VCF lhs, i
     if (prof) profile_record_start(stream);           \
     f_launch<ak, bnm, vec>(stream, p);                \
     if (prof) profile_record_stop(stream, flops);     \
-    return;                                           \
+    launched = true;                                  \
   }
+  bool launched = false;
   FB_FDISPATCH(false, false, true)
-  FB_FDISPATCH(false, true, true)
-  FB_FDISPATCH(true, false, true)
-  FB_FDISPATCH(true, true, true)
-  FB_FDISPATCH(false, false, false)
-  FB_FDISPATCH(false, true, false)
-  FB_FDISPATCH(true, false, false)
-  FB_FDISPATCH(true, true, false)
+  else FB_FDISPATCH(false, true, true)
+  else FB_FDISPATCH(true, false, true)
+  else FB_FDISPATCH(true, true, true)
+  else FB_FDISPATCH(false, false, false)
+  else FB_FDISPATCH(false, true, false)
+  else FB_FDISPATCH(true, false, false)
+  else FB_FDISPATCH(true, true, false)
 #undef FB_FDISPATCH
+  FB_ASSERT(launched, "no GEMM variant matched");
+  if (split_ws) {
+    const long long total = (long long)dst.nrows * dst.ncols;
+    f_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dst.ptr, dst.rs, dst.cs, (int)dst.nrows,
+                                                                               (int)dst.ncols, dst_struct, accum, alpha,
+                                                                               split_ws, splits);
+    FB_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    FB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    ws_free(split_ws);
+  }
 }
 
 }  // namespace fb

@@ -16,6 +16,8 @@ struct GemmF32Params {
   float alpha;
   int accum;
   int tiles_m, tiles_n;
+  int k_split_len;       // split-K (see gemm_f64.cuh): 0 = off
+  i64 c_split_stride;
 };
 
 // dst(struct) = [dst +] alpha * lhs(struct) * rhs(struct); device views, element strides of any sign.
