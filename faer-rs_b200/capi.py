@@ -194,6 +194,13 @@ def load() -> C.CDLL:
     lib.faer_b200_profile_begin.restype = None
     lib.faer_b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
     lib.faer_b200_profile_end.restype = None
+    for suf in ("f64", "f32"):
+        f = getattr(lib, f"faer_b200_bidiag_in_place_{suf}")
+        f.argtypes = [MatMut, MatMut, MatMut]
+        f.restype = None
+        f = getattr(lib, f"faer_b200_tridiag_in_place_{suf}")
+        f.argtypes = [MatMut, MatMut]
+        f.restype = None
     lib.faer_b200_version.argtypes = []
     lib.faer_b200_version.restype = C.c_char_p
     _lib = lib

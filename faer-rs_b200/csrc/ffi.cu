@@ -91,6 +91,27 @@ void householder_seq_entry(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, Faer
   else apply_block_householder_sequence_on_the_left<T>(st, b.view<const T>(), f.view<const T>(), r.view<T>());
   finish_all(st, {&b, &f, &r});
 }
+// ---- reductions to condensed form (svd/bidiag.rs:47-256) ----
+template <class T>
+void bidiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Hl, FaerV0_24_MatMut Hr) {
+  require_device();
+  cudaStream_t st = current_stream();
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
+  StagedMat hl(Hl.ptr, (i64)Hl.nrows, (i64)Hl.ncols, (i64)Hl.row_stride, (i64)Hl.col_stride, sizeof(T), true, true, st);
+  StagedMat hr(Hr.ptr, (i64)Hr.nrows, (i64)Hr.ncols, (i64)Hr.row_stride, (i64)Hr.col_stride, sizeof(T), true, true, st);
+  bidiag_in_place<T>(st, a.view<T>(), hl.view<T>(), hr.view<T>());
+  finish_all(st, {&a, &hl, &hr});
+}
+// evd/tridiag.rs:274-529
+template <class T>
+void tridiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
+  require_device();
+  cudaStream_t st = current_stream();
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
+  StagedMat h(H.ptr, (i64)H.nrows, (i64)H.ncols, (i64)H.row_stride, (i64)H.col_stride, sizeof(T), true, true, st);
+  tridiag_in_place<T>(st, a.view<T>(), h.view<T>());
+  finish_all(st, {&a, &h});
+}
 }  // namespace
 
 extern "C" {
@@ -475,6 +496,16 @@ size_t faer_b200_dist_partial_piv_lu_factor_in_place_f64(void* A_local, size_t l
   FB_ASSERT(n == 0 || is_device_pointer(A_local), "distributed entry points take device-resident local matrices");
   return dist_lu_f64((double*)A_local, (i64)ld, (i64)n, (i64)nb, perm_fwd, perm_inv, lookahead);
 }
+
+void faer_b200_bidiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) {
+  bidiag_entry<double>(A, H_left, H_right);
+}
+void faer_b200_bidiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) {
+  bidiag_entry<float>(A, H_left, H_right);
+}
+
+void faer_b200_tridiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<double>(A, householder); }
+void faer_b200_tridiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<float>(A, householder); }
 
 const char* faer_b200_version(void) { return "faer_b200 0.1 (faer-ffi v0_23 ABI subset, sm_100a)"; }
 

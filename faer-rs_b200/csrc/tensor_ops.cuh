@@ -46,4 +46,13 @@ template <class T>
 i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H);
 i64 qr_recommended_block_size(i64 nrows, i64 ncols);
 
+// ---- bidiag.cu ----
+// A = U B V^H, m >= n, column-major A. Reference: svd/bidiag.rs:47-256. Hl: bl x n, Hr: br x (n-1) (T blocks).
+template <class T>
+void bidiag_in_place(cudaStream_t st, View<T> A, View<T> Hl, View<T> Hr);
+// ---- tridiag.cu ----
+// A = Q T Q^H, self-adjoint A (lower triangle), column-major. Reference: evd/tridiag.rs:274-529. H: b x (n-1).
+template <class T>
+void tridiag_in_place(cudaStream_t st, View<T> A, View<T> H);
+
 }  // namespace fb

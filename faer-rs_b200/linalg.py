@@ -232,6 +232,26 @@ def apply_block_householder_sequence_transpose_on_the_left_in_place(basis, facto
         capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
+def bidiag_in_place(A, H_left, H_right, par=None, params=None) -> None:
+    """svd::bidiag::bidiag_in_place (svd/bidiag.rs:47-256): A = U B V^H for nrows >= ncols, f64 or f32. B ends up on A's
+    diagonal / superdiagonal, the left reflectors below the diagonal (T blocks in H_left, bl x ncols), the right
+    reflectors to the right of the superdiagonal (T blocks in H_right, br x (ncols - 1))."""
+    lib = capi.load()
+    suf = _suf(A)
+    assert _suf(H_left) == suf and _suf(H_right) == suf
+    getattr(lib, f"faer_b200_bidiag_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(H_left), capi.mat_mut(H_right))
+
+
+def tridiag_in_place(A, householder, par=None, params=None) -> None:
+    """evd::tridiag::tridiag_in_place (evd/tridiag.rs:274-529): A = Q T Q^H for a self-adjoint A (only the lower triangle
+    is read / written), f64 or f32. T ends up on A's diagonal / subdiagonal, the reflectors below the subdiagonal, their
+    T blocks in `householder` (b x (n - 1))."""
+    lib = capi.load()
+    suf = _suf(A)
+    assert _suf(householder) == suf
+    getattr(lib, f"faer_b200_tridiag_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(householder))
+
+
 # ---- partial-pivoting LU ---------------------------------------------------------------------------
 @dataclass
 class PartialPivLuInfo:

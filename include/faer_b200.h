@@ -224,6 +224,19 @@ struct FaerV0_24_LltStatus faer_b200_dist_llt_factor_in_place_f64(void *A_local,
  * transposition count. Pivots are identical to the single-GPU entry point's. */
 size_t faer_b200_dist_partial_piv_lu_factor_in_place_f64(void *A_local, size_t ld, size_t n, size_t nb,
                                                          long long *perm_fwd, long long *perm_inv, int lookahead);
+/* ---- reduction to bidiagonal form A = U B V^H (nrows >= ncols). faer-ffi does not export this stage on its own (it is
+ * reached through libfaer_v0_23_svd_*, faer-ffi/src/lib.rs:2345-2366 -> faer/src/linalg/svd/mod.rs:326-431); the entry
+ * mirrors the Rust function it replaces, faer::linalg::svd::bidiag::bidiag_in_place (faer/src/linalg/svd/bidiag.rs:47-54):
+ * B on A's diagonal / superdiagonal, left reflectors below the diagonal with H_left (bl x ncols) holding their T blocks,
+ * right reflectors right of the superdiagonal with H_right (br x (ncols-1)). Device matrices must be column-major. */
+void faer_b200_bidiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
+void faer_b200_bidiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
+/* ---- reduction to tridiagonal form A = Q T Q^H of a self-adjoint matrix (lower triangle read and written; n <= 8192 in
+ * this version). Reached in the reference through libfaer_v0_23_self_adjoint_evd_* (faer-ffi/src/lib.rs:2382-2400 ->
+ * faer/src/linalg/evd/mod.rs); mirrors faer::linalg::evd::tridiag::tridiag_in_place (faer/src/linalg/evd/tridiag.rs:274-280):
+ * T on A's diagonal / subdiagonal, reflectors below the subdiagonal, `householder` (b x (n-1)) holds their T blocks. */
+void faer_b200_tridiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+void faer_b200_tridiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
 /* Version string. */
 const char *faer_b200_version(void);
 

@@ -74,6 +74,16 @@ i64 lu_in_place(Mat<T> A, i64* perm, i64* perm_inv, i64 recursion_threshold);
 // ---- oracle_qr.cpp ----
 // norm_l2: faer/src/linalg/reductions/norm_l2.rs:6-172
 template <class T> typename real_of<T>::type norm_l2(const T* p, i64 n, i64 stride);
+// householder::make_householder_imp: faer/src/linalg/householder.rs:59-107 (`in == nullptr` -> in place)
+template <class T>
+struct HouseholderInfo {
+  typename real_of<T>::type tau;
+  T head_with_beta_inv;
+  typename real_of<T>::type norm;
+};
+template <class T> HouseholderInfo<T> make_householder(T* head, T* out, i64 out_stride, const T* in, i64 in_stride, i64 len);
+// householder::upgrade_householder_factor: householder.rs:132-272
+template <class T> void upgrade_householder_factor(Mat<T> Tf, Mat<const T> V, i64 block_size, i64 prev_block_size);
 // Householder QR without pivoting: faer/src/linalg/qr/no_pivoting/factor.rs:258-301; Q_coeff is block_size x min(m,n);
 // returns the numerical rank.
 template <class T> i64 qr_in_place(Mat<T> A, Mat<T> Q_coeff, i64 blocking_threshold);
@@ -81,5 +91,11 @@ i64 qr_recommended_block_size(i64 nrows, i64 ncols);
 // block reflector application: faer/src/linalg/householder.rs:370-620
 template <class T>
 void apply_block_householder_on_the_left(Mat<const T> V, Mat<const T> Tf, bool conj_lhs, Mat<T> M, bool forward);
+
+// ---- oracle_condensed.cpp ----
+// bidiagonalization A = U B V^H (m >= n): faer/src/linalg/svd/bidiag.rs:47-256. Hl: bl x n, Hr: br x (n-1).
+template <class T> void bidiag_in_place(Mat<T> A, Mat<T> Hl, Mat<T> Hr);
+// tridiagonalization A = Q T Q^H (lower triangle): faer/src/linalg/evd/tridiag.rs:274-529. H: b x (n-1).
+template <class T> void tridiag_in_place(Mat<T> A, Mat<T> H);
 
 }  // namespace oracle

@@ -56,6 +56,10 @@ def load() -> C.CDLL:
     lib.oracle_qr.restype = C.c_longlong
     lib.oracle_qr_recommended_block_size.argtypes = [C.c_longlong, C.c_longlong]
     lib.oracle_qr_recommended_block_size.restype = C.c_longlong
+    lib.oracle_bidiag.argtypes = [C.c_int, OMat, OMat, OMat]
+    lib.oracle_bidiag.restype = C.c_longlong
+    lib.oracle_tridiag.argtypes = [C.c_int, OMat, OMat]
+    lib.oracle_tridiag.restype = C.c_longlong
     lib.oracle_apply_block_householder_left.argtypes = [C.c_int, OMat, OMat, C.c_int, OMat, C.c_int]
     lib.oracle_apply_block_householder_left.restype = C.c_longlong
     lib.oracle_norm_l2.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_longlong]
@@ -167,6 +171,29 @@ def apply_q_sequence(QR, H, M, conj_lhs=False) -> None:
         apply_block_householder_on_the_left(QR[jp:, jp:j], H[:j - jp, jp:j], M[jp:, :], False, conj_lhs=conj_lhs)
         j = jp
         b = bs
+
+
+def bidiag(A, bl: int, br: int):
+    """In-place bidiagonalization A = U B V^H, m >= n (svd/bidiag.rs:47-256). Returns (H_left [bl x n], H_right
+    [br x (n-1)]). B is on A's diagonal / superdiagonal, left reflectors below the diagonal, right reflectors to the
+    right of the superdiagonal."""
+    m, n = A.shape
+    size = min(m, n)
+    Hl = np.zeros((bl, size), dtype=A.dtype, order="F")
+    Hr = np.zeros((br, max(size - 1, 0)), dtype=A.dtype, order="F")
+    r = load().oracle_bidiag(_DT[A.dtype], _om(A), _om(Hl), _om(Hr))
+    assert r == 0
+    return Hl, Hr
+
+
+def tridiag(A, b: int):
+    """In-place tridiagonalization A = Q T Q^H of a self-adjoint matrix, lower triangle only (evd/tridiag.rs:274-529).
+    Returns H [b x (n-1)]. T is on A's diagonal / subdiagonal, reflectors below the subdiagonal."""
+    n = A.shape[0]
+    H = np.zeros((b, max(n - 1, 0)), dtype=A.dtype, order="F")
+    r = load().oracle_tridiag(_DT[A.dtype], _om(A), _om(H))
+    assert r == 0
+    return H
 
 
 def norm_l2(x) -> float:

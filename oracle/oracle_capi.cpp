@@ -79,6 +79,15 @@ long long oracle_apply_block_householder_left(int dtype, OMat V, OMat Tf, int co
   DISPATCH(dtype, apply_block_householder_on_the_left<T>(mc<T>(V), mc<T>(Tf), conj_lhs != 0, mm<T>(M), forward != 0));
   return 0;
 }
+// reductions to condensed form (oracle_condensed.cpp)
+long long oracle_bidiag(int dtype, OMat A, OMat Hl, OMat Hr) {
+  DISPATCH(dtype, bidiag_in_place<T>(mm<T>(A), mm<T>(Hl), mm<T>(Hr)));
+  return 0;
+}
+long long oracle_tridiag(int dtype, OMat A, OMat H) {
+  DISPATCH(dtype, tridiag_in_place<T>(mm<T>(A), mm<T>(H)));
+  return 0;
+}
 double oracle_norm_l2(int dtype, const void* p, long long n, long long stride) {
   switch (dtype) {
     case 0: return norm_l2<float>((const float*)p, n, stride);

@@ -44,16 +44,9 @@ typename real_of<T>::type norm_l2(const T* p, i64 n, i64 stride) {
   return std::sqrt(acc_big) * sml;
 }
 
-template <class T>
-struct HouseholderInfo {
-  typename real_of<T>::type tau;
-  T head_with_beta_inv;
-  typename real_of<T>::type norm;
-};
-
 // householder.rs:59-107. `out`/`in` are column vectors of length len (in == nullptr -> in place).
 template <class T>
-static HouseholderInfo<T> make_householder(T* head, T* out, i64 out_stride, const T* in, i64 in_stride, i64 len) {
+HouseholderInfo<T> make_householder(T* head, T* out, i64 out_stride, const T* in, i64 in_stride, i64 len) {
   typedef typename real_of<T>::type R;
   const R min_pos = std::numeric_limits<R>::min();
   const R inf = std::numeric_limits<R>::infinity();
@@ -126,7 +119,7 @@ static i64 qr_unblocked(Mat<T> A, T* H, i64 H_len, i64 h_stride, i64 row_start, 
 
 // householder.rs:132-272
 template <class T>
-static void upgrade_householder_factor(Mat<T> Tf, Mat<const T> V, i64 block_size, i64 prev_block_size) {
+void upgrade_householder_factor(Mat<T> Tf, Mat<const T> V, i64 block_size, i64 prev_block_size) {
   if (block_size == prev_block_size || Tf.m <= prev_block_size) return;
   const i64 n = V.n;
   const i64 block_count = (Tf.m + block_size - 1) / block_size;
@@ -269,7 +262,9 @@ i64 qr_recommended_block_size(i64 nrows, i64 ncols) {
 #define ORACLE_QR_INST(T)                                                                           \
   template i64 qr_in_place<T>(Mat<T>, Mat<T>, i64);                                                 \
   template void apply_block_householder_on_the_left<T>(Mat<const T>, Mat<const T>, bool, Mat<T>, bool); \
-  template real_of<T>::type norm_l2<T>(const T*, i64, i64);
+  template real_of<T>::type norm_l2<T>(const T*, i64, i64);                                         \
+  template HouseholderInfo<T> make_householder<T>(T*, T*, i64, const T*, i64, i64);                 \
+  template void upgrade_householder_factor<T>(Mat<T>, Mat<const T>, i64, i64);
 ORACLE_QR_INST(double)
 ORACLE_QR_INST(float)
 ORACLE_QR_INST(std::complex<double>)
