@@ -311,8 +311,13 @@ def main():
     # ---- roofline of the dominant kernel (the DMMA GEMM doing the trailing updates), rank 0's view ----
     roof = None
     import ctypes as C
+    # The profiled step runs the SAME block-column schedule with the two-stream look-ahead switched off: with look-ahead
+    # the panel-chain GEMMs share the SMs with the trailing update, and per-launch event times of co-running kernels
+    # overlap (their sum exceeds the step), which says nothing about the kernel. Serial launches give its own duration.
+    A.copy_(A0)
     lib.faer_b200_profile_begin()
-    step()
+    fail, _ = lay.cholesky_in_place(A, n, nb=(nb if distributed else 1024), lookahead=False)
+    assert fail == -1
     barrier()
     flops = C.c_double(0); ms = C.c_double(0); cnt = C.c_ulonglong(0)
     lib.faer_b200_profile_end(C.byref(flops), C.byref(ms), C.byref(cnt))
@@ -340,8 +345,9 @@ def main():
             "peak_source": "measured on this pool: DMMA.8x8x4 issue-bound peak, profiles/r01_f64_peaks.json "
                            "(tcgen05 has no f64 kind; MEASURED_PEAKS.json only has bf16: "
                            f"{bf16} TF/s sustained => frac_of_bf16 = {(ach / bf16) if (ach and bf16) else None})",
-            "how": "CUDA events around every launch of the kernel on the launching stream(s), one extra profiled step "
-                   "right after the timed region (rank 0); achieved = sum(algorithmic flop per launch) / sum(duration)"}
+            "how": "CUDA events around every launch of the kernel on the launching stream, one extra profiled step right "
+                   "after the timed region (rank 0), same block-column schedule with the look-ahead overlap off so that "
+                   "launches do not share the SMs; achieved = sum(algorithmic flop per launch) / sum(duration)"}
 
     # ---- e2e: same metric with HOST (pinned) buffers, copies inside the timed region ----
     e2e = None

@@ -142,12 +142,17 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bidiag_kernel(T* A, i64 cs, int
           const int ch1 = min(m, ch0 + BD_CH);
           if (staged != chunk) {
             if (staged >= 0) __syncthreads();
+            // predicated + unrolled: the 12 loads of four iterations are in flight together
+#pragma unroll 4
             for (int g = ch0 + tid; g < ch1; g += BD_THREADS) {
-              if (g < k) continue;
-              u_s[g - ch0] = g > k ? t_ldcg(&sc.ubuf[g]) * inv_l : T(0);
-              if (pend) {
-                up_s[g - ch0] = t_ldcg(&A[(i64)(k - 1) * cs + g]);
-                z_s[g - ch0] = t_ldcg(&sc.zbuf[g]);
+              const bool on = g >= k;
+              const T uv = (on && g > k) ? t_ldcg(&sc.ubuf[g]) * inv_l : T(0);
+              const T pv = (on && pend) ? t_ldcg(&A[(i64)(k - 1) * cs + g]) : T(0);
+              const T zv = (on && pend) ? t_ldcg(&sc.zbuf[g]) : T(0);
+              if (on) {
+                u_s[g - ch0] = uv;
+                up_s[g - ch0] = pv;
+                z_s[g - ch0] = zv;
               }
             }
             __syncthreads();
@@ -296,8 +301,10 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bidiag_kernel(T* A, i64 cs, int
       for (int cc0 = 0; cc0 < nr; cc0 += BD_CH) {
         const int cn = min(BD_CH, nr - cc0);
         if (cc0 > 0) __syncthreads();
-        if (active)
+        if (active) {
+#pragma unroll 4
           for (int jj = tid; jj < cn; jj += BD_THREADS) z_s[jj] = t_ldcg(&sc.a12[k + 1 + cc0 + jj]);
+        }
         __syncthreads();
         if (valid) {
           const T* Ar = A + (i64)(k + 1 + cc0) * cs + g;

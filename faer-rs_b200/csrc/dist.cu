@@ -9,6 +9,7 @@
 //
 // NCCL is resolved at run time with dlopen("libnccl.so.2") (the copy torch already loaded in a torch process), so
 // libfaer_b200.so has no link-time NCCL dependency and single-GPU users never touch it.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -101,6 +102,93 @@ static void ensure_streams() {
   FB_CUDA_CHECK(cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, lo));
 }
 
+// ---- SM partitioning for the single-GPU look-ahead (CUDA green contexts) ------------------------------------------
+// The panel chain (potf2 / TRSM leaves / small GEMMs / the cooperative LU panel) is latency-bound and must not queue
+// behind the trailing-update GEMM, whose CTAs fill every SM: a pending panel CTA otherwise waits for whole SMs to drain
+// (one 64x64x1024 GEMM tile runs ~100 us). A green context pins the panel stream to its own `P` SMs and the update
+// stream to the rest. FAER_B200_GREEN_SMS=P (multiple of 8; 0 = off) selects the partition size.
+static cudaStream_t g_green_panel = nullptr, g_green_main = nullptr, g_green_urgent = nullptr;
+static int g_green_state = 0;      // 0 = not tried, 1 = active, -1 = unavailable / off
+static int g_green_panel_sms = 0;  // SMs of the panel partition when active
+
+static int green_sms_wanted() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FAER_B200_GREEN_SMS");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+
+static bool ensure_green_streams() {
+  if (g_green_state) return g_green_state > 0;
+  g_green_state = -1;
+  const int want = green_sms_wanted();
+  if (want <= 0) return false;
+#define FB_DRV(name)                                                                                         \
+  decltype(&name) p_##name = nullptr;                                                                       \
+  {                                                                                                          \
+    void* f_ = nullptr;                                                                                      \
+    cudaDriverEntryPointQueryResult q_;                                                                      \
+    if (cudaGetDriverEntryPoint(#name, &f_, cudaEnableDefault, &q_) != cudaSuccess || !f_) {                 \
+      fprintf(stderr, "faer_b200: green contexts unavailable (%s missing); look-ahead uses plain streams\n", #name); \
+      return false;                                                                                          \
+    }                                                                                                        \
+    p_##name = (decltype(&name))f_;                                                                          \
+  }
+#define FB_DRV_OK(call)                                                                                      \
+  {                                                                                                          \
+    const CUresult r_ = (call);                                                                              \
+    if (r_ != CUDA_SUCCESS) {                                                                                \
+      fprintf(stderr, "faer_b200: %s failed (%d); look-ahead uses plain streams\n", #call, (int)r_);         \
+      return false;                                                                                          \
+    }                                                                                                        \
+  }
+  FB_DRV(cuDeviceGet)
+  FB_DRV(cuDeviceGetDevResource)
+  FB_DRV(cuDevSmResourceSplitByCount)
+  FB_DRV(cuDevResourceGenerateDesc)
+  FB_DRV(cuGreenCtxCreate)
+  FB_DRV(cuGreenCtxStreamCreate)
+  int dev = 0;
+  FB_CUDA_CHECK(cudaGetDevice(&dev));
+  FB_CUDA_CHECK(cudaFree(0));  // primary context up
+  CUdevice cudev;
+  FB_DRV_OK(p_cuDeviceGet(&cudev, dev));
+  CUdevResource all, grp[1], rem;
+  FB_DRV_OK(p_cuDeviceGetDevResource(cudev, &all, CU_DEV_RESOURCE_TYPE_SM));
+  unsigned int ngrp = 1;
+  FB_DRV_OK(p_cuDevSmResourceSplitByCount(grp, &ngrp, &all, &rem, 0, (unsigned int)want));
+  if (ngrp < 1 || rem.type != CU_DEV_RESOURCE_TYPE_SM || rem.sm.smCount == 0) {
+    fprintf(stderr, "faer_b200: SM split produced no remainder; look-ahead uses plain streams\n");
+    return false;
+  }
+  CUdevResourceDesc d_panel, d_main;
+  FB_DRV_OK(p_cuDevResourceGenerateDesc(&d_panel, &grp[0], 1));
+  FB_DRV_OK(p_cuDevResourceGenerateDesc(&d_main, &rem, 1));
+  CUgreenCtx g_panel, g_main;
+  FB_DRV_OK(p_cuGreenCtxCreate(&g_panel, d_panel, cudev, CU_GREEN_CTX_DEFAULT_STREAM));
+  FB_DRV_OK(p_cuGreenCtxCreate(&g_main, d_main, cudev, CU_GREEN_CTX_DEFAULT_STREAM));
+  int lo = 0, hi = 0;
+  FB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CUstream s_panel, s_main, s_urgent;
+  FB_DRV_OK(p_cuGreenCtxStreamCreate(&s_panel, g_panel, CU_STREAM_NON_BLOCKING, hi));
+  FB_DRV_OK(p_cuGreenCtxStreamCreate(&s_main, g_main, CU_STREAM_NON_BLOCKING, lo));
+  FB_DRV_OK(p_cuGreenCtxStreamCreate(&s_urgent, g_main, CU_STREAM_NON_BLOCKING, hi));
+#undef FB_DRV
+#undef FB_DRV_OK
+  g_green_panel = (cudaStream_t)s_panel;
+  g_green_main = (cudaStream_t)s_main;
+  g_green_urgent = (cudaStream_t)s_urgent;
+  g_green_panel_sms = (int)grp[0].sm.smCount;
+  if (getenv("FAER_B200_VERBOSE"))
+    fprintf(stderr, "faer_b200: SM partition: %u SMs for the panel chain, %u for trailing updates\n", grp[0].sm.smCount,
+            rem.sm.smCount);
+  g_green_state = 1;
+  return true;
+}
+
 i64 lookahead_min_n() {
   static i64 v = -1;
   if (v < 0) {
@@ -158,6 +246,114 @@ void dist_finalize() {
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// Single-GPU right-looking block-column LLT on a partitioned GPU (green contexts, see above). Three streams:
+//   sp  panel partition            : Cholesky of the diagonal block (the serial potf2 / small-TRSM / small-SYRK chain)
+//   su  update partition, urgent   : update of block column k+1 with panel k, then the panel solve below the diagonal
+//   sm  update partition, bulk     : update of block columns k+2.. with panel k (column k+2 first: it is the next urgent one)
+// Per-element update order is k = 0, 1, ... as in every other driver, so the factor is bit-identical to theirs.
+// -----------------------------------------------------------------------------------------------------------------
+static LltResult llt_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, double reg_delta, double reg_eps) {
+  LltResult res{true, 0, 0};
+  cudaStream_t sp = g_green_panel, su = g_green_urgent, sm = g_green_main;
+  const bool trace = getenv("FAER_B200_TRACE") != nullptr;  // dev aid: print the event timeline of the three streams
+  const unsigned evf = trace ? cudaEventDefault : cudaEventDisableTiming;
+  cudaEvent_t ev_start;
+  FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start, evf));
+  FB_CUDA_CHECK(cudaEventRecord(ev_start, current_stream()));
+  FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_start, 0));
+  FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_start, 0));
+  FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
+  const i64 nblk = nblocks(n, nb);
+  long long* d_info = (long long*)ws_alloc(4 * sizeof(long long));
+  long long h_info[2] = {-1, 0};
+  FB_CUDA_CHECK(cudaMemcpyAsync(d_info, h_info, sizeof(h_info), cudaMemcpyHostToDevice, sp));
+  std::vector<cudaEvent_t> ev_panel((size_t)nblk), ev_diag((size_t)nblk), ev_ready((size_t)nblk), ev_first((size_t)nblk);
+  for (i64 k = 0; k < nblk; ++k) {
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_panel[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_diag[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ready[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_first[(size_t)k], evf));
+  }
+  auto factor_diag = [&](i64 k) {  // on sp
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0);
+    VD diag{A + k0 * ld + k0, kb, kb, 1, ld};
+    llt_cholesky_device_f64(sp, diag, reg_delta, reg_eps, d_info, k0);
+    FB_CUDA_CHECK(cudaEventRecord(ev_diag[(size_t)k], sp));
+  };
+  auto solve_below = [&](i64 k) {  // on su
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_diag[(size_t)k], 0));
+    if (rows > kb) {
+      VD diag{A + k0 * ld + k0, kb, kb, 1, ld};
+      VD below{A + k0 * ld + k0 + kb, rows - kb, kb, 1, ld};
+      solve_lower_triangular_in_place_f64(su, cv(diag), false, below.t());
+    }
+    FB_CUDA_CHECK(cudaEventRecord(ev_panel[(size_t)k], su));
+  };
+  auto update_block_col = [&](cudaStream_t st, i64 k, i64 j) {
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0);
+    const i64 j0 = j * nb, jb = std::min(nb, n - j0);
+    VCD Wj{A + k0 * ld + j0, jb, kb, 1, ld};  // rows of block j in panel k
+    VD djj{A + j0 * ld + j0, jb, jb, 1, ld};
+    gemm_f64(st, djj, TRI_LOWER, 1, Wj, RECT, Wj.t(), RECT, -1.0);
+    const i64 below = n - j0 - jb;
+    if (below > 0) {
+      VCD Wb{A + k0 * ld + j0 + jb, below, kb, 1, ld};
+      VD dbj{A + j0 * ld + j0 + jb, below, jb, 1, ld};
+      gemm_f64(st, dbj, 1, Wb, Wj.t(), -1.0);
+    }
+  };
+  factor_diag(0);
+  solve_below(0);
+  for (i64 k = 0; k < nblk; ++k) {
+    const i64 kn = k + 1;
+    if (kn < nblk) {
+      // su already holds ev_panel[k] in stream order; column kn has its updates 0..k-1 once bulk step k-1 did its first column
+      if (k >= 1) FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_first[(size_t)(k - 1)], 0));
+      update_block_col(su, k, kn);
+      FB_CUDA_CHECK(cudaEventRecord(ev_ready[(size_t)kn], su));
+      FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_ready[(size_t)kn], 0));
+      factor_diag(kn);
+      solve_below(kn);
+    }
+    FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_panel[(size_t)k], 0));
+    for (i64 j = k + 2; j < nblk; ++j) {
+      update_block_col(sm, k, j);
+      if (j == k + 2) FB_CUDA_CHECK(cudaEventRecord(ev_first[(size_t)k], sm));
+    }
+  }
+  FB_CUDA_CHECK(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, sp));
+  FB_CUDA_CHECK(cudaStreamSynchronize(sp));
+  FB_CUDA_CHECK(cudaStreamSynchronize(su));
+  FB_CUDA_CHECK(cudaStreamSynchronize(sm));
+  if (trace) {
+    auto at = [&](cudaEvent_t e) {
+      float ms = 0.f;
+      return cudaEventElapsedTime(&ms, ev_start, e) == cudaSuccess ? ms : -1.f;
+    };
+    fprintf(stderr, "LLT n=%lld nb=%lld timeline (ms since start): k: col-ready diag-done panel-done bulk-first\n", n, nb);
+    for (i64 k = 0; k < nblk; ++k)
+      fprintf(stderr, "  %3lld: %8.3f %8.3f %8.3f %8.3f\n", k, k ? at(ev_ready[(size_t)k]) : 0.f, at(ev_diag[(size_t)k]),
+              at(ev_panel[(size_t)k]), k + 2 < nblk ? at(ev_first[(size_t)k]) : -1.f);
+  }
+  for (i64 k = 0; k < nblk; ++k) {
+    cudaEventDestroy(ev_panel[(size_t)k]);
+    cudaEventDestroy(ev_diag[(size_t)k]);
+    cudaEventDestroy(ev_ready[(size_t)k]);
+    cudaEventDestroy(ev_first[(size_t)k]);
+  }
+  cudaEventDestroy(ev_start);
+  ws_free(d_info);
+  if (h_info[0] >= 0) {
+    res.ok = false;
+    res.non_positive_pivot_index = (size_t)h_info[0];
+  } else {
+    res.dynamic_regularization_count = (size_t)h_info[1];
+  }
+  return res;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // Distributed LLT. A_local: column-major n x local_cols (ld = ld_local >= n): the block columns this rank owns, in
 // increasing global order. On return the lower triangle of the global matrix holds L (strict upper part untouched).
 // Works for P == 1 too (no communicator needed) — the same code path the multi-GPU runs use, so results do not depend
@@ -173,6 +369,7 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   if (n == 0) return res;
   FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
   if (lookahead) ensure_streams();
+  if (lookahead && P == 1 && ensure_green_streams()) return llt_local_partitioned_f64(A_local, ld, n, nb, reg_delta, reg_eps);
   cudaStream_t sp = lookahead ? g_panel_stream : current_stream();
   cudaStream_t sm = lookahead ? g_main_stream : current_stream();
   const bool two_streams = sp != sm && lookahead;

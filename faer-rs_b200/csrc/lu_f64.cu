@@ -381,9 +381,21 @@ struct LuCtx {
 
 constexpr i64 PANEL_SMEM_BUDGET = 200 * 1024;
 
+// Upper bound on the CTAs of one cooperative panel launch. Fewer CTAs than SMs leave room for the trailing-update GEMM
+// of the look-ahead schedule to run next to the (latency-bound) panel; env FAER_B200_LU_PANEL_CTAS overrides.
+int panel_cta_cap(int num_sms) {
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("FAER_B200_LU_PANEL_CTAS");
+    cap = e ? atoi(e) : 0;
+  }
+  return cap > 0 ? std::min(cap, num_sms) : num_sms;
+}
+
 // widest window (<= PANEL_W) whose row slices (ceil(m / #CTAs) rows x (w|1) doubles) fit in shared memory
 int panel_width_for(const LuCtx& ctx, i64 m) {
-  const i64 rows = std::max<i64>(1, (m + ctx.num_sms - 1) / ctx.num_sms);
+  const int cap = panel_cta_cap(ctx.num_sms);
+  const i64 rows = std::max<i64>(1, (m + cap - 1) / cap);
   i64 w = PANEL_SMEM_BUDGET / (8 * rows) - 1;
   if (w > PANEL_W) w = PANEL_W;
   if (w >= 16) w = w / 16 * 16;
@@ -392,7 +404,7 @@ int panel_width_for(const LuCtx& ctx, i64 m) {
 
 void launch_panel(LuCtx& ctx, VD P, int* trans, bool want_plan) {
   const int m = (int)P.nrows, w = (int)P.ncols;
-  int G = (int)std::min<i64>(ctx.num_sms, (m + 63) / 64);
+  int G = (int)std::min<i64>(panel_cta_cap(ctx.num_sms), (m + 63) / 64);
   if (G < 1) G = 1;
   int rows_per_cta = (m + G - 1) / G;
   size_t smem = (size_t)rows_per_cta * (size_t)(w | 1) * sizeof(double);

@@ -73,9 +73,21 @@ __device__ __forceinline__ void reduce_partials(const T* part, int G, T (&out)[N
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int v = 0; v < NV; ++v) out[v] = T(0);
-  for (int b = lane; b < G; b += 32) {
+  // 160 CTAs per round: five predicated records per lane, all loads issued before the first use (one L2 round trip
+  // instead of five dependent ones)
+  for (int b0 = 0; b0 < G; b0 += 160) {
+    T rec[5][NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) out[v] += t_ldcg(&part[(i64)b * PANEL_NV + v]);
+    for (int u = 0; u < 5; ++u) {
+      const int b = b0 + lane + 32 * u;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) rec[u][v] = b < G ? t_ldcg(&part[(i64)b * PANEL_NV + v]) : T(0);
+    }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) out[v] += rec[u][v];
+    }
   }
 #pragma unroll
   for (int v = 0; v < NV; ++v) out[v] = warp_sum(out[v]);

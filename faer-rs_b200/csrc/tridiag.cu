@@ -166,18 +166,23 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(T* A, i64 cs, in
             for (int g = (jb & ~31) + rl; g < n; g += TR) {
               if (g < jb) continue;
               const T xi = x_s[g - gb], ui = u_s[g - gb], wi = w_s[g - gb];
+              // all loads of the row first (independent, in flight together), then the update, then the stores
+              T a[TD_CW];
 #pragma unroll
-              for (int c = 0; c < TD_CW; ++c) {
-                if (c < ncg && g >= jb + c) {
-                  T a = t_ldcg(&Ac[(i64)c * cs + g]);
-                  if (pend) {
-                    a = fma(-wj[c], ui, a);
-                    a = fma(-uj[c], wi, a);
-                    Ac[(i64)c * cs + g] = a;
-                  }
-                  if (g > jb + c) acc[c] = fma(a, xi, acc[c]);
+              for (int c = 0; c < TD_CW; ++c) a[c] = (c < ncg && g >= jb + c) ? t_ldcg(&Ac[(i64)c * cs + g]) : T(0);
+              if (pend) {
+#pragma unroll
+                for (int c = 0; c < TD_CW; ++c) {
+                  a[c] = fma(-wj[c], ui, a[c]);
+                  a[c] = fma(-uj[c], wi, a[c]);
                 }
+#pragma unroll
+                for (int c = 0; c < TD_CW; ++c)
+                  if (c < ncg && g >= jb + c) Ac[(i64)c * cs + g] = a[c];
               }
+#pragma unroll
+              for (int c = 0; c < TD_CW; ++c)
+                if (c < ncg && g > jb + c) acc[c] = fma(a[c], xi, acc[c]);
             }
 #pragma unroll
             for (int c = 0; c < TD_CW; ++c) {
