@@ -11,8 +11,8 @@
 // 3 * 8 B * (n-k)^2) with two global dependencies per column, so the whole column loop is one
 // persistent cooperative kernel (1 CTA per SM) with exactly TWO grid barriers per column:
 //   pass 1 (CTA = contiguous range of COLUMNS, all rows): the vectors u, u_prev, z live in shared memory; each thread
-//     streams rows of a group of 8 columns: a -= u_prev*y_j + z*v_j ; store ; acc_j += u*a. Column dots are CTA-local,
-//     so y_j, the updated row entry A12_j and its contribution to |A12|^2 and <y, A12> need no cross-CTA traffic;
+//     streams a group of 4 columns, 4 rows x 4 columns per iteration: a -= u_prev*y_j + z*v_j ; store ; acc_j += u*a.
+//     Column dots are CTA-local, so y_j, the updated row entry A12_j and its contribution to |A12|^2 and <y, A12> need no cross-CTA traffic;
 //   barrier; every CTA reduces the 7 published partials in a fixed order and forms the right reflector scalars;
 //   pass 2 (CTA = strip of ROWS, all columns): z_i = sum_j A22[i, j] * A12_j is CTA-local per row; the strip owner
 //     finishes z_i (fix-up formula), forms the next column  A[i, k+1] - u_i*y_{k+1} - z_i  (the pending update applied
@@ -31,7 +31,8 @@ namespace fb {
 namespace {
 
 constexpr int BD_THREADS = 512;
-constexpr int BD_CW = 8;       // columns per pass-1 group
+constexpr int BD_CW = 4;       // columns per pass-1 group
+constexpr int BD_RB = 4;       // rows per pass-1 iteration and thread
 constexpr int BD_CH = 8192;    // rows (pass 1) / columns (pass 2) resident in shared memory per chunk
 constexpr int BD_PC = 64;      // columns finalised per batch
 constexpr int BD_NW = BD_THREADS / 32;
@@ -174,31 +175,41 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bidiag_kernel(T* A, i64 cs, int
                 if (c < ncg) A[(i64)(jb + c) * cs + (k - 1)] = vv[c];  // v_ess of row k-1 goes to its final place
             }
             T* Ac = A + (i64)jb * cs;
-            for (int g = ch0 + rl; g < ch1; g += TR) {
-              if (g < k) continue;
-              const T uu = u_s[g - ch0];
-              T a[BD_CW];
+            // BD_RB rows x BD_CW columns per iteration: all BD_RB * BD_CW loads are issued before the first use, so a
+            // thread keeps 16 independent 8-byte loads in flight (the HBM stream needs > 40 KB in flight per SM)
+            for (int g0 = ch0 + rl; g0 < ch1; g0 += BD_RB * TR) {
+              T a[BD_RB][BD_CW];
 #pragma unroll
-              for (int c = 0; c < BD_CW; ++c)
-                if (c < ncg) a[c] = t_ldcg(&Ac[(i64)c * cs + g]);
-              if (pend) {
-                const T pp = up_s[g - ch0], zz = z_s[g - ch0];
+              for (int r = 0; r < BD_RB; ++r) {
+                const int g = g0 + r * TR;
+                const bool rowon = g < ch1 && g >= k;
 #pragma unroll
-                for (int c = 0; c < BD_CW; ++c) {
-                  a[c] = fma(-pp, yv[c], a[c]);
-                  a[c] = fma(-zz, vv[c], a[c]);
-                }
+                for (int c = 0; c < BD_CW; ++c) a[r][c] = (rowon && c < ncg) ? t_ldcg(&Ac[(i64)c * cs + g]) : T(0);
               }
-              if (g == k) {
 #pragma unroll
-                for (int c = 0; c < BD_CW; ++c)
-                  if (c < ncg) a12t[jb + c - cb] = a[c];
-              } else {
+              for (int r = 0; r < BD_RB; ++r) {
+                const int g = g0 + r * TR;
+                if (g >= ch1 || g < k) continue;
+                const T uu = u_s[g - ch0];
+                if (pend) {
+                  const T pp = up_s[g - ch0], zz = z_s[g - ch0];
 #pragma unroll
-                for (int c = 0; c < BD_CW; ++c) {
-                  if (c < ncg) {
-                    if (pend) Ac[(i64)c * cs + g] = a[c];
-                    acc[c] = fma(uu, a[c], acc[c]);
+                  for (int c = 0; c < BD_CW; ++c) {
+                    a[r][c] = fma(-pp, yv[c], a[r][c]);
+                    a[r][c] = fma(-zz, vv[c], a[r][c]);
+                  }
+                }
+                if (g == k) {
+#pragma unroll
+                  for (int c = 0; c < BD_CW; ++c)
+                    if (c < ncg) a12t[jb + c - cb] = a[r][c];
+                } else {
+#pragma unroll
+                  for (int c = 0; c < BD_CW; ++c) {
+                    if (c < ncg) {
+                      if (pend) Ac[(i64)c * cs + g] = a[r][c];
+                      acc[c] = fma(uu, a[r][c], acc[c]);
+                    }
                   }
                 }
               }
@@ -308,8 +319,17 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bidiag_kernel(T* A, i64 cs, int
         __syncthreads();
         if (valid) {
           const T* Ar = A + (i64)(k + 1 + cc0) * cs + g;
-#pragma unroll 8
-          for (int jj = ph; jj < cn; jj += P) acc = fma(t_ldcg(&Ar[(i64)jj * cs]), z_s[jj], acc);
+          // 16 independent loads in flight per thread (fixed order of accumulation: deterministic)
+          int jj = ph;
+          for (; jj + 15 * P < cn; jj += 16 * P) {
+            T v[16];
+#pragma unroll
+            for (int q2 = 0; q2 < 16; ++q2) v[q2] = t_ldcg(&Ar[(i64)(jj + q2 * P) * cs]);
+#pragma unroll
+            for (int q2 = 0; q2 < 16; ++q2) acc = fma(v[q2], z_s[jj + q2 * P], acc);
+          }
+#pragma unroll 4
+          for (; jj < cn; jj += P) acc = fma(t_ldcg(&Ar[(i64)jj * cs]), z_s[jj], acc);
         }
       }
       red[ph * RS + rl] = acc;

@@ -483,6 +483,102 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
 // row swaps to ALL its other columns (left ones too: final L is fully permuted, LAPACK/faer convention), then
 // U_kj = L_kk^-1 A_kj and A_(k+1:, j) -= L_(k+1:, k) U_kj on its own block columns j > k.
 // -----------------------------------------------------------------------------------------------------------------
+// Single-GPU right-looking block-column LU on a partitioned GPU (green contexts; same stream roles as the LLT driver):
+//   sp  panel partition          : recursive panel LU of block column k+1 (cooperative pivot-search kernel + its glue)
+//   su  update partition, urgent : row swaps + U_k,k+1 = L_kk^-1 A_k,k+1 + trailing update of block column k+1
+//   sm  update partition, bulk   : the same for block columns k+2.. (k+2 first) and the row swaps of the left columns
+// The panel kernel is latency-bound (one grid barrier per column) and, as a cooperative launch, could not start while
+// trailing-update CTAs occupied every SM; on its own partition it overlaps with the GEMMs completely.
+static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_trans) {
+  cudaStream_t sp = g_green_panel, su = g_green_urgent, sm = g_green_main;
+  const bool trace = getenv("FAER_B200_TRACE") != nullptr;
+  const unsigned evf = trace ? cudaEventDefault : cudaEventDisableTiming;
+  cudaEvent_t ev_start;
+  FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start, evf));
+  FB_CUDA_CHECK(cudaEventRecord(ev_start, current_stream()));
+  FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_start, 0));
+  FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_start, 0));
+  FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
+  const i64 nblk = nblocks(n, nb);
+  LuWorkspace* wp = lu_ws_create(sp, nb, g_green_panel_sms);
+  LuWorkspace* wu = lu_ws_create(su, nb);
+  LuWorkspace* wm = lu_ws_create(sm, nb);
+  std::vector<cudaEvent_t> ev_panel((size_t)nblk), ev_ready((size_t)nblk), ev_first((size_t)nblk);
+  for (i64 k = 0; k < nblk; ++k) {
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_panel[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ready[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_first[(size_t)k], evf));
+  }
+  auto factor_panel = [&](i64 k) {  // on sp
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    VD panel{A + k0 * ld + k0, rows, kb, 1, ld};
+    lu_factor_window_f64(wp, panel, 0, kb, d_trans + k0);
+    FB_CUDA_CHECK(cudaEventRecord(ev_panel[(size_t)k], sp));
+  };
+  // swaps (+ TRSM / GEMM if `right`) of step k on the columns [c0, c1)
+  auto update_cols = [&](LuWorkspace* w, cudaStream_t st, i64 k, i64 c0, i64 c1, bool right) {
+    if (c1 <= c0) return;
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    VD cols{A + c0 * ld + k0, rows, c1 - c0, 1, ld};
+    lu_apply_transpositions_f64(w, cols, d_trans + k0, kb);
+    if (right) {
+      VCD L11{A + k0 * ld + k0, kb, kb, 1, ld};
+      VD top = cols.sub(0, 0, kb, c1 - c0);
+      solve_lower_triangular_in_place_f64(st, L11, true, top);
+      if (rows > kb) {
+        VCD L21{A + k0 * ld + k0 + kb, rows - kb, kb, 1, ld};
+        gemm_f64(st, cols.sub(kb, 0, rows - kb, c1 - c0), 1, L21, cv(top), -1.0);
+      }
+    }
+  };
+  factor_panel(0);
+  for (i64 k = 0; k < nblk; ++k) {
+    const i64 k0 = k * nb, kb = std::min(nb, n - k0);
+    const i64 kn = k + 1;
+    if (kn < nblk) {
+      const i64 c0 = kn * nb, c1 = std::min(n, c0 + nb);
+      FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_panel[(size_t)k], 0));
+      if (k >= 1) FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_first[(size_t)(k - 1)], 0));
+      update_cols(wu, su, k, c0, c1, true);
+      FB_CUDA_CHECK(cudaEventRecord(ev_ready[(size_t)kn], su));
+      FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_ready[(size_t)kn], 0));
+      factor_panel(kn);
+    }
+    FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_panel[(size_t)k], 0));
+    const i64 c2 = (k + 2) * nb;
+    if (c2 < n) {
+      const i64 c3 = std::min(n, c2 + nb);
+      update_cols(wm, sm, k, c2, c3, true);  // the next urgent column first
+      FB_CUDA_CHECK(cudaEventRecord(ev_first[(size_t)k], sm));
+      update_cols(wm, sm, k, c3, n, true);
+    }
+    update_cols(wm, sm, k, 0, k0, false);  // the left columns only receive the row swaps
+    (void)kb;
+  }
+  FB_CUDA_CHECK(cudaStreamSynchronize(sp));
+  FB_CUDA_CHECK(cudaStreamSynchronize(su));
+  FB_CUDA_CHECK(cudaStreamSynchronize(sm));
+  if (trace) {
+    auto at = [&](cudaEvent_t e) {
+      float ms = 0.f;
+      return cudaEventElapsedTime(&ms, ev_start, e) == cudaSuccess ? ms : -1.f;
+    };
+    fprintf(stderr, "LU n=%lld nb=%lld timeline (ms since start): k: col-ready panel-done bulk-first\n", n, nb);
+    for (i64 k = 0; k < nblk; ++k)
+      fprintf(stderr, "  %3lld: %8.3f %8.3f %8.3f\n", k, k ? at(ev_ready[(size_t)k]) : 0.f, at(ev_panel[(size_t)k]),
+              (k + 2) * nb < n ? at(ev_first[(size_t)k]) : -1.f);
+  }
+  for (i64 k = 0; k < nblk; ++k) {
+    cudaEventDestroy(ev_panel[(size_t)k]);
+    cudaEventDestroy(ev_ready[(size_t)k]);
+    cudaEventDestroy(ev_first[(size_t)k]);
+  }
+  cudaEventDestroy(ev_start);
+  lu_ws_destroy(wm);
+  lu_ws_destroy(wu);
+  lu_ws_destroy(wp);
+}
+
 size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, long long* perm_inv, int lookahead) {
   require_device();
   // `lookahead` bit 0: two-stream look-ahead; bit 1: purely local run (ignore the communicator even if one exists)
@@ -493,6 +589,22 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
   size_t n_trans = 0;
   if (n == 0) return 0;
   FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
+  if (lookahead && P == 1 && ensure_green_streams()) {
+    int* d_trans = (int*)ws_alloc((size_t)n * sizeof(int));
+    lu_local_partitioned_f64(A_local, ld, n, nb, d_trans);
+    std::vector<int> h_trans((size_t)n);
+    FB_CUDA_CHECK(cudaMemcpy(h_trans.data(), d_trans, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    ws_free(d_trans);
+    for (i64 i = 0; i < n; ++i) {
+      const int t = h_trans[(size_t)i];
+      if (t != 0) {
+        std::swap(perm_fwd[i], perm_fwd[i + t]);
+        ++n_trans;
+      }
+    }
+    for (i64 i = 0; i < n; ++i) perm_inv[perm_fwd[i]] = i;
+    return n_trans;
+  }
   if (lookahead) ensure_streams();
   cudaStream_t sp = lookahead ? g_panel_stream : current_stream();
   cudaStream_t sm = lookahead ? g_main_stream : current_stream();

@@ -50,7 +50,7 @@ void lu_solve_in_place_f64(cudaStream_t stream, VCD L, VCD U, const long long* p
 
 // workspace-based LU building blocks (used by dist.cu); all work is enqueued on the stream given at creation
 struct LuWorkspace;
-LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window);
+LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window, int sm_limit = 0);
 void lu_ws_destroy(LuWorkspace* w);
 void lu_factor_window_f64(LuWorkspace* w, VD A, i64 start, i64 end, int* d_trans);
 void lu_apply_transpositions_f64(LuWorkspace* w, VD cols, const int* d_trans, i64 n);

@@ -569,13 +569,15 @@ struct LuWorkspace {
   i64 max_window;
 };
 
-LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window) {
+LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window, int sm_limit) {
   LuWorkspace* w = new LuWorkspace();
   LuCtx& ctx = w->ctx;
   ctx.st = stream;
   int dev = 0;
   FB_CUDA_CHECK(cudaGetDevice(&dev));
   FB_CUDA_CHECK(cudaDeviceGetAttribute(&ctx.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  // a stream bound to an SM partition (green context): the cooperative panel grid must fit the partition
+  if (sm_limit > 0 && sm_limit < ctx.num_sms) ctx.num_sms = sm_limit;
   ctx.recursion_threshold = 16;
   const int G = ctx.num_sms;
   w->max_window = max_window;

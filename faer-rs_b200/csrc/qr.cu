@@ -153,15 +153,28 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(T* __restrict__ A,
 
     // ---- phase B: deterministic reduction over the CTAs (fixed order), then the reflector scalars ----
     {
-      const int v = tid & 63, q = tid >> 6;  // 4 partial sums per value
-      T s = T(0);
-      if (v < QR_NV - 1)
-        for (int b = q; b < G; b += 4) s += t_ldcg(&sc.part[((i64)par * G + b) * QR_NV + v]);
-      __syncthreads();  // red[] reuse
-      if (v < QR_NV - 1) red[q][v] = s;
-      __syncthreads();
-      if (tid < QR_NV - 1) tot[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+      // warp `rg` reduces the values v = rg, rg + 8, ... (QR_NV - 1 = 35 <= 40 values over 8 warps); every lane loads
+      // the records of the CTAs lane, lane + 32, ... (G <= 160, checked on the host): all 25 loads of a lane are issued
+      // before the first use, i.e. ONE L2 round trip per column instead of a chain of G / 4 dependent ones.
+      T rec[5][5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int v = rg + 8 * i;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int b = lane + 32 * u;
+          rec[i][u] = (v < QR_NV - 1 && b < G) ? t_ldcg(&sc.part[((i64)par * G + b) * QR_NV + v]) : T(0);
+        }
+      }
       if (tid < w) rowj[tid] = t_ldcg(&sc.rowv[par * QR_PW + tid]);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int v = rg + 8 * i;
+        T s = ((rec[i][0] + rec[i][1]) + (rec[i][2] + rec[i][3])) + rec[i][4];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0 && v < QR_NV - 1) tot[v] = s;
+      }
       __syncthreads();
     }
     // make_householder (householder.rs:59-107), evaluated redundantly by every thread
@@ -287,7 +300,7 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
   int dev = 0, num_sms = 0;
   FB_CUDA_CHECK(cudaGetDevice(&dev));
   FB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  const int Gmax = num_sms;
+  const int Gmax = std::min(num_sms, 160);  // the panel kernel's record reduction covers <= 160 CTAs
   // scratch
   const size_t part_elems = (size_t)2 * Gmax * QR_NV, rowv_elems = (size_t)2 * QR_PW;
   char* scb = (char*)ws_alloc((part_elems + rowv_elems + QR_PW) * sizeof(T) + 64);

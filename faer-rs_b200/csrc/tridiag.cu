@@ -33,7 +33,8 @@ namespace fb {
 namespace {
 
 constexpr int TD_THREADS = 512;
-constexpr int TD_CW = 8;      // columns per pass-1 group
+constexpr int TD_CW = 4;      // columns per pass-1 group
+constexpr int TD_RB = 4;      // rows per pass-1 iteration and thread
 constexpr int TD_CH = 8192;   // rows resident in shared memory (n <= TD_CH)
 constexpr int TD_PC = 64;     // columns finalised per batch
 constexpr int TD_NW = TD_THREADS / 32;
@@ -163,26 +164,36 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(T* A, i64 cs, in
               acc[c] = T(0);
             }
             T* Ac = A + (i64)jb * cs;
-            for (int g = (jb & ~31) + rl; g < n; g += TR) {
-              if (g < jb) continue;
-              const T xi = x_s[g - gb], ui = u_s[g - gb], wi = w_s[g - gb];
-              // all loads of the row first (independent, in flight together), then the update, then the stores
-              T a[TD_CW];
+            // TD_RB rows x TD_CW columns per iteration: all loads first (16 independent 8-byte loads in flight per
+            // thread), then the update, then the stores
+            for (int g0 = (jb & ~31) + rl; g0 < n; g0 += TD_RB * TR) {
+              T a[TD_RB][TD_CW];
 #pragma unroll
-              for (int c = 0; c < TD_CW; ++c) a[c] = (c < ncg && g >= jb + c) ? t_ldcg(&Ac[(i64)c * cs + g]) : T(0);
-              if (pend) {
+              for (int r = 0; r < TD_RB; ++r) {
+                const int g = g0 + r * TR;
 #pragma unroll
-                for (int c = 0; c < TD_CW; ++c) {
-                  a[c] = fma(-wj[c], ui, a[c]);
-                  a[c] = fma(-uj[c], wi, a[c]);
+                for (int c = 0; c < TD_CW; ++c)
+                  a[r][c] = (g < n && c < ncg && g >= jb + c) ? t_ldcg(&Ac[(i64)c * cs + g]) : T(0);
+              }
+#pragma unroll
+              for (int r = 0; r < TD_RB; ++r) {
+                const int g = g0 + r * TR;
+                if (g >= n || g < jb) continue;
+                const T xi = x_s[g - gb], ui = u_s[g - gb], wi = w_s[g - gb];
+                if (pend) {
+#pragma unroll
+                  for (int c = 0; c < TD_CW; ++c) {
+                    a[r][c] = fma(-wj[c], ui, a[r][c]);
+                    a[r][c] = fma(-uj[c], wi, a[r][c]);
+                  }
+#pragma unroll
+                  for (int c = 0; c < TD_CW; ++c)
+                    if (c < ncg && g >= jb + c) Ac[(i64)c * cs + g] = a[r][c];
                 }
 #pragma unroll
                 for (int c = 0; c < TD_CW; ++c)
-                  if (c < ncg && g >= jb + c) Ac[(i64)c * cs + g] = a[c];
+                  if (c < ncg && g > jb + c) acc[c] = fma(a[r][c], xi, acc[c]);
               }
-#pragma unroll
-              for (int c = 0; c < TD_CW; ++c)
-                if (c < ncg && g > jb + c) acc[c] = fma(a[c], xi, acc[c]);
             }
 #pragma unroll
             for (int c = 0; c < TD_CW; ++c) {
@@ -218,8 +229,16 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(T* A, i64 cs, in
           T acc = T(0);
           if (valid) {
             const T* Ar = A + g;
-#pragma unroll 8
-            for (int j = k + 2 + ph; j <= g; j += P) acc = fma(t_ldcg(&Ar[(i64)j * cs]), x_s[j - gb], acc);
+            int j = k + 2 + ph;
+            for (; j + 15 * P <= g; j += 16 * P) {  // 16 independent loads in flight, fixed accumulation order
+              T v[16];
+#pragma unroll
+              for (int q2 = 0; q2 < 16; ++q2) v[q2] = t_ldcg(&Ar[(i64)(j + q2 * P) * cs]);
+#pragma unroll
+              for (int q2 = 0; q2 < 16; ++q2) acc = fma(v[q2], x_s[j + q2 * P - gb], acc);
+            }
+#pragma unroll 4
+            for (; j <= g; j += P) acc = fma(t_ldcg(&Ar[(i64)j * cs]), x_s[j - gb], acc);
           }
           if (sub > 0) __syncthreads();
           red[ph * RS + rl] = acc;

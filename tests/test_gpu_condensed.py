@@ -5,7 +5,7 @@ Tolerances (written here). What is pinned tightly is what the
 reconstruction identity U^H A V == B (resp. Q^H A Q == T) to 64 * n * eps * max|A|, plus the invariants (singular values /
 eigenvalues) to the same bound. The ENTRIES of a condensed form are not forward-stable functions of A (two backward-stable
 Householder reductions with different summation orders drift apart like a Lanczos recurrence: measured 1e-13 at n = 64,
-2e-10 at n = 300, 3e-10 at n = 700 in f64), so the elementwise comparison with the oracle uses the tight bound only for
+2e-10 at n = 300, 3e-10 at n = 700 in f64), so the elementwise comparison with the oracle uses 1024 * n * eps * max|A| for
 n <= 64 and a drift bound n^2.5 * eps * 16 * max|A| beyond (f64; it still catches sign / convention / indexing errors,
 which are O(1)); f32 compares entries only for n <= 64.
 """
@@ -32,7 +32,7 @@ def _entry_tol(n, dtype, A):
     eps = np.finfo(dtype).eps
     amax = max(1.0, float(np.abs(A).max()))
     if n <= 64:
-        return 64 * n * eps * amax
+        return 1024 * n * eps * amax
     if dtype == np.float32:
         return None
     return 16 * n ** 2.5 * eps * amax
