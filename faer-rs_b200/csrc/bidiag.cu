@@ -391,13 +391,13 @@ void bidiag_in_place(cudaStream_t st, View<T> A, View<T> Hl, View<T> Hr) {
   FB_ASSERT(m <= (i64)BD_THREADS * G - 64 && n < (1ll << 30), "bidiag_in_place: matrix too tall for the row-strip pass");
 
   const size_t elems = (size_t)2 * m + 2 * n + (size_t)2 * G * BD_NV + 8;
-  char* buf = (char*)ws_alloc(elems * sizeof(T) + 64);
+  char* buf = (char*)ws_alloc(elems * sizeof(T) + 96);
   BdScratch<T> sc;
   sc.ubuf = (T*)buf;
   sc.zbuf = sc.ubuf + m;
   sc.ybuf = sc.zbuf + m;
   sc.a12 = sc.ybuf + n;
-  sc.part = sc.a12 + n;
+  sc.part = (T*)(((uintptr_t)(sc.a12 + n) + 15) & ~(uintptr_t)15);  // records are read as 16-byte vectors
   sc.head = sc.part + (size_t)2 * G * BD_NV;
   sc.bar = (unsigned long long*)(((uintptr_t)(sc.head + 8) + 15) & ~(uintptr_t)15);
   FB_CUDA_CHECK(cudaMemsetAsync(sc.bar, 0, 8, st));

@@ -159,7 +159,12 @@ static bool ensure_green_streams() {
   CUdevResource all, grp[1], rem;
   FB_DRV_OK(p_cuDeviceGetDevResource(cudev, &all, CU_DEV_RESOURCE_TYPE_SM));
   unsigned int ngrp = 1;
-  FB_DRV_OK(p_cuDevSmResourceSplitByCount(grp, &ngrp, &all, &rem, 0, (unsigned int)want));
+  // MAX_POTENTIAL_CLUSTER_SIZE: keep the panel group inside as few GPCs as possible so that a 16-CTA cluster fits
+  if (p_cuDevSmResourceSplitByCount(grp, &ngrp, &all, &rem, CU_DEV_SM_RESOURCE_SPLIT_MAX_POTENTIAL_CLUSTER_SIZE,
+                                    (unsigned int)want) != CUDA_SUCCESS) {
+    ngrp = 1;
+    FB_DRV_OK(p_cuDevSmResourceSplitByCount(grp, &ngrp, &all, &rem, 0, (unsigned int)want));
+  }
   if (ngrp < 1 || rem.type != CU_DEV_RESOURCE_TYPE_SM || rem.sm.smCount == 0) {
     fprintf(stderr, "faer_b200: SM split produced no remainder; look-ahead uses plain streams\n");
     return false;
@@ -188,6 +193,19 @@ static bool ensure_green_streams() {
   g_green_state = 1;
   return true;
 }
+
+// ---- host-resident input: stream the matrix through the factorization ------------------------------------------------
+// The C ABI accepts host pointers (the reference is a CPU library). Copy-in / factor / copy-out would leave the GPU idle
+// during 2 x 2.1 GB of PCIe traffic at n = 16384; instead the block columns are uploaded in order on their own stream
+// (only the part on / below the diagonal blocks: the strict upper triangle is never read), the right-looking driver
+// waits for column j only at its first touch, and every finished panel goes home on a third stream at once.
+struct LltHostPipe {
+  double* host;
+  i64 host_ld;
+  cudaStream_t s_d2h;
+  std::vector<cudaEvent_t> up;  // up[j]: block column j is resident on the device
+};
+static LltHostPipe* g_llt_pipe = nullptr;
 
 i64 lookahead_min_n() {
   static i64 v = -1;
@@ -369,7 +387,9 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   if (n == 0) return res;
   FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
   if (lookahead) ensure_streams();
-  if (lookahead && P == 1 && ensure_green_streams()) return llt_local_partitioned_f64(A_local, ld, n, nb, reg_delta, reg_eps);
+  LltHostPipe* pipe = (P == 1 && lookahead) ? g_llt_pipe : nullptr;  // host-resident matrix streamed through (see below)
+  if (!pipe && lookahead && P == 1 && ensure_green_streams())
+    return llt_local_partitioned_f64(A_local, ld, n, nb, reg_delta, reg_eps);
   cudaStream_t sp = lookahead ? g_panel_stream : current_stream();
   cudaStream_t sm = lookahead ? g_main_stream : current_stream();
   const bool two_streams = sp != sm && lookahead;
@@ -413,10 +433,17 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
     }
     if (P > 1) FB_NCCL_CHECK(g_nccl.Broadcast(Wk, Wk, (size_t)rows * kb, ncclDouble, owner, g_comm, sp));
     FB_CUDA_CHECK(cudaEventRecord(ev_bcast[(size_t)k], sp));
+    if (pipe) {  // block column k is final: send it home while the factorization goes on
+      FB_CUDA_CHECK(cudaStreamWaitEvent(pipe->s_d2h, ev_bcast[(size_t)k], 0));
+      FB_CUDA_CHECK(cudaMemcpy2DAsync(pipe->host + k0 * pipe->host_ld + k0, (size_t)pipe->host_ld * 8,
+                                      A_local + k0 * ld + k0, (size_t)ld * 8, (size_t)rows * 8, (size_t)kb,
+                                      cudaMemcpyDeviceToHost, pipe->s_d2h));
+    }
   };
 
   auto update_block_col = [&](cudaStream_t st, i64 k, i64 j) {
     // block column j (> k, owned by me) -= W_k[rows >= j0] * W_k[rows of block j]^T
+    if (pipe && k == 0) FB_CUDA_CHECK(cudaStreamWaitEvent(st, pipe->up[(size_t)j], 0));  // first touch of column j
     const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows_k = n - k0;
     const i64 j0 = j * nb, jb = std::min(nb, n - j0);
     const double* Wk = W[k & 1];
@@ -432,6 +459,7 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
     }
   };
 
+  if (pipe) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, pipe->up[0], 0));
   factor_and_bcast(0);
   for (i64 k = 0; k < nblk; ++k) {
     // trailing updates of step k need panel k
@@ -456,6 +484,7 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   FB_CUDA_CHECK(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, sp));
   FB_CUDA_CHECK(cudaStreamSynchronize(sp));
   if (two_streams) FB_CUDA_CHECK(cudaStreamSynchronize(sm));
+  if (pipe) FB_CUDA_CHECK(cudaStreamSynchronize(pipe->s_d2h));
   for (i64 k = 0; k < nblk; ++k) {
     cudaEventDestroy(ev_bcast[(size_t)k]);
     cudaEventDestroy(ev_used[(size_t)k]);
@@ -483,6 +512,37 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
 // row swaps to ALL its other columns (left ones too: final L is fully permuted, LAPACK/faer convention), then
 // U_kj = L_kk^-1 A_kj and A_(k+1:, j) -= L_(k+1:, k) U_kj on its own block columns j > k.
 // -----------------------------------------------------------------------------------------------------------------
+// LLT of a HOST column-major matrix (lower triangle), transfers overlapped with the factorization (see LltHostPipe).
+LltResult llt_host_pipelined_f64(double* hostA, i64 host_ld, i64 n, i64 nb, double reg_delta, double reg_eps) {
+  require_device();
+  static cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  if (!s_h2d) {
+    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+  }
+  const i64 nblk = nblocks(n, nb);
+  double* dA = (double*)ws_alloc((size_t)n * n * 8);
+  LltHostPipe pipe;
+  pipe.host = hostA;
+  pipe.host_ld = host_ld;
+  pipe.s_d2h = s_d2h;
+  pipe.up.resize((size_t)nblk);
+  for (i64 j = 0; j < nblk; ++j) {
+    const i64 j0 = j * nb, jb = std::min(nb, n - j0);
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&pipe.up[(size_t)j], cudaEventDisableTiming));
+    FB_CUDA_CHECK(cudaMemcpy2DAsync(dA + j0 * n + j0, (size_t)n * 8, hostA + j0 * host_ld + j0, (size_t)host_ld * 8,
+                                    (size_t)(n - j0) * 8, (size_t)jb, cudaMemcpyHostToDevice, s_h2d));
+    FB_CUDA_CHECK(cudaEventRecord(pipe.up[(size_t)j], s_h2d));
+  }
+  g_llt_pipe = &pipe;
+  LltResult r = dist_llt_f64(dA, n, n, nb, reg_delta, reg_eps, /*lookahead | local*/ 3);
+  g_llt_pipe = nullptr;
+  FB_CUDA_CHECK(cudaStreamSynchronize(s_h2d));
+  for (i64 j = 0; j < nblk; ++j) cudaEventDestroy(pipe.up[(size_t)j]);
+  ws_free(dA);
+  return r;
+}
+
 // Single-GPU right-looking block-column LU on a partitioned GPU (green contexts; same stream roles as the LLT driver):
 //   sp  panel partition          : recursive panel LU of block column k+1 (cooperative pivot-search kernel + its glue)
 //   su  update partition, urgent : row swaps + U_k,k+1 = L_kk^-1 A_k,k+1 + trailing update of block column k+1
@@ -501,6 +561,13 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
   FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
   const i64 nblk = nblocks(n, nb);
   LuWorkspace* wp = lu_ws_create(sp, nb, g_green_panel_sms);
+  if (!getenv("FAER_B200_NO_OFFLOAD")) lu_ws_set_big_stream(wp, su);  // big recursion nodes run on the update partition
+  {
+    // leaves on a thread-block cluster (DSMEM exchange) inside the panel partition; FAER_B200_LU_CLUSTER=0 disables
+    const char* e = getenv("FAER_B200_LU_CLUSTER");
+    const int want = e ? atoi(e) : 16;
+    if (want > 0) lu_ws_set_cluster(wp, std::min(want, g_green_panel_sms >= 16 ? 16 : 8));
+  }
   LuWorkspace* wu = lu_ws_create(su, nb);
   LuWorkspace* wm = lu_ws_create(sm, nb);
   std::vector<cudaEvent_t> ev_panel((size_t)nblk), ev_ready((size_t)nblk), ev_first((size_t)nblk);

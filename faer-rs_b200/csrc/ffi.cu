@@ -258,10 +258,19 @@ FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(FaerV0_24_MatMut A, Fa
     delta = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_delta);
   if (regularization.dynamic_regularization_epsilon)
     eps = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_epsilon);
-  Mat a(A, true, st);
-  LltResult r = llt_cholesky_in_place_f64(st, a.s.view<double>(), delta, eps,
-                                          LltParams{params.recursion_threshold, params.block_size});
-  finish_all(st, {&a.s});
+  LltResult r;
+  if (A.nrows > 0 && !is_device_pointer(A.ptr) && A.row_stride == 1 && A.col_stride >= (ptrdiff_t)A.nrows &&
+      (i64)A.nrows >= lookahead_min_n()) {
+    // host matrix: upload / factor / download pipelined block column by block column (dist.cu)
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    const i64 nb = lookahead_block() ? lookahead_block() : 1024;
+    r = llt_host_pipelined_f64((double*)A.ptr, (i64)A.col_stride, (i64)A.nrows, nb, delta, eps);
+  } else {
+    Mat a(A, true, st);
+    r = llt_cholesky_in_place_f64(st, a.s.view<double>(), delta, eps,
+                                  LltParams{params.recursion_threshold, params.block_size});
+    finish_all(st, {&a.s});
+  }
   FaerV0_24_LltStatus out;
   memset(&out, 0, sizeof(out));
   if (r.ok) {

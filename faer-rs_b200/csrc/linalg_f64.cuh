@@ -51,6 +51,8 @@ void lu_solve_in_place_f64(cudaStream_t stream, VCD L, VCD U, const long long* p
 // workspace-based LU building blocks (used by dist.cu); all work is enqueued on the stream given at creation
 struct LuWorkspace;
 LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window, int sm_limit = 0);
+void lu_ws_set_cluster(LuWorkspace* w, int ctas);  // leaves on a thread-block cluster of `ctas` CTAs (0 = off)
+void lu_ws_set_big_stream(LuWorkspace* w, cudaStream_t big);  // see lu_rec: offload target for large recursion nodes
 void lu_ws_destroy(LuWorkspace* w);
 void lu_factor_window_f64(LuWorkspace* w, VD A, i64 start, i64 end, int* d_trans);
 void lu_apply_transpositions_f64(LuWorkspace* w, VD cols, const int* d_trans, i64 n);
@@ -64,6 +66,10 @@ int dist_rank();
 int dist_nranks();
 // A_local: column-major n x (local columns), ld >= n; block column b (width nb) lives on rank b % P.
 LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta, double reg_eps, int lookahead);
+// LLT of a HOST column-major matrix with the PCIe transfers overlapped with the factorization (dist.cu)
+LltResult llt_host_pipelined_f64(double* hostA, i64 host_ld, i64 n, i64 nb, double reg_delta, double reg_eps);
+i64 lookahead_min_n();
+i64 lookahead_block();
 // Distributed P A = L U (square n x n). perm_fwd / perm_inv: HOST arrays of n int64 (identical on every rank).
 size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, long long* perm_inv, int lookahead);
 

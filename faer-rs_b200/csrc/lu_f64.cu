@@ -19,7 +19,10 @@
 //     of 64 transpositions into a net gather list (<= 128 affected rows), and the apply kernel moves all
 //     affected rows of a 32-column strip through shared memory with independent loads (full memory-level
 //     parallelism instead of a dependent swap chain).
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -318,6 +321,203 @@ __global__ void __launch_bounds__(PANEL_THREADS) lu_panel_kernel(double* __restr
   }
 }
 
+// ---- cluster variant of the panel kernel --------------------------------------------------------------------------
+// Same algorithm, but the CTAs form ONE thread-block cluster (8 portable, 16 opt-in) and the per-column exchange goes
+// through distributed shared memory: every CTA stores its candidate (value, row index, the row itself) into the
+// exchange buffer of EVERY CTA of the cluster, one hardware cluster barrier makes the stores visible, and the scan /
+// pivot-row fetch are local shared-memory reads. The grid-barrier version pays three dependent L2 round trips per
+// column (arrival counter, candidate records, winner row; ~4.6 us); here the exchange costs one cluster barrier.
+// The slices live in shared memory as before (<= ~190 KB per CTA), so the panel is narrower for tall matrices
+// (w in {64, 32, 16, 8} by height) and the host recursion supplies the rest (lu_rec).
+constexpr int CL_THREADS = 512;
+constexpr int CL_MAXC = 16;
+
+struct ClExchange {
+  double val[2][CL_MAXC];
+  long long idx[2][CL_MAXC];
+  double row[2][CL_MAXC][PANEL_W];
+  double diag[2][PANEL_W];
+};
+
+__global__ void __launch_bounds__(CL_THREADS) lu_panel_cluster_kernel(double* __restrict__ A, i64 rs, i64 cs, int m, int w,
+                                                                       int rows_per_cta, int* __restrict__ trans,
+                                                                       int* __restrict__ plan_rows,
+                                                                       int* __restrict__ plan_src,
+                                                                       int* __restrict__ plan_cnt) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  extern __shared__ double S[];  // [rows_per_cta][LD]
+  const int LD = w | 1;
+  __shared__ ClExchange X;
+  __shared__ double pr[PANEL_W];
+  __shared__ double dr[PANEL_W];
+  __shared__ double red_val[CL_THREADS / 32];
+  __shared__ long long red_idx[CL_THREADS / 32];
+  __shared__ long long s_piv;
+  __shared__ int s_wincta;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = rank * rows_per_cta;
+  const int nloc = max(0, min(rows_per_cta, m - r0));
+  const int ncol = min(w, m);
+
+  for (int r = tid; r < nloc; r += CL_THREADS) {
+    const double* src = A + (i64)(r0 + r) * rs;
+    double* dst = S + r * LD;
+#pragma unroll 8
+    for (int c = 0; c < w; ++c) dst[c] = src[(i64)c * cs];
+  }
+  double my_val = 0.0;
+  long long my_idx = -1;
+  __syncthreads();
+  for (int r = tid; r < nloc; r += CL_THREADS) {
+    const double v = fabs(S[r * LD + 0]);
+    if (v > 0.0 && cand_better(v, r0 + r, my_val, my_idx < 0 ? (1ll << 62) : my_idx)) {
+      my_val = v;
+      my_idx = r0 + r;
+    }
+  }
+  cluster.sync();  // every CTA of the cluster is resident and its exchange buffer may be written
+
+  for (int j = 0; j < ncol; ++j) {
+    const int par = j & 1;
+    // ---- (1) CTA-wide candidate ----
+    {
+      double v = my_val;
+      long long ix = my_idx < 0 ? (1ll << 62) : my_idx;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+        if (cand_better(ov, oi, v, ix)) {
+          v = ov;
+          ix = oi;
+        }
+      }
+      if (lane == 0) {
+        red_val[warp] = v;
+        red_idx[warp] = ix;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        v = lane < CL_THREADS / 32 ? red_val[lane] : 0.0;
+        ix = lane < CL_THREADS / 32 ? red_idx[lane] : (1ll << 62);
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+          const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+          if (cand_better(ov, oi, v, ix)) {
+            v = ov;
+            ix = oi;
+          }
+        }
+        if (lane == 0) {
+          red_val[0] = v;
+          red_idx[0] = ix;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- (2) publish to every CTA of the cluster: warp `warp` serves destination rank `warp` ----
+    {
+      const double bv = red_val[0];
+      const long long bi = red_idx[0];
+      if (warp < C) {
+        ClExchange* Xr = cluster.map_shared_rank(&X, warp);
+        if (lane == 0) {
+          Xr->val[par][rank] = bv;
+          Xr->idx[par][rank] = bi;
+        }
+        if (bv > 0.0) {
+          const int lr = (int)(bi - r0);
+          for (int c = lane; c < w; c += 32) Xr->row[par][rank][c] = S[lr * LD + c];
+        }
+        if (j >= r0 && j < r0 + nloc) {
+          const int lr = j - r0;
+          for (int c = lane; c < w; c += 32) Xr->diag[par][c] = S[lr * LD + c];
+        }
+      }
+    }
+    cluster.sync();
+    // ---- (3) winner (local scan of the C candidates), pivot row, old diagonal row ----
+    if (warp == 0) {
+      double v = lane < C ? X.val[par][lane] : 0.0;
+      long long ix = lane < C ? X.idx[par][lane] : (1ll << 62);
+      int wc = lane;
+      if (!(v > 0.0)) {
+        v = 0.0;
+        ix = (1ll << 62);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+        const int oc = __shfl_xor_sync(0xffffffffu, wc, off);
+        if (cand_better(ov, oi, v, ix)) {
+          v = ov;
+          ix = oi;
+          wc = oc;
+        }
+      }
+      if (lane == 0) {
+        s_piv = (v > 0.0) ? ix : (long long)j;  // all-zero / all-NaN column keeps imax = row (factor.rs:35-44)
+        s_wincta = (v > 0.0) ? wc : -1;
+      }
+    }
+    __syncthreads();
+    const int piv = (int)s_piv;
+    const int wincta = s_wincta;
+    for (int c = tid; c < w; c += CL_THREADS) {
+      const double d = X.diag[par][c];
+      dr[c] = d;
+      pr[c] = (piv != j) ? X.row[par][wincta][c] : d;
+    }
+    __syncthreads();
+    if (piv != j) {
+      if (piv >= r0 && piv < r0 + nloc)
+        for (int c = tid; c < w; c += CL_THREADS) S[(piv - r0) * LD + c] = dr[c];
+      if (j >= r0 && j < r0 + nloc)
+        for (int c = tid; c < w; c += CL_THREADS) S[(j - r0) * LD + c] = pr[c];
+    }
+    if (rank == 0 && tid == 0) trans[j] = piv - j;
+    __syncthreads();
+    // ---- (4) multipliers + rank-1 update; next column's local arg-max ----
+    const double inv = 1.0 / pr[j];
+    my_val = 0.0;
+    my_idx = -1;
+    for (int r = tid; r < nloc; r += CL_THREADS) {
+      if (r0 + r > j) {
+        double* row = S + r * LD;
+        const double l = row[j] * inv;
+        row[j] = l;
+        for (int c = j + 1; c < w; ++c) row[c] = fma(-l, pr[c], row[c]);
+        if (j + 1 < w) {
+          const double v = fabs(row[j + 1]);
+          if (v > 0.0 && cand_better(v, r0 + r, my_val, my_idx < 0 ? (1ll << 62) : my_idx)) {
+            my_val = v;
+            my_idx = r0 + r;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r < nloc; r += CL_THREADS) {
+    double* dstg = A + (i64)(r0 + r) * rs;
+    const double* srcs = S + r * LD;
+#pragma unroll 8
+    for (int c = 0; c < w; ++c) dstg[(i64)c * cs] = srcs[c];
+  }
+  if (plan_rows != nullptr && rank == 0) {
+    __shared__ int p_ids[2 * SWAP_GROUP], p_cur[2 * SWAP_GROUP];
+    __syncthreads();
+    __threadfence_block();
+    if (warp == 0) build_plan_warp(trans, 0, ncol, p_ids, p_cur, plan_rows, plan_src, plan_cnt, lane);
+  }
+  cluster.sync();  // no CTA may exit while its shared memory can still be addressed by the others
+}
+
 __global__ void __launch_bounds__(32) laswp_plan_kernel(const int* __restrict__ trans, int n, int* __restrict__ plan_rows,
                                                         int* __restrict__ plan_src, int* __restrict__ plan_cnt,
                                                         int ngroups) {
@@ -377,6 +577,9 @@ struct LuCtx {
   PanelScratch sc;
   unsigned long long bar_count;  // host mirror of the barrier counter
   i64 recursion_threshold;       // reference's leaf width (<= it -> unblocked); GPU leaf = cooperative panel
+  int cluster_ctas = 0;           // > 0: factor leaves with the cluster (DSMEM) panel kernel on this many CTAs
+  cudaStream_t st_big = nullptr;  // optional: stream of a larger SM partition for the recursion's big TRSM / GEMM nodes
+  cudaEvent_t ev_to_big = nullptr, ev_from_big = nullptr;
 };
 
 constexpr i64 PANEL_SMEM_BUDGET = 200 * 1024;
@@ -393,7 +596,19 @@ int panel_cta_cap(int num_sms) {
 }
 
 // widest window (<= PANEL_W) whose row slices (ceil(m / #CTAs) rows x (w|1) doubles) fit in shared memory
+constexpr i64 CL_SMEM_BUDGET = 200 * 1024;
+int cluster_width_for(int C, i64 m) {
+  const i64 rows = std::max<i64>(1, (m + C - 1) / C);
+  for (int w = PANEL_W; w >= 1; w >>= 1)
+    if (rows * (i64)(w | 1) * 8 <= CL_SMEM_BUDGET) return w;
+  return 0;
+}
+
 int panel_width_for(const LuCtx& ctx, i64 m) {
+  if (ctx.cluster_ctas > 0) {
+    const int wc = cluster_width_for(ctx.cluster_ctas, m);
+    if (wc >= 4) return wc;
+  }
   const int cap = panel_cta_cap(ctx.num_sms);
   const i64 rows = std::max<i64>(1, (m + cap - 1) / cap);
   i64 w = PANEL_SMEM_BUDGET / (8 * rows) - 1;
@@ -402,7 +617,49 @@ int panel_width_for(const LuCtx& ctx, i64 m) {
   return (int)std::max<i64>(1, w);
 }
 
+// Cluster (DSMEM) panel; returns false when the launch is not possible here (the caller falls back).
+bool launch_panel_cluster(LuCtx& ctx, VD P, int* trans, bool want_plan) {
+  const int m = (int)P.nrows, w = (int)P.ncols, C = ctx.cluster_ctas;
+  if (C <= 0 || w > PANEL_W) return false;
+  int rows_per_cta = (m + C - 1) / C;
+  const size_t smem = (size_t)rows_per_cta * (size_t)(w | 1) * sizeof(double);
+  if (smem > (size_t)CL_SMEM_BUDGET) return false;
+  static bool configured = false;
+  if (!configured) {
+    FB_CUDA_CHECK(cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM_BUDGET));
+    if (C > 8) FB_CUDA_CHECK(cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C);
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx.st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  double* Aptr = P.ptr;
+  i64 rs = P.rs, cs = P.cs;
+  int* pr = want_plan ? ctx.plan_rows : nullptr;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, Aptr, rs, cs, m, w, rows_per_cta, trans, pr,
+                                           ctx.plan_src, ctx.plan_cnt);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    fprintf(stderr, "faer_b200: cluster panel launch failed (%s, %d CTAs); using the grid-barrier panel\n",
+            cudaGetErrorString(e), C);
+    ctx.cluster_ctas = 0;
+    return false;
+  }
+  note_launch();
+  return true;
+}
+
 void launch_panel(LuCtx& ctx, VD P, int* trans, bool want_plan) {
+  if (launch_panel_cluster(ctx, P, trans, want_plan)) return;
   const int m = (int)P.nrows, w = (int)P.ncols;
   int G = (int)std::min<i64>(panel_cta_cap(ctx.num_sms), (m + 63) / 64);
   if (G < 1) G = 1;
@@ -457,8 +714,20 @@ void lu_rec(LuCtx& ctx, VD A, i64 start, i64 end, int* trans) {
   {
     VD A00 = W.sub(0, 0, bs, bs), A01 = W.sub(0, bs, bs, n - bs), A10 = W.sub(bs, 0, m - bs, bs),
        A11 = W.sub(bs, bs, m - bs, n - bs);
-    solve_lower_triangular_in_place_f64(ctx.st, cv(A00), true, A01);
-    gemm_f64(ctx.st, A11, 1, cv(A10), cv(A01), -1.0);
+    // On a partitioned GPU the panel stream owns few SMs: the larger TRSM / GEMM nodes of the recursion go to the
+    // update partition's urgent stream (two event fences, ~10 us) and come back.
+    const bool offload = ctx.st_big != nullptr && n >= 128 && (double)(m - bs) * (double)(n - bs) * (double)bs >= 2e8;
+    cudaStream_t sg = offload ? ctx.st_big : ctx.st;
+    if (offload) {
+      FB_CUDA_CHECK(cudaEventRecord(ctx.ev_to_big, ctx.st));
+      FB_CUDA_CHECK(cudaStreamWaitEvent(sg, ctx.ev_to_big, 0));
+    }
+    solve_lower_triangular_in_place_f64(sg, cv(A00), true, A01);
+    gemm_f64(sg, A11, 1, cv(A10), cv(A01), -1.0);
+    if (offload) {
+      FB_CUDA_CHECK(cudaEventRecord(ctx.ev_from_big, sg));
+      FB_CUDA_CHECK(cudaStreamWaitEvent(ctx.st, ctx.ev_from_big, 0));
+    }
     lu_rec(ctx, W.sub(bs, 0, m - bs, n), bs, n, trans + bs);
   }
   if (has_outside) {
@@ -496,6 +765,7 @@ size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, vo
     FB_CUDA_CHECK(cudaGetDevice(&dev));
     FB_CUDA_CHECK(cudaDeviceGetAttribute(&ctx.num_sms, cudaDevAttrMultiProcessorCount, dev));
     ctx.recursion_threshold = (i64)params.recursion_threshold;
+    if (const char* e = getenv("FAER_B200_LU_CLUSTER")) ctx.cluster_ctas = std::min(atoi(e), CL_MAXC);  // dev knob
     const int G = ctx.num_sms;
     const i64 ngroups_max = (size + SWAP_GROUP - 1) / SWAP_GROUP + 1;
     ctx.d_trans = (int*)ws_alloc((size_t)size * sizeof(int));
@@ -599,8 +869,20 @@ LuWorkspace* lu_ws_create(cudaStream_t stream, i64 max_window, int sm_limit) {
   return w;
 }
 
+void lu_ws_set_cluster(LuWorkspace* w, int ctas) { w->ctx.cluster_ctas = ctas > CL_MAXC ? CL_MAXC : ctas; }
+
+void lu_ws_set_big_stream(LuWorkspace* w, cudaStream_t big) {
+  w->ctx.st_big = big;
+  if (big && !w->ctx.ev_to_big) {
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&w->ctx.ev_to_big, cudaEventDisableTiming));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&w->ctx.ev_from_big, cudaEventDisableTiming));
+  }
+}
+
 void lu_ws_destroy(LuWorkspace* w) {
   if (!w) return;
+  if (w->ctx.ev_to_big) cudaEventDestroy(w->ctx.ev_to_big);
+  if (w->ctx.ev_from_big) cudaEventDestroy(w->ctx.ev_from_big);
   ws_free(w->scb);
   ws_free(w->ctx.plan_cnt);
   ws_free(w->ctx.plan_src);

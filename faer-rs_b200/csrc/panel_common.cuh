@@ -40,6 +40,21 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
   __syncthreads();
 }
 
+// 16-byte vectors of T (float4 / double2) for record exchange through L2
+template <class T> struct Vec16;
+template <> struct Vec16<float> {
+  typedef float4 type;
+  static constexpr int N = 4;
+  __device__ static __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ static __forceinline__ float get(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
+};
+template <> struct Vec16<double> {
+  typedef double2 type;
+  static constexpr int N = 2;
+  __device__ static __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
+  __device__ static __forceinline__ double get(const double2& v, int e) { return e == 0 ? v.x : v.y; }
+};
+
 template <class T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -75,18 +90,22 @@ __device__ __forceinline__ void reduce_partials(const T* part, int G, T (&out)[N
   for (int v = 0; v < NV; ++v) out[v] = T(0);
   // 160 CTAs per round: five predicated records per lane, all loads issued before the first use (one L2 round trip
   // instead of five dependent ones)
+  // (records are 16-byte aligned and read as 16-byte vectors: G^2 records cross the L2 per barrier grid-wide)
+  typedef typename Vec16<T>::type V;
+  constexpr int VEC = Vec16<T>::N, NVEC = (NV + VEC - 1) / VEC, RSTRIDE = PANEL_NV / VEC;
+  const V* pv = reinterpret_cast<const V*>(part);
   for (int b0 = 0; b0 < G; b0 += 160) {
-    T rec[5][NV];
+    V rec[5][NVEC];
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
       const int b = b0 + lane + 32 * u;
 #pragma unroll
-      for (int v = 0; v < NV; ++v) rec[u][v] = b < G ? t_ldcg(&part[(i64)b * PANEL_NV + v]) : T(0);
+      for (int q = 0; q < NVEC; ++q) rec[u][q] = b < G ? __ldcg(&pv[(i64)b * RSTRIDE + q]) : Vec16<T>::zero();
     }
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) out[v] += rec[u][v];
+      for (int v = 0; v < NV; ++v) out[v] += Vec16<T>::get(rec[u][v / VEC], v % VEC);
     }
   }
 #pragma unroll

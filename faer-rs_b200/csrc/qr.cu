@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <limits>
 
+#include "panel_common.cuh"
 #include "runtime.cuh"
 #include "tensor_ops.cuh"
 
@@ -34,7 +35,7 @@ namespace fb {
 
 namespace {
 
-constexpr int QR_PW = 32;        // sub-panel width (columns per cooperative launch)
+constexpr int QR_PW = 32;       // sub-panel width (columns per cooperative launch)
 constexpr int QR_THREADS = 256;  // 8 row groups x 32 column lanes
 constexpr int QR_NV = QR_PW + 4; // published values per CTA and column: dots[PW], sml, med, big, above
 
@@ -46,36 +47,8 @@ struct QrScratch {
 };
 
 __device__ __forceinline__ void qr_grid_barrier(unsigned long long* bar, unsigned long long target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1ull);
-    while (*((volatile unsigned long long*)bar) < target) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
+  grid_barrier(bar, target);  // panel_common.cuh
 }
-
-__device__ __forceinline__ float t_hypot(float a, float b) { return hypotf(a, b); }
-__device__ __forceinline__ double t_hypot(double a, double b) { return hypot(a, b); }
-__device__ __forceinline__ float t_sqrt(float a) { return sqrtf(a); }
-__device__ __forceinline__ double t_sqrt(double a) { return sqrt(a); }
-__device__ __forceinline__ float t_abs(float a) { return fabsf(a); }
-__device__ __forceinline__ double t_abs(double a) { return fabs(a); }
-template <class T> struct TLim;
-template <> struct TLim<float> {
-  __device__ static float min_pos() { return 1.17549435e-38f; }
-  __device__ static float eps() { return 1.1920929e-7f; }
-  __device__ static float inf() { return __int_as_float(0x7f800000); }
-};
-template <> struct TLim<double> {
-  __device__ static double min_pos() { return 2.2250738585072014e-308; }
-  __device__ static double eps() { return 2.220446049250313e-16; }
-  __device__ static double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
-};
-__device__ __forceinline__ float t_ldcg(const float* p) { return __ldcg(p); }
-__device__ __forceinline__ double t_ldcg(const double* p) { return __ldcg(p); }
 
 // A: panel top-left (local row 0 = the diagonal row of panel column 0); mp rows, w <= QR_PW columns.
 // taus: pointer to the T-block diagonal entry of column 0, `tau_stride` elements between consecutive diagonal entries.
@@ -156,24 +129,36 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(T* __restrict__ A,
       // warp `rg` reduces the values v = rg, rg + 8, ... (QR_NV - 1 = 35 <= 40 values over 8 warps); every lane loads
       // the records of the CTAs lane, lane + 32, ... (G <= 160, checked on the host): all 25 loads of a lane are issued
       // before the first use, i.e. ONE L2 round trip per column instead of a chain of G / 4 dependent ones.
-      T rec[5][5];
+      // The records are read as 16-byte vectors: every CTA reads every CTA's record, i.e. G^2 * QR_NV values per column
+      // grid-wide — as scalar loads that is ~0.8 M L2 requests per column and the L2 request rate, not latency, bounds
+      // the panel; vectors cut the requests by 4x (f32) / 2x (f64).
+      typedef typename Vec16<T>::type V;
+      constexpr int VEC = Vec16<T>::N, NVV = QR_NV / VEC, NCH = (NVV + 7) / 8;
+      static_assert(QR_NV % VEC == 0, "record length must be a multiple of the vector width");
+      const V* pv = reinterpret_cast<const V*>(sc.part) + (i64)par * G * NVV;
+      V rec[NCH][5];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int v = rg + 8 * i;
+      for (int i = 0; i < NCH; ++i) {
+        const int c = rg + 8 * i;
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
           const int b = lane + 32 * u;
-          rec[i][u] = (v < QR_NV - 1 && b < G) ? t_ldcg(&sc.part[((i64)par * G + b) * QR_NV + v]) : T(0);
+          rec[i][u] = (c < NVV && b < G) ? __ldcg(&pv[(i64)b * NVV + c]) : Vec16<T>::zero();
         }
       }
       if (tid < w) rowj[tid] = t_ldcg(&sc.rowv[par * QR_PW + tid]);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int v = rg + 8 * i;
-        T s = ((rec[i][0] + rec[i][1]) + (rec[i][2] + rec[i][3])) + rec[i][4];
+      for (int i = 0; i < NCH; ++i) {
+        const int c = rg + 8 * i;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0 && v < QR_NV - 1) tot[v] = s;
+        for (int e = 0; e < VEC; ++e) {
+          T s = ((Vec16<T>::get(rec[i][0], e) + Vec16<T>::get(rec[i][1], e)) +
+                 (Vec16<T>::get(rec[i][2], e) + Vec16<T>::get(rec[i][3], e))) + Vec16<T>::get(rec[i][4], e);
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+          const int v = c * VEC + e;
+          if (lane == 0 && c < NVV && v < QR_NV - 1) tot[v] = s;
+        }
       }
       __syncthreads();
     }
