@@ -114,8 +114,10 @@ static int g_green_panel_sms = 0;  // SMs of the panel partition when active
 static int green_sms_wanted() {
   static int v = -1;
   if (v < 0) {
+    // default 16: measured LU n = 16384 191 ms (plain two-stream look-ahead) -> 168 ms (16-SM panel partition +
+    // cluster panel), profiles/r01_lu_partition.log; 0 switches the partitioned drivers off
     const char* e = getenv("FAER_B200_GREEN_SMS");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 16;
     if (v < 0) v = 0;
   }
   return v;
@@ -388,7 +390,9 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
   if (lookahead) ensure_streams();
   LltHostPipe* pipe = (P == 1 && lookahead) ? g_llt_pipe : nullptr;  // host-resident matrix streamed through (see below)
-  if (!pipe && lookahead && P == 1 && ensure_green_streams())
+  // (LLT gains nothing from the SM partition — 68.9 ms vs 67.3-69.2 ms at n = 16384: its chain kernels are small enough
+  // to slip in between GEMM CTAs — so the partitioned LLT driver stays opt-in: FAER_B200_GREEN_LLT=1)
+  if (!pipe && lookahead && P == 1 && getenv("FAER_B200_GREEN_LLT") && ensure_green_streams())
     return llt_local_partitioned_f64(A_local, ld, n, nb, reg_delta, reg_eps);
   cudaStream_t sp = lookahead ? g_panel_stream : current_stream();
   cudaStream_t sm = lookahead ? g_main_stream : current_stream();
@@ -559,8 +563,22 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
   FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_start, 0));
   FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_start, 0));
   FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
-  const i64 nblk = nblocks(n, nb);
-  LuWorkspace* wp = lu_ws_create(sp, nb, g_green_panel_sms);
+  // Block boundaries. FAER_B200_LU_WIDE=1 makes the blocks of the first half of the columns (where the schedule is
+  // bound by the trailing updates) twice as wide — deeper GEMMs, half the row-swap / TRSM passes; measured neutral at
+  // n = 16384 (170.2 vs 168.1 ms), so uniform blocks are the default.
+  std::vector<i64> b0;
+  {
+    const char* e = getenv("FAER_B200_LU_WIDE");
+    const bool wide = (e ? atoi(e) != 0 : false) && nb <= 512;
+    for (i64 c = 0; c < n;) {
+      b0.push_back(c);
+      c += (wide && 2 * c < n) ? std::min<i64>(2 * nb, n - c) : std::min<i64>(nb, n - c);
+    }
+    b0.push_back(n);
+  }
+  const i64 nblk = (i64)b0.size() - 1;
+  const i64 nbmax = 2 * nb;
+  LuWorkspace* wp = lu_ws_create(sp, nbmax, g_green_panel_sms);
   if (!getenv("FAER_B200_NO_OFFLOAD")) lu_ws_set_big_stream(wp, su);  // big recursion nodes run on the update partition
   {
     // leaves on a thread-block cluster (DSMEM exchange) inside the panel partition; FAER_B200_LU_CLUSTER=0 disables
@@ -568,8 +586,8 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
     const int want = e ? atoi(e) : 16;
     if (want > 0) lu_ws_set_cluster(wp, std::min(want, g_green_panel_sms >= 16 ? 16 : 8));
   }
-  LuWorkspace* wu = lu_ws_create(su, nb);
-  LuWorkspace* wm = lu_ws_create(sm, nb);
+  LuWorkspace* wu = lu_ws_create(su, nbmax);
+  LuWorkspace* wm = lu_ws_create(sm, nbmax);
   std::vector<cudaEvent_t> ev_panel((size_t)nblk), ev_ready((size_t)nblk), ev_first((size_t)nblk);
   for (i64 k = 0; k < nblk; ++k) {
     FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_panel[(size_t)k], evf));
@@ -577,7 +595,7 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
     FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_first[(size_t)k], evf));
   }
   auto factor_panel = [&](i64 k) {  // on sp
-    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    const i64 k0 = b0[(size_t)k], kb = b0[(size_t)k + 1] - k0, rows = n - k0;
     VD panel{A + k0 * ld + k0, rows, kb, 1, ld};
     lu_factor_window_f64(wp, panel, 0, kb, d_trans + k0);
     FB_CUDA_CHECK(cudaEventRecord(ev_panel[(size_t)k], sp));
@@ -585,7 +603,7 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
   // swaps (+ TRSM / GEMM if `right`) of step k on the columns [c0, c1)
   auto update_cols = [&](LuWorkspace* w, cudaStream_t st, i64 k, i64 c0, i64 c1, bool right) {
     if (c1 <= c0) return;
-    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    const i64 k0 = b0[(size_t)k], kb = b0[(size_t)k + 1] - k0, rows = n - k0;
     VD cols{A + c0 * ld + k0, rows, c1 - c0, 1, ld};
     lu_apply_transpositions_f64(w, cols, d_trans + k0, kb);
     if (right) {
@@ -600,10 +618,10 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
   };
   factor_panel(0);
   for (i64 k = 0; k < nblk; ++k) {
-    const i64 k0 = k * nb, kb = std::min(nb, n - k0);
+    const i64 k0 = b0[(size_t)k];
     const i64 kn = k + 1;
     if (kn < nblk) {
-      const i64 c0 = kn * nb, c1 = std::min(n, c0 + nb);
+      const i64 c0 = b0[(size_t)kn], c1 = b0[(size_t)kn + 1];
       FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_panel[(size_t)k], 0));
       if (k >= 1) FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_first[(size_t)(k - 1)], 0));
       update_cols(wu, su, k, c0, c1, true);
@@ -612,15 +630,13 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
       factor_panel(kn);
     }
     FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_panel[(size_t)k], 0));
-    const i64 c2 = (k + 2) * nb;
-    if (c2 < n) {
-      const i64 c3 = std::min(n, c2 + nb);
+    if (k + 2 < nblk) {
+      const i64 c2 = b0[(size_t)k + 2], c3 = b0[(size_t)k + 3];
       update_cols(wm, sm, k, c2, c3, true);  // the next urgent column first
       FB_CUDA_CHECK(cudaEventRecord(ev_first[(size_t)k], sm));
       update_cols(wm, sm, k, c3, n, true);
     }
     update_cols(wm, sm, k, 0, k0, false);  // the left columns only receive the row swaps
-    (void)kb;
   }
   FB_CUDA_CHECK(cudaStreamSynchronize(sp));
   FB_CUDA_CHECK(cudaStreamSynchronize(su));
@@ -633,7 +649,7 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
     fprintf(stderr, "LU n=%lld nb=%lld timeline (ms since start): k: col-ready panel-done bulk-first\n", n, nb);
     for (i64 k = 0; k < nblk; ++k)
       fprintf(stderr, "  %3lld: %8.3f %8.3f %8.3f\n", k, k ? at(ev_ready[(size_t)k]) : 0.f, at(ev_panel[(size_t)k]),
-              (k + 2) * nb < n ? at(ev_first[(size_t)k]) : -1.f);
+              k + 2 < nblk ? at(ev_first[(size_t)k]) : -1.f);
   }
   for (i64 k = 0; k < nblk; ++k) {
     cudaEventDestroy(ev_panel[(size_t)k]);
@@ -656,7 +672,9 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
   size_t n_trans = 0;
   if (n == 0) return 0;
   FB_ASSERT(nb > 0 && nb % 2 == 0, "block size must be positive and even");
-  if (lookahead && P == 1 && ensure_green_streams()) {
+  // the partition pays off where the panel chain is exposed (n = 16384: 191 -> 168 ms); at n = 32768 the schedule is
+  // bound by the trailing updates and giving 16 SMs away costs 2-4 % (963 vs 985-1002 ms): plain look-ahead there
+  if (lookahead && P == 1 && n <= 24576 && ensure_green_streams()) {
     int* d_trans = (int*)ws_alloc((size_t)n * sizeof(int));
     lu_local_partitioned_f64(A_local, ld, n, nb, d_trans);
     std::vector<int> h_trans((size_t)n);

@@ -36,7 +36,10 @@ namespace fb {
 namespace {
 
 constexpr int QR_PW = 32;       // sub-panel width (columns per cooperative launch)
-constexpr int QR_THREADS = 256;  // 8 row groups x 32 column lanes
+// 32 row groups x 32 column lanes: the per-column dot and update loops walk the CTA's rows (443 at 65536 rows) one row
+// per warp and iteration with a dependent shared-memory chain, so their latency divides by the number of warps
+// (measured with 8 warps: 15.8 us per column, 57 % of the samples in those two loops, profiles/r01_qr_panel_f32_ncu.txt)
+constexpr int QR_THREADS = 1024;
 constexpr int QR_NV = QR_PW + 4; // published values per CTA and column: dots[PW], sml, med, big, above
 
 template <class T>
@@ -133,13 +136,13 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(T* __restrict__ A,
       // grid-wide — as scalar loads that is ~0.8 M L2 requests per column and the L2 request rate, not latency, bounds
       // the panel; vectors cut the requests by 4x (f32) / 2x (f64).
       typedef typename Vec16<T>::type V;
-      constexpr int VEC = Vec16<T>::N, NVV = QR_NV / VEC, NCH = (NVV + 7) / 8;
+      constexpr int NWARP = QR_THREADS / 32, VEC = Vec16<T>::N, NVV = QR_NV / VEC, NCH = (NVV + NWARP - 1) / NWARP;
       static_assert(QR_NV % VEC == 0, "record length must be a multiple of the vector width");
       const V* pv = reinterpret_cast<const V*>(sc.part) + (i64)par * G * NVV;
       V rec[NCH][5];
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        const int c = rg + 8 * i;
+        const int c = rg + NWARP * i;
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
           const int b = lane + 32 * u;
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(T* __restrict__ A,
       if (tid < w) rowj[tid] = t_ldcg(&sc.rowv[par * QR_PW + tid]);
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        const int c = rg + 8 * i;
+        const int c = rg + NWARP * i;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           T s = ((Vec16<T>::get(rec[i][0], e) + Vec16<T>::get(rec[i][1], e)) +
