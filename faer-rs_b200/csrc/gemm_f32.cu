@@ -9,7 +9,10 @@
 // Round 1 uses the warp-level `mma.sync.m16n8k8.tf32` form with the same cp.async ring / padded-tile / structure-mask
 // machinery as the f64 kernel; moving this mainloop to tcgen05 `kind::tf32` (TMEM accumulators, TMA operand staging)
 // is the planned next step for this dtype.
+#include <cstdlib>
+
 #include "gemm_f32.cuh"
+#include "gemm_f32_tc.cuh"
 #include "runtime.cuh"
 
 namespace fb {
@@ -297,6 +300,37 @@ inline int f_transpose_struct(int s) {
 }
 inline bool f_aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+// tcgen05 path switch (FAER_B200_F32_TC=0 keeps everything on the mma.sync kernel) and its per-stream packing workspace
+// (grow-only device buffers; work on one stream is ordered, so a stream's buffer can be reused call after call)
+bool f32_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FAER_B200_F32_TC");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+tc::Workspace* f32_tc_workspace(cudaStream_t stream) {
+  struct Slot {
+    cudaStream_t st;
+    tc::Workspace ws;
+    bool used;
+  };
+  static Slot slots[16];
+  for (auto& s : slots)
+    if (s.used && s.st == stream) return &s.ws;
+  for (auto& s : slots)
+    if (!s.used) {
+      s.used = true;
+      s.st = stream;
+      return &s.ws;
+    }
+  // more than 16 distinct streams: recycle slot 0 after draining it
+  cudaStreamSynchronize(slots[0].st);
+  slots[0].st = stream;
+  return &slots[0].ws;
+}
+
 // dst(struct) = [dst +] alpha * sum_z W_z (partial products summed in z order, in double to keep fp32-level accuracy)
 __global__ void f_splitk_reduce_kernel(float* __restrict__ C, i64 rs, i64 cs, int m, int n, int c_struct, int accum,
                                        float alpha, const float* __restrict__ W, int splits) {
@@ -331,6 +365,24 @@ void gemm_f32(cudaStream_t stream, VF dst, int dst_struct, int accum, VCF lhs, i
     dst = d2; lhs = l2; rhs = r2;
     dst_struct = f_transpose_struct(dst_struct);
     lhs_struct = ls; rhs_struct = rs_;
+  }
+  // Large unstructured products go to the tcgen05 kernel (gemm_f32_tc.cuh: TMA + TMEM, 3xTF32 on the 5th-generation
+  // tensor cores; measured 243 TFLOP/s fp32-accurate at n = 8192 against 47 TFLOP/s for the mma.sync kernel below,
+  // profiles/r01_tc_f32_gemm.log). Structured operands / destinations and small products stay on the mma.sync kernel.
+  if (dst_struct == RECT && lhs_struct == RECT && rhs_struct == RECT && f32_tc_enabled() && dst.nrows >= 64 &&
+      dst.ncols >= 64 && lhs.ncols >= 32 && 2.0 * (double)dst.nrows * (double)dst.ncols * (double)lhs.ncols >= 2.5e8) {
+    tc::Operand a{lhs.ptr, (int)lhs.nrows, (int)lhs.ncols, lhs.rs, lhs.cs};
+    tc::Operand b{rhs.ptr, (int)rhs.nrows, (int)rhs.ncols, rhs.rs, rhs.cs};
+    const bool prof_tc = profiling_enabled();
+    if (prof_tc) profile_record_start(stream);
+    const bool ok = tc::gemm_f32_tc(stream, dst.ptr, dst.rs, dst.cs, (int)dst.nrows, (int)dst.ncols, (int)lhs.ncols, accum, a, b,
+                                    alpha, f32_tc_workspace(stream));
+    if (prof_tc) profile_record_stop(stream, 2.0 * (double)dst.nrows * (double)dst.ncols * (double)lhs.ncols);
+    if (ok) {
+      note_launch();
+      return;
+    }
+    (void)cudaGetLastError();
   }
   GemmF32Params p;
   p.m = (int)dst.nrows; p.n = (int)dst.ncols; p.k = (int)lhs.ncols;

@@ -68,3 +68,33 @@ def test_f32_triangular_structures(fb, oracle):
             if ds >= 3:
                 np.fill_diagonal(sel, False)
             assert np.array_equal(got[~sel], C0[~sel])
+
+
+def test_f32_tcgen05_path_layouts(fb, cuda_dev):
+    """Products large enough for the tcgen05 kernel (gemm_f32_tc.cuh), every operand layout / stride sign the packing pass
+    must absorb, Replace and Add, against the fp32 forward bound with an f64 reference."""
+    import torch
+    la = fb.linalg
+    rng = np.random.default_rng(43)
+    m, n, k = 520, 390, 700  # 2 m n k = 2.8e8: above the dispatch threshold; ragged against the 128 / 128 / 32 tiles
+    A = rng.standard_normal((m, k)).astype(np.float32); B = rng.standard_normal((k, n)).astype(np.float32)
+    C0 = rng.standard_normal((m, n)).astype(np.float32)
+    exact_ab = A.astype(np.float64) @ B.astype(np.float64)
+    absab = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)
+    dA = torch.from_numpy(A).to(cuda_dev); dB = torch.from_numpy(B).to(cuda_dev)
+    views_a = {"row-major": dA, "col-major": dA.T.contiguous().T, "reversed rows": torch.flip(dA, [0]).contiguous().flip(0)}
+    views_b = {"row-major": dB, "col-major": dB.T.contiguous().T, "reversed cols": torch.flip(dB, [1]).contiguous().flip(1)}
+    for na, va in views_a.items():
+        for nb_, vb in views_b.items():
+            for add, alpha in [(False, 1.0), (True, -0.5)]:
+                for cmaj in ("row", "col"):
+                    dC = torch.from_numpy(C0).to(cuda_dev)
+                    if cmaj == "col":
+                        dC = dC.T.contiguous().T
+                    if not add:
+                        dC.fill_(float("nan"))
+                    la.matmul(dC, la.Accum.Add if add else la.Accum.Replace, va, vb, alpha)
+                    exact = alpha * exact_ab + (C0.astype(np.float64) if add else 0.0)
+                    bound = 4 * k * U32 * abs(alpha) * absab + 4 * U32 * np.abs(exact) + (4 * U32 * np.abs(C0) if add else 0.0)
+                    err = np.abs(dC.cpu().numpy().astype(np.float64) - exact)
+                    assert np.all(err <= bound), (na, nb_, add, cmaj, float((err / bound).max()))

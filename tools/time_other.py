@@ -34,7 +34,10 @@ if what in ("gemm", "all"):
             del A, B, Cm
 
 if what in ("qr", "all"):
+    only = sys.argv[2] if len(sys.argv) > 2 else ""
     for (m, n, dt, name) in [(16384, 2048, torch.float64, "f64"), (65536, 4096, torch.float32, "f32")]:
+        if only and only != name:
+            continue
         A0 = torch.randn((n, m), dtype=dt, device=dev).T
         A = A0.clone(memory_format=torch.preserve_format)
         bs = la.qr_recommended_block_size(m, n)
