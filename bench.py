@@ -400,6 +400,37 @@ def main():
             del Lh
         del hA, hA0
 
+    # ---- the other two numbers BASELINE.json's metric names (f64 GEMM and LU at the same n), device-resident, N = 1 only;
+    # informational: `value` stays the LLT of configs[1] ----
+    also = None
+    if world == 1 and not args.no_e2e:
+        def _best_ms(f, reps=2):
+            f(); torch.cuda.synchronize(); best = 1e30
+            for _ in range(reps):
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                a0.record(stream); f(); a1.record(stream); torch.cuda.synchronize()
+                best = min(best, a0.elapsed_time(a1))
+            return best
+        del A
+        torch.manual_seed(4321)
+        X = torch.randn((n, n), dtype=torch.float64, device=dev).T
+        Y = torch.randn((n, n), dtype=torch.float64, device=dev).T
+        Z = torch.empty((n, n), dtype=torch.float64, device=dev).T
+        t_gemm = _best_ms(lambda: la.matmul(Z, la.Accum.Replace, X, Y, 1.0))
+        del Y, Z
+        Xw = X.clone(memory_format=torch.preserve_format)
+        pf = torch.zeros(n, dtype=torch.int64, device=dev); pi = torch.zeros(n, dtype=torch.int64, device=dev)
+        t_copy = _best_ms(lambda: Xw.copy_(X))
+
+        def _lu():
+            Xw.copy_(X)
+            la.lu_in_place(Xw, pf, pi)
+        t_lu = _best_ms(_lu) - t_copy
+        also = {"gemm_f64_tflops": 2.0 * n ** 3 / t_gemm / 1e9, "gemm_ms": t_gemm,
+                "lu_f64_tflops": 2.0 * n ** 3 / 3.0 / t_lu / 1e9, "lu_ms": t_lu, "n": n,
+                "what": "device-resident f64 GEMM (Replace, alpha = 1) and partial-pivoting LU (u64 indices) at the same n"}
+        del X, Xw
+
     cpu = None
     proxy = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -422,7 +453,7 @@ def main():
                        "l2": f"inputs ({A0.numel() * 8 / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no flush needed",
                        "probe_residual": resid},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(my_launches),
-            "roofline": roof, "cpu_baseline": cpu, "cpu_lapack_proxy": proxy,
+            "roofline": roof, "cpu_baseline": cpu, "cpu_lapack_proxy": proxy, "also": also,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -310,6 +310,9 @@ bool f32_tc_enabled() {
   }
   return v != 0;
 }
+// split-K partial buffer of the mma.sync kernel: per-stream grow-only scratch (runtime.cu)
+float* f32_split_workspace(cudaStream_t stream, size_t bytes) { return (float*)stream_scratch(stream, bytes); }
+
 tc::Workspace* f32_tc_workspace(cudaStream_t stream) {
   struct Slot {
     cudaStream_t st;
@@ -402,7 +405,8 @@ void gemm_f32(cudaStream_t stream, VF dst, int dst_struct, int accum, VCF lhs, i
         int len = (p.k + splits - 1) / splits;
         len = (len + 63) / 64 * 64;
         splits = (p.k + len - 1) / len;
-        split_ws = (float*)ws_alloc((size_t)splits * p.m * p.n * sizeof(float));
+        // per-stream grow-only buffer (no host synchronisation on the steady state: work on a stream is ordered)
+        split_ws = f32_split_workspace(stream, (size_t)splits * p.m * p.n * sizeof(float));
         p.k_split_len = len;
         p.c_split_stride = (i64)p.m * p.n;
         p.C = split_ws; p.c_rs = 1; p.c_cs = p.m; p.c_struct = RECT;
@@ -453,8 +457,6 @@ void gemm_f32(cudaStream_t stream, VF dst, int dst_struct, int accum, VCF lhs, i
                                                                                split_ws, splits);
     FB_CUDA_CHECK(cudaGetLastError());
     note_launch();
-    FB_CUDA_CHECK(cudaStreamSynchronize(stream));
-    ws_free(split_ws);
   }
 }
 

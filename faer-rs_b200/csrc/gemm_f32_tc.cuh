@@ -15,7 +15,8 @@
 //   warp 0   TMA producer: 4 loads per stage (A_hi, A_lo, B_hi, B_lo: 4 x 16 KB), mbarrier expect_tx
 //   warp 1   MMA issuer (one elected lane): waits `full`, 12 tcgen05.mma per stage, tcgen05.commit -> `empty`
 //   warp 2   TMEM allocation (128 columns) / deallocation
-//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32, alpha / accumulate, coalesced stores with the destination's strides
+//   all 8 warps, once their role loops are done: epilogue — tcgen05.ld 32x32b.x32 (warp w: TMEM lane quarter w % 4,
+//            column half w / 4), alpha / accumulate with batched loads, coalesced stores with the destination's strides
 // 3 stages x 64 KB of shared memory. Out-of-range rows / columns are zero-filled by TMA and masked in the epilogue.
 #pragma once
 #include <cuda.h>
@@ -165,13 +166,18 @@ gemm_f32_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
       }
       umma_commit(tmem_full);    // accumulator complete
     }
-  } else if (warp >= 4) {
+  }
+  __syncwarp();
+  // ---- epilogue, all 8 warps: warp w reads TMEM lane quarter w % 4 (the only one it may access) and the column half
+  // w / 4; the role warps join once their loops are done (short-k products are epilogue-bound) ----
+  {
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;
     const int row = m0 + 32 * q + lane;
+    const int cbeg = (warp >> 2) * (BN / 2);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
       uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
       asm volatile(
@@ -185,16 +191,15 @@ gemm_f32_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (row < m) {
+        float* dst = C + (long long)row * c_rs + (long long)(n0 + c0) * c_cs;
+        // all 32 old values first (independent loads in flight together), then the stores: a load -> store chain per
+        // element made the Add epilogue latency-bound (7 ms for a 65280 x 3840 x 256 update)
+        float old[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = n0 + c0 + i;
-          if (col < n) {
-            float* dst = C + (long long)row * c_rs + (long long)col * c_cs;
-            float val = alpha * __uint_as_float(v[i]);
-            if (accum) val += *dst;
-            *dst = val;
-          }
-        }
+        for (int i = 0; i < 32; ++i) old[i] = (accum && n0 + c0 + i < n) ? dst[(long long)i * c_cs] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (n0 + c0 + i < n) dst[(long long)i * c_cs] = fmaf(alpha, __uint_as_float(v[i]), old[i]);
       }
     }
   }

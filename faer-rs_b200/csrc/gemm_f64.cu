@@ -412,7 +412,7 @@ void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, i
         int len = (p.k + splits - 1) / splits;
         len = (len + 63) / 64 * 64;
         splits = (p.k + len - 1) / len;
-        split_ws = (double*)ws_alloc((size_t)splits * p.m * p.n * sizeof(double));
+        split_ws = (double*)stream_scratch(stream, (size_t)splits * p.m * p.n * sizeof(double));
         p.k_split_len = len;
         p.c_split_stride = (i64)p.m * p.n;
         p.C = split_ws; p.c_rs = 1; p.c_cs = p.m; p.c_struct = RECT;
@@ -467,9 +467,6 @@ void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, i
                                                                              split_ws, splits);
     FB_CUDA_CHECK(cudaGetLastError());
     note_launch();
-    // the pool is stream-agnostic: hand the slices back only once the reduce has consumed them
-    FB_CUDA_CHECK(cudaStreamSynchronize(stream));
-    ws_free(split_ws);
   }
 }
 

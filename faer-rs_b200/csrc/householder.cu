@@ -25,11 +25,14 @@ void householder_build_t(cudaStream_t st, View<const T> V, View<T> Tf) {
 }
 
 template <class T>
-void apply_block_householder_on_the_left(cudaStream_t st, View<const T> V, View<const T> Tf, View<T> M, bool forward) {
+void apply_block_householder_on_the_left(cudaStream_t st, View<const T> V, View<const T> Tf, View<T> M, bool forward,
+                                         T* tmp_buf) {
   const i64 N = V.ncols, m = V.nrows, K = M.ncols;
   FB_ASSERT(Tf.nrows == N && Tf.ncols == N && M.nrows == m && m >= N, "block Householder shape mismatch");
   if (N == 0 || K == 0) return;
-  T* buf = (T*)ws_alloc((size_t)N * K * sizeof(T));
+  // `tmp_buf` (>= N * K elements, owned by the caller) avoids the pool allocation and the host synchronisation that
+  // returning it to the stream-agnostic pool needs
+  T* buf = tmp_buf ? tmp_buf : (T*)ws_alloc((size_t)N * K * sizeof(T));
   View<T> tmp{buf, N, K, 1, N};
   View<const T> Vt = V.sub(0, 0, N, N), Vb = V.sub(N, 0, m - N, N);
   View<T> top = M.sub(0, 0, N, K), bot = M.sub(N, 0, m - N, K);
@@ -39,8 +42,10 @@ void apply_block_householder_on_the_left(cudaStream_t st, View<const T> V, View<
   else solve_upper(st, Tf, false, tmp);
   gemm(st, top, RECT, 1, Vt, UNIT_LOWER, cview(tmp), RECT, T(-1));
   if (m > N) gemm(st, bot, RECT, 1, Vb, RECT, cview(tmp), RECT, T(-1));
-  FB_CUDA_CHECK(cudaStreamSynchronize(st));  // the pool is stream-agnostic
-  ws_free(buf);
+  if (!tmp_buf) {
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));  // the pool is stream-agnostic
+    ws_free(buf);
+  }
 }
 
 // householder.rs:724-765: M <- H_0 H_1 ... H_{k-1} M  (blocks applied last to first)
@@ -79,7 +84,7 @@ template void apply_block_householder_sequence_transpose_on_the_left<float>(cuda
 
 template void householder_build_t<double>(cudaStream_t, View<const double>, View<double>);
 template void householder_build_t<float>(cudaStream_t, View<const float>, View<float>);
-template void apply_block_householder_on_the_left<double>(cudaStream_t, View<const double>, View<const double>, View<double>, bool);
-template void apply_block_householder_on_the_left<float>(cudaStream_t, View<const float>, View<const float>, View<float>, bool);
+template void apply_block_householder_on_the_left<double>(cudaStream_t, View<const double>, View<const double>, View<double>, bool, double*);
+template void apply_block_householder_on_the_left<float>(cudaStream_t, View<const float>, View<const float>, View<float>, bool, float*);
 
 }  // namespace fb

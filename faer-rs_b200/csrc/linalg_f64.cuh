@@ -82,5 +82,8 @@ i64 lookahead_block();
 void* ws_alloc(size_t bytes);  // 256-byte aligned device memory, cached across calls
 void ws_free(void* p);
 void ws_release_all();
+// Per-stream grow-only scratch (split-K partials): work on one stream is ordered, so the buffer is reused call after call
+// without host synchronisation; it is re-allocated (after draining the stream) only when a larger size is requested.
+void* stream_scratch(cudaStream_t stream, size_t bytes);
 
 }  // namespace fb

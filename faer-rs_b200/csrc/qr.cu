@@ -306,6 +306,9 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
     FB_CUDA_CHECK(cudaFuncSetAttribute(qr_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
+  // one W = V^H M buffer for every block-reflector application of this factorization (no per-apply pool round trip and
+  // no host synchronisation inside the column loop)
+  T* apply_tmp = (T*)ws_alloc((size_t)std::min(bs, size) * (size_t)n * sizeof(T));
 
   for (i64 j0 = 0; j0 < size; j0 += bs) {
     const i64 jb = std::min(bs, size - j0);
@@ -342,17 +345,20 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
       View<T> Tss = H.sub(s0, c0, sw, sw);
       householder_build_t<T>(st, Vs, Tss);
       const i64 rest = j0 + jb - (c0 + sw);
-      if (rest > 0) apply_block_householder_on_the_left<T>(st, Vs, cview(Tss), A.sub(c0, c0 + sw, mp, rest), true);
+      if (rest > 0)
+        apply_block_householder_on_the_left<T>(st, Vs, cview(Tss), A.sub(c0, c0 + sw, mp, rest), true, apply_tmp);
     }
     // full T of the block (off-diagonal sub-blocks V_i^H V_j; the diagonal sub-blocks are recomputed identically)
     View<const T> Vb = cview(A.sub(j0, j0, m - j0, jb));
     View<T> Tb = H.sub(0, j0, jb, jb);
     if (jb > QR_PW) householder_build_t<T>(st, Vb, Tb);
-    if (j0 + jb < n) apply_block_householder_on_the_left<T>(st, Vb, cview(Tb), A.sub(j0, j0 + jb, m - j0, n - (j0 + jb)), true);
+    if (j0 + jb < n)
+      apply_block_householder_on_the_left<T>(st, Vb, cview(Tb), A.sub(j0, j0 + jb, m - j0, n - (j0 + jb)), true, apply_tmp);
   }
   int h_flag = 0;
   FB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  ws_free(apply_tmp);
   ws_free(d_flag);
   ws_free(scb);
   return h_flag ? -1 : size;

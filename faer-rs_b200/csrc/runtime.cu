@@ -69,6 +69,43 @@ void* ws_alloc(size_t bytes) {
   return p;
 }
 
+void* stream_scratch(cudaStream_t stream, size_t bytes) {
+  struct Slot {
+    cudaStream_t st;
+    void* p;
+    size_t bytes;
+    bool used;
+  };
+  static Slot slots[16];
+  Slot* s = nullptr;
+  for (auto& c : slots)
+    if (c.used && c.st == stream) s = &c;
+  if (!s)
+    for (auto& c : slots)
+      if (!c.used) {
+        c.used = true;
+        c.st = stream;
+        c.p = nullptr;
+        c.bytes = 0;
+        s = &c;
+        break;
+      }
+  if (!s) {
+    FB_CUDA_CHECK(cudaStreamSynchronize(slots[0].st));
+    slots[0].st = stream;
+    s = &slots[0];
+  }
+  if (bytes > s->bytes) {
+    if (s->p) {
+      FB_CUDA_CHECK(cudaStreamSynchronize(stream));
+      FB_CUDA_CHECK(cudaFree(s->p));
+    }
+    FB_CUDA_CHECK(cudaMalloc(&s->p, bytes));
+    s->bytes = bytes;
+  }
+  return s->p;
+}
+
 void ws_free(void* p) {
   if (!p) return;
   std::lock_guard<std::mutex> lock(g_pool_mutex);

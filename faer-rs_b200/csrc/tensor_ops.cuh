@@ -28,7 +28,8 @@ void householder_build_t(cudaStream_t st, View<const T> V, View<T> Tf);
 // M <- (I - V T^-1 V^H) M  (forward = false)   or   M <- (I - V T^-H V^H) M  (forward = true)
 // Reference: householder.rs:370-620 (apply_block_householder_on_the_left_in_place_generic)
 template <class T>
-void apply_block_householder_on_the_left(cudaStream_t st, View<const T> V, View<const T> Tf, View<T> M, bool forward);
+void apply_block_householder_on_the_left(cudaStream_t st, View<const T> V, View<const T> Tf, View<T> M, bool forward,
+                                         T* tmp_buf = nullptr);
 
 // sequences of block reflectors stored as (basis = V below the diagonal, factor = block_size x size T blocks)
 // Reference: householder.rs:724-808
