@@ -478,8 +478,17 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
       }
       factor_and_bcast(kn);
     }
-    for (i64 j = k + 2; j < nblk; ++j)
-      if ((int)(j % P) == me) update_block_col(sm, k, j);
+    if (P == 1 && k + 2 < nblk && !(pipe && k == 0) && !getenv("FAER_B200_LLT_SPLIT_BULK")) {
+      // single GPU: every remaining block column in ONE structured launch (lower-triangular destination: tiles above
+      // the diagonal exit at once) instead of one launch per block column — no per-launch tail, better L2 reuse
+      const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows_k = n - k0, j0 = (k + 2) * nb;
+      VCD Wr{W[k & 1] + (j0 - k0), n - j0, kb, 1, rows_k};
+      VD dst{A_local + j0 * ld + j0, n - j0, n - j0, 1, ld};
+      gemm_f64(sm, dst, TRI_LOWER, 1, Wr, RECT, Wr.t(), RECT, -1.0);
+    } else {
+      for (i64 j = k + 2; j < nblk; ++j)
+        if ((int)(j % P) == me) update_block_col(sm, k, j);
+    }
     FB_CUDA_CHECK(cudaEventRecord(ev_used[(size_t)k], sm));
   }
   if (two_streams) {

@@ -108,7 +108,15 @@ gemm_f32_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // grouped rasterisation: the ~148 co-resident CTAs cover 16 m-tiles x ~9 n-tiles, so both operands are shared through
+  // L2 (with the plain x-fastest order every wave streamed 64 different A tiles: 15.8 GB of DRAM reads for 1.07 GB of
+  // operands at n = 8192, profiles/r01_tc_gemm8192_ncu.txt)
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  constexpr int GROUP_M = 16;
+  const int pid = blockIdx.x, width = GROUP_M * tiles_n;
+  const int first_m = (pid / width) * GROUP_M;
+  const int gsize = min(tiles_m - first_m, GROUP_M);
+  const int m0 = (first_m + (pid % width) % gsize) * BM, n0 = ((pid % width) / gsize) * BN;
   // split-K: grid.z slices of the k-blocks, each writing its own partial product
   const int kb0 = blockIdx.z * kb_per_split;
   const int kblocks = min(kb_per_split, kblocks_total - kb0);
@@ -233,7 +241,8 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict
       const float v = t[i][tx];
       uint32_t h, l;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-      const float rem = v - __uint_as_float(h);
+      // (an infinite / NaN value keeps a zero correction term: inf - inf would turn inf * x into NaN)
+      const float rem = (__uint_as_float(h) - __uint_as_float(h) == 0.f) ? v - __uint_as_float(h) : 0.f;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
       hi[(size_t)r * Kp + kk] = __uint_as_float(h);
       lo[(size_t)r * Kp + kk] = __uint_as_float(l);
@@ -334,7 +343,7 @@ inline bool gemm_f32_tc(cudaStream_t st, float* C, long long c_rs, long long c_c
       return false;
     configured = true;
   }
-  const dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)splits);
+  const dim3 grid((unsigned)(((m + BM - 1) / BM) * ((n + BN - 1) / BN)), 1u, (unsigned)splits);
   if (splits == 1) {
     gemm_f32_tc_kernel<<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, C, c_rs, c_cs, m, n, kblocks, kblocks, 0, alpha, accum);
   } else {

@@ -98,3 +98,21 @@ def test_f32_tcgen05_path_layouts(fb, cuda_dev):
                     bound = 4 * k * U32 * abs(alpha) * absab + 4 * U32 * np.abs(exact) + (4 * U32 * np.abs(C0) if add else 0.0)
                     err = np.abs(dC.cpu().numpy().astype(np.float64) - exact)
                     assert np.all(err <= bound), (na, nb_, add, cmaj, float((err / bound).max()))
+
+
+@pytest.mark.parametrize("shape", [(40, 30, 50), (520, 390, 700)])  # mma.sync path / tcgen05 path
+def test_f32_matmul_propagates_infinities_like_ieee(fb, shape):
+    """The hi/lo split must not turn inf * x into NaN (inf - inf in the correction term): an fp32 FMA chain, like the
+    reference's kernel, gives +inf for a row of A holding one +inf against positive B."""
+    la = fb.linalg
+    m, n, k = shape
+    rng = np.random.default_rng(44)
+    A = rng.uniform(0.5, 1.0, (m, k)).astype(np.float32); B = rng.uniform(0.5, 1.0, (k, n)).astype(np.float32)
+    A[3, 7] = np.inf
+    C = np.full((m, n), np.nan, dtype=np.float32)
+    la.matmul(C, la.Accum.Replace, A, B, 1.0)
+    assert np.all(np.isposinf(C[3, :]))
+    rest = np.delete(C, 3, axis=0)
+    assert np.all(np.isfinite(rest))
+    want = np.delete(A, 3, axis=0).astype(np.float64) @ B.astype(np.float64)
+    assert np.abs(rest - want).max() <= 1e-4 * np.abs(want).max()

@@ -348,3 +348,22 @@ def test_c64_matmul_vs_oracle(fb, oracle, cuda_dev):
     la.matmul(dC, la.Accum.Replace, dA, dB, 1.0)
     ref = A @ B
     assert np.all(np.abs(dC.cpu().numpy() - ref) <= 8 * n * (2 * U) * (np.abs(A) @ np.abs(B)))
+
+
+def test_plu_large_path_pivots_match_oracle(fb, oracle):
+    """n >= 4096 takes the block-column look-ahead driver (SM-partitioned, cluster panel kernel; dist.cu / lu_f64.cu): its
+    permutation must still be the reference's, bit for bit, and the factors must agree with the oracle's."""
+    la = fb.linalg
+    n = 4096 + 40  # ragged last block
+    rng = np.random.default_rng(77)
+    A = np.asfortranarray(rng.standard_normal((n, n)))
+    want = A.copy(order="F")
+    perm_o, pinv_o, nt_o = oracle.lu(want)
+    got = A.copy(order="F")
+    perm = np.zeros(n, dtype=np.uint64); pinv = np.zeros(n, dtype=np.uint64)
+    info = la.lu_in_place(got, perm, pinv)
+    assert np.array_equal(perm.astype(np.int64), perm_o)
+    assert np.array_equal(pinv.astype(np.int64), pinv_o)
+    assert info.transposition_count == nt_o
+    growth = max(1.0, np.abs(np.triu(want)).max() / np.abs(A).max())
+    assert np.allclose(got, want, rtol=1e-8, atol=1e-8 * growth)
