@@ -112,9 +112,7 @@ __device__ __forceinline__ bool f_needs_fixup(int structure, bool is_rhs, int mn
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  // (an infinite / NaN value keeps a zero correction term: inf - inf would turn inf * y into NaN)
-  const float h = __uint_as_float(hi);
-  const float r = (h - h == 0.0f) ? x - h : 0.0f;
+  const float r = x - __uint_as_float(hi);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 

@@ -241,8 +241,7 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict
       const float v = t[i][tx];
       uint32_t h, l;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-      // (an infinite / NaN value keeps a zero correction term: inf - inf would turn inf * x into NaN)
-      const float rem = (__uint_as_float(h) - __uint_as_float(h) == 0.f) ? v - __uint_as_float(h) : 0.f;
+      const float rem = v - __uint_as_float(h);
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
       hi[(size_t)r * Kp + kk] = __uint_as_float(h);
       lo[(size_t)r * Kp + kk] = __uint_as_float(l);
