@@ -316,7 +316,7 @@ def main():
     # overlap (their sum exceeds the step), which says nothing about the kernel. Serial launches give its own duration.
     A.copy_(A0)
     lib.faer_b200_profile_begin()
-    fail, _ = lay.cholesky_in_place(A, n, nb=(nb if distributed else 1024), lookahead=False)
+    fail, _ = lay.cholesky_in_place(A, n, nb=(nb if distributed else 256), lookahead=False)
     assert fail == -1
     barrier()
     flops = C.c_double(0); ms = C.c_double(0); cnt = C.c_ulonglong(0)
@@ -373,9 +373,9 @@ def main():
 
             def e2e_call():
                 la.cholesky_in_place(hv)  # H2D + factorisation + D2H inside the C-ABI call, synchronous
-            # the call streams block columns (width 1024) through the factorization: only the part on / below the
+            # the call streams block columns (width 256) through the factorization: only the part on / below the
             # diagonal blocks crosses PCIe (the strict upper triangle is neither read nor written by LLT)
-            bw = 1024
+            bw = int(os.environ.get("FAER_B200_NB", "0")) or 256
             bytes_h2d = sum((n - j0) * min(bw, n - j0) * 8 for j0 in range(0, n, bw))
             how = ("libfaer_v0_23_llt_factor_in_place_f64 on a pinned HOST matrix (wall clock around the synchronous call); "
                    "block columns are uploaded / downloaded on copy streams while the factorization runs")

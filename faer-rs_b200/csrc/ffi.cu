@@ -263,7 +263,7 @@ FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(FaerV0_24_MatMut A, Fa
       (i64)A.nrows >= lookahead_min_n()) {
     // host matrix: upload / factor / download pipelined block column by block column (dist.cu)
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
-    const i64 nb = lookahead_block() ? lookahead_block() : 1024;
+    const i64 nb = lookahead_block() ? lookahead_block() : 256;
     r = llt_host_pipelined_f64((double*)A.ptr, (i64)A.col_stride, (i64)A.nrows, nb, delta, eps);
   } else {
     Mat a(A, true, st);

@@ -211,9 +211,11 @@ LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta,
   // single rank): the panel chain (potf2 + solves of block column k+1) overlaps the trailing update of step k.
   // Measured on B200 at n = 16384: 67.5 ms vs 80.8 ms for the purely recursive driver (profiles/r01_lookahead_p1.log).
   if (A.rs == 1 && n >= lookahead_min_n()) {
-    // block width: measured sweep at n = 16384 (profiles/r01_nb_sweep.log): 512 -> 76.7 ms, 768 -> 72.2, 1024 -> 67.3,
-    // 1536 -> 72.4, 2048 -> 72.7
-    const i64 nbl = lookahead_block() ? lookahead_block() : 1024;
+    // block width: with the trailing update of a step as ONE structured launch the short chain of narrow blocks wins
+    // (n = 16384, profiles/r01_nb_sweep2.log): 256 -> 59.3 ms, 512 -> 60.5, 768 -> 67.6, 1024 -> 65.4, 1536 -> 75.4;
+    // n = 8192: 256 -> 14.7 ms, 512 -> 17.1. (With one launch per block column it was the other way round,
+    // profiles/r01_nb_sweep.log: 512 -> 76.7, 1024 -> 67.3.)
+    const i64 nbl = lookahead_block() ? lookahead_block() : 256;
     return dist_llt_f64(A.ptr, A.cs, n, nbl, reg_delta, reg_eps, /*lookahead | local*/ 3);
   }
   const int regularize = (reg_delta > 0.0 && reg_eps > 0.0) ? 1 : 0;
