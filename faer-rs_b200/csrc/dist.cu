@@ -547,9 +547,89 @@ LltResult llt_host_pipelined_f64(double* hostA, i64 host_ld, i64 n, i64 nb, doub
                                     (size_t)(n - j0) * 8, (size_t)jb, cudaMemcpyHostToDevice, s_h2d));
     FB_CUDA_CHECK(cudaEventRecord(pipe.up[(size_t)j], s_h2d));
   }
-  g_llt_pipe = &pipe;
-  LltResult r = dist_llt_f64(dA, n, n, nb, reg_delta, reg_eps, /*lookahead | local*/ 3);
-  g_llt_pipe = nullptr;
+  // Hybrid order, OPT-IN (FAER_B200_HOST_LEFT=1): measured 77-90 ms against 81-84 ms for the plain pipeline at n = 16384
+  // (profiles/r01_e2e_hybrid.log) — the left-looking half is bound by its own potrf / solve chain, so it does not pay yet.
+  // A right-looking factorization cannot get past its first step before
+  // the LAST block column has arrived (every step updates every column), i.e. it idles for the ~24 ms the upload of
+  // n = 16384 takes. While the upload runs, the first half of the block columns is therefore factored LEFT-looking — column
+  // j only needs the panels to its left, so it is processed the moment it lands: one GEMM with k = j0 applies all previous
+  // panels, then potrf + solve, then the finished column goes home. When the upload is complete, one structured GEMM
+  // brings the trailing half up to date and the right-looking look-ahead driver (above) finishes it.
+  const char* hl = getenv("FAER_B200_HOST_LEFT");
+  const i64 J = (hl && atoi(hl) != 0 && nblk >= 8) ? nblk / 2 : 0;
+  LltResult r{true, 0, 0};
+  if (J > 0) {
+    ensure_streams();
+    cudaStream_t sc = g_main_stream;
+    long long* d_info = (long long*)ws_alloc(4 * sizeof(long long));
+    long long h_info[2] = {-1, 0};
+    FB_CUDA_CHECK(cudaMemcpyAsync(d_info, h_info, sizeof(h_info), cudaMemcpyHostToDevice, sc));
+    std::vector<cudaEvent_t> ev_done((size_t)J);
+    for (i64 j = 0; j < J; ++j) {
+      const i64 j0 = j * nb, jb = std::min(nb, n - j0), below = n - j0 - jb;
+      FB_CUDA_CHECK(cudaStreamWaitEvent(sc, pipe.up[(size_t)j], 0));
+      VD djj{dA + j0 * n + j0, jb, jb, 1, n};
+      if (j > 0) {
+        VCD Lj{dA + j0, jb, j0, 1, n};  // rows of block j in the panels 0 .. j-1
+        gemm_f64(sc, djj, TRI_LOWER, 1, Lj, RECT, Lj.t(), RECT, -1.0);
+        if (below > 0) {
+          VCD Lb{dA + j0 + jb, below, j0, 1, n};
+          VD dbj{dA + j0 * n + j0 + jb, below, jb, 1, n};
+          gemm_f64(sc, dbj, 1, Lb, Lj.t(), -1.0);
+        }
+      }
+      llt_cholesky_device_f64(sc, djj, reg_delta, reg_eps, d_info, j0);
+      if (below > 0) {
+        VD bl{dA + j0 * n + j0 + jb, below, jb, 1, n};
+        solve_lower_triangular_in_place_f64(sc, cv(djj), false, bl.t());
+      }
+      FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_done[(size_t)j], cudaEventDisableTiming));
+      FB_CUDA_CHECK(cudaEventRecord(ev_done[(size_t)j], sc));
+      FB_CUDA_CHECK(cudaStreamWaitEvent(s_d2h, ev_done[(size_t)j], 0));
+      FB_CUDA_CHECK(cudaMemcpy2DAsync(hostA + j0 * host_ld + j0, (size_t)host_ld * 8, dA + j0 * n + j0, (size_t)n * 8,
+                                      (size_t)(n - j0) * 8, (size_t)jb, cudaMemcpyDeviceToHost, s_d2h));
+    }
+    // trailing half: all panels 0 .. J-1 at once (needs every remaining column on the device)
+    const i64 J0 = J * nb, nt = n - J0;
+    for (i64 j = J; j < nblk; ++j) FB_CUDA_CHECK(cudaStreamWaitEvent(sc, pipe.up[(size_t)j], 0));
+    {
+      VCD Lt{dA + J0, nt, J0, 1, n};
+      VD dt{dA + J0 * n + J0, nt, nt, 1, n};
+      gemm_f64(sc, dt, TRI_LOWER, 1, Lt, RECT, Lt.t(), RECT, -1.0);
+    }
+    FB_CUDA_CHECK(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, sc));
+    cudaEvent_t ev_half;
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_half, cudaEventDisableTiming));
+    FB_CUDA_CHECK(cudaEventRecord(ev_half, sc));
+    FB_CUDA_CHECK(cudaStreamWaitEvent(current_stream(), ev_half, 0));
+    // right-looking look-ahead driver on the trailing block; its finished panels go home through the same pipe
+    LltHostPipe tail;
+    tail.host = hostA + J0 * host_ld + J0;
+    tail.host_ld = host_ld;
+    tail.s_d2h = s_d2h;
+    tail.up.assign((size_t)(nblk - J), pipe.up[(size_t)(nblk - 1)]);
+    g_llt_pipe = &tail;
+    LltResult rt = dist_llt_f64(dA + J0 * n + J0, n, nt, nb, reg_delta, reg_eps, /*lookahead | local*/ 3);
+    g_llt_pipe = nullptr;
+    FB_CUDA_CHECK(cudaStreamSynchronize(sc));
+    FB_CUDA_CHECK(cudaStreamSynchronize(s_d2h));
+    if (h_info[0] >= 0) {
+      r.ok = false;
+      r.non_positive_pivot_index = (size_t)h_info[0];
+    } else if (!rt.ok) {
+      r.ok = false;
+      r.non_positive_pivot_index = rt.non_positive_pivot_index + (size_t)J0;
+    } else {
+      r.dynamic_regularization_count = (size_t)h_info[1] + rt.dynamic_regularization_count;
+    }
+    for (i64 j = 0; j < J; ++j) cudaEventDestroy(ev_done[(size_t)j]);
+    cudaEventDestroy(ev_half);
+    ws_free(d_info);
+  } else {
+    g_llt_pipe = &pipe;
+    r = dist_llt_f64(dA, n, n, nb, reg_delta, reg_eps, /*lookahead | local*/ 3);
+    g_llt_pipe = nullptr;
+  }
   FB_CUDA_CHECK(cudaStreamSynchronize(s_h2d));
   for (i64 j = 0; j < nblk; ++j) cudaEventDestroy(pipe.up[(size_t)j]);
   ws_free(dA);
