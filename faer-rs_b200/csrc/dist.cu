@@ -9,6 +9,14 @@
 //
 // NCCL is resolved at run time with dlopen("libnccl.so.2") (the copy torch already loaded in a torch process), so
 // libfaer_b200.so has no link-time NCCL dependency and single-GPU users never touch it.
+//
+// The same block-column drivers run the large single-GPU factorizations (P = 1, no communicator). Three single-GPU
+// refinements live here as well:
+//   * SM partitioning with CUDA green contexts (`ensure_green_streams`): the LU panel chain gets its own SMs, the
+//     trailing updates an urgent and a bulk stream on the rest (`lu_local_partitioned_f64`; LLT variant opt-in);
+//   * on one GPU the LLT trailing update of a step is ONE structured launch instead of one per block column;
+//   * host-resident matrices are streamed through the LLT (`llt_host_pipelined_f64`): uploads, factorization and
+//     downloads of finished panels overlap.
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>

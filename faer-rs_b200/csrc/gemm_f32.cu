@@ -6,9 +6,10 @@
 // Each fp32 operand is split in registers into a_hi = tf32(a), a_lo = tf32(a - a_hi) and every product is issued as
 // three tensor-core MMAs (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, small terms first) with fp32 accumulation: the dropped
 // a_lo*b_lo term is O(2^-22) relative, i.e. the result is as accurate as an fp32 FMA chain up to summation order.
-// Round 1 uses the warp-level `mma.sync.m16n8k8.tf32` form with the same cp.async ring / padded-tile / structure-mask
-// machinery as the f64 kernel; moving this mainloop to tcgen05 `kind::tf32` (TMEM accumulators, TMA operand staging)
-// is the planned next step for this dtype.
+// This file holds the warp-level `mma.sync.m16n8k8.tf32` kernel with the same cp.async ring / padded-tile /
+// structure-mask machinery as the f64 kernel — it serves structured (triangular) operands / destinations and small
+// products — and the dispatcher: large unstructured products go to the tcgen05 kernel (`gemm_f32_tc.cuh`: TMA operand
+// staging, TMEM accumulator, `tcgen05.mma.kind::tf32`), 5x faster at n = 8192.
 #include <cstdlib>
 
 #include "gemm_f32.cuh"

@@ -15,6 +15,9 @@
 //     every CTA reduces the candidates redundantly (ties -> lowest row index, zeros/NaNs never selected, exactly
 //     the reference's scan), the two owners exchange rows in shared memory and everybody applies the rank-1
 //     update to its slice while tracking the next column's local arg-max (warp-shuffle reduction);
+//   * inside the SM-partitioned look-ahead driver (dist.cu) the leaves run as ONE thread-block cluster instead
+//     (`lu_panel_cluster_kernel`): candidates are exchanged through distributed shared memory with one hardware
+//     cluster barrier per column — no L2 round trips on the per-column critical path;
 //   * row interchanges outside the window (P3) are applied group-wise: a tiny planning kernel turns each group
 //     of 64 transpositions into a net gather list (<= 128 affected rows), and the apply kernel moves all
 //     affected rows of a 32-column strip through shared memory with independent loads (full memory-level
