@@ -123,6 +123,11 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_matmul_triangular_c64.argtypes = [MatMut, C.c_int, C.c_int, MatRef, C.c_int, MatRef, C.c_int,
                                                         C.c_void_p, P]
     lib.libfaer_v0_23_matmul_triangular_c64.restype = None
+    lib.libfaer_v0_23_matmul_c32.argtypes = [MatMut, C.c_int, MatRef, MatRef, C.c_void_p, P]
+    lib.libfaer_v0_23_matmul_c32.restype = None
+    lib.libfaer_v0_23_matmul_triangular_c32.argtypes = [MatMut, C.c_int, C.c_int, MatRef, C.c_int, MatRef, C.c_int,
+                                                        C.c_void_p, P]
+    lib.libfaer_v0_23_matmul_triangular_c32.restype = None
     for name in ("solve_triangular_lower", "solve_triangular_upper", "solve_unit_triangular_lower",
                  "solve_unit_triangular_upper"):
         f = getattr(lib, f"libfaer_v0_23_{name}_in_place_f64")

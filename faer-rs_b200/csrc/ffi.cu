@@ -211,6 +211,38 @@ void libfaer_v0_23_matmul_triangular_c64(FaerV0_24_MatMut C, FaerV0_24_Block C_b
   matmul_c64_impl(C, (int)C_block, accum, A, (int)A_block, B, (int)B_block, alpha);
 }
 
+static void matmul_c32_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum accum, FaerV0_24_MatRef A, int A_block,
+                            FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha) {
+  require_device();
+  FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
+  cudaStream_t st = current_stream();
+  FB_ASSERT(alpha != nullptr, "null scalar pointer");
+  float a[2];
+  if (is_device_pointer(alpha)) FB_CUDA_CHECK(cudaMemcpy(a, alpha, 8, cudaMemcpyDeviceToHost));
+  else memcpy(a, alpha, 8);
+  const bool copy_in = accum == FaerV0_24_Accum_Add || C_block != FaerV0_24_Block_Rectangular;
+  // elements are 8-byte (re, im) pairs; the views keep strides in complex units and a float* base
+  StagedMat c(C.ptr, (i64)C.nrows, (i64)C.ncols, (i64)C.row_stride, (i64)C.col_stride, 8, copy_in, true, st);
+  StagedMat l(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 8, true, false, st);
+  StagedMat r(B.ptr, (i64)B.nrows, (i64)B.ncols, (i64)B.row_stride, (i64)B.col_stride, 8, true, false, st);
+  VF dv = c.view<float>();
+  VF lv0 = l.view<float>(), rv0 = r.view<float>();
+  gemm_c32(st, dv, C_block, accum == FaerV0_24_Accum_Add ? 1 : 0, cv(lv0), A_block, false, cv(rv0), B_block, false, a[0],
+           a[1]);
+  finish_all(st, {&c, &l, &r});
+}
+void libfaer_v0_23_matmul_c32(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
+                              const FaerV0_24_Scalar* alpha, FaerV0_24_Par par) {
+  (void)par;
+  matmul_c32_impl(C, 0, accum, A, 0, B, 0, alpha);
+}
+void libfaer_v0_23_matmul_triangular_c32(FaerV0_24_MatMut C, FaerV0_24_Block C_block, FaerV0_24_Accum accum,
+                                         FaerV0_24_MatRef A, FaerV0_24_Block A_block, FaerV0_24_MatRef B,
+                                         FaerV0_24_Block B_block, const FaerV0_24_Scalar* alpha, FaerV0_24_Par par) {
+  (void)par;
+  matmul_c32_impl(C, (int)C_block, accum, A, (int)A_block, B, (int)B_block, alpha);
+}
+
 void libfaer_v0_23_solve_triangular_lower_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs,
                                                        FaerV0_24_Par par) {
   (void)L_conj; (void)par;  // conjugation is the identity for real scalars

@@ -27,6 +27,10 @@ inline void gemm_f32(cudaStream_t stream, VF dst, int accum, VCF lhs, VCF rhs, f
   gemm_f32(stream, dst, RECT, accum, lhs, RECT, rhs, RECT, alpha);
 }
 
+// c32 (interleaved complex<f32>) product, 4M formulation on the f32 kernels (gemm_c32.cu); views in complex units
+void gemm_c32(cudaStream_t stream, VF dst, int dst_struct, int accum, VCF lhs, int lhs_struct, bool conj_lhs, VCF rhs,
+              int rhs_struct, bool conj_rhs, float alpha_re, float alpha_im);
+
 // f32 triangular solves (trsm.cu; same algorithm as the f64 ones)
 void solve_lower_triangular_in_place_f32(cudaStream_t stream, VCF tril, bool unit, VF rhs);
 void solve_upper_triangular_in_place_f32(cudaStream_t stream, VCF triu, bool unit, VF rhs);

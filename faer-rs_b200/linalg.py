@@ -52,6 +52,18 @@ def _is_c64(x) -> bool:
     return x.dtype == np.complex128
 
 
+def _is_c32(x) -> bool:
+    if capi._is_torch(x):
+        import torch
+        return x.dtype == torch.complex64
+    return x.dtype == np.complex64
+
+
+def _scalar_c32(v):
+    buf = (C.c_float * 2)(complex(v).real, complex(v).imag)
+    return C.cast(buf, C.c_void_p), buf
+
+
 def _scalar_c64(v):
     buf = (C.c_double * 2)(complex(v).real, complex(v).imag)
     return C.cast(buf, C.c_void_p), buf
@@ -65,8 +77,15 @@ def _is_f32(x) -> bool:
 
 
 def matmul(dst, accum: int, lhs, rhs, alpha, par=None) -> None:
-    """dst = [dst +] alpha * lhs * rhs  (Accum.Replace never reads dst). f64, f32 or c64 (complex128) operands."""
+    """dst = [dst +] alpha * lhs * rhs  (Accum.Replace never reads dst). f64, f32, c64 (complex128) or c32 (complex64)."""
     lib = capi.load()
+    if _is_c32(dst):
+        assert _is_c32(lhs) and _is_c32(rhs)
+        p, keep = _scalar_c32(alpha)
+        lib.libfaer_v0_23_matmul_c32(capi.mat_mut(dst), accum, capi.mat_ref(lhs), capi.mat_ref(rhs), p,
+                                     par or capi.par_default())
+        del keep
+        return
     if _is_f32(dst):
         assert _is_f32(lhs) and _is_f32(rhs)
         a = C.c_float(float(alpha))
@@ -88,6 +107,13 @@ def matmul(dst, accum: int, lhs, rhs, alpha, par=None) -> None:
 def matmul_triangular(dst, dst_structure: int, accum: int, lhs, lhs_structure: int, rhs, rhs_structure: int,
                       alpha: float, par=None) -> None:
     lib = capi.load()
+    if _is_c32(dst):
+        assert _is_c32(lhs) and _is_c32(rhs)
+        p, keep = _scalar_c32(alpha)
+        lib.libfaer_v0_23_matmul_triangular_c32(capi.mat_mut(dst), dst_structure, accum, capi.mat_ref(lhs), lhs_structure,
+                                                capi.mat_ref(rhs), rhs_structure, p, par or capi.par_default())
+        del keep
+        return
     if _is_f32(dst):
         assert _is_f32(lhs) and _is_f32(rhs)
         a = C.c_float(float(alpha))

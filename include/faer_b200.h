@@ -118,6 +118,16 @@ void libfaer_v0_23_matmul_triangular_f32(struct FaerV0_24_MatMut C, enum FaerV0_
                                          enum FaerV0_24_Block B_block, const struct FaerV0_24_Scalar *alpha,
                                          struct FaerV0_24_Par par);
 
+/* c32 (interleaved complex<f32>) variants: faer-ffi/faer.h `libfaer_v0_23_matmul_c32` / `matmul_triangular_c32`
+ * (same funcs! stamping, faer-ffi/src/lib.rs:313-369, 855-894); `alpha` points to a complex<float> scalar. */
+void libfaer_v0_23_matmul_c32(struct FaerV0_24_MatMut C, enum FaerV0_24_Accum accum, struct FaerV0_24_MatRef A,
+                              struct FaerV0_24_MatRef B, const struct FaerV0_24_Scalar *alpha, struct FaerV0_24_Par par);
+void libfaer_v0_23_matmul_triangular_c32(struct FaerV0_24_MatMut C, enum FaerV0_24_Block C_block,
+                                         enum FaerV0_24_Accum accum, struct FaerV0_24_MatRef A,
+                                         enum FaerV0_24_Block A_block, struct FaerV0_24_MatRef B,
+                                         enum FaerV0_24_Block B_block, const struct FaerV0_24_Scalar *alpha,
+                                         struct FaerV0_24_Par par);
+
 /* c64 (interleaved complex<f64>) variants: faer-ffi/faer.h `libfaer_v0_23_matmul_c64` / `matmul_triangular_c64`
  * (same funcs! stamping, faer-ffi/src/lib.rs:313-369, 855-894); `alpha` points to a complex scalar. */
 void libfaer_v0_23_matmul_c64(struct FaerV0_24_MatMut C, enum FaerV0_24_Accum accum, struct FaerV0_24_MatRef A,

@@ -117,3 +117,38 @@ def test_f32_matmul_nonfinite_inputs_stay_confined(fb, shape):
     assert np.all(np.isfinite(rest))
     want = np.delete(A, 3, axis=0).astype(np.float64) @ B.astype(np.float64)
     assert np.abs(rest - want).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_c32_matmul_vs_oracle(fb, oracle):
+    """c32 matmul / triangular matmul (4M formulation on the f32 kernels; the large case takes the tcgen05 kernel with
+    stride-2 planes through its packing pass) vs the oracle's c32 schoolbook product, inside the fp32 forward bound."""
+    la = fb.linalg
+    rng = np.random.default_rng(45)
+
+    def crandn(shape, order):
+        return np.array(rng.standard_normal(shape) + 1j * rng.standard_normal(shape), dtype=np.complex64, order=order)
+
+    for (m, n, k) in [(1, 1, 1), (17, 17, 17), (127, 129, 65), (16, 1, 16), (4, 4, 0), (100, 63, 9), (520, 390, 700)]:
+        for layout in [("F", "F", "F"), ("C", "F", "C")]:
+            for add, alpha in [(False, 1.0), (True, 0.5 - 2.0j), (False, 1.5j)]:
+                A = crandn((m, k), layout[0]); B = crandn((k, n), layout[1]); C0 = crandn((m, n), layout[2])
+                got = C0.copy(order="K")
+                if not add:
+                    got[...] = np.nan
+                la.matmul(got, la.Accum.Add if add else la.Accum.Replace, A, B, alpha)
+                exact = alpha * (A.astype(np.complex128) @ B.astype(np.complex128)) + (C0.astype(np.complex128) if add else 0)
+                bound = 16 * abs(alpha) * max(k, 1) * U32 * (np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)) \
+                    + 8 * U32 * np.abs(exact) + (8 * U32 * np.abs(C0) if add else 0.0) + 1e-30
+                assert np.all(np.abs(got.astype(np.complex128) - exact) <= bound), (m, n, k, layout, add, alpha)
+                if m * n * k <= 200 * 200 * 200:
+                    want = C0.copy(order="K")
+                    if not add:
+                        want[...] = np.nan
+                    oracle.matmul(want, add, A, B, alpha)
+                    assert np.all(np.abs(want.astype(np.complex128) - exact) <= bound)
+    for ds, ls, rs in [(0, 5, 0), (1, 0, 0), (6, 6, 5), (3, 4, 0)]:
+        n = 70
+        A = crandn((n, n), "F"); B = crandn((n, n), "F"); C0 = crandn((n, n), "F")
+        want = C0.copy(order="F"); oracle.matmul_triangular(want, ds, True, A, ls, B, rs, 0.5 + 1j)
+        got = C0.copy(order="F"); la.matmul_triangular(got, ds, la.Accum.Add, A, ls, B, rs, 0.5 + 1j)
+        assert np.all(np.abs(got - want) <= 2e-4 * np.maximum(1.0, np.abs(want))), (ds, ls, rs)
