@@ -1,0 +1,334 @@
+// DRAFT FOR ROUND 2 — compiled by tools/next/ozaki_test.cu only, NOT part of libfaer_b200.so and not reachable from
+// the C ABI. It has been compiled for sm_100a (ptxas accepts every instruction form) but has not run on a GPU yet.
+//
+// f64 GEMM on the 5th-generation tensor cores through int8 slicing ("Ozaki scheme"): the only way to put the f64 hot
+// path on tcgen05 (there is no f64 MMA kind). Numerical model and measured error levels:
+// tools/next/ozaki_emulation.py (8 slices: at or below the error of a plain f64 GEMM relative to |A||B|; 9 slices:
+// below it everywhere).
+//
+// Scheme. Row i of A is scaled by 2^-e_i (|x| < 1), column j of B by 2^-f_j, and every scaled value is split into S
+// signed 7-bit slices, x = A0/64 + A1/(64*128) + A2/(64*128^2) + ... (exact in f64). Then
+//     C_ij = 2^(e_i + f_j) * sum_{d < S} 2^(-12 - 7d) * G_d[i, j],      G_d = sum_{p + q = d} A_p B_q   (int32, exact)
+// i.e. S(S+1)/2 int8 GEMMs (36 for S = 8) instead of one f64 GEMM: 4.5 PFLOP/s-class int8 throughput against 37 TFLOP/s
+// of DMMA, a nominal 125 TFLOP/s f64-equivalent.
+//
+// Kernel. One CTA per 128 x 64 output tile keeps ALL S = 8 order accumulators G_0..G_7 in TMEM at the same time
+// (8 x 64 columns = the full 512-column TMEM), so the operands are streamed ONCE: per 64-deep k-block TMA brings the
+// 8 A slices (8 x 128 x 64 B) and the 8 B slices (8 x 64 x 64 B) = 96 KB into 64B-swizzled shared memory (2 stages),
+// and one elected lane issues the 36 x 2 `tcgen05.mma.kind::i8` (M = 128, N = 64, K = 32) of the stage:
+// 37.7 M int8 MACs per 96 KB of operands keeps the L2 -> SM traffic near 40 B/clk/SM. The epilogue reads the eight
+// int32 accumulators, combines them small-to-large in f64, applies the row / column exponents and alpha, and stores /
+// accumulates into C with its strides.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+namespace fb {
+namespace oz {
+
+constexpr int S = 8;                    // slices
+constexpr int BM = 128, BN = 64, BK = 64, STAGES = 2;
+constexpr int A_SLICE_BYTES = BM * BK;  // 8 KB
+constexpr int B_SLICE_BYTES = BN * BK;  // 4 KB
+constexpr int STAGE_BYTES = S * (A_SLICE_BYTES + B_SLICE_BYTES);  // 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 512;
+
+struct Operand {
+  const double* p;
+  int rows, cols;
+  long long rs, cs;
+};
+
+struct Workspace {
+  char* buf = nullptr;
+  size_t bytes = 0;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) /*SBO = 512 B*/ | (1ull << 46) |
+         (4ull << 61) /*SWIZZLE_64B*/;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D = S32, A = B = signed 8-bit, both K-major, M = 128, N = 64
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__global__ void __launch_bounds__(256, 1)
+gemm_f64_ozaki_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, double* __restrict__ C,
+                      long long c_rs, long long c_cs, int m, int n, int kblocks, const int* __restrict__ ea,
+                      const int* __restrict__ fb_, double alpha, int accum) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  constexpr int GROUP_M = 16;
+  const int pid = blockIdx.x, width = GROUP_M * tiles_n;
+  const int first_m = (pid / width) * GROUP_M;
+  const int gsize = min(tiles_m - first_m, GROUP_M);
+  const int m0 = (first_m + (pid % width) % gsize) * BM, n0 = ((pid % width) / gsize) * BN;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        for (int p = 0; p < S; ++p) tma_load_3d(st + p * A_SLICE_BYTES, &mA, &full[s], kb * BK, m0, p);
+        for (int q = 0; q < S; ++q) tma_load_3d(st + S * A_SLICE_BYTES + q * B_SLICE_BYTES, &mB, &full[s], kb * BK, n0, q);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_base = a_base + S * A_SLICE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 32; ++kk) {
+#pragma unroll
+          for (int d = 0; d < S; ++d) {
+            const uint32_t acc = tmem_base + (uint32_t)(d * BN);  // order d lives in columns [64 d, 64 d + 64)
+#pragma unroll
+            for (int p = 0; p <= d; ++p) {
+              const uint64_t ad = umma_desc_k_sw64(a_base + p * A_SLICE_BYTES + kk * 32);
+              const uint64_t bd = umma_desc_k_sw64(b_base + (d - p) * B_SLICE_BYTES + kk * 32);
+              umma_i8(acc, ad, bd, IDESC, (kb | kk | p) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  }
+  __syncwarp();
+  {
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int row = m0 + 32 * q + lane;
+    const int c0 = (warp >> 2) * 32;  // column half of this warp
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+#pragma unroll 1
+    for (int d = S - 1; d >= 0; --d) {  // small orders first
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(d * BN + c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const double w = scalbn(1.0, -12 - 7 * d);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = fma((double)(int)v[i], w, acc[i]);
+    }
+    if (row < m) {
+      const int er = ea[row];
+      double* dst = C + (long long)row * c_rs + (long long)(n0 + c0) * c_cs;
+      double old[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) old[i] = (accum && n0 + c0 + i < n) ? dst[(long long)i * c_cs] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (n0 + c0 + i < n) dst[(long long)i * c_cs] = fma(alpha, scalbn(acc[i], er + fb_[n0 + c0 + i]), old[i]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// e[r] = exponent with |x(r, :)| * 2^-e < 1 (0 for an all-zero row); x(r, kk) = p[r * rs + kk * cs]. One warp per row.
+__global__ void __launch_bounds__(128) ozaki_exponent_kernel(const double* __restrict__ src, long long rs, long long cs, int rows,
+                                                             int k, int* __restrict__ e) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  double mx = 0.0;
+  for (int kk = lane; kk < k; kk += 32) mx = fmax(mx, fabs(src[(long long)r * rs + (long long)kk * cs]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if (lane == 0) e[r] = mx > 0.0 ? ilogb(mx) + 1 : 0;
+}
+
+// out[p][r][kk] = slice p of x(r, kk) * 2^-e[r] for kk < Kp (zero beyond k)
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ src, long long rs, long long cs, int rows,
+                                                          int k, int Kp, const int* __restrict__ e, int8_t* __restrict__ out) {
+  __shared__ double t[32][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool k_fast = (cs < 0 ? -cs : cs) <= (rs < 0 ? -rs : rs);
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int r = k_fast ? r0 + i : r0 + tx;
+    const int kk = k_fast ? k0 + tx : k0 + i;
+    const double v = (r < rows && kk < k) ? src[(long long)r * rs + (long long)kk * cs] : 0.0;
+    if (k_fast) t[i][tx] = v;
+    else t[tx][i] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, kk = k0 + tx;
+    if (r < rows) {
+      double x = scalbn(t[i][tx], -e[r]) * 64.0;
+#pragma unroll
+      for (int p = 0; p < S; ++p) {
+        const double a = rint(x);
+        out[((size_t)p * rows + r) * Kp + kk] = (int8_t)(int)a;
+        x = (x - a) * 128.0;
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && f) fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+inline bool make_map(CUtensorMap* map, int8_t* base, int rows, int Kp, int box_rows) {
+  const cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)S};
+  const cuuint64_t gstride[2] = {(cuuint64_t)Kp, (cuuint64_t)rows * (cuuint64_t)Kp};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline void release(Workspace* ws) {
+  if (ws->buf) cudaFree(ws->buf);
+  ws->buf = nullptr;
+  ws->bytes = 0;
+}
+
+// C(m x n) = [C +] alpha * A(m x k) * B(k x n) in f64 through int8 slices. k <= 32768 per call (int32 accumulators).
+inline bool gemm_f64_ozaki(cudaStream_t st, double* C, long long c_rs, long long c_cs, int m, int n, int k, int accum, Operand a,
+                           Operand b, double alpha, Workspace* ws) {
+  if (m <= 0 || n <= 0 || k <= 0 || k > 32768 || !encode_fn()) return false;
+  const int Kp = (k + BK - 1) / BK * BK;
+  const size_t a_bytes = (size_t)S * m * Kp, b_bytes = (size_t)S * n * Kp;
+  const size_t need = a_bytes + b_bytes + (size_t)(m + n) * sizeof(int) + 8192;
+  if (need > ws->bytes) {
+    if (ws->buf) {
+      cudaStreamSynchronize(st);
+      cudaFree(ws->buf);
+    }
+    if (cudaMalloc(&ws->buf, need) != cudaSuccess) {
+      ws->buf = nullptr;
+      ws->bytes = 0;
+      return false;
+    }
+    ws->bytes = need;
+  }
+  auto up = [](char* p) { return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); };
+  int8_t* As = reinterpret_cast<int8_t*>(up(ws->buf));
+  int8_t* Bs = reinterpret_cast<int8_t*>(up(reinterpret_cast<char*>(As) + a_bytes));
+  int* ea = reinterpret_cast<int*>(up(reinterpret_cast<char*>(Bs) + b_bytes));
+  int* fb_ = ea + m;
+  if (reinterpret_cast<char*>(fb_ + n) > ws->buf + ws->bytes) return false;
+  ozaki_exponent_kernel<<<(m + 3) / 4, 128, 0, st>>>(a.p, a.rs, a.cs, m, k, ea);
+  ozaki_exponent_kernel<<<(n + 3) / 4, 128, 0, st>>>(b.p, b.cs, b.rs, n, k, fb_);
+  ozaki_slice_kernel<<<dim3(Kp / 32, (m + 31) / 32), 256, 0, st>>>(a.p, a.rs, a.cs, m, k, Kp, ea, As);
+  ozaki_slice_kernel<<<dim3(Kp / 32, (n + 31) / 32), 256, 0, st>>>(b.p, b.cs, b.rs, n, k, Kp, fb_, Bs);
+  CUtensorMap mA, mB;
+  if (!make_map(&mA, As, m, Kp, BM) || !make_map(&mB, Bs, n, Kp, BN)) return false;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_f64_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      return false;
+    configured = true;
+  }
+  const unsigned tiles = (unsigned)(((m + BM - 1) / BM) * ((n + BN - 1) / BN));
+  gemm_f64_ozaki_kernel<<<tiles, 256, SMEM_BYTES, st>>>(mA, mB, C, c_rs, c_cs, m, n, Kp / BK, ea, fb_, alpha, accum);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+}  // namespace oz
+}  // namespace fb
