@@ -14,6 +14,35 @@ namespace oracle {
 // 1580-1582 (Replace must not read dst).
 // The (i,j) loop is register-blocked for speed; each output element still sums in k order.
 // ------------------------------------------------------------------------------------------------
+// acc[b][a] = sum_k conj?(lhs(i0 + a, k)) * conj?(rhs(k, j0 + b)), k ascending (the scalar definition, matmul/mod.rs:1909-1947).
+// Full tiles of a unit-row-stride lhs take the fixed-trip-count loop, which the compiler vectorises along `a`; the
+// per-element operation order is the same on every path, so the results are bitwise independent of the path taken.
+constexpr int OR_BI = 8, OR_BJ = 4;
+template <class T>
+static inline void tile_product(T (&acc)[OR_BJ][OR_BI], const Mat<const T>& lhs, bool conj_lhs, const Mat<const T>& rhs,
+                                bool conj_rhs, i64 i0, i64 ni, i64 j0, i64 nj, i64 K) {
+  for (int b = 0; b < OR_BJ; ++b)
+    for (int a = 0; a < OR_BI; ++a) acc[b][a] = T(0);
+  if (ni == OR_BI && nj == OR_BJ && lhs.rs == 1) {
+    for (i64 k = 0; k < K; ++k) {
+      const T* lp = &lhs(i0, k);
+      T bv[OR_BJ];
+      for (int b = 0; b < OR_BJ; ++b) bv[b] = conj_if(conj_rhs, rhs(k, j0 + b));
+      for (int b = 0; b < OR_BJ; ++b)
+        for (int a = 0; a < OR_BI; ++a) acc[b][a] = acc[b][a] + conj_if(conj_lhs, lp[a]) * bv[b];
+    }
+    return;
+  }
+  for (i64 k = 0; k < K; ++k) {
+    T bv[OR_BJ];
+    for (i64 b = 0; b < nj; ++b) bv[b] = conj_if(conj_rhs, rhs(k, j0 + b));
+    for (i64 a = 0; a < ni; ++a) {
+      const T av = conj_if(conj_lhs, lhs(i0 + a, k));
+      for (i64 b = 0; b < nj; ++b) acc[b][a] = acc[b][a] + av * bv[b];
+    }
+  }
+}
+
 template <class T>
 void matmul(Mat<T> dst, bool add, Mat<const T> lhs, bool conj_lhs, Mat<const T> rhs, bool conj_rhs, T alpha) {
   const i64 M = dst.m, N = dst.n, K = lhs.n;
@@ -24,27 +53,18 @@ void matmul(Mat<T> dst, bool add, Mat<const T> lhs, bool conj_lhs, Mat<const T> 
         for (i64 i = 0; i < M; ++i) dst(i, j) = T(0);
     return;
   }
-  constexpr int BI = 8, BJ = 4;
+  constexpr int BI = OR_BI, BJ = OR_BJ;
   const i64 nbj = (N + BJ - 1) / BJ;
 #pragma omp parallel for schedule(dynamic, 1)
   for (i64 jb = 0; jb < nbj; ++jb) {
     const i64 j0 = jb * BJ, nj = std::min<i64>(BJ, N - j0);
     for (i64 i0 = 0; i0 < M; i0 += BI) {
       const i64 ni = std::min<i64>(BI, M - i0);
-      T acc[BI][BJ];
-      for (int a = 0; a < BI; ++a)
-        for (int b = 0; b < BJ; ++b) acc[a][b] = T(0);
-      for (i64 k = 0; k < K; ++k) {
-        T bv[BJ];
-        for (i64 b = 0; b < nj; ++b) bv[b] = conj_if(conj_rhs, rhs(k, j0 + b));
-        for (i64 a = 0; a < ni; ++a) {
-          const T av = conj_if(conj_lhs, lhs(i0 + a, k));
-          for (i64 b = 0; b < nj; ++b) acc[a][b] = acc[a][b] + av * bv[b];
-        }
-      }
+      T acc[BJ][BI];
+      tile_product<T>(acc, lhs, conj_lhs, rhs, conj_rhs, i0, ni, j0, nj, K);
       for (i64 b = 0; b < nj; ++b)
         for (i64 a = 0; a < ni; ++a) {
-          T v = acc[a][b] * alpha;
+          T v = acc[b][a] * alpha;
           if (add) v = dst(i0 + a, j0 + b) + v;
           dst(i0 + a, j0 + b) = v;
         }
@@ -80,6 +100,38 @@ void matmul_triangular(Mat<T> dst, int dst_s, bool add, Mat<const T> lhs, int lh
                        int rhs_s, bool conj_rhs, T alpha) {
   const i64 M = dst.m, N = dst.n, K = lhs.n;
   if (M == 0 || N == 0) return;
+  if (lhs_s == RECT && rhs_s == RECT) {
+    // Unstructured operands, structured destination (the SYRK-type trailing updates): same per-element arithmetic as
+    // the loop below (acc over k ascending, then * alpha, then + dst), computed on 8 x 4 register tiles like matmul();
+    // tiles entirely outside the selected triangle are skipped. Bitwise the same results, ~an order of magnitude faster.
+    constexpr int BI = OR_BI, BJ = OR_BJ;
+    const i64 nbj = (N + BJ - 1) / BJ;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (i64 jb = 0; jb < nbj; ++jb) {
+      const i64 j0 = jb * BJ, nj = std::min<i64>(BJ, N - j0);
+      for (i64 i0 = 0; i0 < M; i0 += BI) {
+        const i64 ni = std::min<i64>(BI, M - i0);
+        if (dst_s != RECT) {
+          if (s_lower(dst_s) && i0 + ni - 1 < j0) continue;  // tile strictly above the diagonal
+          if (s_upper(dst_s) && i0 > j0 + nj - 1) continue;  // tile strictly below the diagonal
+        }
+        T acc[BJ][BI];
+        tile_product<T>(acc, lhs, conj_lhs, rhs, conj_rhs, i0, ni, j0, nj, K);
+        for (i64 b = 0; b < nj; ++b)
+          for (i64 a = 0; a < ni; ++a) {
+            const i64 i = i0 + a, j = j0 + b;
+            if (dst_s != RECT) {
+              if (i == j && s_nodiag(dst_s)) continue;
+              if (i != j && (s_lower(dst_s) ? (i < j) : (i > j))) continue;
+            }
+            T v = acc[b][a] * alpha;
+            if (add) v = dst(i, j) + v;
+            dst(i, j) = v;
+          }
+      }
+    }
+    return;
+  }
 #pragma omp parallel for schedule(dynamic, 4)
   for (i64 j = 0; j < N; ++j) {
     for (i64 i = 0; i < M; ++i) {
