@@ -204,6 +204,76 @@ static bool ensure_green_streams() {
   return true;
 }
 
+// A second, independently sized partition for drivers whose panel kernel needs more SMs than the LU one (the QR panel
+// keeps its slices in shared memory: >= 42 CTAs at 65536 rows). Created on first use, one per requested size, never
+// resized. Used only by the opt-in look-ahead QR driver (qr.cu, FAER_B200_QR_LOOKAHEAD=1) — NOT RUN ON A GPU YET.
+bool partition_streams(int panel_sms, cudaStream_t* panel, cudaStream_t* urgent, cudaStream_t* bulk, int* got_panel_sms) {
+  struct Set {
+    int want;
+    int state;  // 0 = unused slot, 1 = ok, -1 = failed
+    cudaStream_t sp, su, sm;
+    int sms;
+  };
+  static Set sets[4] = {};
+  Set* s = nullptr;
+  for (auto& c : sets)
+    if (c.state != 0 && c.want == panel_sms) s = &c;
+  if (!s) {
+    for (auto& c : sets)
+      if (c.state == 0) {
+        s = &c;
+        break;
+      }
+    if (!s) return false;
+    s->want = panel_sms;
+    s->state = -1;
+    void* f[6] = {};
+    const char* names[6] = {"cuDeviceGet", "cuDeviceGetDevResource", "cuDevSmResourceSplitByCount", "cuDevResourceGenerateDesc",
+                            "cuGreenCtxCreate", "cuGreenCtxStreamCreate"};
+    for (int i = 0; i < 6; ++i) {
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(names[i], &f[i], cudaEnableDefault, &q) != cudaSuccess || !f[i]) return false;
+    }
+    auto p_get = (decltype(&cuDeviceGet))f[0];
+    auto p_res = (decltype(&cuDeviceGetDevResource))f[1];
+    auto p_split = (decltype(&cuDevSmResourceSplitByCount))f[2];
+    auto p_desc = (decltype(&cuDevResourceGenerateDesc))f[3];
+    auto p_ctx = (decltype(&cuGreenCtxCreate))f[4];
+    auto p_stream = (decltype(&cuGreenCtxStreamCreate))f[5];
+    int dev = 0;
+    FB_CUDA_CHECK(cudaGetDevice(&dev));
+    FB_CUDA_CHECK(cudaFree(0));
+    CUdevice cudev;
+    CUdevResource all, grp[1], rem;
+    unsigned int ngrp = 1;
+    CUdevResourceDesc d_panel, d_main;
+    CUgreenCtx g_panel, g_main;
+    CUstream sp, su, sm;
+    int lo = 0, hi = 0;
+    FB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (p_get(&cudev, dev) != CUDA_SUCCESS || p_res(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS ||
+        p_split(grp, &ngrp, &all, &rem, 0, (unsigned int)panel_sms) != CUDA_SUCCESS || ngrp < 1 ||
+        rem.type != CU_DEV_RESOURCE_TYPE_SM || rem.sm.smCount == 0 || p_desc(&d_panel, &grp[0], 1) != CUDA_SUCCESS ||
+        p_desc(&d_main, &rem, 1) != CUDA_SUCCESS || p_ctx(&g_panel, d_panel, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+        p_ctx(&g_main, d_main, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+        p_stream(&sp, g_panel, CU_STREAM_NON_BLOCKING, hi) != CUDA_SUCCESS ||
+        p_stream(&su, g_main, CU_STREAM_NON_BLOCKING, hi) != CUDA_SUCCESS ||
+        p_stream(&sm, g_main, CU_STREAM_NON_BLOCKING, lo) != CUDA_SUCCESS)
+      return false;
+    s->sp = (cudaStream_t)sp;
+    s->su = (cudaStream_t)su;
+    s->sm = (cudaStream_t)sm;
+    s->sms = (int)grp[0].sm.smCount;
+    s->state = 1;
+  }
+  if (s->state != 1) return false;
+  *panel = s->sp;
+  *urgent = s->su;
+  *bulk = s->sm;
+  *got_panel_sms = s->sms;
+  return true;
+}
+
 // ---- host-resident input: stream the matrix through the factorization ------------------------------------------------
 // The C ABI accepts host pointers (the reference is a CPU library). Copy-in / factor / copy-out would leave the GPU idle
 // during 2 x 2.1 GB of PCIe traffic at n = 16384; instead the block columns are uploaded in order on their own stream
