@@ -168,6 +168,17 @@ def load() -> C.CDLL:
             f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
             f.argtypes = [MatRef, MatRef, C.c_int, MatMut, P, MemAlloc]
             f.restype = None
+        f = getattr(lib, f"libfaer_v0_23_qr_solve_lstsq_in_place_scratch_{suf}")
+        f.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, P]
+        f.restype = Layout
+        for name in ("qr_solve_in_place", "qr_solve_transpose_in_place"):
+            f = getattr(lib, f"libfaer_v0_23_{name}_scratch_{suf}")
+            f.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, P]
+            f.restype = Layout
+        for name in ("qr_solve_lstsq_in_place", "qr_solve_in_place", "qr_solve_transpose_in_place"):
+            f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
+            f.argtypes = [MatRef, MatRef, MatRef, C.c_int, MatMut, P, MemAlloc]
+            f.restype = None
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.argtypes = [C.c_size_t, C.c_size_t, P]
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.restype = Layout
     lib.libfaer_v0_23_llt_solve_in_place_f64.argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]

@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 using namespace fb;
@@ -111,6 +112,40 @@ void tridiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
   StagedMat h(H.ptr, (i64)H.nrows, (i64)H.ncols, (i64)H.row_stride, (i64)H.col_stride, sizeof(T), true, true, st);
   tridiag_in_place<T>(st, a.view<T>(), h.view<T>());
   finish_all(st, {&a, &h});
+}
+// ---- solves on the QR factors (qr/no_pivoting/solve.rs) ----
+// mode 0: solve_lstsq_in_place_with_conj (solve.rs:38-76): rhs <- Q^H rhs, then R[..size, ..] x = rhs[..size, ..]
+// mode 1: solve_in_place_with_conj (solve.rs:96-119): the same on a square factorization
+// mode 2: solve_transpose_in_place_with_conj (solve.rs:140-176): rhs <- R^-T rhs (lower solve on the transposed view),
+//         then rhs <- conj(Q) rhs. Real scalar types only: the conj arguments are no-ops.
+template <class T>
+void qr_solve_entry(FaerV0_24_MatRef Qb, FaerV0_24_MatRef Qc, FaerV0_24_MatRef R, FaerV0_24_MatMut rhs, int mode) {
+  require_device();
+  cudaStream_t st = current_stream();
+  const size_t m = Qb.nrows, n = Qb.ncols, size = m < n ? m : n;
+  FB_ASSERT(Qc.nrows > 0 && rhs.nrows == m && m >= n && Qc.ncols == size && R.nrows >= size && R.ncols == n,
+            "QR solve shape mismatch");
+  if (mode != 0) FB_ASSERT(m == n && R.nrows == n, "QR solve: the factorization must be square");
+  if (size == 0 || rhs.ncols == 0) return;
+  StagedMat b(Qb.ptr, (i64)m, (i64)n, (i64)Qb.row_stride, (i64)Qb.col_stride, sizeof(T), true, false, st);
+  StagedMat f(Qc.ptr, (i64)Qc.nrows, (i64)Qc.ncols, (i64)Qc.row_stride, (i64)Qc.col_stride, sizeof(T), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, sizeof(T), true, true, st);
+  // callers normally pass the packed QR matrix for both Q_basis and R (solve.rs:232-246): stage it once
+  const bool alias = R.ptr == Qb.ptr && R.row_stride == Qb.row_stride && R.col_stride == Qb.col_stride;
+  std::unique_ptr<StagedMat> rr;
+  if (!alias)
+    rr.reset(new StagedMat(R.ptr, (i64)size, (i64)n, (i64)R.row_stride, (i64)R.col_stride, sizeof(T), true, false, st));
+  View<const T> Rv = (alias ? b.view<const T>() : rr->view<const T>()).sub(0, 0, (i64)size, (i64)n);
+  View<T> x = r.view<T>();
+  if (mode == 2) {
+    solve_lower(st, Rv.t(), false, x);
+    apply_block_householder_sequence_on_the_left<T>(st, b.view<const T>(), f.view<const T>(), x);
+  } else {
+    apply_block_householder_sequence_transpose_on_the_left<T>(st, b.view<const T>(), f.view<const T>(), x);
+    solve_upper(st, Rv, false, x.sub(0, 0, (i64)size, x.ncols));
+  }
+  finish_all(st, {&b, &f, &r});
+  if (rr) rr->finish();
 }
 }  // namespace
 
@@ -403,6 +438,40 @@ FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f6
                                                                    FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {        \
     (void)conj; (void)par; (void)mem;                                                                                  \
     householder_seq_entry<T>(basis, factor, rhs, true);                                                                \
+  }                                                                                                                    \
+  /* scratch: apply_block_householder_sequence_[transpose_]on_the_left_in_place_scratch (solve.rs:3-37) */           \
+  FaerV0_24_Layout libfaer_v0_23_qr_solve_lstsq_in_place_scratch_##SUF(size_t nrows, size_t ncols, size_t block_size,  \
+                                                                       size_t rhs_ncols, FaerV0_24_Par par) {          \
+    (void)nrows; (void)ncols; (void)par;                                                                               \
+    return FaerV0_24_Layout{block_size * rhs_ncols * sizeof(T), 64};                                                   \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_qr_solve_in_place_scratch_##SUF(size_t dim, size_t block_size, size_t rhs_ncols,      \
+                                                                 FaerV0_24_Par par) {                                  \
+    (void)dim; (void)par;                                                                                              \
+    return FaerV0_24_Layout{block_size * rhs_ncols * sizeof(T), 64};                                                   \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_qr_solve_transpose_in_place_scratch_##SUF(size_t dim, size_t block_size,              \
+                                                                           size_t rhs_ncols, FaerV0_24_Par par) {      \
+    (void)dim; (void)par;                                                                                              \
+    return FaerV0_24_Layout{block_size * rhs_ncols * sizeof(T), 64};                                                   \
+  }                                                                                                                    \
+  void libfaer_v0_23_qr_solve_lstsq_in_place_##SUF(FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff, FaerV0_24_MatRef R, \
+                                                   FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,     \
+                                                   FaerV0_24_MemAlloc mem) {                                           \
+    (void)A_conj; (void)par; (void)mem;                                                                                \
+    qr_solve_entry<T>(Q_basis, Q_coeff, R, rhs, 0);                                                                    \
+  }                                                                                                                    \
+  void libfaer_v0_23_qr_solve_in_place_##SUF(FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff, FaerV0_24_MatRef R,   \
+                                             FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,           \
+                                             FaerV0_24_MemAlloc mem) {                                                 \
+    (void)A_conj; (void)par; (void)mem;                                                                                \
+    qr_solve_entry<T>(Q_basis, Q_coeff, R, rhs, 1);                                                                    \
+  }                                                                                                                    \
+  void libfaer_v0_23_qr_solve_transpose_in_place_##SUF(FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff,             \
+                                                       FaerV0_24_MatRef R, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, \
+                                                       FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                    \
+    (void)A_conj; (void)par; (void)mem;                                                                                \
+    qr_solve_entry<T>(Q_basis, Q_coeff, R, rhs, 2);                                                                    \
   }
 FB_QR_FFI(f64, double)
 FB_QR_FFI(f32, float)

@@ -258,6 +258,31 @@ def apply_block_householder_sequence_transpose_on_the_left_in_place(basis, facto
         capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
+def _qr_solve(name, Q_basis, Q_coeff, R, rhs, conj, par):
+    lib = capi.load()
+    suf = _suf(rhs)
+    assert _suf(Q_basis) == suf and _suf(Q_coeff) == suf and _suf(R) == suf
+    getattr(lib, f"libfaer_v0_23_{name}_{suf}")(capi.mat_ref(Q_basis), capi.mat_ref(Q_coeff), capi.mat_ref(R), conj,
+                                               capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
+def qr_solve_lstsq_in_place(Q_basis, Q_coeff, R, rhs, conj: int = CONJ_NO, par=None) -> None:
+    """qr::no_pivoting::solve::solve_lstsq_in_place_with_conj (qr/no_pivoting/solve.rs:38-76): least-squares solution of
+    A x = rhs from the packed factors (Q_basis and R are normally the same matrix). rhs is m x k; the solution is
+    left in rhs[:ncols, :], the rest of rhs holds the residual's components along the orthogonal complement."""
+    _qr_solve("qr_solve_lstsq_in_place", Q_basis, Q_coeff, R, rhs, conj, par)
+
+
+def qr_solve_in_place(Q_basis, Q_coeff, R, rhs, conj: int = CONJ_NO, par=None) -> None:
+    """qr::no_pivoting::solve::solve_in_place_with_conj (solve.rs:96-119): rhs <- A^-1 rhs, square A."""
+    _qr_solve("qr_solve_in_place", Q_basis, Q_coeff, R, rhs, conj, par)
+
+
+def qr_solve_transpose_in_place(Q_basis, Q_coeff, R, rhs, conj: int = CONJ_NO, par=None) -> None:
+    """qr::no_pivoting::solve::solve_transpose_in_place_with_conj (solve.rs:140-176): rhs <- A^-T rhs, square A."""
+    _qr_solve("qr_solve_transpose_in_place", Q_basis, Q_coeff, R, rhs, conj, par)
+
+
 def bidiag_in_place(A, H_left, H_right, par=None, params=None) -> None:
     """svd::bidiag::bidiag_in_place (svd/bidiag.rs:47-256): A = U B V^H for nrows >= ncols, f64 or f32. B ends up on A's
     diagonal / superdiagonal, the left reflectors below the diagonal (T blocks in H_left, bl x ncols), the right

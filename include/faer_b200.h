@@ -197,6 +197,25 @@ struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u64_
 void libfaer_v0_23_partial_piv_lu_solve_in_place_u32_f64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 void libfaer_v0_23_partial_piv_lu_solve_in_place_u64_f64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
+/* solves on the QR factors: faer-ffi/src/lib.rs:1560-1660 (qr_solve_in_place[_scratch] 1560-1592,
+ * qr_solve_transpose_in_place[_scratch] 1593-1625, qr_solve_lstsq_in_place[_scratch] 1626-1660); faer.h:5828, 5864, 5906,
+ * 5946, 5990, 6026 (f64; the f32 declarations are the neighbouring ones). Semantics: faer/src/linalg/qr/no_pivoting/solve.rs:38-76
+ * (lstsq: rhs <- Q^H rhs, then the upper solve with R[..size, ..] on the first `size` rows of rhs; the solution is
+ * rhs[..ncols, ..]), 96-119 (square solve), 140-176 (transpose solve). Q_basis and R are normally the same packed
+ * matrix returned by qr_factor_in_place. Real types: A_conj is a no-op. */
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_lstsq_in_place_scratch_f64(size_t nrows, size_t ncols, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_in_place_scratch_f64(size_t dim, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_transpose_in_place_scratch_f64(size_t dim, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_qr_solve_lstsq_in_place_f64(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_in_place_f64(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_transpose_in_place_f64(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_lstsq_in_place_scratch_f32(size_t nrows, size_t ncols, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_in_place_scratch_f32(size_t dim, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_transpose_in_place_scratch_f32(size_t dim, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_qr_solve_lstsq_in_place_f32(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_in_place_f32(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_transpose_in_place_f32(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+
 /* global parallelism + allocation helpers.   faer-ffi/src/lib.rs:2521-2569, faer.h:724, 2034, 3080, 6108 */
 struct FaerV0_24_Par libfaer_v0_23_get_global_par(void);
 void libfaer_v0_23_set_global_par(struct FaerV0_24_Par par);

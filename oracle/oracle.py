@@ -173,6 +173,33 @@ def apply_q_sequence(QR, H, M, conj_lhs=False) -> None:
         b = bs
 
 
+def qr_solve_lstsq(QR, H, rhs, conj_QR=False) -> None:
+    """qr::no_pivoting::solve::solve_lstsq_in_place_with_conj (qr/no_pivoting/solve.rs:38-76): rhs <- op(Q)^H rhs (the
+    transpose sequence with conj_QR composed with Yes), then the upper solve with op(R)[..size, ..] on rhs[..size, ..];
+    op = conj if conj_QR. Q_basis and R are both the packed QR matrix, as in the reference's own test
+    (solve.rs:232-246)."""
+    m, n = QR.shape
+    size = min(m, n)
+    assert m >= n and rhs.shape[0] == m and H.shape[1] == size
+    apply_q_transpose_sequence(QR, H, rhs, conj_lhs=not conj_QR)
+    solve_triangular(QR[:size, :n], rhs[:size, :], lower=False, unit=False, conj=conj_QR)
+
+
+def qr_solve(QR, H, rhs, conj_QR=False) -> None:
+    """solve_in_place_with_conj (solve.rs:96-119): the square case of the above."""
+    assert QR.shape[0] == QR.shape[1]
+    qr_solve_lstsq(QR, H, rhs, conj_QR)
+
+
+def qr_solve_transpose(QR, H, rhs, conj_QR=False) -> None:
+    """solve_transpose_in_place_with_conj (solve.rs:140-176): lower solve with op(R)^T, then the forward sequence with
+    conj_QR composed with Yes, i.e. rhs <- op(A)^-T rhs."""
+    n = QR.shape[0]
+    assert QR.shape[1] == n and rhs.shape[0] == n
+    solve_triangular(QR.T, rhs, lower=True, unit=False, conj=conj_QR)
+    apply_q_sequence(QR, H, rhs, conj_lhs=not conj_QR)
+
+
 def bidiag(A, bl: int, br: int):
     """In-place bidiagonalization A = U B V^H, m >= n (svd/bidiag.rs:47-256). Returns (H_left [bl x n], H_right
     [br x (n-1)]). B is on A's diagonal / superdiagonal, left reflectors below the diagonal, right reflectors to the
