@@ -320,7 +320,7 @@ int dist_unique_id(void* out128) {
 }
 
 int dist_init(int rank, int nranks, const void* id128) {
-  require_device();
+  FB_ENTRY();
   if (!load_nccl()) return -1;
   if (g_comm) return 0;
   ncclUniqueId id;
@@ -458,7 +458,7 @@ static LltResult llt_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, dou
 // on P: every output element receives its rank-nb updates in the same order k = 0, 1, ...
 // -----------------------------------------------------------------------------------------------------------------
 LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta, double reg_eps, int lookahead) {
-  require_device();
+  FB_ENTRY();
   // `lookahead` bit 0: two-stream look-ahead; bit 1: purely local run (ignore the communicator even if one exists)
   const bool local_only = (lookahead & 2) != 0;
   lookahead &= 1;
@@ -605,7 +605,7 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
 // -----------------------------------------------------------------------------------------------------------------
 // LLT of a HOST column-major matrix (lower triangle), transfers overlapped with the factorization (see LltHostPipe).
 LltResult llt_host_pipelined_f64(double* hostA, i64 host_ld, i64 n, i64 nb, double reg_delta, double reg_eps) {
-  require_device();
+  FB_ENTRY();
   static cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   if (!s_h2d) {
     FB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
@@ -830,7 +830,7 @@ static void lu_local_partitioned_f64(double* A, i64 ld, i64 n, i64 nb, int* d_tr
 }
 
 size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, long long* perm_inv, int lookahead) {
-  require_device();
+  FB_ENTRY();
   // `lookahead` bit 0: two-stream look-ahead; bit 1: purely local run (ignore the communicator even if one exists)
   const bool local_only = (lookahead & 2) != 0;
   lookahead &= 1;

@@ -47,7 +47,7 @@ void finish_all(cudaStream_t st, std::initializer_list<StagedMat*> mats) {
 }
 
 void solve_tri(FaerV0_24_MatRef T, FaerV0_24_MatMut rhs, bool lower, bool unit) {
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   FB_ASSERT(T.nrows == T.ncols && rhs.nrows == T.ncols, "triangular solve shape mismatch");
   Mat t(T, st);
@@ -62,7 +62,7 @@ void solve_tri(FaerV0_24_MatRef T, FaerV0_24_MatMut rhs, bool lower, bool unit) 
 // ---- Householder QR (no pivoting) + block-Householder sequence application, f64 and f32 ----
 template <class T>
 FaerV0_24_QrStatus qr_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Q) {
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   const size_t size = A.nrows < A.ncols ? A.nrows : A.ncols;
   FB_ASSERT(Q.nrows > 0 && Q.ncols == size, "Q_coeff must be block_size x min(nrows, ncols)");
@@ -83,7 +83,7 @@ FaerV0_24_QrStatus qr_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Q) {
 }
 template <class T>
 void householder_seq_entry(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, FaerV0_24_MatMut rhs, bool transpose) {
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   StagedMat b(basis.ptr, (i64)basis.nrows, (i64)basis.ncols, (i64)basis.row_stride, (i64)basis.col_stride, sizeof(T), true, false, st);
   StagedMat f(factor.ptr, (i64)factor.nrows, (i64)factor.ncols, (i64)factor.row_stride, (i64)factor.col_stride, sizeof(T), true, false, st);
@@ -95,7 +95,7 @@ void householder_seq_entry(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, Faer
 // ---- reductions to condensed form (svd/bidiag.rs:47-256) ----
 template <class T>
 void bidiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Hl, FaerV0_24_MatMut Hr) {
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
   StagedMat hl(Hl.ptr, (i64)Hl.nrows, (i64)Hl.ncols, (i64)Hl.row_stride, (i64)Hl.col_stride, sizeof(T), true, true, st);
@@ -106,7 +106,7 @@ void bidiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Hl, FaerV0_24_MatMut Hr) 
 // evd/tridiag.rs:274-529
 template <class T>
 void tridiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
   StagedMat h(H.ptr, (i64)H.nrows, (i64)H.ncols, (i64)H.row_stride, (i64)H.col_stride, sizeof(T), true, true, st);
@@ -120,7 +120,7 @@ void tridiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
 //         then rhs <- conj(Q) rhs. Real scalar types only: the conj arguments are no-ops.
 template <class T>
 void qr_solve_entry(FaerV0_24_MatRef Qb, FaerV0_24_MatRef Qc, FaerV0_24_MatRef R, FaerV0_24_MatMut rhs, int mode) {
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   const size_t m = Qb.nrows, n = Qb.ncols, size = m < n ? m : n;
   FB_ASSERT(Qc.nrows > 0 && rhs.nrows == m && m >= n && Qc.ncols == size && R.nrows >= size && R.ncols == n,
@@ -154,7 +154,7 @@ extern "C" {
 void libfaer_v0_23_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
                               const FaerV0_24_Scalar* alpha, FaerV0_24_Par par) {
   (void)par;
-  require_device();
+  FB_ENTRY();
   FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
   cudaStream_t st = current_stream();
   const double a = read_scalar_f64(alpha);
@@ -169,7 +169,7 @@ void libfaer_v0_23_matmul_triangular_f64(FaerV0_24_MatMut C, FaerV0_24_Block C_b
                                          FaerV0_24_MatRef A, FaerV0_24_Block A_block, FaerV0_24_MatRef B,
                                          FaerV0_24_Block B_block, const FaerV0_24_Scalar* alpha, FaerV0_24_Par par) {
   (void)par;
-  require_device();
+  FB_ENTRY();
   FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
   cudaStream_t st = current_stream();
   const double a = read_scalar_f64(alpha);
@@ -184,7 +184,7 @@ void libfaer_v0_23_matmul_triangular_f64(FaerV0_24_MatMut C, FaerV0_24_Block C_b
 // ---- f32 matmul (3xTF32 tensor-core kernel) ----
 static void matmul_f32_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum accum, FaerV0_24_MatRef A, int A_block,
                             FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha) {
-  require_device();
+  FB_ENTRY();
   FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
   cudaStream_t st = current_stream();
   FB_ASSERT(alpha != nullptr, "null scalar pointer");
@@ -214,7 +214,7 @@ void libfaer_v0_23_matmul_triangular_f32(FaerV0_24_MatMut C, FaerV0_24_Block C_b
 // ---- c64 matmul (interleaved complex<f64>; `alpha` points to a complex scalar) ----
 static void matmul_c64_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum accum, FaerV0_24_MatRef A, int A_block,
                             FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha) {
-  require_device();
+  FB_ENTRY();
   FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
   cudaStream_t st = current_stream();
   FB_ASSERT(alpha != nullptr, "null scalar pointer");
@@ -248,7 +248,7 @@ void libfaer_v0_23_matmul_triangular_c64(FaerV0_24_MatMut C, FaerV0_24_Block C_b
 
 static void matmul_c32_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum accum, FaerV0_24_MatRef A, int A_block,
                             FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha) {
-  require_device();
+  FB_ENTRY();
   FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
   cudaStream_t st = current_stream();
   FB_ASSERT(alpha != nullptr, "null scalar pointer");
@@ -317,7 +317,7 @@ FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(FaerV0_24_MatMut A, Fa
                                                           FaerV0_24_Par par, FaerV0_24_MemAlloc mem,
                                                           FaerV0_24_LltParams params) {
   (void)par; (void)mem;
-  require_device();
+  FB_ENTRY();
   FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
   cudaStream_t st = current_stream();
   double delta = 0.0, eps = 0.0;
@@ -374,7 +374,7 @@ FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_f64(si
 
 static FaerV0_24_PartialPivLuStatus lu_entry(FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd,
                                              FaerV0_24_PartialPivLuParams params, int idx_bytes) {
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   // NB: faer.hpp fills SliceMut.len with BYTES while the Rust side reads elements, so the
   // permutation length is taken from A.nrows, never from `len`.
@@ -485,7 +485,7 @@ FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_f64(size_t dim, size_t
 void libfaer_v0_23_llt_solve_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,
                                           FaerV0_24_MemAlloc mem) {
   (void)A_conj; (void)par; (void)mem;
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   FB_ASSERT(L.nrows == L.ncols && rhs.nrows == L.nrows, "LLT solve shape mismatch");
   Mat l(L, st);
@@ -507,7 +507,7 @@ static std::vector<long long> read_perm(const void* p, size_t n, int idx_bytes) 
 }
 static void lu_solve_entry(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_SliceRef perm_fwd, FaerV0_24_MatMut rhs,
                            int idx_bytes) {
-  require_device();
+  FB_ENTRY();
   cudaStream_t st = current_stream();
   const size_t n = L.nrows;
   FB_ASSERT(L.ncols == n && U.nrows == n && U.ncols == n && rhs.nrows == n, "LU solve shape mismatch");
@@ -571,15 +571,21 @@ int faer_b200_device_count(void) {
   }
   return n;
 }
-void faer_b200_set_stream(void* cuda_stream) { set_current_stream((cudaStream_t)cuda_stream); }
+void faer_b200_set_stream(void* cuda_stream) { std::lock_guard<std::recursive_mutex> lock(entry_mutex()); set_current_stream((cudaStream_t)cuda_stream); }
 unsigned long long faer_b200_launch_count(void) { return g_launch_count; }
-void faer_b200_release_workspace(void) { ws_release_all(); }
-void faer_b200_profile_begin(void) { profile_begin(); }
-void faer_b200_profile_end(double* flops, double* ms, unsigned long long* count) { profile_end(flops, ms, count); }
+void faer_b200_release_workspace(void) { std::lock_guard<std::recursive_mutex> lock(entry_mutex()); ws_release_all(); }
+void faer_b200_profile_begin(void) { std::lock_guard<std::recursive_mutex> lock(entry_mutex()); profile_begin(); }
+void faer_b200_profile_end(double* flops, double* ms, unsigned long long* count) {
+  std::lock_guard<std::recursive_mutex> lock(entry_mutex()); 
+  profile_end(flops, ms, count);
+}
 // ---- multi-GPU extensions (dist.cu) ----
 int faer_b200_dist_unique_id(void* out128) { return dist_unique_id(out128); }
-int faer_b200_dist_init(int rank, int nranks, const void* id128) { return dist_init(rank, nranks, id128); }
-void faer_b200_dist_finalize(void) { dist_finalize(); }
+int faer_b200_dist_init(int rank, int nranks, const void* id128) {
+  std::lock_guard<std::recursive_mutex> lock(entry_mutex()); 
+  return dist_init(rank, nranks, id128);
+}
+void faer_b200_dist_finalize(void) { std::lock_guard<std::recursive_mutex> lock(entry_mutex()); dist_finalize(); }
 FaerV0_24_LltStatus faer_b200_dist_llt_factor_in_place_f64(void* A_local, size_t ld, size_t n, size_t nb,
                                                            FaerV0_24_LltRegularization regularization, int lookahead) {
   double delta = 0.0, eps = 0.0;

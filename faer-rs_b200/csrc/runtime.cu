@@ -23,6 +23,11 @@ bool g_checked_device = false;
 cudaStream_t current_stream() { return g_stream; }
 void set_current_stream(cudaStream_t s) { g_stream = s; }
 
+std::recursive_mutex& entry_mutex() {
+  static std::recursive_mutex m;
+  return m;
+}
+
 void require_device() {
   if (g_checked_device) return;
   int n = 0;

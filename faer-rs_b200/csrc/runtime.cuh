@@ -3,12 +3,22 @@
 #include "common.cuh"
 #include "linalg_f64.cuh"
 
+#include <mutex>
+
 namespace fb {
 
 cudaStream_t current_stream();
 void set_current_stream(cudaStream_t s);
 // abort()s with a clear message if no CUDA device is usable (there is no CPU fallback).
 void require_device();
+// Every compute entry point of the C ABI holds this lock for the whole call. The library keeps per-process state
+// (current stream, workspace pool, per-stream scratch, packed-operand workspaces, SM partitions, launch counter) and one
+// GPU runs one factorization at a time anyway, so concurrent callers (the reference's entry points are reentrant) are
+// serialised instead of racing. Recursive: entry points may call each other.
+std::recursive_mutex& entry_mutex();
+#define FB_ENTRY()                                                              \
+  std::lock_guard<std::recursive_mutex> fb_entry_lock_(::fb::entry_mutex()); \
+  ::fb::require_device()
 bool is_device_pointer(const void* p);
 
 // Optional per-launch timing of the dominant kernel (bench.py roofline): CUDA events around each GEMM launch.

@@ -81,3 +81,41 @@ def test_product_does_not_touch_the_oracle():
                 assert "oracle" not in txt.lower(), f"{f} mentions the oracle: the product path must not depend on it"
     out = subprocess.check_output(["ldd", os.path.join(pkg, "libfaer_b200.so")], text=True)
     assert "oracle" not in out
+
+
+def test_qr_solve_scratch_queries(fb):
+    """qr/no_pivoting/solve.rs:3-37: all three solves need the block-Householder sequence scratch,
+    temp_mat_scratch(block_size, rhs_ncols)."""
+    lib = fb.load()
+    par = fb.capi.par_default()
+    for suf, sz in (("f64", 8), ("f32", 4)):
+        lay = getattr(lib, f"libfaer_v0_23_qr_solve_lstsq_in_place_scratch_{suf}")(1000, 300, 32, 7, par)
+        assert lay.len_bytes == 32 * 7 * sz
+        for name in ("qr_solve_in_place", "qr_solve_transpose_in_place"):
+            lay = getattr(lib, f"libfaer_v0_23_{name}_scratch_{suf}")(300, 16, 5, par)
+            assert lay.len_bytes == 16 * 5 * sz
+
+
+def test_state_touching_entry_points_are_serialised(fb):
+    """The entry points that touch per-process state take the library's entry lock (runtime.cuh: FB_ENTRY); hammer the
+    ones that need no GPU from several threads (ctypes drops the GIL during the calls)."""
+    import threading
+    lib = fb.load()
+    errs = []
+
+    def work():
+        try:
+            for _ in range(2000):
+                lib.faer_b200_set_stream(None)
+                lib.faer_b200_launch_count()
+                lib.faer_b200_release_workspace()
+                p = lib.libfaer_v0_23_alloc(256, 64)
+                assert p and p % 64 == 0
+                lib.libfaer_v0_23_dealloc(p, 256, 64)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work) for _ in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
