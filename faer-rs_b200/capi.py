@@ -130,9 +130,10 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_matmul_triangular_c32.restype = None
     for name in ("solve_triangular_lower", "solve_triangular_upper", "solve_unit_triangular_lower",
                  "solve_unit_triangular_upper"):
-        f = getattr(lib, f"libfaer_v0_23_{name}_in_place_f64")
-        f.argtypes = [MatRef, C.c_int, MatMut, P]
-        f.restype = None
+        for suf in ("f64", "f32"):
+            f = getattr(lib, f"libfaer_v0_23_{name}_in_place_{suf}")
+            f.argtypes = [MatRef, C.c_int, MatMut, P]
+            f.restype = None
     lib.libfaer_v0_23_LltParams_f64.argtypes = []
     lib.libfaer_v0_23_LltParams_f64.restype = LltParams
     lib.libfaer_v0_23_llt_factor_in_place_scratch_f64.argtypes = [C.c_size_t, P, LltParams]

@@ -46,17 +46,16 @@ void finish_all(cudaStream_t st, std::initializer_list<StagedMat*> mats) {
   for (auto* m : mats) m->finish();
 }
 
+template <class S>
 void solve_tri(FaerV0_24_MatRef T, FaerV0_24_MatMut rhs, bool lower, bool unit) {
   FB_ENTRY();
   cudaStream_t st = current_stream();
   FB_ASSERT(T.nrows == T.ncols && rhs.nrows == T.ncols, "triangular solve shape mismatch");
-  Mat t(T, st);
-  Mat r(rhs, true, st);
-  if (lower)
-    solve_lower_triangular_in_place_f64(st, t.s.view<const double>(), unit, r.s.view<double>());
-  else
-    solve_upper_triangular_in_place_f64(st, t.s.view<const double>(), unit, r.s.view<double>());
-  finish_all(st, {&t.s, &r.s});
+  StagedMat t(T.ptr, (i64)T.nrows, (i64)T.ncols, (i64)T.row_stride, (i64)T.col_stride, sizeof(S), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, sizeof(S), true, true, st);
+  if (lower) solve_lower(st, t.view<const S>(), unit, r.view<S>());  // tensor_ops.cuh: f64 / f32 spellings of trsm.cu
+  else solve_upper(st, t.view<const S>(), unit, r.view<S>());
+  finish_all(st, {&t, &r});
 }
 
 // ---- Householder QR (no pivoting) + block-Householder sequence application, f64 and f32 ----
@@ -278,26 +277,30 @@ void libfaer_v0_23_matmul_triangular_c32(FaerV0_24_MatMut C, FaerV0_24_Block C_b
   matmul_c32_impl(C, (int)C_block, accum, A, (int)A_block, B, (int)B_block, alpha);
 }
 
-void libfaer_v0_23_solve_triangular_lower_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs,
-                                                       FaerV0_24_Par par) {
-  (void)L_conj; (void)par;  // conjugation is the identity for real scalars
-  solve_tri(L, rhs, true, false);
-}
-void libfaer_v0_23_solve_triangular_upper_in_place_f64(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs,
-                                                       FaerV0_24_Par par) {
-  (void)U_conj; (void)par;
-  solve_tri(U, rhs, false, false);
-}
-void libfaer_v0_23_solve_unit_triangular_lower_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj,
-                                                            FaerV0_24_MatMut rhs, FaerV0_24_Par par) {
-  (void)L_conj; (void)par;
-  solve_tri(L, rhs, true, true);
-}
-void libfaer_v0_23_solve_unit_triangular_upper_in_place_f64(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj,
-                                                            FaerV0_24_MatMut rhs, FaerV0_24_Par par) {
-  (void)U_conj; (void)par;
-  solve_tri(U, rhs, false, true);
-}
+#define FB_TRSM_FFI(SUF, T)                                                                                            \
+  void libfaer_v0_23_solve_triangular_lower_in_place_##SUF(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs, \
+                                                           FaerV0_24_Par par) {                                        \
+    (void)L_conj; (void)par;                                                                                           \
+    solve_tri<T>(L, rhs, true, false);                                                                                 \
+  }                                                                                                                    \
+  void libfaer_v0_23_solve_triangular_upper_in_place_##SUF(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs, \
+                                                           FaerV0_24_Par par) {                                        \
+    (void)U_conj; (void)par;                                                                                           \
+    solve_tri<T>(U, rhs, false, false);                                                                                \
+  }                                                                                                                    \
+  void libfaer_v0_23_solve_unit_triangular_lower_in_place_##SUF(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj,             \
+                                                                FaerV0_24_MatMut rhs, FaerV0_24_Par par) {             \
+    (void)L_conj; (void)par;                                                                                           \
+    solve_tri<T>(L, rhs, true, true);                                                                                  \
+  }                                                                                                                    \
+  void libfaer_v0_23_solve_unit_triangular_upper_in_place_##SUF(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj,             \
+                                                                FaerV0_24_MatMut rhs, FaerV0_24_Par par) {             \
+    (void)U_conj; (void)par;                                                                                           \
+    solve_tri<T>(U, rhs, false, true);                                                                                 \
+  }
+FB_TRSM_FFI(f64, double)
+FB_TRSM_FFI(f32, float)
+#undef FB_TRSM_FFI
 
 // ---- LLT ----
 FaerV0_24_LltParams libfaer_v0_23_LltParams_f64(void) {

@@ -134,10 +134,15 @@ def matmul_triangular(dst, dst_structure: int, accum: int, lhs, lhs_structure: i
 
 
 def _solve(name, tri, rhs, conj, par):
-    _check_f64(tri, rhs)
+    """triangular_solve.rs:220-419; f64 or f32."""
+    suf = "f32" if _is_f32(rhs) else "f64"
+    if suf == "f32":
+        assert _is_f32(tri), "f32 entry point needs float32 operands"
+    else:
+        _check_f64(tri, rhs)
     lib = capi.load()
-    getattr(lib, f"libfaer_v0_23_{name}_in_place_f64")(capi.mat_ref(tri), conj, capi.mat_mut(rhs),
-                                                       par or capi.par_default())
+    getattr(lib, f"libfaer_v0_23_{name}_in_place_{suf}")(capi.mat_ref(tri), conj, capi.mat_mut(rhs),
+                                                         par or capi.par_default())
 
 
 def solve_lower_triangular_in_place(tril, rhs, conj: int = CONJ_NO, par=None) -> None:

@@ -147,6 +147,15 @@ void libfaer_v0_23_solve_unit_triangular_lower_in_place_f64(struct FaerV0_24_Mat
                                                             struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
 void libfaer_v0_23_solve_unit_triangular_upper_in_place_f64(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj,
                                                             struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+/* f32: faer.h:6125-6215 */
+void libfaer_v0_23_solve_triangular_lower_in_place_f32(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj L_conj,
+                                                       struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_triangular_upper_in_place_f32(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj,
+                                                       struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_unit_triangular_lower_in_place_f32(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj L_conj,
+                                                            struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_unit_triangular_upper_in_place_f32(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj,
+                                                            struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
 
 /* LLT.   params: faer-ffi/src/lib.rs:650-654 (+408-456), faer.h:636; scratch: lib.rs:984-995; factor: lib.rs:996-1010, faer.h:4036-4040 */
 struct FaerV0_24_LltParams libfaer_v0_23_LltParams_f64(void);
