@@ -191,6 +191,12 @@ def load() -> C.CDLL:
         f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_f64")
         f.argtypes = [MatRef, MatRef, C.c_int, SliceMut, SliceMut, MatMut, P, MemAlloc]
         f.restype = None
+        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_{it}_f64")
+        f.argtypes = [C.c_size_t, C.c_size_t, P]
+        f.restype = Layout
+        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_{it}_f64")
+        f.argtypes = [MatRef, MatRef, C.c_int, SliceMut, SliceMut, MatMut, P, MemAlloc]
+        f.restype = None
     lib.libfaer_v0_23_get_global_par.argtypes = []
     lib.libfaer_v0_23_get_global_par.restype = Par
     lib.libfaer_v0_23_set_global_par.argtypes = [Par]

@@ -508,17 +508,21 @@ static std::vector<long long> read_perm(const void* p, size_t n, int idx_bytes) 
     out[i] = idx_bytes == 4 ? (long long)((const uint32_t*)raw.data())[i] : (long long)((const uint64_t*)raw.data())[i];
   return out;
 }
-static void lu_solve_entry(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_SliceRef perm_fwd, FaerV0_24_MatMut rhs,
-                           int idx_bytes) {
+// transpose = false: perm is perm_fwd (solve.rs:21-54); transpose = true: perm is perm_bwd (solve.rs:55-86)
+static void lu_solve_entry(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_SliceRef perm_slice, FaerV0_24_MatMut rhs,
+                           int idx_bytes, bool transpose = false) {
   FB_ENTRY();
   cudaStream_t st = current_stream();
   const size_t n = L.nrows;
   FB_ASSERT(L.ncols == n && U.nrows == n && U.ncols == n && rhs.nrows == n, "LU solve shape mismatch");
-  std::vector<long long> perm = read_perm(perm_fwd.ptr, n, idx_bytes);  // length from L.nrows (see lu_entry note)
+  std::vector<long long> perm = read_perm(perm_slice.ptr, n, idx_bytes);  // length from L.nrows (see lu_entry note)
   for (size_t i = 0; i < n; ++i) FB_ASSERT(perm[i] >= 0 && (size_t)perm[i] < n, "invalid permutation entry");
   Mat l(L, st), u(U, st);
   Mat r(rhs, true, st);
-  lu_solve_in_place_f64(st, l.s.view<const double>(), u.s.view<const double>(), perm.data(), r.s.view<double>());
+  if (transpose)
+    lu_solve_transpose_in_place_f64(st, l.s.view<const double>(), u.s.view<const double>(), perm.data(), r.s.view<double>());
+  else
+    lu_solve_in_place_f64(st, l.s.view<const double>(), u.s.view<const double>(), perm.data(), r.s.view<double>());
   finish_all(st, {&l.s, &u.s, &r.s});
 }
 FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u32_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
@@ -540,6 +544,26 @@ void libfaer_v0_23_partial_piv_lu_solve_in_place_u64_f64(FaerV0_24_MatRef L, Fae
                                                          FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
   (void)A_conj; (void)perm_bwd; (void)par; (void)mem;
   lu_solve_entry(L, U, perm_fwd, rhs, 8);
+}
+FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u32_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
+  (void)par;
+  return FaerV0_24_Layout{dim * rhs_ncols * sizeof(double), 64};
+}
+FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u64_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
+  (void)par;
+  return FaerV0_24_Layout{dim * rhs_ncols * sizeof(double), 64};
+}
+void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u32_f64(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj,
+                                                                   FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,
+                                                                   FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
+  (void)A_conj; (void)perm_fwd; (void)par; (void)mem;
+  lu_solve_entry(L, U, perm_bwd, rhs, 4, true);
+}
+void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_f64(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj,
+                                                                   FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,
+                                                                   FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
+  (void)A_conj; (void)perm_fwd; (void)par; (void)mem;
+  lu_solve_entry(L, U, perm_bwd, rhs, 8, true);
 }
 
 // ---- global par / alloc ----

@@ -47,6 +47,8 @@ size_t lu_partial_piv_in_place_f64(cudaStream_t stream, VD A, void* perm_fwd, vo
 void permute_rows_in_place_f64(cudaStream_t stream, VD rhs, const long long* perm_fwd_host);
 void llt_solve_in_place_f64(cudaStream_t stream, VCD L, VD rhs);
 void lu_solve_in_place_f64(cudaStream_t stream, VCD L, VCD U, const long long* perm_fwd_host, VD rhs);
+// rhs <- A^-T rhs (lu/partial_pivoting/solve.rs:55-86); perm_bwd: HOST int64 array, the inverse row permutation
+void lu_solve_transpose_in_place_f64(cudaStream_t stream, VCD L, VCD U, const long long* perm_bwd_host, VD rhs);
 
 // workspace-based LU building blocks (used by dist.cu); all work is enqueued on the stream given at creation
 struct LuWorkspace;

@@ -6,6 +6,9 @@
 //   lu::partial_pivoting::solve::solve_in_place_with_conj   faer/src/linalg/lu/partial_pivoting/solve.rs:21-54
 //       rhs <- P rhs (permute_rows_in_place: dst[i, :] = src[perm_fwd[i], :], perm/mod.rs:256-294),
 //       unit-lower solve with L, upper solve with U
+//   lu::partial_pivoting::solve::solve_transpose_in_place_with_conj   lu/partial_pivoting/solve.rs:55-86
+//       lower solve with U^T, unit-upper solve with L^T, then rhs <- P^-1 rhs (permute_rows_in_place with the inverse
+//       permutation, whose forward array is perm_bwd)
 #include <vector>
 
 #include "runtime.cuh"
@@ -62,6 +65,14 @@ void lu_solve_in_place_f64(cudaStream_t stream, VCD L, VCD U, const long long* p
   permute_rows_in_place_f64(stream, rhs, perm_fwd);
   solve_lower_triangular_in_place_f64(stream, L, true, rhs);
   solve_upper_triangular_in_place_f64(stream, U, false, rhs);
+}
+
+void lu_solve_transpose_in_place_f64(cudaStream_t stream, VCD L, VCD U, const long long* perm_bwd, VD rhs) {
+  const i64 n = L.nrows;
+  FB_ASSERT(L.ncols == n && U.nrows == n && U.ncols == n && rhs.nrows == n, "LU solve shape mismatch");
+  solve_lower_triangular_in_place_f64(stream, U.t(), false, rhs);
+  solve_upper_triangular_in_place_f64(stream, L.t(), true, rhs);
+  permute_rows_in_place_f64(stream, rhs, perm_bwd);
 }
 
 }  // namespace fb

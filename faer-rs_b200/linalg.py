@@ -220,6 +220,18 @@ def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None) ->
         par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
+def lu_solve_transpose_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None) -> None:
+    """lu::partial_pivoting::solve::solve_transpose_in_place_with_conj (lu/partial_pivoting/solve.rs:55-86):
+    rhs <- A^-T rhs from the packed factors and the row permutation (its inverse array is the one used)."""
+    _check_f64(LU, rhs)
+    lib = capi.load()
+    isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
+    it = {4: "u32", 8: "u64"}[isz]
+    getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_{it}_f64")(
+        capi.mat_ref(LU), capi.mat_ref(LU), conj, capi.slice_mut(perm), capi.slice_mut(perm_inv), capi.mat_mut(rhs),
+        par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
 # ---- Householder QR (no pivoting) -----------------------------------------------------------------
 @dataclass
 class QrInfo:
