@@ -208,19 +208,21 @@ def llt_solve_in_place(L, rhs, conj: int = CONJ_NO, par=None) -> None:
                                              capi.MemAlloc(None, 0))
 
 
-def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None) -> None:
+def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None, U=None) -> None:
     """lu::partial_pivoting::solve::solve_in_place_with_conj (lu/partial_pivoting/solve.rs:21-54):
-    rhs <- A^-1 rhs from the packed factors (L unit-lower below the diagonal, U on/above) and the row permutation."""
+    rhs <- A^-1 rhs from the packed factors (L unit-lower below the diagonal, U on/above) and the row permutation.
+    With `U` given, `LU` is read as L only (its strict lower part) and `U` as the upper factor, as the reference's
+    separate `L`, `U` arguments."""
     _check_f64(LU, rhs)
     lib = capi.load()
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
     it = {4: "u32", 8: "u64"}[isz]
     getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_f64")(
-        capi.mat_ref(LU), capi.mat_ref(LU), conj, capi.slice_mut(perm), capi.slice_mut(perm_inv), capi.mat_mut(rhs),
+        capi.mat_ref(LU), capi.mat_ref(LU if U is None else U), conj, capi.slice_mut(perm), capi.slice_mut(perm_inv), capi.mat_mut(rhs),
         par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
-def lu_solve_transpose_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None) -> None:
+def lu_solve_transpose_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None, U=None) -> None:
     """lu::partial_pivoting::solve::solve_transpose_in_place_with_conj (lu/partial_pivoting/solve.rs:55-86):
     rhs <- A^-T rhs from the packed factors and the row permutation (its inverse array is the one used)."""
     _check_f64(LU, rhs)
@@ -228,7 +230,7 @@ def lu_solve_transpose_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, pa
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
     it = {4: "u32", 8: "u64"}[isz]
     getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_{it}_f64")(
-        capi.mat_ref(LU), capi.mat_ref(LU), conj, capi.slice_mut(perm), capi.slice_mut(perm_inv), capi.mat_mut(rhs),
+        capi.mat_ref(LU), capi.mat_ref(LU if U is None else U), conj, capi.slice_mut(perm), capi.slice_mut(perm_inv), capi.mat_mut(rhs),
         par or capi.par_default(), capi.MemAlloc(None, 0))
 
 

@@ -17,5 +17,6 @@ _pkg = sys.modules[_NAME]
 capi = _pkg.capi
 linalg = _pkg.linalg
 dist = _pkg.dist
+solvers = _pkg.solvers
 load = _pkg.load
 PKG_DIR = _PKG_DIR
