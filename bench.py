@@ -96,12 +96,14 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU legs (oracle = test infrastructure; this is one of the two places allowed to execute it)
 # ---------------------------------------------------------------------------------------------------
-def cpu_llt_sample(target_seconds: float = 15.0, n_cap: int = 8192):
+def cpu_llt_sample(target_seconds: float = 15.0, n_cap: int = 12288):
     """Time the CPU restatement of faer's LLT on all host cores on a bounded sample (same generator, smaller n)."""
     from oracle import oracle as orc
     orc.load()
-    # The restatement keeps faer's 128-wide recursion, i.e. thousands of small OpenMP regions: beyond ~32 threads the
-    # fork/join cost dominates (measured on the GPU box: 0.0007 TFLOP/s with 128 threads vs 0.017 with 64), so cap the team.
+    # The restatement keeps faer's 128-wide recursion, i.e. many small OpenMP regions: beyond ~32 threads the fork/join
+    # cost dominated on the GPU box (first version: 0.0007 TFLOP/s with 128 threads vs 0.017 with 64), so the team is
+    # capped. Since then the products run cache-blocked on packed panels and the triangular solves fork once per solve
+    # (bitwise the same results; 5x faster on 8 cores here), but the cap has not been re-measured on the box.
     cores = max(1, min(os.cpu_count() or 1, 32))
     orc.set_num_threads(cores)
     rng = np.random.default_rng(0)
@@ -148,7 +150,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     times = []
-    base, n, _ = cpu_llt_sample(target_seconds=6.0, n_cap=6144)
+    base, n, _ = cpu_llt_sample(target_seconds=6.0, n_cap=8192)
     from oracle import oracle as orc
     rng = np.random.default_rng(1)
     for it in range(args.warmup + args.steps):

@@ -1,8 +1,11 @@
 // TEST INFRASTRUCTURE — NOT PRODUCT CODE. See oracle.hpp for the contract and the parity-pinning statement.
 #include "oracle.hpp"
 
+#include <omp.h>
+
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 namespace oracle {
 
@@ -43,6 +46,117 @@ static inline void tile_product(T (&acc)[OR_BJ][OR_BI], const Mat<const T>& lhs,
   }
 }
 
+// ---- cache-blocked form of the same definition -----------------------------------------------------------------
+// Large products run on packed panels (the classical MC x KC / KC x NC blocking): a task owns an MC x NC block of dst,
+// packs the operands KC columns at a time into contiguous 8-row / 4-column micro-panels (conjugation applied while
+// packing, zero padding at the edges) and keeps the raw accumulators of its block in a local buffer between K blocks.
+// Every output element is still  acc = 0; acc = acc + a_ik * b_kj for k ascending; v = acc * alpha; dst (+)= v  with
+// unfused multiply and add, so the results are bitwise those of the loops above and below; only the memory traffic
+// changes (the unpacked loop touches one cache line of lhs per k). Tasks are independent: OpenMP over the 2-D grid.
+constexpr i64 OR_MC = 128, OR_NC = 64, OR_KC = 256;
+
+static inline bool s_lower(int s);
+static inline bool s_upper(int s);
+static inline bool s_nodiag(int s);
+
+template <class T>
+static inline void micro_kernel(T* __restrict c, const T* __restrict ap, const T* __restrict bp, i64 kc) {
+  T acc[OR_BJ][OR_BI];
+  for (int b = 0; b < OR_BJ; ++b)
+    for (int a = 0; a < OR_BI; ++a) acc[b][a] = c[b * OR_BI + a];
+  for (i64 k = 0; k < kc; ++k) {
+    const T* __restrict av = ap + k * OR_BI;
+    const T* __restrict bv = bp + k * OR_BJ;
+    for (int b = 0; b < OR_BJ; ++b)
+      for (int a = 0; a < OR_BI; ++a) acc[b][a] = acc[b][a] + av[a] * bv[b];
+  }
+  for (int b = 0; b < OR_BJ; ++b)
+    for (int a = 0; a < OR_BI; ++a) c[b * OR_BI + a] = acc[b][a];
+}
+
+// dst_s selects the written part of dst (RECT: all of it); lhs and rhs are unstructured.
+template <class T>
+static void gemm_blocked(Mat<T> dst, int dst_s, bool add, Mat<const T> lhs, bool conj_lhs, Mat<const T> rhs, bool conj_rhs,
+                         T alpha) {
+  const i64 M = dst.m, N = dst.n, K = lhs.n;
+  const i64 nic = (M + OR_MC - 1) / OR_MC, njc = (N + OR_NC - 1) / OR_NC;
+  constexpr i64 TI = OR_MC / OR_BI, TJ = OR_NC / OR_BJ;
+#pragma omp parallel
+  {
+    std::vector<T> Ap((size_t)OR_MC * OR_KC), Bp((size_t)OR_KC * OR_NC), Cb((size_t)OR_MC * OR_NC);
+#pragma omp for schedule(dynamic, 1) collapse(2)
+    for (i64 jc = 0; jc < njc; ++jc) {
+      for (i64 ic = 0; ic < nic; ++ic) {
+        const i64 i0 = ic * OR_MC, mc = std::min<i64>(OR_MC, M - i0);
+        const i64 j0 = jc * OR_NC, nc = std::min<i64>(OR_NC, N - j0);
+        if (dst_s != RECT) {
+          if (s_lower(dst_s) && i0 + mc - 1 < j0) continue;  // block strictly above the diagonal
+          if (s_upper(dst_s) && i0 > j0 + nc - 1) continue;  // block strictly below the diagonal
+        }
+        const i64 ti = (mc + OR_BI - 1) / OR_BI, tj = (nc + OR_BJ - 1) / OR_BJ;
+        std::fill(Cb.begin(), Cb.begin() + (size_t)(ti * tj) * OR_BI * OR_BJ, T(0));
+        for (i64 p0 = 0; p0 < K; p0 += OR_KC) {
+          const i64 kc = std::min<i64>(OR_KC, K - p0);
+          // Bp[t][k][4], Ap[t][k][8]
+          for (i64 t = 0; t < tj; ++t) {
+            T* bp = Bp.data() + (size_t)t * kc * OR_BJ;
+            const i64 jb = j0 + t * OR_BJ, nj = std::min<i64>(OR_BJ, N - jb);
+            for (i64 k = 0; k < kc; ++k)
+              for (i64 b = 0; b < OR_BJ; ++b) bp[k * OR_BJ + b] = b < nj ? conj_if(conj_rhs, rhs(p0 + k, jb + b)) : T(0);
+          }
+          for (i64 t = 0; t < ti; ++t) {
+            T* ap = Ap.data() + (size_t)t * kc * OR_BI;
+            const i64 ib = i0 + t * OR_BI, ni = std::min<i64>(OR_BI, M - ib);
+            if (ni == OR_BI && lhs.rs == 1 && !conj_lhs) {
+              for (i64 k = 0; k < kc; ++k) std::memcpy(ap + k * OR_BI, &lhs(ib, p0 + k), sizeof(T) * OR_BI);
+            } else {
+              for (i64 k = 0; k < kc; ++k)
+                for (i64 a = 0; a < OR_BI; ++a) ap[k * OR_BI + a] = a < ni ? conj_if(conj_lhs, lhs(ib + a, p0 + k)) : T(0);
+            }
+          }
+          for (i64 t2 = 0; t2 < tj; ++t2) {
+            const i64 jb = j0 + t2 * OR_BJ, nj = std::min<i64>(OR_BJ, N - jb);
+            for (i64 t1 = 0; t1 < ti; ++t1) {
+              const i64 ib = i0 + t1 * OR_BI, ni = std::min<i64>(OR_BI, M - ib);
+              if (dst_s != RECT) {
+                if (s_lower(dst_s) && ib + ni - 1 < jb) continue;
+                if (s_upper(dst_s) && ib > jb + nj - 1) continue;
+              }
+              micro_kernel<T>(Cb.data() + (size_t)(t2 * ti + t1) * OR_BI * OR_BJ, Ap.data() + (size_t)t1 * kc * OR_BI,
+                              Bp.data() + (size_t)t2 * kc * OR_BJ, kc);
+            }
+          }
+        }
+        for (i64 t2 = 0; t2 < tj; ++t2) {
+          const i64 jb = j0 + t2 * OR_BJ, nj = std::min<i64>(OR_BJ, N - jb);
+          for (i64 t1 = 0; t1 < ti; ++t1) {
+            const i64 ib = i0 + t1 * OR_BI, ni = std::min<i64>(OR_BI, M - ib);
+            if (dst_s != RECT) {
+              if (s_lower(dst_s) && ib + ni - 1 < jb) continue;
+              if (s_upper(dst_s) && ib > jb + nj - 1) continue;
+            }
+            const T* c = Cb.data() + (size_t)(t2 * ti + t1) * OR_BI * OR_BJ;
+            for (i64 b = 0; b < nj; ++b)
+              for (i64 a = 0; a < ni; ++a) {
+                const i64 i = ib + a, j = jb + b;
+                if (dst_s != RECT) {
+                  if (i == j && s_nodiag(dst_s)) continue;
+                  if (i != j && (s_lower(dst_s) ? (i < j) : (i > j))) continue;
+                }
+                T v = c[b * OR_BI + a] * alpha;
+                if (add) v = dst(i, j) + v;
+                dst(i, j) = v;
+              }
+          }
+        }
+      }
+    }
+  }
+  (void)TI; (void)TJ;
+}
+// the blocked form pays off once the operands no longer sit in the first-level cache
+static inline bool use_blocked(i64 M, i64 N, i64 K) { return K >= 16 && M * N >= 64 * 64 && M * N * K >= (i64)1 << 20; }
+
 template <class T>
 void matmul(Mat<T> dst, bool add, Mat<const T> lhs, bool conj_lhs, Mat<const T> rhs, bool conj_rhs, T alpha) {
   const i64 M = dst.m, N = dst.n, K = lhs.n;
@@ -53,9 +167,13 @@ void matmul(Mat<T> dst, bool add, Mat<const T> lhs, bool conj_lhs, Mat<const T> 
         for (i64 i = 0; i < M; ++i) dst(i, j) = T(0);
     return;
   }
+  if (use_blocked(M, N, K)) {
+    gemm_blocked<T>(dst, RECT, add, lhs, conj_lhs, rhs, conj_rhs, alpha);
+    return;
+  }
   constexpr int BI = OR_BI, BJ = OR_BJ;
   const i64 nbj = (N + BJ - 1) / BJ;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) if (M * N * K >= 32768)
   for (i64 jb = 0; jb < nbj; ++jb) {
     const i64 j0 = jb * BJ, nj = std::min<i64>(BJ, N - j0);
     for (i64 i0 = 0; i0 < M; i0 += BI) {
@@ -104,6 +222,10 @@ void matmul_triangular(Mat<T> dst, int dst_s, bool add, Mat<const T> lhs, int lh
     // Unstructured operands, structured destination (the SYRK-type trailing updates): same per-element arithmetic as
     // the loop below (acc over k ascending, then * alpha, then + dst), computed on 8 x 4 register tiles like matmul();
     // tiles entirely outside the selected triangle are skipped. Bitwise the same results, ~an order of magnitude faster.
+    if (K > 0 && use_blocked(M, N, K)) {
+      gemm_blocked<T>(dst, dst_s, add, lhs, conj_lhs, rhs, conj_rhs, alpha);
+      return;
+    }
     constexpr int BI = OR_BI, BJ = OR_BJ;
     const i64 nbj = (N + BJ - 1) / BJ;
 #pragma omp parallel for schedule(dynamic, 1)
@@ -209,12 +331,31 @@ static void solve_lower_rec(Mat<const T> L, bool conj, bool unit, Mat<T> rhs) {
   solve_lower_rec(L11, conj, unit, bot);
 }
 
+// The right-hand-side columns are independent and every product element is computed the same way whatever the blocking,
+// so solving chunks of columns on different threads changes no value (the reference splits the same way,
+// triangular_solve.rs:420-576); inside a chunk the recursion and its products run on the calling thread.
 template <class T>
-void solve_lower(Mat<const T> tril, bool conj, bool unit, Mat<T> rhs) { solve_lower_rec(tril, conj, unit, rhs); }
+static void solve_lower_cols(Mat<const T> tril, bool conj, bool unit, Mat<T> rhs) {
+  const i64 k = rhs.n;
+  const int nt = omp_get_max_threads();
+  if (k < 32 || nt <= 1 || omp_in_parallel() || tril.m < 8) {
+    solve_lower_rec(tril, conj, unit, rhs);
+    return;
+  }
+  const i64 chunk = std::max<i64>(8, (k + 4 * nt - 1) / (4 * nt));
+  const i64 nchunks = (k + chunk - 1) / chunk;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (i64 c = 0; c < nchunks; ++c) {
+    const i64 c0 = c * chunk;
+    solve_lower_rec(tril, conj, unit, rhs.sub(0, c0, rhs.m, std::min(chunk, k - c0)));
+  }
+}
+template <class T>
+void solve_lower(Mat<const T> tril, bool conj, bool unit, Mat<T> rhs) { solve_lower_cols(tril, conj, unit, rhs); }
 template <class T>
 void solve_upper(Mat<const T> triu, bool conj, bool unit, Mat<T> rhs) {
   if (triu.m == 0 || rhs.n == 0) return;
-  solve_lower_rec(triu.rev_rows_cols(), conj, unit, rhs.rev_rows());
+  solve_lower_cols(triu.rev_rows_cols(), conj, unit, rhs.rev_rows());
 }
 
 // ------------------------------------------------------------------------------------------------
