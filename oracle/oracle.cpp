@@ -457,6 +457,105 @@ i64 llt_in_place(Mat<T> A, typename real_of<T>::type delta, typename real_of<T>:
 }
 
 // ------------------------------------------------------------------------------------------------
+// LDLT. Reference: faer/src/linalg/cholesky/ldlt/factor.rs
+//   cholesky_in_place 725-767: D lives in a scratch row during the factorization; afterwards A(i, i) = D[i] for
+//        i < n (success) or i <= index (ZeroPivot { index }); the strict lower part holds the unit-lower L.
+//   cholesky_block_left_looking 499-...: `if true ||` forwards to cholesky_recursion_right_looking(is_llt = false) 367-498:
+//        recurse on A00; conj(A00) X = A10^T with the UNIT-lower solve (X = L10 D0); L10 = X * recip(D0) column by
+//        column; A11(lower) -= L10 X^H. The x86 build forms the product through `spicy_matmul` (diagonal applied inside an
+//        un-vendored GEMM, 447-470); the portable branch (471-492) multiplies L10 by the saved X, which is restated here
+//        — X is kept in a temporary instead of the upper triangle, which the x86 path leaves untouched.
+//   leaf (simd_cholesky 7-177 == cholesky_fallback 299-366 up to fusing): a_ij <- fma(conj(a_jk) * (-D_k), a_ik, a_ij),
+//        k ascending; d = Re(a_jj); regularisation 122-144: sign +1 and d <= eps -> delta (counted); sign -1 and
+//        d >= -eps -> -delta; no sign and |d| <= eps -> copysign-like (d < 0 ? -delta : delta); only the first case
+//        increments the count; D_j = d; d == 0 or non-finite -> ZeroPivot(j); column j (diagonal included) *= recip(d).
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static i64 ldlt_leaf(Mat<T> A, typename real_of<T>::type* D, bool regularize, typename real_of<T>::type eps,
+                     typename real_of<T>::type delta, const signed char* signs, i64* count) {
+  typedef typename real_of<T>::type R;
+  const i64 n = A.m;
+  for (i64 j = 0; j < n; ++j) {
+    for (i64 i = j; i < n; ++i) {
+      T a = A(i, j);
+      for (i64 k = 0; k < j; ++k) a = fma_(mul_real(conj_if(true, A(j, k)), -D[k]), A(i, k), a);
+      A(i, j) = a;
+    }
+    R diag = real_part(A(j, j));
+    if (regularize) {
+      const int sign = signs ? (int)signs[j] : 0;
+      const bool small_or_negative = diag <= eps;
+      const bool minus_small_or_positive = diag >= -eps;
+      if (sign == 1 && small_or_negative) {
+        diag = delta;
+        *count += 1;
+      } else if (sign == -1 && minus_small_or_positive) {
+        diag = -delta;
+      } else if (small_or_negative && minus_small_or_positive) {
+        diag = diag < R(0) ? -delta : delta;
+      }
+    }
+    D[j] = diag;
+    if (diag == R(0) || !std::isfinite(diag)) return j;
+    const R inv = R(1) / diag;
+    for (i64 i = j; i < n; ++i) A(i, j) = mul_real(A(i, j), inv);
+  }
+  return -1;
+}
+
+template <class T>
+static i64 ldlt_rec(Mat<T> A, typename real_of<T>::type* D, bool regularize, typename real_of<T>::type eps,
+                    typename real_of<T>::type delta, const signed char* signs, i64 recursion_threshold, i64 block_size,
+                    i64* count) {
+  typedef typename real_of<T>::type R;
+  const i64 n = A.n;
+  if (n <= recursion_threshold) return ldlt_leaf(A, D, regularize, eps, delta, signs, count);
+  const i64 bs0 = std::min(next_pow2(n) / 2, block_size);
+  for (i64 j = 0; j < n;) {
+    const i64 bs = std::min(bs0, n - j);
+    Mat<T> A00 = A.sub(j, j, bs, bs);
+    const i64 fail = ldlt_rec(A00, D + j, regularize, eps, delta, signs ? signs + j : nullptr, recursion_threshold, bs, count);
+    if (fail >= 0) return j + fail;
+    const i64 rem = n - j - bs;
+    if (rem > 0) {
+      Mat<T> A10 = A.sub(j + bs, j, rem, bs);
+      Mat<T> A11 = A.sub(j + bs, j + bs, rem, rem);
+      Mat<const T> cA00{A00.p, A00.m, A00.n, A00.rs, A00.cs};
+      solve_lower<T>(cA00, /*conj=*/true, /*unit=*/true, A10.t());
+      std::vector<T> xbuf((size_t)rem * (size_t)bs);
+      Mat<T> X{xbuf.data(), rem, bs, 1, rem};
+      for (i64 k = 0; k < bs; ++k) {
+        const R d = R(1) / D[j + k];
+        for (i64 i = 0; i < rem; ++i) {
+          const T a = A10(i, k);
+          X(i, k) = a;
+          A10(i, k) = mul_real(a, d);
+        }
+      }
+      Mat<const T> cA10{A10.p, A10.m, A10.n, A10.rs, A10.cs};
+      Mat<const T> cX{X.p, X.m, X.n, X.rs, X.cs};
+      matmul_triangular<T>(A11, TRI_LOWER, true, cA10, RECT, false, cX.t(), RECT, true, T(-1));
+    }
+    j += bs;
+  }
+  return -1;
+}
+
+template <class T>
+i64 ldlt_in_place(Mat<T> A, typename real_of<T>::type delta, typename real_of<T>::type eps, const signed char* signs,
+                  i64 recursion_threshold, i64 block_size, i64* reg_count) {
+  typedef typename real_of<T>::type R;
+  *reg_count = 0;
+  const i64 n = A.m;
+  std::vector<R> D((size_t)std::max<i64>(n, 1), R(0));
+  const bool regularize = delta > R(0) && eps > R(0);  // ldlt/factor.rs:744-745
+  const i64 fail = ldlt_rec(A, D.data(), regularize, eps, delta, signs, recursion_threshold, block_size, reg_count);
+  const i64 init = fail >= 0 ? fail + 1 : n;           // 757-765
+  for (i64 i = 0; i < init; ++i) A(i, i) = T(D[(size_t)i]);
+  return fail;
+}
+
+// ------------------------------------------------------------------------------------------------
 // LU with partial pivoting. Reference: faer/src/linalg/lu/partial_pivoting/factor.rs
 //   lu_in_place 234-295: perm <- identity; transpositions from the recursion; perm.swap(i, i + t_i) in order;
 //                        m < n tail: unit-lower solve of the right block; perm_inv[perm[i]] = i.
@@ -554,6 +653,7 @@ i64 lu_in_place(Mat<T> A, i64* perm, i64* perm_inv, i64 recursion_threshold) {
   template void solve_lower<T>(Mat<const T>, bool, bool, Mat<T>);                                                \
   template void solve_upper<T>(Mat<const T>, bool, bool, Mat<T>);                                                \
   template i64 llt_in_place<T>(Mat<T>, real_of<T>::type, real_of<T>::type, i64, i64, i64*);                      \
+  template i64 ldlt_in_place<T>(Mat<T>, real_of<T>::type, real_of<T>::type, const signed char*, i64, i64, i64*);  \
   template i64 lu_in_place<T>(Mat<T>, i64*, i64*, i64);
 ORACLE_INST(double)
 ORACLE_INST(float)

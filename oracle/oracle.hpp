@@ -66,6 +66,13 @@ template <class T>
 i64 llt_in_place(Mat<T> A, typename real_of<T>::type delta, typename real_of<T>::type eps, i64 recursion_threshold,
                  i64 block_size, i64* reg_count);
 
+// LDLT: faer/src/linalg/cholesky/ldlt/factor.rs:725-767 (cholesky_in_place), 367-498 (recursion, is_llt = false), 7-177 (leaf).
+// Returns -1 on success, else the ZeroPivot index. D ends on the diagonal of A, unit-lower L strictly below it.
+// signs: optional expected signs of the pivots (+1 / -1 / 0), used by the dynamic regularisation only.
+template <class T>
+i64 ldlt_in_place(Mat<T> A, typename real_of<T>::type delta, typename real_of<T>::type eps, const signed char* signs,
+                  i64 recursion_threshold, i64 block_size, i64* reg_count);
+
 // LU: faer/src/linalg/lu/partial_pivoting/factor.rs:234-295 (recursion 68-187, leaf 19-67)
 // perm / perm_inv: i64 arrays of length nrows. returns transposition count.
 template <class T>

@@ -50,6 +50,9 @@ def load() -> C.CDLL:
     lib.oracle_llt.argtypes = [C.c_int, OMat, C.c_double, C.c_double, C.c_longlong, C.c_longlong,
                                C.POINTER(C.c_longlong)]
     lib.oracle_llt.restype = C.c_longlong
+    lib.oracle_ldlt.argtypes = [C.c_int, OMat, C.c_double, C.c_double, C.c_void_p, C.c_longlong, C.c_longlong,
+                                C.POINTER(C.c_longlong)]
+    lib.oracle_ldlt.restype = C.c_longlong
     lib.oracle_lu.argtypes = [C.c_int, OMat, C.c_void_p, C.c_void_p, C.c_longlong]
     lib.oracle_lu.restype = C.c_longlong
     lib.oracle_qr.argtypes = [C.c_int, OMat, OMat, C.c_longlong]
@@ -116,6 +119,33 @@ def llt(A, delta=0.0, eps=0.0, recursion_threshold=64, block_size=128):
     r = load().oracle_llt(_DT[A.dtype], _om(A), float(delta), float(eps), recursion_threshold, block_size, C.byref(cnt))
     assert r != -100
     return int(r), int(cnt.value)
+
+
+def ldlt(A, delta=0.0, eps=0.0, signs=None, recursion_threshold=64, block_size=128):
+    """In-place LDLT of the lower triangle (cholesky/ldlt/factor.rs:725-767): D on the diagonal, unit-lower L strictly
+    below it. Returns (ZeroPivot index or -1, regularisation count). signs: optional int8 array of expected pivot signs."""
+    assert A.shape[0] == A.shape[1]
+    cnt = C.c_longlong(0)
+    sp = None
+    if signs is not None:
+        signs = np.ascontiguousarray(signs, dtype=np.int8)
+        assert signs.size == A.shape[0]
+        sp = signs.ctypes.data
+    r = load().oracle_ldlt(_DT[A.dtype], _om(A), float(delta), float(eps), sp, recursion_threshold, block_size,
+                           C.byref(cnt))
+    assert r != -100
+    return int(r), int(cnt.value)
+
+
+def ldlt_solve(LD, rhs, conj_lhs=False) -> None:
+    """cholesky::ldlt::solve::solve_in_place_with_conj (ldlt/solve.rs:11-49): unit-lower solve with L, rows scaled by
+    recip(Re d_i), unit-upper solve with L^T under conj composed with Yes."""
+    n = LD.shape[0]
+    assert LD.shape[1] == n and rhs.shape[0] == n
+    solve_triangular(LD, rhs, lower=True, unit=True, conj=conj_lhs)
+    d = (1.0 / np.real(np.diagonal(LD))).astype(np.real(LD[:1, :1]).dtype)
+    rhs *= d[:, None]
+    solve_triangular(LD.T, rhs, lower=False, unit=True, conj=not conj_lhs)
 
 
 def lu(A, recursion_threshold=16):

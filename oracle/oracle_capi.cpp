@@ -58,6 +58,15 @@ long long oracle_llt(int dtype, OMat A, double delta, double eps, long long recu
   return r;
 }
 
+// LDLT: returns -1 on success, else the ZeroPivot index; signs may be null.
+long long oracle_ldlt(int dtype, OMat A, double delta, double eps, const signed char* signs, long long recursion_threshold,
+                      long long block_size, long long* reg_count) {
+  long long r = -100;
+  DISPATCH(dtype, r = ldlt_in_place<T>(mm<T>(A), (real_of<T>::type)delta, (real_of<T>::type)eps, signs, recursion_threshold,
+                                       block_size, reg_count));
+  return r;
+}
+
 // perm / perm_inv: int64[nrows]; returns the transposition count.
 long long oracle_lu(int dtype, OMat A, long long* perm, long long* perm_inv, long long recursion_threshold) {
   long long r = -100;
