@@ -3,7 +3,7 @@
 tolerance eps * 128 * n) for the real scalar types, plus the accessors' contracts (split_LU, thin_R, compute_Q, P,
 reconstruct, inverse, least squares, Side::Upper, LltError).
 
-Run twice: on the GPU through the C ABI (tests/test_gpu_solvers.py) and on the CPU with `solvers.la` swapped for an
+Run twice: on the GPU through the C ABI (tests/test_gpu_zz3_solvers.py) and on the CPU with `solvers.la` swapped for an
 oracle-backed stand-in (tests/test_solvers_host_logic_cpu.py), which checks the host-side logic of solvers.py itself
 (buffer ownership, factor splitting, call order) without a GPU. The stand-in lives in the tests: the product never
 routes through the oracle.

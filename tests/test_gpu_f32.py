@@ -153,30 +153,3 @@ def test_c32_matmul_vs_oracle(fb, oracle):
         got = C0.copy(order="F"); la.matmul_triangular(got, ds, la.Accum.Add, A, ls, B, rs, 0.5 + 1j)
         assert np.all(np.abs(got - want) <= 2e-4 * np.maximum(1.0, np.abs(want))), (ds, ls, rs)
 
-
-def test_f32_triangular_solve_vs_oracle(fb, oracle, cuda_dev):
-    """f32 triangular solves through the C ABI (triangular_solve.rs:220-419; same recursion and leaf kernel as f64,
-    updates on the f32 GEMM) against the oracle and the componentwise backward bound of substitution
-    |T x - b| <= c n u |T| |x|."""
-    la = fb.linalg
-    rng = np.random.default_rng(43)
-    u = np.finfo(np.float32).eps
-    fns = {(True, False): la.solve_lower_triangular_in_place, (True, True): la.solve_unit_lower_triangular_in_place,
-           (False, False): la.solve_upper_triangular_in_place, (False, True): la.solve_unit_upper_triangular_in_place}
-    for n, k in [(1, 1), (2, 3), (5, 5), (33, 70), (64, 130), (129, 70), (600, 130)]:
-        T = np.asfortranarray((rng.standard_normal((n, n)) / max(n, 1) + 2 * np.eye(n)).astype(np.float32))
-        for lower, unit in itertools.product((True, False), (True, False)):
-            for order in "FC":
-                Bm = np.array(rng.standard_normal((n, k)), dtype=np.float32, order=order)
-                want = Bm.copy(order="K")
-                oracle.solve_triangular(T, want, lower, unit)
-                got = Bm.copy(order="K")
-                fns[(lower, unit)](T, got)
-                tol = u * 16 * n * max(1.0, float(np.abs(want).max()))
-                assert np.all(np.abs(got - want) <= tol), (n, k, lower, unit, order)
-                Tt = (np.tril(T) if lower else np.triu(T)).astype(np.float64)
-                if unit:
-                    np.fill_diagonal(Tt, 1.0)
-                x = got.astype(np.float64)
-                resid = np.abs(Tt @ x - Bm.astype(np.float64))
-                assert np.all(resid <= 8 * n * u * (np.abs(Tt) @ np.abs(x)) + 1e-30), (n, k, lower, unit, order)

@@ -54,25 +54,3 @@ def test_lu_solve(fb, oracle, cuda_dev, idx):
     la.lu_solve_in_place(dA, dp, dpi, dB)
     assert np.allclose(dB.cpu().numpy(), np.linalg.solve(A, B), rtol=1e-8, atol=1e-9)
 
-
-@pytest.mark.parametrize("idx", [np.uint64, np.uint32])
-def test_lu_solve_transpose(fb, oracle, cuda_dev, idx):
-    """lu/partial_pivoting/solve.rs:55-86: A^T x = b from the factors of A (lower solve with U^T, unit-upper solve with
-    L^T, inverse row permutation); expected values from numpy and from the same composition on the CPU."""
-    la = fb.linalg
-    rng = np.random.default_rng(33)
-    for n, k in [(1, 1), (50, 3), (200, 7), (400, 130), (1000, 16)]:
-        A = np.asfortranarray(rng.standard_normal((n, n)))
-        B = np.asfortranarray(rng.standard_normal((n, k)))
-        LU = A.copy(order="F"); p = np.zeros(n, idx); pi = np.zeros(n, idx)
-        la.lu_in_place(LU, p, pi)
-        X = B.copy(order="F"); la.lu_solve_transpose_in_place(LU, p, pi, X)
-        cond = np.linalg.cond(A)
-        assert np.all(np.abs(A.T @ X - B) <= EPS * 128 * 8 * n * cond * max(1.0, np.abs(B).max())), (n, k)
-        assert np.allclose(X, np.linalg.solve(A.T, B), rtol=1e-7 * max(1, cond / 1e4), atol=1e-9), (n, k)
-        # the same composition on the CPU from the same factors
-        Xo = B.copy(order="F")
-        oracle.solve_triangular(LU.T, Xo, lower=True, unit=False)
-        oracle.solve_triangular(LU.T, Xo, lower=False, unit=True)
-        Xo = Xo[pi.astype(np.int64)]
-        assert np.allclose(X, Xo, rtol=1e-9 * max(1, cond / 1e2), atol=1e-11 * max(1, cond)), (n, k)

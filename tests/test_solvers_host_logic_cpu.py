@@ -1,7 +1,7 @@
 """Host-side logic of faer_b200.solvers on the CPU: `solvers.la` (the C-ABI mirror, which needs a GPU) is swapped for a
 stand-in with the same function signatures backed by the oracle, and the shared cases of tests/solvers_cases.py run
 against it. This checks what solvers.py itself does (ownership, split_LU, triangle selection, call order, shapes,
-error propagation); tests/test_gpu_solvers.py runs the same cases through libfaer_b200.so on the GPU."""
+error propagation); tests/test_gpu_zz3_solvers.py runs the same cases through libfaer_b200.so on the GPU."""
 import types
 
 import numpy as np
