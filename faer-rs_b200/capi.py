@@ -77,6 +77,22 @@ class LltStatus(C.Structure):
     _fields_ = [("tag", C.c_int), ("body", _StatusBody)]
 
 
+class LdltParams(C.Structure):
+    _fields_ = [("recursion_threshold", C.c_size_t), ("block_size", C.c_size_t)]
+
+
+class LdltRegularization(C.Structure):
+    """faer.h:368-381; dynamic_regularization_signs: i8 slice, null ptr = none."""
+    _fields_ = [("dynamic_regularization_delta", C.c_void_p), ("dynamic_regularization_epsilon", C.c_void_p),
+                ("dynamic_regularization_signs", SliceMut)]
+
+
+class LdltStatus(C.Structure):
+    """tag: 0 Ok{dynamic_regularization_count}, 1 ZeroPivot{index}, 2 Unknown (faer.h:346-366)."""
+    _anonymous_ = ("body",)
+    _fields_ = [("tag", C.c_int), ("body", _StatusBody)]
+
+
 class PartialPivLuStatus(C.Structure):
     """tag: 0 Ok{transposition_count}, 1 Unknown (faer.h:412-427)."""
     _anonymous_ = ("body",)
@@ -180,6 +196,16 @@ def load() -> C.CDLL:
             f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
             f.argtypes = [MatRef, MatRef, MatRef, C.c_int, MatMut, P, MemAlloc]
             f.restype = None
+    lib.libfaer_v0_23_LdltParams_f64.argtypes = []
+    lib.libfaer_v0_23_LdltParams_f64.restype = LdltParams
+    lib.libfaer_v0_23_ldlt_factor_in_place_scratch_f64.argtypes = [C.c_size_t, P, LdltParams]
+    lib.libfaer_v0_23_ldlt_factor_in_place_scratch_f64.restype = Layout
+    lib.libfaer_v0_23_ldlt_factor_in_place_f64.argtypes = [MatMut, LdltRegularization, P, MemAlloc, LdltParams]
+    lib.libfaer_v0_23_ldlt_factor_in_place_f64.restype = LdltStatus
+    lib.libfaer_v0_23_ldlt_solve_in_place_scratch_f64.argtypes = [C.c_size_t, C.c_size_t, P]
+    lib.libfaer_v0_23_ldlt_solve_in_place_scratch_f64.restype = Layout
+    lib.libfaer_v0_23_ldlt_solve_in_place_f64.argtypes = [MatRef, VecMut, C.c_int, MatMut, P, MemAlloc]
+    lib.libfaer_v0_23_ldlt_solve_in_place_f64.restype = None
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.argtypes = [C.c_size_t, C.c_size_t, P]
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.restype = Layout
     lib.libfaer_v0_23_llt_solve_in_place_f64.argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]

@@ -353,6 +353,89 @@ FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(FaerV0_24_MatMut A, Fa
   return out;
 }
 
+// ---- LDLT (no pivoting); DRAFT, see ldlt_f64.cu ----
+FaerV0_24_LdltParams libfaer_v0_23_LdltParams_f64(void) {
+  return FaerV0_24_LdltParams{64, 128};  // reference defaults: ldlt/factor.rs:705-714
+}
+FaerV0_24_Layout libfaer_v0_23_ldlt_factor_in_place_scratch_f64(size_t dim, FaerV0_24_Par par, FaerV0_24_LdltParams params) {
+  (void)par; (void)params;
+  return FaerV0_24_Layout{dim * sizeof(double), 64};  // temp_mat_scratch::<T>(dim, 1), ldlt/factor.rs:715-724
+}
+FaerV0_24_LdltStatus libfaer_v0_23_ldlt_factor_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_LdltRegularization regularization,
+                                                            FaerV0_24_Par par, FaerV0_24_MemAlloc mem,
+                                                            FaerV0_24_LdltParams params) {
+  (void)par; (void)mem;
+  FB_ENTRY();
+  FB_ASSERT(A.nrows == A.ncols, "LDLT needs a square matrix");
+  cudaStream_t st = current_stream();
+  double delta = 0.0, eps = 0.0;
+  if (regularization.dynamic_regularization_delta)
+    delta = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_delta);
+  if (regularization.dynamic_regularization_epsilon)
+    eps = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_epsilon);
+  // expected signs: i8 slice, null = none (faer-ffi/src/lib.rs:838-848); host slices are mirrored on the device
+  const signed char* d_signs = nullptr;
+  signed char* signs_mirror = nullptr;
+  const FaerV0_24_SliceMut sg = regularization.dynamic_regularization_signs;
+  if (sg.ptr != nullptr && A.nrows > 0) {
+    FB_ASSERT(sg.len >= A.nrows, "dynamic_regularization_signs is shorter than the matrix dimension");
+    if (is_device_pointer(sg.ptr)) {
+      d_signs = (const signed char*)sg.ptr;
+    } else {
+      signs_mirror = (signed char*)ws_alloc(A.nrows);
+      FB_CUDA_CHECK(cudaMemcpyAsync(signs_mirror, sg.ptr, A.nrows, cudaMemcpyHostToDevice, st));
+      d_signs = signs_mirror;
+    }
+  }
+  Mat a(A, true, st);
+  const LdltResult r = ldlt_in_place_f64(st, a.s.view<double>(), delta, eps, d_signs,
+                                         LltParams{params.recursion_threshold, params.block_size});
+  finish_all(st, {&a.s});
+  if (signs_mirror) ws_free(signs_mirror);
+  FaerV0_24_LdltStatus out;
+  memset(&out, 0, sizeof(out));
+  if (r.ok) {
+    out.tag = FaerV0_24_LdltStatus_Ok;
+    out.ok.dynamic_regularization_count = r.dynamic_regularization_count;
+  } else {
+    out.tag = FaerV0_24_LdltStatus_ZeroPivot;
+    out.zero_pivot.index = r.zero_pivot_index;
+  }
+  return out;
+}
+FaerV0_24_Layout libfaer_v0_23_ldlt_solve_in_place_scratch_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
+  (void)dim; (void)rhs_ncols; (void)par;
+  return FaerV0_24_Layout{0, 1};  // StackReq::EMPTY (ldlt/solve.rs:3-10)
+}
+void libfaer_v0_23_ldlt_solve_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_VecRef D, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs,
+                                           FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
+  (void)A_conj; (void)par; (void)mem;
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t n = L.nrows;
+  FB_ASSERT(L.ncols == n && D.len == n && rhs.nrows == n, "LDLT solve shape mismatch");
+  if (n == 0 || rhs.ncols == 0) return;
+  Mat l(L, st);
+  Mat r(rhs, true, st);
+  // D: usually the diagonal of the factored matrix (stride = row_stride + col_stride). A host vector is gathered into a
+  // compact device copy; a device vector is read in place.
+  const double* d_ptr = (const double*)D.ptr;
+  i64 d_stride = (i64)D.stride;
+  double* d_mirror = nullptr;
+  if (!is_device_pointer(D.ptr)) {
+    std::vector<double> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = ((const double*)D.ptr)[(ptrdiff_t)i * D.stride];
+    d_mirror = (double*)ws_alloc(n * sizeof(double));
+    FB_CUDA_CHECK(cudaMemcpyAsync(d_mirror, h.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));  // `h` is pageable and local
+    d_ptr = d_mirror;
+    d_stride = 1;
+  }
+  ldlt_solve_in_place_f64(st, l.s.view<const double>(), d_ptr, d_stride, r.s.view<double>());
+  finish_all(st, {&l.s, &r.s});
+  if (d_mirror) ws_free(d_mirror);
+}
+
 // ---- partial-pivoting LU ----
 FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f64(void) {
   // reference defaults: faer/src/linalg/lu/partial_pivoting/factor.rs:212-222

@@ -29,6 +29,18 @@ struct LltResult {
 // `reg_delta`/`reg_eps`: dynamic regularisation (active iff both > 0), reference llt/factor.rs:85-87.
 LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, LltParams params);
 
+// LDLT without pivoting (ldlt_f64.cu; reference cholesky/ldlt/factor.rs:725-767): D on the diagonal, unit-lower L strictly
+// below it, strict upper triangle untouched. d_signs: device int8[n] of expected pivot signs, or null.
+struct LdltResult {
+  bool ok;
+  size_t dynamic_regularization_count;  // valid if ok
+  size_t zero_pivot_index;              // valid if !ok
+};
+LdltResult ldlt_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, const signed char* d_signs,
+                             LltParams params);
+// rhs <- (L D L^T)^-1 rhs (ldlt/solve.rs:11-49); D: device pointer, dstride elements apart
+void ldlt_solve_in_place_f64(cudaStream_t stream, VCD L, const double* D, i64 dstride, VD rhs);
+
 // same factorisation, device-only (no sync / read-back); status accumulates in d_info (see llt_f64.cu)
 void llt_cholesky_device_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, long long* d_info, i64 j0);
 

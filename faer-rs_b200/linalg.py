@@ -200,6 +200,56 @@ def cholesky_in_place(A, regularization=(0.0, 0.0), par=None, params=None) -> Ll
     raise RuntimeError("LltStatus::Unknown")
 
 
+# ---- LDLT (no pivoting) ---------------------------------------------------------------------------
+@dataclass
+class LdltInfo:
+    dynamic_regularization_count: int
+
+
+class LdltError(Exception):
+    """ZeroPivot { index } (faer/src/linalg/cholesky/ldlt/factor.rs:689-692)."""
+
+    def __init__(self, index: int):
+        super().__init__(f"ZeroPivot {{ index: {index} }}")
+        self.index = index
+
+
+def ldlt_in_place(A, regularization=(0.0, 0.0), signs=None, par=None, params=None) -> LdltInfo:
+    """cholesky::ldlt::factor::cholesky_in_place (ldlt/factor.rs:725-767): in-place LDLT of the lower triangle, D on the
+    diagonal and the unit-lower L strictly below it. regularization = (delta, epsilon); signs: optional int8 array (numpy)
+    or int8 CUDA tensor of expected pivot signs. Raises LdltError."""
+    _check_f64(A)
+    lib = capi.load()
+    params = params or lib.libfaer_v0_23_LdltParams_f64()
+    par = par or capi.par_default()
+    delta = C.c_double(float(regularization[0]))
+    eps = C.c_double(float(regularization[1]))
+    sl = capi.SliceMut(None, 0)
+    if signs is not None:
+        if not capi._is_torch(signs):
+            signs = np.ascontiguousarray(signs, dtype=np.int8)
+        sl = capi.slice_mut(signs)
+        assert sl.len == A.shape[0]
+    reg = capi.LdltRegularization(C.cast(C.pointer(delta), C.c_void_p), C.cast(C.pointer(eps), C.c_void_p), sl)
+    st = lib.libfaer_v0_23_ldlt_factor_in_place_f64(capi.mat_mut(A), reg, par, capi.MemAlloc(None, 0), params)
+    if st.tag == 0:
+        return LdltInfo(int(st.value))
+    if st.tag == 1:
+        raise LdltError(int(st.value))
+    raise RuntimeError("LdltStatus::Unknown")
+
+
+def ldlt_solve_in_place(LD, rhs, conj: int = CONJ_NO, par=None) -> None:
+    """cholesky::ldlt::solve::solve_in_place_with_conj (ldlt/solve.rs:11-49): rhs <- (L D L^T)^-1 rhs with L the unit-lower
+    part of LD and D its diagonal (passed as a strided vector over the same storage, as `L.diagonal()` in the reference)."""
+    _check_f64(LD, rhs)
+    lib = capi.load()
+    p, m, n, rs, cs = capi._fields(LD)
+    assert m == n
+    lib.libfaer_v0_23_ldlt_solve_in_place_f64(capi.mat_ref(LD), capi.VecMut(p, n, rs + cs), conj, capi.mat_mut(rhs),
+                                              par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
 def llt_solve_in_place(L, rhs, conj: int = CONJ_NO, par=None) -> None:
     """cholesky::llt::solve::solve_in_place_with_conj (llt/solve.rs:12-35): rhs <- (L L^H)^-1 rhs."""
     _check_f64(L, rhs)

@@ -67,6 +67,23 @@ typedef struct FaerV0_24_LltRegularization {
   const FaerV0_24_Real *dynamic_regularization_epsilon;
 } FaerV0_24_LltRegularization;
 
+typedef struct FaerV0_24_LdltParams { size_t recursion_threshold; size_t block_size; } FaerV0_24_LdltParams;
+typedef struct FaerV0_24_LdltRegularization {
+  const FaerV0_24_Real *dynamic_regularization_delta;
+  const FaerV0_24_Real *dynamic_regularization_epsilon;
+  struct FaerV0_24_SliceMut dynamic_regularization_signs; /* i8 */
+} FaerV0_24_LdltRegularization;
+typedef enum FaerV0_24_LdltStatus_Tag { FaerV0_24_LdltStatus_Ok, FaerV0_24_LdltStatus_ZeroPivot, FaerV0_24_LdltStatus_Unknown } FaerV0_24_LdltStatus_Tag;
+typedef struct FaerV0_24_LdltStatus_FaerV0_24_Ok_Body { size_t dynamic_regularization_count; } FaerV0_24_LdltStatus_FaerV0_24_Ok_Body;
+typedef struct FaerV0_24_LdltStatus_FaerV0_24_ZeroPivot_Body { size_t index; } FaerV0_24_LdltStatus_FaerV0_24_ZeroPivot_Body;
+typedef struct FaerV0_24_LdltStatus {
+  FaerV0_24_LdltStatus_Tag tag;
+  union {
+    FaerV0_24_LdltStatus_FaerV0_24_Ok_Body ok;
+    FaerV0_24_LdltStatus_FaerV0_24_ZeroPivot_Body zero_pivot;
+  };
+} FaerV0_24_LdltStatus;
+
 /* ---- status unions: faer-ffi/src/lib.rs:552-629, C layout faer-ffi/faer.h:383-469 ---- */
 typedef enum FaerV0_24_LltStatus_Tag { FaerV0_24_LltStatus_Ok, FaerV0_24_LltStatus_NonPositivePivot, FaerV0_24_LltStatus_Unknown } FaerV0_24_LltStatus_Tag;
 typedef struct FaerV0_24_LltStatus_FaerV0_24_Ok_Body { size_t dynamic_regularization_count; } FaerV0_24_LltStatus_FaerV0_24_Ok_Body;
@@ -165,6 +182,17 @@ struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(struct FaerV0_2
                                                                  struct FaerV0_24_LltRegularization regularization,
                                                                  struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem,
                                                                  struct FaerV0_24_LltParams params);
+
+/* LDLT without pivoting.  types: faer.h:162-165 (LdltParams), 340-344 (VecRef), 346-381 (LdltStatus,
+ * LdltRegularization);  params: lib.rs:660;  factor: lib.rs:1190-1217, faer.h:3802, 3830;  solve: lib.rs:1218-1246, faer.h:3974,
+ * 4004.  Semantics: faer/src/linalg/cholesky/ldlt/factor.rs:725-767 (D on the diagonal of A, unit-lower L strictly below, strict
+ * upper triangle untouched; ZeroPivot { index }), solve.rs:11-49.  dynamic_regularization_signs: i8 slice or null ptr.
+ * Written after round 1's last GPU session: see csrc/ldlt_f64.cu for its status. */
+struct FaerV0_24_LdltParams libfaer_v0_23_LdltParams_f64(void);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_factor_in_place_scratch_f64(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LdltParams params);
+struct FaerV0_24_LdltStatus libfaer_v0_23_ldlt_factor_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_LdltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LdltParams params);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_solve_in_place_scratch_f64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_solve_in_place_f64(struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
 /* partial-pivoting LU.   params: lib.rs:679-684, faer.h:648; scratch: lib.rs:1952-1965; factor: lib.rs:1966-1983, faer.h:4456-4461 */
 struct FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f64(void);
