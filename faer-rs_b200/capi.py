@@ -178,7 +178,8 @@ def load() -> C.CDLL:
         f = getattr(lib, f"libfaer_v0_23_qr_factor_in_place_{suf}")
         f.argtypes = [MatMut, MatMut, P, MemAlloc, QrParams]
         f.restype = QrStatus
-        for name in ("apply_householder_on_the_left", "apply_householder_transpose_on_the_left"):
+        for name in ("apply_householder_on_the_left", "apply_householder_transpose_on_the_left",
+                     "apply_householder_on_the_right", "apply_householder_transpose_on_the_right"):
             f = getattr(lib, f"libfaer_v0_23_{name}_scratch_{suf}")
             f.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t]
             f.restype = Layout

@@ -80,6 +80,9 @@ FaerV0_24_QrStatus qr_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Q) {
   }
   return out;
 }
+inline FaerV0_24_MatMut transposed(FaerV0_24_MatMut m) {
+  return FaerV0_24_MatMut{m.ptr, m.ncols, m.nrows, m.col_stride, m.row_stride};
+}
 template <class T>
 void householder_seq_entry(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, FaerV0_24_MatMut rhs, bool transpose) {
   FB_ENTRY();
@@ -524,6 +527,27 @@ FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f6
                                                                    FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {        \
     (void)conj; (void)par; (void)mem;                                                                                  \
     householder_seq_entry<T>(basis, factor, rhs, true);                                                                \
+  }                                                                                                                    \
+  /* on the right = the transposed sequence on the left of the transposed view, and vice versa (householder.rs:813-854) */ \
+  FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_right_scratch_##SUF(size_t dim, size_t block_size, size_t lhs_nrows) { \
+    (void)dim;                                                                                                         \
+    return FaerV0_24_Layout{block_size * lhs_nrows * sizeof(T), 64};                                                   \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_right_scratch_##SUF(size_t dim, size_t block_size, \
+                                                                                         size_t lhs_nrows) {           \
+    (void)dim;                                                                                                         \
+    return FaerV0_24_Layout{block_size * lhs_nrows * sizeof(T), 64};                                                   \
+  }                                                                                                                    \
+  void libfaer_v0_23_apply_householder_on_the_right_##SUF(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, FaerV0_24_Conj conj, \
+                                                          FaerV0_24_MatMut lhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) { \
+    (void)conj; (void)par; (void)mem;                                                                                  \
+    householder_seq_entry<T>(basis, factor, transposed(lhs), true);                                                    \
+  }                                                                                                                    \
+  void libfaer_v0_23_apply_householder_transpose_on_the_right_##SUF(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor,   \
+                                                                    FaerV0_24_Conj conj, FaerV0_24_MatMut lhs,         \
+                                                                    FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {       \
+    (void)conj; (void)par; (void)mem;                                                                                  \
+    householder_seq_entry<T>(basis, factor, transposed(lhs), false);                                                   \
   }                                                                                                                    \
   /* scratch: apply_block_householder_sequence_[transpose_]on_the_left_in_place_scratch (solve.rs:3-37) */           \
   FaerV0_24_Layout libfaer_v0_23_qr_solve_lstsq_in_place_scratch_##SUF(size_t nrows, size_t ncols, size_t block_size,  \

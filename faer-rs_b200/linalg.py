@@ -327,6 +327,20 @@ def apply_block_householder_sequence_transpose_on_the_left_in_place(basis, facto
         capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
+def apply_block_householder_sequence_on_the_right_in_place(basis, factor, lhs, conj: int = CONJ_NO, par=None) -> None:
+    """householder.rs:813-831: lhs <- lhs Q."""
+    lib = capi.load()
+    getattr(lib, f"libfaer_v0_23_apply_householder_on_the_right_{_suf(lhs)}")(
+        capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(lhs), par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
+def apply_block_householder_sequence_transpose_on_the_right_in_place(basis, factor, lhs, conj: int = CONJ_YES, par=None) -> None:
+    """householder.rs:836-854: lhs <- lhs Q^H."""
+    lib = capi.load()
+    getattr(lib, f"libfaer_v0_23_apply_householder_transpose_on_the_right_{_suf(lhs)}")(
+        capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(lhs), par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
 def _qr_solve(name, Q_basis, Q_coeff, R, rhs, conj, par):
     lib = capi.load()
     suf = _suf(rhs)

@@ -223,6 +223,15 @@ void libfaer_v0_23_apply_householder_on_the_left_f64(struct FaerV0_24_MatRef hou
 void libfaer_v0_23_apply_householder_on_the_left_f32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 void libfaer_v0_23_apply_householder_transpose_on_the_left_f64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 void libfaer_v0_23_apply_householder_transpose_on_the_left_f32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+/* on the right: lib.rs:1471-1518; householder.rs:813-854 (lhs <- lhs Q  and  lhs <- lhs Q^H through the transposed view) */
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_right_scratch_f64(size_t dim, size_t block_size, size_t lhs_nrows);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_right_scratch_f64(size_t dim, size_t block_size, size_t lhs_nrows);
+void libfaer_v0_23_apply_householder_on_the_right_f64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut lhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_transpose_on_the_right_f64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut lhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_right_scratch_f32(size_t dim, size_t block_size, size_t lhs_nrows);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_right_scratch_f32(size_t dim, size_t block_size, size_t lhs_nrows);
+void libfaer_v0_23_apply_householder_on_the_right_f32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut lhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_transpose_on_the_right_f32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut lhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
 /* solves on top of the factors.   llt: faer-ffi/src/lib.rs:1012-1038, faer.h:4188, 4216;
  * LU: lib.rs:1985-2020, faer.h:4786, 4884. L and U are views of the factored matrix (L: unit-lower part, U: upper part). */

@@ -59,3 +59,31 @@ def test_lu_solve_transpose(fb, oracle, cuda_dev, idx):
         oracle.solve_triangular(LU.T, Xo, lower=False, unit=True)
         Xo = Xo[pi.astype(np.int64)]
         assert np.allclose(X, Xo, rtol=1e-9 * max(1, cond / 1e2), atol=1e-11 * max(1, cond)), (n, k)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_apply_householder_on_the_right(fb, oracle, cuda_dev, dtype):
+    """householder.rs:813-854: lhs <- lhs Q and lhs <- lhs Q^H (the left sequences on the transposed view), against Q formed
+    explicitly with the left application and against the oracle."""
+    la = fb.linalg
+    rng = np.random.default_rng(44)
+    u = np.finfo(dtype).eps
+    for (m, n, k) in [(5, 3, 4), (64, 64, 7), (200, 60, 33), (300, 300, 129)]:
+        A = np.asfortranarray(rng.standard_normal((m, n)).astype(dtype))
+        QR = A.copy(order="F")
+        bs = la.qr_recommended_block_size(m, n)
+        H = np.zeros((bs, min(m, n)), dtype=dtype, order="F")
+        la.qr_in_place(QR, H)
+        Q = np.asfortranarray(np.eye(m, dtype=dtype))
+        la.apply_block_householder_sequence_on_the_left_in_place(QR, H, Q)
+        for order in "FC":
+            M0 = np.array(rng.standard_normal((k, m)), dtype=dtype, order=order)
+            tol = 64 * u * m * max(1.0, np.abs(M0).max())
+            got = M0.copy(order="K"); la.apply_block_householder_sequence_on_the_right_in_place(QR, H, got)
+            assert np.abs(got - M0 @ Q).max() <= tol, (m, n, k, order)
+            want = M0.copy(order="K"); oracle.apply_q_transpose_sequence(QR, H, want.T)   # (Q^T M^T)^T = M Q
+            assert np.abs(got - want).max() <= tol, (m, n, k, order)
+            got = M0.copy(order="K"); la.apply_block_householder_sequence_transpose_on_the_right_in_place(QR, H, got)
+            assert np.abs(got - M0 @ Q.T).max() <= tol, (m, n, k, order)
+            want = M0.copy(order="K"); oracle.apply_q_sequence(QR, H, want.T)             # (Q M^T)^T = M Q^T
+            assert np.abs(got - want).max() <= tol, (m, n, k, order)
