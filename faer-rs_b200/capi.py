@@ -197,6 +197,16 @@ def load() -> C.CDLL:
             f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
             f.argtypes = [MatRef, MatRef, MatRef, C.c_int, MatMut, P, MemAlloc]
             f.restype = None
+    lib.libfaer_v0_23_LltParams_f32.argtypes = []
+    lib.libfaer_v0_23_LltParams_f32.restype = LltParams
+    lib.libfaer_v0_23_llt_factor_in_place_scratch_f32.argtypes = [C.c_size_t, P, LltParams]
+    lib.libfaer_v0_23_llt_factor_in_place_scratch_f32.restype = Layout
+    lib.libfaer_v0_23_llt_factor_in_place_f32.argtypes = [MatMut, LltRegularization, P, MemAlloc, LltParams]
+    lib.libfaer_v0_23_llt_factor_in_place_f32.restype = LltStatus
+    lib.libfaer_v0_23_llt_solve_in_place_scratch_f32.argtypes = [C.c_size_t, C.c_size_t, P]
+    lib.libfaer_v0_23_llt_solve_in_place_scratch_f32.restype = Layout
+    lib.libfaer_v0_23_llt_solve_in_place_f32.argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]
+    lib.libfaer_v0_23_llt_solve_in_place_f32.restype = None
     lib.libfaer_v0_23_LdltParams_f64.argtypes = []
     lib.libfaer_v0_23_LdltParams_f64.restype = LdltParams
     lib.libfaer_v0_23_ldlt_factor_in_place_scratch_f64.argtypes = [C.c_size_t, P, LdltParams]

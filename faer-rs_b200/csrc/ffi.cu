@@ -356,6 +356,59 @@ FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(FaerV0_24_MatMut A, Fa
   return out;
 }
 
+// ---- f32 LLT (llt_f32.cu: the recursive driver with the f32 leaf; first hardware run pending) ----
+static float read_real_f32(const void* p) {
+  float v;
+  if (is_device_pointer(p)) FB_CUDA_CHECK(cudaMemcpy(&v, p, sizeof(float), cudaMemcpyDeviceToHost));
+  else memcpy(&v, p, sizeof(float));
+  return v;
+}
+FaerV0_24_LltParams libfaer_v0_23_LltParams_f32(void) { return FaerV0_24_LltParams{64, 128}; }
+FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_f32(size_t dim, FaerV0_24_Par par, FaerV0_24_LltParams params) {
+  (void)par; (void)params;
+  return FaerV0_24_Layout{dim * sizeof(float), 64};  // temp_mat_scratch::<T>(dim, 1), llt/factor.rs:58-66
+}
+FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_LltRegularization regularization,
+                                                          FaerV0_24_Par par, FaerV0_24_MemAlloc mem,
+                                                          FaerV0_24_LltParams params) {
+  (void)par; (void)mem;
+  FB_ENTRY();
+  FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
+  cudaStream_t st = current_stream();
+  float delta = 0.0f, eps = 0.0f;
+  if (regularization.dynamic_regularization_delta) delta = read_real_f32(regularization.dynamic_regularization_delta);
+  if (regularization.dynamic_regularization_epsilon) eps = read_real_f32(regularization.dynamic_regularization_epsilon);
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(float), true, true, st);
+  const LltResult r = llt_cholesky_in_place_f32(st, a.view<float>(), delta, eps,
+                                                LltParams{params.recursion_threshold, params.block_size});
+  finish_all(st, {&a});
+  FaerV0_24_LltStatus out;
+  memset(&out, 0, sizeof(out));
+  if (r.ok) {
+    out.tag = FaerV0_24_LltStatus_Ok;
+    out.ok.dynamic_regularization_count = r.dynamic_regularization_count;
+  } else {
+    out.tag = FaerV0_24_LltStatus_NonPositivePivot;
+    out.non_positive_pivot.index = r.non_positive_pivot_index;
+  }
+  return out;
+}
+FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_f32(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
+  (void)dim; (void)rhs_ncols; (void)par;
+  return FaerV0_24_Layout{0, 1};
+}
+void libfaer_v0_23_llt_solve_in_place_f32(FaerV0_24_MatRef L, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,
+                                          FaerV0_24_MemAlloc mem) {
+  (void)A_conj; (void)par; (void)mem;
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  FB_ASSERT(L.nrows == L.ncols && rhs.nrows == L.nrows, "LLT solve shape mismatch");
+  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, sizeof(float), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, sizeof(float), true, true, st);
+  llt_solve_in_place_f32(st, l.view<const float>(), r.view<float>());
+  finish_all(st, {&l, &r});
+}
+
 // ---- LDLT (no pivoting); DRAFT, see ldlt_f64.cu ----
 FaerV0_24_LdltParams libfaer_v0_23_LdltParams_f64(void) {
   return FaerV0_24_LdltParams{64, 128};  // reference defaults: ldlt/factor.rs:705-714

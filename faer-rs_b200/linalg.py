@@ -180,19 +180,24 @@ def llt_params_default():
 
 
 def cholesky_in_place(A, regularization=(0.0, 0.0), par=None, params=None) -> LltInfo:
-    """In-place LLT of the lower triangle of A. regularization = (delta, epsilon). Raises LltError."""
-    _check_f64(A)
+    """In-place LLT of the lower triangle of A (f64, or f32 on the recursive driver). regularization = (delta, epsilon).
+    Raises LltError."""
     lib = capi.load()
-    params = params or lib.libfaer_v0_23_LltParams_f64()
+    if _is_f32(A):
+        suf, real = "f32", C.c_float
+    else:
+        _check_f64(A)
+        suf, real = "f64", C.c_double
+    params = params or getattr(lib, f"libfaer_v0_23_LltParams_{suf}")()
     par = par or capi.par_default()
     n = A.shape[0]
-    lay = lib.libfaer_v0_23_llt_factor_in_place_scratch_f64(n, par, params)
+    lay = getattr(lib, f"libfaer_v0_23_llt_factor_in_place_scratch_{suf}")(n, par, params)
     scratch = np.empty(lay.len_bytes + lay.align_bytes, dtype=np.uint8)
-    delta = C.c_double(float(regularization[0]))
-    eps = C.c_double(float(regularization[1]))
+    delta = real(float(regularization[0]))
+    eps = real(float(regularization[1]))
     reg = capi.LltRegularization(C.cast(C.pointer(delta), C.c_void_p), C.cast(C.pointer(eps), C.c_void_p))
-    st = lib.libfaer_v0_23_llt_factor_in_place_f64(capi.mat_mut(A), reg, par,
-                                                   capi.MemAlloc(scratch.ctypes.data, scratch.size), params)
+    st = getattr(lib, f"libfaer_v0_23_llt_factor_in_place_{suf}")(capi.mat_mut(A), reg, par,
+                                                                 capi.MemAlloc(scratch.ctypes.data, scratch.size), params)
     if st.tag == 0:
         return LltInfo(int(st.value))
     if st.tag == 1:
@@ -251,11 +256,16 @@ def ldlt_solve_in_place(LD, rhs, conj: int = CONJ_NO, par=None) -> None:
 
 
 def llt_solve_in_place(L, rhs, conj: int = CONJ_NO, par=None) -> None:
-    """cholesky::llt::solve::solve_in_place_with_conj (llt/solve.rs:12-35): rhs <- (L L^H)^-1 rhs."""
-    _check_f64(L, rhs)
+    """cholesky::llt::solve::solve_in_place_with_conj (llt/solve.rs:12-35): rhs <- (L L^H)^-1 rhs. f64 or f32."""
     lib = capi.load()
-    lib.libfaer_v0_23_llt_solve_in_place_f64(capi.mat_ref(L), conj, capi.mat_mut(rhs), par or capi.par_default(),
-                                             capi.MemAlloc(None, 0))
+    if _is_f32(rhs):
+        assert _is_f32(L)
+        suf = "f32"
+    else:
+        _check_f64(L, rhs)
+        suf = "f64"
+    getattr(lib, f"libfaer_v0_23_llt_solve_in_place_{suf}")(capi.mat_ref(L), conj, capi.mat_mut(rhs),
+                                                            par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None, U=None) -> None:

@@ -183,6 +183,14 @@ struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(struct FaerV0_2
                                                                  struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem,
                                                                  struct FaerV0_24_LltParams params);
 
+/* f32 LLT: faer.h:636 (LltParams_f32), 4036-4048 (factor), 4180-4216 (solve); same semantics as the f64 entry points.
+ * Recursive driver with the f32 leaf (csrc/llt_f32.cu); first hardware run pending. */
+struct FaerV0_24_LltParams libfaer_v0_23_LltParams_f32(void);
+struct FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_f32(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LltParams params);
+struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_LltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LltParams params);
+struct FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_f32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_solve_in_place_f32(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+
 /* LDLT without pivoting.  types: faer.h:162-165 (LdltParams), 340-344 (VecRef), 346-381 (LdltStatus,
  * LdltRegularization);  params: lib.rs:660;  factor: lib.rs:1190-1217, faer.h:3802, 3830;  solve: lib.rs:1218-1246, faer.h:3974,
  * 4004.  Semantics: faer/src/linalg/cholesky/ldlt/factor.rs:725-767 (D on the diagonal of A, unit-lower L strictly below, strict
