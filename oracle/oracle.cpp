@@ -81,9 +81,11 @@ static void gemm_blocked(Mat<T> dst, int dst_s, bool add, Mat<const T> lhs, bool
   const i64 M = dst.m, N = dst.n, K = lhs.n;
   const i64 nic = (M + OR_MC - 1) / OR_MC, njc = (N + OR_NC - 1) / OR_NC;
   constexpr i64 TI = OR_MC / OR_BI, TJ = OR_NC / OR_BJ;
-#pragma omp parallel
+  // no more threads than blocks (hosts with hundreds of hardware threads), buffers only for threads that get a block
+  const int nthr = (int)std::max<i64>(1, std::min<i64>(omp_get_max_threads(), nic * njc));
+#pragma omp parallel num_threads(nthr)
   {
-    std::vector<T> Ap((size_t)OR_MC * OR_KC), Bp((size_t)OR_KC * OR_NC), Cb((size_t)OR_MC * OR_NC);
+    std::vector<T> Ap, Bp, Cb;
 #pragma omp for schedule(dynamic, 1) collapse(2)
     for (i64 jc = 0; jc < njc; ++jc) {
       for (i64 ic = 0; ic < nic; ++ic) {
@@ -92,6 +94,11 @@ static void gemm_blocked(Mat<T> dst, int dst_s, bool add, Mat<const T> lhs, bool
         if (dst_s != RECT) {
           if (s_lower(dst_s) && i0 + mc - 1 < j0) continue;  // block strictly above the diagonal
           if (s_upper(dst_s) && i0 > j0 + nc - 1) continue;  // block strictly below the diagonal
+        }
+        if (Ap.empty()) {
+          Ap.resize((size_t)OR_MC * OR_KC);
+          Bp.resize((size_t)OR_KC * OR_NC);
+          Cb.resize((size_t)OR_MC * OR_NC);
         }
         const i64 ti = (mc + OR_BI - 1) / OR_BI, tj = (nc + OR_BJ - 1) / OR_BJ;
         std::fill(Cb.begin(), Cb.begin() + (size_t)(ti * tj) * OR_BI * OR_BJ, T(0));
