@@ -432,6 +432,18 @@ def main():
                 "lu_f64_tflops": 2.0 * n ** 3 / 3.0 / t_lu / 1e9, "lu_ms": t_lu, "n": n,
                 "what": "device-resident f64 GEMM (Replace, alpha = 1) and partial-pivoting LU (u64 indices) at the same n"}
         del X, Xw
+        # ---- the other BASELINE.json configs (f32 QR 65536 x 4096, bidiagonalization and c64 GEMM at n = 8192), timed by
+        # tools/bench_other_configs.py in a CHILD process: informational, and nothing that happens there (not even an abort)
+        # can touch this line's headline fields ----
+        try:
+            import subprocess
+            child = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools",
+                                                                 "bench_other_configs.py")],
+                                   capture_output=True, text=True, timeout=300)
+            last = [ln for ln in child.stdout.strip().splitlines() if ln.startswith("{")]
+            also["other_configs"] = json.loads(last[-1]) if last else {"error": f"exit {child.returncode}: {child.stderr[-300:]}"}
+        except Exception as e:  # pragma: no cover
+            also["other_configs"] = {"error": repr(e)}
 
     cpu = None
     proxy = None
