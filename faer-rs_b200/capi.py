@@ -77,6 +77,22 @@ class LltStatus(C.Structure):
     _fields_ = [("tag", C.c_int), ("body", _StatusBody)]
 
 
+class BidiagParams(C.Structure):
+    _fields_ = [("par_threshold", C.c_size_t)]
+
+
+class SvdParams(C.Structure):
+    """faer.h:196-201."""
+    _fields_ = [("bidiag", BidiagParams), ("qr", QrParams), ("recursion_threshold", C.c_size_t),
+                ("qr_ratio_threshold", C.c_double)]
+
+
+class SvdStatus(C.Structure):
+    """tag: 0 Ok, 1 NoConvergence (faer.h:471-490)."""
+    _anonymous_ = ("body",)
+    _fields_ = [("tag", C.c_int), ("body", _StatusBody)]
+
+
 class LdltParams(C.Structure):
     _fields_ = [("recursion_threshold", C.c_size_t), ("block_size", C.c_size_t)]
 
@@ -197,6 +213,17 @@ def load() -> C.CDLL:
             f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
             f.argtypes = [MatRef, MatRef, MatRef, C.c_int, MatMut, P, MemAlloc]
             f.restype = None
+    for suf in ("f64", "f32"):
+        getattr(lib, f"libfaer_v0_23_BidiagParams_{suf}").argtypes = []
+        getattr(lib, f"libfaer_v0_23_BidiagParams_{suf}").restype = BidiagParams
+        getattr(lib, f"libfaer_v0_23_SvdParams_{suf}").argtypes = []
+        getattr(lib, f"libfaer_v0_23_SvdParams_{suf}").restype = SvdParams
+        f = getattr(lib, f"libfaer_v0_23_svd_scratch_{suf}")
+        f.argtypes = [C.c_size_t, C.c_size_t, C.c_int, C.c_int, P, SvdParams]
+        f.restype = Layout
+        f = getattr(lib, f"libfaer_v0_23_svd_{suf}")
+        f.argtypes = [MatRef, MatMut, VecMut, MatMut, P, MemAlloc, SvdParams]
+        f.restype = SvdStatus
     lib.libfaer_v0_23_LltParams_f32.argtypes = []
     lib.libfaer_v0_23_LltParams_f32.restype = LltParams
     lib.libfaer_v0_23_llt_factor_in_place_scratch_f32.argtypes = [C.c_size_t, P, LltParams]

@@ -149,6 +149,28 @@ void qr_solve_entry(FaerV0_24_MatRef Qb, FaerV0_24_MatRef Qc, FaerV0_24_MatRef R
   finish_all(st, {&b, &f, &r});
   if (rr) rr->finish();
 }
+// ---- singular values (svd/mod.rs:530-648 with u = v = None) ----
+template <class T>
+FaerV0_24_SvdStatus svd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t size = A.nrows < A.ncols ? A.nrows : A.ncols;
+  FB_ASSERT(S.len == size && (size == 0 || S.stride >= 1), "svd: S must have min(nrows, ncols) entries and a positive stride");
+  FB_ASSERT(U.ncols == 0 && V.ncols == 0,
+            "svd: singular vectors are not built on the GPU path yet (pass U and V with ncols == 0 for the values)");
+  FaerV0_24_SvdStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_SvdStatus_Ok;
+  if (size == 0) return out;
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, false, st);
+  T* s_dev = (T*)ws_alloc(size * sizeof(T));
+  singular_values<T>(st, a.view<const T>(), s_dev);
+  // strided scatter into the caller's vector (host or device)
+  FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), size, cudaMemcpyDefault, st));
+  finish_all(st, {&a});
+  ws_free(s_dev);
+  return out;
+}
 }  // namespace
 
 extern "C" {
@@ -725,6 +747,29 @@ void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_f64(FaerV0_24_Mat
   (void)A_conj; (void)perm_fwd; (void)par; (void)mem;
   lu_solve_entry(L, U, perm_bwd, rhs, 8, true);
 }
+
+// ---- SVD: singular values only for now (see svd.cu) ----
+#define FB_SVD_FFI(SUF, T)                                                                                             \
+  FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_##SUF(void) { return FaerV0_24_BidiagParams{192 * 256}; }          \
+  FaerV0_24_SvdParams libfaer_v0_23_SvdParams_##SUF(void) {                                                            \
+    /* svd/mod.rs:49-58: recursion_threshold 128, qr_ratio_threshold 11/6 */                                          \
+    return FaerV0_24_SvdParams{FaerV0_24_BidiagParams{192 * 256}, FaerV0_24_QrParams{48 * 48, 192 * 256}, 128, 11.0 / 6.0}; \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_svd_scratch_##SUF(size_t nrows, size_t ncols, FaerV0_24_ComputeSvdVectors compute_U,  \
+                                                   FaerV0_24_ComputeSvdVectors compute_V, FaerV0_24_Par par,           \
+                                                   FaerV0_24_SvdParams params) {                                       \
+    (void)compute_U; (void)compute_V; (void)par; (void)params;                                                         \
+    /* the GPU path keeps its workspace (a copy of A) in the device pool; reported so that callers size like faer */   \
+    return FaerV0_24_Layout{nrows * ncols * sizeof(T), 64};                                                            \
+  }                                                                                                                    \
+  FaerV0_24_SvdStatus libfaer_v0_23_svd_##SUF(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V, \
+                                              FaerV0_24_Par par, FaerV0_24_MemAlloc mem, FaerV0_24_SvdParams params) { \
+    (void)par; (void)mem; (void)params;                                                                                \
+    return svd_entry<T>(A, U, S, V);                                                                                   \
+  }
+FB_SVD_FFI(f64, double)
+FB_SVD_FFI(f32, float)
+#undef FB_SVD_FFI
 
 // ---- global par / alloc ----
 FaerV0_24_Par libfaer_v0_23_get_global_par(void) {

@@ -1,0 +1,110 @@
+// Singular values on the GPU (BASELINE.json configs[4], "SVD via bidiagonalization"; SURVEY.md §8f rank 4, values only):
+// A (or A^T for wide inputs, svd/mod.rs:560-575) is copied, reduced to bidiagonal form by the HBM-bound persistent kernel
+// of bidiag.cu, and the singular values of the bidiagonal come from one bisection thread per value (bidiag_sv.cuh).
+// Reference: faer/src/linalg/svd/mod.rs:530-648 (`svd` with u = v = None, as `MatRef::singular_values`, solvers.rs:457-487).
+// Differences, both documented in DESIGN.md: (1) the reference takes a QR factorization first when nrows / ncols exceeds
+// params.qr_ratio_threshold (11/6) and reaches the values through bidiag_svd (QR iteration / divide and conquer); here the
+// matrix is bidiagonalised directly and the values are located by Sturm counts — same values to n * eps * sigma_max, the
+// small ones to high relative accuracy; (2) singular VECTORS are not built yet (the D&C merges and back-transforms are
+// the next row): the entry point refuses them instead of returning something else.
+// STATUS: driver written after round 1's last GPU session; bidiag.cu is validated, bidiag_sv.cuh is checked on the CPU
+// (the same header compiled for the host), the three small kernels below have not run yet.
+#include "bidiag_sv.cuh"
+#include "runtime.cuh"
+#include "tensor_ops.cuh"
+
+namespace fb {
+
+namespace {
+
+template <class T>
+__global__ void copy_to_colmajor_kernel(T* __restrict__ dst, i64 ld, const T* __restrict__ src, i64 rs, i64 cs, i64 m, i64 n) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = blockIdx.y;
+  if (i < m && j < n) dst[j * ld + i] = src[i * rs + j * cs];
+}
+
+template <class T>
+__global__ void extract_bidiag_kernel(const T* __restrict__ A, i64 cs, int n, T* __restrict__ d, T* __restrict__ e) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    d[i] = A[(i64)i + (i64)i * cs];
+    if (i + 1 < n) e[i] = A[(i64)i + (i64)(i + 1) * cs];
+  }
+}
+
+// bb[0] = Gershgorin bound of T_GK (>= sigma_max), bb[1] = max b_j^2
+template <class T>
+__global__ void __launch_bounds__(256) gk_bound_kernel(const T* __restrict__ d, const T* __restrict__ e, int n,
+                                                        T* __restrict__ bb) {
+  __shared__ T s_bound[256], s_b2[256];
+  T bound = 0, b2 = 0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const T a = fabs(d[i]), b = i + 1 < n ? fabs(e[i]) : T(0), c = i > 0 ? fabs(e[i - 1]) : T(0);
+    bound = fmax(bound, fmax(a + b, a + c));
+    b2 = fmax(b2, fmax(a * a, b * b));
+  }
+  s_bound[threadIdx.x] = bound;
+  s_b2[threadIdx.x] = b2;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      s_bound[threadIdx.x] = fmax(s_bound[threadIdx.x], s_bound[threadIdx.x + s]);
+      s_b2[threadIdx.x] = fmax(s_b2[threadIdx.x], s_b2[threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    bb[0] = s_bound[0] * (T(1) + T(4) * bsv::Lim<T>::eps()) + bsv::Lim<T>::safmin();
+    bb[1] = s_b2[0];
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(64) gk_values_kernel(const T* __restrict__ d, const T* __restrict__ e, int n,
+                                                        const T* __restrict__ bb, T* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = bsv::gk_kth_largest<T>(d, e, n, 1, 1, k, bb[0], bb[1]);
+}
+
+}  // namespace
+
+// S (device, compact, min(m, n) entries) <- singular values of A in non-increasing order. A: device view, any strides.
+template <class T>
+void singular_values(cudaStream_t st, View<const T> A, T* S) {
+  View<const T> M = A.ncols > A.nrows ? A.t() : A;
+  const i64 m = M.nrows, n = M.ncols;
+  if (n == 0) return;
+  FB_ASSERT(n < 65536 && m < (1ll << 31), "singular_values: dimension too large for the copy launch");
+  T* W = (T*)ws_alloc((size_t)m * (size_t)n * sizeof(T));
+  {
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
+    copy_to_colmajor_kernel<T><<<grid, 256, 0, st>>>(W, m, M.ptr, M.rs, M.cs, m, n);
+    FB_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+  }
+  // one-row Householder factors: only the taus are produced, no T blocks (bidiag.cu skips them for a single row)
+  T* h = (T*)ws_alloc((size_t)(2 * n + 2) * sizeof(T));
+  View<T> Hl{h, 1, n, 1, 1}, Hr{h + n, 1, n - 1, 1, 1};
+  bidiag_in_place<T>(st, View<T>{W, m, n, 1, m}, Hl, Hr);
+  T* de = (T*)ws_alloc((size_t)(2 * n + 2) * sizeof(T));
+  T *d = de, *e = de + n, *bb = de + 2 * n;
+  extract_bidiag_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, m, (int)n, d, e);
+  FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  gk_bound_kernel<T><<<1, 256, 0, st>>>(d, e, (int)n, bb);
+  FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  gk_values_kernel<T><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d, e, (int)n, bb, S);
+  FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  ws_free(de);
+  ws_free(h);
+  ws_free(W);
+}
+
+template void singular_values<double>(cudaStream_t, View<const double>, double*);
+template void singular_values<float>(cudaStream_t, View<const float>, float*);
+
+}  // namespace fb

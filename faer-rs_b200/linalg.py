@@ -376,6 +376,30 @@ def qr_solve_transpose_in_place(Q_basis, Q_coeff, R, rhs, conj: int = CONJ_NO, p
     _qr_solve("qr_solve_transpose_in_place", Q_basis, Q_coeff, R, rhs, conj, par)
 
 
+def singular_values(A, par=None, params=None):
+    """`svd` with u = v = None (svd/mod.rs:530-648), as `MatRef::singular_values` (solvers.rs:457-487): the
+    min(nrows, ncols) singular values of A in non-increasing order, as a numpy vector (host input) or a CUDA tensor (device
+    input). f64 or f32. Singular vectors are not built on the GPU path yet."""
+    lib = capi.load()
+    suf = _suf(A)
+    m, n = A.shape
+    size = min(m, n)
+    if capi._is_torch(A):
+        import torch
+        S = torch.zeros(size, dtype=A.dtype, device=A.device)
+        sv = capi.VecMut(S.data_ptr(), size, 1)
+    else:
+        S = np.zeros(size, dtype=A.dtype)
+        sv = capi.VecMut(S.ctypes.data, size, 1)
+    params = params or getattr(lib, f"libfaer_v0_23_SvdParams_{suf}")()
+    none = capi.MatMut(None, 0, 0, 0, 0)
+    st = getattr(lib, f"libfaer_v0_23_svd_{suf}")(capi.mat_ref(A), none, sv, none, par or capi.par_default(),
+                                                  capi.MemAlloc(None, 0), params)
+    if st.tag != 0:
+        raise RuntimeError("SvdError::NoConvergence")
+    return S
+
+
 def bidiag_in_place(A, H_left, H_right, par=None, params=None) -> None:
     """svd::bidiag::bidiag_in_place (svd/bidiag.rs:47-256): A = U B V^H for nrows >= ncols, f64 or f32. B ends up on A's
     diagonal / superdiagonal, the left reflectors below the diagonal (T blocks in H_left, bl x ncols), the right

@@ -404,3 +404,8 @@ def partial_piv_lu(A) -> PartialPivLu:
 
 def qr(A) -> Qr:
     return Qr.new(A)
+
+
+def singular_values(A):
+    """`A.singular_values()` (solvers.rs:457-487): non-increasing, through `svd` with no vectors."""
+    return la.singular_values(A)

@@ -84,6 +84,26 @@ typedef struct FaerV0_24_LdltStatus {
   };
 } FaerV0_24_LdltStatus;
 
+/* SVD types: faer.h:87-99 (ComputeSvdVectors, BidiagParams), 196-201 (SvdParams), 471-490 (SvdStatus); VecMut lib.rs / faer.h */
+typedef enum FaerV0_24_ComputeSvdVectors { FaerV0_24_ComputeSvdVectors_No, FaerV0_24_ComputeSvdVectors_Thin, FaerV0_24_ComputeSvdVectors_Full } FaerV0_24_ComputeSvdVectors;
+typedef struct FaerV0_24_BidiagParams { size_t par_threshold; } FaerV0_24_BidiagParams;
+typedef struct FaerV0_24_SvdParams {
+  struct FaerV0_24_BidiagParams bidiag;
+  struct FaerV0_24_QrParams qr;
+  size_t recursion_threshold;
+  double qr_ratio_threshold;
+} FaerV0_24_SvdParams;
+typedef enum FaerV0_24_SvdStatus_Tag { FaerV0_24_SvdStatus_Ok, FaerV0_24_SvdStatus_NoConvergence } FaerV0_24_SvdStatus_Tag;
+typedef struct FaerV0_24_SvdStatus_FaerV0_24_Ok_Body { size_t padding; } FaerV0_24_SvdStatus_FaerV0_24_Ok_Body;
+typedef struct FaerV0_24_SvdStatus_FaerV0_24_NoConvergence_Body { size_t padding; } FaerV0_24_SvdStatus_FaerV0_24_NoConvergence_Body;
+typedef struct FaerV0_24_SvdStatus {
+  FaerV0_24_SvdStatus_Tag tag;
+  union {
+    FaerV0_24_SvdStatus_FaerV0_24_Ok_Body ok;
+    FaerV0_24_SvdStatus_FaerV0_24_NoConvergence_Body no_convergence;
+  };
+} FaerV0_24_SvdStatus;
+
 /* ---- status unions: faer-ffi/src/lib.rs:552-629, C layout faer-ffi/faer.h:383-469 ---- */
 typedef enum FaerV0_24_LltStatus_Tag { FaerV0_24_LltStatus_Ok, FaerV0_24_LltStatus_NonPositivePivot, FaerV0_24_LltStatus_Unknown } FaerV0_24_LltStatus_Tag;
 typedef struct FaerV0_24_LltStatus_FaerV0_24_Ok_Body { size_t dynamic_regularization_count; } FaerV0_24_LltStatus_FaerV0_24_Ok_Body;
@@ -182,6 +202,19 @@ struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(struct FaerV0_2
                                                                  struct FaerV0_24_LltRegularization regularization,
                                                                  struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem,
                                                                  struct FaerV0_24_LltParams params);
+
+/* SVD (BASELINE.json configs[4]): lib.rs:2326-2366, faer.h:504 (BidiagParams), 708 (SvdParams), 6230-6268 (svd, svd_scratch);
+ * semantics faer/src/linalg/svd/mod.rs:530-648. SINGULAR VALUES ONLY for now: U and V must be passed with ncols == 0 (the
+ * reference's "None"); S receives min(nrows, ncols) values in non-increasing order. See csrc/svd.cu for the algorithm and
+ * its status (written after round 1's last GPU session). */
+struct FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_f64(void);
+struct FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_f32(void);
+struct FaerV0_24_SvdParams libfaer_v0_23_SvdParams_f64(void);
+struct FaerV0_24_SvdParams libfaer_v0_23_SvdParams_f32(void);
+struct FaerV0_24_Layout libfaer_v0_23_svd_scratch_f64(size_t nrows, size_t ncols, enum FaerV0_24_ComputeSvdVectors compute_U, enum FaerV0_24_ComputeSvdVectors compute_V, struct FaerV0_24_Par par, struct FaerV0_24_SvdParams params);
+struct FaerV0_24_Layout libfaer_v0_23_svd_scratch_f32(size_t nrows, size_t ncols, enum FaerV0_24_ComputeSvdVectors compute_U, enum FaerV0_24_ComputeSvdVectors compute_V, struct FaerV0_24_Par par, struct FaerV0_24_SvdParams params);
+struct FaerV0_24_SvdStatus libfaer_v0_23_svd_f64(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_MatMut V, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SvdParams params);
+struct FaerV0_24_SvdStatus libfaer_v0_23_svd_f32(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_MatMut V, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SvdParams params);
 
 /* f32 LLT: faer.h:636 (LltParams_f32), 4036-4048 (factor), 4180-4216 (solve); same semantics as the f64 entry points.
  * Recursive driver with the f32 leaf (csrc/llt_f32.cu); first hardware run pending. */
