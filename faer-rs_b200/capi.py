@@ -77,6 +77,21 @@ class LltStatus(C.Structure):
     _fields_ = [("tag", C.c_int), ("body", _StatusBody)]
 
 
+class TridiagParams(C.Structure):
+    _fields_ = [("par_threshold", C.c_size_t)]
+
+
+class SelfAdjointEvdParams(C.Structure):
+    """faer.h:191-194."""
+    _fields_ = [("tridiag", TridiagParams), ("recursion_threshold", C.c_size_t)]
+
+
+class EvdStatus(C.Structure):
+    """tag: 0 Ok, 1 NoConvergence (faer.h:260-279)."""
+    _anonymous_ = ("body",)
+    _fields_ = [("tag", C.c_int), ("body", _StatusBody)]
+
+
 class BidiagParams(C.Structure):
     _fields_ = [("par_threshold", C.c_size_t)]
 
@@ -224,6 +239,16 @@ def load() -> C.CDLL:
         f = getattr(lib, f"libfaer_v0_23_svd_{suf}")
         f.argtypes = [MatRef, MatMut, VecMut, MatMut, P, MemAlloc, SvdParams]
         f.restype = SvdStatus
+        getattr(lib, f"libfaer_v0_23_TridiagParams_{suf}").argtypes = []
+        getattr(lib, f"libfaer_v0_23_TridiagParams_{suf}").restype = TridiagParams
+        getattr(lib, f"libfaer_v0_23_SelfAdjointEvdParams_{suf}").argtypes = []
+        getattr(lib, f"libfaer_v0_23_SelfAdjointEvdParams_{suf}").restype = SelfAdjointEvdParams
+        f = getattr(lib, f"libfaer_v0_23_self_adjoint_evd_scratch_{suf}")
+        f.argtypes = [C.c_size_t, C.c_int, P, SelfAdjointEvdParams]
+        f.restype = Layout
+        f = getattr(lib, f"libfaer_v0_23_self_adjoint_evd_{suf}")
+        f.argtypes = [MatRef, MatMut, VecMut, P, MemAlloc, SelfAdjointEvdParams]
+        f.restype = EvdStatus
     lib.libfaer_v0_23_LltParams_f32.argtypes = []
     lib.libfaer_v0_23_LltParams_f32.restype = LltParams
     lib.libfaer_v0_23_llt_factor_in_place_scratch_f32.argtypes = [C.c_size_t, P, LltParams]

@@ -149,6 +149,27 @@ void qr_solve_entry(FaerV0_24_MatRef Qb, FaerV0_24_MatRef Qc, FaerV0_24_MatRef R
   finish_all(st, {&b, &f, &r});
   if (rr) rr->finish();
 }
+// ---- eigenvalues of a self-adjoint matrix (evd/mod.rs:270-353 with u = None) ----
+template <class T>
+FaerV0_24_EvdStatus self_adjoint_evd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t n = A.nrows;
+  FB_ASSERT(A.ncols == n && S.len == n && (n == 0 || S.stride >= 1), "self_adjoint_evd: square A, S of length n, positive stride");
+  FB_ASSERT(U.ncols == 0,
+            "self_adjoint_evd: eigenvectors are not built on the GPU path yet (pass U with ncols == 0 for the values)");
+  FaerV0_24_EvdStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_EvdStatus_Ok;
+  if (n == 0) return out;
+  StagedMat a(A.ptr, (i64)n, (i64)n, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, false, st);
+  T* s_dev = (T*)ws_alloc(n * sizeof(T));
+  self_adjoint_eigenvalues<T>(st, a.view<const T>(), s_dev);
+  FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), n, cudaMemcpyDefault, st));
+  finish_all(st, {&a});
+  ws_free(s_dev);
+  return out;
+}
 // ---- singular values (svd/mod.rs:530-648 with u = v = None) ----
 template <class T>
 FaerV0_24_SvdStatus svd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V) {
@@ -770,6 +791,27 @@ void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_f64(FaerV0_24_Mat
 FB_SVD_FFI(f64, double)
 FB_SVD_FFI(f32, float)
 #undef FB_SVD_FFI
+
+// ---- self-adjoint EVD: eigenvalues only for now (see evd.cu) ----
+#define FB_EVD_FFI(SUF, T)                                                                                             \
+  FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_##SUF(void) { return FaerV0_24_TridiagParams{192 * 256}; }       \
+  FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_##SUF(void) {                                      \
+    return FaerV0_24_SelfAdjointEvdParams{FaerV0_24_TridiagParams{192 * 256}, 128}; /* evd/mod.rs:82-90 */             \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_##SUF(size_t dim, FaerV0_24_ComputeEigenvectors compute_U,   \
+                                                                FaerV0_24_Par par, FaerV0_24_SelfAdjointEvdParams params) { \
+    (void)compute_U; (void)par; (void)params;                                                                          \
+    return FaerV0_24_Layout{dim * dim * sizeof(T), 64}; /* the copy of A (kept in the device pool here) */             \
+  }                                                                                                                    \
+  FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_##SUF(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, \
+                                                           FaerV0_24_Par par, FaerV0_24_MemAlloc mem,                  \
+                                                           FaerV0_24_SelfAdjointEvdParams params) {                    \
+    (void)par; (void)mem; (void)params;                                                                                \
+    return self_adjoint_evd_entry<T>(A, U, S);                                                                         \
+  }
+FB_EVD_FFI(f64, double)
+FB_EVD_FFI(f32, float)
+#undef FB_EVD_FFI
 
 // ---- global par / alloc ----
 FaerV0_24_Par libfaer_v0_23_get_global_par(void) {

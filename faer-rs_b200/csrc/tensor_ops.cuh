@@ -51,6 +51,11 @@ i64 qr_recommended_block_size(i64 nrows, i64 ncols);
 // A = U B V^H, m >= n, column-major A. Reference: svd/bidiag.rs:47-256. Hl: bl x n, Hr: br x (n-1) (T blocks).
 template <class T>
 void bidiag_in_place(cudaStream_t st, View<T> A, View<T> Hl, View<T> Hr);
+// ---- evd.cu ----
+// S (device, compact, n entries) <- eigenvalues (nondecreasing) of the self-adjoint matrix whose lower triangle is in A
+// (evd/mod.rs:270-353 with u = None)
+template <class T>
+void self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S);
 // ---- svd.cu ----
 // S (device, compact, min(m, n) entries) <- the singular values of A, non-increasing (svd/mod.rs:530-648 with u = v = None)
 template <class T>

@@ -400,6 +400,29 @@ def singular_values(A, par=None, params=None):
     return S
 
 
+def self_adjoint_eigenvalues(A, par=None, params=None):
+    """`self_adjoint_evd` with u = None (evd/mod.rs:270-353), as `MatRef::self_adjoint_eigenvalues(Side::Lower)`
+    (solvers.rs:417-456): the eigenvalues of the self-adjoint matrix whose LOWER triangle is in A, nondecreasing, as a numpy
+    vector (host input) or a CUDA tensor (device input). f64 or f32, n <= 8192. Eigenvectors are not built on the GPU yet."""
+    lib = capi.load()
+    suf = _suf(A)
+    n = A.shape[0]
+    assert A.shape[1] == n
+    if capi._is_torch(A):
+        import torch
+        S = torch.zeros(n, dtype=A.dtype, device=A.device)
+        sv = capi.VecMut(S.data_ptr(), n, 1)
+    else:
+        S = np.zeros(n, dtype=A.dtype)
+        sv = capi.VecMut(S.ctypes.data, n, 1)
+    params = params or getattr(lib, f"libfaer_v0_23_SelfAdjointEvdParams_{suf}")()
+    st = getattr(lib, f"libfaer_v0_23_self_adjoint_evd_{suf}")(capi.mat_ref(A), capi.MatMut(None, 0, 0, 0, 0), sv,
+                                                               par or capi.par_default(), capi.MemAlloc(None, 0), params)
+    if st.tag != 0:
+        raise RuntimeError("EvdError::NoConvergence")
+    return S
+
+
 def bidiag_in_place(A, H_left, H_right, par=None, params=None) -> None:
     """svd::bidiag::bidiag_in_place (svd/bidiag.rs:47-256): A = U B V^H for nrows >= ncols, f64 or f32. B ends up on A's
     diagonal / superdiagonal, the left reflectors below the diagonal (T blocks in H_left, bl x ncols), the right

@@ -409,3 +409,8 @@ def qr(A) -> Qr:
 def singular_values(A):
     """`A.singular_values()` (solvers.rs:457-487): non-increasing, through `svd` with no vectors."""
     return la.singular_values(A)
+
+
+def self_adjoint_eigenvalues(A, side: int = Side.Lower):
+    """`A.self_adjoint_eigenvalues(side)` (solvers.rs:417-456): nondecreasing; only the chosen triangle of A is read."""
+    return la.self_adjoint_eigenvalues(A if side == Side.Lower else A.T)

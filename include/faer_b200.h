@@ -104,6 +104,21 @@ typedef struct FaerV0_24_SvdStatus {
   };
 } FaerV0_24_SvdStatus;
 
+/* self-adjoint EVD types: faer.h:67-70 (ComputeEigenvectors), 187-194 (TridiagParams, SelfAdjointEvdParams), 260-279 (EvdStatus) */
+typedef enum FaerV0_24_ComputeEigenvectors { FaerV0_24_ComputeEigenvectors_No, FaerV0_24_ComputeEigenvectors_Yes } FaerV0_24_ComputeEigenvectors;
+typedef struct FaerV0_24_TridiagParams { size_t par_threshold; } FaerV0_24_TridiagParams;
+typedef struct FaerV0_24_SelfAdjointEvdParams { struct FaerV0_24_TridiagParams tridiag; size_t recursion_threshold; } FaerV0_24_SelfAdjointEvdParams;
+typedef enum FaerV0_24_EvdStatus_Tag { FaerV0_24_EvdStatus_Ok, FaerV0_24_EvdStatus_NoConvergence } FaerV0_24_EvdStatus_Tag;
+typedef struct FaerV0_24_EvdStatus_FaerV0_24_Ok_Body { size_t padding; } FaerV0_24_EvdStatus_FaerV0_24_Ok_Body;
+typedef struct FaerV0_24_EvdStatus_FaerV0_24_NoConvergence_Body { size_t padding; } FaerV0_24_EvdStatus_FaerV0_24_NoConvergence_Body;
+typedef struct FaerV0_24_EvdStatus {
+  FaerV0_24_EvdStatus_Tag tag;
+  union {
+    FaerV0_24_EvdStatus_FaerV0_24_Ok_Body ok;
+    FaerV0_24_EvdStatus_FaerV0_24_NoConvergence_Body no_convergence;
+  };
+} FaerV0_24_EvdStatus;
+
 /* ---- status unions: faer-ffi/src/lib.rs:552-629, C layout faer-ffi/faer.h:383-469 ---- */
 typedef enum FaerV0_24_LltStatus_Tag { FaerV0_24_LltStatus_Ok, FaerV0_24_LltStatus_NonPositivePivot, FaerV0_24_LltStatus_Unknown } FaerV0_24_LltStatus_Tag;
 typedef struct FaerV0_24_LltStatus_FaerV0_24_Ok_Body { size_t dynamic_regularization_count; } FaerV0_24_LltStatus_FaerV0_24_Ok_Body;
@@ -215,6 +230,18 @@ struct FaerV0_24_Layout libfaer_v0_23_svd_scratch_f64(size_t nrows, size_t ncols
 struct FaerV0_24_Layout libfaer_v0_23_svd_scratch_f32(size_t nrows, size_t ncols, enum FaerV0_24_ComputeSvdVectors compute_U, enum FaerV0_24_ComputeSvdVectors compute_V, struct FaerV0_24_Par par, struct FaerV0_24_SvdParams params);
 struct FaerV0_24_SvdStatus libfaer_v0_23_svd_f64(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_MatMut V, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SvdParams params);
 struct FaerV0_24_SvdStatus libfaer_v0_23_svd_f32(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_MatMut V, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SvdParams params);
+
+/* Self-adjoint EVD: lib.rs:2367-2400, faer.h:696, 720, 6064, 6098; semantics faer/src/linalg/evd/mod.rs:270-353 (the LOWER triangle
+ * of A is read; eigenvalues in nondecreasing order). EIGENVALUES ONLY for now: U must be passed with ncols == 0; n <= 8192.
+ * See csrc/evd.cu for the algorithm and its status (written after round 1's last GPU session). */
+struct FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_f64(void);
+struct FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_f32(void);
+struct FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_f64(void);
+struct FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_f32(void);
+struct FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_f64(size_t dim, enum FaerV0_24_ComputeEigenvectors compute_U, struct FaerV0_24_Par par, struct FaerV0_24_SelfAdjointEvdParams params);
+struct FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_f32(size_t dim, enum FaerV0_24_ComputeEigenvectors compute_U, struct FaerV0_24_Par par, struct FaerV0_24_SelfAdjointEvdParams params);
+struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_f64(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SelfAdjointEvdParams params);
+struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_f32(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SelfAdjointEvdParams params);
 
 /* f32 LLT: faer.h:636 (LltParams_f32), 4036-4048 (factor), 4180-4216 (solve); same semantics as the f64 entry points.
  * Recursive driver with the f32 leaf (csrc/llt_f32.cu); first hardware run pending. */
