@@ -244,14 +244,23 @@ def ldlt_in_place(A, regularization=(0.0, 0.0), signs=None, par=None, params=Non
     raise RuntimeError("LdltStatus::Unknown")
 
 
-def ldlt_solve_in_place(LD, rhs, conj: int = CONJ_NO, par=None) -> None:
+def ldlt_solve_in_place(LD, rhs, conj: int = CONJ_NO, par=None, D=None) -> None:
     """cholesky::ldlt::solve::solve_in_place_with_conj (ldlt/solve.rs:11-49): rhs <- (L D L^T)^-1 rhs with L the unit-lower
-    part of LD and D its diagonal (passed as a strided vector over the same storage, as `L.diagonal()` in the reference)."""
+    part of LD. D defaults to the diagonal of LD (passed as a strided vector over the same storage, as `L.diagonal()` in
+    the reference); a separate contiguous vector can be given instead, as `Ldlt::D()`."""
     _check_f64(LD, rhs)
     lib = capi.load()
     p, m, n, rs, cs = capi._fields(LD)
     assert m == n
-    lib.libfaer_v0_23_ldlt_solve_in_place_f64(capi.mat_ref(LD), capi.VecMut(p, n, rs + cs), conj, capi.mat_mut(rhs),
+    if D is None:
+        dv = capi.VecMut(p, n, rs + cs)
+    elif capi._is_torch(D):
+        assert D.dim() == 1 and D.numel() == n and D.is_contiguous()
+        dv = capi.VecMut(D.data_ptr(), n, 1)
+    else:
+        assert D.ndim == 1 and D.size == n and D.dtype == np.float64 and D.flags.c_contiguous
+        dv = capi.VecMut(D.ctypes.data, n, 1)
+    lib.libfaer_v0_23_ldlt_solve_in_place_f64(capi.mat_ref(LD), dv, conj, capi.mat_mut(rhs),
                                               par or capi.par_default(), capi.MemAlloc(None, 0))
 
 

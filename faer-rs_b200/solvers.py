@@ -25,7 +25,7 @@ import numpy as np
 
 from . import capi
 from . import linalg as la
-from .linalg import LltError  # noqa: F401  (re-exported: Llt.new raises it)
+from .linalg import LdltError, LltError  # noqa: F401  (re-exported: Llt.new / Ldlt.new raise them)
 
 
 class Side:
@@ -245,6 +245,57 @@ class Llt(_Solve):
         return out
 
 
+class Ldlt(_Solve):
+    """A = L D L^T without pivoting (solvers.rs:818-872): unit-lower L (explicit unit diagonal, zero strict upper part) and
+    the diagonal D as a vector. `Ldlt.new(A, side)` raises LdltError(index) on a zero pivot."""
+
+    def __init__(self, L, D):
+        self._L, self._D = L, D
+
+    @classmethod
+    def new(cls, A, side: int = Side.Lower) -> "Ldlt":
+        assert A.ndim == 2 and A.shape[0] == A.shape[1]
+        n = A.shape[0]
+        L = _zeros(A, n, n)
+        _assign(L, _tri(A if side == Side.Lower else A.T, lower=True))
+        la.ldlt_in_place(L)  # default regularization and params; LdltError propagates
+        if _t(L):
+            D = L.diagonal().clone()
+        else:
+            D = np.ascontiguousarray(np.diagonal(L).copy())
+        _fill_diag_one(L)
+        _zero_strict_upper(L)
+        return cls(L, D)
+
+    def L(self):
+        return self._L
+
+    def D(self):
+        return self._D
+
+    def nrows(self) -> int:
+        return self._L.shape[0]
+
+    ncols = nrows
+
+    def _like(self):
+        return self._L
+
+    def _solve_core(self, rhs) -> None:
+        la.ldlt_solve_in_place(self._L, rhs, D=self._D)
+
+    _solve_transpose_core = _solve_core  # real scalars: A^T = A
+
+    def reconstruct(self):
+        """ldlt/reconstruct.rs: L D L^H."""
+        LDm = _owned(self._L)
+        if _t(LDm):
+            LDm.mul_(self._D.unsqueeze(0))
+        else:
+            LDm *= self._D[None, :]
+        return mul(LDm, self._L.T)
+
+
 class PartialPivLu(_Solve):
     """P A = L U (solvers.rs:981-1034). `P()` returns (perm_fwd, perm_bwd): (P A)[i, :] = A[perm_fwd[i], :]."""
 
@@ -396,6 +447,10 @@ class Qr(_Solve):
 # `A.llt(side)`, `A.partial_piv_lu()`, `A.qr()` (solvers.rs:346-392) as free functions
 def llt(A, side: int = Side.Lower) -> Llt:
     return Llt.new(A, side)
+
+
+def ldlt(A, side: int = Side.Lower) -> Ldlt:
+    return Ldlt.new(A, side)
 
 
 def partial_piv_lu(A) -> PartialPivLu:

@@ -119,3 +119,30 @@ def run_all(sv):
     # ---- `&A * &B` ----
     C = sv.mul(A, B[:n, :])
     assert C.shape == (n, n2) and approx(C, A @ B[:n, :], n, np.abs(A).max() * np.abs(B).max() * n)
+
+
+def run_ldlt(sv):
+    """Ldlt (solvers.rs:818-872) on a symmetric indefinite matrix with a dominant diagonal: test_solver identities, L / D
+    contracts, both sides, ZeroPivot. Separate from run_all so that the GPU run of the validated decompositions does not
+    depend on the LDLT kernel (first hardware run pending)."""
+    rng = np.random.default_rng(7)
+    n = 50
+    G = rng.standard_normal((n, n))
+    s = np.where(rng.random(n) < 0.4, -1.0, 1.0)
+    A = np.asfortranarray((G + G.T) / np.sqrt(n) + np.diag(4.0 * s))
+    dec = sv.ldlt(A, sv.Side.Lower)
+    L, D = dec.L(), dec.D()
+    assert np.all(np.diag(L) == 1) and np.all(np.triu(L, 1) == 0) and D.shape == (n,)
+    assert approx(L @ np.diag(D) @ L.T, A, n, np.abs(A).max())
+    assert (np.asarray(D) < 0).sum() == (np.linalg.eigvalsh(A) < 0).sum()
+    check_solver(A, dec, np.linalg.cond(A))
+    poisoned = A.copy(order="F"); poisoned[np.tril_indices(n, -1)] = np.nan
+    up = sv.Ldlt.new(poisoned, sv.Side.Upper)
+    assert np.allclose(up.L(), L, rtol=1e-12, atol=1e-14) and np.allclose(up.D(), D, rtol=1e-12, atol=1e-14)
+    bad = A.copy(order="F")
+    bad[:4, :4] = np.diag([2.0, 4.0, 8.0, 0.0]); bad[3, :3] = bad[:3, 3] = [2.0, 4.0, 8.0]; bad[3, 3] = 14.0
+    try:
+        sv.ldlt(bad)
+        raise AssertionError("expected LdltError")
+    except sv.LdltError as e:
+        assert e.index == 3

@@ -96,3 +96,10 @@ def test_ldlt_device_resident_large(fb, cuda_dev):
     x = torch.randn((n, 6), dtype=torch.float64, device=cuda_dev)
     r = A0 @ x - L @ (D[:, None] * (L.T @ x))
     assert float(r.abs().max()) <= 128 * U * n * float(A0.abs().max()) * float(x.abs().max())
+
+
+def test_ldlt_solver_class(fb, cuda_dev):
+    """faer_b200.solvers.Ldlt through the C ABI: the shared cases of tests/solvers_cases.py (also run on the CPU with the
+    oracle-backed stand-in)."""
+    from solvers_cases import run_ldlt
+    run_ldlt(fb.solvers)

@@ -7,7 +7,7 @@ import types
 import numpy as np
 import pytest
 
-from solvers_cases import run_all
+from solvers_cases import run_all, run_ldlt
 
 
 def oracle_backed_la(fb, oracle):
@@ -22,6 +22,18 @@ def oracle_backed_la(fb, oracle):
     def llt_solve_in_place(L, rhs, conj=0, par=None):
         oracle.solve_triangular(L, rhs, lower=True, unit=False)
         oracle.solve_triangular(L.T, rhs, lower=False, unit=False)
+
+    def ldlt_in_place(A, regularization=(0.0, 0.0), signs=None, par=None, params=None):
+        fail, count = oracle.ldlt(A, regularization[0], regularization[1], signs)
+        if fail >= 0:
+            raise real.LdltError(fail)
+        return count
+
+    def ldlt_solve_in_place(LD, rhs, conj=0, par=None, D=None):
+        packed = np.array(LD, order="F", copy=True)
+        if D is not None:
+            np.fill_diagonal(packed, D)
+        oracle.ldlt_solve(packed, rhs)
 
     def lu_in_place(A, perm, perm_inv, par=None, params=None):
         p, pi, _ = oracle.lu(A)
@@ -71,6 +83,7 @@ def oracle_backed_la(fb, oracle):
     return types.SimpleNamespace(
         Accum=real.Accum, BlockStructure=real.BlockStructure, LltError=real.LltError,
         cholesky_in_place=cholesky_in_place, llt_solve_in_place=llt_solve_in_place, lu_in_place=lu_in_place,
+        ldlt_in_place=ldlt_in_place, ldlt_solve_in_place=ldlt_solve_in_place, LdltError=real.LdltError,
         lu_solve_in_place=lu_solve_in_place, lu_solve_transpose_in_place=lu_solve_transpose_in_place,
         qr_recommended_block_size=oracle.qr_recommended_block_size, qr_in_place=qr_in_place,
         qr_solve_lstsq_in_place=qr_solve_lstsq_in_place, qr_solve_in_place=qr_solve_in_place,
@@ -82,6 +95,7 @@ def test_solvers_host_logic_against_oracle_backend(fb, oracle, monkeypatch):
     sv = fb.solvers
     monkeypatch.setattr(sv, "la", oracle_backed_la(fb, oracle))
     run_all(sv)
+    run_ldlt(sv)
 
 
 def test_split_lu_contract(fb):

@@ -19,6 +19,9 @@ def tev(tmp_path_factory):
     subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out,
                            os.path.join(ROOT, "tools", "emul", "tridiag_ev_host.cpp")])
     lib = C.CDLL(out)
+    for name in ('tev_f64', 'tev_f32'):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]  # 64-bit pointers
+        getattr(lib, name).restype = None
 
     def run(d, e):
         dt = d.dtype
