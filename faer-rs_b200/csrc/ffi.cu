@@ -172,7 +172,8 @@ FaerV0_24_EvdStatus self_adjoint_evd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut 
 }
 // ---- singular values (svd/mod.rs:530-648 with u = v = None) ----
 template <class T>
-FaerV0_24_SvdStatus svd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V) {
+FaerV0_24_SvdStatus svd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V,
+                              double qr_ratio_threshold) {
   FB_ENTRY();
   cudaStream_t st = current_stream();
   const size_t size = A.nrows < A.ncols ? A.nrows : A.ncols;
@@ -185,7 +186,7 @@ FaerV0_24_SvdStatus svd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_
   if (size == 0) return out;
   StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, false, st);
   T* s_dev = (T*)ws_alloc(size * sizeof(T));
-  singular_values<T>(st, a.view<const T>(), s_dev);
+  singular_values<T>(st, a.view<const T>(), s_dev, qr_ratio_threshold > 0.0 ? qr_ratio_threshold : 11.0 / 6.0);
   // strided scatter into the caller's vector (host or device)
   FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), size, cudaMemcpyDefault, st));
   finish_all(st, {&a});
@@ -785,8 +786,8 @@ void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_f64(FaerV0_24_Mat
   }                                                                                                                    \
   FaerV0_24_SvdStatus libfaer_v0_23_svd_##SUF(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V, \
                                               FaerV0_24_Par par, FaerV0_24_MemAlloc mem, FaerV0_24_SvdParams params) { \
-    (void)par; (void)mem; (void)params;                                                                                \
-    return svd_entry<T>(A, U, S, V);                                                                                   \
+    (void)par; (void)mem;                                                                                              \
+    return svd_entry<T>(A, U, S, V, params.qr_ratio_threshold);                                                        \
   }
 FB_SVD_FFI(f64, double)
 FB_SVD_FFI(f32, float)

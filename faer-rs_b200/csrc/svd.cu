@@ -2,10 +2,10 @@
 // A (or A^T for wide inputs, svd/mod.rs:560-575) is copied, reduced to bidiagonal form by the HBM-bound persistent kernel
 // of bidiag.cu, and the singular values of the bidiagonal come from one bisection thread per value (bidiag_sv.cuh).
 // Reference: faer/src/linalg/svd/mod.rs:530-648 (`svd` with u = v = None, as `MatRef::singular_values`, solvers.rs:457-487).
-// Differences, both documented in DESIGN.md: (1) the reference takes a QR factorization first when nrows / ncols exceeds
-// params.qr_ratio_threshold (11/6) and reaches the values through bidiag_svd (QR iteration / divide and conquer); here the
-// matrix is bidiagonalised directly and the values are located by Sturm counts — same values to n * eps * sigma_max, the
-// small ones to high relative accuracy; (2) singular VECTORS are not built yet (the D&C merges and back-transforms are
+// Like the reference, a QR factorization comes first when nrows / ncols exceeds params.qr_ratio_threshold (11/6) and R is
+// bidiagonalised instead. Differences, both documented in DESIGN.md: (1) the reference reaches the values of the bidiagonal
+// through bidiag_svd (QR iteration / divide and conquer); here they are located by Sturm counts — same values to
+// n * eps * sigma_max, the small ones to high relative accuracy; (2) singular VECTORS are not built yet (the D&C merges and back-transforms are
 // the next row): the entry point refuses them instead of returning something else.
 // STATUS: driver written after round 1's last GPU session; bidiag.cu is validated, bidiag_sv.cuh is checked on the CPU
 // (the same header compiled for the host), the three small kernels below have not run yet.
@@ -22,6 +22,14 @@ __global__ void copy_to_colmajor_kernel(T* __restrict__ dst, i64 ld, const T* __
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const i64 j = blockIdx.y;
   if (i < m && j < n) dst[j * ld + i] = src[i * rs + j * cs];
+}
+
+// R (n x n, column-major, ld = n) <- the upper triangle of the leading n x n block of QR (ld = ldq), zero below the diagonal
+template <class T>
+__global__ void copy_upper_kernel(T* __restrict__ R, i64 n, const T* __restrict__ QR, i64 ldq) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = blockIdx.y;
+  if (i < n && j < n) R[j * n + i] = i <= j ? QR[j * ldq + i] : T(0);
 }
 
 template <class T>
@@ -71,25 +79,48 @@ __global__ void __launch_bounds__(64) gk_values_kernel(const T* __restrict__ d, 
 
 // S (device, compact, min(m, n) entries) <- singular values of A in non-increasing order. A: device view, any strides.
 template <class T>
-void singular_values(cudaStream_t st, View<const T> A, T* S) {
+void singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_threshold) {
   View<const T> M = A.ncols > A.nrows ? A.t() : A;
   const i64 m = M.nrows, n = M.ncols;
   if (n == 0) return;
   FB_ASSERT(n < 65536 && m < (1ll << 31), "singular_values: dimension too large for the copy launch");
   T* W = (T*)ws_alloc((size_t)m * (size_t)n * sizeof(T));
-  {
+  auto copy_in = [&]() {
     dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
     copy_to_colmajor_kernel<T><<<grid, 256, 0, st>>>(W, m, M.ptr, M.rs, M.cs, m, n);
     FB_CUDA_CHECK(cudaGetLastError());
     note_launch();
+  };
+  copy_in();
+  // Tall inputs: the singular values of A are those of R (svd/mod.rs:594-633): one QR (GEMM-rich) and then an n x n
+  // bidiagonalization instead of an m x n one (every column step of which streams the whole trailing matrix).
+  // A rank-deficient input is reported by the QR driver; then the copy is restored and bidiagonalised directly.
+  i64 mb = m;  // rows of the matrix that is bidiagonalised
+  T* R = nullptr;
+  if ((double)m / (double)n > qr_ratio_threshold && n > 1) {
+    const i64 bs = qr_recommended_block_size(m, n);
+    T* Hq = (T*)ws_alloc((size_t)bs * (size_t)n * sizeof(T));
+    const i64 rank = qr_in_place<T>(st, View<T>{W, m, n, 1, m}, View<T>{Hq, bs, n, 1, bs});
+    ws_free(Hq);
+    if (rank == n) {
+      R = (T*)ws_alloc((size_t)n * (size_t)n * sizeof(T));
+      dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+      copy_upper_kernel<T><<<grid, 256, 0, st>>>(R, n, W, m);
+      FB_CUDA_CHECK(cudaGetLastError());
+      note_launch();
+      mb = n;
+    } else {
+      copy_in();
+    }
   }
+  T* Bm = R ? R : W;
   // one-row Householder factors: only the taus are produced, no T blocks (bidiag.cu skips them for a single row)
   T* h = (T*)ws_alloc((size_t)(2 * n + 2) * sizeof(T));
   View<T> Hl{h, 1, n, 1, 1}, Hr{h + n, 1, n - 1, 1, 1};
-  bidiag_in_place<T>(st, View<T>{W, m, n, 1, m}, Hl, Hr);
+  bidiag_in_place<T>(st, View<T>{Bm, mb, n, 1, mb}, Hl, Hr);
   T* de = (T*)ws_alloc((size_t)(2 * n + 2) * sizeof(T));
   T *d = de, *e = de + n, *bb = de + 2 * n;
-  extract_bidiag_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, m, (int)n, d, e);
+  extract_bidiag_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bm, mb, (int)n, d, e);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
   gk_bound_kernel<T><<<1, 256, 0, st>>>(d, e, (int)n, bb);
@@ -101,10 +132,11 @@ void singular_values(cudaStream_t st, View<const T> A, T* S) {
   FB_CUDA_CHECK(cudaStreamSynchronize(st));
   ws_free(de);
   ws_free(h);
+  if (R) ws_free(R);
   ws_free(W);
 }
 
-template void singular_values<double>(cudaStream_t, View<const double>, double*);
-template void singular_values<float>(cudaStream_t, View<const float>, float*);
+template void singular_values<double>(cudaStream_t, View<const double>, double*, double);
+template void singular_values<float>(cudaStream_t, View<const float>, float*, double);
 
 }  // namespace fb

@@ -58,8 +58,9 @@ template <class T>
 void self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S);
 // ---- svd.cu ----
 // S (device, compact, min(m, n) entries) <- the singular values of A, non-increasing (svd/mod.rs:530-648 with u = v = None)
+// qr_ratio_threshold: SvdParams::qr_ratio_threshold (11/6): taller inputs go through QR first
 template <class T>
-void singular_values(cudaStream_t st, View<const T> A, T* S);
+void singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_threshold);
 // ---- tridiag.cu ----
 // A = Q T Q^H, self-adjoint A (lower triangle), column-major. Reference: evd/tridiag.rs:274-529. H: b x (n-1).
 template <class T>

@@ -28,6 +28,10 @@ def test_singular_values_vs_lapack(fb, cuda_dev, dtype):
     s = la.singular_values(np.asfortranarray(B)); ref = np.linalg.svd(B.astype(np.float64), compute_uv=False)
     assert np.abs(s - ref).max() <= 64 * 200 * u * ref.max()
     assert fb.solvers.singular_values(np.asfortranarray(B)).shape == (120,)
+    # tall and rank-deficient: the QR-first path (nrows / ncols > 11/6) reports the deficiency and the driver falls back
+    B = rng.standard_normal((300, 5)).astype(dtype) @ rng.standard_normal((5, 100)).astype(dtype)
+    s = la.singular_values(np.asfortranarray(B)); ref = np.linalg.svd(B.astype(np.float64), compute_uv=False)
+    assert np.abs(s - ref).max() <= 64 * 300 * u * ref.max()
 
 
 def test_singular_values_n8192_device(fb, cuda_dev):
