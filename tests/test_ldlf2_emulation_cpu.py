@@ -92,3 +92,57 @@ def test_zero_pivot_regularisation_and_offsets(emu, oracle):
     want = A.copy(order="F"); ro = oracle.ldlt(want, delta=1e-2, eps=1e-9, signs=sg)
     got = A.copy(order="F"); assert emu(got, 1e-2, 1e-9, signs=sg) == ro == (-1, 2)
     assert np.array_equal(np.tril(got), np.tril(want))
+
+
+def test_recursive_driver_model(emu, oracle):
+    """ldlt_rec (csrc/ldlt_f64.cu) restated step by step on the host: same split rule (a multiple of the 128-wide leaf
+    closest to n / 2), leaf = the kernel transcription, unit-lower solve of the panel against A11 whose diagonal already
+    holds D, W <- X and A21 <- X * recip(D) column by column, A22(lower) -= A21 W^T, recursion on A22 with the global column
+    offset. Checks the driver's algebra (not its CUDA calls) against the oracle and the reconstruction."""
+    rng = np.random.default_rng(84)
+    u = np.finfo(np.float64).eps
+    NB = 128
+
+    def rec(A, j0, info):
+        n = A.shape[0]
+        if n <= NB:
+            if info[0] >= 0:
+                return
+            blk = np.asfortranarray(A.copy())
+            f, c = emu(blk, j0=j0)
+            A[...] = blk
+            if f >= 0:
+                info[0] = f
+            info[1] += c
+            return
+        n1 = ((n // 2 + NB - 1) // NB) * NB
+        if n1 >= n:
+            n1 = ((n - 1) // NB) * NB
+        A11, A21, A22 = A[:n1, :n1], A[n1:, :n1], A[n1:, n1:]
+        rec(A11, j0, info)
+        oracle.solve_triangular(A11, A21.T, lower=True, unit=True)          # X^T = L11^-1 A21^T
+        W = np.asfortranarray(A21.copy())
+        with np.errstate(all="ignore"):                                        # after a zero pivot the GPU driver also runs on
+            A21 *= (1.0 / np.diagonal(A11))[None, :]
+        oracle.matmul_triangular(A22, 1, True, A21, 0, W.T, 0, -1.0)        # dst structure 1 = TriangularLower
+        rec(A22, j0 + n1, info)
+
+    for n in [129, 200, 256, 257, 400, 700, 1000]:
+        A = _indefinite(rng, n)
+        got = A.copy(order="F")
+        info = [-1, 0]
+        rec(got, 0, info)
+        assert info == [-1, 0], n
+        assert np.array_equal(np.triu(got, 1), np.triu(A, 1)), n
+        L = np.tril(got, -1) + np.eye(n); D = np.diagonal(got)
+        assert np.abs(L @ np.diag(D) @ L.T - A).max() <= 64 * n * u * np.abs(A).max(), n
+        want = A.copy(order="F"); assert oracle.ldlt(want) == (-1, 0)
+        assert np.allclose(np.tril(got), np.tril(want), rtol=1e-9, atol=1e-11), n
+    # failure inside the second leaf: global index through j0
+    n = 300
+    A = _indefinite(rng, n)
+    A[140, :] = 0.0; A[:, 140] = 0.0                                        # column 140 decoupled, zero pivot
+    got = A.copy(order="F"); info = [-1, 0]
+    rec(got, 0, info)
+    assert info[0] == 140
+    assert oracle.ldlt(A.copy(order="F"))[0] == 140
