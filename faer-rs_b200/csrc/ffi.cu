@@ -814,6 +814,105 @@ FB_EVD_FFI(f64, double)
 FB_EVD_FFI(f32, float)
 #undef FB_EVD_FFI
 
+// ---- reconstruct / inverse on the factors (reconstruct.cu; f64, qr_reconstruct also f32) ----
+FaerV0_24_Layout libfaer_v0_23_llt_reconstruct_scratch_f64(size_t dim, FaerV0_24_Par par) {
+  (void)dim; (void)par;
+  return FaerV0_24_Layout{0, 1};  // StackReq::EMPTY (llt/reconstruct.rs:3-6)
+}
+void libfaer_v0_23_llt_reconstruct_f64(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
+  (void)par; (void)mem;
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  Mat a(A, true, st);  // only the lower triangle is written: the rest of A must survive the round trip
+  Mat l(L, st);
+  llt_reconstruct_f64(st, a.s.view<double>(), l.s.view<const double>());
+  finish_all(st, {&a.s, &l.s});
+}
+FaerV0_24_Layout libfaer_v0_23_llt_inverse_scratch_f64(size_t dim, FaerV0_24_Par par) {
+  (void)par;
+  return FaerV0_24_Layout{dim * dim * sizeof(double), 64};  // temp_mat_scratch(dim, dim) (llt/inverse.rs:3-8)
+}
+void libfaer_v0_23_llt_inverse_f64(FaerV0_24_MatMut A_inv, FaerV0_24_MatRef L, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
+  (void)par; (void)mem;
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  Mat a(A_inv, true, st);
+  Mat l(L, st);
+  llt_inverse_f64(st, a.s.view<double>(), l.s.view<const double>());
+  finish_all(st, {&a.s, &l.s});
+}
+static void lu_recon_entry(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_SliceRef perm, int idx_bytes,
+                           bool inverse) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t m = L.nrows;
+  std::vector<long long> p = read_perm(perm.ptr, m, idx_bytes);
+  for (size_t i = 0; i < m; ++i) FB_ASSERT(p[i] >= 0 && (size_t)p[i] < m, "invalid permutation entry");
+  Mat a(A, false, st);
+  Mat l(L, st), u(U, st);
+  if (inverse) lu_inverse_f64(st, a.s.view<double>(), l.s.view<const double>(), u.s.view<const double>(), p.data());
+  else lu_reconstruct_f64(st, a.s.view<double>(), l.s.view<const double>(), u.s.view<const double>(), p.data());
+  finish_all(st, {&a.s, &l.s, &u.s});
+}
+#define FB_LU_RECON_FFI(IT, BYTES)                                                                                     \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_reconstruct_scratch_##IT##_f64(size_t nrows, size_t ncols, FaerV0_24_Par par) { \
+    (void)par;                                                                                                         \
+    return FaerV0_24_Layout{nrows * ncols * sizeof(double), 64};                                                       \
+  }                                                                                                                    \
+  void libfaer_v0_23_partial_piv_lu_reconstruct_##IT##_f64(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_MatRef U, \
+                                                           FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,   \
+                                                           FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                \
+    (void)perm_fwd; (void)par; (void)mem;                                                                              \
+    lu_recon_entry(A, L, U, perm_bwd, BYTES, false);                                                                   \
+  }                                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_inverse_scratch_##IT##_f64(size_t dim, FaerV0_24_Par par) {            \
+    (void)par;                                                                                                         \
+    return FaerV0_24_Layout{dim * dim * sizeof(double), 64};                                                           \
+  }                                                                                                                    \
+  void libfaer_v0_23_partial_piv_lu_inverse_##IT##_f64(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_MatRef U,     \
+                                                       FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,       \
+                                                       FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                    \
+    (void)perm_bwd; (void)par; (void)mem;                                                                              \
+    lu_recon_entry(A, L, U, perm_fwd, BYTES, true);                                                                    \
+  }
+FB_LU_RECON_FFI(u32, 4)
+FB_LU_RECON_FFI(u64, 8)
+#undef FB_LU_RECON_FFI
+#define FB_QR_RECON_FFI(SUF, T)                                                                                        \
+  FaerV0_24_Layout libfaer_v0_23_qr_reconstruct_scratch_##SUF(size_t nrows, size_t ncols, size_t block_size, FaerV0_24_Par par) { \
+    (void)nrows; (void)par;                                                                                            \
+    return FaerV0_24_Layout{block_size * ncols * sizeof(T), 64};                                                       \
+  }                                                                                                                    \
+  void libfaer_v0_23_qr_reconstruct_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff,      \
+                                          FaerV0_24_MatRef R, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {             \
+    (void)par; (void)mem;                                                                                              \
+    FB_ENTRY();                                                                                                        \
+    cudaStream_t st = current_stream();                                                                                \
+    StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), false, true, st);  \
+    StagedMat b(Q_basis.ptr, (i64)Q_basis.nrows, (i64)Q_basis.ncols, (i64)Q_basis.row_stride, (i64)Q_basis.col_stride, sizeof(T), true, false, st); \
+    StagedMat f(Q_coeff.ptr, (i64)Q_coeff.nrows, (i64)Q_coeff.ncols, (i64)Q_coeff.row_stride, (i64)Q_coeff.col_stride, sizeof(T), true, false, st); \
+    StagedMat r(R.ptr, (i64)R.nrows, (i64)R.ncols, (i64)R.row_stride, (i64)R.col_stride, sizeof(T), true, false, st);  \
+    qr_reconstruct<T>(st, a.view<T>(), b.view<const T>(), f.view<const T>(), r.view<const T>());                       \
+    finish_all(st, {&a, &b, &f, &r});                                                                                  \
+  }
+FB_QR_RECON_FFI(f64, double)
+FB_QR_RECON_FFI(f32, float)
+#undef FB_QR_RECON_FFI
+FaerV0_24_Layout libfaer_v0_23_qr_inverse_scratch_f64(size_t dim, size_t block_size, FaerV0_24_Par par) {
+  (void)par;
+  return FaerV0_24_Layout{block_size * dim * sizeof(double), 64};
+}
+void libfaer_v0_23_qr_inverse_f64(FaerV0_24_MatMut A, FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff, FaerV0_24_MatRef R,
+                                  FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {
+  (void)par; (void)mem;
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  Mat a(A, false, st);
+  Mat b(Q_basis, st), f(Q_coeff, st), r(R, st);
+  qr_inverse_f64(st, a.s.view<double>(), b.s.view<const double>(), f.s.view<const double>(), r.s.view<const double>());
+  finish_all(st, {&a.s, &b.s, &f.s, &r.s});
+}
+
 // ---- global par / alloc ----
 FaerV0_24_Par libfaer_v0_23_get_global_par(void) {
   FaerV0_24_Par p;

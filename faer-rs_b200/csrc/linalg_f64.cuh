@@ -29,6 +29,13 @@ struct LltResult {
 // `reg_delta`/`reg_eps`: dynamic regularisation (active iff both > 0), reference llt/factor.rs:85-87.
 LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, LltParams params);
 
+// reconstruct.cu: `*_reconstruct` / `*_inverse` on the factors (f64); perm arrays are HOST int64
+void llt_reconstruct_f64(cudaStream_t st, VD out, VCD L);
+void llt_inverse_f64(cudaStream_t st, VD out, VCD L);
+void lu_reconstruct_f64(cudaStream_t st, VD out, VCD L, VCD U, const long long* perm_bwd_host);
+void lu_inverse_f64(cudaStream_t st, VD out, VCD L, VCD U, const long long* perm_fwd_host);
+void qr_inverse_f64(cudaStream_t st, VD out, VCD Q_basis, VCD Q_coeff, VCD R);
+
 // LDLT without pivoting (ldlt_f64.cu; reference cholesky/ldlt/factor.rs:725-767): D on the diagonal, unit-lower L strictly
 // below it, strict upper triangle untouched. d_signs: device int8[n] of expected pivot signs, or null.
 struct LdltResult {

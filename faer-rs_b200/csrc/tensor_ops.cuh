@@ -51,6 +51,10 @@ i64 qr_recommended_block_size(i64 nrows, i64 ncols);
 // A = U B V^H, m >= n, column-major A. Reference: svd/bidiag.rs:47-256. Hl: bl x n, Hr: br x (n-1) (T blocks).
 template <class T>
 void bidiag_in_place(cudaStream_t st, View<T> A, View<T> Hl, View<T> Hr);
+// ---- reconstruct.cu ----
+// out = Q [R; 0]  (qr/no_pivoting/reconstruct.rs:13-39)
+template <class T>
+void qr_reconstruct(cudaStream_t st, View<T> out, View<const T> Q_basis, View<const T> Q_coeff, View<const T> R);
 // ---- evd.cu ----
 // S (device, compact, n entries) <- eigenvalues (nondecreasing) of the self-adjoint matrix whose lower triangle is in A
 // (evd/mod.rs:270-353 with u = None)
