@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Safety net for the GPU box: a GPU test that hangs (a kernel that never returns blocks inside C code, where a signal
+    cannot interrupt it) is ended by pytest-timeout's thread method instead of holding the box until the driver's limit.
+    The validated GPU suite takes about a minute in total; 900 s per test is far above any legitimate run."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(900, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """CPU oracle (test infrastructure; builds oracle/liboracle.so on first use)."""
