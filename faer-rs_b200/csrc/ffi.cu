@@ -73,7 +73,7 @@ FaerV0_24_QrStatus qr_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Q) {
   FaerV0_24_QrStatus out;
   memset(&out, 0, sizeof(out));
   if (rank < 0) {
-    out.tag = FaerV0_24_QrStatus_Unknown;  // rank-deficient input: not handled by the GPU path yet (see qr.cu)
+    out.tag = FaerV0_24_QrStatus_Unknown;
   } else {
     out.tag = FaerV0_24_QrStatus_Ok;
     out.ok.rank = (size_t)rank;

@@ -21,9 +21,18 @@
 //   * the sub-panel's T block and the block's full T are tall-skinny V^H V products (split-K DMMA / 3xTF32 GEMM);
 //   * reflector blocks are applied to the rest of the block and to the trailing matrix with the block-Householder
 //     GEMM composition (householder.cu).
-// Rank deficiency: the reference skips columns whose norm falls below eps*16*(m-row)*norm and compacts the reflectors
-// (factor.rs:52-83). The GPU path DETECTS that event (same test) and reports it (QrStatus::Unknown) instead of
-// continuing — full-rank inputs (row == col throughout) are handled completely.
+// Rank deficiency: the reference skips columns whose norm falls below eps*16*(m-row)*norm, keeps `row` where it is and
+// writes later reflectors out of place into column `row` (factor.rs:40-83), so the reflectors stay compacted in the
+// first `rank` columns and R becomes a staircase. Two drivers produce exactly that:
+//   * the fast driver assumes row == col (full rank so far). Its panel kernel runs the same rank test and only REPORTS
+//     the first failing column; the driver checks that flag once per block of `block_size` columns, before the block's
+//     reflector is applied to the trailing matrix. The block's columns are saved before they are touched, so on a report
+//     they are restored and
+//   * the general driver (`qr_general_from`) takes over from (row, col) = the start of that block: sub-panels of <= 16
+//     columns through `qr_panel_general_kernel` (separate pivot row and column counters, reflectors written to their own
+//     shared-memory columns and stored in column `row` of A, the zero fill of factor.rs:46-48), one host read-back of
+//     the number of reflectors per sub-panel, T blocks indexed by reflector (= row) number as in factor.rs:184-239.
+//   Q_coeff's columns >= rank are zero-filled with +inf on the block diagonals (factor.rs:287-299).
 #include <algorithm>
 #include <limits>
 #include <vector>
@@ -244,6 +253,191 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(T* __restrict__ A,
   }
 }
 
+// ---- general (column-skipping) sub-panel: reference qr_in_place_unblocked (factor.rs:11-86) with row != col ----------
+constexpr int QRG_PW = 16;        // panel columns per launch
+constexpr int QRG_THREADS = 512;  // 16 warps: lane = panel column (lanes >= w idle), warp = row group
+constexpr int QRG_NV = QRG_PW + 4;  // published per CTA and column: dots[16], sml, big, above, (pad)
+
+// A: at (row0, col0) — local row 0 is the first pivot row, panel column 0 is global column col0 = row0 + d0.
+// Vout: at (row0, row0) — reflector l (pivot row row0 + l) is stored in column l of Vout, rows > l.
+// max_refl: reflectors this launch may produce (<= w). taus[l * tau_stride]: tau of reflector l.
+// info[0] <- number of reflectors produced (`new_row - row`).
+template <class T>
+__global__ void __launch_bounds__(QRG_THREADS) qr_panel_general_kernel(T* __restrict__ A, T* __restrict__ Vout, i64 rs, i64 cs,
+                                                                        int mp, int w, int d0, int max_refl, int rows_per_cta,
+                                                                        T* __restrict__ taus, i64 tau_stride, QrScratch<T> sc,
+                                                                        const T* __restrict__ above2, int* __restrict__ info) {
+  extern __shared__ unsigned char qr_smem_raw[];
+  T* S = reinterpret_cast<T*>(qr_smem_raw);  // [rows_per_cta][LD]: columns 0..w-1 = panel, w..2w-1 = reflectors
+  const int LD = (2 * w) | 1;
+  constexpr int NWARP = QRG_THREADS / 32;
+  __shared__ T red[NWARP][QRG_NV];
+  __shared__ T tot[QRG_NV];
+  __shared__ T rowj[QRG_PW];
+  __shared__ T kc[QRG_PW];
+
+  const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
+  const int G = gridDim.x, bid = blockIdx.x;
+  const int r0 = bid * rows_per_cta;
+  const int nloc = max(0, min(rows_per_cta, mp - r0));
+
+  const T min_pos = TLim<T>::min_pos();
+  const T sml = t_sqrt(min_pos), big = t_sqrt(T(1) / min_pos);
+  const T eps = TLim<T>::eps();
+
+  for (int r = tid; r < nloc; r += QRG_THREADS) {
+    const T* src = A + (i64)(r0 + r) * rs;
+    T* dst = S + r * LD;
+    for (int c = 0; c < w; ++c) dst[c] = src[(i64)c * cs];
+    for (int c = 0; c < w; ++c) dst[w + c] = T(0);
+  }
+  __syncthreads();
+
+  unsigned long long nbar = 0;
+  int lr = 0, jend = 0;  // pivot row (local), first unprocessed panel column
+  for (int j = 0; j < w && lr < max_refl; ++j) {
+    jend = j + 1;
+    const int par = j & 1;
+    // ---- phase A: partial dots of the tail (rows > lr) of column j with columns c >= j, partial norms ----
+    T acc = T(0), a_sml = T(0), a_big = T(0), a_above = T(0);
+    for (int r = rg; r < nloc; r += NWARP) {
+      const int il = r0 + r;
+      const T x = S[r * LD + j];
+      if (il > lr) {
+        if (lane >= j && lane < w) acc = fma(x, S[r * LD + lane], acc);
+        if (lane == j) {
+          const T xs = x * sml, xb = x * big;
+          a_sml = fma(xs, xs, a_sml);
+          a_big = fma(xb, xb, a_big);
+        }
+      } else if (il < lr && lane == j) {
+        a_above = fma(x, x, a_above);
+      }
+    }
+    if (lane < QRG_PW) red[rg][lane] = acc;
+    if (lane == j) {
+      red[rg][QRG_PW + 0] = a_sml;
+      red[rg][QRG_PW + 1] = a_big;
+      red[rg][QRG_PW + 2] = a_above;
+    }
+    __syncthreads();
+    if (tid < QRG_NV - 1) {
+      T s = T(0);
+#pragma unroll
+      for (int q = 0; q < NWARP; ++q) s += red[q][tid];
+      sc.part[((i64)par * G + bid) * QRG_NV + tid] = s;
+    }
+    if (lr >= r0 && lr < r0 + nloc) {
+      if (tid < w) sc.rowv[par * QR_PW + tid] = S[(lr - r0) * LD + tid];
+    }
+    ++nbar;
+    qr_grid_barrier(sc.bar, nbar * (unsigned long long)G);
+
+    // ---- phase B: fixed-order reduction over the CTAs, identical in every CTA ----
+    for (int v = rg; v < QRG_NV - 1; v += NWARP) {
+      T s = T(0);
+      for (int b = lane; b < G; b += 32) s += t_ldcg(&sc.part[((i64)par * G + b) * QRG_NV + v]);
+      s = warp_sum(s);
+      if (lane == 0) tot[v] = s;
+    }
+    if (rg == NWARP - 1 && lane < w) rowj[lane] = t_ldcg(&sc.rowv[par * QR_PW + lane]);
+    __syncthreads();
+    const T acc_med = tot[j], acc_sml = tot[QRG_PW + 0], acc_big = tot[QRG_PW + 1];
+    const T tail_norm = norm_from_acc(acc_sml, acc_med, acc_big, sml, big);
+    T head = rowj[j];
+    T head_norm = t_abs(head);
+    if (head_norm < min_pos) {
+      head = T(0);
+      head_norm = T(0);
+    }
+    T tau, inv = T(0), norm, new_head = head;
+    const bool no_tail = tail_norm < min_pos;
+    if (no_tail) {
+      tau = TLim<T>::inf();
+      norm = head_norm;
+    } else {
+      norm = t_hypot(head_norm, tail_norm);
+      const T sign = head_norm != T(0) ? head * (T(1) / head_norm) : T(1);
+      const T signed_norm = sign * norm;
+      inv = T(1) / (head + signed_norm);
+      new_head = -signed_norm;
+      const T tt = tail_norm * t_abs(inv);
+      tau = T(0.5) * (T(1) + tt * tt);
+    }
+    // rank test (factor.rs:52-83)
+    const T norm_above = t_sqrt(above2[j] + tot[QRG_PW + 2]);
+    const T total = t_hypot(norm, norm_above);
+    const T threshold = eps * T((double)(mp - lr) * 16.0) * total;
+    const T tau_inv = T(1) / tau;
+    bool apply = false, advance = false;
+    if (tau_inv < min_pos) {
+      advance = norm > T(0);
+    } else if (norm > threshold) {
+      apply = true;
+      advance = true;
+    }
+    if (bid == 0 && tid == 0) taus[(i64)lr * tau_stride] = tau;
+    if (tid < w) {
+      const T dot = rowj[tid] + inv * tot[tid];  // head_c + v^H a_c
+      kc[tid] = (apply && tid > j) ? -(dot * tau_inv) : T(0);
+    }
+    __syncthreads();
+    // ---- phase C: head, zero fill, reflector, update of the remaining panel columns ----
+    const int gap = d0 + j - lr;  // col - row
+    if (lr >= r0 && lr < r0 + nloc && rg == ((lr - r0) & (NWARP - 1))) {
+      T* row = S + (lr - r0) * LD;
+      if (lane == j) row[j] = no_tail ? head : new_head;
+      if (lane > j && lane < w) row[lane] += kc[lane];
+    }
+    for (int r = rg; r < nloc; r += NWARP) {
+      const int il = r0 + r;
+      if (il > lr) {
+        const T x = S[r * LD + j];
+        const T vi = no_tail ? T(0) : x * inv;
+        __syncwarp();
+        if (lane == j) {
+          S[r * LD + w + lr] = vi;                // reflector lr (overwrites a skipped attempt at the same pivot row)
+          if (il <= lr + gap) S[r * LD + j] = T(0);  // factor.rs:46-48
+        } else if (lane > j && lane < w) {
+          S[r * LD + lane] = fma(kc[lane], vi, S[r * LD + lane]);
+        }
+      }
+    }
+    if (advance) ++lr;
+    __syncthreads();
+  }
+  if (bid == 0 && tid == 0) info[0] = lr;
+  const int local = lr;
+  for (int r = tid; r < nloc; r += QRG_THREADS) {
+    const int il = r0 + r;
+    T* dstg = A + (i64)il * rs;
+    const T* srcs = S + r * LD;
+    for (int c = 0; c < w; ++c)
+      if (c >= jend || il <= d0 + c) dstg[(i64)c * cs] = srcs[c];
+    T* dstv = Vout + (i64)il * rs;
+    for (int l = 0; l < local; ++l)
+      if (il > l) dstv[(i64)l * cs] = srcs[w + l];
+  }
+}
+
+// Q_coeff columns >= rank: zero, +inf on the diagonal of their T block (factor.rs:287-299)
+template <class T>
+__global__ void qr_coeff_fixup_kernel(T* __restrict__ H, i64 rs, i64 cs, int bs, i64 rank, i64 size) {
+  const i64 c = rank + blockIdx.x;
+  if (c >= size) return;
+  for (int i = threadIdx.x; i < bs; i += blockDim.x) H[(i64)i * rs + c * cs] = (i == (int)(c % bs)) ? TLim<T>::inf() : T(0);
+}
+
+// dst (compact column-major, ld = nrows) <-> src view
+template <class T>
+__global__ void qr_save_kernel(T* __restrict__ buf, T* __restrict__ A, i64 rs, i64 cs, i64 nrows, bool restore) {
+  const i64 c = blockIdx.y;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (i64)gridDim.x * blockDim.x) {
+    if (restore) A[i * rs + c * cs] = buf[c * nrows + i];
+    else buf[c * nrows + i] = A[i * rs + c * cs];
+  }
+}
+
 // above2[c] = sum_{i < nrows} A[i, c]^2 for c < w  (one CTA per column; only feeds the rank test)
 template <class T>
 __global__ void __launch_bounds__(256) col_sumsq_kernel(const T* __restrict__ A, i64 rs, i64 cs, i64 nrows, T* out) {
@@ -414,6 +608,89 @@ static i64 qr_in_place_lookahead(cudaStream_t st, View<T> A, View<T> H, cudaStre
   return h_flag ? -1 : size;
 }
 
+// General driver: continues the factorization from the state (row, col) with the reference's column-skipping logic
+// (factor.rs:137-256 on sub-panels of <= QRG_PW columns; every sub-panel's reflector is applied to all the columns to its
+// right at once). `row` must be a multiple of the block size. Synchronous: one read-back per sub-panel. Returns the rank.
+template <class T>
+static i64 qr_general_from(cudaStream_t st, View<T> A, View<T> H, i64 row, i64 col, QrScratch<T> sc, T* above2, int* d_info,
+                           T* apply_tmp, int Gmax) {
+  const i64 m = A.nrows, n = A.ncols, size = std::min(m, n), bs = H.nrows;
+  static bool configured = false;
+  if (!configured) {
+    FB_CUDA_CHECK(cudaFuncSetAttribute(qr_panel_general_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  while (row < size && col < n) {
+    const i64 start = row;
+    i64 offset = 0, pieces = 0;
+    const i64 blk = std::min(bs, std::min(size - row, n - col));
+    while (offset < blk && col < n) {
+      const i64 w = std::min<i64>(QRG_PW, std::min(blk - offset, n - col));
+      const i64 mp = m - row;
+      if (row > 0) {
+        col_sumsq_kernel<T><<<(unsigned)w, 256, 0, st>>>(A.at(0, col), A.rs, A.cs, row, above2);
+        FB_CUDA_CHECK(cudaGetLastError());
+        note_launch();
+      } else {
+        FB_CUDA_CHECK(cudaMemsetAsync(above2, 0, QR_PW * sizeof(T), st));
+      }
+      int G = (int)std::min<i64>(Gmax, (mp + 63) / 64);
+      if (G < 1) G = 1;
+      int rows_per_cta = (int)((mp + G - 1) / G);
+      const size_t smem = (size_t)rows_per_cta * (size_t)((2 * (int)w) | 1) * sizeof(T);
+      FB_ASSERT(smem <= 200 * 1024, "QR panel too tall for the shared-memory slices");
+      FB_CUDA_CHECK(cudaMemsetAsync(sc.bar, 0, 8, st));
+      T* Ap = A.at(row, col);
+      T* Vp = A.at(row, row);
+      i64 rs = A.rs, cs = A.cs;
+      int mpi = (int)mp, wi = (int)w, d0 = (int)(col - row), max_refl = (int)std::min<i64>(w, size - row);
+      T* taus = H.at(offset, row);
+      i64 tau_stride = H.rs + H.cs;
+      const T* ab = above2;
+      void* args[] = {&Ap, &Vp, &rs, &cs, &mpi, &wi, &d0, &max_refl, &rows_per_cta, &taus, &tau_stride, &sc, &ab, &d_info};
+      FB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)qr_panel_general_kernel<T>, dim3(G), dim3(QRG_THREADS), args, smem, st));
+      note_launch();
+      int local_i = 0;
+      FB_CUDA_CHECK(cudaMemcpyAsync(&local_i, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+      FB_CUDA_CHECK(cudaStreamSynchronize(st));
+      const i64 local = local_i;
+      FB_ASSERT(local >= 0 && local <= w, "QR panel returned an impossible reflector count");
+      if (local > 0) {
+        View<const T> Vs = cview(A.sub(row, row, mp, local));
+        View<T> Tss = H.sub(offset, row, local, local);
+        householder_build_t<T>(st, Vs, Tss);
+        const i64 rest = n - (col + w);
+        if (rest > 0) apply_block_householder_on_the_left<T>(st, Vs, cview(Tss), A.sub(row, col + w, mp, rest), true, apply_tmp);
+        ++pieces;
+      }
+      offset += local;
+      row += local;
+      col += w;
+    }
+    // full T of the block of reflectors [start, start + offset)
+    if (pieces > 1) householder_build_t<T>(st, cview(A.sub(start, start, m - start, offset)), H.sub(0, start, offset, offset));
+  }
+  return row;
+}
+
+template <class T>
+static void qr_coeff_fixup(cudaStream_t st, View<T> H, i64 rank) {
+  const i64 size = H.ncols;
+  if (rank >= size) return;
+  qr_coeff_fixup_kernel<T><<<(unsigned)(size - rank), 64, 0, st>>>(H.ptr, H.rs, H.cs, (int)H.nrows, rank, size);
+  FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+}
+
+template <class T>
+static void qr_save_block(cudaStream_t st, T* buf, View<T> blk, bool restore) {
+  if (blk.nrows == 0 || blk.ncols == 0) return;
+  dim3 grid((unsigned)std::min<i64>((blk.nrows + 255) / 256, 1024), (unsigned)blk.ncols);
+  qr_save_kernel<T><<<grid, 256, 0, st>>>(buf, blk.ptr, blk.rs, blk.cs, blk.nrows, restore);
+  FB_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+}
+
 template <class T>
 i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
   const i64 m = A.nrows, n = A.ncols, size = std::min(m, n), bs = H.nrows;
@@ -431,7 +708,11 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
       if (partition_streams(sms, &sp, &su, &sm, &got) && got > 0) {
         const i64 g0 = std::min<i64>(std::min(got, 160), (m + 63) / 64);
         const i64 rows0 = (m + g0 - 1) / g0;  // the first sub-panel is the tallest
-        if (rows0 * (i64)(QR_PW | 1) * (i64)sizeof(T) <= 200 * 1024) return qr_in_place_lookahead<T>(st, A, H, sp, su, sm, got);
+        if (rows0 * (i64)(QR_PW | 1) * (i64)sizeof(T) <= 200 * 1024) {
+          const i64 r = qr_in_place_lookahead<T>(st, A, H, sp, su, sm, got);
+          if (r >= 0) return r;
+          FB_ASSERT(false, "look-ahead QR driver met a rank-deficient column (use the default driver)");
+        }
       }
     }
   }
@@ -459,9 +740,14 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
   // one W = V^H M buffer for every block-reflector application of this factorization (no per-apply pool round trip and
   // no host synchronisation inside the column loop)
   T* apply_tmp = (T*)ws_alloc((size_t)std::min(bs, size) * (size_t)n * sizeof(T));
+  // the current block's columns as they were before its sub-panels touched them (restart point of the general driver)
+  T* saved = (T*)ws_alloc((size_t)m * (size_t)std::min(bs, size) * sizeof(T));
+  i64 rank = size;
+  bool general = false;
 
   for (i64 j0 = 0; j0 < size; j0 += bs) {
     const i64 jb = std::min(bs, size - j0);
+    qr_save_block<T>(st, saved, A.sub(j0, j0, m - j0, jb), false);
     for (i64 s0 = 0; s0 < jb; s0 += QR_PW) {
       const i64 sw = std::min<i64>(QR_PW, jb - s0), c0 = j0 + s0;
       const i64 mp = m - c0;
@@ -498,6 +784,16 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
       if (rest > 0)
         apply_block_householder_on_the_left<T>(st, Vs, cview(Tss), A.sub(c0, c0 + sw, mp, rest), true, apply_tmp);
     }
+    // one status read per block, before the block's reflector touches the trailing matrix
+    int h_flag = 0;
+    FB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_flag) {
+      qr_save_block<T>(st, saved, A.sub(j0, j0, m - j0, jb), true);
+      rank = qr_general_from<T>(st, A, H, j0, j0, sc, above2, d_flag, apply_tmp, Gmax);
+      general = true;
+      break;
+    }
     // full T of the block (off-diagonal sub-blocks V_i^H V_j; the diagonal sub-blocks are recomputed identically)
     View<const T> Vb = cview(A.sub(j0, j0, m - j0, jb));
     View<T> Tb = H.sub(0, j0, jb, jb);
@@ -505,13 +801,13 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
     if (j0 + jb < n)
       apply_block_householder_on_the_left<T>(st, Vb, cview(Tb), A.sub(j0, j0 + jb, m - j0, n - (j0 + jb)), true, apply_tmp);
   }
-  int h_flag = 0;
-  FB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (general) qr_coeff_fixup<T>(st, H, rank);
   FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  ws_free(saved);
   ws_free(apply_tmp);
   ws_free(d_flag);
   ws_free(scb);
-  return h_flag ? -1 : size;
+  return rank;
 }
 
 template i64 qr_in_place<double>(cudaStream_t, View<double>, View<double>);

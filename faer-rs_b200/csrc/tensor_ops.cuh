@@ -41,8 +41,7 @@ void apply_block_householder_sequence_transpose_on_the_left(cudaStream_t st, Vie
 
 // ---- qr.cu ----
 // Householder QR without pivoting, reference qr/no_pivoting/factor.rs:258-301. H: block_size x min(m, n).
-// Returns the rank, or -1 if a rank-deficient column was met (full support of the reference's column-skipping logic is
-// not implemented on the GPU path yet; the caller reports QrStatus::Unknown instead of returning wrong factors).
+// Returns the rank (dependent columns are skipped and the reflectors compacted as factor.rs:40-83 does).
 template <class T>
 i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H);
 i64 qr_recommended_block_size(i64 nrows, i64 ncols);

@@ -320,7 +320,8 @@ def qr_recommended_block_size(nrows: int, ncols: int) -> int:
 
 def qr_in_place(A, Q_coeff, par=None, params=None) -> QrInfo:
     """qr::no_pivoting::factor::qr_in_place (qr/no_pivoting/factor.rs:258-301). Q_coeff: block_size x min(m, n).
-    f64 or f32. Raises RuntimeError on a rank-deficient input (not handled by the GPU path yet)."""
+    f64 or f32. Returns QrInfo(rank): dependent columns are skipped and the reflectors compacted exactly as the reference
+    does (factor.rs:40-83); Q_coeff's columns >= rank are zero with +inf on their block diagonals (287-299)."""
     lib = capi.load()
     suf = _suf(A)
     assert _suf(Q_coeff) == suf
@@ -328,7 +329,7 @@ def qr_in_place(A, Q_coeff, par=None, params=None) -> QrInfo:
     st = getattr(lib, f"libfaer_v0_23_qr_factor_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(Q_coeff),
                                                                par or capi.par_default(), capi.MemAlloc(None, 0), params)
     if st.tag != 0:
-        raise RuntimeError("QrStatus::Unknown (rank-deficient input is not supported by the B200 QR path yet)")
+        raise RuntimeError("QrStatus::Unknown")
     return QrInfo(int(st.value))
 
 
