@@ -342,6 +342,10 @@ def load() -> C.CDLL:
         f = getattr(lib, f"faer_b200_tridiag_in_place_{suf}")
         f.argtypes = [MatMut, MatMut]
         f.restype = None
+    lib.faer_b200_set_option.argtypes = [C.c_char_p, C.c_longlong]
+    lib.faer_b200_set_option.restype = C.c_int
+    lib.faer_b200_get_option.argtypes = [C.c_char_p]
+    lib.faer_b200_get_option.restype = C.c_longlong
     lib.faer_b200_version.argtypes = []
     lib.faer_b200_version.restype = C.c_char_p
     _lib = lib

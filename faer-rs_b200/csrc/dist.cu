@@ -265,6 +265,9 @@ bool partition_streams(int panel_sms, cudaStream_t* panel, cudaStream_t* urgent,
     s->sm = (cudaStream_t)sm;
     s->sms = (int)grp[0].sm.smCount;
     s->state = 1;
+    register_stream_sms(s->sp, (int)grp[0].sm.smCount);
+    register_stream_sms(s->su, (int)rem.sm.smCount);
+    register_stream_sms(s->sm, (int)rem.sm.smCount);
   }
   if (s->state != 1) return false;
   *panel = s->sp;

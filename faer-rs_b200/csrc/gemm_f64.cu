@@ -11,6 +11,8 @@
 //     that intersect the diagonal pay the extra pass), fully-masked k-ranges are skipped, triangular dst
 //     tiles above/below the diagonal exit immediately and diagonal tiles mask the store.
 #include "gemm_f64.cuh"
+#include "gemm_f64_sliced.cuh"
+#include "gemm_f64_ws.cuh"
 #include "runtime.cuh"
 
 namespace fb {
@@ -353,6 +355,29 @@ inline int transpose_struct(int s) {
   }
 }
 
+inline int ws_mode() { return (int)get_option(OPT_GEMM_WS); }
+
+// per-stream grow-only workspace of the int8-sliced path (slices of both operands + exponents)
+oz::Workspace* sliced_workspace(cudaStream_t stream) {
+  struct Slot {
+    cudaStream_t st;
+    oz::Workspace ws;
+    bool used;
+  };
+  static Slot slots[8];
+  for (auto& s : slots)
+    if (s.used && s.st == stream) return &s.ws;
+  for (auto& s : slots)
+    if (!s.used) {
+      s.used = true;
+      s.st = stream;
+      return &s.ws;
+    }
+  cudaStreamSynchronize(slots[0].st);
+  slots[0].st = stream;
+  return &slots[0].ws;
+}
+
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 // dst(struct) = [dst +] alpha * sum_z W_z  (W_z: compact column-major m x n partial products, summed in z order)
@@ -442,6 +467,32 @@ void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, i
   if (lhs_struct != RECT) flops *= 0.5;
   if (rhs_struct != RECT) flops *= 0.5;
   const bool prof = profiling_enabled();
+  // opt-in (f64_gemm_mode = 1): large unstructured products as int8-sliced tcgen05 products (gemm_f64_sliced.cuh)
+  if (get_option(OPT_F64_GEMM_MODE) == 1 && !split_ws && dst_struct == RECT && lhs_struct == RECT && rhs_struct == RECT &&
+      p.m >= 256 && p.n >= 256 && p.k >= 128 && p.k <= 32768) {
+    oz::Operand a{lhs.ptr, p.m, p.k, lhs.rs, lhs.cs};
+    oz::Operand b{rhs.ptr, p.k, p.n, rhs.rs, rhs.cs};
+    if (prof) profile_record_start(stream);
+    const bool ok = oz::gemm_f64_ozaki(stream, dst.ptr, dst.rs, dst.cs, p.m, p.n, p.k, accum, a, b, alpha, sliced_workspace(stream));
+    if (prof) profile_record_stop(stream, flops);
+    if (ok) {
+      note_launch();
+      return;
+    }
+    (void)cudaGetLastError();
+  }
+  // large rectangular-operand products: the TMA-fed warp-specialised kernel (gemm_f64_ws.cuh)
+  if (ws_mode() != 0 && !split_ws) {
+    const long long tiles_ws = (long long)((p.m + ws64::BM - 1) / ws64::BM) * ((p.n + ws64::BN - 1) / ws64::BN);
+    if ((ws_mode() == 2 || (tiles_ws >= 96 && p.k >= 32))) {
+      if (prof) profile_record_start(stream);
+      const bool took = ws64::try_gemm_f64_ws(stream, p);
+      if (took) {
+        if (prof) profile_record_stop(stream, flops);
+        return;
+      }
+    }
+  }
 #define FB_DISPATCH(ak, bnm, vec)                                   \
   if (AK == ak && BNM == bnm && VEC == vec) {                       \
     if (prof) profile_record_start(stream);                         \

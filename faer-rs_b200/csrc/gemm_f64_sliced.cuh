@@ -1,10 +1,18 @@
-// DRAFT FOR ROUND 2 — compiled by tools/next/ozaki_test.cu only, NOT part of libfaer_b200.so and not reachable from
-// the C ABI. It has been compiled for sm_100a (ptxas accepts every instruction form) but has not run on a GPU yet.
-//
 // f64 GEMM on the 5th-generation tensor cores through int8 slicing ("Ozaki scheme"): the only way to put the f64 hot
-// path on tcgen05 (there is no f64 MMA kind). Numerical model and measured error levels:
-// tools/next/ozaki_emulation.py (8 slices: at or below the error of a plain f64 GEMM relative to |A||B|; 9 slices:
-// below it everywhere).
+// path on tcgen05 (there is no f64 MMA kind). OPT-IN (`faer_b200_set_option("f64_gemm_mode", 1)` or
+// FAER_B200_F64_GEMM_MODE=1): `matmul` with rectangular operands / destination, m, n >= 256, 128 <= k <= 32768; every
+// other product, and every product in the default mode, runs on the native f64 tensor op (DMMA).
+//
+// Accuracy contract (tests/test_gpu_zz10_gemm_ws_sliced.py): with S = 8 slices every entry satisfies
+//     |C_ij - (alpha A B [+ C])_ij| <= 16 u * (|alpha| |A| |B|)_ij,   u = 2^-53,
+// independent of k (the int32 accumulation is exact; the only roundings are the 8th-slice truncation, 2^-56 relative to the
+// row / column maxima, and the f64 recombination). A plain f64 GEMM guarantees k u (|A||B|)_ij and achieves ~sqrt(k) u, so for
+// operands whose rows (of A) / columns (of B) are not graded over more than ~2^6 the sliced product is at least as accurate;
+// measured on B200: 3e-17 ... 7e-16 relative to (|A||B|)_ij, profiles/r02_sliced_gemm_bringup.log. Rows of A (columns of B)
+// with a dynamic range beyond 2^50 lose the small entries' low bits (they are scaled by the row maximum) — the contract
+// above still holds because it is relative to |A||B|, but it is a different error distribution than DMMA's; hence opt-in.
+// Measured throughput: 62 / 70 / 74 TFLOP/s f64-equivalent at n = 4096 / 8192 / 16384 (slicing passes included), against
+// 31.9 TFLOP/s for the DMMA kernel at n = 16384 and a DMMA peak of 36.9.
 //
 // Scheme. Row i of A is scaled by 2^-e_i (|x| < 1), column j of B by 2^-f_j, and every scaled value is split into S
 // signed 7-bit slices, x = A0/64 + A1/(64*128) + A2/(64*128^2) + ... (exact in f64). Then

@@ -1,6 +1,7 @@
 // Process-wide runtime state: stream, launch counter, device workspace pool, host<->device staging.
 #include "runtime.cuh"
 
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -22,6 +23,75 @@ bool g_checked_device = false;
 
 cudaStream_t current_stream() { return g_stream; }
 void set_current_stream(cudaStream_t s) { g_stream = s; }
+
+namespace {
+struct StreamSms {
+  cudaStream_t st;
+  int sms;
+};
+std::vector<StreamSms> g_stream_sms;
+int g_device_sms = 0;
+}  // namespace
+void register_stream_sms(cudaStream_t st, int sms) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (auto& e : g_stream_sms)
+    if (e.st == st) {
+      e.sms = sms;
+      return;
+    }
+  g_stream_sms.push_back(StreamSms{st, sms});
+}
+int stream_sms(cudaStream_t st) {
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (auto& e : g_stream_sms)
+      if (e.st == st) return e.sms;
+  }
+  if (g_device_sms == 0) {
+    int dev = 0;
+    FB_CUDA_CHECK(cudaGetDevice(&dev));
+    FB_CUDA_CHECK(cudaDeviceGetAttribute(&g_device_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return g_device_sms;
+}
+
+namespace {
+struct OptDef {
+  const char* name;
+  const char* env;
+  long long dflt;
+};
+const OptDef g_opt_defs[OPT_COUNT] = {{"gemm_ws", "FAER_B200_GEMM_WS", 1}, {"f64_gemm_mode", "FAER_B200_F64_GEMM_MODE", 0}};
+long long g_opt_vals[OPT_COUNT];
+bool g_opt_init = false;
+void opts_init() {
+  if (g_opt_init) return;
+  for (int i = 0; i < OPT_COUNT; ++i) {
+    const char* e = getenv(g_opt_defs[i].env);
+    g_opt_vals[i] = e ? atoll(e) : g_opt_defs[i].dflt;
+  }
+  g_opt_init = true;
+}
+}  // namespace
+long long get_option(int opt) {
+  opts_init();
+  return g_opt_vals[opt];
+}
+bool set_option_by_name(const char* name, long long value) {
+  opts_init();
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, g_opt_defs[i].name) == 0) {
+      g_opt_vals[i] = value;
+      return true;
+    }
+  return false;
+}
+long long get_option_by_name(const char* name) {
+  opts_init();
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, g_opt_defs[i].name) == 0) return g_opt_vals[i];
+  return -1;
+}
 
 std::recursive_mutex& entry_mutex() {
   static std::recursive_mutex m;

@@ -142,9 +142,10 @@ def cholesky_in_place(A_local, n: int, nb: int = 512, regularization=(0.0, 0.0),
 
 
 # ---- distributed LU -----------------------------------------------------------------------------------
-def lu_in_place(A_local, n: int, nb: int = 512, lookahead: bool = True):
+def lu_in_place(A_local, n: int, nb: int = 512, lookahead=True):
     """Distributed in-place P A = L U (square n x n). Returns (perm_fwd, perm_inv, transposition_count) as numpy int64
-    arrays (identical on every rank); (P A)[i, :] = A[perm_fwd[i], :]."""
+    arrays (identical on every rank); (P A)[i, :] = A[perm_fwd[i], :]. `lookahead`: bool, or the driver's bit mask
+    (1 = look-ahead, 2 = purely local run that ignores an existing communicator; 3 = both)."""
     import torch
     lib = capi.load()
     _bind(lib)
@@ -153,5 +154,6 @@ def lu_in_place(A_local, n: int, nb: int = 512, lookahead: bool = True):
     ld = A_local.stride(1) if A_local.shape[1] > 1 else max(n, 1)
     perm = np.zeros(n, dtype=np.int64); pinv = np.zeros(n, dtype=np.int64)
     cnt = lib.faer_b200_dist_partial_piv_lu_factor_in_place_f64(A_local.data_ptr(), ld, n, nb, perm.ctypes.data,
-                                                                pinv.ctypes.data, 1 if lookahead else 0)
+                                                                pinv.ctypes.data,
+                                                                int(lookahead) if not isinstance(lookahead, bool) else (1 if lookahead else 0))
     return perm, pinv, int(cnt)

@@ -410,6 +410,13 @@ void faer_b200_bidiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_M
  * T on A's diagonal / subdiagonal, reflectors below the subdiagonal, `householder` (b x (n-1)) holds their T blocks. */
 void faer_b200_tridiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
 void faer_b200_tridiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+/* Run-time options (initial values from the environment variable in brackets). Returns 0, or -1 for an unknown name.
+ *   "gemm_ws"        [FAER_B200_GEMM_WS]        0 never / 1 heuristic (default) / 2 always use the TMA-fed warp-specialised
+ *                                                f64 GEMM (csrc/gemm_f64_ws.cuh) where the operands qualify
+ *   "f64_gemm_mode"  [FAER_B200_F64_GEMM_MODE]  0 native f64 tensor op (default) / 1 int8-sliced tcgen05 products for large
+ *                                                unstructured matmuls (csrc/gemm_f64_sliced.cuh states the accuracy contract) */
+int faer_b200_set_option(const char *name, long long value);
+long long faer_b200_get_option(const char *name);
 /* Version string. */
 const char *faer_b200_version(void);
 
