@@ -76,10 +76,10 @@ __global__ void __launch_bounds__(64) st_values_kernel(const T* __restrict__ d, 
 
 // S (device, compact, n entries) <- eigenvalues of the self-adjoint matrix whose LOWER triangle is in A, nondecreasing.
 template <class T>
-void self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S) {
+bool self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S) {
   const i64 n = A.nrows;
   FB_ASSERT(A.ncols == n, "self_adjoint_eigenvalues: square matrix required");
-  if (n == 0) return;
+  if (n == 0) return true;
   FB_ASSERT(n < 65536, "self_adjoint_eigenvalues: dimension too large for the copy launch");
   T* W = (T*)ws_alloc((size_t)n * (size_t)n * sizeof(T));
   {
@@ -95,6 +95,7 @@ void self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S) {
   extract_tridiag_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, n, (int)n, d, e);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
+  const bool finite = device_all_finite<T>(st, d, n) && (n < 2 || device_all_finite<T>(st, e, n - 1));
   st_bounds_kernel<T><<<1, 256, 0, st>>>(d, e, (int)n, bb);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
@@ -105,9 +106,10 @@ void self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S) {
   ws_free(de);
   ws_free(h);
   ws_free(W);
+  return finite;
 }
 
-template void self_adjoint_eigenvalues<double>(cudaStream_t, View<const double>, double*);
-template void self_adjoint_eigenvalues<float>(cudaStream_t, View<const float>, float*);
+template bool self_adjoint_eigenvalues<double>(cudaStream_t, View<const double>, double*);
+template bool self_adjoint_eigenvalues<float>(cudaStream_t, View<const float>, float*);
 
 }  // namespace fb

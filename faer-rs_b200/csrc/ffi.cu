@@ -149,28 +149,38 @@ void qr_solve_entry(FaerV0_24_MatRef Qb, FaerV0_24_MatRef Qc, FaerV0_24_MatRef R
   finish_all(st, {&b, &f, &r});
   if (rr) rr->finish();
 }
-// ---- eigenvalues of a self-adjoint matrix (evd/mod.rs:270-353 with u = None) ----
+// ---- self-adjoint eigendecomposition (evd/mod.rs:270-418): eigenvalues by bisection when U is not wanted, divide and
+// conquer + Householder back-transform otherwise. Non-finite input -> EvdStatus::NoConvergence, as the reference ----
 template <class T>
 FaerV0_24_EvdStatus self_adjoint_evd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S) {
   FB_ENTRY();
   cudaStream_t st = current_stream();
   const size_t n = A.nrows;
   FB_ASSERT(A.ncols == n && S.len == n && (n == 0 || S.stride >= 1), "self_adjoint_evd: square A, S of length n, positive stride");
-  FB_ASSERT(U.ncols == 0,
-            "self_adjoint_evd: eigenvectors are not built on the GPU path yet (pass U with ncols == 0 for the values)");
+  const bool want_u = U.ncols != 0;
+  if (want_u) FB_ASSERT(U.nrows == n && U.ncols == n, "self_adjoint_evd: U must be n x n (or have no columns)");
   FaerV0_24_EvdStatus out;
   memset(&out, 0, sizeof(out));
   out.tag = FaerV0_24_EvdStatus_Ok;
   if (n == 0) return out;
   StagedMat a(A.ptr, (i64)n, (i64)n, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, false, st);
   T* s_dev = (T*)ws_alloc(n * sizeof(T));
-  self_adjoint_eigenvalues<T>(st, a.view<const T>(), s_dev);
-  FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), n, cudaMemcpyDefault, st));
-  finish_all(st, {&a});
+  bool ok;
+  if (want_u) {
+    StagedMat u(U.ptr, (i64)n, (i64)n, (i64)U.row_stride, (i64)U.col_stride, sizeof(T), false, true, st);
+    ok = self_adjoint_evd_with_vectors<T>(st, a.view<const T>(), u.view<T>(), s_dev, 1);
+    if (ok) FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), n, cudaMemcpyDefault, st));
+    finish_all(st, {&a, &u});
+  } else {
+    ok = self_adjoint_eigenvalues<T>(st, a.view<const T>(), s_dev);
+    if (ok) FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), n, cudaMemcpyDefault, st));
+    finish_all(st, {&a});
+  }
   ws_free(s_dev);
+  if (!ok) out.tag = FaerV0_24_EvdStatus_NoConvergence;
   return out;
 }
-// ---- singular values (svd/mod.rs:530-648 with u = v = None) ----
+// ---- SVD (svd/mod.rs:530-672): U.ncols == 0 / V.ncols == 0 mean "do not compute" (faer-ffi/src/lib.rs:2354-2355) ----
 template <class T>
 FaerV0_24_SvdStatus svd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V,
                               double qr_ratio_threshold) {
@@ -178,19 +188,34 @@ FaerV0_24_SvdStatus svd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_
   cudaStream_t st = current_stream();
   const size_t size = A.nrows < A.ncols ? A.nrows : A.ncols;
   FB_ASSERT(S.len == size && (size == 0 || S.stride >= 1), "svd: S must have min(nrows, ncols) entries and a positive stride");
-  FB_ASSERT(U.ncols == 0 && V.ncols == 0,
-            "svd: singular vectors are not built on the GPU path yet (pass U and V with ncols == 0 for the values)");
+  const bool want_u = U.ncols != 0, want_v = V.ncols != 0;
+  if (want_u) FB_ASSERT(U.nrows == A.nrows && (U.ncols == A.nrows || U.ncols == size), "svd: U must be nrows x {size, nrows}");
+  if (want_v) FB_ASSERT(V.nrows == A.ncols && (V.ncols == A.ncols || V.ncols == size), "svd: V must be ncols x {size, ncols}");
   FaerV0_24_SvdStatus out;
   memset(&out, 0, sizeof(out));
   out.tag = FaerV0_24_SvdStatus_Ok;
-  if (size == 0) return out;
+  const double ratio = qr_ratio_threshold > 0.0 ? qr_ratio_threshold : 11.0 / 6.0;
+  if (size == 0 && !want_u && !want_v) return out;
   StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, false, st);
-  T* s_dev = (T*)ws_alloc(size * sizeof(T));
-  singular_values<T>(st, a.view<const T>(), s_dev, qr_ratio_threshold > 0.0 ? qr_ratio_threshold : 11.0 / 6.0);
-  // strided scatter into the caller's vector (host or device)
-  FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), size, cudaMemcpyDefault, st));
-  finish_all(st, {&a});
+  T* s_dev = (T*)ws_alloc((size + 1) * sizeof(T));
+  bool ok;
+  if (want_u || want_v) {
+    StagedMat u(U.ptr, (i64)U.nrows, (i64)U.ncols, (i64)U.row_stride, (i64)U.col_stride, sizeof(T), false, true, st);
+    StagedMat v(V.ptr, (i64)V.nrows, (i64)V.ncols, (i64)V.row_stride, (i64)V.col_stride, sizeof(T), false, true, st);
+    View<T> uv = want_u ? u.view<T>() : View<T>{nullptr, 0, 0, 1, 1};
+    View<T> vv = want_v ? v.view<T>() : View<T>{nullptr, 0, 0, 1, 1};
+    ok = svd_with_vectors<T>(st, a.view<const T>(), uv, s_dev, 1, vv, ratio);
+    if (ok && size)
+      FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), size, cudaMemcpyDefault, st));
+    finish_all(st, {&a, &u, &v});
+  } else {
+    ok = singular_values<T>(st, a.view<const T>(), s_dev, ratio);
+    // strided scatter into the caller's vector (host or device)
+    if (ok) FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * sizeof(T), s_dev, sizeof(T), sizeof(T), size, cudaMemcpyDefault, st));
+    finish_all(st, {&a});
+  }
   ws_free(s_dev);
+  if (!ok) out.tag = FaerV0_24_SvdStatus_NoConvergence;
   return out;
 }
 }  // namespace
@@ -770,7 +795,7 @@ void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_f64(FaerV0_24_Mat
   lu_solve_entry(L, U, perm_bwd, rhs, 8, true);
 }
 
-// ---- SVD: singular values only for now (see svd.cu) ----
+// ---- SVD (svd.cu: values by bisection; svd_vectors.cu: with U / V) ----
 #define FB_SVD_FFI(SUF, T)                                                                                             \
   FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_##SUF(void) { return FaerV0_24_BidiagParams{192 * 256}; }          \
   FaerV0_24_SvdParams libfaer_v0_23_SvdParams_##SUF(void) {                                                            \
@@ -793,7 +818,7 @@ FB_SVD_FFI(f64, double)
 FB_SVD_FFI(f32, float)
 #undef FB_SVD_FFI
 
-// ---- self-adjoint EVD: eigenvalues only for now (see evd.cu) ----
+// ---- self-adjoint EVD (evd.cu: values by bisection; svd_vectors.cu + tridiag_dc.cu: with eigenvectors) ----
 #define FB_EVD_FFI(SUF, T)                                                                                             \
   FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_##SUF(void) { return FaerV0_24_TridiagParams{192 * 256}; }       \
   FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_##SUF(void) {                                      \

@@ -370,18 +370,19 @@ inline bool try_gemm_f64_ws(cudaStream_t stream, const GemmF64Params& q) {
   // a tile takes ~0.13 us per unit of k on half an SM: ~100 us per CTA
   p.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, 768 / std::max(q.k, 1)));
   const int grid = (int)((tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
-  auto launch = [&](auto kern) {
-    static bool configured = false;
-    if (!configured) {
+  // one opt-in to > 48 KB of dynamic shared memory per kernel variant
+  static bool configured[4] = {false, false, false, false};
+  auto launch = [&](int which, void (*kern)(CUtensorMap, CUtensorMap, Params)) {
+    if (!configured[which]) {
       FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      configured = true;
+      configured[which] = true;
     }
     kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, p);
   };
-  if (ak && bk) launch(gemm_f64_ws_kernel<true, true>);
-  else if (ak && !bk) launch(gemm_f64_ws_kernel<true, false>);
-  else if (!ak && bk) launch(gemm_f64_ws_kernel<false, true>);
-  else launch(gemm_f64_ws_kernel<false, false>);
+  if (ak && bk) launch(0, gemm_f64_ws_kernel<true, true>);
+  else if (ak && !bk) launch(1, gemm_f64_ws_kernel<true, false>);
+  else if (!ak && bk) launch(2, gemm_f64_ws_kernel<false, true>);
+  else launch(3, gemm_f64_ws_kernel<false, false>);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
   return true;

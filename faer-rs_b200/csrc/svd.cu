@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(64) gk_values_kernel(const T* __restrict__ d, 
 
 // S (device, compact, min(m, n) entries) <- singular values of A in non-increasing order. A: device view, any strides.
 template <class T>
-void singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_threshold) {
+bool singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_threshold) {
   View<const T> M = A.ncols > A.nrows ? A.t() : A;
   const i64 m = M.nrows, n = M.ncols;
-  if (n == 0) return;
+  if (n == 0) return true;
   FB_ASSERT(n < 65536 && m < (1ll << 31), "singular_values: dimension too large for the copy launch");
   T* W = (T*)ws_alloc((size_t)m * (size_t)n * sizeof(T));
   auto copy_in = [&]() {
@@ -123,6 +123,9 @@ void singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_thr
   extract_bidiag_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bm, mb, (int)n, d, e);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
+  // a non-finite bidiagonal has no singular values: the reference returns SvdError::NoConvergence (svd/mod.rs:282-286);
+  // fmax / fmin in the bounds kernel would silently drop the NaNs otherwise
+  const bool finite = device_all_finite<T>(st, d, n) && (n < 2 || device_all_finite<T>(st, e, n - 1));
   gk_bound_kernel<T><<<1, 256, 0, st>>>(d, e, (int)n, bb);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
@@ -134,9 +137,10 @@ void singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_thr
   ws_free(h);
   if (R) ws_free(R);
   ws_free(W);
+  return finite;
 }
 
-template void singular_values<double>(cudaStream_t, View<const double>, double*, double);
-template void singular_values<float>(cudaStream_t, View<const float>, float*, double);
+template bool singular_values<double>(cudaStream_t, View<const double>, double*, double);
+template bool singular_values<float>(cudaStream_t, View<const float>, float*, double);
 
 }  // namespace fb

@@ -57,13 +57,24 @@ void qr_reconstruct(cudaStream_t st, View<T> out, View<const T> Q_basis, View<co
 // ---- evd.cu ----
 // S (device, compact, n entries) <- eigenvalues (nondecreasing) of the self-adjoint matrix whose lower triangle is in A
 // (evd/mod.rs:270-353 with u = None)
+// returns false if the tridiagonal form is not finite (EvdError::NoConvergence in the reference)
 template <class T>
-void self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S);
+bool self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S);
 // ---- svd.cu ----
 // S (device, compact, min(m, n) entries) <- the singular values of A, non-increasing (svd/mod.rs:530-648 with u = v = None)
 // qr_ratio_threshold: SvdParams::qr_ratio_threshold (11/6): taller inputs go through QR first
+// returns false if the bidiagonal form is not finite (SvdError::NoConvergence, svd/mod.rs:282-286)
 template <class T>
-void singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_threshold);
+bool singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_threshold);
+// ---- svd_vectors.cu: decompositions WITH vectors (f64 arithmetic), false on non-finite input ----
+template <class TA>
+bool svd_with_vectors(cudaStream_t st, View<const TA> A, View<TA> U, TA* S, i64 sstride, View<TA> V, double qr_ratio_threshold);
+template <class TA>
+bool self_adjoint_evd_with_vectors(cudaStream_t st, View<const TA> A, View<TA> U, TA* S, i64 sstride);
+template <class T>
+bool device_all_finite(cudaStream_t st, const T* x, i64 n);
+// ---- tridiag_dc.cu: divide-and-conquer eigensolver of a symmetric tridiagonal matrix (device arrays) ----
+bool tridiag_dc_f64(cudaStream_t st, const double* d, const double* e, i64 n, double* lam, double* Q, i64 ldq);
 // ---- tridiag.cu ----
 // A = Q T Q^H, self-adjoint A (lower triangle), column-major. Reference: evd/tridiag.rs:274-529. H: b x (n-1).
 template <class T>

@@ -438,7 +438,7 @@ def qr_inverse(out, Q_basis, Q_coeff, R, par=None) -> None:
 def singular_values(A, par=None, params=None):
     """`svd` with u = v = None (svd/mod.rs:530-648), as `MatRef::singular_values` (solvers.rs:457-487): the
     min(nrows, ncols) singular values of A in non-increasing order, as a numpy vector (host input) or a CUDA tensor (device
-    input). f64 or f32. Singular vectors are not built on the GPU path yet."""
+    input). f64 or f32."""
     lib = capi.load()
     suf = _suf(A)
     m, n = A.shape
@@ -462,7 +462,7 @@ def singular_values(A, par=None, params=None):
 def self_adjoint_eigenvalues(A, par=None, params=None):
     """`self_adjoint_evd` with u = None (evd/mod.rs:270-353), as `MatRef::self_adjoint_eigenvalues(Side::Lower)`
     (solvers.rs:417-456): the eigenvalues of the self-adjoint matrix whose LOWER triangle is in A, nondecreasing, as a numpy
-    vector (host input) or a CUDA tensor (device input). f64 or f32, n <= 8192. Eigenvectors are not built on the GPU yet."""
+    vector (host input) or a CUDA tensor (device input). f64 or f32, n <= 8192."""
     lib = capi.load()
     suf = _suf(A)
     n = A.shape[0]
@@ -480,6 +480,53 @@ def self_adjoint_eigenvalues(A, par=None, params=None):
     if st.tag != 0:
         raise RuntimeError("EvdError::NoConvergence")
     return S
+
+
+class ComputeSvdVectors:
+    """svd/mod.rs:21-28 (faer-ffi/src/lib.rs:462-477)"""
+    No, Thin, Full = 0, 1, 2
+
+
+def _new_mat(like, nrows, ncols):
+    """column-major matrix of the same kind (numpy / torch device) and dtype as `like`"""
+    if capi._is_torch(like):
+        import torch
+        return torch.zeros((ncols, nrows), dtype=like.dtype, device=like.device).T
+    return np.zeros((nrows, ncols), dtype=like.dtype, order="F")
+
+
+def svd(A, S, U=None, V=None, par=None, params=None) -> None:
+    """svd::svd (svd/mod.rs:530-672) through `libfaer_v0_23_svd_<T>` (faer-ffi/src/lib.rs:2345-2366): A = U diag(S) V^H with S
+    (length min(nrows, ncols)) non-increasing. U: None, nrows x size (thin) or nrows x nrows (full); V likewise with ncols.
+    f64 or f32 (f32 computes in f64). Raises RuntimeError("SvdError::NoConvergence") on non-finite input."""
+    lib = capi.load()
+    suf = _suf(A)
+    size = min(A.shape)
+    assert S.shape == (size,)
+    sv = capi.VecMut(S.data_ptr() if capi._is_torch(S) else S.ctypes.data, size, 1)
+    none = capi.MatMut(None, 0, 0, 0, 0)
+    params = params or getattr(lib, f"libfaer_v0_23_SvdParams_{suf}")()
+    st = getattr(lib, f"libfaer_v0_23_svd_{suf}")(capi.mat_ref(A), capi.mat_mut(U) if U is not None else none, sv,
+                                                  capi.mat_mut(V) if V is not None else none, par or capi.par_default(),
+                                                  capi.MemAlloc(None, 0), params)
+    if st.tag != 0:
+        raise RuntimeError("SvdError::NoConvergence")
+
+
+def self_adjoint_evd(A, S, U=None, par=None, params=None) -> None:
+    """evd::self_adjoint_evd (evd/mod.rs:270-418) through `libfaer_v0_23_self_adjoint_evd_<T>`: the LOWER triangle of A is
+    read; S nondecreasing; U (n x n or None) the eigenvectors. Raises RuntimeError("EvdError::NoConvergence") on non-finite input."""
+    lib = capi.load()
+    suf = _suf(A)
+    n = A.shape[0]
+    assert A.shape[1] == n and S.shape == (n,)
+    sv = capi.VecMut(S.data_ptr() if capi._is_torch(S) else S.ctypes.data, n, 1)
+    params = params or getattr(lib, f"libfaer_v0_23_SelfAdjointEvdParams_{suf}")()
+    st = getattr(lib, f"libfaer_v0_23_self_adjoint_evd_{suf}")(capi.mat_ref(A), capi.mat_mut(U) if U is not None else
+                                                               capi.MatMut(None, 0, 0, 0, 0), sv, par or capi.par_default(),
+                                                               capi.MemAlloc(None, 0), params)
+    if st.tag != 0:
+        raise RuntimeError("EvdError::NoConvergence")
 
 
 def bidiag_in_place(A, H_left, H_right, par=None, params=None) -> None:

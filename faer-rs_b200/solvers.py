@@ -444,6 +444,102 @@ class Qr(_Solve):
         return out
 
 
+class Svd:
+    """`Svd<T>` (solvers.rs:1324-1400): `new` = full U and V, `new_thin` = the first min(nrows, ncols) columns of each;
+    A = U diag(S) V^H, S non-increasing. Accessors U(), V(), S() as in the reference; pseudoinverse() = V S^+ U^H
+    (solvers.rs:1390-1400 / svd::pseudoinverse_from_svd)."""
+
+    def __init__(self, U, S, V):
+        self._U, self._S, self._V = U, S, V
+
+    @classmethod
+    def _new(cls, A, thin: bool):
+        m, n = A.shape
+        size = min(m, n)
+        U = la._new_mat(A, m, size if thin else m)
+        V = la._new_mat(A, n, size if thin else n)
+        if capi._is_torch(A):
+            import torch
+            S = torch.zeros(size, dtype=A.dtype, device=A.device)
+        else:
+            S = np.zeros(size, dtype=A.dtype)
+        la.svd(A, S, U, V)
+        return cls(U, S, V)
+
+    @classmethod
+    def new(cls, A):
+        return cls._new(A, False)
+
+    @classmethod
+    def new_thin(cls, A):
+        return cls._new(A, True)
+
+    def U(self):
+        return self._U
+
+    def V(self):
+        return self._V
+
+    def S(self):
+        return self._S
+
+    def pseudoinverse(self):
+        """V diag(1 / s_i for s_i above eps * max(nrows, ncols) * s_max, else 0) U^H (svd/mod.rs pseudoinverse_from_svd)."""
+        S = self._S
+        size = S.shape[0]
+        if size == 0:
+            return la._new_mat(self._U, self._V.shape[0], self._U.shape[0])
+        xp_abs = abs
+        smax = float(S[0])
+        eps = float(np.finfo(np.float64 if str(S.dtype).endswith("64") else np.float32).eps)
+        tol = eps * max(self._U.shape[0], self._V.shape[0]) * smax
+        inv = S.clone() if capi._is_torch(S) else S.copy()
+        mask = S > tol
+        inv[mask] = 1.0 / S[mask]
+        inv[~mask] = 0
+        Vt = self._V[:, :size] * inv[None, :]
+        out = la._new_mat(self._U, self._V.shape[0], self._U.shape[0])
+        la.matmul(out, la.Accum.Replace, Vt, self._U[:, :size].T, 1.0)
+        return out
+
+
+class SelfAdjointEigen:
+    """`SelfAdjointEigen<T>` (solvers.rs:1459-1520): A = U diag(S) U^H from the chosen triangle, S nondecreasing."""
+
+    def __init__(self, U, S):
+        self._U, self._S = U, S
+
+    @classmethod
+    def new(cls, A, side: int = Side.Lower):
+        n = A.shape[0]
+        U = la._new_mat(A, n, n)
+        if capi._is_torch(A):
+            import torch
+            S = torch.zeros(n, dtype=A.dtype, device=A.device)
+        else:
+            S = np.zeros(n, dtype=A.dtype)
+        la.self_adjoint_evd(A if side == Side.Lower else A.T, S, U)
+        return cls(U, S)
+
+    def U(self):
+        return self._U
+
+    def S(self):
+        return self._S
+
+
+def svd(A) -> Svd:
+    return Svd.new(A)
+
+
+def thin_svd(A) -> Svd:
+    return Svd.new_thin(A)
+
+
+def self_adjoint_eigen(A, side: int = Side.Lower) -> SelfAdjointEigen:
+    return SelfAdjointEigen.new(A, side)
+
+
 # `A.llt(side)`, `A.partial_piv_lu()`, `A.qr()` (solvers.rs:346-392) as free functions
 def llt(A, side: int = Side.Lower) -> Llt:
     return Llt.new(A, side)
