@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bidiag_kernel(T* A, i64 cs, int
       reduce_partials<T, 7>(sc.part + (((nbar - 1) & 1) * G) * BD_NV, G, s);
       const T norm = norm_from_acc(s[0], s[1], s[2], sml, big);
       const T tail_raw = norm_from_acc(s[3], s[4], s[5], sml, big);
-      const T norm_inv = norm != T(0) ? T(1) / norm : T(1);
+      // (a subnormal norm would overflow its reciprocal in f32: such a row is numerically zero)
+      const T norm_inv = norm >= min_pos ? T(1) / norm : T(1);
       const T y1 = t_ldcg(&sc.ybuf[k + 1]);
       const T head_n = t_ldcg(&sc.a12[k + 1]) * norm_inv;
       // (k + 1 < size here: with m >= n the last column leaves through the nr == 0 exit above)

@@ -110,6 +110,36 @@ bool self_adjoint_eigenvalues(cudaStream_t st, View<const T> A, T* S) {
 }
 
 template bool self_adjoint_eigenvalues<double>(cudaStream_t, View<const double>, double*);
-template bool self_adjoint_eigenvalues<float>(cudaStream_t, View<const float>, float*);
+
+namespace {
+template <class TD, class TS>
+__global__ void evd_cast_copy_kernel(TD* __restrict__ dst, i64 ld, const TS* __restrict__ src, i64 rs, i64 cs, i64 m, i64 c0) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = c0 + blockIdx.y;
+  if (i < m) dst[j * ld + i] = (TD)src[i * rs + j * cs];
+}
+}  // namespace
+
+// f32 through an f64 copy (see svd.cu: same reasons)
+template <>
+bool self_adjoint_eigenvalues<float>(cudaStream_t st, View<const float> A, float* S) {
+  const i64 n = A.nrows;
+  FB_ASSERT(A.ncols == n, "self_adjoint_eigenvalues: square matrix required");
+  if (n == 0) return true;
+  double* W = (double*)ws_alloc((size_t)n * (size_t)n * 8);
+  for (i64 c0 = 0; c0 < n; c0 += 65535) {
+    const i64 nc = std::min<i64>(65535, n - c0);
+    evd_cast_copy_kernel<double, float><<<dim3((unsigned)((n + 255) / 256), (unsigned)nc), 256, 0, st>>>(W, n, A.ptr, A.rs, A.cs, n, c0);
+    note_launch();
+  }
+  double* S64 = (double*)ws_alloc((size_t)n * 8);
+  const bool ok = self_adjoint_eigenvalues<double>(st, View<const double>{W, n, n, 1, n}, S64);
+  evd_cast_copy_kernel<float, double><<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, st>>>(S, n, S64, 1, n, n, 0);
+  note_launch();
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  ws_free(S64);
+  ws_free(W);
+  return ok;
+}
 
 }  // namespace fb

@@ -1022,6 +1022,40 @@ void faer_b200_bidiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, 
 void faer_b200_tridiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<double>(A, householder); }
 void faer_b200_tridiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<float>(A, householder); }
 
+void faer_b200_spicy_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Block C_block, const unsigned long long* row_idx, size_t nrow_idx,
+                                const unsigned long long* col_idx, size_t ncol_idx, FaerV0_24_Accum accum, FaerV0_24_MatRef A,
+                                FaerV0_24_MatRef B, const double* D, const FaerV0_24_Scalar* alpha) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  FB_ASSERT(A.ncols == B.nrows, "spicy_matmul shape mismatch");
+  FB_ASSERT(!row_idx || nrow_idx == A.nrows, "spicy_matmul: one row index per row of A");
+  FB_ASSERT(!col_idx || ncol_idx == B.ncols, "spicy_matmul: one column index per column of B");
+  if (row_idx && !is_device_pointer(row_idx))
+    for (size_t i = 0; i < nrow_idx; ++i) FB_ASSERT(row_idx[i] < C.nrows, "spicy_matmul: row index out of range");
+  if (col_idx && !is_device_pointer(col_idx))
+    for (size_t j = 0; j < ncol_idx; ++j) FB_ASSERT(col_idx[j] < C.ncols, "spicy_matmul: column index out of range");
+  const double a = read_scalar_f64(alpha);
+  Mat c(C, true, st);  // scattered destinations keep the untouched entries: always stage the old contents
+  Mat lhs(A, st), rhs(B, st);
+  // indices and diagonal: device copies of host arrays
+  auto to_dev = [&](const void* p, size_t bytes) -> void* {
+    if (!p || bytes == 0) return nullptr;
+    if (is_device_pointer(p)) return (void*)p;
+    void* d = ws_alloc(bytes);
+    FB_CUDA_CHECK(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, st));
+    return d;
+  };
+  void* dri = to_dev(row_idx, nrow_idx * 8);
+  void* dci = to_dev(col_idx, ncol_idx * 8);
+  void* dd = to_dev(D, (size_t)A.ncols * 8);
+  spicy_matmul_f64(st, c.s.view<double>(), (int)C_block, (const long long*)dri, (const long long*)dci,
+                   accum == FaerV0_24_Accum_Add ? 1 : 0, lhs.s.view<const double>(), rhs.s.view<const double>(), (const double*)dd, 1, a);
+  finish_all(st, {&c.s, &lhs.s, &rhs.s});
+  if (dri && dri != (void*)row_idx) ws_free(dri);
+  if (dci && dci != (void*)col_idx) ws_free(dci);
+  if (dd && dd != (void*)D) ws_free(dd);
+}
+
 int faer_b200_set_option(const char* name, long long value) { return set_option_by_name(name, value) ? 0 : -1; }
 long long faer_b200_get_option(const char* name) { return get_option_by_name(name); }
 

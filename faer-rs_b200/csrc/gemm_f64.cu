@@ -521,4 +521,96 @@ void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, i
   }
 }
 
+// ---- "spicy" matmul (reference faer/src/linalg/matmul/internal/mod.rs:45-379): dst[row_idx[i], col_idx[j]] (+)= alpha *
+// (lhs * diag(d) * rhs)[i, j] for the (i, j) the block structure of the PRODUCT keeps; used by LDLT's trailing updates
+// (cholesky/ldlt/factor.rs:447-492) and the supernodal sparse Cholesky fronts. All pointers are device pointers.
+// Large TMA-readable operands: ONE launch of the warp-specialised kernel with the diagonal folded into the lhs fragments
+// (prologue) and the scatter folded into the store (epilogue). Otherwise the reference's own fallback composition
+// (internal/mod.rs:206-379): scale, structured product into a temporary, masked scatter.
+namespace {
+__global__ void scale_cols_kernel(double* __restrict__ dst, i64 ld, const double* __restrict__ src, i64 rs, i64 cs, i64 m,
+                                  const double* __restrict__ d, i64 dstride) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = blockIdx.y;
+  if (i < m) dst[j * ld + i] = src[i * rs + j * cs] * d[j * dstride];
+}
+__global__ void spicy_scatter_kernel(double* __restrict__ C, i64 rs, i64 cs, const double* __restrict__ out, i64 m, i64 n,
+                                     const long long* __restrict__ ri, const long long* __restrict__ ci, int c_struct, int accum,
+                                     i64 j0) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = j0 + blockIdx.y;
+  if (i >= m || j >= n) return;
+  const bool nodiag = is_strict(c_struct) || is_unit(c_struct);
+  if (is_lower(c_struct) && (i < j || (i == j && nodiag))) return;
+  if (is_upper(c_struct) && (i > j || (i == j && nodiag))) return;
+  double* p = C + (ri ? ri[i] : i) * rs + (ci ? ci[j] : j) * cs;
+  const double v = out[j * m + i];
+  *p = accum ? *p + v : v;
+}
+}  // namespace
+
+void spicy_matmul_f64(cudaStream_t st, VD C, int c_struct, const long long* row_idx, const long long* col_idx, int accum, VCD A,
+                      VCD B, const double* diag, i64 diag_stride, double alpha) {
+  const i64 m = A.nrows, n = B.ncols, k = A.ncols;
+  FB_ASSERT(B.nrows == k, "spicy_matmul shape mismatch");
+  if (!row_idx) FB_ASSERT(C.nrows == m, "spicy_matmul: dst rows");
+  if (!col_idx) FB_ASSERT(C.ncols == n, "spicy_matmul: dst columns");
+  if (m == 0 || n == 0) return;
+  if (k == 0 && accum) return;
+  FB_ASSERT(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "dimension too large");
+  if (k > 0 && ws_mode() != 0) {
+    GemmF64Params p;
+    p.m = (int)m; p.n = (int)n; p.k = (int)k;
+    p.A = A.ptr; p.a_rs = A.rs; p.a_cs = A.cs; p.a_struct = RECT;
+    p.B = B.ptr; p.b_rs = B.rs; p.b_cs = B.cs; p.b_struct = RECT;
+    p.C = C.ptr; p.c_rs = C.rs; p.c_cs = C.cs; p.c_struct = c_struct;
+    p.alpha = alpha; p.accum = accum; p.k_split_len = 0; p.c_split_stride = 0;
+    const long long tiles = (long long)((m + ws64::BM - 1) / ws64::BM) * ((n + ws64::BN - 1) / ws64::BN);
+    if (ws_mode() == 2 || (tiles >= 32 && k >= 16)) {
+      ws64::Spicy sp;
+      sp.row_idx = row_idx; sp.col_idx = col_idx; sp.diag = diag; sp.diag_stride = diag_stride;
+      if (ws64::try_gemm_f64_ws(st, p, &sp)) return;
+    }
+  }
+  // fallback composition
+  double* scaled = nullptr;
+  VCD lhs = A;
+  if (diag && k > 0) {
+    scaled = (double*)ws_alloc((size_t)m * (size_t)k * 8);
+    for (i64 c0 = 0; c0 < k; c0 += 65535) {
+      const i64 nc = std::min<i64>(65535, k - c0);
+      scale_cols_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)nc), 256, 0, st>>>(scaled + c0 * m, m, A.ptr + c0 * A.cs, A.rs, A.cs,
+                                                                                        m, diag + c0 * diag_stride, diag_stride);
+      note_launch();
+    }
+    lhs = VCD{scaled, m, k, 1, m};
+  }
+  const bool gather = row_idx || col_idx;
+  double* outb = gather ? (double*)ws_alloc((size_t)m * (size_t)n * 8) : nullptr;
+  VD out = gather ? VD{outb, m, n, 1, m} : C;
+  const int acc2 = gather ? 0 : accum;
+  if (c_struct == RECT) {
+    gemm_f64(st, out, RECT, acc2, lhs, RECT, B, RECT, alpha);
+  } else {
+    const i64 size = std::min(m, n);
+    gemm_f64(st, out.sub(0, 0, size, size), c_struct, acc2, lhs.sub(0, 0, size, k), RECT, B.sub(0, 0, k, size), RECT, alpha);
+    if (is_lower(c_struct) && m > n)
+      gemm_f64(st, out.sub(size, 0, m - size, size), RECT, acc2, lhs.sub(size, 0, m - size, k), RECT, B.sub(0, 0, k, size), RECT, alpha);
+    else if (is_upper(c_struct) && n > m)
+      gemm_f64(st, out.sub(0, size, size, n - size), RECT, acc2, lhs.sub(0, 0, size, k), RECT, B.sub(0, size, k, n - size), RECT, alpha);
+  }
+  if (gather) {
+    for (i64 c0 = 0; c0 < n; c0 += 65535) {
+      const i64 nc = std::min<i64>(65535, n - c0);
+      spicy_scatter_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)nc), 256, 0, st>>>(C.ptr, C.rs, C.cs, outb, m, n, row_idx, col_idx,
+                                                                                           c_struct, accum, c0);
+      note_launch();
+    }
+  }
+  FB_CUDA_CHECK(cudaGetLastError());
+  if (outb || scaled) FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (outb) ws_free(outb);
+  if (scaled) ws_free(scaled);
+}
+
 }  // namespace fb

@@ -34,6 +34,11 @@ struct GemmF64Params {
 void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, int lhs_struct, VCD rhs, int rhs_struct,
               double alpha);
 
+// "spicy" matmul (matmul/internal/mod.rs:45-379): dst[row_idx[i], col_idx[j]] (+)= alpha (lhs diag(d) rhs)[i, j], masked by the
+// block structure of the product. row_idx / col_idx / diag: DEVICE pointers or null.
+void spicy_matmul_f64(cudaStream_t st, VD dst, int dst_struct, const long long* row_idx, const long long* col_idx, int accum,
+                      VCD lhs, VCD rhs, const double* diag, i64 diag_stride, double alpha);
+
 inline void gemm_f64(cudaStream_t stream, VD dst, int accum, VCD lhs, VCD rhs, double alpha) {
   gemm_f64(stream, dst, RECT, accum, lhs, RECT, rhs, RECT, alpha);
 }

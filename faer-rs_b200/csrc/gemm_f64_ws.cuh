@@ -87,6 +87,11 @@ struct Params {
   double alpha;
   int tiles_m, tiles_n;
   int tiles_per_cta;
+  // "spicy" variant (matmul/internal/mod.rs:45-379): dst[row_idx[i], col_idx[j]] (+)= alpha (A diag(d) B)[i, j]
+  const long long* row_idx;  // device, m entries, or null
+  const long long* col_idx;  // device, n entries, or null
+  const double* diag;        // device, k entries `diag_stride` apart, or null
+  i64 diag_stride;
 };
 
 // ---- static tile schedule: tile `idx` of the launch -> (tm, tn); identical in every warp of every CTA ---------------
@@ -140,7 +145,7 @@ __device__ __forceinline__ uint32_t off_k_major(int mn, int kk) {
   return (uint32_t)(mn * 128 + ((((kk >> 1) ^ (mn & 7)) << 4) | ((kk & 1) << 3)));
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR>
+template <bool A_KMAJOR, bool B_KMAJOR, bool SPICY>
 __global__ void __launch_bounds__(THREADS, 2)   // 128 registers per thread at launch, re-divided below
 gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   extern __shared__ uint8_t ws_smem_raw[];
@@ -244,6 +249,17 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
     for (int kt = 0; kt < nkt; ++kt, ++it) {
       const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+      double dk[4] = {1.0, 1.0, 1.0, 1.0};
+      if constexpr (SPICY) {
+        if (p.diag) {  // this lane's four k indices of the stage: K4(ss, t)
+          const int base_k = (t == 0) ? 0 : (t == 1) ? 3 : (t == 2) ? 12 : 15;
+#pragma unroll
+          for (int ss = 0; ss < 4; ++ss) {
+            const int kg = kt * BK + (base_k ^ ((ss & 1) | ((ss & 2) << 1)));
+            dk[ss] = kg < p.k ? p.diag[(i64)kg * p.diag_stride] : 0.0;
+          }
+        }
+      }
       mbar_wait(&full[s], ph);
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
@@ -253,6 +269,7 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         for (int i = 0; i < WMI; ++i) {
           if constexpr (A_KMAJOR) a[i] = lds64(sa + offA[ss][0] + i * 8 * 128);
           else a[i] = lds64(sa + offA[ss][i & 1] + (i >> 1) * 2048);
+          if constexpr (SPICY) a[i] *= dk[ss];
         }
 #pragma unroll
         for (int j = 0; j < WNI; ++j) {
@@ -272,8 +289,18 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
     for (int i = 0; i < WMI; ++i) {
       const int row = m0 + wm0 + i * 8 + g;
+      i64 roff = (i64)row * p.c_rs;
+      if constexpr (SPICY) {
+        if (p.row_idx) roff = row < p.m ? (i64)p.row_idx[row] * p.c_rs : 0;
+      }
       double cv[WNI][2];
       bool ok[WNI][2];
+      auto coloff = [&](int col) -> i64 {
+        if constexpr (SPICY) {
+          if (p.col_idx) return col < p.n ? (i64)p.col_idx[col] * p.c_cs : 0;
+        }
+        return (i64)col * p.c_cs;
+      };
 #pragma unroll
       for (int j = 0; j < WNI; ++j) {
 #pragma unroll
@@ -283,7 +310,7 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (c_low && (row < col || (row == col && c_nodiag))) v = false;
           if (c_up && (row > col || (row == col && c_nodiag))) v = false;
           ok[j][e] = v;
-          cv[j][e] = (add && v) ? p.C[(i64)row * p.c_rs + (i64)col * p.c_cs] : 0.0;
+          cv[j][e] = (add && v) ? p.C[roff + coloff(col)] : 0.0;
         }
       }
 #pragma unroll
@@ -291,7 +318,7 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = n0 + j * 8 + 2 * t + e;
-          if (ok[j][e]) p.C[(i64)row * p.c_rs + (i64)col * p.c_cs] = alpha * acc[i][j][e] + cv[j][e];
+          if (ok[j][e]) p.C[roff + coloff(col)] = alpha * acc[i][j][e] + cv[j][e];
         }
       }
     }
@@ -339,7 +366,13 @@ inline bool tma_layout(const double* ptr, i64 rows, i64 k, i64 s_mn, i64 s_k, bo
 }
 
 // Launches the kernel if the problem qualifies; returns false otherwise (caller falls back to the cp.async kernel).
-inline bool try_gemm_f64_ws(cudaStream_t stream, const GemmF64Params& q) {
+struct Spicy {
+  const long long* row_idx = nullptr;
+  const long long* col_idx = nullptr;
+  const double* diag = nullptr;
+  i64 diag_stride = 1;
+};
+inline bool try_gemm_f64_ws(cudaStream_t stream, const GemmF64Params& q, const Spicy* sp = nullptr) {
   if (q.a_struct != RECT || q.b_struct != RECT || q.k_split_len > 0) return false;
   if (!encode_fn()) return false;
   bool ak = false, bk = false;
@@ -351,6 +384,10 @@ inline bool try_gemm_f64_ws(cudaStream_t stream, const GemmF64Params& q) {
   p.C = q.C; p.c_rs = q.c_rs; p.c_cs = q.c_cs;
   p.m = q.m; p.n = q.n; p.k = q.k;
   p.c_struct = q.c_struct; p.accum = q.accum; p.alpha = q.alpha;
+  p.row_idx = sp ? sp->row_idx : nullptr;
+  p.col_idx = sp ? sp->col_idx : nullptr;
+  p.diag = sp ? sp->diag : nullptr;
+  p.diag_stride = sp ? sp->diag_stride : 1;
   p.tiles_m = (q.m + BM - 1) / BM;
   p.tiles_n = (q.n + BN - 1) / BN;
   long long tiles = (long long)p.tiles_m * p.tiles_n;
@@ -371,7 +408,7 @@ inline bool try_gemm_f64_ws(cudaStream_t stream, const GemmF64Params& q) {
   p.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, 768 / std::max(q.k, 1)));
   const int grid = (int)((tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
   // one opt-in to > 48 KB of dynamic shared memory per kernel variant
-  static bool configured[4] = {false, false, false, false};
+  static bool configured[8] = {false, false, false, false, false, false, false, false};
   auto launch = [&](int which, void (*kern)(CUtensorMap, CUtensorMap, Params)) {
     if (!configured[which]) {
       FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -379,10 +416,17 @@ inline bool try_gemm_f64_ws(cudaStream_t stream, const GemmF64Params& q) {
     }
     kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, p);
   };
-  if (ak && bk) launch(0, gemm_f64_ws_kernel<true, true>);
-  else if (ak && !bk) launch(1, gemm_f64_ws_kernel<true, false>);
-  else if (!ak && bk) launch(2, gemm_f64_ws_kernel<false, true>);
-  else launch(3, gemm_f64_ws_kernel<false, false>);
+  if (!sp) {
+    if (ak && bk) launch(0, gemm_f64_ws_kernel<true, true, false>);
+    else if (ak && !bk) launch(1, gemm_f64_ws_kernel<true, false, false>);
+    else if (!ak && bk) launch(2, gemm_f64_ws_kernel<false, true, false>);
+    else launch(3, gemm_f64_ws_kernel<false, false, false>);
+  } else {
+    if (ak && bk) launch(4, gemm_f64_ws_kernel<true, true, true>);
+    else if (ak && !bk) launch(5, gemm_f64_ws_kernel<true, false, true>);
+    else if (!ak && bk) launch(6, gemm_f64_ws_kernel<false, true, true>);
+    else launch(7, gemm_f64_ws_kernel<false, false, true>);
+  }
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
   return true;

@@ -160,16 +160,13 @@ __global__ void __launch_bounds__(LDL_THREADS) ldlf2_kernel(double* __restrict__
   if (tid == 0 && s_count) info[1] += s_count;
 }
 
-// W <- A21 (compact column-major, ld = n2);  A21(:, k) <- A21(:, k) * recip(d_k),  d_k = Dblk[k * dstride]
-__global__ void ldlt_scale_copy_kernel(double* __restrict__ A21, i64 rs, i64 cs, i64 n2, i64 n1,
-                                       const double* __restrict__ Dblk, i64 dstride, double* __restrict__ W) {
+// A21(:, k) <- A21(:, k) * recip(d_k),  d_k = Dblk[k * dstride]
+__global__ void ldlt_scale_kernel(double* __restrict__ A21, i64 rs, i64 cs, i64 n2, i64 n1, const double* __restrict__ Dblk,
+                                  i64 dstride) {
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const i64 k = blockIdx.y;
   if (i >= n2 || k >= n1) return;
-  const double inv = 1.0 / Dblk[k * dstride];
-  const double x = A21[i * rs + k * cs];
-  W[k * n2 + i] = x;
-  A21[i * rs + k * cs] = x * inv;
+  A21[i * rs + k * cs] *= 1.0 / Dblk[k * dstride];
 }
 
 // rhs(i, :) <- rhs(i, :) * recip(d_i)
@@ -206,17 +203,15 @@ void ldlt_rec(const LdltCtx& ctx, VD A, i64 j0) {
   ldlt_rec(ctx, A11, j0);
   // conj(L11) X = A21^T with the unit-lower solve: X = L21 D1  (ldlt/factor.rs:427-433)
   solve_lower_triangular_in_place_f64(ctx.stream, cv(A11), true, A21.t());
-  // W <- X, A21 <- X * recip(D1)  (471-481); the pool buffer is reused in stream order, this driver has one stream
-  double* W = (double*)ws_alloc((size_t)n2 * (size_t)n1 * sizeof(double));
+  // A21 <- X * recip(D1) = L21 in place, then A22(lower) -= L21 D1 L21^H as ONE "spicy" product with the diagonal folded
+  // into the lhs fragments (ldlt/factor.rs:447-470, the reference's has_spicy_matmul branch; the copy of X that its other
+  // branch keeps, 471-492, is not needed)
   FB_ASSERT(n1 < 65536, "LDLT block too wide for one scale launch");
   dim3 grid((unsigned)((n2 + 255) / 256), (unsigned)n1);
-  ldlt_scale_copy_kernel<<<grid, 256, 0, ctx.stream>>>(A21.ptr, A21.rs, A21.cs, n2, n1, A11.ptr, A11.rs + A11.cs, W);
+  ldlt_scale_kernel<<<grid, 256, 0, ctx.stream>>>(A21.ptr, A21.rs, A21.cs, n2, n1, A11.ptr, A11.rs + A11.cs);
   FB_CUDA_CHECK(cudaGetLastError());
   note_launch();
-  // A22(lower) += -1 * L21 * X^H  (482-492)
-  VCD Wv{W, n2, n1, 1, n2};
-  gemm_f64(ctx.stream, A22, TRI_LOWER, 1, cv(A21), RECT, Wv.t(), RECT, -1.0);
-  ws_free(W);
+  spicy_matmul_f64(ctx.stream, A22, TRI_LOWER, nullptr, nullptr, 1, cv(A21), cv(A21).t(), A11.ptr, A11.rs + A11.cs, -1.0);
   ldlt_rec(ctx, A22, j0 + n1);
 }
 

@@ -141,6 +141,37 @@ bool singular_values(cudaStream_t st, View<const T> A, T* S, double qr_ratio_thr
 }
 
 template bool singular_values<double>(cudaStream_t, View<const double>, double*, double);
-template bool singular_values<float>(cudaStream_t, View<const float>, float*, double);
+
+namespace {
+template <class TD, class TS>
+__global__ void cast_copy_kernel(TD* __restrict__ dst, i64 ld, const TS* __restrict__ src, i64 rs, i64 cs, i64 m, i64 c0) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = c0 + blockIdx.y;
+  if (i < m) dst[j * ld + i] = (TD)src[i * rs + j * cs];
+}
+}  // namespace
+
+// f32: the condensed form is computed in f64 on a copy (as the f32 decompositions with vectors do, svd_vectors.cu): the
+// values come out to f32 accuracy relative to sigma_max at least, and an exactly rank-deficient f32 input cannot push
+// subnormal intermediates through the f32 bidiagonalization kernel
+template <>
+bool singular_values<float>(cudaStream_t st, View<const float> A, float* S, double qr_ratio_threshold) {
+  const i64 m = A.nrows, n = A.ncols, size = std::min(m, n);
+  if (size == 0) return true;
+  double* W = (double*)ws_alloc((size_t)m * (size_t)n * 8);
+  for (i64 c0 = 0; c0 < n; c0 += 65535) {
+    const i64 nc = std::min<i64>(65535, n - c0);
+    cast_copy_kernel<double, float><<<dim3((unsigned)((m + 255) / 256), (unsigned)nc), 256, 0, st>>>(W, m, A.ptr, A.rs, A.cs, m, c0);
+    note_launch();
+  }
+  double* S64 = (double*)ws_alloc((size_t)size * 8);
+  const bool ok = singular_values<double>(st, View<const double>{W, m, n, 1, m}, S64, qr_ratio_threshold);
+  cast_copy_kernel<float, double><<<dim3((unsigned)((size + 255) / 256), 1), 256, 0, st>>>(S, size, S64, 1, size, size, 0);
+  note_launch();
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  ws_free(S64);
+  ws_free(W);
+  return ok;
+}
 
 }  // namespace fb

@@ -41,6 +41,7 @@ constexpr int TD_NW = TD_THREADS / 32;
 
 template <class T>
 struct TdScratch {
+  T* vecg;   // [G][3][n] x / u / w of the current column for CTAs whose trailing block does not fit shared memory yet (or null)
   T* ycomb;  // [n]   y before the "- b (1; x)" correction
   T* ycol;   // [n]   column sums of pass 1
   T* cbuf;   // [2][n] column k (+1) with the older pending update applied; [k] holds the diagonal entry
@@ -51,10 +52,10 @@ struct TdScratch {
 template <class T>
 __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(T* A, i64 cs, int n, T* H, i64 hs, TdScratch<T> sc) {
   extern __shared__ unsigned char td_smem_raw[];
-  T* x_s = reinterpret_cast<T*>(td_smem_raw);  // [TD_CH] scaled tail of the current reflector (global row - gb)
-  T* u_s = x_s + TD_CH;                        // [TD_CH] previous reflector
-  T* w_s = u_s + TD_CH;                        // [TD_CH] pending y
-  T* part = w_s + TD_CH;                       // [TD_PC][32]  (pass 2: red[TD_THREADS])
+  T* xs0 = reinterpret_cast<T*>(td_smem_raw);  // [TD_CH] scaled tail of the current reflector (global row - gb)
+  T* us0 = xs0 + TD_CH;                        // [TD_CH] previous reflector
+  T* ws0 = us0 + TD_CH;                        // [TD_CH] pending y
+  T* part = ws0 + TD_CH;                       // [TD_PC][32]  (pass 2: red[TD_THREADS])
   T* fin = part + TD_PC * 32;                  // [TD_NW][PANEL_NV]
   T* scal = fin + TD_NW * PANEL_NV;            // [16]
 
@@ -82,6 +83,12 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(T* A, i64 cs, in
     if (bid == 0 && tid == 0) A[(i64)k * cs + k] = t_ldcg(&cur[k]) - (y1 + y1);  // tridiag.rs:311
     if (len == 0) break;
     const int gb = (k + 1) & ~31;
+    // the three vectors cover rows gb .. n-1: in shared memory once that fits (n - gb <= TD_CH), until then in this CTA's
+    // private slice of global memory (L2-resident; n > 8192 only). Written and read by this CTA alone.
+    const bool vec_in_smem = n - gb <= TD_CH;
+    T* x_s = vec_in_smem ? xs0 : sc.vecg + (size_t)bid * 3 * n;
+    T* u_s = vec_in_smem ? us0 : x_s + n;
+    T* w_s = vec_in_smem ? ws0 : u_s + n;
 
     // ================= vector phase =================
     // column k with the pending update (tridiag.rs:312-316), u and the corrected pending y, for rows >= k+1
@@ -293,14 +300,16 @@ void tridiag_in_place(cudaStream_t st, View<T> A, View<T> H) {
   if (n == 0) return;
   FB_ASSERT(n <= 1 || H.nrows > 0, "tridiag_in_place: empty Householder factor");
   FB_ASSERT(A.rs == 1, "tridiag_in_place: column-major (row stride 1) matrix required");
-  FB_ASSERT(n <= TD_CH, "tridiag_in_place: n <= 8192 in this version (vectors are kept in shared memory)");
+  FB_ASSERT(n < (1ll << 30), "tridiag_in_place: dimension too large");
   int dev = 0, num_sms = 0;
   FB_CUDA_CHECK(cudaGetDevice(&dev));
   FB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   const int G = num_sms;
-  const size_t elems = (size_t)4 * n + (size_t)2 * G * PANEL_NV + 8;
+  const size_t vec_elems = n > TD_CH ? (size_t)G * 3 * (size_t)n : 0;
+  const size_t elems = (size_t)4 * n + (size_t)2 * G * PANEL_NV + 32 + vec_elems;
   char* buf = (char*)ws_alloc(elems * sizeof(T) + 64);
   TdScratch<T> sc;
+  sc.vecg = vec_elems ? (T*)buf + ((size_t)4 * n + (size_t)2 * G * PANEL_NV + 8 + 8) : nullptr;
   sc.ycomb = (T*)buf;
   sc.ycol = sc.ycomb + n;
   sc.cbuf = sc.ycol + n;

@@ -482,6 +482,21 @@ def self_adjoint_eigenvalues(A, par=None, params=None):
     return S
 
 
+def spicy_matmul(C, C_block: int, row_idx, col_idx, accum: int, A, B, D, alpha: float) -> None:
+    """linalg::matmul::internal::spicy_matmul (matmul/internal/mod.rs:45-379), real f64:
+    C[row_idx[i], col_idx[j]] (+)= alpha * (A diag(D) B)[i, j] for the (i, j) that `C_block` (block structure of the product)
+    keeps. row_idx / col_idx: None or uint64 numpy arrays; D: None or a float64 numpy vector of length A.ncols."""
+    lib = capi.load()
+    _check_f64(C, A, B)
+    ri = None if row_idx is None else np.ascontiguousarray(row_idx, dtype=np.uint64)
+    ci = None if col_idx is None else np.ascontiguousarray(col_idx, dtype=np.uint64)
+    dv = None if D is None else np.ascontiguousarray(D, dtype=np.float64)
+    a = np.array([alpha], dtype=np.float64)
+    lib.faer_b200_spicy_matmul_f64(capi.mat_mut(C), int(C_block), None if ri is None else ri.ctypes.data, 0 if ri is None else ri.size,
+                                   None if ci is None else ci.ctypes.data, 0 if ci is None else ci.size, int(accum), capi.mat_ref(A),
+                                   capi.mat_ref(B), None if dv is None else dv.ctypes.data, a.ctypes.data)
+
+
 class ComputeSvdVectors:
     """svd/mod.rs:21-28 (faer-ffi/src/lib.rs:462-477)"""
     No, Thin, Full = 0, 1, 2

@@ -410,6 +410,14 @@ void faer_b200_bidiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_M
  * T on A's diagonal / subdiagonal, reflectors below the subdiagonal, `householder` (b x (n-1)) holds their T blocks. */
 void faer_b200_tridiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
 void faer_b200_tridiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+/* "spicy" matmul: C[row_idx[i], col_idx[j]] (+)= alpha * (A diag(D) B)[i, j] for the (i, j) that C_block keeps (block structure
+ * of the PRODUCT). Mirrors faer::linalg::matmul::internal::spicy_matmul (faer/src/linalg/matmul/internal/mod.rs:45-58), which
+ * faer-ffi does not export (it is an internal of LDLT and of the sparse supernodal Cholesky): row_idx / col_idx may be NULL
+ * (then C has A.nrows rows / B.ncols columns), D (A.ncols entries) may be NULL; host or device pointers. Real f64. */
+void faer_b200_spicy_matmul_f64(struct FaerV0_24_MatMut C, enum FaerV0_24_Block C_block, const unsigned long long *row_idx,
+                                size_t nrow_idx, const unsigned long long *col_idx, size_t ncol_idx, enum FaerV0_24_Accum accum,
+                                struct FaerV0_24_MatRef A, struct FaerV0_24_MatRef B, const double *D,
+                                const struct FaerV0_24_Scalar *alpha);
 /* Run-time options (initial values from the environment variable in brackets). Returns 0, or -1 for an unknown name.
  *   "gemm_ws"        [FAER_B200_GEMM_WS]        0 never / 1 heuristic (default) / 2 always use the TMA-fed warp-specialised
  *                                                f64 GEMM (csrc/gemm_f64_ws.cuh) where the operands qualify

@@ -28,6 +28,9 @@ def oracle():
     """CPU oracle (test infrastructure; builds oracle/liboracle.so on first use)."""
     from oracle import oracle as orc
     orc.load()
+    # the oracle forks an OpenMP team per product / solve; on a many-core GPU box the fork-join cost of a 100+ thread team
+    # dominates the small test problems (measured: the QR parity tests took 5 minutes instead of seconds)
+    orc.set_num_threads(max(1, min(os.cpu_count() or 1, 16)))
     return orc
 
 
