@@ -860,29 +860,49 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
     for (i64 i = 0; i < n; ++i) perm_inv[perm_fwd[i]] = i;
     return n_trans;
   }
+  // Stream roles (P >= 1). With an SM partition (green contexts) the panel chain owns its SMs:
+  //   sp  panel factorization (cluster kernels; big recursion nodes go to su)     su  look-ahead column update (urgent)
+  //   sm  bulk trailing updates                                                   sb  the NCCL broadcast (plain stream)
+  // Without a partition (FAER_B200_GREEN_SMS=0 or no look-ahead) sp = su = sb is the high-priority stream.
   if (lookahead) ensure_streams();
-  cudaStream_t sp = lookahead ? g_panel_stream : current_stream();
-  cudaStream_t sm = lookahead ? g_main_stream : current_stream();
+  const bool part = lookahead && !getenv("FAER_B200_DIST_NO_PARTITION") && ensure_green_streams();
+  cudaStream_t sp = part ? g_green_panel : (lookahead ? g_panel_stream : current_stream());
+  cudaStream_t su = part ? g_green_urgent : sp;
+  cudaStream_t sm = part ? g_green_main : (lookahead ? g_main_stream : current_stream());
+  cudaStream_t sb = part ? g_panel_stream : sp;
   const bool two_streams = sp != sm && lookahead;
   if (!two_streams) sm = sp;
+  const bool trace = getenv("FAER_B200_TRACE") != nullptr;
+  const unsigned evf = trace ? cudaEventDefault : cudaEventDisableTiming;
   cudaEvent_t ev_start;
-  FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start, evf));
   FB_CUDA_CHECK(cudaEventRecord(ev_start, current_stream()));
-  FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_start, 0));
-  if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
+  for (cudaStream_t st : {sp, su, sm, sb})
+    if (st != current_stream()) FB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_start, 0));
 
   const i64 nblk = nblocks(n, nb);
   const i64 ncols_loc = local_cols(n, nb, P, me);
-  double* W[2];
-  W[0] = (double*)ws_alloc((size_t)n * nb * 8);
-  W[1] = (double*)ws_alloc((size_t)n * nb * 8);
+  constexpr int NW = 3;  // panel buffers in flight
+  double* W[NW];
+  for (int i = 0; i < NW; ++i) W[i] = (double*)ws_alloc((size_t)n * nb * 8);
   int* d_trans = (int*)ws_alloc((size_t)n * sizeof(int));
-  LuWorkspace* wp = lu_ws_create(sp, nb);
+  LuWorkspace* wp = lu_ws_create(sp, nb, part ? g_green_panel_sms : 0);
+  if (part) {
+    if (!getenv("FAER_B200_NO_OFFLOAD")) lu_ws_set_big_stream(wp, su);
+    const char* e = getenv("FAER_B200_LU_CLUSTER");
+    const int want = e ? atoi(e) : 16;
+    if (want > 0) lu_ws_set_cluster(wp, std::min(want, g_green_panel_sms >= 16 ? 16 : 8));
+  }
+  LuWorkspace* wu = (su != sp) ? lu_ws_create(su, nb) : wp;
   LuWorkspace* wm = two_streams ? lu_ws_create(sm, nb) : wp;
-  std::vector<cudaEvent_t> ev_bcast((size_t)nblk), ev_used((size_t)nblk);
+  std::vector<cudaEvent_t> ev_fact((size_t)nblk), ev_bcast((size_t)nblk), ev_used((size_t)nblk), ev_first((size_t)nblk),
+      ev_ready((size_t)nblk);
   for (i64 k = 0; k < nblk; ++k) {
-    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_bcast[(size_t)k], cudaEventDisableTiming));
-    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_used[(size_t)k], cudaEventDisableTiming));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fact[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_bcast[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_used[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_first[(size_t)k], evf));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ready[(size_t)k], evf));
   }
   // number of local columns that belong to blocks with index < b
   auto cols_before = [&](i64 b) {
@@ -891,31 +911,48 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
     return cnt;
   };
 
+  // panel k: factored by its owner on sp (in place), packed into W[k % NW], broadcast on sb. The buffer is free once
+  // every local update of step k - NW is done (ev_used on sm; the urgent update of that step precedes it on su).
   auto factor_and_bcast = [&](i64 k) {
     const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
     const int owner = (int)(k % P);
-    double* Wk = W[k & 1];
-    if (k >= 2) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - 2)], 0));
+    double* Wk = W[k % NW];
     if (owner == me) {
       double* pk = A_local + local_off(k, nb, P) * ld + k0;
       VD panel{pk, rows, kb, 1, ld};
       lu_factor_window_f64(wp, panel, 0, kb, d_trans + k0);
+      if (k >= NW) {
+        FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - NW)], 0));
+        if (su != sp && k - NW + 1 < nblk) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_ready[(size_t)(k - NW + 1)], 0));
+      }
       pack(sp, Wk, pk, ld, rows, kb);
+      FB_CUDA_CHECK(cudaEventRecord(ev_fact[(size_t)k], sp));
     }
     if (P > 1) {
+      if (sb != sp) {
+        if (owner == me) FB_CUDA_CHECK(cudaStreamWaitEvent(sb, ev_fact[(size_t)k], 0));
+        else if (k >= NW) {
+          FB_CUDA_CHECK(cudaStreamWaitEvent(sb, ev_used[(size_t)(k - NW)], 0));
+          if (k - NW + 1 < nblk) FB_CUDA_CHECK(cudaStreamWaitEvent(sb, ev_ready[(size_t)(k - NW + 1)], 0));
+        }
+      } else if (owner != me && k >= NW) {
+        FB_CUDA_CHECK(cudaStreamWaitEvent(sb, ev_used[(size_t)(k - NW)], 0));
+      }
       FB_NCCL_CHECK(g_nccl.GroupStart());
-      FB_NCCL_CHECK(g_nccl.Broadcast(Wk, Wk, (size_t)rows * kb, ncclDouble, owner, g_comm, sp));
-      FB_NCCL_CHECK(g_nccl.Broadcast(d_trans + k0, d_trans + k0, (size_t)kb, ncclInt32, owner, g_comm, sp));
+      FB_NCCL_CHECK(g_nccl.Broadcast(Wk, Wk, (size_t)rows * kb, ncclDouble, owner, g_comm, sb));
+      FB_NCCL_CHECK(g_nccl.Broadcast(d_trans + k0, d_trans + k0, (size_t)kb, ncclInt32, owner, g_comm, sb));
       FB_NCCL_CHECK(g_nccl.GroupEnd());
+      FB_CUDA_CHECK(cudaEventRecord(ev_bcast[(size_t)k], sb));
+    } else {
+      FB_CUDA_CHECK(cudaEventRecord(ev_bcast[(size_t)k], sp));
     }
-    FB_CUDA_CHECK(cudaEventRecord(ev_bcast[(size_t)k], sp));
   };
 
   // swaps (+ TRSM/GEMM if `right`) of step k on the local column range [c0, c1)
   auto update_cols = [&](LuWorkspace* w, cudaStream_t st, i64 k, i64 c0, i64 c1, bool right) {
     if (c1 <= c0) return;
     const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
-    const double* Wk = W[k & 1];
+    const double* Wk = W[k % NW];
     VD cols{A_local + c0 * ld + k0, rows, c1 - c0, 1, ld};
     lu_apply_transpositions_f64(w, cols, d_trans + k0, kb);
     if (right) {
@@ -932,8 +969,7 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
   factor_and_bcast(0);
   for (i64 k = 0; k < nblk; ++k) {
     const i64 kb = std::min(nb, n - k * nb);
-    if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_bcast[(size_t)k], 0));
-    const i64 left_end = cols_before(k);                               // blocks < k
+    const i64 left_end = cols_before(k);                                // blocks < k
     const i64 right_begin = left_end + (((int)(k % P) == me) ? kb : 0);  // skip the panel itself on its owner
     i64 sm_right_begin = right_begin;
     const i64 kn = k + 1;
@@ -941,21 +977,53 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
       if ((int)(kn % P) == me) {
         const i64 cb = cols_before(kn);
         const i64 knb = std::min(nb, n - kn * nb);
-        if (two_streams && k >= 1) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - 1)], 0));
-        update_cols(wp, sp, k, cb, cb + knb, true);
+        if (two_streams) {
+          FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_bcast[(size_t)k], 0));
+          // block k+1 received step k-1's update on the bulk stream (first thing it did in that step)
+          if (k >= 1) FB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_first[(size_t)(k - 1)], 0));
+        }
+        update_cols(wu, su, k, cb, cb + knb, true);
+        FB_CUDA_CHECK(cudaEventRecord(ev_ready[(size_t)kn], su));
+        if (su != sp) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_ready[(size_t)kn], 0));
         sm_right_begin = cb + knb;  // block k+1 is my first block to the right of k
+      } else {
+        FB_CUDA_CHECK(cudaEventRecord(ev_ready[(size_t)kn], su));  // nothing urgent here: keeps the event defined
       }
       factor_and_bcast(kn);
     }
+    if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_bcast[(size_t)k], 0));
+    // bulk: my block k+2 first (its owner's urgent stream needs it next), then the rest, then the left columns (swaps only)
+    i64 first_end = sm_right_begin;
+    if (k + 2 < nblk && (int)((k + 2) % P) == me) {
+      const i64 cb2 = cols_before(k + 2);
+      first_end = cb2 + std::min(nb, n - (k + 2) * nb);
+    }
+    update_cols(wm, sm, k, sm_right_begin, first_end, true);
+    FB_CUDA_CHECK(cudaEventRecord(ev_first[(size_t)k], sm));
+    update_cols(wm, sm, k, first_end, ncols_loc, true);
     update_cols(wm, sm, k, 0, left_end, false);
-    update_cols(wm, sm, k, sm_right_begin, ncols_loc, true);
     FB_CUDA_CHECK(cudaEventRecord(ev_used[(size_t)k], sm));
   }
-  if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(nblk - 1)], 0));
   std::vector<int> h_trans((size_t)n);
-  FB_CUDA_CHECK(cudaMemcpyAsync(h_trans.data(), d_trans, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, sp));
+  FB_CUDA_CHECK(cudaStreamSynchronize(sb));
   FB_CUDA_CHECK(cudaStreamSynchronize(sp));
-  if (two_streams) FB_CUDA_CHECK(cudaStreamSynchronize(sm));
+  FB_CUDA_CHECK(cudaStreamSynchronize(su));
+  FB_CUDA_CHECK(cudaStreamSynchronize(sm));
+  FB_CUDA_CHECK(cudaMemcpy(h_trans.data(), d_trans, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (trace && me == 0) {
+    auto at = [&](cudaEvent_t e) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev_start, e) == cudaSuccess) return ms;
+      (void)cudaGetLastError();
+      return -1.f;
+    };
+    fprintf(stderr, "dist LU n=%lld nb=%lld P=%d rank 0 timeline (ms): k: col-ready factored(owner) bcast-done bulk-first bulk-done\n",
+            n, nb, P);
+    for (i64 k = 0; k < nblk; ++k)
+      fprintf(stderr, "  %3lld: %8.3f %8.3f %8.3f %8.3f %8.3f\n", k, k ? at(ev_ready[(size_t)k]) : 0.f,
+              (int)(k % P) == me ? at(ev_fact[(size_t)k]) : -1.f, at(ev_bcast[(size_t)k]), at(ev_first[(size_t)k]),
+              at(ev_used[(size_t)k]));
+  }
   for (i64 i = 0; i < n; ++i) {
     const int t = h_trans[(size_t)i];
     if (t != 0) {
@@ -965,15 +1033,18 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
   }
   for (i64 i = 0; i < n; ++i) perm_inv[perm_fwd[i]] = i;
   for (i64 k = 0; k < nblk; ++k) {
+    cudaEventDestroy(ev_fact[(size_t)k]);
     cudaEventDestroy(ev_bcast[(size_t)k]);
     cudaEventDestroy(ev_used[(size_t)k]);
+    cudaEventDestroy(ev_first[(size_t)k]);
+    cudaEventDestroy(ev_ready[(size_t)k]);
   }
   cudaEventDestroy(ev_start);
   if (wm != wp) lu_ws_destroy(wm);
+  if (wu != wp) lu_ws_destroy(wu);
   lu_ws_destroy(wp);
   ws_free(d_trans);
-  ws_free(W[1]);
-  ws_free(W[0]);
+  for (int i = NW - 1; i >= 0; --i) ws_free(W[i]);
   return n_trans;
 }
 

@@ -145,8 +145,17 @@ __device__ __forceinline__ uint32_t off_k_major(int mn, int kk) {
   return (uint32_t)(mn * 128 + ((((kk >> 1) ^ (mn & 7)) << 4) | ((kk & 1) << 3)));
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, bool SPICY>
-__global__ void __launch_bounds__(THREADS, 2)   // 128 registers per thread at launch, re-divided below
+// VAR (bring-up variants, selected by FAER_B200_WS_VAR): 0 = production; 1 = no setmaxnreg, one CTA per SM; 5 = the kernel as
+// first written (no proxy fence before a stage is released, old dst values through L1), kept to reproduce the failure below.
+//
+// Stage release. The consumers read a stage with ld.shared (generic proxy) and the producer's next TMA load overwrites it
+// through the async proxy: a write-after-read ACROSS proxies, which the mbarrier hand-over alone does not order. Measured
+// (profiles/r02_ws_variants.log): without `fence.proxy.async` before the arrive on `empty[s]`, Add-mode products with two
+// CTAs per SM returned a few wrong 32 x 8 blocks per launch (a warp had read B fragments the next load had already replaced);
+// with the fence, 0 wrong entries in every repetition at the same speed. The old values of dst are read with ld.global.cg:
+// they are used once, and keeping them out of L1 leaves it to nothing at all (the operands arrive by TMA).
+template <bool A_KMAJOR, bool B_KMAJOR, bool SPICY, int VAR = 0>
+__global__ void __launch_bounds__(THREADS, VAR == 1 ? 1 : 2)   // 128 registers per thread at launch, re-divided below
 gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   extern __shared__ uint8_t ws_smem_raw[];
   const uint32_t smem_base = (smem_u32(ws_smem_raw) + 1023u) & ~1023u;
@@ -170,7 +179,7 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   if (warp < 4) {
     // ================= producer warpgroup =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if constexpr (VAR != 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
       uint32_t it = 0;  // global k-step counter: stage = it % STAGES, phase = (it / STAGES) & 1
       for (int i = 0; i < p.tiles_per_cta; ++i) {
@@ -202,7 +211,7 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
 
   // ================= consumer warpgroup =================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  if constexpr (VAR != 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp - 4) * (WMI * 8);  // warp tile rows [wm0, wm0 + 32) x all 64 columns
   // per-lane fragment offsets for the 4 DMMA sub-steps of a stage: k index K4(s, t) = {0,3,12,15}[t] ^ {0,1,4,5}[s]
@@ -281,6 +290,7 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < WNI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
+      if constexpr (VAR != 5) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
@@ -310,7 +320,8 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (c_low && (row < col || (row == col && c_nodiag))) v = false;
           if (c_up && (row > col || (row == col && c_nodiag))) v = false;
           ok[j][e] = v;
-          cv[j][e] = (add && v) ? p.C[roff + coloff(col)] : 0.0;
+          if constexpr (VAR != 5) cv[j][e] = (add && v) ? __ldcg(p.C + roff + coloff(col)) : 0.0;
+          else cv[j][e] = (add && v) ? p.C[roff + coloff(col)] : 0.0;
         }
       }
 #pragma unroll
@@ -408,15 +419,26 @@ inline bool try_gemm_f64_ws(cudaStream_t stream, const GemmF64Params& q, const S
   p.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, 768 / std::max(q.k, 1)));
   const int grid = (int)((tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
   // one opt-in to > 48 KB of dynamic shared memory per kernel variant
-  static bool configured[8] = {false, false, false, false, false, false, false, false};
+  static bool configured[16] = {};
+  static int var = -1, extra_smem = 0;
+  if (var < 0) {
+    const char* e = getenv("FAER_B200_WS_VAR");  // bring-up knob
+    var = e ? atoi(e) : 0;
+    const char* x = getenv("FAER_B200_WS_EXTRA_SMEM");  // bring-up knob: > 14 KB forces one CTA per SM
+    extra_smem = x ? atoi(x) : 0;
+  }
+  const int smem_bytes = SMEM_BYTES + extra_smem;
   auto launch = [&](int which, void (*kern)(CUtensorMap, CUtensorMap, Params)) {
     if (!configured[which]) {
-      FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
       configured[which] = true;
     }
-    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, p);
+    kern<<<grid, THREADS, smem_bytes, stream>>>(mapA, mapB, p);
   };
-  if (!sp) {
+  if (!sp && var != 0 && !ak) {
+    if (var == 1) { if (bk) launch(8, gemm_f64_ws_kernel<false, true, false, 1>); else launch(9, gemm_f64_ws_kernel<false, false, false, 1>); }
+    else { if (bk) launch(10, gemm_f64_ws_kernel<false, true, false, 5>); else launch(11, gemm_f64_ws_kernel<false, false, false, 5>); }
+  } else if (!sp) {
     if (ak && bk) launch(0, gemm_f64_ws_kernel<true, true, false>);
     else if (ak && !bk) launch(1, gemm_f64_ws_kernel<true, false, false>);
     else if (!ak && bk) launch(2, gemm_f64_ws_kernel<false, true, false>);

@@ -65,6 +65,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
 
 // Net effect of transpositions [t0, t1) (rows relative to the view) as a gather list (dst row <- src row), built
 // by ONE WARP. Slots 0..63 are the group's own rows t0..t0+63, pivot rows outside are appended (warp-parallel search).
+template <bool TRANS_IN_SMEM = false>
 __device__ __forceinline__ void build_plan_warp(const int* trans, int t0, int t1, int* ids, int* cur,
                                                 int* __restrict__ out_rows, int* __restrict__ out_src,
                                                 int* __restrict__ out_cnt, int lane) {
@@ -75,7 +76,8 @@ __device__ __forceinline__ void build_plan_warp(const int* trans, int t0, int t1
   __syncwarp();
   int cnt = SWAP_GROUP;
   for (int t = t0; t < t1; ++t) {
-    const int a = t, b = t + __ldcg(trans + t);  // L2 read: may have been written earlier in this kernel
+    // global list: L2 read (it may have been written earlier in this kernel)
+    const int a = t, b = t + (TRANS_IN_SMEM ? trans[t] : __ldcg(trans + t));
     if (a == b) continue;  // uniform
     const int qa = a - t0;
     int qb;
@@ -521,6 +523,340 @@ __global__ void __launch_bounds__(CL_THREADS) lu_panel_cluster_kernel(double* __
   cluster.sync();  // no CTA may exit while its shared memory can still be addressed by the others
 }
 
+// ---- fused sub-panel kernel (one cluster, one launch for up to SP_MAXW columns) -----------------------------------
+// The cluster panel above keeps every row slice in shared memory, so for tall panels its windows are narrow (8 columns
+// at 32768 rows) and the host recursion over them costs more in small launches (row swaps, TRSM leaves, thin GEMMs)
+// than the pivot chain itself (profiles/r01_lu_partition.log: 4.5 - 10 us per column end to end). This kernel factors
+// a whole W-column sub-panel (W <= 256) in ONE launch: the sub-panel stays in global memory (L2-resident: 32768 x 128
+// doubles = 33 MB), only the current window of WW columns is staged in shared memory, and the steps the recursion did
+// with separate launches are done in place, Crout order (each entry is written once):
+//   S1  window columns  -= L[:, 0:j0] * U[0:j0, window]          (row slice per CTA, WW accumulators per thread)
+//   S2  pivot search / swap / rank-1 update of the window, one hardware cluster barrier per column, candidates and rows
+//       exchanged through distributed shared memory (as lu_panel_cluster_kernel, with fewer CTA barriers per column)
+//   S3  the window's transpositions applied to the other columns of the sub-panel (gather plan, columns dealt to CTAs)
+//   S4  rows of U to the right of the window: (A[j0:j0+ww, c] - L[j0:j0+ww, 0:j0] U[0:j0, c]), then the unit-lower
+//       solve with the window's top block (columns dealt to CTAs)
+// Same pivot rule as the reference's scan (largest |a|, lowest row, zeros / NaNs never chosen), same swaps, multipliers
+// by reciprocal-multiply; the floating-point operation ORDER differs from the recursive formulation (as any blocked LU
+// does), which the parity tests cover by comparing permutations exactly and factors to tolerance.
+constexpr int SP_THREADS = 512;
+constexpr int SP_MAXW = 256;  // widest fused sub-panel
+constexpr int SP_MAXWW = 32;  // widest window
+constexpr int SP_CG = 8;      // right-hand columns per S4 chunk
+
+struct SpExchange {
+  double val[2][CL_MAXC];
+  long long idx[2][CL_MAXC];
+  double row[2][CL_MAXC][SP_MAXWW];
+  double diag[2][SP_MAXWW];
+};
+
+template <int WW>
+__global__ void __launch_bounds__(SP_THREADS) lu_subpanel_cluster_kernel(double* __restrict__ A, i64 rs, i64 cs, int m,
+                                                                          int W, int rows_per_cta,
+                                                                          int* __restrict__ trans,
+                                                                          long long* __restrict__ prof) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  constexpr int LD = WW | 1;
+  // dev aid: cycle counts per phase, accumulated by thread 0 of CTA 0 (prof == nullptr in production)
+  long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+  const bool profiling = prof != nullptr && rank == 0 && threadIdx.x == 0;
+  auto tick = [&](int slot) {
+    if (profiling) {
+      const long long now = clock64();
+      pt[slot] += now - tlast;
+      tlast = now;
+    }
+  };
+  extern __shared__ double smem_sp[];
+  double* S = smem_sp;                                  // [rows_per_cta][LD]   window slice
+  double* R1 = S + (size_t)rows_per_cta * LD;           // [W][WW]: S1: U[0:j0, window] (k-major); S4: L rows [ww][j0]
+  double* R2 = R1 + (size_t)W * WW;                     // [W][SP_CG]   S4: U[0:j0, chunk]
+  __shared__ SpExchange X;
+  __shared__ double L11s[SP_MAXWW][SP_MAXWW + 1];
+  __shared__ double X4[SP_MAXWW][SP_CG];
+  __shared__ double red_val[SP_THREADS / 32];
+  __shared__ long long red_idx[SP_THREADS / 32];
+  __shared__ int trans_s[SP_MAXW];
+  __shared__ int p_ids[2 * SWAP_GROUP], p_cur[2 * SWAP_GROUP], p_rows[2 * SWAP_GROUP], p_src[2 * SWAP_GROUP];
+  __shared__ int p_cnt;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = rank * rows_per_cta;
+  const int nloc = max(0, min(rows_per_cta, m - r0));
+  constexpr long long NOIDX = (1ll << 62);
+
+  cluster.sync();  // every CTA of the cluster is resident: its exchange buffer may be written
+  if (profiling) tlast = clock64();
+
+  for (int j0 = 0; j0 < W; j0 += WW) {
+    const int ww = min(WW, W - j0);
+    // ================= S1: stage the window, apply the sub-panel's earlier columns (Crout) =================
+    for (int e = tid; e < j0 * WW; e += SP_THREADS) {
+      const int k = e / WW, c = e - k * WW;
+      R1[e] = c < ww ? __ldcg(A + (i64)k * rs + (i64)(j0 + c) * cs) : 0.0;
+    }
+    __syncthreads();
+    double my_val = 0.0;
+    long long my_idx = -1;
+    for (int r = tid; r < nloc; r += SP_THREADS) {
+      const int gr = r0 + r;
+      double acc[WW];
+      if (gr >= j0) {
+        const double* arow = A + (i64)gr * rs;
+#pragma unroll
+        for (int c = 0; c < WW; ++c) acc[c] = c < ww ? __ldcg(arow + (i64)(j0 + c) * cs) : 0.0;
+        int k = 0;
+        for (; k + 4 <= j0; k += 4) {
+          const double l0 = __ldcg(arow + (i64)k * cs), l1 = __ldcg(arow + (i64)(k + 1) * cs),
+                       l2 = __ldcg(arow + (i64)(k + 2) * cs), l3 = __ldcg(arow + (i64)(k + 3) * cs);
+          const double* u = R1 + (size_t)k * WW;
+#pragma unroll
+          for (int c = 0; c < WW; ++c) acc[c] = fma(-l0, u[c], acc[c]);
+#pragma unroll
+          for (int c = 0; c < WW; ++c) acc[c] = fma(-l1, u[WW + c], acc[c]);
+#pragma unroll
+          for (int c = 0; c < WW; ++c) acc[c] = fma(-l2, u[2 * WW + c], acc[c]);
+#pragma unroll
+          for (int c = 0; c < WW; ++c) acc[c] = fma(-l3, u[3 * WW + c], acc[c]);
+        }
+        for (; k < j0; ++k) {
+          const double l0 = __ldcg(arow + (i64)k * cs);
+          const double* u = R1 + (size_t)k * WW;
+#pragma unroll
+          for (int c = 0; c < WW; ++c) acc[c] = fma(-l0, u[c], acc[c]);
+        }
+        const double v = fabs(acc[0]);
+        if (v > 0.0 && cand_better(v, gr, my_val, my_idx < 0 ? NOIDX : my_idx)) {
+          my_val = v;
+          my_idx = gr;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < WW; ++c) acc[c] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < WW; ++c) S[r * LD + c] = acc[c];
+    }
+    tick(0);
+    // ================= S2: the window's columns =================
+    for (int j = 0; j < ww; ++j) {
+      const int par = j & 1;
+      const int dj = j0 + j;  // global row of the diagonal
+      {
+        double v = my_val;
+        long long ix = my_idx < 0 ? NOIDX : my_idx;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+          const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+          if (cand_better(ov, oi, v, ix)) {
+            v = ov;
+            ix = oi;
+          }
+        }
+        if (lane == 0) {
+          red_val[warp] = v;
+          red_idx[warp] = ix;
+        }
+      }
+      __syncthreads();  // also orders the S stores of S1 / the previous column's update before the row reads below
+      {
+        // every warp reduces the 16 warp candidates redundantly (no second CTA barrier)
+        double v = lane < SP_THREADS / 32 ? red_val[lane] : 0.0;
+        long long ix = lane < SP_THREADS / 32 ? red_idx[lane] : NOIDX;
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+          const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+          if (cand_better(ov, oi, v, ix)) {
+            v = ov;
+            ix = oi;
+          }
+        }
+        v = __shfl_sync(0xffffffffu, v, 0);
+        ix = __shfl_sync(0xffffffffu, ix, 0);
+        // publish to every CTA of the cluster: warp `warp` serves destination rank `warp`
+        if (warp < C) {
+          SpExchange* Xr = cluster.map_shared_rank(&X, warp);
+          if (lane == 0) {
+            Xr->val[par][rank] = v;
+            Xr->idx[par][rank] = ix;
+          }
+          if (v > 0.0) {
+            const int lr = (int)(ix - r0);
+            if (lane < ww) Xr->row[par][rank][lane] = S[lr * LD + lane];
+          }
+          if (dj >= r0 && dj < r0 + nloc) {
+            const int lr = dj - r0;
+            if (lane < ww) Xr->diag[par][lane] = S[lr * LD + lane];
+          }
+        }
+      }
+      tick(1);
+      cluster.sync();
+      tick(2);
+      // winner: every warp scans the C candidates redundantly
+      int piv, wincta;
+      {
+        double v = lane < C ? X.val[par][lane] : 0.0;
+        long long ix = lane < C ? X.idx[par][lane] : NOIDX;
+        int wc = lane;
+        if (!(v > 0.0)) {
+          v = 0.0;
+          ix = NOIDX;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+          const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
+          const int oc = __shfl_xor_sync(0xffffffffu, wc, off);
+          if (cand_better(ov, oi, v, ix)) {
+            v = ov;
+            ix = oi;
+            wc = oc;
+          }
+        }
+        v = __shfl_sync(0xffffffffu, v, 0);
+        ix = __shfl_sync(0xffffffffu, ix, 0);
+        wc = __shfl_sync(0xffffffffu, wc, 0);
+        // an all-zero / all-NaN column keeps imax = row (reference factor.rs:35-44)
+        piv = (v > 0.0) ? (int)ix : dj;
+        wincta = (v > 0.0) ? wc : -1;
+      }
+      const double* prow = (piv != dj) ? X.row[par][wincta] : X.diag[par];
+      const double* drow = X.diag[par];
+      if (piv != dj && warp == 0 && lane < ww) {
+        if (piv >= r0 && piv < r0 + nloc) S[(piv - r0) * LD + lane] = drow[lane];
+        if (dj >= r0 && dj < r0 + nloc) S[(dj - r0) * LD + lane] = prow[lane];
+      }
+      if (tid == 0) {
+        trans_s[dj] = piv - dj;
+        if (rank == 0) trans[dj] = piv - dj;
+      }
+      __syncthreads();
+      // multipliers + rank-1 update of the slice; next column's local arg-max
+      const double inv = 1.0 / prow[j];
+      my_val = 0.0;
+      my_idx = -1;
+      for (int r = tid; r < nloc; r += SP_THREADS) {
+        const int gr = r0 + r;
+        if (gr > dj) {
+          double* row = S + r * LD;
+          const double l = row[j] * inv;
+          row[j] = l;
+          for (int c = j + 1; c < ww; ++c) row[c] = fma(-l, prow[c], row[c]);
+          if (j + 1 < ww) {
+            const double v = fabs(row[j + 1]);
+            if (v > 0.0 && cand_better(v, gr, my_val, my_idx < 0 ? NOIDX : my_idx)) {
+              my_val = v;
+              my_idx = gr;
+            }
+          }
+        }
+      }
+      tick(3);
+    }
+    __syncthreads();
+    // store the window (rows above j0 hold finished U entries written in S4: not ours to touch)
+    for (int r = tid; r < nloc; r += SP_THREADS) {
+      const int gr = r0 + r;
+      if (gr >= j0) {
+        double* dstg = A + (i64)gr * rs + (i64)j0 * cs;
+        const double* srcs = S + r * LD;
+#pragma unroll
+        for (int c = 0; c < WW; ++c)
+          if (c < ww) dstg[(i64)c * cs] = srcs[c];
+      }
+    }
+    const int nother = W - ww;  // columns of the sub-panel outside the window
+    if (nother == 0) break;     // uniform
+    // ================= S3: the window's transpositions on the other columns =================
+    if (warp == 0) build_plan_warp<true>(trans_s, j0, j0 + ww, p_ids, p_cur, p_rows, p_src, &p_cnt, lane);
+    cluster.sync();  // (A) window stores visible cluster-wide; plan visible CTA-wide
+    tick(4);
+    {
+      const int cnt = p_cnt;
+      const int q = tid & (2 * SWAP_GROUP - 1), cb = tid >> 7;  // 128 plan slots x 4 columns in flight
+      const bool act = q < cnt;
+      const i64 srow = act ? (i64)p_src[q] : 0, drow = act ? (i64)p_rows[q] : 0;
+      // my columns: oc = rank, rank + C, ... over the nother other columns
+      for (int base = rank; base < nother; base += 4 * C) {
+        const int oc = base + cb * C;
+        const bool on = act && oc < nother && cnt > 0;
+        const int col = oc < j0 ? oc : oc + ww;
+        double v = 0.0;
+        if (on) v = __ldcg(A + srow * rs + (i64)col * cs);
+        __syncthreads();
+        if (on) A[drow * rs + (i64)col * cs] = v;
+        __syncthreads();
+      }
+    }
+    const int nright = W - j0 - ww;
+    tick(5);
+    if (nright > 0) {
+      cluster.sync();  // (B) swapped rows visible
+      // ================= S4: rows j0 .. j0+ww of U to the right of the window =================
+      // L rows of the window's diagonal block rows against the earlier columns, and the block itself
+      for (int e = tid; e < ww * j0; e += SP_THREADS) {
+        const int i = e / j0, k = e - i * j0;
+        R1[e] = __ldcg(A + (i64)(j0 + i) * rs + (i64)k * cs);  // [i][k], leading dimension j0
+      }
+      for (int e = tid; e < ww * ww; e += SP_THREADS) {
+        const int i = e / ww, i2 = e - i * ww;
+        L11s[i][i2] = __ldcg(A + (i64)(j0 + i) * rs + (i64)(j0 + i2) * cs);
+      }
+      // my right-hand columns: rc = rank, rank + C, ...; SP_CG at a time
+      for (int cbase = rank; cbase < nright; cbase += SP_CG * C) {
+        __syncthreads();
+        for (int e = tid; e < j0 * SP_CG; e += SP_THREADS) {
+          const int cl = e / j0, k = e - cl * j0;  // k fastest: coalesced along the column
+          const int rc = cbase + cl * C;
+          R2[k * SP_CG + cl] = rc < nright ? __ldcg(A + (i64)k * rs + (i64)(j0 + ww + rc) * cs) : 0.0;
+        }
+        __syncthreads();
+        if (tid < ww * SP_CG) {
+          const int i = tid / SP_CG, cl = tid - i * SP_CG;
+          const int rc = cbase + cl * C;
+          double x = 0.0;
+          if (rc < nright) {
+            x = __ldcg(A + (i64)(j0 + i) * rs + (i64)(j0 + ww + rc) * cs);
+            const double* lr = R1 + (size_t)i * j0;
+            for (int k = 0; k < j0; ++k) x = fma(-lr[k], R2[k * SP_CG + cl], x);
+          }
+          X4[i][cl] = x;
+        }
+        __syncthreads();
+        if (tid < SP_CG) {
+          const int cl = tid;
+          const int rc = cbase + cl * C;
+          if (rc < nright) {
+            double xs[SP_MAXWW];
+#pragma unroll
+            for (int i = 0; i < SP_MAXWW; ++i) {
+              if (i < ww) {
+                double x = X4[i][cl];
+#pragma unroll
+                for (int i2 = 0; i2 < SP_MAXWW; ++i2)
+                  if (i2 < i) x = fma(-L11s[i][i2], xs[i2], x);
+                xs[i] = x;
+                A[(i64)(j0 + i) * rs + (i64)(j0 + ww + rc) * cs] = x;
+              }
+            }
+          }
+        }
+      }
+    }
+    cluster.sync();  // (C) U rows / swapped columns visible before the next window reads them
+    tick(6);
+  }
+  if (profiling)
+    for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)prof + i, (unsigned long long)pt[i]);
+  cluster.sync();  // no CTA may exit while its shared memory can still be addressed by the others
+}
+
 __global__ void __launch_bounds__(32) laswp_plan_kernel(const int* __restrict__ trans, int n, int* __restrict__ plan_rows,
                                                         int* __restrict__ plan_src, int* __restrict__ plan_cnt,
                                                         int ngroups) {
@@ -661,6 +997,83 @@ bool launch_panel_cluster(LuCtx& ctx, VD P, int* trans, bool want_plan) {
   return true;
 }
 
+// dev aid (FAER_B200_LU_SUBPANEL_PROF=1): 8 cycle counters accumulated by the fused sub-panel kernel, printed at exit
+long long* g_subpanel_prof = nullptr;
+void subpanel_prof_report() {
+  if (!g_subpanel_prof) return;
+  long long h[8];
+  if (cudaMemcpy(h, g_subpanel_prof, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  const char* names[8] = {"S1 stage+crout", "S2 reduce+publish", "S2 cluster.sync", "S2 swap+update", "store+plan+sync A",
+                          "S3 swaps", "S4 + syncs B,C", "-"};
+  fprintf(stderr, "faer_b200: fused LU sub-panel cycles (CTA 0 thread 0, all launches):");
+  for (int i = 0; i < 7; ++i) fprintf(stderr, "  %s %.3f Mcyc", names[i], (double)h[i] * 1e-6);
+  fprintf(stderr, "\n");
+}
+
+// Fused sub-panel (one cluster launch for the whole window); returns false when it does not apply here.
+int subpanel_max_width() {
+  static int w = -1;
+  if (w < 0) {
+    const char* e = getenv("FAER_B200_LU_FUSED_W");  // 0 disables the fused sub-panel kernel
+    w = e ? atoi(e) : 128;
+    if (w > SP_MAXW) w = SP_MAXW;
+  }
+  return w;
+}
+
+template <int WW>
+cudaError_t launch_subpanel_t(LuCtx& ctx, VD P, int* trans, int rows_per_cta, size_t smem) {
+  const int C = ctx.cluster_ctas;
+  static bool configured = false;
+  if (!g_subpanel_prof && getenv("FAER_B200_LU_SUBPANEL_PROF")) {
+    FB_CUDA_CHECK(cudaMalloc(&g_subpanel_prof, 64));
+    FB_CUDA_CHECK(cudaMemset(g_subpanel_prof, 0, 64));
+    atexit(subpanel_prof_report);
+  }
+  if (!configured) {
+    FB_CUDA_CHECK(cudaFuncSetAttribute(lu_subpanel_cluster_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM_BUDGET));
+    FB_CUDA_CHECK(cudaFuncSetAttribute(lu_subpanel_cluster_kernel<WW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C);
+  cfg.blockDim = dim3(SP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx.st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  double* Aptr = P.ptr;
+  i64 rs = P.rs, cs = P.cs;
+  int m = (int)P.nrows, W = (int)P.ncols;
+  long long* prof = g_subpanel_prof;
+  return cudaLaunchKernelEx(&cfg, lu_subpanel_cluster_kernel<WW>, Aptr, rs, cs, m, W, rows_per_cta, trans, prof);
+}
+
+bool launch_subpanel(LuCtx& ctx, VD P, int* trans) {
+  const int C = ctx.cluster_ctas;
+  const i64 m = P.nrows, W = P.ncols;
+  if (C <= 0 || W > subpanel_max_width() || W > m) return false;
+  const int rows_per_cta = (int)((m + C - 1) / C);
+  auto bytes = [&](int ww) { return ((size_t)rows_per_cta * (size_t)(ww | 1) + (size_t)W * ww + (size_t)W * SP_CG) * sizeof(double); };
+  cudaError_t e;
+  if (bytes(32) <= (size_t)CL_SMEM_BUDGET) e = launch_subpanel_t<32>(ctx, P, trans, rows_per_cta, bytes(32));
+  else if (bytes(16) <= (size_t)CL_SMEM_BUDGET) e = launch_subpanel_t<16>(ctx, P, trans, rows_per_cta, bytes(16));
+  else if (bytes(8) <= (size_t)CL_SMEM_BUDGET) e = launch_subpanel_t<8>(ctx, P, trans, rows_per_cta, bytes(8));
+  else return false;
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    fprintf(stderr, "faer_b200: fused LU sub-panel launch failed (%s, %d CTAs); using the recursion\n", cudaGetErrorString(e), C);
+    return false;
+  }
+  note_launch();
+  return true;
+}
+
 void launch_panel(LuCtx& ctx, VD P, int* trans, bool want_plan) {
   if (launch_panel_cluster(ctx, P, trans, want_plan)) return;
   const int m = (int)P.nrows, w = (int)P.ncols;
@@ -706,6 +1119,17 @@ void lu_rec(LuCtx& ctx, VD A, i64 start, i64 end, int* trans) {
     if (has_outside) {
       apply_plan(ctx, A.sub(0, 0, m, start), 1);
       apply_plan(ctx, A.sub(0, end, m, ncols - end), 1);
+    }
+    return;
+  }
+  if (launch_subpanel(ctx, A.sub(0, start, m, n), trans)) {
+    if (has_outside) {
+      const int ngroups = (int)((n + SWAP_GROUP - 1) / SWAP_GROUP);
+      laswp_plan_kernel<<<ngroups, 32, 0, ctx.st>>>(trans, (int)n, ctx.plan_rows, ctx.plan_src, ctx.plan_cnt, ngroups);
+      FB_CUDA_CHECK(cudaGetLastError());
+      note_launch();
+      apply_plan(ctx, A.sub(0, 0, m, start), ngroups);
+      apply_plan(ctx, A.sub(0, end, m, ncols - end), ngroups);
     }
     return;
   }

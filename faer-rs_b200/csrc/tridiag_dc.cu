@@ -353,6 +353,17 @@ bool tridiag_dc_f64(cudaStream_t st, const double* d_in, const double* e_in, i64
   if (n > 1) FB_CUDA_CHECK(cudaMemcpyAsync(b.e, e_in, (nd - 1) * 8, cudaMemcpyDeviceToDevice, st));
   dc_scale_kernel<<<1, 256, 0, st>>>(b.d, b.e, (int)n, b.scale);
   note_launch();
+  {
+    // non-finite input: stop here (the reference returns NoConvergence, svd/mod.rs:282-286); NaNs in the deflation /
+    // sorting stages would otherwise turn into wild indices
+    double h_sc[2] = {1.0, 0.0};
+    FB_CUDA_CHECK(cudaMemcpyAsync(h_sc, b.scale, 16, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_sc[1] != 0.0) {
+      ws_free(pool);
+      return false;
+    }
+  }
   if (!merges.empty()) {
     dc_tear_kernel<<<(unsigned)((merges.size() + 127) / 128), 128, 0, st>>>(b.d, b.e, d_merges, (int)merges.size(), b.rho, b.sgn);
     note_launch();

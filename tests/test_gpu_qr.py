@@ -93,13 +93,20 @@ def _check_rank_deficient(la, oracle, A, bs, rank_true, dtype):
     sc = max(1.0, float(np.abs(A).max()))
     tol = 128 * u * np.sqrt(8 * max(m, n)) * sc * 4
     Q = form_q(la, QR, H)
-    assert np.all(np.abs(Q @ np.triu(QR) - A) <= tol), key
+    # a column the rank test drops keeps a remainder of norm <= its threshold eps * 16 * (m - row) * ||column|| (factor.rs:52-59)
+    # below the staircase, which Q R does not reproduce: that bound is part of the contract (visible in f32, where it exceeds
+    # the backward-error tolerance of the kept columns)
+    dropped = 16.0 * m * u * np.linalg.norm(A.astype(np.float64), axis=0)[None, :]
+    assert np.all(np.abs(Q @ np.triu(QR) - A) <= tol + dropped), key
     assert np.all(np.abs(Q.T @ Q - np.eye(m)) <= tol), key
     if rank != rank_o:
         # both are legal outcomes: reflectors beyond the true rank come from rounding noise (a column whose remaining part is
         # noise passes or fails the threshold, or has an exactly zero tail and advances `row` with an identity reflector,
         # factor.rs:60-63, depending on the summation order). The reference's own test only asks for rank >= true rank.
-        assert abs(rank - rank_o) <= max(2, size // 50) and min(rank, rank_o) >= min(rank_true, size), key
+        # (tiny problems: after the first reflector of a rank-1 4 x 20 f32 matrix every tail is either exactly zero or noise, so
+        # anything between the true rank and `size` is legal)
+        slack = size if size <= 8 else max(2, size // 50)
+        assert abs(rank - rank_o) <= slack and min(rank, rank_o) >= min(rank_true, size), key
         return  # the reference's criterion above is all that applies then
     loose = 4e3 * u * max(m, n)
     assert np.allclose(np.triu(QR)[:size], np.triu(QRo)[:size], rtol=loose, atol=loose * sc), key
