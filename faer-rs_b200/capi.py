@@ -345,6 +345,10 @@ def load() -> C.CDLL:
     lib.faer_b200_spicy_matmul_f64.argtypes = [MatMut, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, MatRef,
                                                MatRef, C.c_void_p, C.c_void_p]
     lib.faer_b200_spicy_matmul_f64.restype = None
+    lib.faer_b200_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_ssize_t, C.c_ssize_t,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_ssize_t, C.c_bool, C.c_void_p,
+                                   C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_ssize_t, C.c_bool, C.c_void_p, C.c_size_t]
+    lib.faer_b200_gemm.restype = None
     lib.faer_b200_set_option.argtypes = [C.c_char_p, C.c_longlong]
     lib.faer_b200_set_option.restype = C.c_int
     lib.faer_b200_get_option.argtypes = [C.c_char_p]

@@ -284,7 +284,8 @@ void libfaer_v0_23_matmul_triangular_f32(FaerV0_24_MatMut C, FaerV0_24_Block C_b
 
 // ---- c64 matmul (interleaved complex<f64>; `alpha` points to a complex scalar) ----
 static void matmul_c64_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum accum, FaerV0_24_MatRef A, int A_block,
-                            FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha) {
+                            FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha, bool conj_a = false,
+                            bool conj_b = false) {
   FB_ENTRY();
   FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
   cudaStream_t st = current_stream();
@@ -301,7 +302,7 @@ static void matmul_c64_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum acc
   VD dv = as_c(c);
   VD lv0 = as_c(l), rv0 = as_c(r);
   // view<double>() scaled pointer arithmetic by 8 bytes, but strides are in complex units: rebuild from the raw pointer
-  gemm_c64(st, dv, C_block, accum == FaerV0_24_Accum_Add ? 1 : 0, cv(lv0), A_block, false, cv(rv0), B_block, false, a[0],
+  gemm_c64(st, dv, C_block, accum == FaerV0_24_Accum_Add ? 1 : 0, cv(lv0), A_block, conj_a, cv(rv0), B_block, conj_b, a[0],
            a[1]);
   finish_all(st, {&c, &l, &r});
 }
@@ -318,7 +319,8 @@ void libfaer_v0_23_matmul_triangular_c64(FaerV0_24_MatMut C, FaerV0_24_Block C_b
 }
 
 static void matmul_c32_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum accum, FaerV0_24_MatRef A, int A_block,
-                            FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha) {
+                            FaerV0_24_MatRef B, int B_block, const FaerV0_24_Scalar* alpha, bool conj_a = false,
+                            bool conj_b = false) {
   FB_ENTRY();
   FB_ASSERT(C.nrows == A.nrows && C.ncols == B.ncols && A.ncols == B.nrows, "matmul shape mismatch");
   cudaStream_t st = current_stream();
@@ -333,7 +335,7 @@ static void matmul_c32_impl(FaerV0_24_MatMut C, int C_block, FaerV0_24_Accum acc
   StagedMat r(B.ptr, (i64)B.nrows, (i64)B.ncols, (i64)B.row_stride, (i64)B.col_stride, 8, true, false, st);
   VF dv = c.view<float>();
   VF lv0 = l.view<float>(), rv0 = r.view<float>();
-  gemm_c32(st, dv, C_block, accum == FaerV0_24_Accum_Add ? 1 : 0, cv(lv0), A_block, false, cv(rv0), B_block, false, a[0],
+  gemm_c32(st, dv, C_block, accum == FaerV0_24_Accum_Add ? 1 : 0, cv(lv0), A_block, conj_a, cv(rv0), B_block, conj_b, a[0],
            a[1]);
   finish_all(st, {&c, &l, &r});
 }
@@ -1054,6 +1056,82 @@ void faer_b200_spicy_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Block C_block, con
   if (dri && dri != (void*)row_idx) ws_free(dri);
   if (dci && dci != (void*)col_idx) ws_free(dci);
   if (dd && dd != (void*)D) ws_free(dd);
+}
+
+// ---- inner seam: the type-erased product call faer makes in three places (private_gemm_x86::gemm at
+// faer/src/linalg/matmul/mod.rs:1373-1411, matmul/triangular.rs:641-680, matmul/internal/mod.rs:143-201), same parameter list.
+void faer_b200_gemm(int dtype, int itype, int instr_set, size_t m, size_t n, size_t k, void* dst, ptrdiff_t dst_rs, ptrdiff_t dst_cs,
+                    const void* row_idx, const void* col_idx, int dst_kind, int accum, const void* lhs, ptrdiff_t lhs_rs,
+                    ptrdiff_t lhs_cs, bool conj_lhs, const void* diag, ptrdiff_t diag_stride, const void* rhs, ptrdiff_t rhs_rs,
+                    ptrdiff_t rhs_cs, bool conj_rhs, const void* alpha, size_t n_threads) {
+  (void)instr_set; (void)n_threads;
+  FB_ASSERT(dtype >= 0 && dtype <= 3, "faer_b200_gemm: dtype must be FaerB200_GemmDType_{F32,F64,C32,C64}");
+  FB_ASSERT(dst_kind >= 0 && dst_kind <= 2, "faer_b200_gemm: dst_kind must be FaerB200_GemmDstKind_{Lower,Upper,Full}");
+  const FaerV0_24_Accum acc = accum ? FaerV0_24_Accum_Add : FaerV0_24_Accum_Replace;
+  const int block = dst_kind == FaerB200_GemmDstKind_Full ? (int)FaerV0_24_Block_Rectangular
+                                                          : dst_kind == FaerB200_GemmDstKind_Lower ? (int)FaerV0_24_Block_TriangularLower
+                                                                                                   : (int)FaerV0_24_Block_TriangularUpper;
+  if (block != (int)FaerV0_24_Block_Rectangular) FB_ASSERT(m == n, "faer_b200_gemm: a triangular destination is square");
+  const bool plain = !row_idx && !col_idx && !diag;
+  FaerV0_24_MatRef A{lhs, m, k, lhs_rs, lhs_cs}, B{rhs, k, n, rhs_rs, rhs_cs};
+  if (plain && dtype != FaerB200_GemmDType_F64) {
+    FaerV0_24_MatMut C{dst, m, n, dst_rs, dst_cs};
+    const FaerV0_24_Scalar* a = (const FaerV0_24_Scalar*)alpha;
+    if (dtype == FaerB200_GemmDType_F32) matmul_f32_impl(C, block, acc, A, 0, B, 0, a);
+    else if (dtype == FaerB200_GemmDType_C64) matmul_c64_impl(C, block, acc, A, 0, B, 0, a, conj_lhs, conj_rhs);
+    else matmul_c32_impl(C, block, acc, A, 0, B, 0, a, conj_lhs, conj_rhs);
+    return;
+  }
+  FB_ASSERT(dtype == FaerB200_GemmDType_F64, "faer_b200_gemm: scatter indices / diagonal scaling are built for f64 only");
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  // index arrays as 64-bit device arrays; the destination's extent is what the indices reach
+  auto host_idx = [&](const void* p, size_t cnt) {
+    std::vector<unsigned long long> v(cnt);
+    if (!p) return v;
+    const size_t w = itype == FaerB200_GemmIType_U32 ? 4 : 8;
+    std::vector<unsigned char> raw(cnt * w);
+    if (is_device_pointer(p)) FB_CUDA_CHECK(cudaMemcpy(raw.data(), p, raw.size(), cudaMemcpyDeviceToHost));
+    else memcpy(raw.data(), p, raw.size());
+    for (size_t i = 0; i < cnt; ++i) v[i] = w == 4 ? (unsigned long long)((const uint32_t*)raw.data())[i] : ((const uint64_t*)raw.data())[i];
+    return v;
+  };
+  const std::vector<unsigned long long> ri = host_idx(row_idx, m), ci = host_idx(col_idx, n);
+  size_t c_rows = m, c_cols = n;
+  if (row_idx) { c_rows = 0; for (auto x : ri) c_rows = std::max<size_t>(c_rows, (size_t)x + 1); }
+  if (col_idx) { c_cols = 0; for (auto x : ci) c_cols = std::max<size_t>(c_cols, (size_t)x + 1); }
+  auto to_dev = [&](const void* p, size_t bytes) -> void* {
+    if (bytes == 0) return nullptr;
+    void* d = ws_alloc(bytes);
+    FB_CUDA_CHECK(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, st));
+    return d;
+  };
+  void* dri = row_idx ? to_dev(ri.data(), m * 8) : nullptr;
+  void* dci = col_idx ? to_dev(ci.data(), n * 8) : nullptr;
+  // diagonal: device pointers are used in place (with their stride), host ones are gathered into a compact device copy
+  const double* dd = (const double*)diag;
+  void* dd_own = nullptr;
+  i64 dstride = (i64)diag_stride;
+  std::vector<double> hd;
+  if (diag && !is_device_pointer(diag)) {
+    hd.resize(k);
+    for (size_t q = 0; q < k; ++q) hd[q] = ((const double*)diag)[(ptrdiff_t)q * diag_stride];
+    dd_own = to_dev(hd.data(), k * 8);
+    dd = (const double*)dd_own;
+    dstride = 1;
+  }
+  const double a = read_scalar_f64((const FaerV0_24_Scalar*)alpha);
+  FaerV0_24_MatMut C{dst, c_rows, c_cols, dst_rs, dst_cs};
+  const bool keep_old = accum != 0 || row_idx || col_idx || block != (int)FaerV0_24_Block_Rectangular;
+  Mat c(C, keep_old, st);
+  Mat l(A, st), r(B, st);
+  if (m > 0 && n > 0)
+    spicy_matmul_f64(st, c.s.view<double>(), block, (const long long*)dri, (const long long*)dci, accum ? 1 : 0,
+                     l.s.view<const double>(), r.s.view<const double>(), dd, dstride, a);
+  finish_all(st, {&c.s, &l.s, &r.s});  // synchronises the stream: the host vectors above may go
+  if (dri) ws_free(dri);
+  if (dci) ws_free(dci);
+  if (dd_own) ws_free(dd_own);
 }
 
 int faer_b200_set_option(const char* name, long long value) { return set_option_by_name(name, value) ? 0 : -1; }

@@ -483,8 +483,16 @@ void gemm_f64(cudaStream_t stream, VD dst, int dst_struct, int accum, VCD lhs, i
   }
   // large rectangular-operand products: the TMA-fed warp-specialised kernel (gemm_f64_ws.cuh)
   if (ws_mode() != 0 && !split_ws) {
-    const long long tiles_ws = (long long)((p.m + ws64::BM - 1) / ws64::BM) * ((p.n + ws64::BN - 1) / ws64::BN);
-    if ((ws_mode() == 2 || (tiles_ws >= 96 && p.k >= 32))) {
+    // Heuristic (profiles/r02_ws_shapes.log, one B200): the ws kernel wins where its 128 x 64 tiles fill >= 3 waves of two
+    // CTAs per SM and the contraction is deep enough to amortise a tile's epilogue: 34.1 vs 30.8 TFLOP/s on the LU update
+    // (k = 512), 32.5 vs 31.2 on the lower-triangular update at k = 512, 36.5 vs 31.8 on square products; the cp.async
+    // kernel (64 x 64 tiles, three CTAs per SM) keeps short contractions into a triangular destination (k = 256: 29.9 vs
+    // 29.4) and products with few tiles (16384 x 256 x 256: 19.8 vs 13.7).
+    long long tiles_ws = (long long)((p.m + ws64::BM - 1) / ws64::BM) * ((p.n + ws64::BN - 1) / ws64::BN);
+    if (dst_struct != RECT) tiles_ws = tiles_ws / 2 + 1;
+    const long long wave = 2ll * stream_sms(stream);
+    const bool deep = dst_struct == RECT ? p.k >= 256 : p.k >= 512;
+    if (ws_mode() == 2 || (tiles_ws >= 3 * wave && deep)) {
       if (prof) profile_record_start(stream);
       const bool took = ws64::try_gemm_f64_ws(stream, p);
       if (took) {

@@ -12,7 +12,7 @@
 //     turn over and a higher-priority stream — the panel chain of the look-ahead factorizations — gets in), 2 per SM,
 //     each with a producer warpgroup (one working warp) and a consumer warpgroup of 4 warps;
 //     CTA tile 128 x 64, warp tile 32 x 64 (64 accumulator doubles = 128 registers per thread), 16-deep k-steps. The
-//     register file is re-divided at run time with setmaxnreg (producer warpgroup 40, consumers 216 registers per thread);
+//     register file is re-divided at run time with setmaxnreg (producer warpgroup 24, consumers 232 registers per thread);
 //   * producer: one elected lane issues cp.async.bulk.tensor (TMA, SASS UTMALDG) loads of both operand slabs into a
 //     4-stage ring of 128B-swizzled shared-memory tiles and signals `full[s]` through the mbarrier's transaction count;
 //     out-of-range rows / columns / k are zero-filled by the TMA unit (no predication in the loop);
@@ -87,6 +87,12 @@ struct Params {
   double alpha;
   int tiles_m, tiles_n;
   int tiles_per_cta;
+  // Stagger of the two CTAs that share an SM: both start together and their tiles take the same time, so without it they
+  // reach their epilogues together and the DMMA pipe idles (ncu, k = 256: tensor pipe 78.7 % active). The second-slot CTAs of
+  // the first wave (blockIdx in [sm_slots, 2 sm_slots)) start their first tile half a tile late; their successors inherit
+  // the phase because a CTA is replaced when its predecessor on the same SM exits.
+  int sm_slots;          // SMs the launch can use (stream's partition)
+  long long stagger_cycles;  // 0 = off
   // "spicy" variant (matmul/internal/mod.rs:45-379): dst[row_idx[i], col_idx[j]] (+)= alpha (A diag(d) B)[i, j]
   const long long* row_idx;  // device, m entries, or null
   const long long* col_idx;  // device, n entries, or null
@@ -179,7 +185,7 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   if (warp < 4) {
     // ================= producer warpgroup =================
-    if constexpr (VAR != 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if constexpr (VAR != 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (warp == 0 && lane == 0) {
       uint32_t it = 0;  // global k-step counter: stage = it % STAGES, phase = (it / STAGES) & 1
       for (int i = 0; i < p.tiles_per_cta; ++i) {
@@ -211,7 +217,7 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
 
   // ================= consumer warpgroup =================
-  if constexpr (VAR != 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  if constexpr (VAR != 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp - 4) * (WMI * 8);  // warp tile rows [wm0, wm0 + 32) x all 64 columns
   // per-lane fragment offsets for the 4 DMMA sub-steps of a stage: k index K4(s, t) = {0,3,12,15}[t] ^ {0,1,4,5}[s]
@@ -243,6 +249,11 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const bool c_nodiag = is_strict(cs_) || is_unit(cs_);
   const double alpha = p.alpha;
   const bool add = p.accum != 0;
+
+  if (p.stagger_cycles > 0 && (int)blockIdx.x >= p.sm_slots && (int)blockIdx.x < 2 * p.sm_slots) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.stagger_cycles) __nanosleep(256);
+  }
 
   uint32_t it = 0;
   for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
@@ -295,41 +306,52 @@ gemm_f64_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       if (lane == 0) mbar_arrive(&empty[s]);
     }
 
-    // ---- epilogue: dst = [dst +] alpha * acc, masked by dst structure and bounds ----
+    // ---- epilogue: dst = [dst +] alpha * acc, masked by dst structure and bounds. Add mode: the old values of row block
+    // i + 1 are requested before row block i is combined and stored (two register sets), so the four row blocks cost about
+    // two global-memory round trips instead of four ----
+    auto coloff = [&](int col) -> i64 {
+      if constexpr (SPICY) {
+        if (p.col_idx) return col < p.n ? (i64)p.col_idx[col] * p.c_cs : 0;
+      }
+      return (i64)col * p.c_cs;
+    };
+    auto rowoff = [&](int row) -> i64 {
+      if constexpr (SPICY) {
+        if (p.row_idx) return row < p.m ? (i64)p.row_idx[row] * p.c_rs : 0;
+      }
+      return (i64)row * p.c_rs;
+    };
+    auto kept = [&](int row, int col) -> bool {
+      bool v = row < p.m && col < p.n;
+      if (c_low && (row < col || (row == col && c_nodiag))) v = false;
+      if (c_up && (row > col || (row == col && c_nodiag))) v = false;
+      return v;
+    };
+    double cv[2][WNI][2];
+    auto load_old = [&](int i, double (&dst)[WNI][2]) {
+      const int row = m0 + wm0 + i * 8 + g;
+      const i64 roff = rowoff(row);
+#pragma unroll
+      for (int j = 0; j < WNI; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = n0 + j * 8 + 2 * t + e;
+          if constexpr (VAR != 5) dst[j][e] = kept(row, col) ? __ldcg(p.C + roff + coloff(col)) : 0.0;
+          else dst[j][e] = kept(row, col) ? p.C[roff + coloff(col)] : 0.0;
+        }
+    };
+    if (add) load_old(0, cv[0]);
 #pragma unroll
     for (int i = 0; i < WMI; ++i) {
+      if (add && i + 1 < WMI) load_old(i + 1, cv[(i + 1) & 1]);
       const int row = m0 + wm0 + i * 8 + g;
-      i64 roff = (i64)row * p.c_rs;
-      if constexpr (SPICY) {
-        if (p.row_idx) roff = row < p.m ? (i64)p.row_idx[row] * p.c_rs : 0;
-      }
-      double cv[WNI][2];
-      bool ok[WNI][2];
-      auto coloff = [&](int col) -> i64 {
-        if constexpr (SPICY) {
-          if (p.col_idx) return col < p.n ? (i64)p.col_idx[col] * p.c_cs : 0;
-        }
-        return (i64)col * p.c_cs;
-      };
+      const i64 roff = rowoff(row);
 #pragma unroll
       for (int j = 0; j < WNI; ++j) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = n0 + j * 8 + 2 * t + e;
-          bool v = row < p.m && col < p.n;
-          if (c_low && (row < col || (row == col && c_nodiag))) v = false;
-          if (c_up && (row > col || (row == col && c_nodiag))) v = false;
-          ok[j][e] = v;
-          if constexpr (VAR != 5) cv[j][e] = (add && v) ? __ldcg(p.C + roff + coloff(col)) : 0.0;
-          else cv[j][e] = (add && v) ? p.C[roff + coloff(col)] : 0.0;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < WNI; ++j) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = n0 + j * 8 + 2 * t + e;
-          if (ok[j][e]) p.C[roff + coloff(col)] = alpha * acc[i][j][e] + cv[j][e];
+          if (kept(row, col)) p.C[roff + coloff(col)] = add ? (alpha * acc[i][j][e] + cv[i & 1][j][e]) : alpha * acc[i][j][e];
         }
       }
     }
@@ -418,6 +440,16 @@ inline bool try_gemm_f64_ws(cudaStream_t stream, const GemmF64Params& q, const S
   // a tile takes ~0.13 us per unit of k on half an SM: ~100 us per CTA
   p.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, 768 / std::max(q.k, 1)));
   const int grid = (int)((tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
+  {
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* e = getenv("FAER_B200_WS_STAGGER");  // 0 switches the stagger off (dev knob)
+      stagger = e ? atoi(e) : 1;
+    }
+    p.sm_slots = stream_sms(stream);
+    // half a tile at the full rate of one SM: (k / 16) k-steps x 512 DMMA x 4 clocks / 2
+    p.stagger_cycles = (stagger && grid >= 2 * p.sm_slots) ? (long long)((q.k + BK - 1) / BK) * 1024 : 0;
+  }
   // one opt-in to > 48 KB of dynamic shared memory per kernel variant
   static bool configured[16] = {};
   static int var = -1, extra_smem = 0;

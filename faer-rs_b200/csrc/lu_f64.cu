@@ -528,14 +528,17 @@ __global__ void __launch_bounds__(CL_THREADS) lu_panel_cluster_kernel(double* __
 // at 32768 rows) and the host recursion over them costs more in small launches (row swaps, TRSM leaves, thin GEMMs)
 // than the pivot chain itself (profiles/r01_lu_partition.log: 4.5 - 10 us per column end to end). This kernel factors
 // a whole W-column sub-panel (W <= 256) in ONE launch: the sub-panel stays in global memory (L2-resident: 32768 x 128
-// doubles = 33 MB), only the current window of WW columns is staged in shared memory, and the steps the recursion did
-// with separate launches are done in place, Crout order (each entry is written once):
-//   S1  window columns  -= L[:, 0:j0] * U[0:j0, window]          (row slice per CTA, WW accumulators per thread)
+// doubles = 33 MB), the current window of WW columns lives in REGISTERS (thread t of a CTA owns the rows t, t + 512, ...
+// of the CTA's slice: R rows x WW columns, R * WW = 32 doubles), and the steps the recursion did with separate launches
+// are done in place, Crout order (each entry is written once):
+//   S1  window columns  -= L[:, 0:j0] * U[0:j0, window]          (R x WW accumulators per thread, U block in shared memory)
 //   S2  pivot search / swap / rank-1 update of the window, one hardware cluster barrier per column, candidates and rows
-//       exchanged through distributed shared memory (as lu_panel_cluster_kernel, with fewer CTA barriers per column)
+//       exchanged through distributed shared memory; the column loop is fully unrolled so the window stays in registers
 //   S3  the window's transpositions applied to the other columns of the sub-panel (gather plan, columns dealt to CTAs)
 //   S4  rows of U to the right of the window: (A[j0:j0+ww, c] - L[j0:j0+ww, 0:j0] U[0:j0, c]), then the unit-lower
 //       solve with the window's top block (columns dealt to CTAs)
+// First version (window slice in shared memory, profiles/r02_lu_subpanel_phases.log): 5.0 us per column at 16384 rows, of
+// which 1.1 us in the shared-memory rank-1 update and 0.5 us in a Crout pass with 4 loads in flight per thread.
 // Same pivot rule as the reference's scan (largest |a|, lowest row, zeros / NaNs never chosen), same swaps, multipliers
 // by reciprocal-multiply; the floating-point operation ORDER differs from the recursive formulation (as any blocked LU
 // does), which the parity tests cover by comparing permutations exactly and factors to tolerance.
@@ -544,253 +547,354 @@ constexpr int SP_MAXW = 256;  // widest fused sub-panel
 constexpr int SP_MAXWW = 32;  // widest window
 constexpr int SP_CG = 8;      // right-hand columns per S4 chunk
 
-struct SpExchange {
-  double val[2][CL_MAXC];
-  long long idx[2][CL_MAXC];
-  double row[2][CL_MAXC][SP_MAXWW];
-  double diag[2][SP_MAXWW];
+// One candidate record as it travels between CTAs: 16-byte header + the candidate row (always SP_MAXWW slots, WW sent)
+struct alignas(16) SpRec {
+  double val;
+  long long idx;
+  double row[SP_MAXWW];
 };
 
-template <int WW>
+// ---- cluster exchange primitives: bulk shared -> remote-shared copies that signal the DESTINATION's mbarrier ----
+__device__ __forceinline__ uint32_t sp_mapa(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void sp_bulk_to_cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void sp_mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sp_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// Warp-wide (value, row) arg-max with the reference's tie rule (largest value, lowest row), result in every lane.
+// v >= 0 and not NaN (0 = "no candidate"); the bit pattern of a non-negative double orders like the value, so the maximum is
+// found with two 32-bit integer reductions and the lowest row among the lanes that hold it with a third.
+__device__ __forceinline__ void warp_argmax(double& v, int& ix) {
+  const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  const bool top = hi == mh && lo == ml;
+  const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)ix : 0xffffffffu);
+  v = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  ix = (int)mi;
+}
+
+template <int WW, int R>
 __global__ void __launch_bounds__(SP_THREADS) lu_subpanel_cluster_kernel(double* __restrict__ A, i64 rs, i64 cs, int m,
                                                                           int W, int rows_per_cta,
                                                                           int* __restrict__ trans,
+                                                                          int* __restrict__ plan_rows,
+                                                                          int* __restrict__ plan_src,
+                                                                          int* __restrict__ plan_cnt,
                                                                           long long* __restrict__ prof) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-  constexpr int LD = WW | 1;
   // dev aid: cycle counts per phase, accumulated by thread 0 of CTA 0 (prof == nullptr in production)
-  long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+  __shared__ long long pt[9];  // [8] = time of the last tick
   const bool profiling = prof != nullptr && rank == 0 && threadIdx.x == 0;
+  if (profiling)
+    for (int i = 0; i < 9; ++i) pt[i] = 0;
   auto tick = [&](int slot) {
     if (profiling) {
       const long long now = clock64();
-      pt[slot] += now - tlast;
-      tlast = now;
+      pt[slot] += now - pt[8];
+      pt[8] = now;
     }
   };
   extern __shared__ double smem_sp[];
-  double* S = smem_sp;                                  // [rows_per_cta][LD]   window slice
-  double* R1 = S + (size_t)rows_per_cta * LD;           // [W][WW]: S1: U[0:j0, window] (k-major); S4: L rows [ww][j0]
-  double* R2 = R1 + (size_t)W * WW;                     // [W][SP_CG]   S4: U[0:j0, chunk]
-  __shared__ SpExchange X;
+  double* R1 = smem_sp;                  // [W][WW]: S1: U[0:j0, window] (k-major); S4: L rows [ww][j0]
+  double* R2 = R1 + (size_t)W * WW;      // [W][SP_CG]   S4: U[0:j0, chunk]
+  __shared__ SpRec Xrec[2][CL_MAXC];                 // received candidate records [parity][source CTA]
+  __shared__ alignas(16) double Xdiag[2][SP_MAXWW];  // received diagonal row [parity]
+  __shared__ SpRec rec_s[2];                         // send staging [parity]
+  __shared__ alignas(16) double diag_s[2][SP_MAXWW];
+  __shared__ alignas(8) unsigned long long xbar[2];  // one mbarrier per parity: all of a column's records have landed
   __shared__ double L11s[SP_MAXWW][SP_MAXWW + 1];
   __shared__ double X4[SP_MAXWW][SP_CG];
   __shared__ double red_val[SP_THREADS / 32];
-  __shared__ long long red_idx[SP_THREADS / 32];
+  __shared__ int red_idx[SP_THREADS / 32];
   __shared__ int trans_s[SP_MAXW];
-  __shared__ int p_ids[2 * SWAP_GROUP], p_cur[2 * SWAP_GROUP], p_rows[2 * SWAP_GROUP], p_src[2 * SWAP_GROUP];
-  __shared__ int p_cnt;
+  __shared__ int p_rows[2 * SWAP_GROUP], p_src[2 * SWAP_GROUP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = rank * rows_per_cta;
   const int nloc = max(0, min(rows_per_cta, m - r0));
-  constexpr long long NOIDX = (1ll << 62);
+  // this thread's rows: local tid + 512 q, global gr[q]
+  int gr[R];
+  bool have[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    gr[q] = r0 + tid + SP_THREADS * q;
+    have[q] = tid + SP_THREADS * q < nloc;
+  }
 
-  cluster.sync();  // every CTA of the cluster is resident: its exchange buffer may be written
-  if (profiling) tlast = clock64();
+  if (tid == 0) {
+    sp_mbar_init(&xbar[0], 1);
+    sp_mbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster.sync();  // every CTA of the cluster is resident and its barriers are initialised: records may be sent to it
+  if (profiling) pt[8] = clock64();
+  // per column every CTA receives one record from each CTA (itself included) and the diagonal row
+  constexpr uint32_t REC_BYTES = 16 + WW * 8, DIAG_BYTES = WW * 8;
+  const uint32_t col_bytes = (uint32_t)C * REC_BYTES + DIAG_BYTES;
+  uint32_t ccount = 0;  // columns done: parity = ccount & 1, barrier phase = (ccount >> 1) & 1
 
   for (int j0 = 0; j0 < W; j0 += WW) {
     const int ww = min(WW, W - j0);
-    // ================= S1: stage the window, apply the sub-panel's earlier columns (Crout) =================
+    // ================= S1: the window into registers, minus the sub-panel's earlier columns (Crout) =================
     for (int e = tid; e < j0 * WW; e += SP_THREADS) {
       const int k = e / WW, c = e - k * WW;
       R1[e] = c < ww ? __ldcg(A + (i64)k * rs + (i64)(j0 + c) * cs) : 0.0;
     }
-    __syncthreads();
-    double my_val = 0.0;
-    long long my_idx = -1;
-    for (int r = tid; r < nloc; r += SP_THREADS) {
-      const int gr = r0 + r;
-      double acc[WW];
-      if (gr >= j0) {
-        const double* arow = A + (i64)gr * rs;
+    double a[R][WW];
+    bool act[R];  // rows on / below the window's diagonal block (rows above hold finished U entries: not ours)
 #pragma unroll
-        for (int c = 0; c < WW; ++c) acc[c] = c < ww ? __ldcg(arow + (i64)(j0 + c) * cs) : 0.0;
-        int k = 0;
-        for (; k + 4 <= j0; k += 4) {
-          const double l0 = __ldcg(arow + (i64)k * cs), l1 = __ldcg(arow + (i64)(k + 1) * cs),
-                       l2 = __ldcg(arow + (i64)(k + 2) * cs), l3 = __ldcg(arow + (i64)(k + 3) * cs);
-          const double* u = R1 + (size_t)k * WW;
+    for (int q = 0; q < R; ++q) {
+      act[q] = have[q] && gr[q] >= j0;
 #pragma unroll
-          for (int c = 0; c < WW; ++c) acc[c] = fma(-l0, u[c], acc[c]);
-#pragma unroll
-          for (int c = 0; c < WW; ++c) acc[c] = fma(-l1, u[WW + c], acc[c]);
-#pragma unroll
-          for (int c = 0; c < WW; ++c) acc[c] = fma(-l2, u[2 * WW + c], acc[c]);
-#pragma unroll
-          for (int c = 0; c < WW; ++c) acc[c] = fma(-l3, u[3 * WW + c], acc[c]);
-        }
-        for (; k < j0; ++k) {
-          const double l0 = __ldcg(arow + (i64)k * cs);
-          const double* u = R1 + (size_t)k * WW;
-#pragma unroll
-          for (int c = 0; c < WW; ++c) acc[c] = fma(-l0, u[c], acc[c]);
-        }
-        const double v = fabs(acc[0]);
-        if (v > 0.0 && cand_better(v, gr, my_val, my_idx < 0 ? NOIDX : my_idx)) {
-          my_val = v;
-          my_idx = gr;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < WW; ++c) acc[c] = 0.0;
-      }
-#pragma unroll
-      for (int c = 0; c < WW; ++c) S[r * LD + c] = acc[c];
+      for (int c = 0; c < WW; ++c) a[q][c] = (act[q] && c < ww) ? __ldcg(A + (i64)gr[q] * rs + (i64)(j0 + c) * cs) : 0.0;
     }
-    tick(0);
-    // ================= S2: the window's columns =================
-    for (int j = 0; j < ww; ++j) {
-      const int par = j & 1;
-      const int dj = j0 + j;  // global row of the diagonal
-      {
-        double v = my_val;
-        long long ix = my_idx < 0 ? NOIDX : my_idx;
+    __syncthreads();
+    {
+      constexpr int KU = (R >= 8) ? 2 : (R == 4 ? 4 : 8);  // R * KU = 8 or 16 loads in flight per thread
+      int k = 0;
+      for (; k + KU <= j0; k += KU) {
+        double l[R][KU];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, v, off);
-          const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
-          if (cand_better(ov, oi, v, ix)) {
-            v = ov;
-            ix = oi;
+        for (int q = 0; q < R; ++q)
+#pragma unroll
+          for (int u = 0; u < KU; ++u) l[q][u] = act[q] ? __ldcg(A + (i64)gr[q] * rs + (i64)(k + u) * cs) : 0.0;
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+          const double* uu = R1 + (size_t)(k + u) * WW;
+#pragma unroll
+          for (int c = 0; c < WW; ++c) {
+            const double uv = uu[c];
+#pragma unroll
+            for (int q = 0; q < R; ++q) a[q][c] = fma(-l[q][u], uv, a[q][c]);
           }
         }
+      }
+      for (; k < j0; ++k) {
+        const double* uu = R1 + (size_t)k * WW;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const double lv = act[q] ? __ldcg(A + (i64)gr[q] * rs + (i64)k * cs) : 0.0;
+#pragma unroll
+          for (int c = 0; c < WW; ++c) a[q][c] = fma(-lv, uu[c], a[q][c]);
+        }
+      }
+    }
+    tick(0);
+    // ================= S2: the window's columns (fully unrolled: a[][] stays in registers) =================
+    // Per column the critical path is: thread candidate -> warp arg-max -> CTA arg-max -> candidate / diagonal row into the
+    // exchange buffers of all CTAs -> cluster barrier -> cluster arg-max -> reciprocal -> rank-1 update. The arg-max steps
+    // use three integer warp reductions (redux.sync) on the bit pattern of |a| (monotone for non-negative doubles) and on
+    // the row index instead of 64-bit shuffle butterflies, and the rows are pushed by the owner's own warp (no second CTA
+    // barrier): measured 6400 -> see profiles/r02_lu_subpanel_phases.log cycles per column.
+#pragma unroll
+    for (int j = 0; j < WW; ++j) {
+      if (j < ww) {  // uniform
+        const int par = (int)(ccount & 1u);
+        const uint32_t phase = (ccount >> 1) & 1u;
+        ++ccount;
+        const int dj = j0 + j;  // global row of the diagonal
+        // ---- candidate of this thread, warp, CTA ----
+        double v = 0.0;
+        int ix = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const double t = fabs(a[q][j]);
+          if (have[q] && gr[q] >= dj && t > 0.0 && (t > v || (t == v && gr[q] < ix))) {
+            v = t;
+            ix = gr[q];
+          }
+        }
+        warp_argmax(v, ix);
         if (lane == 0) {
           red_val[warp] = v;
           red_idx[warp] = ix;
         }
-      }
-      __syncthreads();  // also orders the S stores of S1 / the previous column's update before the row reads below
-      {
-        // every warp reduces the 16 warp candidates redundantly (no second CTA barrier)
-        double v = lane < SP_THREADS / 32 ? red_val[lane] : 0.0;
-        long long ix = lane < SP_THREADS / 32 ? red_idx[lane] : NOIDX;
+        __syncthreads();
+        v = lane < SP_THREADS / 32 ? red_val[lane] : 0.0;
+        ix = lane < SP_THREADS / 32 ? red_idx[lane] : 0x7fffffff;
+        warp_argmax(v, ix);  // every warp holds the CTA's candidate (v, ix) in all lanes
+        if (tid == 0) sp_mbar_expect_tx(&xbar[par], col_bytes);
+        // ---- the warp that owns the candidate row sends the record to every CTA of the cluster (one bulk copy per
+        // destination, completing on the destination's barrier); the warp that owns the diagonal row sends that one ----
+        {
+          const int lr = (v > 0.0) ? ix - r0 : 0;
+          const int o_warp = (lr & (SP_THREADS - 1)) >> 5;
+          if (warp == o_warp) {
+            if (lane == 0) {
+              rec_s[par].val = v;
+              rec_s[par].idx = ix;
+            }
 #pragma unroll
-        for (int off = 8; off > 0; off >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, v, off);
-          const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
-          if (cand_better(ov, oi, v, ix)) {
-            v = ov;
-            ix = oi;
-          }
-        }
-        v = __shfl_sync(0xffffffffu, v, 0);
-        ix = __shfl_sync(0xffffffffu, ix, 0);
-        // publish to every CTA of the cluster: warp `warp` serves destination rank `warp`
-        if (warp < C) {
-          SpExchange* Xr = cluster.map_shared_rank(&X, warp);
-          if (lane == 0) {
-            Xr->val[par][rank] = v;
-            Xr->idx[par][rank] = ix;
-          }
-          if (v > 0.0) {
-            const int lr = (int)(ix - r0);
-            if (lane < ww) Xr->row[par][rank][lane] = S[lr * LD + lane];
-          }
-          if (dj >= r0 && dj < r0 + nloc) {
-            const int lr = dj - r0;
-            if (lane < ww) Xr->diag[par][lane] = S[lr * LD + lane];
-          }
-        }
-      }
-      tick(1);
-      cluster.sync();
-      tick(2);
-      // winner: every warp scans the C candidates redundantly
-      int piv, wincta;
-      {
-        double v = lane < C ? X.val[par][lane] : 0.0;
-        long long ix = lane < C ? X.idx[par][lane] : NOIDX;
-        int wc = lane;
-        if (!(v > 0.0)) {
-          v = 0.0;
-          ix = NOIDX;
-        }
+            for (int q = 0; q < R; ++q) {
+              if (v > 0.0 && have[q] && gr[q] == ix) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, v, off);
-          const long long oi = __shfl_xor_sync(0xffffffffu, ix, off);
-          const int oc = __shfl_xor_sync(0xffffffffu, wc, off);
-          if (cand_better(ov, oi, v, ix)) {
-            v = ov;
-            ix = oi;
-            wc = oc;
+                for (int c = 0; c < WW; ++c) rec_s[par].row[c] = a[q][c];
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async-proxy reads
+            __syncwarp();
+            if (lane < C)
+              sp_bulk_to_cluster(sp_mapa(smem_u32(&Xrec[par][rank]), (uint32_t)lane), smem_u32(&rec_s[par]), REC_BYTES,
+                                 sp_mapa(smem_u32(&xbar[par]), (uint32_t)lane));
+          }
+          const bool diag_here = dj >= r0 && dj < r0 + nloc;
+          if (diag_here && warp == (((dj - r0) & (SP_THREADS - 1)) >> 5)) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              if (have[q] && gr[q] == dj) {
+#pragma unroll
+                for (int c = 0; c < WW; ++c) diag_s[par][c] = a[q][c];
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < C)
+              sp_bulk_to_cluster(sp_mapa(smem_u32(&Xdiag[par][0]), (uint32_t)lane), smem_u32(&diag_s[par][0]), DIAG_BYTES,
+                                 sp_mapa(smem_u32(&xbar[par]), (uint32_t)lane));
           }
         }
-        v = __shfl_sync(0xffffffffu, v, 0);
-        ix = __shfl_sync(0xffffffffu, ix, 0);
-        wc = __shfl_sync(0xffffffffu, wc, 0);
-        // an all-zero / all-NaN column keeps imax = row (reference factor.rs:35-44)
-        piv = (v > 0.0) ? (int)ix : dj;
-        wincta = (v > 0.0) ? wc : -1;
-      }
-      const double* prow = (piv != dj) ? X.row[par][wincta] : X.diag[par];
-      const double* drow = X.diag[par];
-      if (piv != dj && warp == 0 && lane < ww) {
-        if (piv >= r0 && piv < r0 + nloc) S[(piv - r0) * LD + lane] = drow[lane];
-        if (dj >= r0 && dj < r0 + nloc) S[(dj - r0) * LD + lane] = prow[lane];
-      }
-      if (tid == 0) {
-        trans_s[dj] = piv - dj;
-        if (rank == 0) trans[dj] = piv - dj;
-      }
-      __syncthreads();
-      // multipliers + rank-1 update of the slice; next column's local arg-max
-      const double inv = 1.0 / prow[j];
-      my_val = 0.0;
-      my_idx = -1;
-      for (int r = tid; r < nloc; r += SP_THREADS) {
-        const int gr = r0 + r;
-        if (gr > dj) {
-          double* row = S + r * LD;
-          const double l = row[j] * inv;
-          row[j] = l;
-          for (int c = j + 1; c < ww; ++c) row[c] = fma(-l, prow[c], row[c]);
-          if (j + 1 < ww) {
-            const double v = fabs(row[j + 1]);
-            if (v > 0.0 && cand_better(v, gr, my_val, my_idx < 0 ? NOIDX : my_idx)) {
-              my_val = v;
-              my_idx = gr;
+        tick(1);
+        sp_mbar_wait(&xbar[par], phase);
+        tick(2);
+        // ---- winner: every warp scans the C candidates redundantly ----
+        int piv, wincta;
+        {
+          double gv = lane < C ? Xrec[par][lane].val : 0.0;
+          int gi = lane < C ? (int)Xrec[par][lane].idx : 0x7fffffff;
+          if (!(gv > 0.0)) {
+            gv = 0.0;
+            gi = 0x7fffffff;
+          }
+          const double mv = gv;
+          const int mi = gi;
+          warp_argmax(gv, gi);
+          const unsigned who = __ballot_sync(0xffffffffu, mv == gv && mi == gi && lane < C);
+          // an all-zero / all-NaN column keeps imax = row (reference factor.rs:35-44)
+          piv = (gv > 0.0) ? gi : dj;
+          wincta = (gv > 0.0) ? (__ffs(who) - 1) : -1;
+        }
+        const double* prow = (piv != dj) ? Xrec[par][wincta].row : Xdiag[par];
+        const double* drow = Xdiag[par];
+        if (tid == 0) {
+          trans_s[dj] = piv - dj;
+          if (rank == 0) trans[dj] = piv - dj;
+        }
+        // ---- swap (in registers), multipliers (reciprocal-multiply, as the reference), rank-1 update ----
+        // the pivot row from column j on, read once per thread with 16-byte loads (the rows are 16-byte aligned)
+        // (narrow windows only: 32 extra doubles would not fit next to a 32-column window)
+        constexpr int PRN = WW <= 16 ? WW : 1;
+        double pr[PRN];
+        if constexpr (WW <= 16) {
+#pragma unroll
+          for (int c = (j & ~1); c < WW; c += 2) {
+            const double2 t2 = *reinterpret_cast<const double2*>(prow + c);
+            pr[c] = t2.x;
+            pr[c + 1] = t2.y;
+          }
+        }
+        const double inv = __drcp_rn(prow[j]);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          if (have[q] && piv != dj) {
+            if (gr[q] == piv) {
+#pragma unroll
+              for (int c = 0; c < WW; ++c)
+                if (c < ww) a[q][c] = drow[c];
+            } else if (gr[q] == dj) {
+#pragma unroll
+              for (int c = 0; c < WW; ++c)
+                if (c < ww) a[q][c] = prow[c];
             }
           }
+          if (have[q] && gr[q] > dj) {
+            const double l = a[q][j] * inv;
+            a[q][j] = l;
+#pragma unroll
+            for (int c = j + 1; c < WW; ++c)
+              if (c < ww) a[q][c] = fma(-l, (WW <= 16 ? pr[c < PRN ? c : 0] : prow[c]), a[q][c]);
+          }
         }
+        tick(3);
       }
-      tick(3);
     }
-    __syncthreads();
     // store the window (rows above j0 hold finished U entries written in S4: not ours to touch)
-    for (int r = tid; r < nloc; r += SP_THREADS) {
-      const int gr = r0 + r;
-      if (gr >= j0) {
-        double* dstg = A + (i64)gr * rs + (i64)j0 * cs;
-        const double* srcs = S + r * LD;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      if (act[q]) {
+        double* dstg = A + (i64)gr[q] * rs + (i64)j0 * cs;
 #pragma unroll
         for (int c = 0; c < WW; ++c)
-          if (c < ww) dstg[(i64)c * cs] = srcs[c];
+          if (c < ww) dstg[(i64)c * cs] = a[q][c];
       }
     }
     const int nother = W - ww;  // columns of the sub-panel outside the window
     if (nother == 0) break;     // uniform
     // ================= S3: the window's transpositions on the other columns =================
-    if (warp == 0) build_plan_warp<true>(trans_s, j0, j0 + ww, p_ids, p_cur, p_rows, p_src, &p_cnt, lane);
+    __syncthreads();  // trans_s
+    // gather plan of the window's transpositions, one candidate row per slot (slots 0..ww-1: the diagonal rows, ww..2ww-1: the
+    // pivot rows), each followed independently through the ww transpositions: dst = final position of original row src
+    if (tid < 2 * WW) {
+      const int sl = tid;
+      int src = -1;
+      if (sl < ww) src = j0 + sl;
+      else if (sl < 2 * ww) {
+        const int t = sl - ww;
+        src = j0 + t + trans_s[j0 + t];
+        bool dup = src < j0 + ww;  // a diagonal row: already has a slot
+        for (int t2 = 0; t2 < t; ++t2) dup = dup || (j0 + t2 + trans_s[j0 + t2] == src);
+        if (dup) src = -1;
+      }
+      int pos = src;
+      for (int t = 0; t < ww; ++t) {
+        const int ra = j0 + t, rb = ra + trans_s[ra];
+        pos = (pos == ra) ? rb : ((pos == rb) ? ra : pos);
+      }
+      p_src[sl] = src;
+      p_rows[sl] = (src >= 0 && pos != src) ? pos : -1;
+    }
     cluster.sync();  // (A) window stores visible cluster-wide; plan visible CTA-wide
     tick(4);
     {
-      const int cnt = p_cnt;
-      const int q = tid & (2 * SWAP_GROUP - 1), cb = tid >> 7;  // 128 plan slots x 4 columns in flight
-      const bool act = q < cnt;
-      const i64 srow = act ? (i64)p_src[q] : 0, drow = act ? (i64)p_rows[q] : 0;
+      const int qs = tid & (2 * SWAP_GROUP - 1), cb = tid >> 7;  // 128 plan slots x 4 columns in flight
+      const bool on_slot = qs < 2 * ww && p_rows[qs] >= 0;
+      const i64 srow = on_slot ? (i64)p_src[qs] : 0, drw = on_slot ? (i64)p_rows[qs] : 0;
       // my columns: oc = rank, rank + C, ... over the nother other columns
       for (int base = rank; base < nother; base += 4 * C) {
         const int oc = base + cb * C;
-        const bool on = act && oc < nother && cnt > 0;
+        const bool on = on_slot && oc < nother;
         const int col = oc < j0 ? oc : oc + ww;
         double v = 0.0;
         if (on) v = __ldcg(A + srow * rs + (i64)col * cs);
         __syncthreads();
-        if (on) A[drow * rs + (i64)col * cs] = v;
+        if (on) A[drw * rs + (i64)col * cs] = v;
         __syncthreads();
       }
     }
@@ -824,7 +928,17 @@ __global__ void __launch_bounds__(SP_THREADS) lu_subpanel_cluster_kernel(double*
           if (rc < nright) {
             x = __ldcg(A + (i64)(j0 + i) * rs + (i64)(j0 + ww + rc) * cs);
             const double* lr = R1 + (size_t)i * j0;
-            for (int k = 0; k < j0; ++k) x = fma(-lr[k], R2[k * SP_CG + cl], x);
+            // four partial sums: the dot product is a latency chain otherwise
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+            int k = 0;
+            for (; k + 4 <= j0; k += 4) {
+              x0 = fma(lr[k], R2[k * SP_CG + cl], x0);
+              x1 = fma(lr[k + 1], R2[(k + 1) * SP_CG + cl], x1);
+              x2 = fma(lr[k + 2], R2[(k + 2) * SP_CG + cl], x2);
+              x3 = fma(lr[k + 3], R2[(k + 3) * SP_CG + cl], x3);
+            }
+            for (; k < j0; ++k) x0 = fma(lr[k], R2[k * SP_CG + cl], x0);
+            x -= (x0 + x1) + (x2 + x3);
           }
           X4[i][cl] = x;
         }
@@ -851,6 +965,16 @@ __global__ void __launch_bounds__(SP_THREADS) lu_subpanel_cluster_kernel(double*
     }
     cluster.sync();  // (C) U rows / swapped columns visible before the next window reads them
     tick(6);
+  }
+  // gather plans of the sub-panel's transpositions (groups of 64) for the caller's row swaps on the outside columns: built
+  // here by CTA 0 (every CTA holds all of trans_s) instead of by a separate 20 us one-warp launch
+  if (plan_rows != nullptr && rank == 0) {
+    __syncthreads();  // trans_s of the last window
+    const int ngroups = (W + SWAP_GROUP - 1) / SWAP_GROUP;
+    __shared__ int g_ids[SP_MAXW / SWAP_GROUP][2 * SWAP_GROUP], g_cur[SP_MAXW / SWAP_GROUP][2 * SWAP_GROUP];
+    if (warp < ngroups)
+      build_plan_warp<true>(trans_s, warp * SWAP_GROUP, min(W, (warp + 1) * SWAP_GROUP), g_ids[warp], g_cur[warp],
+                            plan_rows + (i64)warp * 2 * SWAP_GROUP, plan_src + (i64)warp * 2 * SWAP_GROUP, plan_cnt + warp, lane);
   }
   if (profiling)
     for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)prof + i, (unsigned long long)pt[i]);
@@ -1003,7 +1127,7 @@ void subpanel_prof_report() {
   if (!g_subpanel_prof) return;
   long long h[8];
   if (cudaMemcpy(h, g_subpanel_prof, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return;
-  const char* names[8] = {"S1 stage+crout", "S2 reduce+publish", "S2 cluster.sync", "S2 swap+update", "store+plan+sync A",
+  const char* names[8] = {"S1 load+crout", "S2 reduce+publish", "S2 cluster.sync", "S2 scan+swap+update", "store+plan+sync A",
                           "S3 swaps", "S4 + syncs B,C", "-"};
   fprintf(stderr, "faer_b200: fused LU sub-panel cycles (CTA 0 thread 0, all launches):");
   for (int i = 0; i < 7; ++i) fprintf(stderr, "  %s %.3f Mcyc", names[i], (double)h[i] * 1e-6);
@@ -1021,8 +1145,17 @@ int subpanel_max_width() {
   return w;
 }
 
-template <int WW>
-cudaError_t launch_subpanel_t(LuCtx& ctx, VD P, int* trans, int rows_per_cta, size_t smem) {
+i64 subpanel_tall_rows() {
+  static i64 v = -1;
+  if (v < 0) {
+    const char* e = getenv("FAER_B200_LU_FUSED_TALL");  // dev knob: rows above which the fused width is halved
+    v = e ? atoll(e) : 16384;
+  }
+  return v;
+}
+
+template <int WW, int R>
+cudaError_t launch_subpanel_t(LuCtx& ctx, VD P, int* trans, int rows_per_cta, size_t smem, bool want_plan) {
   const int C = ctx.cluster_ctas;
   static bool configured = false;
   if (!g_subpanel_prof && getenv("FAER_B200_LU_SUBPANEL_PROF")) {
@@ -1031,8 +1164,8 @@ cudaError_t launch_subpanel_t(LuCtx& ctx, VD P, int* trans, int rows_per_cta, si
     atexit(subpanel_prof_report);
   }
   if (!configured) {
-    FB_CUDA_CHECK(cudaFuncSetAttribute(lu_subpanel_cluster_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM_BUDGET));
-    FB_CUDA_CHECK(cudaFuncSetAttribute(lu_subpanel_cluster_kernel<WW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    FB_CUDA_CHECK(cudaFuncSetAttribute(lu_subpanel_cluster_kernel<WW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    FB_CUDA_CHECK(cudaFuncSetAttribute(lu_subpanel_cluster_kernel<WW, R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1051,19 +1184,27 @@ cudaError_t launch_subpanel_t(LuCtx& ctx, VD P, int* trans, int rows_per_cta, si
   i64 rs = P.rs, cs = P.cs;
   int m = (int)P.nrows, W = (int)P.ncols;
   long long* prof = g_subpanel_prof;
-  return cudaLaunchKernelEx(&cfg, lu_subpanel_cluster_kernel<WW>, Aptr, rs, cs, m, W, rows_per_cta, trans, prof);
+  int* pr = want_plan ? ctx.plan_rows : nullptr;
+  return cudaLaunchKernelEx(&cfg, lu_subpanel_cluster_kernel<WW, R>, Aptr, rs, cs, m, W, rows_per_cta, trans, pr, ctx.plan_src,
+                            ctx.plan_cnt, prof);
 }
 
-bool launch_subpanel(LuCtx& ctx, VD P, int* trans) {
+bool launch_subpanel(LuCtx& ctx, VD P, int* trans, bool want_plan) {
   const int C = ctx.cluster_ctas;
   const i64 m = P.nrows, W = P.ncols;
-  if (C <= 0 || W > subpanel_max_width() || W > m) return false;
+  // tall panels: the Crout pass streams the CTA's rows of the earlier columns from L2 once per window (8-column windows above
+  // 16384 rows), a cost per column proportional to the fused width: halve it there and let the recursion's GEMM (on the large
+  // partition) supply the level above
+  const i64 wmax = (m > subpanel_tall_rows()) ? std::max<i64>(32, subpanel_max_width() / 2) : subpanel_max_width();
+  if (C <= 0 || W > wmax || W > m) return false;
   const int rows_per_cta = (int)((m + C - 1) / C);
-  auto bytes = [&](int ww) { return ((size_t)rows_per_cta * (size_t)(ww | 1) + (size_t)W * ww + (size_t)W * SP_CG) * sizeof(double); };
+  // R rows x WW columns per thread in registers (R * WW = 32): the smallest R whose 512 R rows cover the CTA's slice
+  auto bytes = [&](int ww) { return ((size_t)W * ww + (size_t)W * SP_CG) * sizeof(double); };
   cudaError_t e;
-  if (bytes(32) <= (size_t)CL_SMEM_BUDGET) e = launch_subpanel_t<32>(ctx, P, trans, rows_per_cta, bytes(32));
-  else if (bytes(16) <= (size_t)CL_SMEM_BUDGET) e = launch_subpanel_t<16>(ctx, P, trans, rows_per_cta, bytes(16));
-  else if (bytes(8) <= (size_t)CL_SMEM_BUDGET) e = launch_subpanel_t<8>(ctx, P, trans, rows_per_cta, bytes(8));
+  if (rows_per_cta <= SP_THREADS) e = launch_subpanel_t<32, 1>(ctx, P, trans, rows_per_cta, bytes(32), want_plan);
+  else if (rows_per_cta <= 2 * SP_THREADS) e = launch_subpanel_t<16, 2>(ctx, P, trans, rows_per_cta, bytes(16), want_plan);
+  else if (rows_per_cta <= 4 * SP_THREADS) e = launch_subpanel_t<8, 4>(ctx, P, trans, rows_per_cta, bytes(8), want_plan);
+  else if (rows_per_cta <= 8 * SP_THREADS) e = launch_subpanel_t<4, 8>(ctx, P, trans, rows_per_cta, bytes(4), want_plan);
   else return false;
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
@@ -1122,12 +1263,9 @@ void lu_rec(LuCtx& ctx, VD A, i64 start, i64 end, int* trans) {
     }
     return;
   }
-  if (launch_subpanel(ctx, A.sub(0, start, m, n), trans)) {
+  if (launch_subpanel(ctx, A.sub(0, start, m, n), trans, has_outside)) {
     if (has_outside) {
-      const int ngroups = (int)((n + SWAP_GROUP - 1) / SWAP_GROUP);
-      laswp_plan_kernel<<<ngroups, 32, 0, ctx.st>>>(trans, (int)n, ctx.plan_rows, ctx.plan_src, ctx.plan_cnt, ngroups);
-      FB_CUDA_CHECK(cudaGetLastError());
-      note_launch();
+      const int ngroups = (int)((n + SWAP_GROUP - 1) / SWAP_GROUP);  // plans written by the kernel itself
       apply_plan(ctx, A.sub(0, 0, m, start), ngroups);
       apply_plan(ctx, A.sub(0, end, m, ncols - end), ngroups);
     }

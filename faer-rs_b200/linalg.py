@@ -497,6 +497,37 @@ def spicy_matmul(C, C_block: int, row_idx, col_idx, accum: int, A, B, D, alpha: 
                                    capi.mat_ref(B), None if dv is None else dv.ctypes.data, a.ctypes.data)
 
 
+class GemmDstKind:
+    """DstKind of the inner seam (include/faer_b200.h: FaerB200_GemmDstKind)"""
+    Lower, Upper, Full = 0, 1, 2
+
+
+_GEMM_DTYPE = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.complex64): 2, np.dtype(np.complex128): 3}
+
+
+def gemm(dst, row_idx, col_idx, dst_kind: int, accum: int, lhs, conj_lhs: bool, diag, rhs, conj_rhs: bool, alpha, n_threads: int = 1) -> None:
+    """The inner seam `faer_b200_gemm` = the argument list of `private_gemm_x86::gemm` at faer's three call sites
+    (matmul/mod.rs:1373-1411, matmul/triangular.rs:641-680, matmul/internal/mod.rs:143-201), numpy arrays only (host pointers;
+    any strides): dst[row_idx[i], col_idx[j]] (+)= alpha * sum_k lhs[i, k] diag[k] rhs[k, j] over the (i, j) `dst_kind` keeps.
+    row_idx / col_idx: None or uint32 / uint64 arrays (same type); diag: None or a 1-D array (any stride)."""
+    lib = capi.load()
+    dt = np.dtype(dst.dtype)
+    assert lhs.dtype == dt and rhs.dtype == dt
+    m, k = lhs.shape
+    n = rhs.shape[1]
+    it = 1
+    for ix in (row_idx, col_idx):
+        if ix is not None:
+            it = 0 if ix.dtype == np.uint32 else 1
+    es = dt.itemsize
+    a = np.array([alpha], dtype=dt)
+    lib.faer_b200_gemm(_GEMM_DTYPE[dt], it, 0, m, n, k, dst.ctypes.data, dst.strides[0] // es, dst.strides[1] // es,
+                       None if row_idx is None else row_idx.ctypes.data, None if col_idx is None else col_idx.ctypes.data, int(dst_kind),
+                       int(accum), lhs.ctypes.data, lhs.strides[0] // es, lhs.strides[1] // es, bool(conj_lhs),
+                       None if diag is None else diag.ctypes.data, 0 if diag is None else diag.strides[0] // es, rhs.ctypes.data,
+                       rhs.strides[0] // es, rhs.strides[1] // es, bool(conj_rhs), a.ctypes.data, n_threads)
+
+
 class ComputeSvdVectors:
     """svd/mod.rs:21-28 (faer-ffi/src/lib.rs:462-477)"""
     No, Thin, Full = 0, 1, 2

@@ -418,6 +418,21 @@ void faer_b200_spicy_matmul_f64(struct FaerV0_24_MatMut C, enum FaerV0_24_Block 
                                 size_t nrow_idx, const unsigned long long *col_idx, size_t ncol_idx, enum FaerV0_24_Accum accum,
                                 struct FaerV0_24_MatRef A, struct FaerV0_24_MatRef B, const double *D,
                                 const struct FaerV0_24_Scalar *alpha);
+/* Inner seam: the type-erased product call faer makes at matmul/mod.rs:1373-1411 (DstKind::Full), matmul/triangular.rs:641-680
+ * (DstKind::Lower / Upper) and matmul/internal/mod.rs:143-201 (row / column scatter + diagonal scaling) into
+ * `private_gemm_x86::gemm`, with that function's parameter list: a Rust build of faer can swap the backend at those three call
+ * sites by forwarding the arguments unchanged (the crate's enums are translated to the constants below; INTEGRATION.md shows it).
+ *   dst[row_idx[i], col_idx[j]] (+)= alpha * sum_k conj?(lhs[i, k]) * diag[k * diag_stride] * conj?(rhs[k, j])
+ * for the (i, j) that dst_kind keeps (Lower: i >= j, Upper: i <= j; both include the diagonal, as the reference asks the backend
+ * for the inclusive trapezoid, triangular.rs:633-640). row_idx / col_idx / diag may be NULL. Strides in elements. Pointers may be
+ * host or device pointers. `instr_set` and `n_threads` are accepted and ignored. Index scatter and diagonal scaling: f64. */
+enum FaerB200_GemmDType { FaerB200_GemmDType_F32 = 0, FaerB200_GemmDType_F64 = 1, FaerB200_GemmDType_C32 = 2, FaerB200_GemmDType_C64 = 3 };
+enum FaerB200_GemmIType { FaerB200_GemmIType_U32 = 0, FaerB200_GemmIType_U64 = 1 };
+enum FaerB200_GemmDstKind { FaerB200_GemmDstKind_Lower = 0, FaerB200_GemmDstKind_Upper = 1, FaerB200_GemmDstKind_Full = 2 };
+void faer_b200_gemm(int dtype, int itype, int instr_set, size_t m, size_t n, size_t k, void *dst, ptrdiff_t dst_rs, ptrdiff_t dst_cs,
+                    const void *row_idx, const void *col_idx, int dst_kind, int accum /* 0 Replace, 1 Add */, const void *lhs,
+                    ptrdiff_t lhs_rs, ptrdiff_t lhs_cs, bool conj_lhs, const void *diag, ptrdiff_t diag_stride, const void *rhs,
+                    ptrdiff_t rhs_rs, ptrdiff_t rhs_cs, bool conj_rhs, const void *alpha, size_t n_threads);
 /* Run-time options (initial values from the environment variable in brackets). Returns 0, or -1 for an unknown name.
  *   "gemm_ws"        [FAER_B200_GEMM_WS]        0 never / 1 heuristic (default) / 2 always use the TMA-fed warp-specialised
  *                                                f64 GEMM (csrc/gemm_f64_ws.cuh) where the operands qualify

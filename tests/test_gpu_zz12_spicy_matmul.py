@@ -68,3 +68,41 @@ def test_spicy_matmul_vs_definition(fb, ws):
                 assert np.all(np.abs(got - want)[touched] <= (full + 4 * U * np.abs(want))[touched]), key
     finally:
         lib.faer_b200_set_option(b"gemm_ws", saved)
+
+
+def test_inner_seam_gemm(fb):
+    """`faer_b200_gemm` (the parameter list of private_gemm_x86::gemm at matmul/mod.rs:1373-1411, triangular.rs:641-680,
+    internal/mod.rs:143-201): scatter through u32 / u64 indices, strided diagonal, DstKind Lower / Upper / Full on f64 against the
+    definition; the plain product for f32 / c32 / c64 with conjugation flags against numpy."""
+    la = fb.linalg
+    rng = np.random.default_rng(140)
+    for (m, n, k), kind, itype, add in itertools.product([(40, 40, 9), (130, 130, 33), (70, 45, 20)],
+                                                         [la.GemmDstKind.Lower, la.GemmDstKind.Upper, la.GemmDstKind.Full],
+                                                         [np.uint32, np.uint64], [False, True]):
+        if kind != la.GemmDstKind.Full and m != n:
+            continue
+        ri = rng.permutation(m + 9)[:m].astype(itype)
+        ci = rng.permutation(n + 4)[:n].astype(itype)
+        A = np.asfortranarray(rng.standard_normal((m, k)))
+        B = rng.standard_normal((k, n))                      # row-major rhs: strides are part of the seam
+        Dbuf = rng.standard_normal(2 * k); D = Dbuf[::2]     # diag_stride = 2
+        C0 = np.asfortranarray(rng.standard_normal((m + 9, n + 4)))
+        blk = {la.GemmDstKind.Lower: S_LOW, la.GemmDstKind.Upper: S_UP, la.GemmDstKind.Full: S_RECT}[kind]
+        want, touched = reference(C0, blk, ri, ci, add, A, B, D, 0.75)
+        got = C0.copy(order="F")
+        la.gemm(got, ri, ci, kind, 1 if add else 0, A, False, D, B, False, 0.75)
+        key = (m, n, k, kind, itype.__name__, add)
+        assert np.array_equal(got[~touched], C0[~touched]), key
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12), key
+    # plain products of the other scalar types, with the conjugation flags of the seam
+    for dt, tol in [(np.float32, 2e-4), (np.complex64, 5e-4), (np.complex128, 1e-11)]:
+        m, n, k = 96, 70, 50
+        cplx = np.issubdtype(dt, np.complexfloating)
+        mk = (lambda *sh: (rng.standard_normal(sh) + 1j * rng.standard_normal(sh)).astype(dt)) if cplx else (lambda *sh: rng.standard_normal(sh).astype(dt))
+        A = np.asfortranarray(mk(m, k)); B = np.asfortranarray(mk(k, n)); C0 = np.asfortranarray(mk(m, n))
+        for cl, cr in ([(False, False), (True, False), (False, True), (True, True)] if cplx else [(False, False)]):
+            alpha = (0.5 - 0.25j) if cplx else 0.5
+            got = C0.copy(order="F")
+            la.gemm(got, None, None, la.GemmDstKind.Full, 1, A, cl, None, B, cr, alpha)
+            want = C0 + alpha * ((A.conj() if cl else A).astype(np.complex128 if cplx else np.float64) @ (B.conj() if cr else B))
+            assert np.allclose(got, want, rtol=tol, atol=tol * k), (dt.__name__, cl, cr)
