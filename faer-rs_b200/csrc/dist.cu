@@ -206,7 +206,8 @@ static bool ensure_green_streams() {
 
 // A second, independently sized partition for drivers whose panel kernel needs more SMs than the LU one (the QR panel
 // keeps its slices in shared memory: >= 42 CTAs at 65536 rows). Created on first use, one per requested size, never
-// resized. Used only by the opt-in look-ahead QR driver (qr.cu, FAER_B200_QR_LOOKAHEAD=1) — NOT RUN ON A GPU YET.
+// resized. Used only by the opt-in look-ahead QR driver (qr.cu, FAER_B200_QR_LOOKAHEAD=<SMs>; measured slower than the default
+// driver, profiles/r02_qr_lookahead_sweep.log).
 bool partition_streams(int panel_sms, cudaStream_t* panel, cudaStream_t* urgent, cudaStream_t* bulk, int* got_panel_sms) {
   struct Set {
     int want;

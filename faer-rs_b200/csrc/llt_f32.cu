@@ -2,7 +2,7 @@
 // same recurrence: a_ic <- fmaf(-l_cj, l_ij, a_ic), regularise / test / sqrtf / reciprocal-multiply, ldlt/factor.rs:7-177),
 // trailing updates on the f32 GEMM (3xTF32, tcgen05 for large products), panel solves on the f32 triangular solve.
 // The look-ahead block-column drivers (dist.cu) are f64-only, so large f32 problems use the recursive driver.
-// STATUS: written after round 1's last GPU session (a type-substituted copy of validated code); first hardware run pending.
+// STATUS: a type-substituted copy of the validated f64 leaf and recursive driver (tests/test_gpu_zz5_llt_f32.py).
 // Reference: faer/src/linalg/cholesky/llt/factor.rs:68-97 -> ldlt/factor.rs:367-498; solve: llt/solve.rs:12-35.
 #include "gemm_f32.cuh"
 #include "linalg_f64.cuh"

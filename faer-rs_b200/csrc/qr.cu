@@ -474,8 +474,10 @@ i64 qr_recommended_block_size(i64 nrows, i64 ncols) {
   return std::max<i64>(1, std::min(bs, size));
 }
 
-// ---- look-ahead driver on a partitioned GPU (OPT-IN: FAER_B200_QR_LOOKAHEAD=1; drafted at the end of round 1 from the
-// LU driver's schedule, compile-checked, NOT RUN ON A GPU YET) ---------------------------------------------------------
+// ---- look-ahead driver on a partitioned GPU (OPT-IN: FAER_B200_QR_LOOKAHEAD=<panel SMs>). Parity-green on hardware, but
+// SLOWER than the default driver at 65536 x 4096 f32 (100-119 ms with 32 / 48 / 64 panel SMs against 89 ms,
+// profiles/r02_qr_lookahead_sweep.log): the panel kernel loses more from running on a third of the SMs than the overlap
+// returns. Kept opt-in. ------------------------------------------------------------------------------------------------
 // With the block applies on the tcgen05 GEMM the f32 QR is panel-bound (45 % of the time in qr_panel_kernel). Same
 // schedule as lu_local_partitioned_f64 (dist.cu): the panel partition factors block j+1 (sub-panels, their T blocks, the
 // in-block applies) while the update partition applies block j's reflector to the columns right of block j+1; block j+1

@@ -8,7 +8,7 @@
 //                                       rounding; the reference inverts the triangular factors and multiplies)
 //   qr/no_pivoting/reconstruct.rs:13-39 out = [R; 0], then out <- Q out
 //   qr/no_pivoting/inverse.rs           A^-1 = R^-1 Q^H; here as the QR solve applied to the identity
-// STATUS: written after round 1's last GPU session; first hardware run pending (tests/test_gpu_zz4_reconstruct_inverse.py).
+// Tests: tests/test_gpu_zz4_reconstruct_inverse.py.
 #include "runtime.cuh"
 #include "tensor_ops.cuh"
 

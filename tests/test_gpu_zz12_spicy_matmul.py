@@ -95,8 +95,8 @@ def test_inner_seam_gemm(fb):
         assert np.array_equal(got[~touched], C0[~touched]), key
         assert np.allclose(got, want, rtol=1e-12, atol=1e-12), key
     # plain products of the other scalar types, with the conjugation flags of the seam
-    for dt, tol in [(np.float32, 2e-4), (np.complex64, 5e-4), (np.complex128, 1e-11)]:
-        m, n, k = 96, 70, 50
+    for dt, tol, (m, n, k) in [(np.float32, 2e-4, (96, 70, 50)), (np.complex64, 5e-4, (96, 70, 50)), (np.complex128, 1e-11, (96, 70, 50)),
+                               (np.complex128, 1e-11, (530, 512, 260))]:   # the last one: planar-operand path of gemm_c64.cu
         cplx = np.issubdtype(dt, np.complexfloating)
         mk = (lambda *sh: (rng.standard_normal(sh) + 1j * rng.standard_normal(sh)).astype(dt)) if cplx else (lambda *sh: rng.standard_normal(sh).astype(dt))
         A = np.asfortranarray(mk(m, k)); B = np.asfortranarray(mk(k, n)); C0 = np.asfortranarray(mk(m, n))

@@ -83,3 +83,27 @@ except Exception as e:  # pragma: no cover
     out["singular_values_f64_n8192_ms"] = None
     out["singular_values_error"] = repr(e)
     print(json.dumps(out), flush=True)
+
+# configs[4] with vectors: svd(A, Full U, Full V) at n = 8192 (bidiagonalization + divide and conquer on the Golub-Kahan form +
+# QR stabilisation + back-transforms; csrc/svd_vectors.cu), and the self-adjoint EVD with vectors at the same n. Residual of the
+# factorization checked on a probe (not timed).
+try:
+    S8 = torch.zeros(n4, dtype=torch.float64, device=dev)
+    U8 = torch.zeros((n4, n4), dtype=torch.float64, device=dev).T
+    V8 = torch.zeros((n4, n4), dtype=torch.float64, device=dev).T
+    t = best_ms(lambda: la.svd(A8, S8, U8, V8), reps=1)
+    out["svd_full_vectors_f64_n8192_ms"] = t
+    x = torch.randn((n4, 2), dtype=torch.float64, device=dev)
+    r = (A8 @ x - U8 @ (S8[:, None] * (V8.T @ x))).abs().max() / (A8.abs().max() * n4)
+    out["svd_probe_residual"] = float(r)
+    print(json.dumps(out), flush=True)
+    del U8, V8
+    H8 = (A8 + A8.T).T.contiguous().T
+    W8 = torch.zeros((n4, n4), dtype=torch.float64, device=dev).T
+    t = best_ms(lambda: la.self_adjoint_evd(H8, S8, W8), reps=1)
+    out["self_adjoint_evd_vectors_f64_n8192_ms"] = t
+    out["evd_probe_residual"] = float((H8 @ x - W8 @ (S8[:, None] * (W8.T @ x))).abs().max() / (H8.abs().max() * n4))
+    print(json.dumps(out), flush=True)
+except Exception as e:  # pragma: no cover
+    out["svd_vectors_error"] = repr(e)
+    print(json.dumps(out), flush=True)
