@@ -666,8 +666,14 @@ def main():
                 la.cholesky_in_place(hv)  # H2D + factorisation + D2H inside the C-ABI call, synchronous
             # the call streams block columns (width 256) through the factorization: only the part on / below the
             # diagonal blocks crosses PCIe (the strict upper triangle is neither read nor written by LLT)
+            # (the driver's block boundaries, csrc/dist.cu: llt_block_bounds — 256-wide, 128-wide in the last 6144 columns)
             bw = int(os.environ.get("FAER_B200_NB", "0")) or 256
-            bytes_h2d = sum((n - j0) * min(bw, n - j0) * 8 for j0 in range(0, n, bw))
+            tail = int(os.environ.get("FAER_B200_LLT_TAIL", "6144"))
+            bytes_h2d, j0 = 0, 0
+            while j0 < n:
+                w = min(128 if (bw > 128 and n - j0 <= tail) else bw, n - j0)
+                bytes_h2d += (n - j0) * w * 8
+                j0 += w
             how = ("libfaer_v0_23_llt_factor_in_place_f64 on a pinned HOST matrix (wall clock around the synchronous call); "
                    "block columns are uploaded / downloaded on copy streams while the factorization runs")
         hA.copy_(hA0); e2e_call()  # warm-up (pool allocation)

@@ -291,6 +291,26 @@ struct LltHostPipe {
 };
 static LltHostPipe* g_llt_pipe = nullptr;
 
+// Block-column boundaries of the single-GPU LLT drivers. Uniform width nb while the trailing updates bound the schedule; in
+// the tail (remaining order <= FAER_B200_LLT_TAIL, default 6144: profiles/r02_llt_tail_blocks.log) the panel chain does — potf2 + the 128-wide TRSM / SYRK
+// inside a 256-block + the panel solve's leaves: 0.6 ms per 256 columns against 0.4 ms with 128-wide blocks (no inner
+// recursion, half the leaves) — so the blocks narrow to 128 there. P > 1 keeps uniform blocks (ownership is b % P).
+static std::vector<i64> llt_block_bounds(i64 n, i64 nb, bool uniform) {
+  static i64 tail = -1;
+  if (tail < 0) {
+    const char* e = getenv("FAER_B200_LLT_TAIL");
+    tail = e ? atoll(e) : 6144;
+  }
+  std::vector<i64> b0;
+  for (i64 c = 0; c < n;) {
+    b0.push_back(c);
+    const i64 w = (!uniform && nb > 128 && n - c <= tail) ? 128 : nb;
+    c += std::min<i64>(w, n - c);
+  }
+  b0.push_back(n);
+  return b0;
+}
+
 i64 lookahead_min_n() {
   static i64 v = -1;
   if (v < 0) {
@@ -487,7 +507,9 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_start, 0));
   if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
 
-  const i64 nblk = nblocks(n, nb);
+  const std::vector<i64> b0 = llt_block_bounds(n, nb, /*uniform*/ P > 1 || !lookahead);
+  const i64 nblk = (i64)b0.size() - 1;
+  auto col_off = [&](i64 b) { return P == 1 ? b0[(size_t)b] : local_off(b, nb, P) ; };  // local column of block b (owned)
   // two panel buffers (double buffering for look-ahead)
   double* W[2];
   W[0] = (double*)ws_alloc((size_t)n * nb * 8);
@@ -503,12 +525,12 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
 
   auto factor_and_bcast = [&](i64 k) {
     // runs on sp. Panel k: rows k0..n of block column k.
-    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows = n - k0;
+    const i64 k0 = b0[(size_t)k], kb = b0[(size_t)k + 1] - k0, rows = n - k0;
     const int owner = (int)(k % P);
     double* Wk = W[k & 1];
     if (k >= 2) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - 2)], 0));  // buffer reuse
     if (owner == me) {
-      double* pk = A_local + local_off(k, nb, P) * ld + k0;
+      double* pk = A_local + col_off(k) * ld + k0;
       VD diag{pk, kb, kb, 1, ld};
       llt_cholesky_device_f64(sp, diag, reg_delta, reg_eps, d_info, k0);
       if (rows > kb) {
@@ -530,10 +552,10 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   auto update_block_col = [&](cudaStream_t st, i64 k, i64 j) {
     // block column j (> k, owned by me) -= W_k[rows >= j0] * W_k[rows of block j]^T
     if (pipe && k == 0) FB_CUDA_CHECK(cudaStreamWaitEvent(st, pipe->up[(size_t)j], 0));  // first touch of column j
-    const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows_k = n - k0;
-    const i64 j0 = j * nb, jb = std::min(nb, n - j0);
+    const i64 k0 = b0[(size_t)k], kb = b0[(size_t)k + 1] - k0, rows_k = n - k0;
+    const i64 j0 = b0[(size_t)j], jb = b0[(size_t)j + 1] - j0;
     const double* Wk = W[k & 1];
-    double* pj = A_local + local_off(j, nb, P) * ld + j0;
+    double* pj = A_local + col_off(j) * ld + j0;
     VCD Wj{Wk + (j0 - k0), jb, kb, 1, rows_k};                       // rows of block j in the panel
     VD djj{pj, jb, jb, 1, ld};
     gemm_f64(st, djj, TRI_LOWER, 1, Wj, RECT, Wj.t(), RECT, -1.0);    // diagonal block: lower triangle only
@@ -563,7 +585,7 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
     if (P == 1 && k + 2 < nblk && !(pipe && k == 0) && !getenv("FAER_B200_LLT_SPLIT_BULK")) {
       // single GPU: every remaining block column in ONE structured launch (lower-triangular destination: tiles above
       // the diagonal exit at once) instead of one launch per block column — no per-launch tail, better L2 reuse
-      const i64 k0 = k * nb, kb = std::min(nb, n - k0), rows_k = n - k0, j0 = (k + 2) * nb;
+      const i64 k0 = b0[(size_t)k], kb = b0[(size_t)k + 1] - k0, rows_k = n - k0, j0 = b0[(size_t)k + 2];
       VCD Wr{W[k & 1] + (j0 - k0), n - j0, kb, 1, rows_k};
       VD dst{A_local + j0 * ld + j0, n - j0, n - j0, 1, ld};
       gemm_f64(sm, dst, TRI_LOWER, 1, Wr, RECT, Wr.t(), RECT, -1.0);
@@ -615,7 +637,11 @@ LltResult llt_host_pipelined_f64(double* hostA, i64 host_ld, i64 n, i64 nb, doub
     FB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
     FB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
   }
-  const i64 nblk = nblocks(n, nb);
+  // the left-looking first half (opt-in) walks uniform blocks; the default path shares dist_llt_f64's boundaries
+  const char* hl0 = getenv("FAER_B200_HOST_LEFT");
+  const bool hybrid = hl0 && atoi(hl0) != 0;
+  const std::vector<i64> b0 = llt_block_bounds(n, nb, /*uniform*/ hybrid);
+  const i64 nblk = (i64)b0.size() - 1;
   double* dA = (double*)ws_alloc((size_t)n * n * 8);
   LltHostPipe pipe;
   pipe.host = hostA;
@@ -623,7 +649,7 @@ LltResult llt_host_pipelined_f64(double* hostA, i64 host_ld, i64 n, i64 nb, doub
   pipe.s_d2h = s_d2h;
   pipe.up.resize((size_t)nblk);
   for (i64 j = 0; j < nblk; ++j) {
-    const i64 j0 = j * nb, jb = std::min(nb, n - j0);
+    const i64 j0 = b0[(size_t)j], jb = b0[(size_t)j + 1] - j0;
     FB_CUDA_CHECK(cudaEventCreateWithFlags(&pipe.up[(size_t)j], cudaEventDisableTiming));
     FB_CUDA_CHECK(cudaMemcpy2DAsync(dA + j0 * n + j0, (size_t)n * 8, hostA + j0 * host_ld + j0, (size_t)host_ld * 8,
                                     (size_t)(n - j0) * 8, (size_t)jb, cudaMemcpyHostToDevice, s_h2d));
@@ -637,8 +663,7 @@ LltResult llt_host_pipelined_f64(double* hostA, i64 host_ld, i64 n, i64 nb, doub
   // j only needs the panels to its left, so it is processed the moment it lands: one GEMM with k = j0 applies all previous
   // panels, then potrf + solve, then the finished column goes home. When the upload is complete, one structured GEMM
   // brings the trailing half up to date and the right-looking look-ahead driver (above) finishes it.
-  const char* hl = getenv("FAER_B200_HOST_LEFT");
-  const i64 J = (hl && atoi(hl) != 0 && nblk >= 8) ? nblk / 2 : 0;
+  const i64 J = (hybrid && nblk >= 8) ? nblk / 2 : 0;
   LltResult r{true, 0, 0};
   if (J > 0) {
     ensure_streams();
@@ -689,7 +714,7 @@ LltResult llt_host_pipelined_f64(double* hostA, i64 host_ld, i64 n, i64 nb, doub
     tail.host = hostA + J0 * host_ld + J0;
     tail.host_ld = host_ld;
     tail.s_d2h = s_d2h;
-    tail.up.assign((size_t)(nblk - J), pipe.up[(size_t)(nblk - 1)]);
+    tail.up.assign(llt_block_bounds(nt, nb, false).size(), pipe.up[(size_t)(nblk - 1)]);
     g_llt_pipe = &tail;
     LltResult rt = dist_llt_f64(dA + J0 * n + J0, n, nt, nb, reg_delta, reg_eps, /*lookahead | local*/ 3);
     g_llt_pipe = nullptr;
