@@ -1,7 +1,7 @@
 // Multi-GPU (one process per GPU) 1-D block-column-cyclic factorizations with NCCL panel broadcast over NVLink.
 //
 // The reference is a single-process CPU library (no collective anywhere), so this file has no reference
-// counterpart; it distributes the SAME factorizations (llt_f64.cu / lu_f64.cu kernels) the single-GPU entry points
+// counterpart; it distributes the SAME factorizations (llt.cu / lu_f64.cu kernels) the single-GPU entry points
 // use. SURVEY.md §8e: block column b (width nb) is owned by rank b % P; at step k the owner factors panel k,
 // broadcasts it (plus the pivots for LU) and every rank updates only its own block columns — one exchange per panel,
 // no reduction on the data path. Look-ahead: the owner of panel k+1 updates and factors it on a high-priority

@@ -427,7 +427,7 @@ FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(FaerV0_24_MatMut A, Fa
   return out;
 }
 
-// ---- f32 LLT (llt_f32.cu: the recursive driver with the f32 leaf) ----
+// ---- f32 LLT (llt.cu: the templated leaf kernel and recursive driver instantiated for float) ----
 static float read_real_f32(const void* p) {
   float v;
   if (is_device_pointer(p)) FB_CUDA_CHECK(cudaMemcpy(&v, p, sizeof(float), cudaMemcpyDeviceToHost));

@@ -35,7 +35,7 @@ void gemm_c32(cudaStream_t stream, VF dst, int dst_struct, int accum, VCF lhs, i
 void solve_lower_triangular_in_place_f32(cudaStream_t stream, VCF tril, bool unit, VF rhs);
 void solve_upper_triangular_in_place_f32(cudaStream_t stream, VCF triu, bool unit, VF rhs);
 
-// f32 LLT (llt_f32.cu): same contract as llt_cholesky_in_place_f64 / llt_solve_in_place_f64 (linalg_f64.cuh)
+// f32 LLT (llt.cu, instantiated for float): same contract as llt_cholesky_in_place_f64 / llt_solve_in_place_f64 (linalg_f64.cuh)
 struct LltResult;
 struct LltParams;
 LltResult llt_cholesky_in_place_f32(cudaStream_t stream, VF A, float reg_delta, float reg_eps, LltParams params);

@@ -11,7 +11,7 @@
 //       regularisation 122-144 (expected signs); d == 0 or non-finite -> ZeroPivot(c); column c *= recip(d_c).
 //   solve.rs:11-49: unit-lower solve with L, rows scaled by recip(d_i), unit-upper solve with L^H.
 //
-// B200 mapping: the same shape as the LLT path (llt_f64.cu, left untouched): one CTA factors a <= 128-wide diagonal block
+// B200 mapping: the same shape as the LLT path (llt.cu, left untouched): one CTA factors a <= 128-wide diagonal block
 // with the block in registers (16 update warps) while 4 pivot warps keep a bit-identical copy of the diagonal and do the
 // serial pivot arithmetic of column j + 1 during the update of column j; the host recursion splits in halves so that the
 // flops are DMMA GEMMs with a large contracted dimension. The only extra traffic against LLT is the copy of the solved

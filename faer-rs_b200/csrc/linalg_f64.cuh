@@ -48,7 +48,7 @@ LdltResult ldlt_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double
 // rhs <- (L D L^T)^-1 rhs (ldlt/solve.rs:11-49); D: device pointer, dstride elements apart
 void ldlt_solve_in_place_f64(cudaStream_t stream, VCD L, const double* D, i64 dstride, VD rhs);
 
-// same factorisation, device-only (no sync / read-back); status accumulates in d_info (see llt_f64.cu)
+// same factorisation, device-only (no sync / read-back); status accumulates in d_info (see llt.cu)
 void llt_cholesky_device_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, long long* d_info, i64 j0);
 
 // ---- lu::partial_pivoting::factor (reference: faer/src/linalg/lu/partial_pivoting/factor.rs:234-295) ----

@@ -1,4 +1,4 @@
-// P1 + driver: in-place lower Cholesky (LLT), f64.
+// P1 + driver: in-place lower Cholesky (LLT), f64 and f32 (one templated leaf kernel and recursive driver).
 //
 // Reference: faer/src/linalg/cholesky/llt/factor.rs:68-97 -> ldlt/factor.rs:367-498
 // (`cholesky_recursion_right_looking`: for each block column: factor A00, A10 <- A10 * L00^-H,
@@ -17,6 +17,7 @@
 //   * each column costs one __syncthreads; the unscaled pivot column travels through a double-buffered shared vector.
 // The panel solve is G3 and the trailing update is the lower-masked DMMA GEMM (G2). A device status word carries the
 // first failing column / the regularisation count and is read back once per factorisation.
+#include "gemm_f32.cuh"
 #include "linalg_f64.cuh"
 
 namespace fb {
@@ -28,12 +29,20 @@ constexpr int POTF2_UPD_WARPS = 16;
 constexpr int POTF2_THREADS = POTF2_UPD_WARPS * 32 + POTF2_MAX;  // 512 update threads + 128 pivot threads
 constexpr int POTF2_CB = POTF2_MAX / POTF2_UPD_WARPS;           // column slots per update thread (8)
 
+// scalar-type dispatch of the two building blocks the recursion calls (G3 solve, lower-masked GEMM)
+inline void solve_lower(cudaStream_t st, VCD tri, bool unit, VD rhs) { solve_lower_triangular_in_place_f64(st, tri, unit, rhs); }
+inline void solve_lower(cudaStream_t st, VCF tri, bool unit, VF rhs) { solve_lower_triangular_in_place_f32(st, tri, unit, rhs); }
+// dst(lower) -= a * a^H
+inline void gemm_lower_update(cudaStream_t st, VD dst, VCD a) { gemm_f64(st, dst, TRI_LOWER, 1, a, RECT, a.t(), RECT, -1.0); }
+inline void gemm_lower_update(cudaStream_t st, VF dst, VCF a) { gemm_f32(st, dst, TRI_LOWER, 1, a, RECT, a.t(), RECT, -1.0f); }
+
 // info[0]: first failing global column (or -1), info[1]: regularisation count
-__global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict__ A, i64 rs, i64 cs, int n, i64 j0,
-                                                               int regularize, double eps, double delta,
+template <class T>
+__global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(T* __restrict__ A, i64 rs, i64 cs, int n, i64 j0,
+                                                               int regularize, T eps, T delta,
                                                                long long* __restrict__ info) {
-  __shared__ double colbuf[2][POTF2_MAX];
-  __shared__ double s_inv[2];
+  __shared__ T colbuf[2][POTF2_MAX];
+  __shared__ T s_inv[2];
   __shared__ int s_fail[2];
   __shared__ int s_count;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -43,15 +52,15 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
   if (tid == 0) s_count = 0;
 
   // update threads: rows i = lane + 32a, columns c = warp + 16b, kept iff c <= i < n
-  double a[4][POTF2_CB];
-  double dp = 0.0;  // pivot threads: diagonal entry p
+  T a[4][POTF2_CB];
+  T dp = T(0);  // pivot threads: diagonal entry p
   if (is_upd) {
 #pragma unroll
     for (int ai = 0; ai < 4; ++ai)
 #pragma unroll
       for (int bi = 0; bi < POTF2_CB; ++bi) {
         const int i = lane + 32 * ai, c = warp + POTF2_UPD_WARPS * bi;
-        a[ai][bi] = (i < n && c <= i) ? A[(i64)i * rs + (i64)c * cs] : 0.0;
+        a[ai][bi] = (i < n && c <= i) ? A[(i64)i * rs + (i64)c * cs] : T(0);
       }
   } else if (p < n) {
     dp = A[(i64)p * rs + (i64)p * cs];
@@ -59,7 +68,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
   __syncthreads();  // s_count initialised
 
   // serial pivot arithmetic of column jc (reference ldlt/factor.rs:122-160), done by ONE pivot thread
-  auto publish_pivot = [&](int jc, double d) {
+  auto publish_pivot = [&](int jc, T d) {
     int fail = 0;
     if (regularize) {
       if (d <= eps) {  // LLT: sign == +1
@@ -67,13 +76,13 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
         s_count += 1;  // single writer per column, ordered by the per-column barrier
       }
     }
-    double inv = 0.0;
-    if (!(d > 0.0)) {
+    T inv = T(0);
+    if (!(d > T(0))) {
       fail = 1;
     } else {
-      const double sd = sqrt(d);
-      if (sd == 0.0 || !isfinite(sd)) fail = 1;
-      else inv = 1.0 / sd;
+      const T sd = sqrt(d);
+      if (sd == T(0) || !isfinite(sd)) fail = 1;
+      else inv = T(1) / sd;
     }
     s_inv[jc & 1] = inv;
     s_fail[jc & 1] = fail;
@@ -90,17 +99,17 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
   __syncthreads();
 
   for (int j = 0; j < n; ++j) {
-    const double* col = colbuf[j & 1];
+    const T* col = colbuf[j & 1];
     if (s_fail[j & 1]) {
       if (tid == 0) info[0] = j0 + j;
       return;
     }
-    const double inv = s_inv[j & 1];
+    const T inv = s_inv[j & 1];
     if (!is_upd) {
       // pivot group: keep the diagonal current with the SAME fma the update threads apply to a_pp, then start the
       // next column's pivot arithmetic immediately
       if (p > j && p < n) {
-        const double l = col[p] * inv;
+        const T l = col[p] * inv;
         dp = fma(-l, l, dp);
         if (p == j + 1) publish_pivot(j + 1, dp);
       }
@@ -119,14 +128,14 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
       // trailing update: a_ic <- fma(-l_cj, l_ij, a_ic) for j < c <= i. The column test depends only on
       // (warp, bi, j): warp-uniform, so dead column slots are BRANCHED over (no predicated-off instruction issue).
       if (warp + POTF2_UPD_WARPS * (POTF2_CB - 1) > j) {
-        double li[4];
+        T li[4];
 #pragma unroll
         for (int ai = 0; ai < 4; ++ai) li[ai] = col[lane + 32 * ai] * inv;
 #pragma unroll
         for (int bi = 0; bi < POTF2_CB; ++bi) {
           const int c = warp + POTF2_UPD_WARPS * bi;
           if (c > j && c < n) {
-            const double lc = col[c] * inv;
+            const T lc = col[c] * inv;
 #pragma unroll
             for (int ai = 0; ai < 4; ++ai) {
               const int i = lane + 32 * ai;
@@ -140,10 +149,10 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
       // owners of column j+1 publish it (unscaled) into the other buffer
       if (j + 1 < n && warp == ((j + 1) & (POTF2_UPD_WARPS - 1))) {
         const int nbk = (j + 1) / POTF2_UPD_WARPS;
-        double* nxt = colbuf[(j + 1) & 1];
+        T* nxt = colbuf[(j + 1) & 1];
 #pragma unroll
         for (int ai = 0; ai < 4; ++ai) {
-          double v = 0.0;
+          T v = T(0);
 #pragma unroll
           for (int bi = 0; bi < POTF2_CB; ++bi)
             if (bi == nbk) v = a[ai][bi];
@@ -156,10 +165,11 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(double* __restrict
   if (tid == 0 && s_count) info[1] += s_count;
 }
 
+template <class T>
 struct LltCtx {
   cudaStream_t stream;
   int regularize;
-  double eps, delta;
+  T eps, delta;
   long long* d_info;
   i64 nb;  // leaf (diagonal block) size, <= POTF2_MAX
 };
@@ -168,10 +178,11 @@ struct LltCtx {
 // update the trailing lower triangle, continue) but split in HALVES instead of fixed 128-wide steps, so that
 // almost all flops are DMMA GEMMs with a large contracted dimension (k = n/2, n/4, ...): the trailing matrix is
 // read/written O(log n) times instead of n/128 times. Leaves (<= nb) are the single-CTA potf2 kernel.
-void llt_rec(const LltCtx& ctx, VD A, i64 j0) {
+template <class T>
+void llt_rec(const LltCtx<T>& ctx, View<T> A, i64 j0) {
   const i64 n = A.nrows;
   if (n <= ctx.nb) {
-    potf2_kernel<<<1, POTF2_THREADS, 0, ctx.stream>>>(A.ptr, A.rs, A.cs, (int)n, j0, ctx.regularize, ctx.eps, ctx.delta,
+    potf2_kernel<T><<<1, POTF2_THREADS, 0, ctx.stream>>>(A.ptr, A.rs, A.cs, (int)n, j0, ctx.regularize, ctx.eps, ctx.delta,
                                                       ctx.d_info);
     FB_CUDA_CHECK(cudaGetLastError());
     note_launch();
@@ -181,15 +192,44 @@ void llt_rec(const LltCtx& ctx, VD A, i64 j0) {
   i64 n1 = ((n / 2 + ctx.nb - 1) / ctx.nb) * ctx.nb;
   if (n1 >= n) n1 = ((n - 1) / ctx.nb) * ctx.nb;
   const i64 n2 = n - n1;
-  VD A11 = A.sub(0, 0, n1, n1), A21 = A.sub(n1, 0, n2, n1), A22 = A.sub(n1, n1, n2, n2);
+  View<T> A11 = A.sub(0, 0, n1, n1), A21 = A.sub(n1, 0, n2, n1), A22 = A.sub(n1, n1, n2, n2);
   llt_rec(ctx, A11, j0);
   // conj(L11) X = A21^T   (reference ldlt/factor.rs:421-426)
-  solve_lower_triangular_in_place_f64(ctx.stream, cv(A11), false, A21.t());
+  solve_lower(ctx.stream, cv(A11), false, A21.t());
   // A22(lower) += -1 * A21 * A21^H   (reference ldlt/factor.rs:435-446)
-  gemm_f64(ctx.stream, A22, TRI_LOWER, 1, cv(A21), RECT, cv(A21).t(), RECT, -1.0);
+  gemm_lower_update(ctx.stream, A22, cv(A21));
   llt_rec(ctx, A22, j0 + n1);
 }
 
+}  // namespace
+
+namespace {
+// the recursive driver with its own status word (one read-back per factorisation)
+template <class T>
+LltResult llt_recursive_in_place(cudaStream_t stream, View<T> A, T reg_delta, T reg_eps, LltParams params) {
+  LltResult res{true, 0, 0};
+  const int regularize = (reg_delta > T(0) && reg_eps > T(0)) ? 1 : 0;
+  i64 nb = (i64)params.block_size;
+  if (nb <= 0 || nb > POTF2_MAX) nb = POTF2_MAX;
+
+  long long* d_info = (long long*)ws_alloc(2 * sizeof(long long));
+  long long h_info[2] = {-1, 0};
+  FB_CUDA_CHECK(cudaMemcpyAsync(d_info, h_info, sizeof(h_info), cudaMemcpyHostToDevice, stream));
+
+  LltCtx<T> ctx{stream, regularize, reg_eps, reg_delta, d_info, nb};
+  llt_rec<T>(ctx, A, 0);
+
+  FB_CUDA_CHECK(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, stream));
+  FB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  ws_free(d_info);
+  if (h_info[0] >= 0) {
+    res.ok = false;
+    res.non_positive_pivot_index = (size_t)h_info[0];
+  } else {
+    res.dynamic_regularization_count = (size_t)h_info[1];
+  }
+  return res;
+}
 }  // namespace
 
 // Device-side variant for callers that own the status word (multi-GPU driver): no synchronisation, no read-back.
@@ -198,8 +238,8 @@ void llt_cholesky_device_f64(cudaStream_t stream, VD A, double reg_delta, double
   FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
   if (A.nrows == 0) return;
   const int regularize = (reg_delta > 0.0 && reg_eps > 0.0) ? 1 : 0;
-  LltCtx ctx{stream, regularize, reg_eps, reg_delta, d_info, POTF2_MAX};
-  llt_rec(ctx, A, j0);
+  LltCtx<double> ctx{stream, regularize, reg_eps, reg_delta, d_info, POTF2_MAX};
+  llt_rec<double>(ctx, A, j0);
 }
 
 LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, LltParams params) {
@@ -218,27 +258,21 @@ LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta,
     const i64 nbl = lookahead_block() ? lookahead_block() : 256;
     return dist_llt_f64(A.ptr, A.cs, n, nbl, reg_delta, reg_eps, /*lookahead | local*/ 3);
   }
-  const int regularize = (reg_delta > 0.0 && reg_eps > 0.0) ? 1 : 0;
-  i64 nb = (i64)params.block_size;
-  if (nb <= 0 || nb > POTF2_MAX) nb = POTF2_MAX;
+  return llt_recursive_in_place<double>(stream, A, reg_delta, reg_eps, params);
+}
 
-  long long* d_info = (long long*)ws_alloc(2 * sizeof(long long));
-  long long h_info[2] = {-1, 0};
-  FB_CUDA_CHECK(cudaMemcpyAsync(d_info, h_info, sizeof(h_info), cudaMemcpyHostToDevice, stream));
+// f32: the same leaf kernel and recursive driver instantiated for float (trailing updates on the 3xTF32 GEMM — tcgen05 for large
+// products —, panel solves on the f32 triangular solve). The look-ahead block-column drivers (dist.cu) are f64-only.
+LltResult llt_cholesky_in_place_f32(cudaStream_t stream, VF A, float reg_delta, float reg_eps, LltParams params) {
+  FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
+  if (A.nrows == 0) return LltResult{true, 0, 0};
+  return llt_recursive_in_place<float>(stream, A, reg_delta, reg_eps, params);
+}
 
-  LltCtx ctx{stream, regularize, reg_eps, reg_delta, d_info, nb};
-  llt_rec(ctx, A, 0);
-
-  FB_CUDA_CHECK(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, stream));
-  FB_CUDA_CHECK(cudaStreamSynchronize(stream));
-  ws_free(d_info);
-  if (h_info[0] >= 0) {
-    res.ok = false;
-    res.non_positive_pivot_index = (size_t)h_info[0];
-  } else {
-    res.dynamic_regularization_count = (size_t)h_info[1];
-  }
-  return res;
+void llt_solve_in_place_f32(cudaStream_t stream, VCF L, VF rhs) {
+  FB_ASSERT(L.nrows == L.ncols && rhs.nrows == L.nrows, "LLT solve shape mismatch");
+  solve_lower_triangular_in_place_f32(stream, L, false, rhs);
+  solve_upper_triangular_in_place_f32(stream, L.t(), false, rhs);
 }
 
 }  // namespace fb

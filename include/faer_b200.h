@@ -268,7 +268,7 @@ struct FaerV0_24_Layout libfaer_v0_23_qr_inverse_scratch_f64(size_t dim, size_t 
 void libfaer_v0_23_qr_inverse_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
 /* f32 LLT: faer.h:636 (LltParams_f32), 4036-4048 (factor), 4180-4216 (solve); same semantics as the f64 entry points.
- * Recursive driver with the f32 leaf (csrc/llt_f32.cu). */
+ * The templated leaf kernel and recursive driver of csrc/llt.cu instantiated for float. */
 struct FaerV0_24_LltParams libfaer_v0_23_LltParams_f32(void);
 struct FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_f32(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LltParams params);
 struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_LltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LltParams params);

@@ -123,8 +123,7 @@ def run_all(sv):
 
 def run_ldlt(sv):
     """Ldlt (solvers.rs:818-872) on a symmetric indefinite matrix with a dominant diagonal: test_solver identities, L / D
-    contracts, both sides, ZeroPivot. Separate from run_all so that the GPU run of the validated decompositions does not
-    depend on the LDLT kernel (first hardware run pending)."""
+    contracts, both sides, ZeroPivot. Separate from run_all (its own kernel: csrc/ldlt_f64.cu)."""
     rng = np.random.default_rng(7)
     n = 50
     G = rng.standard_normal((n, n))

@@ -1,5 +1,5 @@
-"""`*_reconstruct` / `*_inverse` on the factors through the C ABI (csrc/reconstruct.cu; compositions of validated kernels,
-written after the round's last GPU session — first hardware run pending). Reference tests restated for f64:
+"""`*_reconstruct` / `*_inverse` on the factors through the C ABI (csrc/reconstruct.cu; compositions of validated kernels).
+Reference tests restated for f64:
 llt/reconstruct.rs and inverse.rs tests (n = 50, eps * n), lu/partial_pivoting/reconstruct.rs and inverse.rs tests,
 qr/no_pivoting/reconstruct.rs tests ((100, 50) and (50, 100)) and inverse.rs tests."""
 import numpy as np

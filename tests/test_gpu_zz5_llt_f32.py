@@ -1,5 +1,5 @@
-"""f32 LLT through the C ABI (csrc/llt_f32.cu: the validated f64 leaf kernel and recursive driver with the scalar type
-changed) against the oracle in f32. FIRST RUN ON HARDWARE pending; sorts last for that reason.
+"""f32 LLT through the C ABI (csrc/llt.cu: the templated leaf kernel and recursive driver instantiated for float) against the
+oracle in f32.
 Contract as for f64 (tests/test_gpu_parity.py): error index and regularisation count exact, leaf blocks (n <= 64)
 bit-identical to the oracle's leaf, L L^T = A within 64 n u |A|, strict upper triangle untouched, solve within the
 backward bound."""

@@ -1,6 +1,5 @@
 """GPU tests of LDLT through the C ABI against the oracle's restatement, which
-tests/test_oracle_ldlt_cpu.py pins to the reference's own tests. FIRST RUN ON HARDWARE: the kernel and driver
-(csrc/ldlt_f64.cu) were written after the round's last GPU session; this file sorts last for that reason.
+tests/test_oracle_ldlt_cpu.py pins to the reference's own tests (kernel and driver: csrc/ldlt_f64.cu).
 
 Contract: ZeroPivot index and regularisation count exact; D and L within 64 n u |A| of the reconstruction and close to
 the oracle's (same recurrence, different blocking); leaf blocks (n <= 64) bit-identical to the oracle's leaf; the strict

@@ -1,6 +1,5 @@
 """Singular values through the C ABI (`svd` with U = V = None; BASELINE.json configs[4]) against LAPACK: bidiagonalization
-on the GPU + one bisection thread per value. FIRST RUN ON HARDWARE pending (csrc/svd.cu: three small kernels and the
-driver were written after the round's last GPU session; the bisection routine itself is checked on the CPU by
+on the GPU + one bisection thread per value (csrc/svd.cu; the bisection routine itself is checked on the CPU by
 tests/test_bidiag_sv_cpu.py, bidiag.cu by tests/test_gpu_condensed.py). Tolerance: the reference's own SVD tests use
 eps * n on unit-scale matrices (svd/mod.rs tests); here 32 max(m, n) u sigma_max."""
 import numpy as np

@@ -1,6 +1,5 @@
 """Eigenvalues of a self-adjoint matrix through the C ABI (`self_adjoint_evd` with U = None) against LAPACK:
-tridiagonalization on the GPU + one bisection thread per value. FIRST RUN ON HARDWARE pending (csrc/evd.cu: the small
-kernels and the driver were written after the round's last GPU session; the bisection routine is checked on the CPU by
+tridiagonalization on the GPU + one bisection thread per value (csrc/evd.cu; the bisection routine is checked on the CPU by
 tests/test_tridiag_ev_cpu.py, tridiag.cu by tests/test_gpu_condensed.py). Tolerance 32 n u |lambda|_max (the reference's
 EVD tests use eps * n on unit-scale matrices)."""
 import numpy as np

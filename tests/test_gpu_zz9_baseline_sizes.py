@@ -1,8 +1,7 @@
 """BASELINE.json configs at their full sizes, through size-independent properties (the oracle would take many minutes
 there): configs[2] LU n = 32768 on one GPU, configs[3] f32 QR 65536 x 4096, configs[4] bidiagonalization n = 8192 and c64
 GEMM n = 8192, plus tridiagonalization n = 8192. configs[1] (LLT n = 16384) is tests/test_gpu_parity.py. Operands live
-on the device; torch is the checker (probe products), never the path under test. This file sorts last on purpose:
-these cases were written after the round's last GPU session."""
+on the device; torch is the checker (probe products), never the path under test."""
 import numpy as np
 import pytest
 
