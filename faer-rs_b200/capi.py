@@ -187,14 +187,14 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_llt_factor_in_place_scratch_f64.restype = Layout
     lib.libfaer_v0_23_llt_factor_in_place_f64.argtypes = [MatMut, LltRegularization, P, MemAlloc, LltParams]
     lib.libfaer_v0_23_llt_factor_in_place_f64.restype = LltStatus
-    if hasattr(lib, "libfaer_v0_23_PartialPivLuParams_f64"):
-        lib.libfaer_v0_23_PartialPivLuParams_f64.argtypes = []
-        lib.libfaer_v0_23_PartialPivLuParams_f64.restype = PartialPivLuParams
+    for suf in ("f64", "f32"):
+        getattr(lib, f"libfaer_v0_23_PartialPivLuParams_{suf}").argtypes = []
+        getattr(lib, f"libfaer_v0_23_PartialPivLuParams_{suf}").restype = PartialPivLuParams
         for it in ("u32", "u64"):
-            f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_{it}_f64")
+            f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_{it}_{suf}")
             f.argtypes = [C.c_size_t, C.c_size_t, P, PartialPivLuParams]
             f.restype = Layout
-            f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_{it}_f64")
+            f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_{it}_{suf}")
             f.argtypes = [MatMut, SliceMut, SliceMut, P, MemAlloc, PartialPivLuParams]
             f.restype = PartialPivLuStatus
     for suf in ("f64", "f32"):
@@ -302,17 +302,17 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.restype = Layout
     lib.libfaer_v0_23_llt_solve_in_place_f64.argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]
     lib.libfaer_v0_23_llt_solve_in_place_f64.restype = None
-    for it in ("u32", "u64"):
-        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_{it}_f64")
+    for it, suf in [(i, s_) for i in ("u32", "u64") for s_ in ("f64", "f32")]:
+        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_{it}_{suf}")
         f.argtypes = [C.c_size_t, C.c_size_t, P]
         f.restype = Layout
-        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_f64")
+        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_{suf}")
         f.argtypes = [MatRef, MatRef, C.c_int, SliceMut, SliceMut, MatMut, P, MemAlloc]
         f.restype = None
-        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_{it}_f64")
+        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_{it}_{suf}")
         f.argtypes = [C.c_size_t, C.c_size_t, P]
         f.restype = Layout
-        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_{it}_f64")
+        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_{it}_{suf}")
         f.argtypes = [MatRef, MatRef, C.c_int, SliceMut, SliceMut, MatMut, P, MemAlloc]
         f.restype = None
     lib.libfaer_v0_23_get_global_par.argtypes = []

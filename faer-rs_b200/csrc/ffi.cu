@@ -220,6 +220,34 @@ FaerV0_24_SvdStatus svd_entry(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_
 }
 }  // namespace
 
+// widening / narrowing copies and the f32 row gather of the f32 LU entry points (below)
+namespace {
+template <class TD, class TS>
+__global__ void ffi_cast_kernel(TD* __restrict__ dst, i64 drs, i64 dcs, const TS* __restrict__ src, i64 srs, i64 scs, i64 m,
+                                i64 c0) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = c0 + blockIdx.y;
+  if (i < m) dst[i * drs + j * dcs] = (TD)src[i * srs + j * scs];
+}
+template <class TD, class TS>
+void ffi_cast(cudaStream_t st, TD* dst, i64 drs, i64 dcs, const TS* src, i64 srs, i64 scs, i64 m, i64 n) {
+  if (m == 0 || n == 0) return;
+  for (i64 c0 = 0; c0 < n; c0 += 65535) {
+    const i64 nc = std::min<i64>(65535, n - c0);
+    ffi_cast_kernel<TD, TS><<<dim3((unsigned)((m + 255) / 256), (unsigned)nc), 256, 0, st>>>(dst, drs, dcs, src, srs, scs, m, c0);
+    note_launch();
+  }
+  FB_CUDA_CHECK(cudaGetLastError());
+}
+__global__ void ffi_gather_rows_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, i64 rs, i64 cs, i64 nrows,
+                                           const long long* __restrict__ perm) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 c = blockIdx.y;
+  if (i < nrows) dst[c * nrows + i] = src[perm[i] * rs + c * cs];
+}
+}  // namespace
+
+
 extern "C" {
 
 void libfaer_v0_23_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
@@ -616,6 +644,58 @@ FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f6
   return lu_entry(A, perm_fwd, perm_bwd, params, 8);
 }
 
+// ---- f32 partial-pivoting LU: computed in f64, like the f32 `svd` / `self_adjoint_evd`. The f32 matrix is widened on the
+// device, factored by the f64 drivers (fused sub-panel kernel, TMA-fed GEMM, SM partition) and rounded back: the factors carry
+// one f32 rounding instead of an f32 elimination's accumulated ones, and the pivot search sees f64 values (so a pivot can
+// differ from an all-f32 elimination's where two candidates agree to f32 precision — either choice is a valid partial
+// pivot). The solves run on the native f32 triangular solves.
+FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f32(void) { return libfaer_v0_23_PartialPivLuParams_f64(); }
+FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32_f32(size_t nrows, size_t ncols, FaerV0_24_Par par,
+                                                                              FaerV0_24_PartialPivLuParams params) {
+  (void)par; (void)params;
+  return lu_scratch(nrows, ncols, 4);
+}
+FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_f32(size_t nrows, size_t ncols, FaerV0_24_Par par,
+                                                                              FaerV0_24_PartialPivLuParams params) {
+  (void)par; (void)params;
+  return lu_scratch(nrows, ncols, 8);
+}
+static FaerV0_24_PartialPivLuStatus lu_entry_f32(FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd,
+                                                 FaerV0_24_PartialPivLuParams params, int idx_bytes) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  FB_ASSERT(A.nrows == 0 || (perm_fwd.ptr != nullptr && perm_bwd.ptr != nullptr), "null permutation slice");
+  const i64 m = (i64)A.nrows, n = (i64)A.ncols;
+  StagedMat a(A.ptr, m, n, (i64)A.row_stride, (i64)A.col_stride, 4, true, true, st);
+  VF av = a.view<float>();
+  const i64 ld = std::max<i64>(1, (m + 1) & ~(i64)1);
+  double* W = (double*)ws_alloc((size_t)ld * (size_t)std::max<i64>(n, 1) * 8);
+  ffi_cast<double, float>(st, W, 1, ld, av.ptr, av.rs, av.cs, m, n);
+  const size_t cnt = lu_partial_piv_in_place_f64(st, VD{W, m, n, 1, ld}, perm_fwd.ptr, perm_bwd.ptr, idx_bytes,
+                                                 PartialPivLuParams{params.recursion_threshold, params.block_size,
+                                                                    params.par_threshold});
+  ffi_cast<float, double>(st, av.ptr, av.rs, av.cs, W, 1, ld, m, n);
+  finish_all(st, {&a});
+  ws_free(W);
+  FaerV0_24_PartialPivLuStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_PartialPivLuStatus_Ok;
+  out.ok.transposition_count = cnt;
+  return out;
+}
+FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u32_f32(
+    FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd, FaerV0_24_Par par, FaerV0_24_MemAlloc mem,
+    FaerV0_24_PartialPivLuParams params) {
+  (void)par; (void)mem;
+  return lu_entry_f32(A, perm_fwd, perm_bwd, params, 4);
+}
+FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f32(
+    FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd, FaerV0_24_Par par, FaerV0_24_MemAlloc mem,
+    FaerV0_24_PartialPivLuParams params) {
+  (void)par; (void)mem;
+  return lu_entry_f32(A, perm_fwd, perm_bwd, params, 8);
+}
+
 // ---- Householder QR (no pivoting) + block-Householder sequence application, f64 and f32 (helpers above) ----
 #define FB_QR_FFI(SUF, T)                                                                                              \
   FaerV0_24_QrParams libfaer_v0_23_QrParams_##SUF(void) { return FaerV0_24_QrParams{48 * 48, 192 * 256}; }             \
@@ -796,6 +876,71 @@ void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_f64(FaerV0_24_Mat
   (void)A_conj; (void)perm_fwd; (void)par; (void)mem;
   lu_solve_entry(L, U, perm_bwd, rhs, 8, true);
 }
+
+// f32 LU solves (lu/partial_pivoting/solve.rs:21-86) on the native f32 triangular solves
+static void lu_solve_entry_f32(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_SliceRef perm_slice, FaerV0_24_MatMut rhs,
+                               int idx_bytes, bool transpose) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t n = L.nrows;
+  FB_ASSERT(L.ncols == n && U.nrows == n && U.ncols == n && rhs.nrows == n, "LU solve shape mismatch");
+  std::vector<long long> perm = read_perm(perm_slice.ptr, n, idx_bytes);
+  for (size_t i = 0; i < n; ++i) FB_ASSERT(perm[i] >= 0 && (size_t)perm[i] < n, "invalid permutation entry");
+  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, 4, true, false, st);
+  StagedMat u(U.ptr, (i64)U.nrows, (i64)U.ncols, (i64)U.row_stride, (i64)U.col_stride, 4, true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 4, true, true, st);
+  VCF lv = l.view<const float>(), uv = u.view<const float>();
+  VF rv = r.view<float>();
+  const i64 k = rv.ncols;
+  auto permute = [&]() {  // rhs[i, :] <- rhs[perm[i], :]
+    if (n == 0 || k == 0) return;
+    FB_ASSERT(k < 65536, "too many right-hand sides for one permutation launch");
+    long long* d_perm = (long long*)ws_alloc(n * 8);
+    float* tmp = (float*)ws_alloc(n * (size_t)k * 4);
+    FB_CUDA_CHECK(cudaMemcpyAsync(d_perm, perm.data(), n * 8, cudaMemcpyHostToDevice, st));
+    ffi_gather_rows_f32_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)k), 256, 0, st>>>(tmp, rv.ptr, rv.rs, rv.cs, (i64)n, d_perm);
+    note_launch();
+    ffi_cast<float, float>(st, rv.ptr, rv.rs, rv.cs, tmp, 1, (i64)n, (i64)n, k);
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    ws_free(tmp);
+    ws_free(d_perm);
+  };
+  if (!transpose) {
+    permute();
+    solve_lower_triangular_in_place_f32(st, lv, true, rv);
+    solve_upper_triangular_in_place_f32(st, uv, false, rv);
+  } else {
+    solve_lower_triangular_in_place_f32(st, uv.t(), false, rv);
+    solve_upper_triangular_in_place_f32(st, lv.t(), true, rv);
+    permute();
+  }
+  finish_all(st, {&l, &u, &r});
+}
+#define FB_LU_SOLVE_F32(IT, BYTES)                                                                                              \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_##IT##_f32(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) { \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{dim * rhs_ncols * sizeof(float), 64};                                                               \
+  }                                                                                                                             \
+  void libfaer_v0_23_partial_piv_lu_solve_in_place_##IT##_f32(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj,    \
+                                                             FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,          \
+                                                             FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) { \
+    (void)A_conj; (void)perm_bwd; (void)par; (void)mem;                                                                         \
+    lu_solve_entry_f32(L, U, perm_fwd, rhs, BYTES, false);                                                                      \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_##IT##_f32(size_t dim, size_t rhs_ncols,       \
+                                                                                            FaerV0_24_Par par) {                \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{dim * rhs_ncols * sizeof(float), 64};                                                               \
+  }                                                                                                                             \
+  void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_##IT##_f32(                                                        \
+      FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj, FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,   \
+      FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                                                        \
+    (void)A_conj; (void)perm_fwd; (void)par; (void)mem;                                                                         \
+    lu_solve_entry_f32(L, U, perm_bwd, rhs, BYTES, true);                                                                       \
+  }
+FB_LU_SOLVE_F32(u32, 4)
+FB_LU_SOLVE_F32(u64, 8)
+#undef FB_LU_SOLVE_F32
 
 // ---- SVD (svd.cu: values by bisection; svd_vectors.cu: with U / V) ----
 #define FB_SVD_FFI(SUF, T)                                                                                             \

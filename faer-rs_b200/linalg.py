@@ -282,11 +282,12 @@ def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None, U=
     rhs <- A^-1 rhs from the packed factors (L unit-lower below the diagonal, U on/above) and the row permutation.
     With `U` given, `LU` is read as L only (its strict lower part) and `U` as the upper factor, as the reference's
     separate `L`, `U` arguments."""
-    _check_f64(LU, rhs)
     lib = capi.load()
+    suf = _suf(LU)
+    assert _suf(rhs) == suf
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
     it = {4: "u32", 8: "u64"}[isz]
-    getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_f64")(
+    getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_{suf}")(
         capi.mat_ref(LU), capi.mat_ref(LU if U is None else U), conj, capi.slice_mut(perm), capi.slice_mut(perm_inv), capi.mat_mut(rhs),
         par or capi.par_default(), capi.MemAlloc(None, 0))
 
@@ -294,11 +295,12 @@ def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None, U=
 def lu_solve_transpose_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None, U=None) -> None:
     """lu::partial_pivoting::solve::solve_transpose_in_place_with_conj (lu/partial_pivoting/solve.rs:55-86):
     rhs <- A^-T rhs from the packed factors and the row permutation (its inverse array is the one used)."""
-    _check_f64(LU, rhs)
     lib = capi.load()
+    suf = _suf(LU)
+    assert _suf(rhs) == suf
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
     it = {4: "u32", 8: "u64"}[isz]
-    getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_{it}_f64")(
+    getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_{it}_{suf}")(
         capi.mat_ref(LU), capi.mat_ref(LU if U is None else U), conj, capi.slice_mut(perm), capi.slice_mut(perm_inv), capi.mat_mut(rhs),
         par or capi.par_default(), capi.MemAlloc(None, 0))
 
@@ -603,17 +605,17 @@ class PartialPivLuInfo:
 
 def lu_in_place(A, perm, perm_inv, par=None, params=None) -> PartialPivLuInfo:
     """In-place P A = L U. `perm`/`perm_inv`: uint32/uint64 arrays (numpy) or int32/int64 CUDA tensors of
-    length nrows; (P A)[i, :] = A[perm[i], :]."""
-    _check_f64(A)
+    length nrows; (P A)[i, :] = A[perm[i], :]. f64, or f32 (computed in f64 on the device and rounded back)."""
     lib = capi.load()
-    params = params or lib.libfaer_v0_23_PartialPivLuParams_f64()
+    suf = _suf(A)
+    params = params or getattr(lib, f"libfaer_v0_23_PartialPivLuParams_{suf}")()
     par = par or capi.par_default()
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
     it = {4: "u32", 8: "u64"}[isz]
     m, n = A.shape
-    lay = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_{it}_f64")(m, n, par, params)
+    lay = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_{it}_{suf}")(m, n, par, params)
     scratch = np.empty(lay.len_bytes + lay.align_bytes, dtype=np.uint8)
-    st = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_{it}_f64")(
+    st = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_{it}_{suf}")(
         capi.mat_mut(A), capi.slice_mut(perm), capi.slice_mut(perm_inv), par,
         capi.MemAlloc(scratch.ctypes.data, scratch.size), params)
     if st.tag != 0:

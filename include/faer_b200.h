@@ -292,6 +292,13 @@ struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32
 struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_f64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
 struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u32_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
 struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
+/* f32: the same entry points; computed in f64 on the device (the matrix is widened, factored by the f64 drivers and rounded
+ * back: csrc/ffi.cu), the solves on the native f32 triangular solves. faer.h:648, 4456-4461 / lib.rs:1952-2020 for f32. */
+struct FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f32(void);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32_f32(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_f32(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u32_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
 
 /* Householder QR without pivoting + block-Householder sequence application, f64 and f32.
  * params: faer-ffi/src/lib.rs:671-675, faer.h:670; recommended_block_size: lib.rs:1520-1527, faer.h:5718;
@@ -340,6 +347,14 @@ struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_sc
 struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u64_f64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
 void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u32_f64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_f64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u32_f32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u64_f32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_solve_in_place_u32_f32(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_partial_piv_lu_solve_in_place_u64_f32(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u32_f32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u64_f32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u32_f32(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_f32(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
 /* solves on the QR factors: faer-ffi/src/lib.rs:1560-1660 (qr_solve_in_place[_scratch] 1560-1592,
  * qr_solve_transpose_in_place[_scratch] 1593-1625, qr_solve_lstsq_in_place[_scratch] 1626-1660); faer.h:5828, 5864, 5906,
