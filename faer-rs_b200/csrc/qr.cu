@@ -721,9 +721,20 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
   int dev = 0, num_sms = 0;
   FB_CUDA_CHECK(cudaGetDevice(&dev));
   FB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  const int Gmax = std::min(num_sms, 160);  // the panel kernel's record reduction covers <= 160 CTAs
+  const int Gfull = std::min(num_sms, 160);  // the panel kernel's record reduction covers <= 160 CTAs
+  int Gmax = Gfull;
+  {
+    // fewer, fatter CTAs shorten the per-column grid exchange (barrier participants, records every CTA reads) at the price
+    // of longer per-CTA row loops; FAER_B200_QR_PANEL_CTAS caps the grid (the slices must still fit shared memory)
+    static int cap = -1;
+    if (cap < 0) {
+      const char* e = getenv("FAER_B200_QR_PANEL_CTAS");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap > 0) Gmax = std::min(Gmax, cap);
+  }
   // scratch
-  const size_t part_elems = (size_t)2 * Gmax * QR_NV, rowv_elems = (size_t)2 * QR_PW;
+  const size_t part_elems = (size_t)2 * Gfull * QR_NV, rowv_elems = (size_t)2 * QR_PW;
   char* scb = (char*)ws_alloc((part_elems + rowv_elems + QR_PW) * sizeof(T) + 64);
   QrScratch<T> sc;
   sc.part = (T*)scb;
@@ -763,6 +774,11 @@ i64 qr_in_place(cudaStream_t st, View<T> A, View<T> H) {
       }
       int G = (int)std::min<i64>(Gmax, (mp + 63) / 64);
       if (G < 1) G = 1;
+      {
+        // the slices must fit shared memory whatever the cap says
+        const i64 gmin = ((i64)mp * (i64)((int)sw | 1) * (i64)sizeof(T) + 200 * 1024 - 1) / (200 * 1024);
+        G = (int)std::min<i64>(std::max<i64>(G, gmin), std::min(num_sms, 160));
+      }
       int rows_per_cta = (int)((mp + G - 1) / G);
       const size_t smem = (size_t)rows_per_cta * (size_t)((int)sw | 1) * sizeof(T);
       FB_ASSERT(smem <= 200 * 1024, "QR panel too tall for the shared-memory slices");

@@ -320,9 +320,19 @@ void StagedMat::finish() {
     else if (mode_ == 2)
       FB_CUDA_CHECK(cudaMemcpy2DAsync(base, (size_t)rs_ * elem_, buf_, (size_t)dev_rs_ * elem_, (size_t)ncols_ * elem_,
                                       (size_t)nrows_, cudaMemcpyDeviceToHost, stream_));
-    else
-      FB_CUDA_CHECK(cudaMemcpyAsync(base + span_lo_ * (i64)elem_, buf_, (size_t)span_elems_ * elem_,
-                                    cudaMemcpyDeviceToHost, stream_));
+    else {
+      // general strides: the mirror covers the whole spanned address range, but only the view's OWN elements go back —
+      // another output of the same call may live in the gaps (e.g. A = buf[0::2], Q_coeff = buf[1::2]) and must not be
+      // overwritten with the stale bytes this mirror was filled with
+      std::vector<char> tmp((size_t)span_elems_ * elem_);
+      FB_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), buf_, tmp.size(), cudaMemcpyDeviceToHost, stream_));
+      FB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      for (i64 j = 0; j < ncols_; ++j)
+        for (i64 i = 0; i < nrows_; ++i) {
+          const i64 off = (i * rs_ + j * cs_) * (i64)elem_;
+          memcpy(base + off, tmp.data() + (off - span_lo_ * (i64)elem_), elem_);
+        }
+    }
     FB_CUDA_CHECK(cudaStreamSynchronize(stream_));
   }
   ws_free(buf_);

@@ -213,3 +213,23 @@ def test_qr_tall_skinny_property_f32(fb, cuda_dev):
     assert float(B[n:, :].abs().max()) <= 128 * u * scale
     Rl = np.linalg.qr(A0.cpu().numpy().astype(np.float64), mode="r")
     assert np.allclose(np.abs(R.cpu().numpy()), np.abs(Rl), rtol=2e-3, atol=2e-3 * np.abs(Rl).max())
+
+
+def test_qr_outputs_interleaved_in_one_host_buffer(fb):
+    """Two host outputs of one call living in the same address range (A = buf[0::2], Q_coeff = buf[1::2]; general strides are
+    mirrored by address range inside the call): each must come back complete — only a view's own elements are written back."""
+    la = fb.linalg
+    rng = np.random.default_rng(77)
+    m, n, bs = 60, 24, 8
+    A0 = np.asfortranarray(rng.standard_normal((m, n)))
+    want = A0.copy(order="F"); Hw = np.zeros((bs, n), order="F")
+    la.qr_in_place(want, Hw)
+    big = np.full(2 * m * n, 7.0)
+    A = big[0::2][:m * n].reshape((m, n), order="F")
+    H = big[1::2][:bs * n].reshape((bs, n), order="F")
+    A[...] = A0
+    H[...] = 0.0
+    assert A.strides == (16, 16 * m) and not A.flags.f_contiguous
+    la.qr_in_place(A, H)
+    assert np.array_equal(A, want) and np.array_equal(H, Hw)
+    assert np.all(big[1::2][bs * n:] == 7.0)  # the rest of the odd slots was nobody's
