@@ -507,40 +507,9 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
   FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_start, 0));
   if (two_streams) FB_CUDA_CHECK(cudaStreamWaitEvent(sm, ev_start, 0));
 
-  const std::vector<i64> b0 = llt_block_bounds(n, nb, /*uniform*/ P > 1);
+  const std::vector<i64> b0 = llt_block_bounds(n, nb, /*uniform*/ P > 1 || !lookahead);
   const i64 nblk = (i64)b0.size() - 1;
   auto col_off = [&](i64 b) { return P == 1 ? b0[(size_t)b] : local_off(b, nb, P) ; };  // local column of block b (owned)
-  // Single GPU: the trailing update of TWO consecutive full-width panels is applied as one k = 2 nb product (roles 1 / 2 = first /
-  // second panel of a pair): at nb = 256 the k = 512 update runs on the TMA-fed kernel at 32.5 TFLOP/s where two k = 256 updates
-  // get 29.9 (profiles/r02_ws_shapes.log). The panel chain keeps its 256-wide steps: the look-ahead update of the next block
-  // column takes the pair's panels straight from the matrix (they are final). FAER_B200_LLT_NO_PAIR=1 switches it off.
-  std::vector<int> role((size_t)nblk, 0);
-  if (P == 1 && nb >= 256 && !getenv("FAER_B200_LLT_NO_PAIR") && !getenv("FAER_B200_LLT_SPLIT_BULK")) {
-    for (i64 k = 0; k + 2 < nblk;) {
-      if (b0[(size_t)k + 1] - b0[(size_t)k] == nb && b0[(size_t)k + 2] - b0[(size_t)k + 1] == nb) {
-        role[(size_t)k] = 1;
-        role[(size_t)k + 1] = 2;
-        k += 2;
-      } else {
-        ++k;
-      }
-    }
-  }
-  // block column j (> k) -= pair(k - 1, k) * pair(k - 1, k)[rows of block j]^T, panels read in place (P == 1)
-  auto update_block_col_pair = [&](cudaStream_t st, i64 k, i64 j, bool first_touch) {
-    if (pipe && first_touch) FB_CUDA_CHECK(cudaStreamWaitEvent(st, pipe->up[(size_t)j], 0));
-    const i64 p0 = b0[(size_t)k - 1], pw = b0[(size_t)k + 1] - p0;
-    const i64 j0 = b0[(size_t)j], jb = b0[(size_t)j + 1] - j0;
-    VCD Wj{A_local + p0 * ld + j0, jb, pw, 1, ld};
-    VD djj{A_local + j0 * ld + j0, jb, jb, 1, ld};
-    gemm_f64(st, djj, TRI_LOWER, 1, Wj, RECT, Wj.t(), RECT, -1.0);
-    const i64 below = n - j0 - jb;
-    if (below > 0) {
-      VCD Wb{A_local + p0 * ld + j0 + jb, below, pw, 1, ld};
-      VD dbj{A_local + j0 * ld + j0 + jb, below, jb, 1, ld};
-      gemm_f64(st, dbj, 1, Wb, Wj.t(), -1.0);
-    }
-  };
   // two panel buffers (double buffering for look-ahead)
   double* W[2];
   W[0] = (double*)ws_alloc((size_t)n * nb * 8);
@@ -609,25 +578,11 @@ LltResult dist_llt_f64(double* A_local, i64 ld, i64 n, i64 nb, double reg_delta,
         // look-ahead: bring block column k+1 up to date first (on the panel stream), then factor + broadcast it
         // block column k+1 has received updates 0..k-1 on sm; order sp after them
         if (two_streams && k >= 1) FB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_used[(size_t)(k - 1)], 0));
-        if (role[(size_t)k] == 2) update_block_col_pair(sp, k, kn, /*first touch*/ k == 1);
-        else update_block_col(sp, k, kn);
+        update_block_col(sp, k, kn);
       }
       factor_and_bcast(kn);
     }
-    if (role[(size_t)k] == 1) {
-      // first panel of a pair: its trailing update is applied together with the next panel's
-    } else if (role[(size_t)k] == 2) {
-      if (pipe && k == 1) {
-        // host-resident input: these are the first touches of the block columns >= 3 — one launch per column, each waiting
-        // for its own upload, so that the updates trail the transfer instead of waiting for all of it
-        for (i64 j = k + 2; j < nblk; ++j) update_block_col_pair(sm, k, j, true);
-      } else if (k + 2 < nblk) {
-        const i64 p0 = b0[(size_t)k - 1], pw = b0[(size_t)k + 1] - p0, j0 = b0[(size_t)k + 2];
-        VCD Wr{A_local + p0 * ld + j0, n - j0, pw, 1, ld};
-        VD dst{A_local + j0 * ld + j0, n - j0, n - j0, 1, ld};
-        gemm_f64(sm, dst, TRI_LOWER, 1, Wr, RECT, Wr.t(), RECT, -1.0);
-      }
-    } else if (P == 1 && k + 2 < nblk && !(pipe && k == 0) && !getenv("FAER_B200_LLT_SPLIT_BULK")) {
+    if (P == 1 && k + 2 < nblk && !(pipe && k == 0) && !getenv("FAER_B200_LLT_SPLIT_BULK")) {
       // single GPU: every remaining block column in ONE structured launch (lower-triangular destination: tiles above
       // the diagonal exit at once) instead of one launch per block column — no per-launch tail, better L2 reuse
       const i64 k0 = b0[(size_t)k], kb = b0[(size_t)k + 1] - k0, rows_k = n - k0, j0 = b0[(size_t)k + 2];
