@@ -29,6 +29,9 @@ constexpr int POTF2_UPD_WARPS = 16;
 constexpr int POTF2_THREADS = POTF2_UPD_WARPS * 32 + POTF2_MAX;  // 512 update threads + 128 pivot threads
 constexpr int POTF2_CB = POTF2_MAX / POTF2_UPD_WARPS;           // column slots per update thread (8)
 
+__device__ __forceinline__ double recip_rn(double x) { return __drcp_rn(x); }
+__device__ __forceinline__ float recip_rn(float x) { return __frcp_rn(x); }
+
 // scalar-type dispatch of the two building blocks the recursion calls (G3 solve, lower-masked GEMM)
 inline void solve_lower(cudaStream_t st, VCD tri, bool unit, VD rhs) { solve_lower_triangular_in_place_f64(st, tri, unit, rhs); }
 inline void solve_lower(cudaStream_t st, VCF tri, bool unit, VF rhs) { solve_lower_triangular_in_place_f32(st, tri, unit, rhs); }
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_kernel(T* __restrict__ A,
     } else {
       const T sd = sqrt(d);
       if (sd == T(0) || !isfinite(sd)) fail = 1;
-      else inv = T(1) / sd;
+      else inv = recip_rn(sd);  // correctly rounded reciprocal = T(1) / sd bit for bit, without the division's slow path
     }
     s_inv[jc & 1] = inv;
     s_fail[jc & 1] = fail;
