@@ -13,8 +13,9 @@ dev = torch.device("cuda:0")
 lib = faer_b200.load()
 lib.faer_b200_set_stream(torch.cuda.current_stream().cuda_stream)
 ws = [int(x) for x in sys.argv[1:]] or [128, 512]
+ms = [int(x) for x in os.environ.get("PANEL_ROWS", "32768,16384,8192,2048,512").split(",")]
 for w in ws:
-    for m in [32768, 16384, 8192, 2048, 512]:
+    for m in ms:
         A0 = torch.randn((w, m), dtype=torch.float64, device=dev).T
         A = A0.clone(memory_format=torch.preserve_format)
         p = torch.zeros(m, dtype=torch.int64, device=dev); pi = torch.zeros(m, dtype=torch.int64, device=dev)
