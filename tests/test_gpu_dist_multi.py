@@ -1,5 +1,5 @@
 """Multi-rank parity on hardware (needs >= 2 GPUs; skipped on a single-GPU box): torchrun over NCCL, the distributed LLT and LU on
-2 (and 4 when visible) ranks against the single-GPU run of the same matrices — permutations / status bit-exact, factors to
+2 (and 4 / 8 when visible) ranks against the single-GPU run of the same matrices — permutations / status bit-exact, factors to
 rounding, reconstruction probes (tools/dist_parity.py). The world-size-2 logic of the layout is covered on CPU by
 tests/test_dist_cpu.py (gloo)."""
 import os
@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_distributed_factorizations_match_single_gpu(cuda_dev, world):
     import torch
     if torch.cuda.device_count() < world:
