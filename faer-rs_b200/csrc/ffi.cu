@@ -591,6 +591,85 @@ void libfaer_v0_23_ldlt_solve_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_VecRef 
   if (d_mirror) ws_free(d_mirror);
 }
 
+// ---- c64 triangular solves and LLT (cplx_c64.cu: faer's recursions on the complex GEMM + two complex leaf kernels) ----
+static void solve_tri_c64(FaerV0_24_MatRef T, FaerV0_24_Conj conj, FaerV0_24_MatMut rhs, bool lower, bool unit) {
+  FB_ENTRY();
+  FB_ASSERT(T.nrows == T.ncols && rhs.nrows == T.nrows, "triangular solve shape mismatch");
+  cudaStream_t st = current_stream();
+  StagedMat t(T.ptr, (i64)T.nrows, (i64)T.ncols, (i64)T.row_stride, (i64)T.col_stride, 16, true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 16, true, true, st);
+  VD tv = t.view<double>(), rv = r.view<double>();  // complex-unit strides on a double* base, as gemm_c64 takes them
+  if (lower) solve_lower_triangular_in_place_c64(st, cv(tv), unit, conj == FaerV0_24_Conj_Yes, rv);
+  else solve_upper_triangular_in_place_c64(st, cv(tv), unit, conj == FaerV0_24_Conj_Yes, rv);
+  finish_all(st, {&t, &r});
+}
+void libfaer_v0_23_solve_triangular_lower_in_place_c64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs,
+                                                       FaerV0_24_Par par) {
+  (void)par;
+  solve_tri_c64(L, L_conj, rhs, true, false);
+}
+void libfaer_v0_23_solve_triangular_upper_in_place_c64(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs,
+                                                       FaerV0_24_Par par) {
+  (void)par;
+  solve_tri_c64(U, U_conj, rhs, false, false);
+}
+void libfaer_v0_23_solve_unit_triangular_lower_in_place_c64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs,
+                                                            FaerV0_24_Par par) {
+  (void)par;
+  solve_tri_c64(L, L_conj, rhs, true, true);
+}
+void libfaer_v0_23_solve_unit_triangular_upper_in_place_c64(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs,
+                                                            FaerV0_24_Par par) {
+  (void)par;
+  solve_tri_c64(U, U_conj, rhs, false, true);
+}
+FaerV0_24_LltParams libfaer_v0_23_LltParams_c64(void) { return FaerV0_24_LltParams{64, 128}; }
+FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_c64(size_t dim, FaerV0_24_Par par, FaerV0_24_LltParams params) {
+  (void)par; (void)params;
+  return FaerV0_24_Layout{dim * 16, 64};  // temp_mat_scratch::<T>(dim, 1), llt/factor.rs:58-66
+}
+FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_c64(FaerV0_24_MatMut A, FaerV0_24_LltRegularization regularization,
+                                                          FaerV0_24_Par par, FaerV0_24_MemAlloc mem, FaerV0_24_LltParams params) {
+  (void)par; (void)mem; (void)params;
+  FB_ENTRY();
+  FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
+  cudaStream_t st = current_stream();
+  double delta = 0.0, eps = 0.0;  // the regularisation parameters are Real = f64 for c64
+  if (regularization.dynamic_regularization_delta)
+    delta = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_delta);
+  if (regularization.dynamic_regularization_epsilon)
+    eps = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_epsilon);
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 16, true, true, st);
+  const LltResult r = llt_cholesky_in_place_c64(st, a.view<double>(), delta, eps);
+  finish_all(st, {&a});
+  FaerV0_24_LltStatus out;
+  memset(&out, 0, sizeof(out));
+  if (r.ok) {
+    out.tag = FaerV0_24_LltStatus_Ok;
+    out.ok.dynamic_regularization_count = r.dynamic_regularization_count;
+  } else {
+    out.tag = FaerV0_24_LltStatus_NonPositivePivot;
+    out.non_positive_pivot.index = r.non_positive_pivot_index;
+  }
+  return out;
+}
+FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_c64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
+  (void)dim; (void)rhs_ncols; (void)par;
+  return FaerV0_24_Layout{0, 1};
+}
+void libfaer_v0_23_llt_solve_in_place_c64(FaerV0_24_MatRef L, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,
+                                          FaerV0_24_MemAlloc mem) {
+  (void)par; (void)mem;
+  FB_ENTRY();
+  FB_ASSERT(L.nrows == L.ncols && rhs.nrows == L.nrows, "LLT solve shape mismatch");
+  cudaStream_t st = current_stream();
+  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, 16, true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 16, true, true, st);
+  VD lv = l.view<double>();
+  llt_solve_in_place_c64(st, cv(lv), A_conj == FaerV0_24_Conj_Yes, r.view<double>());
+  finish_all(st, {&l, &r});
+}
+
 // ---- partial-pivoting LU ----
 FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f64(void) {
   // reference defaults: faer/src/linalg/lu/partial_pivoting/factor.rs:212-222
@@ -941,6 +1020,76 @@ static void lu_solve_entry_f32(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24
 FB_LU_SOLVE_F32(u32, 4)
 FB_LU_SOLVE_F32(u64, 8)
 #undef FB_LU_SOLVE_F32
+
+// ---- c64 partial-pivoting LU (cplx_c64.cu) ----
+FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_c64(void) { return libfaer_v0_23_PartialPivLuParams_f64(); }
+static void write_perm(void* dst, const std::vector<long long>& v, int idx_bytes) {
+  if (v.empty()) return;
+  std::vector<unsigned char> buf(v.size() * (size_t)idx_bytes);
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (idx_bytes == 4) ((uint32_t*)buf.data())[i] = (uint32_t)v[i];
+    else ((uint64_t*)buf.data())[i] = (uint64_t)v[i];
+  }
+  if (is_device_pointer(dst)) FB_CUDA_CHECK(cudaMemcpy(dst, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+  else memcpy(dst, buf.data(), buf.size());
+}
+static FaerV0_24_PartialPivLuStatus lu_entry_c64(FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd,
+                                                 int idx_bytes) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  FB_ASSERT(A.nrows == 0 || (perm_fwd.ptr != nullptr && perm_bwd.ptr != nullptr), "null permutation slice");
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 16, true, true, st);
+  std::vector<long long> pf(A.nrows), pb(A.nrows);
+  const size_t cnt = lu_partial_piv_in_place_c64(st, a.view<double>(), pf.data(), pb.data());
+  finish_all(st, {&a});
+  write_perm(perm_fwd.ptr, pf, idx_bytes);
+  write_perm(perm_bwd.ptr, pb, idx_bytes);
+  FaerV0_24_PartialPivLuStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_PartialPivLuStatus_Ok;
+  out.ok.transposition_count = cnt;
+  return out;
+}
+static void lu_solve_entry_c64(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj conj, FaerV0_24_SliceRef perm_slice,
+                               FaerV0_24_MatMut rhs, int idx_bytes) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t n = L.nrows;
+  FB_ASSERT(L.ncols == n && U.nrows == n && U.ncols == n && rhs.nrows == n, "LU solve shape mismatch");
+  std::vector<long long> perm = read_perm(perm_slice.ptr, n, idx_bytes);
+  for (size_t i = 0; i < n; ++i) FB_ASSERT(perm[i] >= 0 && (size_t)perm[i] < n, "invalid permutation entry");
+  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, 16, true, false, st);
+  StagedMat u(U.ptr, (i64)U.nrows, (i64)U.ncols, (i64)U.row_stride, (i64)U.col_stride, 16, true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 16, true, true, st);
+  VD lv = l.view<double>(), uv = u.view<double>();
+  lu_solve_in_place_c64(st, cv(lv), cv(uv), conj == FaerV0_24_Conj_Yes, perm.data(), r.view<double>());
+  finish_all(st, {&l, &u, &r});
+}
+#define FB_LU_C64(IT, BYTES)                                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_##IT##_c64(size_t nrows, size_t ncols, FaerV0_24_Par par, \
+                                                                                   FaerV0_24_PartialPivLuParams params) {      \
+    (void)par; (void)params;                                                                                                    \
+    return lu_scratch(nrows, ncols, BYTES);                                                                                     \
+  }                                                                                                                             \
+  FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_##IT##_c64(                                         \
+      FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd, FaerV0_24_Par par, FaerV0_24_MemAlloc mem,   \
+      FaerV0_24_PartialPivLuParams params) {                                                                                    \
+    (void)par; (void)mem; (void)params;                                                                                         \
+    return lu_entry_c64(A, perm_fwd, perm_bwd, BYTES);                                                                          \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_##IT##_c64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) { \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{dim * rhs_ncols * 16, 64};                                                                          \
+  }                                                                                                                             \
+  void libfaer_v0_23_partial_piv_lu_solve_in_place_##IT##_c64(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj,    \
+                                                             FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,          \
+                                                             FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) { \
+    (void)perm_bwd; (void)par; (void)mem;                                                                                       \
+    lu_solve_entry_c64(L, U, A_conj, perm_fwd, rhs, BYTES);                                                                     \
+  }
+FB_LU_C64(u32, 4)
+FB_LU_C64(u64, 8)
+#undef FB_LU_C64
 
 // ---- SVD (svd.cu: values by bisection; svd_vectors.cu: with U / V) ----
 #define FB_SVD_FFI(SUF, T)                                                                                             \

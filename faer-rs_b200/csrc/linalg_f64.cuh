@@ -25,6 +25,15 @@ struct LltResult {
   size_t dynamic_regularization_count;  // valid if ok
   size_t non_positive_pivot_index;      // valid if !ok
 };
+// ---- c64 triangular solves and LLT (cplx_c64.cu); views in COMPLEX element units ----
+void solve_lower_triangular_in_place_c64(cudaStream_t st, VCD tril, bool unit, bool conj, VD rhs);
+void solve_upper_triangular_in_place_c64(cudaStream_t st, VCD triu, bool unit, bool conj, VD rhs);
+LltResult llt_cholesky_in_place_c64(cudaStream_t st, VD A, double reg_delta, double reg_eps);
+void llt_solve_in_place_c64(cudaStream_t st, VCD L, bool conj, VD rhs);
+// c64 partial-pivoting LU (perm arrays: HOST int64 of length nrows) and the solve on its factors
+size_t lu_partial_piv_in_place_c64(cudaStream_t st, VD A, long long* perm_fwd, long long* perm_inv);
+void lu_solve_in_place_c64(cudaStream_t st, VCD L, VCD U, bool conj, const long long* perm_fwd, VD rhs);
+
 // In-place lower Cholesky of the lower triangle of A (strict upper triangle untouched).
 // `reg_delta`/`reg_eps`: dynamic regularisation (active iff both > 0), reference llt/factor.rs:85-87.
 LltResult llt_cholesky_in_place_f64(cudaStream_t stream, VD A, double reg_delta, double reg_eps, LltParams params);

@@ -134,12 +134,16 @@ def matmul_triangular(dst, dst_structure: int, accum: int, lhs, lhs_structure: i
 
 
 def _solve(name, tri, rhs, conj, par):
-    """triangular_solve.rs:220-419; f64 or f32."""
-    suf = "f32" if _is_f32(rhs) else "f64"
-    if suf == "f32":
+    """triangular_solve.rs:220-419; f64, f32 or c64 (complex128; `conj` solves with conj(tri))."""
+    if _is_c64(rhs):
+        assert _is_c64(tri), "c64 entry point needs complex128 operands"
+        suf = "c64"
+    elif _is_f32(rhs):
         assert _is_f32(tri), "f32 entry point needs float32 operands"
+        suf = "f32"
     else:
         _check_f64(tri, rhs)
+        suf = "f64"
     lib = capi.load()
     getattr(lib, f"libfaer_v0_23_{name}_in_place_{suf}")(capi.mat_ref(tri), conj, capi.mat_mut(rhs),
                                                          par or capi.par_default())
@@ -180,10 +184,12 @@ def llt_params_default():
 
 
 def cholesky_in_place(A, regularization=(0.0, 0.0), par=None, params=None) -> LltInfo:
-    """In-place LLT of the lower triangle of A (f64, or f32 on the recursive driver). regularization = (delta, epsilon).
+    """In-place LLT of the lower triangle of A (f64; f32 and c64 on the recursive drivers). regularization = (delta, epsilon).
     Raises LltError."""
     lib = capi.load()
-    if _is_f32(A):
+    if _is_c64(A):
+        suf, real = "c64", C.c_double
+    elif _is_f32(A):
         suf, real = "f32", C.c_float
     else:
         _check_f64(A)
@@ -265,9 +271,12 @@ def ldlt_solve_in_place(LD, rhs, conj: int = CONJ_NO, par=None, D=None) -> None:
 
 
 def llt_solve_in_place(L, rhs, conj: int = CONJ_NO, par=None) -> None:
-    """cholesky::llt::solve::solve_in_place_with_conj (llt/solve.rs:12-35): rhs <- (L L^H)^-1 rhs. f64 or f32."""
+    """cholesky::llt::solve::solve_in_place_with_conj (llt/solve.rs:12-35): rhs <- (L L^H)^-1 rhs. f64, f32 or c64."""
     lib = capi.load()
-    if _is_f32(rhs):
+    if _is_c64(rhs):
+        assert _is_c64(L)
+        suf = "c64"
+    elif _is_f32(rhs):
         assert _is_f32(L)
         suf = "f32"
     else:
@@ -283,8 +292,8 @@ def lu_solve_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, par=None, U=
     With `U` given, `LU` is read as L only (its strict lower part) and `U` as the upper factor, as the reference's
     separate `L`, `U` arguments."""
     lib = capi.load()
-    suf = _suf(LU)
-    assert _suf(rhs) == suf
+    suf = _suf_lu(LU)
+    assert _suf_lu(rhs) == suf
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
     it = {4: "u32", 8: "u64"}[isz]
     getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_{suf}")(
@@ -313,6 +322,10 @@ class QrInfo:
 
 def _suf(x) -> str:
     return "f32" if _is_f32(x) else "f64"
+
+
+def _suf_lu(x) -> str:
+    return "c64" if _is_c64(x) else _suf(x)
 
 
 def qr_recommended_block_size(nrows: int, ncols: int) -> int:
@@ -605,9 +618,9 @@ class PartialPivLuInfo:
 
 def lu_in_place(A, perm, perm_inv, par=None, params=None) -> PartialPivLuInfo:
     """In-place P A = L U. `perm`/`perm_inv`: uint32/uint64 arrays (numpy) or int32/int64 CUDA tensors of
-    length nrows; (P A)[i, :] = A[perm[i], :]. f64, or f32 (computed in f64 on the device and rounded back)."""
+    length nrows; (P A)[i, :] = A[perm[i], :]. f64, c64, or f32 (computed in f64 on the device and rounded back)."""
     lib = capi.load()
-    suf = _suf(A)
+    suf = _suf_lu(A)
     params = params or getattr(lib, f"libfaer_v0_23_PartialPivLuParams_{suf}")()
     par = par or capi.par_default()
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize

@@ -287,6 +287,30 @@ struct FaerV0_24_Layout libfaer_v0_23_ldlt_solve_in_place_scratch_f64(size_t dim
 void libfaer_v0_23_ldlt_solve_in_place_f64(struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
 /* partial-pivoting LU.   params: lib.rs:679-684, faer.h:648; scratch: lib.rs:1952-1965; factor: lib.rs:1966-1983, faer.h:4456-4461 */
+/* c64 (complex<f64>, interleaved) triangular solves and LLT: faer.h:6130-6143, 636, 4036-4048 / lib.rs:896-937, 984-1038 stamped
+ * for c64. `L_conj` / `A_conj` are honoured (solve with conj(T)). Regularisation parameters point to f64 (Real of c64). */
+void libfaer_v0_23_solve_triangular_lower_in_place_c64(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj L_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_triangular_upper_in_place_c64(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_unit_triangular_lower_in_place_c64(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj L_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_unit_triangular_upper_in_place_c64(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+struct FaerV0_24_LltParams libfaer_v0_23_LltParams_c64(void);
+struct FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_c64(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LltParams params);
+struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_LltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LltParams params);
+struct FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_c64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_solve_in_place_c64(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+
+/* c64 partial-pivoting LU (pivot = first row attaining the largest |re| + |im|, faer-traits abs1) and the solve on its factors
+ * (`A_conj` honoured): faer.h:648, 4456-4461, 4786-4884 / lib.rs:1952-2020 stamped for c64. */
+struct FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_c64(void);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32_c64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_c64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u32_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u32_c64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u64_c64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_solve_in_place_u32_c64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_partial_piv_lu_solve_in_place_u64_c64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+
 struct FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f64(void);
 struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32_f64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
 struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_f64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
