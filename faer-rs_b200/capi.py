@@ -177,7 +177,7 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_matmul_triangular_c32.restype = None
     for name in ("solve_triangular_lower", "solve_triangular_upper", "solve_unit_triangular_lower",
                  "solve_unit_triangular_upper"):
-        for suf in ("f64", "f32", "c64"):
+        for suf in ("f64", "f32", "c64", "c32"):
             f = getattr(lib, f"libfaer_v0_23_{name}_in_place_{suf}")
             f.argtypes = [MatRef, C.c_int, MatMut, P]
             f.restype = None
@@ -187,7 +187,7 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_llt_factor_in_place_scratch_f64.restype = Layout
     lib.libfaer_v0_23_llt_factor_in_place_f64.argtypes = [MatMut, LltRegularization, P, MemAlloc, LltParams]
     lib.libfaer_v0_23_llt_factor_in_place_f64.restype = LltStatus
-    for suf in ("f64", "f32", "c64"):
+    for suf in ("f64", "f32", "c64", "c32"):
         getattr(lib, f"libfaer_v0_23_PartialPivLuParams_{suf}").argtypes = []
         getattr(lib, f"libfaer_v0_23_PartialPivLuParams_{suf}").restype = PartialPivLuParams
         for it in ("u32", "u64"):
@@ -197,7 +197,7 @@ def load() -> C.CDLL:
             f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_factor_in_place_{it}_{suf}")
             f.argtypes = [MatMut, SliceMut, SliceMut, P, MemAlloc, PartialPivLuParams]
             f.restype = PartialPivLuStatus
-    for suf in ("f64", "f32"):
+    for suf in ("f64", "f32", "c64", "c32"):
         getattr(lib, f"libfaer_v0_23_QrParams_{suf}").argtypes = []
         getattr(lib, f"libfaer_v0_23_QrParams_{suf}").restype = QrParams
         f = getattr(lib, f"libfaer_v0_23_qr_recommended_block_size_{suf}")
@@ -278,7 +278,7 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_qr_inverse_scratch_f64.restype = Layout
     lib.libfaer_v0_23_qr_inverse_f64.argtypes = [MatMut, MatRef, MatRef, MatRef, P, MemAlloc]
     lib.libfaer_v0_23_qr_inverse_f64.restype = None
-    for suf in ("f32", "c64"):
+    for suf in ("f32", "c64", "c32"):
         getattr(lib, f"libfaer_v0_23_LltParams_{suf}").argtypes = []
         getattr(lib, f"libfaer_v0_23_LltParams_{suf}").restype = LltParams
         getattr(lib, f"libfaer_v0_23_llt_factor_in_place_scratch_{suf}").argtypes = [C.c_size_t, P, LltParams]
@@ -303,15 +303,13 @@ def load() -> C.CDLL:
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.restype = Layout
     lib.libfaer_v0_23_llt_solve_in_place_f64.argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]
     lib.libfaer_v0_23_llt_solve_in_place_f64.restype = None
-    for it, suf in [(i, s_) for i in ("u32", "u64") for s_ in ("f64", "f32", "c64")]:
+    for it, suf in [(i, s_) for i in ("u32", "u64") for s_ in ("f64", "f32", "c64", "c32")]:
         f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_{it}_{suf}")
         f.argtypes = [C.c_size_t, C.c_size_t, P]
         f.restype = Layout
         f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_in_place_{it}_{suf}")
         f.argtypes = [MatRef, MatRef, C.c_int, SliceMut, SliceMut, MatMut, P, MemAlloc]
         f.restype = None
-        if suf == "c64":
-            continue
         f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_{it}_{suf}")
         f.argtypes = [C.c_size_t, C.c_size_t, P]
         f.restype = Layout

@@ -248,6 +248,196 @@ __global__ void ffi_gather_rows_f32_kernel(float* __restrict__ dst, const float*
 }  // namespace
 
 
+
+// ---- complex (c64 / c32) triangular solves, LLT and partial-pivoting LU: cplx.cu, templated over the real type R; the device
+// views are in complex-unit strides on an R* base, as the complex GEMMs take them ----
+inline void cplx_solve_lower(cudaStream_t st, View<const double> t, bool unit, bool conj, View<double> r) { solve_lower_triangular_in_place_c64(st, t, unit, conj, r); }
+inline void cplx_solve_lower(cudaStream_t st, View<const float> t, bool unit, bool conj, View<float> r) { solve_lower_triangular_in_place_c32(st, t, unit, conj, r); }
+inline void cplx_solve_upper(cudaStream_t st, View<const double> t, bool unit, bool conj, View<double> r) { solve_upper_triangular_in_place_c64(st, t, unit, conj, r); }
+inline void cplx_solve_upper(cudaStream_t st, View<const float> t, bool unit, bool conj, View<float> r) { solve_upper_triangular_in_place_c32(st, t, unit, conj, r); }
+inline LltResult cplx_llt(cudaStream_t st, View<double> a, double delta, double eps) { return llt_cholesky_in_place_c64(st, a, delta, eps); }
+inline LltResult cplx_llt(cudaStream_t st, View<float> a, float delta, float eps) { return llt_cholesky_in_place_c32(st, a, delta, eps); }
+inline void cplx_llt_solve(cudaStream_t st, View<const double> l, bool conj, View<double> r) { llt_solve_in_place_c64(st, l, conj, r); }
+inline void cplx_llt_solve(cudaStream_t st, View<const float> l, bool conj, View<float> r) { llt_solve_in_place_c32(st, l, conj, r); }
+inline size_t cplx_lu(cudaStream_t st, View<double> a, long long* pf, long long* pb) { return lu_partial_piv_in_place_c64(st, a, pf, pb); }
+inline size_t cplx_lu(cudaStream_t st, View<float> a, long long* pf, long long* pb) { return lu_partial_piv_in_place_c32(st, a, pf, pb); }
+inline void cplx_lu_solve(cudaStream_t st, View<const double> l, View<const double> u, bool conj, const long long* p, View<double> r) { lu_solve_in_place_c64(st, l, u, conj, p, r); }
+inline void cplx_lu_solve(cudaStream_t st, View<const float> l, View<const float> u, bool conj, const long long* p, View<float> r) { lu_solve_in_place_c32(st, l, u, conj, p, r); }
+inline void cplx_lu_solve_t(cudaStream_t st, View<const double> l, View<const double> u, bool conj, const long long* p, View<double> r) { lu_solve_transpose_in_place_c64(st, l, u, conj, p, r); }
+inline void cplx_lu_solve_t(cudaStream_t st, View<const float> l, View<const float> u, bool conj, const long long* p, View<float> r) { lu_solve_transpose_in_place_c32(st, l, u, conj, p, r); }
+inline double read_real(const void* p, double) { return read_scalar_f64((const FaerV0_24_Scalar*)p); }
+inline float read_real(const void* p, float) {
+  FB_ASSERT(p != nullptr, "null scalar pointer");
+  float v;
+  if (is_device_pointer(p)) FB_CUDA_CHECK(cudaMemcpy(&v, p, sizeof(float), cudaMemcpyDeviceToHost));
+  else memcpy(&v, p, sizeof(float));
+  return v;
+}
+
+template <class R>
+void solve_tri_cplx(FaerV0_24_MatRef T, FaerV0_24_Conj conj, FaerV0_24_MatMut rhs, bool lower, bool unit) {
+  FB_ENTRY();
+  FB_ASSERT(T.nrows == T.ncols && rhs.nrows == T.nrows, "triangular solve shape mismatch");
+  cudaStream_t st = current_stream();
+  StagedMat t(T.ptr, (i64)T.nrows, (i64)T.ncols, (i64)T.row_stride, (i64)T.col_stride, 2 * sizeof(R), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 2 * sizeof(R), true, true, st);
+  if (lower) cplx_solve_lower(st, t.view<const R>(), unit, conj == FaerV0_24_Conj_Yes, r.view<R>());
+  else cplx_solve_upper(st, t.view<const R>(), unit, conj == FaerV0_24_Conj_Yes, r.view<R>());
+  finish_all(st, {&t, &r});
+}
+template <class R>
+FaerV0_24_LltStatus llt_factor_cplx(FaerV0_24_MatMut A, FaerV0_24_LltRegularization regularization) {
+  FB_ENTRY();
+  FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
+  cudaStream_t st = current_stream();
+  R delta = 0, eps = 0;  // the regularisation parameters are T::Real
+  if (regularization.dynamic_regularization_delta) delta = read_real(regularization.dynamic_regularization_delta, R());
+  if (regularization.dynamic_regularization_epsilon) eps = read_real(regularization.dynamic_regularization_epsilon, R());
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 2 * sizeof(R), true, true, st);
+  const LltResult r = cplx_llt(st, a.view<R>(), delta, eps);
+  finish_all(st, {&a});
+  FaerV0_24_LltStatus out;
+  memset(&out, 0, sizeof(out));
+  if (r.ok) {
+    out.tag = FaerV0_24_LltStatus_Ok;
+    out.ok.dynamic_regularization_count = r.dynamic_regularization_count;
+  } else {
+    out.tag = FaerV0_24_LltStatus_NonPositivePivot;
+    out.non_positive_pivot.index = r.non_positive_pivot_index;
+  }
+  return out;
+}
+template <class R>
+void llt_solve_cplx(FaerV0_24_MatRef L, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs) {
+  FB_ENTRY();
+  FB_ASSERT(L.nrows == L.ncols && rhs.nrows == L.nrows, "LLT solve shape mismatch");
+  cudaStream_t st = current_stream();
+  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, 2 * sizeof(R), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 2 * sizeof(R), true, true, st);
+  cplx_llt_solve(st, l.view<const R>(), A_conj == FaerV0_24_Conj_Yes, r.view<R>());
+  finish_all(st, {&l, &r});
+}
+// index slices (u32 / u64) <-> host int64
+static std::vector<long long> read_perm(const void* p, size_t n, int idx_bytes) {
+  std::vector<unsigned char> raw(n * (size_t)idx_bytes);
+  if (n) {
+    if (is_device_pointer(p)) FB_CUDA_CHECK(cudaMemcpy(raw.data(), p, raw.size(), cudaMemcpyDeviceToHost));
+    else memcpy(raw.data(), p, raw.size());
+  }
+  std::vector<long long> out(n);
+  for (size_t i = 0; i < n; ++i)
+    out[i] = idx_bytes == 4 ? (long long)((const uint32_t*)raw.data())[i] : (long long)((const uint64_t*)raw.data())[i];
+  return out;
+}
+static void write_perm(void* dst, const std::vector<long long>& v, int idx_bytes) {
+  if (v.empty()) return;
+  std::vector<unsigned char> buf(v.size() * (size_t)idx_bytes);
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (idx_bytes == 4) ((uint32_t*)buf.data())[i] = (uint32_t)v[i];
+    else ((uint64_t*)buf.data())[i] = (uint64_t)v[i];
+  }
+  if (is_device_pointer(dst)) FB_CUDA_CHECK(cudaMemcpy(dst, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+  else memcpy(dst, buf.data(), buf.size());
+}
+template <class R>
+FaerV0_24_PartialPivLuStatus lu_entry_cplx(FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd, int idx_bytes) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  FB_ASSERT(A.nrows == 0 || (perm_fwd.ptr != nullptr && perm_bwd.ptr != nullptr), "null permutation slice");
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 2 * sizeof(R), true, true, st);
+  std::vector<long long> pf(A.nrows), pb(A.nrows);
+  const size_t cnt = cplx_lu(st, a.view<R>(), pf.data(), pb.data());
+  finish_all(st, {&a});
+  write_perm(perm_fwd.ptr, pf, idx_bytes);
+  write_perm(perm_bwd.ptr, pb, idx_bytes);
+  FaerV0_24_PartialPivLuStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_PartialPivLuStatus_Ok;
+  out.ok.transposition_count = cnt;
+  return out;
+}
+template <class R>
+void lu_solve_entry_cplx(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj conj, FaerV0_24_SliceRef perm_slice, FaerV0_24_MatMut rhs,
+                         int idx_bytes, bool transpose = false) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t n = L.nrows;
+  FB_ASSERT(L.ncols == n && U.nrows == n && U.ncols == n && rhs.nrows == n, "LU solve shape mismatch");
+  std::vector<long long> perm = read_perm(perm_slice.ptr, n, idx_bytes);
+  for (size_t i = 0; i < n; ++i) FB_ASSERT(perm[i] >= 0 && (size_t)perm[i] < n, "invalid permutation entry");
+  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, 2 * sizeof(R), true, false, st);
+  StagedMat u(U.ptr, (i64)U.nrows, (i64)U.ncols, (i64)U.row_stride, (i64)U.col_stride, 2 * sizeof(R), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 2 * sizeof(R), true, true, st);
+  // transpose = false: perm is perm_fwd (solve.rs:21-54); transpose = true: perm is perm_bwd (solve.rs:55-86)
+  if (transpose) cplx_lu_solve_t(st, l.view<const R>(), u.view<const R>(), conj == FaerV0_24_Conj_Yes, perm.data(), r.view<R>());
+  else cplx_lu_solve(st, l.view<const R>(), u.view<const R>(), conj == FaerV0_24_Conj_Yes, perm.data(), r.view<R>());
+  finish_all(st, {&l, &u, &r});
+}
+
+
+// complex Householder QR / block-Householder sequences / QR solves (cplx.cu)
+inline i64 cplx_qr(cudaStream_t st, View<double> a, View<double> q, i64 thr) { return qr_in_place_c64(st, a, q, thr); }
+inline i64 cplx_qr(cudaStream_t st, View<float> a, View<float> q, i64 thr) { return qr_in_place_c32(st, a, q, thr); }
+inline void cplx_hh_seq(cudaStream_t st, View<const double> b, View<const double> f, bool conj, View<double> r, bool tr) { apply_householder_sequence_left_c64(st, b, f, conj, r, tr); }
+inline void cplx_hh_seq(cudaStream_t st, View<const float> b, View<const float> f, bool conj, View<float> r, bool tr) { apply_householder_sequence_left_c32(st, b, f, conj, r, tr); }
+template <class V>
+inline V cplx_sub(V v, i64 i, i64 j, i64 m, i64 n) { return V{v.ptr + 2 * (i * v.rs + j * v.cs), m, n, v.rs, v.cs}; }
+
+template <class R>
+FaerV0_24_QrStatus qr_entry_cplx(FaerV0_24_MatMut A, FaerV0_24_MatMut Q, FaerV0_24_QrParams params) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t size = A.nrows < A.ncols ? A.nrows : A.ncols;
+  FB_ASSERT(Q.nrows > 0 && Q.ncols == size, "Q_coeff must be block_size x min(nrows, ncols)");
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 2 * sizeof(R), true, true, st);
+  StagedMat q(Q.ptr, (i64)Q.nrows, (i64)Q.ncols, (i64)Q.row_stride, (i64)Q.col_stride, 2 * sizeof(R), true, true, st);
+  const i64 rank = cplx_qr(st, a.view<R>(), q.view<R>(), (i64)params.blocking_threshold);
+  finish_all(st, {&a, &q});
+  FaerV0_24_QrStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_QrStatus_Ok;
+  out.ok.rank = (size_t)rank;
+  return out;
+}
+template <class R>
+void householder_seq_entry_cplx(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, FaerV0_24_Conj conj, FaerV0_24_MatMut rhs, bool transpose) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  StagedMat b(basis.ptr, (i64)basis.nrows, (i64)basis.ncols, (i64)basis.row_stride, (i64)basis.col_stride, 2 * sizeof(R), true, false, st);
+  StagedMat f(factor.ptr, (i64)factor.nrows, (i64)factor.ncols, (i64)factor.row_stride, (i64)factor.col_stride, 2 * sizeof(R), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 2 * sizeof(R), true, true, st);
+  cplx_hh_seq(st, b.view<const R>(), f.view<const R>(), conj == FaerV0_24_Conj_Yes, r.view<R>(), transpose);
+  finish_all(st, {&b, &f, &r});
+}
+// qr/no_pivoting/solve.rs:38-176 for complex T. mode 0: least squares (m >= n), 1: square solve, 2: transpose solve
+template <class R>
+void qr_solve_entry_cplx(FaerV0_24_MatRef Qb, FaerV0_24_MatRef Qc, FaerV0_24_MatRef Rm, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, int mode) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t m = Qb.nrows, n = Qb.ncols, size = m < n ? m : n;
+  FB_ASSERT(Qc.nrows > 0 && rhs.nrows == m && m >= n && Qc.ncols == size && Rm.nrows >= size && Rm.ncols == n, "QR solve shape mismatch");
+  if (mode != 0) FB_ASSERT(m == n && Rm.nrows == n, "QR solve: the factorization must be square");
+  if (size == 0 || rhs.ncols == 0) return;
+  const bool conj = A_conj == FaerV0_24_Conj_Yes;
+  StagedMat b(Qb.ptr, (i64)m, (i64)n, (i64)Qb.row_stride, (i64)Qb.col_stride, 2 * sizeof(R), true, false, st);
+  StagedMat f(Qc.ptr, (i64)Qc.nrows, (i64)Qc.ncols, (i64)Qc.row_stride, (i64)Qc.col_stride, 2 * sizeof(R), true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 2 * sizeof(R), true, true, st);
+  const bool alias = Rm.ptr == Qb.ptr && Rm.row_stride == Qb.row_stride && Rm.col_stride == Qb.col_stride;
+  std::unique_ptr<StagedMat> rr;
+  if (!alias) rr.reset(new StagedMat(Rm.ptr, (i64)size, (i64)n, (i64)Rm.row_stride, (i64)Rm.col_stride, 2 * sizeof(R), true, false, st));
+  View<const R> Rv = cplx_sub(alias ? b.view<const R>() : rr->view<const R>(), 0, 0, (i64)size, (i64)n);
+  View<R> x = r.view<R>();
+  if (mode == 2) {
+    cplx_solve_lower(st, Rv.t(), false, conj, x);               // op(R)^T y = rhs
+    cplx_hh_seq(st, b.view<const R>(), f.view<const R>(), !conj, x, false);  // the forward sequence with conj composed with Yes
+  } else {
+    cplx_hh_seq(st, b.view<const R>(), f.view<const R>(), !conj, x, true);   // op(Q)^H rhs
+    cplx_solve_upper(st, Rv, false, conj, cplx_sub(x, 0, 0, (i64)size, x.ncols));
+  }
+  finish_all(st, {&b, &f, &r});
+  if (rr) rr->finish();
+}
+
 extern "C" {
 
 void libfaer_v0_23_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
@@ -591,84 +781,51 @@ void libfaer_v0_23_ldlt_solve_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_VecRef 
   if (d_mirror) ws_free(d_mirror);
 }
 
-// ---- c64 triangular solves and LLT (cplx_c64.cu: faer's recursions on the complex GEMM + two complex leaf kernels) ----
-static void solve_tri_c64(FaerV0_24_MatRef T, FaerV0_24_Conj conj, FaerV0_24_MatMut rhs, bool lower, bool unit) {
-  FB_ENTRY();
-  FB_ASSERT(T.nrows == T.ncols && rhs.nrows == T.nrows, "triangular solve shape mismatch");
-  cudaStream_t st = current_stream();
-  StagedMat t(T.ptr, (i64)T.nrows, (i64)T.ncols, (i64)T.row_stride, (i64)T.col_stride, 16, true, false, st);
-  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 16, true, true, st);
-  VD tv = t.view<double>(), rv = r.view<double>();  // complex-unit strides on a double* base, as gemm_c64 takes them
-  if (lower) solve_lower_triangular_in_place_c64(st, cv(tv), unit, conj == FaerV0_24_Conj_Yes, rv);
-  else solve_upper_triangular_in_place_c64(st, cv(tv), unit, conj == FaerV0_24_Conj_Yes, rv);
-  finish_all(st, {&t, &r});
-}
-void libfaer_v0_23_solve_triangular_lower_in_place_c64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs,
-                                                       FaerV0_24_Par par) {
-  (void)par;
-  solve_tri_c64(L, L_conj, rhs, true, false);
-}
-void libfaer_v0_23_solve_triangular_upper_in_place_c64(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs,
-                                                       FaerV0_24_Par par) {
-  (void)par;
-  solve_tri_c64(U, U_conj, rhs, false, false);
-}
-void libfaer_v0_23_solve_unit_triangular_lower_in_place_c64(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs,
-                                                            FaerV0_24_Par par) {
-  (void)par;
-  solve_tri_c64(L, L_conj, rhs, true, true);
-}
-void libfaer_v0_23_solve_unit_triangular_upper_in_place_c64(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs,
-                                                            FaerV0_24_Par par) {
-  (void)par;
-  solve_tri_c64(U, U_conj, rhs, false, true);
-}
-FaerV0_24_LltParams libfaer_v0_23_LltParams_c64(void) { return FaerV0_24_LltParams{64, 128}; }
-FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_c64(size_t dim, FaerV0_24_Par par, FaerV0_24_LltParams params) {
-  (void)par; (void)params;
-  return FaerV0_24_Layout{dim * 16, 64};  // temp_mat_scratch::<T>(dim, 1), llt/factor.rs:58-66
-}
-FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_c64(FaerV0_24_MatMut A, FaerV0_24_LltRegularization regularization,
-                                                          FaerV0_24_Par par, FaerV0_24_MemAlloc mem, FaerV0_24_LltParams params) {
-  (void)par; (void)mem; (void)params;
-  FB_ENTRY();
-  FB_ASSERT(A.nrows == A.ncols, "LLT needs a square matrix");
-  cudaStream_t st = current_stream();
-  double delta = 0.0, eps = 0.0;  // the regularisation parameters are Real = f64 for c64
-  if (regularization.dynamic_regularization_delta)
-    delta = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_delta);
-  if (regularization.dynamic_regularization_epsilon)
-    eps = read_scalar_f64((const FaerV0_24_Scalar*)regularization.dynamic_regularization_epsilon);
-  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 16, true, true, st);
-  const LltResult r = llt_cholesky_in_place_c64(st, a.view<double>(), delta, eps);
-  finish_all(st, {&a});
-  FaerV0_24_LltStatus out;
-  memset(&out, 0, sizeof(out));
-  if (r.ok) {
-    out.tag = FaerV0_24_LltStatus_Ok;
-    out.ok.dynamic_regularization_count = r.dynamic_regularization_count;
-  } else {
-    out.tag = FaerV0_24_LltStatus_NonPositivePivot;
-    out.non_positive_pivot.index = r.non_positive_pivot_index;
+// ---- c64 / c32 triangular solves and LLT (cplx.cu: faer's recursions on the complex GEMMs + scalar complex leaf kernels) ----
+#define FB_CPLX_TRSM_LLT(SUF, R)                                                                                                \
+  void libfaer_v0_23_solve_triangular_lower_in_place_##SUF(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs,     \
+                                                           FaerV0_24_Par par) {                                                 \
+    (void)par;                                                                                                                  \
+    solve_tri_cplx<R>(L, L_conj, rhs, true, false);                                                                             \
+  }                                                                                                                             \
+  void libfaer_v0_23_solve_triangular_upper_in_place_##SUF(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs,     \
+                                                           FaerV0_24_Par par) {                                                 \
+    (void)par;                                                                                                                  \
+    solve_tri_cplx<R>(U, U_conj, rhs, false, false);                                                                            \
+  }                                                                                                                             \
+  void libfaer_v0_23_solve_unit_triangular_lower_in_place_##SUF(FaerV0_24_MatRef L, FaerV0_24_Conj L_conj, FaerV0_24_MatMut rhs, \
+                                                                FaerV0_24_Par par) {                                            \
+    (void)par;                                                                                                                  \
+    solve_tri_cplx<R>(L, L_conj, rhs, true, true);                                                                              \
+  }                                                                                                                             \
+  void libfaer_v0_23_solve_unit_triangular_upper_in_place_##SUF(FaerV0_24_MatRef U, FaerV0_24_Conj U_conj, FaerV0_24_MatMut rhs, \
+                                                                FaerV0_24_Par par) {                                            \
+    (void)par;                                                                                                                  \
+    solve_tri_cplx<R>(U, U_conj, rhs, false, true);                                                                             \
+  }                                                                                                                             \
+  FaerV0_24_LltParams libfaer_v0_23_LltParams_##SUF(void) { return FaerV0_24_LltParams{64, 128}; }                              \
+  FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_##SUF(size_t dim, FaerV0_24_Par par, FaerV0_24_LltParams params) { \
+    (void)par; (void)params;                                                                                                    \
+    return FaerV0_24_Layout{dim * 2 * sizeof(R), 64}; /* temp_mat_scratch::<T>(dim, 1), llt/factor.rs:58-66 */                  \
+  }                                                                                                                             \
+  FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_##SUF(FaerV0_24_MatMut A, FaerV0_24_LltRegularization regularization,   \
+                                                              FaerV0_24_Par par, FaerV0_24_MemAlloc mem,                        \
+                                                              FaerV0_24_LltParams params) {                                     \
+    (void)par; (void)mem; (void)params;                                                                                         \
+    return llt_factor_cplx<R>(A, regularization);                                                                               \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_##SUF(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {            \
+    (void)dim; (void)rhs_ncols; (void)par;                                                                                      \
+    return FaerV0_24_Layout{0, 1};                                                                                              \
+  }                                                                                                                             \
+  void libfaer_v0_23_llt_solve_in_place_##SUF(FaerV0_24_MatRef L, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs,                  \
+                                              FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                                      \
+    (void)par; (void)mem;                                                                                                       \
+    llt_solve_cplx<R>(L, A_conj, rhs);                                                                                          \
   }
-  return out;
-}
-FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_c64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
-  (void)dim; (void)rhs_ncols; (void)par;
-  return FaerV0_24_Layout{0, 1};
-}
-void libfaer_v0_23_llt_solve_in_place_c64(FaerV0_24_MatRef L, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,
-                                          FaerV0_24_MemAlloc mem) {
-  (void)par; (void)mem;
-  FB_ENTRY();
-  FB_ASSERT(L.nrows == L.ncols && rhs.nrows == L.nrows, "LLT solve shape mismatch");
-  cudaStream_t st = current_stream();
-  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, 16, true, false, st);
-  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 16, true, true, st);
-  VD lv = l.view<double>();
-  llt_solve_in_place_c64(st, cv(lv), A_conj == FaerV0_24_Conj_Yes, r.view<double>());
-  finish_all(st, {&l, &r});
-}
+FB_CPLX_TRSM_LLT(c64, double)
+FB_CPLX_TRSM_LLT(c32, float)
+#undef FB_CPLX_TRSM_LLT
 
 // ---- partial-pivoting LU ----
 FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f64(void) {
@@ -870,6 +1027,100 @@ FB_QR_FFI(f64, double)
 FB_QR_FFI(f32, float)
 #undef FB_QR_FFI
 
+// ---- complex Householder QR, block-Householder sequences and the QR solves (cplx.cu) ----
+#define FB_QR_CPLX_FFI(SUF, R)                                                                                                  \
+  FaerV0_24_QrParams libfaer_v0_23_QrParams_##SUF(void) { return FaerV0_24_QrParams{48 * 48, 192 * 256}; }                      \
+  size_t libfaer_v0_23_qr_recommended_block_size_##SUF(size_t nrows, size_t ncols) {                                            \
+    return (size_t)qr_recommended_block_size((i64)nrows, (i64)ncols);                                                           \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_qr_factor_in_place_scratch_##SUF(size_t nrows, size_t ncols, size_t block_size,                \
+                                                                  FaerV0_24_Par par, FaerV0_24_QrParams params) {               \
+    (void)nrows; (void)par; (void)params;                                                                                       \
+    return FaerV0_24_Layout{block_size * ncols * 2 * sizeof(R), 64};                                                            \
+  }                                                                                                                             \
+  FaerV0_24_QrStatus libfaer_v0_23_qr_factor_in_place_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatMut Q_coeff, FaerV0_24_Par par,    \
+                                                            FaerV0_24_MemAlloc mem, FaerV0_24_QrParams params) {                \
+    (void)par; (void)mem;                                                                                                       \
+    return qr_entry_cplx<R>(A, Q_coeff, params);                                                                                \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_left_scratch_##SUF(size_t dim, size_t block_size, size_t rhs_ncols) { \
+    (void)dim;                                                                                                                  \
+    return FaerV0_24_Layout{block_size * rhs_ncols * 2 * sizeof(R), 64};                                                        \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_left_scratch_##SUF(size_t dim, size_t block_size,           \
+                                                                                        size_t rhs_ncols) {                     \
+    (void)dim;                                                                                                                  \
+    return FaerV0_24_Layout{block_size * rhs_ncols * 2 * sizeof(R), 64};                                                        \
+  }                                                                                                                             \
+  void libfaer_v0_23_apply_householder_on_the_left_##SUF(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, FaerV0_24_Conj conj,  \
+                                                         FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {     \
+    (void)par; (void)mem;                                                                                                       \
+    householder_seq_entry_cplx<R>(basis, factor, conj, rhs, false);                                                             \
+  }                                                                                                                             \
+  void libfaer_v0_23_apply_householder_transpose_on_the_left_##SUF(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor,             \
+                                                                   FaerV0_24_Conj conj, FaerV0_24_MatMut rhs,                   \
+                                                                   FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                 \
+    (void)par; (void)mem;                                                                                                       \
+    householder_seq_entry_cplx<R>(basis, factor, conj, rhs, true);                                                              \
+  }                                                                                                                             \
+  /* on the right = the transposed sequence on the left of the transposed view, and vice versa (householder.rs:813-854) */     \
+  FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_right_scratch_##SUF(size_t dim, size_t block_size, size_t lhs_nrows) { \
+    (void)dim;                                                                                                                  \
+    return FaerV0_24_Layout{block_size * lhs_nrows * 2 * sizeof(R), 64};                                                        \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_right_scratch_##SUF(size_t dim, size_t block_size,          \
+                                                                                         size_t lhs_nrows) {                    \
+    (void)dim;                                                                                                                  \
+    return FaerV0_24_Layout{block_size * lhs_nrows * 2 * sizeof(R), 64};                                                        \
+  }                                                                                                                             \
+  void libfaer_v0_23_apply_householder_on_the_right_##SUF(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, FaerV0_24_Conj conj, \
+                                                          FaerV0_24_MatMut lhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {    \
+    (void)par; (void)mem;                                                                                                       \
+    householder_seq_entry_cplx<R>(basis, factor, conj, transposed(lhs), true);                                                  \
+  }                                                                                                                             \
+  void libfaer_v0_23_apply_householder_transpose_on_the_right_##SUF(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor,            \
+                                                                    FaerV0_24_Conj conj, FaerV0_24_MatMut lhs,                  \
+                                                                    FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                \
+    (void)par; (void)mem;                                                                                                       \
+    householder_seq_entry_cplx<R>(basis, factor, conj, transposed(lhs), false);                                                 \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_qr_solve_lstsq_in_place_scratch_##SUF(size_t nrows, size_t ncols, size_t block_size,           \
+                                                                       size_t rhs_ncols, FaerV0_24_Par par) {                   \
+    (void)nrows; (void)ncols; (void)par;                                                                                        \
+    return FaerV0_24_Layout{block_size * rhs_ncols * 2 * sizeof(R), 64};                                                        \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_qr_solve_in_place_scratch_##SUF(size_t dim, size_t block_size, size_t rhs_ncols,               \
+                                                                 FaerV0_24_Par par) {                                           \
+    (void)dim; (void)par;                                                                                                       \
+    return FaerV0_24_Layout{block_size * rhs_ncols * 2 * sizeof(R), 64};                                                        \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_qr_solve_transpose_in_place_scratch_##SUF(size_t dim, size_t block_size,                       \
+                                                                           size_t rhs_ncols, FaerV0_24_Par par) {               \
+    (void)dim; (void)par;                                                                                                       \
+    return FaerV0_24_Layout{block_size * rhs_ncols * 2 * sizeof(R), 64};                                                        \
+  }                                                                                                                             \
+  void libfaer_v0_23_qr_solve_lstsq_in_place_##SUF(FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff, FaerV0_24_MatRef Rm,     \
+                                                   FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,              \
+                                                   FaerV0_24_MemAlloc mem) {                                                    \
+    (void)par; (void)mem;                                                                                                       \
+    qr_solve_entry_cplx<R>(Q_basis, Q_coeff, Rm, A_conj, rhs, 0);                                                               \
+  }                                                                                                                             \
+  void libfaer_v0_23_qr_solve_in_place_##SUF(FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff, FaerV0_24_MatRef Rm,           \
+                                             FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs, FaerV0_24_Par par,                    \
+                                             FaerV0_24_MemAlloc mem) {                                                          \
+    (void)par; (void)mem;                                                                                                       \
+    qr_solve_entry_cplx<R>(Q_basis, Q_coeff, Rm, A_conj, rhs, 1);                                                               \
+  }                                                                                                                             \
+  void libfaer_v0_23_qr_solve_transpose_in_place_##SUF(FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff,                      \
+                                                       FaerV0_24_MatRef Rm, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs,        \
+                                                       FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                             \
+    (void)par; (void)mem;                                                                                                       \
+    qr_solve_entry_cplx<R>(Q_basis, Q_coeff, Rm, A_conj, rhs, 2);                                                               \
+  }
+FB_QR_CPLX_FFI(c64, double)
+FB_QR_CPLX_FFI(c32, float)
+#undef FB_QR_CPLX_FFI
+
 // ---- solves on top of the factors ----
 FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_f64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {
   (void)dim; (void)rhs_ncols; (void)par;
@@ -887,17 +1138,6 @@ void libfaer_v0_23_llt_solve_in_place_f64(FaerV0_24_MatRef L, FaerV0_24_Conj A_c
   finish_all(st, {&l.s, &r.s});
 }
 
-static std::vector<long long> read_perm(const void* p, size_t n, int idx_bytes) {
-  std::vector<unsigned char> raw(n * (size_t)idx_bytes);
-  if (n) {
-    if (is_device_pointer(p)) FB_CUDA_CHECK(cudaMemcpy(raw.data(), p, raw.size(), cudaMemcpyDeviceToHost));
-    else memcpy(raw.data(), p, raw.size());
-  }
-  std::vector<long long> out(n);
-  for (size_t i = 0; i < n; ++i)
-    out[i] = idx_bytes == 4 ? (long long)((const uint32_t*)raw.data())[i] : (long long)((const uint64_t*)raw.data())[i];
-  return out;
-}
 // transpose = false: perm is perm_fwd (solve.rs:21-54); transpose = true: perm is perm_bwd (solve.rs:55-86)
 static void lu_solve_entry(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_SliceRef perm_slice, FaerV0_24_MatMut rhs,
                            int idx_bytes, bool transpose = false) {
@@ -1021,75 +1261,47 @@ FB_LU_SOLVE_F32(u32, 4)
 FB_LU_SOLVE_F32(u64, 8)
 #undef FB_LU_SOLVE_F32
 
-// ---- c64 partial-pivoting LU (cplx_c64.cu) ----
+// ---- c64 / c32 partial-pivoting LU (cplx.cu) ----
 FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_c64(void) { return libfaer_v0_23_PartialPivLuParams_f64(); }
-static void write_perm(void* dst, const std::vector<long long>& v, int idx_bytes) {
-  if (v.empty()) return;
-  std::vector<unsigned char> buf(v.size() * (size_t)idx_bytes);
-  for (size_t i = 0; i < v.size(); ++i) {
-    if (idx_bytes == 4) ((uint32_t*)buf.data())[i] = (uint32_t)v[i];
-    else ((uint64_t*)buf.data())[i] = (uint64_t)v[i];
-  }
-  if (is_device_pointer(dst)) FB_CUDA_CHECK(cudaMemcpy(dst, buf.data(), buf.size(), cudaMemcpyHostToDevice));
-  else memcpy(dst, buf.data(), buf.size());
-}
-static FaerV0_24_PartialPivLuStatus lu_entry_c64(FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd,
-                                                 int idx_bytes) {
-  FB_ENTRY();
-  cudaStream_t st = current_stream();
-  FB_ASSERT(A.nrows == 0 || (perm_fwd.ptr != nullptr && perm_bwd.ptr != nullptr), "null permutation slice");
-  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, 16, true, true, st);
-  std::vector<long long> pf(A.nrows), pb(A.nrows);
-  const size_t cnt = lu_partial_piv_in_place_c64(st, a.view<double>(), pf.data(), pb.data());
-  finish_all(st, {&a});
-  write_perm(perm_fwd.ptr, pf, idx_bytes);
-  write_perm(perm_bwd.ptr, pb, idx_bytes);
-  FaerV0_24_PartialPivLuStatus out;
-  memset(&out, 0, sizeof(out));
-  out.tag = FaerV0_24_PartialPivLuStatus_Ok;
-  out.ok.transposition_count = cnt;
-  return out;
-}
-static void lu_solve_entry_c64(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj conj, FaerV0_24_SliceRef perm_slice,
-                               FaerV0_24_MatMut rhs, int idx_bytes) {
-  FB_ENTRY();
-  cudaStream_t st = current_stream();
-  const size_t n = L.nrows;
-  FB_ASSERT(L.ncols == n && U.nrows == n && U.ncols == n && rhs.nrows == n, "LU solve shape mismatch");
-  std::vector<long long> perm = read_perm(perm_slice.ptr, n, idx_bytes);
-  for (size_t i = 0; i < n; ++i) FB_ASSERT(perm[i] >= 0 && (size_t)perm[i] < n, "invalid permutation entry");
-  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, 16, true, false, st);
-  StagedMat u(U.ptr, (i64)U.nrows, (i64)U.ncols, (i64)U.row_stride, (i64)U.col_stride, 16, true, false, st);
-  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, 16, true, true, st);
-  VD lv = l.view<double>(), uv = u.view<double>();
-  lu_solve_in_place_c64(st, cv(lv), cv(uv), conj == FaerV0_24_Conj_Yes, perm.data(), r.view<double>());
-  finish_all(st, {&l, &u, &r});
-}
-#define FB_LU_C64(IT, BYTES)                                                                                                    \
-  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_##IT##_c64(size_t nrows, size_t ncols, FaerV0_24_Par par, \
-                                                                                   FaerV0_24_PartialPivLuParams params) {      \
+FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_c32(void) { return libfaer_v0_23_PartialPivLuParams_f64(); }
+#define FB_LU_CPLX(IT, BYTES, SUF, R)                                                                                           \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_##IT##_##SUF(size_t nrows, size_t ncols, FaerV0_24_Par par, \
+                                                                                     FaerV0_24_PartialPivLuParams params) {    \
     (void)par; (void)params;                                                                                                    \
     return lu_scratch(nrows, ncols, BYTES);                                                                                     \
   }                                                                                                                             \
-  FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_##IT##_c64(                                         \
+  FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_##IT##_##SUF(                                       \
       FaerV0_24_MatMut A, FaerV0_24_SliceMut perm_fwd, FaerV0_24_SliceMut perm_bwd, FaerV0_24_Par par, FaerV0_24_MemAlloc mem,   \
       FaerV0_24_PartialPivLuParams params) {                                                                                    \
     (void)par; (void)mem; (void)params;                                                                                         \
-    return lu_entry_c64(A, perm_fwd, perm_bwd, BYTES);                                                                          \
+    return lu_entry_cplx<R>(A, perm_fwd, perm_bwd, BYTES);                                                                      \
   }                                                                                                                             \
-  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_##IT##_c64(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) { \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_##IT##_##SUF(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) { \
     (void)par;                                                                                                                  \
-    return FaerV0_24_Layout{dim * rhs_ncols * 16, 64};                                                                          \
+    return FaerV0_24_Layout{dim * rhs_ncols * 2 * sizeof(R), 64};                                                               \
   }                                                                                                                             \
-  void libfaer_v0_23_partial_piv_lu_solve_in_place_##IT##_c64(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj,    \
-                                                             FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,          \
-                                                             FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) { \
+  void libfaer_v0_23_partial_piv_lu_solve_in_place_##IT##_##SUF(FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj,  \
+                                                               FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,        \
+                                                               FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) { \
     (void)perm_bwd; (void)par; (void)mem;                                                                                       \
-    lu_solve_entry_c64(L, U, A_conj, perm_fwd, rhs, BYTES);                                                                     \
+    lu_solve_entry_cplx<R>(L, U, A_conj, perm_fwd, rhs, BYTES);                                                                 \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_##IT##_##SUF(size_t dim, size_t rhs_ncols,     \
+                                                                                              FaerV0_24_Par par) {              \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{dim * rhs_ncols * 2 * sizeof(R), 64};                                                               \
+  }                                                                                                                             \
+  void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_##IT##_##SUF(                                                      \
+      FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_Conj A_conj, FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,   \
+      FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                                                        \
+    (void)perm_fwd; (void)par; (void)mem;                                                                                       \
+    lu_solve_entry_cplx<R>(L, U, A_conj, perm_bwd, rhs, BYTES, true);                                                           \
   }
-FB_LU_C64(u32, 4)
-FB_LU_C64(u64, 8)
-#undef FB_LU_C64
+FB_LU_CPLX(u32, 4, c64, double)
+FB_LU_CPLX(u64, 8, c64, double)
+FB_LU_CPLX(u32, 4, c32, float)
+FB_LU_CPLX(u64, 8, c32, float)
+#undef FB_LU_CPLX
 
 // ---- SVD (svd.cu: values by bisection; svd_vectors.cu: with U / V) ----
 #define FB_SVD_FFI(SUF, T)                                                                                             \

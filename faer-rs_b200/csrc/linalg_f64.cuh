@@ -25,7 +25,7 @@ struct LltResult {
   size_t dynamic_regularization_count;  // valid if ok
   size_t non_positive_pivot_index;      // valid if !ok
 };
-// ---- c64 triangular solves and LLT (cplx_c64.cu); views in COMPLEX element units ----
+// ---- c64 triangular solves, LLT and LU (cplx.cu; the c32 twins are declared in gemm_f32.cuh); views in COMPLEX element units ----
 void solve_lower_triangular_in_place_c64(cudaStream_t st, VCD tril, bool unit, bool conj, VD rhs);
 void solve_upper_triangular_in_place_c64(cudaStream_t st, VCD triu, bool unit, bool conj, VD rhs);
 LltResult llt_cholesky_in_place_c64(cudaStream_t st, VD A, double reg_delta, double reg_eps);
@@ -33,6 +33,10 @@ void llt_solve_in_place_c64(cudaStream_t st, VCD L, bool conj, VD rhs);
 // c64 partial-pivoting LU (perm arrays: HOST int64 of length nrows) and the solve on its factors
 size_t lu_partial_piv_in_place_c64(cudaStream_t st, VD A, long long* perm_fwd, long long* perm_inv);
 void lu_solve_in_place_c64(cudaStream_t st, VCD L, VCD U, bool conj, const long long* perm_fwd, VD rhs);
+void lu_solve_transpose_in_place_c64(cudaStream_t st, VCD L, VCD U, bool conj, const long long* perm_bwd, VD rhs);
+// c64 Householder QR without pivoting (returns the rank) and rhs <- Q rhs / Q^H rhs by the block-Householder sequence
+i64 qr_in_place_c64(cudaStream_t st, VD A, VD Q_coeff, i64 blocking_threshold);
+void apply_householder_sequence_left_c64(cudaStream_t st, VCD basis, VCD factor, bool conj, VD rhs, bool transpose);
 
 // In-place lower Cholesky of the lower triangle of A (strict upper triangle untouched).
 // `reg_delta`/`reg_eps`: dynamic regularisation (active iff both > 0), reference llt/factor.rs:85-87.

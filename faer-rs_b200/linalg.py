@@ -134,10 +134,13 @@ def matmul_triangular(dst, dst_structure: int, accum: int, lhs, lhs_structure: i
 
 
 def _solve(name, tri, rhs, conj, par):
-    """triangular_solve.rs:220-419; f64, f32 or c64 (complex128; `conj` solves with conj(tri))."""
+    """triangular_solve.rs:220-419; f64, f32, c64 (complex128) or c32 (complex64); `conj` solves with conj(tri)."""
     if _is_c64(rhs):
         assert _is_c64(tri), "c64 entry point needs complex128 operands"
         suf = "c64"
+    elif _is_c32(rhs):
+        assert _is_c32(tri), "c32 entry point needs complex64 operands"
+        suf = "c32"
     elif _is_f32(rhs):
         assert _is_f32(tri), "f32 entry point needs float32 operands"
         suf = "f32"
@@ -184,11 +187,13 @@ def llt_params_default():
 
 
 def cholesky_in_place(A, regularization=(0.0, 0.0), par=None, params=None) -> LltInfo:
-    """In-place LLT of the lower triangle of A (f64; f32 and c64 on the recursive drivers). regularization = (delta, epsilon).
-    Raises LltError."""
+    """In-place LLT of the lower triangle of A (f64; f32, c64 and c32 on the recursive drivers). regularization = (delta,
+    epsilon). Raises LltError."""
     lib = capi.load()
     if _is_c64(A):
         suf, real = "c64", C.c_double
+    elif _is_c32(A):
+        suf, real = "c32", C.c_float
     elif _is_f32(A):
         suf, real = "f32", C.c_float
     else:
@@ -271,11 +276,14 @@ def ldlt_solve_in_place(LD, rhs, conj: int = CONJ_NO, par=None, D=None) -> None:
 
 
 def llt_solve_in_place(L, rhs, conj: int = CONJ_NO, par=None) -> None:
-    """cholesky::llt::solve::solve_in_place_with_conj (llt/solve.rs:12-35): rhs <- (L L^H)^-1 rhs. f64, f32 or c64."""
+    """cholesky::llt::solve::solve_in_place_with_conj (llt/solve.rs:12-35): rhs <- (L L^H)^-1 rhs. f64, f32, c64 or c32."""
     lib = capi.load()
     if _is_c64(rhs):
         assert _is_c64(L)
         suf = "c64"
+    elif _is_c32(rhs):
+        assert _is_c32(L)
+        suf = "c32"
     elif _is_f32(rhs):
         assert _is_f32(L)
         suf = "f32"
@@ -305,8 +313,8 @@ def lu_solve_transpose_in_place(LU, perm, perm_inv, rhs, conj: int = CONJ_NO, pa
     """lu::partial_pivoting::solve::solve_transpose_in_place_with_conj (lu/partial_pivoting/solve.rs:55-86):
     rhs <- A^-T rhs from the packed factors and the row permutation (its inverse array is the one used)."""
     lib = capi.load()
-    suf = _suf(LU)
-    assert _suf(rhs) == suf
+    suf = _suf_lu(LU)
+    assert _suf_lu(rhs) == suf
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
     it = {4: "u32", 8: "u64"}[isz]
     getattr(lib, f"libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_{it}_{suf}")(
@@ -325,7 +333,7 @@ def _suf(x) -> str:
 
 
 def _suf_lu(x) -> str:
-    return "c64" if _is_c64(x) else _suf(x)
+    return "c64" if _is_c64(x) else "c32" if _is_c32(x) else _suf(x)
 
 
 def qr_recommended_block_size(nrows: int, ncols: int) -> int:
@@ -335,11 +343,11 @@ def qr_recommended_block_size(nrows: int, ncols: int) -> int:
 
 def qr_in_place(A, Q_coeff, par=None, params=None) -> QrInfo:
     """qr::no_pivoting::factor::qr_in_place (qr/no_pivoting/factor.rs:258-301). Q_coeff: block_size x min(m, n).
-    f64 or f32. Returns QrInfo(rank): dependent columns are skipped and the reflectors compacted exactly as the reference
+    f64, f32, c64 or c32. Returns QrInfo(rank): dependent columns are skipped and the reflectors compacted exactly as the reference
     does (factor.rs:40-83); Q_coeff's columns >= rank are zero with +inf on their block diagonals (287-299)."""
     lib = capi.load()
-    suf = _suf(A)
-    assert _suf(Q_coeff) == suf
+    suf = _suf_lu(A)
+    assert _suf_lu(Q_coeff) == suf
     params = params or getattr(lib, f"libfaer_v0_23_QrParams_{suf}")()
     st = getattr(lib, f"libfaer_v0_23_qr_factor_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(Q_coeff),
                                                                par or capi.par_default(), capi.MemAlloc(None, 0), params)
@@ -351,35 +359,35 @@ def qr_in_place(A, Q_coeff, par=None, params=None) -> QrInfo:
 def apply_block_householder_sequence_on_the_left_in_place(basis, factor, rhs, conj: int = CONJ_NO, par=None) -> None:
     """householder.rs:724-765: rhs <- Q rhs."""
     lib = capi.load()
-    getattr(lib, f"libfaer_v0_23_apply_householder_on_the_left_{_suf(rhs)}")(
+    getattr(lib, f"libfaer_v0_23_apply_householder_on_the_left_{_suf_lu(rhs)}")(
         capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def apply_block_householder_sequence_transpose_on_the_left_in_place(basis, factor, rhs, conj: int = CONJ_YES, par=None) -> None:
     """householder.rs:768-808: rhs <- Q^H rhs."""
     lib = capi.load()
-    getattr(lib, f"libfaer_v0_23_apply_householder_transpose_on_the_left_{_suf(rhs)}")(
+    getattr(lib, f"libfaer_v0_23_apply_householder_transpose_on_the_left_{_suf_lu(rhs)}")(
         capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def apply_block_householder_sequence_on_the_right_in_place(basis, factor, lhs, conj: int = CONJ_NO, par=None) -> None:
     """householder.rs:813-831: lhs <- lhs Q."""
     lib = capi.load()
-    getattr(lib, f"libfaer_v0_23_apply_householder_on_the_right_{_suf(lhs)}")(
+    getattr(lib, f"libfaer_v0_23_apply_householder_on_the_right_{_suf_lu(lhs)}")(
         capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(lhs), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def apply_block_householder_sequence_transpose_on_the_right_in_place(basis, factor, lhs, conj: int = CONJ_YES, par=None) -> None:
     """householder.rs:836-854: lhs <- lhs Q^H."""
     lib = capi.load()
-    getattr(lib, f"libfaer_v0_23_apply_householder_transpose_on_the_right_{_suf(lhs)}")(
+    getattr(lib, f"libfaer_v0_23_apply_householder_transpose_on_the_right_{_suf_lu(lhs)}")(
         capi.mat_ref(basis), capi.mat_ref(factor), conj, capi.mat_mut(lhs), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def _qr_solve(name, Q_basis, Q_coeff, R, rhs, conj, par):
     lib = capi.load()
-    suf = _suf(rhs)
-    assert _suf(Q_basis) == suf and _suf(Q_coeff) == suf and _suf(R) == suf
+    suf = _suf_lu(rhs)
+    assert _suf_lu(Q_basis) == suf and _suf_lu(Q_coeff) == suf and _suf_lu(R) == suf
     getattr(lib, f"libfaer_v0_23_{name}_{suf}")(capi.mat_ref(Q_basis), capi.mat_ref(Q_coeff), capi.mat_ref(R), conj,
                                                capi.mat_mut(rhs), par or capi.par_default(), capi.MemAlloc(None, 0))
 
@@ -618,7 +626,7 @@ class PartialPivLuInfo:
 
 def lu_in_place(A, perm, perm_inv, par=None, params=None) -> PartialPivLuInfo:
     """In-place P A = L U. `perm`/`perm_inv`: uint32/uint64 arrays (numpy) or int32/int64 CUDA tensors of
-    length nrows; (P A)[i, :] = A[perm[i], :]. f64, c64, or f32 (computed in f64 on the device and rounded back)."""
+    length nrows; (P A)[i, :] = A[perm[i], :]. f64, c64, c32, or f32 (computed in f64 on the device and rounded back)."""
     lib = capi.load()
     suf = _suf_lu(A)
     params = params or getattr(lib, f"libfaer_v0_23_PartialPivLuParams_{suf}")()

@@ -311,6 +311,27 @@ struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u64_
 void libfaer_v0_23_partial_piv_lu_solve_in_place_u32_c64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 void libfaer_v0_23_partial_piv_lu_solve_in_place_u64_c64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
+/* c32 (complex<f32>, interleaved) twins of the c64 entry points above: same faer.h / lib.rs templates stamped for c32, same
+ * contracts; regularisation parameters point to f32 (Real of c32). */
+void libfaer_v0_23_solve_triangular_lower_in_place_c32(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj L_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_triangular_upper_in_place_c32(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_unit_triangular_lower_in_place_c32(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj L_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+void libfaer_v0_23_solve_unit_triangular_upper_in_place_c32(struct FaerV0_24_MatRef U, enum FaerV0_24_Conj U_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par);
+struct FaerV0_24_LltParams libfaer_v0_23_LltParams_c32(void);
+struct FaerV0_24_Layout libfaer_v0_23_llt_factor_in_place_scratch_c32(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LltParams params);
+struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_LltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LltParams params);
+struct FaerV0_24_Layout libfaer_v0_23_llt_solve_in_place_scratch_c32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_solve_in_place_c32(struct FaerV0_24_MatRef L, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_c32(void);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32_c32(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_c32(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u32_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place_u64_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_SliceMut perm_fwd, struct FaerV0_24_SliceMut perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_PartialPivLuParams params);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u32_c32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_in_place_scratch_u64_c32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_solve_in_place_u32_c32(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_partial_piv_lu_solve_in_place_u64_c32(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+
 struct FaerV0_24_PartialPivLuParams libfaer_v0_23_PartialPivLuParams_f64(void);
 struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u32_f64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
 struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_factor_in_place_scratch_u64_f64(size_t nrows, size_t ncols, struct FaerV0_24_Par par, struct FaerV0_24_PartialPivLuParams params);
@@ -328,8 +349,8 @@ struct FaerV0_24_PartialPivLuStatus libfaer_v0_23_partial_piv_lu_factor_in_place
  * params: faer-ffi/src/lib.rs:671-675, faer.h:670; recommended_block_size: lib.rs:1520-1527, faer.h:5718;
  * scratch/factor: lib.rs:1528-1558, faer.h:5592-5602; apply_householder_*: lib.rs:1423-1518, faer.h:754-759.
  * Q_coeff is block_size x min(nrows, ncols): one upper-triangular T block per block of columns (tau on the diagonal,
- * faer's convention tau = (1 + |v_tail|^2)/2). Rank-deficient inputs return QrStatus_Unknown on this backend (the
- * reference's column-skipping path is not implemented on the GPU yet). */
+ * faer's convention tau = (1 + |v_tail|^2)/2). Rank-deficient inputs take the reference's
+ * column-skipping path (exact `rank`, +inf on the skipped T diagonals). */
 struct FaerV0_24_QrParams libfaer_v0_23_QrParams_f64(void);
 struct FaerV0_24_QrParams libfaer_v0_23_QrParams_f32(void);
 size_t libfaer_v0_23_qr_recommended_block_size_f64(size_t nrows, size_t ncols);
@@ -481,6 +502,57 @@ int faer_b200_set_option(const char *name, long long value);
 long long faer_b200_get_option(const char *name);
 /* Version string. */
 const char *faer_b200_version(void);
+
+/* complex (c64 / c32, interleaved) Householder QR without pivoting, the block-Householder sequence applications and the QR solves:
+ * the same faer.h / lib.rs templates as the f64 / f32 entry points above stamped for c64 / c32 (qr/no_pivoting/factor.rs:11-301 with
+ * the exact rank of the reference's column-skipping path, householder.rs:724-854, qr/no_pivoting/solve.rs:38-176). The conjugation
+ * arguments (`householder_conj`, `A_conj`) are honoured. */
+struct FaerV0_24_QrParams libfaer_v0_23_QrParams_c64(void);
+struct FaerV0_24_QrParams libfaer_v0_23_QrParams_c32(void);
+size_t libfaer_v0_23_qr_recommended_block_size_c64(size_t nrows, size_t ncols);
+size_t libfaer_v0_23_qr_recommended_block_size_c32(size_t nrows, size_t ncols);
+struct FaerV0_24_Layout libfaer_v0_23_qr_factor_in_place_scratch_c64(size_t nrows, size_t ncols, size_t block_size, struct FaerV0_24_Par par, struct FaerV0_24_QrParams params);
+struct FaerV0_24_Layout libfaer_v0_23_qr_factor_in_place_scratch_c32(size_t nrows, size_t ncols, size_t block_size, struct FaerV0_24_Par par, struct FaerV0_24_QrParams params);
+struct FaerV0_24_QrStatus libfaer_v0_23_qr_factor_in_place_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut Q_coeff, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_QrParams params);
+struct FaerV0_24_QrStatus libfaer_v0_23_qr_factor_in_place_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut Q_coeff, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_QrParams params);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_left_scratch_c64(size_t dim, size_t block_size, size_t rhs_ncols);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_left_scratch_c32(size_t dim, size_t block_size, size_t rhs_ncols);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_left_scratch_c64(size_t dim, size_t block_size, size_t rhs_ncols);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_left_scratch_c32(size_t dim, size_t block_size, size_t rhs_ncols);
+void libfaer_v0_23_apply_householder_on_the_left_c64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_on_the_left_c32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_transpose_on_the_left_c64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_transpose_on_the_left_c32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_right_scratch_c64(size_t dim, size_t block_size, size_t lhs_nrows);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_on_the_right_scratch_c32(size_t dim, size_t block_size, size_t lhs_nrows);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_right_scratch_c64(size_t dim, size_t block_size, size_t lhs_nrows);
+struct FaerV0_24_Layout libfaer_v0_23_apply_householder_transpose_on_the_right_scratch_c32(size_t dim, size_t block_size, size_t lhs_nrows);
+void libfaer_v0_23_apply_householder_on_the_right_c64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut lhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_on_the_right_c32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut lhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_transpose_on_the_right_c64(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut lhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_apply_householder_transpose_on_the_right_c32(struct FaerV0_24_MatRef householder_basis, struct FaerV0_24_MatRef householder_factor, enum FaerV0_24_Conj householder_conj, struct FaerV0_24_MatMut lhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_lstsq_in_place_scratch_c64(size_t nrows, size_t ncols, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_lstsq_in_place_scratch_c32(size_t nrows, size_t ncols, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_in_place_scratch_c64(size_t dim, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_in_place_scratch_c32(size_t dim, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_transpose_in_place_scratch_c64(size_t dim, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_qr_solve_transpose_in_place_scratch_c32(size_t dim, size_t block_size, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_qr_solve_lstsq_in_place_c64(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_lstsq_in_place_c32(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_in_place_c64(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_in_place_c32(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_transpose_in_place_c64(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_qr_solve_transpose_in_place_c32(struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+
+/* complex partial-pivoting LU: the transpose solve (lu/partial_pivoting/solve.rs:55-86; `A_conj` honoured, `perm_bwd` is the one read) */
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u32_c64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u32_c32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u64_c64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_scratch_u64_c32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u32_c64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u32_c32(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_c64(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_partial_piv_lu_solve_transpose_in_place_u64_c32(struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, enum FaerV0_24_Conj A_conj, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
 #ifdef __cplusplus
 }

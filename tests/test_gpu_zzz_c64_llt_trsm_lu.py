@@ -1,4 +1,4 @@
-"""c64 (complex128) triangular solves and Cholesky LLT through the C ABI (csrc/cplx_c64.cu) against the oracle's c64 restatement
+"""c64 (complex128) triangular solves and Cholesky LLT through the C ABI (csrc/cplx.cu) against the oracle's c64 restatement
 of the same recursions (triangular_solve.rs:220-604 with the conjugation flag, cholesky/llt/factor.rs:68-97 for complex T):
 solves within the backward bound for all four variants x conj, LLT: L L^H = A within 64 n u |A|, close to the oracle's factor,
 strict upper triangle untouched, NonPositivePivot index and regularisation count exact, the solve on the factor."""
@@ -103,3 +103,5 @@ def test_c64_lu_vs_oracle(fb, oracle):
                     X = B.copy(order="F"); la.lu_solve_in_place(got, p, pi, X, conj)
                     Ae = A.conj() if conj else A
                     assert np.max(np.abs(Ae @ X - B)) <= 256 * n * U * np.linalg.cond(A) * np.max(np.abs(B)), (n, conj)
+                    X = B.copy(order="F"); la.lu_solve_transpose_in_place(got, p, pi, X, conj)  # solve.rs:55-86
+                    assert np.max(np.abs(Ae.T @ X - B)) <= 256 * n * U * np.linalg.cond(A) * np.max(np.abs(B)), (n, conj, "T")
