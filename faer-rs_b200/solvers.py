@@ -14,8 +14,9 @@ and faer/src/mat/mat_ops.rs:869-897 (`Mul` for matrices -> `mul`).
 
 Every flop runs in libfaer_b200.so through `linalg.py`; this module only owns buffers, splits the packed factors and
 orders the calls the way the reference does. Operands are numpy arrays (host; staged by the library) or torch CUDA
-tensors (device; used in place); results are of the same kind, column-major. Real scalar types only (f64 everywhere,
-f32 for Qr), so the conjugate variants coincide with the plain ones, as `Conj` does for real `T` in the reference.
+tensors (device; used in place); results are of the same kind, column-major. Llt, PartialPivLu and Qr take real (f64; Qr and Llt
+also f32) and complex (c64 / c32) matrices — the reference's own `test_all_solvers` runs on c64 —, with the `Conj` argument of
+the C ABI carrying the conjugate / adjoint variants; Ldlt, Svd and SelfAdjointEigen are real-only (their kernels are).
 `inverse` is `solve` applied to the identity (the reference has dedicated kernels: `*/inverse.rs`); same result up
 to rounding.
 """
@@ -60,6 +61,25 @@ def _identity(like, m, n):
     else:
         np.fill_diagonal(out, 1)
     return out
+
+
+def _is_cplx(x) -> bool:
+    if _t(x):
+        return x.is_complex()
+    return np.iscomplexobj(x)
+
+
+def _conj(x):
+    """Element-wise conjugate as an owned value (the identity for real scalars)."""
+    if not _is_cplx(x):
+        return x
+    if _t(x):
+        return x.conj().resolve_conj()
+    return np.conj(x)
+
+
+def _adjoint(x):
+    return _conj(x).T
 
 
 def _zero_strict_upper(A):
@@ -141,49 +161,60 @@ class _Solve:
     def ncols(self) -> int:
         raise NotImplementedError
 
-    def _solve_core(self, rhs) -> None:  # SolveCore::solve_in_place_with_conj
+    def _solve_core(self, rhs, conj: int) -> None:  # SolveCore::solve_in_place_with_conj: rhs <- conj?(A)^-1 rhs
         raise NotImplementedError
 
-    def _solve_transpose_core(self, rhs) -> None:  # SolveCore::solve_transpose_in_place_with_conj
+    def _solve_transpose_core(self, rhs, conj: int) -> None:  # SolveCore::solve_transpose_in_place_with_conj: conj?(A)^-T rhs
         raise NotImplementedError
 
-    # in place
-    def solve_in_place(self, rhs) -> None:
+    def _sq(self, rhs):
         r = _as_2d(rhs)
         assert self.nrows() == self.ncols() == r.shape[0]
-        self._solve_core(r)
+        return r
+
+    # in place (solvers.rs:93-185)
+    def solve_in_place(self, rhs) -> None:
+        self._solve_core(self._sq(rhs), la.CONJ_NO)
+
+    def solve_conjugate_in_place(self, rhs) -> None:
+        self._solve_core(self._sq(rhs), la.CONJ_YES)
 
     def solve_transpose_in_place(self, rhs) -> None:
-        r = _as_2d(rhs)
-        assert self.nrows() == self.ncols() == r.shape[0]
-        self._solve_transpose_core(r)
+        self._solve_transpose_core(self._sq(rhs), la.CONJ_NO)
 
-    solve_conjugate_in_place = solve_in_place          # real scalars: conj(A) = A
-    solve_adjoint_in_place = solve_transpose_in_place  # real scalars: A^H = A^T
+    def solve_adjoint_in_place(self, rhs) -> None:
+        self._solve_transpose_core(self._sq(rhs), la.CONJ_YES)
 
     # owned results
-    def solve(self, rhs):
+    def _owned_solve(self, rhs, f):
         out = _owned(_as_2d(rhs))
-        self.solve_in_place(out)
+        f(out)
         return out
+
+    def solve(self, rhs):
+        return self._owned_solve(rhs, self.solve_in_place)
+
+    def solve_conjugate(self, rhs):
+        return self._owned_solve(rhs, self.solve_conjugate_in_place)
 
     def solve_transpose(self, rhs):
-        out = _owned(_as_2d(rhs))
-        self.solve_transpose_in_place(out)
-        return out
+        return self._owned_solve(rhs, self.solve_transpose_in_place)
 
-    solve_conjugate = solve
-    solve_adjoint = solve_transpose
+    def solve_adjoint(self, rhs):
+        return self._owned_solve(rhs, self.solve_adjoint_in_place)
 
-    # X A = lhs  <=>  A^T X^T = lhs^T   (solvers.rs:186-282)
+    # X op(A) = lhs  <=>  op(A)^T X^T = lhs^T   (solvers.rs:186-282)
     def rsolve(self, lhs):
         return _owned(self.solve_transpose(_as_2d(lhs).T).T)
+
+    def rsolve_conjugate(self, lhs):
+        return _owned(self.solve_adjoint(_as_2d(lhs).T).T)
 
     def rsolve_transpose(self, lhs):
         return _owned(self.solve(_as_2d(lhs).T).T)
 
-    rsolve_conjugate = rsolve
-    rsolve_adjoint = rsolve_transpose
+    def rsolve_adjoint(self, lhs):
+        return _owned(self.solve_conjugate(_as_2d(lhs).T).T)
 
     def rsolve_in_place(self, lhs) -> None:
         _assign(lhs, self.rsolve(lhs))
@@ -194,7 +225,7 @@ class _Solve:
     def inverse(self):
         assert self.nrows() == self.ncols()
         out = _identity(self._like(), self.nrows(), self.nrows())
-        self._solve_core(out)
+        self._solve_core(out, la.CONJ_NO)
         return out
 
     def _like(self):
@@ -202,7 +233,7 @@ class _Solve:
 
 
 class Llt(_Solve):
-    """A = L L^T (solvers.rs:770-816). `Llt.new(A, side)` raises LltError(index) on a non-positive pivot."""
+    """A = L L^H (solvers.rs:770-816). `Llt.new(A, side)` raises LltError(index) on a non-positive pivot."""
 
     def __init__(self, L):
         self._L = L
@@ -213,7 +244,7 @@ class Llt(_Solve):
         n = A.shape[0]
         L = _zeros(A, n, n)
         # copy_from_triangular_lower(A) / (A.adjoint()): only the chosen triangle of A is read
-        _assign(L, _tri(A if side == Side.Lower else A.T, lower=True))
+        _assign(L, _tri(A if side == Side.Lower else _adjoint(A), lower=True))
         la.cholesky_in_place(L)  # default regularization and params; LltError propagates
         _zero_strict_upper(L)
         return cls(L)
@@ -229,10 +260,12 @@ class Llt(_Solve):
     def _like(self):
         return self._L
 
-    def _solve_core(self, rhs) -> None:
-        la.llt_solve_in_place(self._L, rhs)
+    def _solve_core(self, rhs, conj: int) -> None:
+        la.llt_solve_in_place(self._L, rhs, conj)
 
-    _solve_transpose_core = _solve_core  # conj composed with Yes (solvers.rs:1883-1904): the identity for real scalars
+    def _solve_transpose_core(self, rhs, conj: int) -> None:
+        # A^T = conj(A) for a self-adjoint A: conj composed with Yes (solvers.rs:1883-1904)
+        la.llt_solve_in_place(self._L, rhs, la.CONJ_NO if conj == la.CONJ_YES else la.CONJ_YES)
 
     def reconstruct(self):
         """llt/reconstruct.rs: lower triangle of L L^H through the triangular product, then mirrored
@@ -240,8 +273,8 @@ class Llt(_Solve):
         n = self.nrows()
         out = _zeros(self._L, n, n)
         la.matmul_triangular(out, la.BlockStructure.TriangularLower, la.Accum.Replace, self._L,
-                             la.BlockStructure.TriangularLower, self._L.T, la.BlockStructure.TriangularUpper, 1.0)
-        _assign(out, _tri(out, lower=True) + _tri(out, lower=True, k=-1).T)
+                             la.BlockStructure.TriangularLower, _adjoint(self._L), la.BlockStructure.TriangularUpper, 1.0)
+        _assign(out, _tri(out, lower=True) + _adjoint(_tri(out, lower=True, k=-1)))
         return out
 
 
@@ -255,6 +288,7 @@ class Ldlt(_Solve):
     @classmethod
     def new(cls, A, side: int = Side.Lower) -> "Ldlt":
         assert A.ndim == 2 and A.shape[0] == A.shape[1]
+        assert not _is_cplx(A), "Ldlt: real scalars only on this backend"
         n = A.shape[0]
         L = _zeros(A, n, n)
         _assign(L, _tri(A if side == Side.Lower else A.T, lower=True))
@@ -281,8 +315,8 @@ class Ldlt(_Solve):
     def _like(self):
         return self._L
 
-    def _solve_core(self, rhs) -> None:
-        la.ldlt_solve_in_place(self._L, rhs, D=self._D)
+    def _solve_core(self, rhs, conj: int) -> None:
+        la.ldlt_solve_in_place(self._L, rhs, D=self._D)  # real scalars: conj(A) = A
 
     _solve_transpose_core = _solve_core  # real scalars: A^T = A
 
@@ -336,11 +370,11 @@ class PartialPivLu(_Solve):
     def _like(self):
         return self._L
 
-    def _solve_core(self, rhs) -> None:
-        la.lu_solve_in_place(self._L, self._fwd, self._bwd, rhs, U=self._U)
+    def _solve_core(self, rhs, conj: int) -> None:
+        la.lu_solve_in_place(self._L, self._fwd, self._bwd, rhs, conj, U=self._U)
 
-    def _solve_transpose_core(self, rhs) -> None:
-        la.lu_solve_transpose_in_place(self._L, self._fwd, self._bwd, rhs, U=self._U)
+    def _solve_transpose_core(self, rhs, conj: int) -> None:
+        la.lu_solve_transpose_in_place(self._L, self._fwd, self._bwd, rhs, conj, U=self._U)
 
     def reconstruct(self):
         """lu/partial_pivoting/reconstruct.rs: tmp = L U by structured products, then out[perm_fwd[i], :] = tmp[i, :]."""
@@ -414,25 +448,33 @@ class Qr(_Solve):
         la.apply_block_householder_sequence_on_the_left_in_place(self._Qb, self._Qc, Q)
         return Q
 
-    def _solve_core(self, rhs) -> None:
-        la.qr_solve_in_place(self._Qb, self._Qc, self._R, rhs)
+    def _solve_core(self, rhs, conj: int) -> None:
+        la.qr_solve_in_place(self._Qb, self._Qc, self._R, rhs, conj)
 
-    def _solve_transpose_core(self, rhs) -> None:
-        la.qr_solve_transpose_in_place(self._Qb, self._Qc, self._R, rhs)
+    def _solve_transpose_core(self, rhs, conj: int) -> None:
+        la.qr_solve_transpose_in_place(self._Qb, self._Qc, self._R, rhs, conj)
 
     # SolveLstsq (solvers.rs:639-690)
-    def solve_lstsq_in_place(self, rhs) -> None:
+    def _lstsq(self, rhs, conj: int) -> None:
         r = _as_2d(rhs)
         assert self._m == r.shape[0] and self._m >= self._n
-        la.qr_solve_lstsq_in_place(self._Qb, self._Qc, self._R, r)
+        la.qr_solve_lstsq_in_place(self._Qb, self._Qc, self._R, r, conj)
+
+    def solve_lstsq_in_place(self, rhs) -> None:
+        self._lstsq(rhs, la.CONJ_NO)
+
+    def solve_conjugate_lstsq_in_place(self, rhs) -> None:
+        self._lstsq(rhs, la.CONJ_YES)
 
     def solve_lstsq(self, rhs):
         out = _owned(_as_2d(rhs))
         self.solve_lstsq_in_place(out)
         return _owned(out[:self._n, :])  # truncate(ncols, rhs_ncols)
 
-    solve_conjugate_lstsq_in_place = solve_lstsq_in_place
-    solve_conjugate_lstsq = solve_lstsq
+    def solve_conjugate_lstsq(self, rhs):
+        out = _owned(_as_2d(rhs))
+        self.solve_conjugate_lstsq_in_place(out)
+        return _owned(out[:self._n, :])
 
     def reconstruct(self):
         """qr/no_pivoting/reconstruct.rs: out = R padded to m rows, then out <- Q out."""

@@ -1,6 +1,6 @@
 """Shared checks for faer_b200.solvers, restating the reference's `test_all_solvers`
 (faer/src/linalg/solvers.rs:2919-2977: n = 50, three right-hand sides, eight solve / rsolve identities per decomposition,
-tolerance eps * 128 * n) for the real scalar types, plus the accessors' contracts (split_LU, thin_R, compute_Q, P,
+tolerance eps * 128 * n) for f64 and — as the reference itself runs it — c64 (`cplx=True`), plus the accessors' contracts (split_LU, thin_R, compute_Q, P,
 reconstruct, inverse, least squares, Side::Upper, LltError).
 
 Run twice: on the GPU through the C ABI (tests/test_gpu_zz3_solvers.py) and on the CPU with `solvers.la` swapped for an
@@ -18,21 +18,29 @@ def approx(a, b, n, scale=1.0):
     return bool(np.all(np.abs(np.asarray(a) - np.asarray(b)) <= tol * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))))
 
 
+def randn(rng, shape, cplx):
+    x = rng.standard_normal(shape)
+    if cplx:
+        x = x + 1j * rng.standard_normal(shape)
+    return np.asfortranarray(x)
+
+
 def check_solver(A, dec, cond):
-    """test_solver_imp (solvers.rs:2921-2946), real case."""
+    """test_solver_imp (solvers.rs:2921-2946): the eight identities, with conjugate / adjoint meaning what they say for c64."""
     rng = np.random.default_rng(0xC0FFEE)
     n, k = A.shape[0], 3
-    R = np.asfortranarray(rng.standard_normal((n, k)))
-    L = np.asfortranarray(rng.standard_normal((k, n)))
+    cplx = np.iscomplexobj(A)
+    R = randn(rng, (n, k), cplx)
+    L = randn(rng, (k, n), cplx)
     s = max(1.0, cond) * max(1.0, np.abs(A).max())
     assert approx(A @ dec.solve(R), R, n, s)
-    assert approx(A @ dec.solve_conjugate(R), R, n, s)
+    assert approx(A.conj() @ dec.solve_conjugate(R), R, n, s)
     assert approx(A.T @ dec.solve_transpose(R), R, n, s)
-    assert approx(A.T @ dec.solve_adjoint(R), R, n, s)
+    assert approx(A.conj().T @ dec.solve_adjoint(R), R, n, s)
     assert approx(dec.rsolve(L) @ A, L, n, s)
-    assert approx(dec.rsolve_conjugate(L) @ A, L, n, s)
+    assert approx(dec.rsolve_conjugate(L) @ A.conj(), L, n, s)
     assert approx(dec.rsolve_transpose(L) @ A.T, L, n, s)
-    assert approx(dec.rsolve_adjoint(L) @ A.T, L, n, s)
+    assert approx(dec.rsolve_adjoint(L) @ A.conj().T, L, n, s)
     # in-place forms and vectors
     X = R.copy(order="F"); dec.solve_in_place(X)
     assert np.allclose(X, dec.solve(R), rtol=1e-12, atol=1e-14)  # same calls: the two forms agree
@@ -44,10 +52,10 @@ def check_solver(A, dec, cond):
     assert approx(dec.reconstruct(), A, n, s)
 
 
-def run_all(sv):
+def run_all(sv, cplx=False):
     rng = np.random.default_rng(0)
     n = 50
-    A = np.asfortranarray(rng.standard_normal((n, n)))
+    A = randn(rng, (n, n), cplx)
     cond = np.linalg.cond(A)
 
     # ---- PartialPivLu (solvers.rs:981-1034) ----
@@ -55,14 +63,15 @@ def run_all(sv):
     assert (lu.nrows(), lu.ncols()) == (n, n)
     Lf, Uf = lu.L(), lu.U()
     assert np.all(np.triu(Lf, 1) == 0) and np.all(np.diag(Lf) == 1) and np.all(np.tril(Uf, -1) == 0)
-    assert np.all(np.abs(np.tril(Lf, -1)) <= 1.0)  # partial pivoting
+    # partial pivoting: |l| <= 1 for reals; the complex pivot rule is abs1 = |re| + |im|, hence |l| <= sqrt(2)
+    assert np.all(np.abs(np.tril(Lf, -1)) <= (np.sqrt(2.0) * (1 + 1e-14) if cplx else 1.0))
     fwd, bwd = lu.P()
     assert sorted(int(i) for i in fwd) == list(range(n)) and all(int(bwd[int(fwd[i])]) == i for i in range(n))
     assert approx(Lf @ Uf, A[np.asarray(fwd, dtype=np.int64)], n, np.abs(A).max() * n)
     check_solver(A, lu, cond)
     # rectangular factorizations: split_LU's two branches and reconstruct
     for (m2, n2) in [(70, 30), (30, 70)]:
-        B = np.asfortranarray(rng.standard_normal((m2, n2)))
+        B = randn(rng, (m2, n2), cplx)
         d = sv.PartialPivLu.new(B)
         size = min(m2, n2)
         assert d.L().shape == ((m2, n2) if m2 >= n2 else (size, size))
@@ -76,32 +85,37 @@ def run_all(sv):
     assert qr.Q_coeff().shape[1] == n and qr.R().shape == (n, n) and np.all(np.tril(qr.R(), -1) == 0)
     assert np.all(np.diag(qr.Q_basis()) == 1) and np.all(np.triu(qr.Q_basis(), 1) == 0)
     Q = qr.compute_Q()
-    assert approx(Q.T @ Q, np.eye(n), n) and approx(Q @ qr.R(), A, n, np.abs(A).max() * n)
+    assert approx(Q.conj().T @ Q, np.eye(n), n) and approx(Q @ qr.R(), A, n, np.abs(A).max() * n)
     check_solver(A, qr, cond)
     m2, n2 = 120, 40
-    B = np.asfortranarray(rng.standard_normal((m2, n2)))
-    rhs = np.asfortranarray(rng.standard_normal((m2, 4)))
+    B = randn(rng, (m2, n2), cplx)
+    rhs = randn(rng, (m2, 4), cplx)
     d = sv.Qr.new(B)
     assert d.Q_basis().shape == (m2, n2) and d.R().shape == (n2, n2) and d.thin_R().shape == (n2, n2)
     tq = d.compute_thin_Q()
-    assert tq.shape == (m2, n2) and approx(tq.T @ tq, np.eye(n2), m2) and approx(tq @ d.thin_R(), B, m2, np.abs(B).max() * n2)
+    assert tq.shape == (m2, n2) and approx(tq.conj().T @ tq, np.eye(n2), m2) and approx(tq @ d.thin_R(), B, m2, np.abs(B).max() * n2)
     assert approx(d.compute_Q()[:, :n2], tq, m2)
     x = d.solve_lstsq(rhs)
     assert x.shape == (n2, 4)
     assert approx(x, np.linalg.lstsq(B, rhs, rcond=None)[0], m2, np.linalg.cond(B))
-    assert np.allclose(d.solve_conjugate_lstsq(rhs), x, rtol=1e-12, atol=1e-14)
+    xc = d.solve_conjugate_lstsq(rhs)  # least squares with conj(B)
+    assert approx(xc, np.linalg.lstsq(B.conj(), rhs, rcond=None)[0], m2, np.linalg.cond(B))
+    if not cplx:
+        assert np.allclose(xc, x, rtol=1e-12, atol=1e-14)
     assert approx(d.reconstruct(), B, m2, np.abs(B).max() * n2)
-    wide = np.asfortranarray(rng.standard_normal((30, 70)))
+    wide = randn(rng, (30, 70), cplx)
     d = sv.Qr.new(wide)
     assert d.Q_basis().shape == (30, 30) and d.R().shape == (30, 70) and d.thin_R().shape == (30, 70)
     assert approx(d.compute_Q() @ d.R(), wide, 70, np.abs(wide).max() * 30)
     assert approx(d.reconstruct(), wide, 70, np.abs(wide).max() * 30)
 
     # ---- Llt (solvers.rs:770-816) ----
-    S = np.asfortranarray(A @ A.T)
+    S = np.asfortranarray(A @ A.conj().T)
     llt = sv.llt(S, sv.Side.Lower)
-    assert np.all(np.triu(llt.L(), 1) == 0) and np.all(np.diag(llt.L()) > 0)
-    assert approx(llt.L() @ llt.L().T, S, n, np.abs(S).max())
+    assert np.all(np.triu(llt.L(), 1) == 0) and np.all(np.diag(llt.L()).real > 0)
+    # (the factorization reads Re(a_jj) and scales the stored element: a rounding-level imaginary part of S's diagonal stays one)
+    assert np.all(np.abs(np.diag(llt.L()).imag) <= 1e-14 * np.diag(llt.L()).real)
+    assert approx(llt.L() @ llt.L().conj().T, S, n, np.abs(S).max())
     check_solver(S, llt, np.linalg.cond(S))
     # only the chosen triangle is read
     poisoned = S.copy(order="F"); poisoned[np.triu_indices(n, 1)] = np.nan

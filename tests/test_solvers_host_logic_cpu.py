@@ -20,8 +20,9 @@ def oracle_backed_la(fb, oracle):
         return count
 
     def llt_solve_in_place(L, rhs, conj=0, par=None):
-        oracle.solve_triangular(L, rhs, lower=True, unit=False)
-        oracle.solve_triangular(L.T, rhs, lower=False, unit=False)
+        # conj?(L) y = rhs, then conj?(L)^H x = y (llt/solve.rs:12-35)
+        oracle.solve_triangular(L, rhs, lower=True, unit=False, conj=bool(conj))
+        oracle.solve_triangular(L.T, rhs, lower=False, unit=False, conj=not conj)
 
     def ldlt_in_place(A, regularization=(0.0, 0.0), signs=None, par=None, params=None):
         fail, count = oracle.ldlt(A, regularization[0], regularization[1], signs)
@@ -42,12 +43,12 @@ def oracle_backed_la(fb, oracle):
 
     def lu_solve_in_place(LU, perm, perm_inv, rhs, conj=0, par=None, U=None):
         rhs[...] = rhs[np.asarray(perm, dtype=np.int64)]
-        oracle.solve_triangular(LU, rhs, lower=True, unit=True)
-        oracle.solve_triangular(LU if U is None else U, rhs, lower=False, unit=False)
+        oracle.solve_triangular(LU, rhs, lower=True, unit=True, conj=bool(conj))
+        oracle.solve_triangular(LU if U is None else U, rhs, lower=False, unit=False, conj=bool(conj))
 
     def lu_solve_transpose_in_place(LU, perm, perm_inv, rhs, conj=0, par=None, U=None):
-        oracle.solve_triangular((LU if U is None else U).T, rhs, lower=True, unit=False)
-        oracle.solve_triangular(LU.T, rhs, lower=False, unit=True)
+        oracle.solve_triangular((LU if U is None else U).T, rhs, lower=True, unit=False, conj=bool(conj))
+        oracle.solve_triangular(LU.T, rhs, lower=False, unit=True, conj=bool(conj))
         rhs[...] = rhs[np.asarray(perm_inv, dtype=np.int64)]
 
     def qr_in_place(A, Q_coeff, par=None, params=None):
@@ -63,16 +64,16 @@ def oracle_backed_la(fb, oracle):
         return QR
 
     def qr_solve_lstsq_in_place(Q_basis, Q_coeff, R, rhs, conj=0, par=None):
-        oracle.qr_solve_lstsq(_packed(Q_basis, R), Q_coeff, rhs)
+        oracle.qr_solve_lstsq(_packed(Q_basis, R), Q_coeff, rhs, conj_QR=bool(conj))
 
     def qr_solve_in_place(Q_basis, Q_coeff, R, rhs, conj=0, par=None):
-        oracle.qr_solve(_packed(Q_basis, R), Q_coeff, rhs)
+        oracle.qr_solve(_packed(Q_basis, R), Q_coeff, rhs, conj_QR=bool(conj))
 
     def qr_solve_transpose_in_place(Q_basis, Q_coeff, R, rhs, conj=0, par=None):
-        oracle.qr_solve_transpose(_packed(Q_basis, R), Q_coeff, rhs)
+        oracle.qr_solve_transpose(_packed(Q_basis, R), Q_coeff, rhs, conj_QR=bool(conj))
 
     def apply_seq(basis, factor, rhs, conj=0, par=None):
-        oracle.apply_q_sequence(basis, factor, rhs)
+        oracle.apply_q_sequence(basis, factor, rhs, conj_lhs=bool(conj))
 
     def matmul(dst, accum, lhs, rhs, alpha, par=None):
         oracle.matmul(dst, accum == real.Accum.Add, lhs, rhs, alpha)
@@ -81,7 +82,7 @@ def oracle_backed_la(fb, oracle):
         oracle.matmul_triangular(dst, ds, accum == real.Accum.Add, lhs, ls, rhs, rs, alpha)
 
     return types.SimpleNamespace(
-        Accum=real.Accum, BlockStructure=real.BlockStructure, LltError=real.LltError,
+        Accum=real.Accum, BlockStructure=real.BlockStructure, LltError=real.LltError, CONJ_NO=real.CONJ_NO, CONJ_YES=real.CONJ_YES,
         cholesky_in_place=cholesky_in_place, llt_solve_in_place=llt_solve_in_place, lu_in_place=lu_in_place,
         ldlt_in_place=ldlt_in_place, ldlt_solve_in_place=ldlt_solve_in_place, LdltError=real.LdltError,
         lu_solve_in_place=lu_solve_in_place, lu_solve_transpose_in_place=lu_solve_transpose_in_place,
@@ -95,6 +96,7 @@ def test_solvers_host_logic_against_oracle_backend(fb, oracle, monkeypatch):
     sv = fb.solvers
     monkeypatch.setattr(sv, "la", oracle_backed_la(fb, oracle))
     run_all(sv)
+    run_all(sv, cplx=True)  # the reference's test_all_solvers runs on c64 (solvers.rs:2919-2977)
     run_ldlt(sv)
 
 
