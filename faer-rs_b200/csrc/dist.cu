@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "runtime.cuh"
+#include "tensor_ops.cuh"
 
 namespace fb {
 
@@ -1073,5 +1074,83 @@ size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, 
   for (int i = NW - 1; i >= 0; --i) ws_free(W[i]);
   return n_trans;
 }
+
+// ---- distributed Householder QR without pivoting ("QR: broadcast (V panel, T)") ----------------------------------
+// A (m x n, m >= n) in the 1-D block-column-cyclic layout with block width = the Householder block size bs: at step k the owner
+// factors its block column below the diagonal with the single-GPU driver (qr.cu: same panel kernels, same T blocks as a
+// single-GPU run with this block size), the factored panel (V below the diagonal, R on / above it) and its T block are broadcast
+// (two ncclBroadcast per block), and every rank applies (I - V T^-H V^H) to its own columns to the right. Q_coeff (bs x n,
+// leading dimension bs, DEVICE memory) is replicated: every rank ends with all T blocks. No look-ahead yet: the panel and
+// the updates alternate on the caller's stream. A rank-deficient block stops the run on every rank (returns -1): the
+// reference's column skipping crosses block boundaries, which the single-GPU general driver handles and this one does not.
+// `flags` bit 1: purely local run (ignore the communicator), as for the LLT / LU drivers.
+template <class T>
+static i64 dist_qr_impl(T* A_local, i64 ld, i64 m, i64 n, i64 bs, T* Q_coeff, int flags) {
+  FB_ENTRY();
+  const bool local_only = (flags & 2) != 0;
+  const int P = (g_comm && !local_only) ? g_nranks : 1, me = (g_comm && !local_only) ? g_rank : 0;
+  FB_ASSERT(m >= n, "distributed QR: nrows >= ncols");
+  FB_ASSERT(bs > 0, "block size must be positive");
+  if (n == 0) return 0;
+  cudaStream_t st = current_stream();
+  const ncclDataType_t dt = sizeof(T) == 8 ? ncclDouble : ncclFloat;
+  const i64 nblk = nblocks(n, bs), my_cols = local_cols(n, bs, P, me);
+  T* W = P > 1 ? (T*)ws_alloc((size_t)m * (size_t)bs * sizeof(T)) : nullptr;
+  T* tmp = (T*)ws_alloc((size_t)bs * (size_t)std::max<i64>(my_cols, 1) * sizeof(T));
+  int* d_status = (int*)ws_alloc(sizeof(int));
+  i64 result = n;
+  for (i64 k = 0; k < nblk; ++k) {
+    const i64 j0 = k * bs, jb = std::min(bs, n - j0), rows = m - j0;
+    const int owner = (int)(k % P);
+    T* Tk = Q_coeff + j0 * bs;  // bs x jb block of the replicated factor (the jb x jb T block in its first rows)
+    View<T> Hk{Tk, jb, jb, 1, bs};
+    View<const T> V;
+    int status = 0;
+    if (owner == me) {
+      T* pk = A_local + local_off(k, bs, P) * ld + j0;
+      View<T> panel{pk, rows, jb, 1, ld};
+      const i64 r = qr_in_place<T>(st, panel, Hk);  // synchronises st
+      status = r < jb ? 1 : 0;
+      if (P > 1) {
+        FB_CUDA_CHECK(cudaMemcpy2DAsync(W, (size_t)rows * sizeof(T), pk, (size_t)ld * sizeof(T), (size_t)rows * sizeof(T), (size_t)jb,
+                                        cudaMemcpyDeviceToDevice, st));
+        V = View<const T>{W, rows, jb, 1, rows};
+      } else {
+        V = View<const T>{pk, rows, jb, 1, ld};
+      }
+    } else {
+      V = View<const T>{W, rows, jb, 1, rows};
+    }
+    if (P > 1) {
+      FB_CUDA_CHECK(cudaMemcpyAsync(d_status, &status, sizeof(int), cudaMemcpyHostToDevice, st));
+      FB_NCCL_CHECK(g_nccl.Broadcast(d_status, d_status, 1, ncclInt32, owner, g_comm, st));
+      FB_NCCL_CHECK(g_nccl.Broadcast(W, W, (size_t)rows * (size_t)jb, dt, owner, g_comm, st));
+      FB_NCCL_CHECK(g_nccl.Broadcast(Tk, Tk, (size_t)bs * (size_t)jb, dt, owner, g_comm, st));
+      FB_CUDA_CHECK(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+      FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (status) {
+      result = -1;
+      break;
+    }
+    // my columns to the right of block k: local storage is ordered by block index, so they are the tail of A_local
+    i64 t0 = 0;
+    for (i64 b = me; b <= k; b += P) t0 += std::min(bs, n - b * bs);
+    if (my_cols > t0)
+      apply_block_householder_on_the_left<T>(st, V, cview(Hk), View<T>{A_local + t0 * ld + j0, rows, my_cols - t0, 1, ld}, true, tmp);
+  }
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  ws_free(d_status);
+  ws_free(tmp);
+  if (W) ws_free(W);
+  return result;
+}
+i64 dist_qr_f64(double* A_local, i64 ld, i64 m, i64 n, i64 bs, double* Q_coeff, int flags) {
+  return dist_qr_impl<double>(A_local, ld, m, n, bs, Q_coeff, flags);
+}
+i64 dist_qr_f32(float* A_local, i64 ld, i64 m, i64 n, i64 bs, float* Q_coeff, int flags) {
+  return dist_qr_impl<float>(A_local, ld, m, n, bs, Q_coeff, flags);
+}
+
 
 }  // namespace fb

@@ -1520,6 +1520,17 @@ size_t faer_b200_dist_partial_piv_lu_factor_in_place_f64(void* A_local, size_t l
   return dist_lu_f64((double*)A_local, (i64)ld, (i64)n, (i64)nb, perm_fwd, perm_inv, lookahead);
 }
 
+long long faer_b200_dist_qr_factor_in_place_f64(void* A_local, size_t ld, size_t nrows, size_t ncols, size_t block_size, void* Q_coeff,
+                                                int flags) {
+  FB_ASSERT(ncols == 0 || (is_device_pointer(A_local) && is_device_pointer(Q_coeff)), "distributed entry points take device-resident matrices");
+  return dist_qr_f64((double*)A_local, (i64)ld, (i64)nrows, (i64)ncols, (i64)block_size, (double*)Q_coeff, flags);
+}
+long long faer_b200_dist_qr_factor_in_place_f32(void* A_local, size_t ld, size_t nrows, size_t ncols, size_t block_size, void* Q_coeff,
+                                                int flags) {
+  FB_ASSERT(ncols == 0 || (is_device_pointer(A_local) && is_device_pointer(Q_coeff)), "distributed entry points take device-resident matrices");
+  return dist_qr_f32((float*)A_local, (i64)ld, (i64)nrows, (i64)ncols, (i64)block_size, (float*)Q_coeff, flags);
+}
+
 void faer_b200_bidiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) {
   bidiag_entry<double>(A, H_left, H_right);
 }

@@ -106,6 +106,10 @@ i64 lookahead_min_n();
 i64 lookahead_block();
 // Distributed P A = L U (square n x n). perm_fwd / perm_inv: HOST arrays of n int64 (identical on every rank).
 size_t dist_lu_f64(double* A_local, i64 ld, i64 n, i64 nb, long long* perm_fwd, long long* perm_inv, int lookahead);
+// distributed Householder QR (m >= n; block width = Householder block size bs; Q_coeff bs x n on the device, replicated);
+// returns n, or -1 when a block turned out rank-deficient
+i64 dist_qr_f64(double* A_local, i64 ld, i64 m, i64 n, i64 bs, double* Q_coeff, int flags);
+i64 dist_qr_f32(float* A_local, i64 ld, i64 m, i64 n, i64 bs, float* Q_coeff, int flags);
 
 // single-GPU entry points switch to the look-ahead block-column driver above this size (env FAER_B200_LOOKAHEAD_MIN_N,
 // default 4096; 0 disables) with this block width (env FAER_B200_NB, default 1024)

@@ -1,4 +1,4 @@
-"""Multi-GPU front end: 1-D block-column-cyclic layout helpers + the distributed LLT entry point.
+"""Multi-GPU front end: 1-D block-column-cyclic layout helpers, the distributed LLT / LU entry points and the column-split GEMM.
 
 One process per GPU (torchrun); `torch.distributed` is the plumbing (rendezvous, id exchange, status reduction); the
 data path is the library's own NCCL broadcast of each factored panel (csrc/dist.cu), issued on a high-priority CUDA
@@ -63,6 +63,14 @@ def gather_block_cyclic(locals_, n: int, nb: int, nranks: int):
     return out
 
 
+def column_slab(ncols: int, nranks: int, rank: int) -> tuple[int, int]:
+    """[start, stop) of the contiguous column slab of `rank` in a 1-D column split of ncols columns over nranks ranks: widths
+    differ by at most one, slabs ordered by rank (GEMM shards by output columns, no reduction)."""
+    base, extra = divmod(ncols, nranks)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
 # ---- communicator ------------------------------------------------------------------------------------
 def init_from_torch_distributed() -> None:
     """Create the library's NCCL communicator over the default torch.distributed group (collective call)."""
@@ -108,6 +116,10 @@ def _bind(lib) -> None:
     lib.faer_b200_dist_partial_piv_lu_factor_in_place_f64.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                                                       C.c_void_p, C.c_void_p, C.c_int]
     lib.faer_b200_dist_partial_piv_lu_factor_in_place_f64.restype = C.c_size_t
+    for suf in ("f64", "f32"):
+        f = getattr(lib, f"faer_b200_dist_qr_factor_in_place_{suf}")
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int]
+        f.restype = C.c_longlong
     _bound = True
 
 
@@ -157,3 +169,46 @@ def lu_in_place(A_local, n: int, nb: int = 512, lookahead=True):
                                                                 pinv.ctypes.data,
                                                                 int(lookahead) if not isinstance(lookahead, bool) else (1 if lookahead else 0))
     return perm, pinv, int(cnt)
+
+
+# ---- distributed QR -----------------------------------------------------------------------------------
+def qr_in_place(A_local, nrows: int, ncols: int, block_size: int, local_only: bool = False):
+    """Distributed in-place Householder QR without pivoting (nrows >= ncols; f64 or f32). `A_local`: torch CUDA tensor, column-major
+    view (nrows x local_cols) of the block columns of width `block_size` owned by this rank. Returns Q_coeff (block_size x ncols
+    CUDA tensor, column-major, identical on every rank). Raises RuntimeError on a rank-deficient block (the reference's column
+    skipping crosses block boundaries: use linalg.qr_in_place on one GPU for such inputs)."""
+    import torch
+    lib = capi.load()
+    _bind(lib)
+    assert capi._is_torch(A_local) and A_local.is_cuda and A_local.dtype in (torch.float64, torch.float32)
+    assert A_local.shape[0] == nrows and (A_local.shape[1] == 0 or A_local.stride(0) == 1) and nrows >= ncols
+    ld = A_local.stride(1) if A_local.shape[1] > 1 else max(nrows, 1)
+    H = torch.zeros((ncols, block_size), dtype=A_local.dtype, device=A_local.device).T  # column-major, ld = block_size
+    suf = "f64" if A_local.dtype == torch.float64 else "f32"
+    r = getattr(lib, f"faer_b200_dist_qr_factor_in_place_{suf}")(A_local.data_ptr(), ld, nrows, ncols, block_size, H.data_ptr(),
+                                                                 2 if local_only else 0)
+    if r < 0:
+        raise RuntimeError("distributed QR met a rank-deficient block")
+    return H
+
+
+# ---- distributed GEMM: 1-D column split -----------------------------------------------------------------
+def matmul(C_local, accum, A, B_local, alpha=1.0, src_rank=None, par=None) -> None:
+    """C[:, slab] = [C[:, slab] +] alpha * A @ B[:, slab] on every rank, slab = column_slab(ncols, world, rank): the
+    independent-output-tiles sharding of SURVEY.md 8e. `A` is replicated; `B_local` / `C_local` are this rank's column slabs.
+    There is NO data-path collective in the product itself (each rank runs the single-GPU kernels on its slab; the k-order of
+    every output element is the single-GPU one). If `src_rank` is given, `A` only holds valid data on that rank and is first
+    broadcast over the default torch.distributed group (one NCCL broadcast, the only exchange)."""
+    from . import linalg as la
+    if src_rank is not None:
+        import torch.distributed as td
+        if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+            assert capi._is_torch(A), "broadcasting A needs a torch tensor"
+            # broadcast the storage as it is laid out (column-major views are transposes of contiguous tensors)
+            buf = A if A.is_contiguous() else A.T
+            assert buf.is_contiguous(), "A must be contiguous in row- or column-major order to be broadcast in place"
+            td.broadcast(buf, src=src_rank)
+    assert A.shape[0] == C_local.shape[0] and A.shape[1] == B_local.shape[0] and B_local.shape[1] == C_local.shape[1]
+    if C_local.shape[1] == 0:
+        return
+    la.matmul(C_local, accum, A, B_local, alpha, par)

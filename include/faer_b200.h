@@ -457,6 +457,16 @@ struct FaerV0_24_LltStatus faer_b200_dist_llt_factor_in_place_f64(void *A_local,
  * transposition count. Pivots are identical to the single-GPU entry point's. */
 size_t faer_b200_dist_partial_piv_lu_factor_in_place_f64(void *A_local, size_t ld, size_t n, size_t nb,
                                                          long long *perm_fwd, long long *perm_inv, int lookahead);
+/* Distributed Householder QR without pivoting (the owner factors its block column, broadcasts the factored panel
+ * and its T block, every rank applies the block reflector to its own columns). nrows >= ncols; the layout's block width is the
+ * Householder block size `block_size` (the reference's Q_coeff.nrows, qr/no_pivoting/factor.rs:258-301). Q_coeff: DEVICE,
+ * block_size x ncols column-major with leading dimension block_size, replicated (every rank ends with all T blocks).
+ * Returns ncols, or -1 (on every rank) when a block is rank-deficient: use the single-GPU entry point for such inputs.
+ * `flags` bit 1: purely local run that ignores an existing communicator. */
+long long faer_b200_dist_qr_factor_in_place_f64(void *A_local, size_t ld, size_t nrows, size_t ncols, size_t block_size,
+                                                void *Q_coeff, int flags);
+long long faer_b200_dist_qr_factor_in_place_f32(void *A_local, size_t ld, size_t nrows, size_t ncols, size_t block_size,
+                                                void *Q_coeff, int flags);
 /* ---- reduction to bidiagonal form A = U B V^H (nrows >= ncols). faer-ffi does not export this stage on its own (it is
  * reached through libfaer_v0_23_svd_*, faer-ffi/src/lib.rs:2345-2366 -> faer/src/linalg/svd/mod.rs:326-431); the entry
  * mirrors the Rust function it replaces, faer::linalg::svd::bidiag::bidiag_in_place (faer/src/linalg/svd/bidiag.rs:47-54):

@@ -168,3 +168,117 @@ def test_layout_helpers():
         A = np.arange(n * n, dtype=np.float64).reshape(n, n)
         locs = [lay.scatter_block_cyclic(A, nb, P, r) for r in range(P)]
         assert np.array_equal(lay.gather_block_cyclic(locs, n, nb, P), A)
+
+
+def test_column_slabs_partition_the_columns():
+    import faer_b200  # noqa: F401
+    from faer_rs_b200 import dist as lay
+    for ncols in [0, 1, 7, 64, 100, 4097]:
+        for P in [1, 2, 3, 4, 8]:
+            slabs = [lay.column_slab(ncols, P, r) for r in range(P)]
+            assert slabs[0][0] == 0 and slabs[-1][1] == ncols
+            assert all(slabs[r][1] == slabs[r + 1][0] for r in range(P - 1))
+            widths = [b - a for a, b in slabs]
+            assert max(widths) - min(widths) <= 1 and sorted(widths, reverse=True) == widths
+
+
+def _gemm_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import faer_b200  # noqa: F401
+    from faer_rs_b200 import dist as lay
+    from faer_rs_b200 import linalg as la
+    from oracle import oracle as orc
+
+    # the per-rank product is the library's single-GPU matmul; on the CPU the oracle stands in for it (test infrastructure)
+    def cpu_matmul(dst, accum, lhs, rhs, alpha, par=None):
+        d = np.asfortranarray(dst.numpy().copy()); orc.matmul(d, accum == la.Accum.Add, np.asfortranarray(lhs.numpy()),
+                                                              np.asfortranarray(rhs.numpy()), alpha)
+        dst.copy_(torch.from_numpy(d))
+    la.matmul = cpu_matmul
+    m, k, n = 37, 29, 45
+    rng = np.random.default_rng(3)  # replicated inputs, same seed on every rank
+    A = rng.standard_normal((m, k)); B = rng.standard_normal((k, n)); C0 = rng.standard_normal((m, n))
+    a, b = lay.column_slab(n, world, rank)
+    At = torch.from_numpy(A.copy()) if rank == 1 else torch.zeros((m, k), dtype=torch.float64)  # A only valid on rank 1
+    Cl = torch.from_numpy(np.ascontiguousarray(C0[:, a:b]))
+    lay.matmul(Cl, la.Accum.Add, At, torch.from_numpy(np.ascontiguousarray(B[:, a:b])), 0.5, src_rank=1)
+    np.save(os.path.join(out_dir, f"c{rank}.npy"), Cl.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_column_split_gemm_gloo_world2(tmp_path):
+    """SURVEY.md 8e GEMM row: 1-D column split, A broadcast from the rank that holds it, no collective in the product; the slabs
+    concatenate to the single-process result."""
+    world, port = 2, _free_port()
+    mp.spawn(_gemm_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((37, 29)); B = rng.standard_normal((29, 45)); C0 = rng.standard_normal((37, 45))
+    got = np.concatenate([np.load(tmp_path / f"c{r}.npy") for r in range(world)], axis=1)
+    assert np.allclose(got, C0 + 0.5 * A @ B, rtol=1e-13, atol=1e-13)
+
+
+def _qr_worker(rank, world, port, m, n, bs, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import faer_b200  # noqa: F401
+    from faer_rs_b200 import dist as lay
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(11)  # replicated global input
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    loc = lay.scatter_block_cyclic(A, bs, world, rank)
+    H = np.zeros((bs, n), order="F")
+    # ---- distributed QR schedule (mirrors csrc/dist.cu::dist_qr_impl) ----
+    for k in range(lay.num_blocks(n, bs)):
+        j0 = k * bs; jb = min(bs, n - j0); owner = lay.owner_of_block(k, world)
+        W = np.zeros((m - j0, jb), order="F"); Tk = np.zeros((bs, jb), order="F")
+        if owner == rank:
+            off = lay.local_col_offset(k, bs, world)
+            panel = np.asfortranarray(loc[j0:, off:off + jb])
+            Hk, r = orc.qr(panel, block_size=jb)
+            assert r == jb
+            loc[j0:, off:off + jb] = panel
+            W[:, :] = panel; Tk[:jb, :] = Hk
+        for buf in (W, Tk):  # the two broadcasts of the step: factored panel, T block
+            t = torch.from_numpy(np.ascontiguousarray(buf))
+            dist.broadcast(t, src=owner)
+            buf[...] = t.numpy()
+        H[:, j0:j0 + jb] = Tk
+        t0 = sum(min(bs, n - b * bs) for b in range(rank, k + 1, world))  # my columns to the right of block k are the local tail
+        if loc.shape[1] > t0:
+            M = np.asfortranarray(loc[j0:, t0:])
+            orc.apply_block_householder_on_the_left(W, np.asfortranarray(Tk[:jb, :jb]), M, forward=True)
+            loc[j0:, t0:] = M
+    np.save(os.path.join(out_dir, f"qr{rank}.npy"), loc)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "qrH.npy"), H)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m,n,bs", [(70, 50, 8), (64, 64, 16), (90, 33, 8)])
+def test_block_cyclic_qr_schedule_gloo_world2(tmp_path, oracle, m, n, bs):
+    """SURVEY.md 8e QR row: owner factors its block column, broadcasts (V panel, T), every rank updates its own columns; the result
+    is the single-process blocked QR with the same block size (factors and T blocks to rounding)."""
+    import faer_b200  # noqa: F401
+    from faer_rs_b200 import dist as lay
+    world, port = 2, _free_port()
+    mp.spawn(_qr_worker, args=(world, port, m, n, bs, str(tmp_path)), nprocs=world, join=True)
+    got = lay.gather_block_cyclic([np.load(tmp_path / f"qr{r}.npy") for r in range(world)], n, bs, world)
+    H = np.load(tmp_path / "qrH.npy")
+    rng = np.random.default_rng(11)
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    want = A.copy(order="F"); Ho, rank = oracle.qr(want, block_size=bs)
+    assert rank == n
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-10)
+    for j in range(0, n, bs):
+        b = min(bs, n - j)
+        assert np.allclose(np.triu(H[:b, j:j + b]), np.triu(Ho[:b, j:j + b]), rtol=1e-10, atol=1e-10)
