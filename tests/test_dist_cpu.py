@@ -264,13 +264,13 @@ def _qr_worker(rank, world, port, m, n, bs, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("m,n,bs", [(70, 50, 8), (64, 64, 16), (90, 33, 8)])
-def test_block_cyclic_qr_schedule_gloo_world2(tmp_path, oracle, m, n, bs):
+@pytest.mark.parametrize("m,n,bs,world", [(70, 50, 8, 2), (64, 64, 16, 2), (90, 33, 8, 2), (100, 77, 8, 3), (60, 40, 4, 4)])
+def test_block_cyclic_qr_schedule_gloo(tmp_path, oracle, m, n, bs, world):
     """SURVEY.md 8e QR row: owner factors its block column, broadcasts (V panel, T), every rank updates its own columns; the result
     is the single-process blocked QR with the same block size (factors and T blocks to rounding)."""
     import faer_b200  # noqa: F401
     from faer_rs_b200 import dist as lay
-    world, port = 2, _free_port()
+    port = _free_port()
     mp.spawn(_qr_worker, args=(world, port, m, n, bs, str(tmp_path)), nprocs=world, join=True)
     got = lay.gather_block_cyclic([np.load(tmp_path / f"qr{r}.npy") for r in range(world)], n, bs, world)
     H = np.load(tmp_path / "qrH.npy")
