@@ -1,7 +1,6 @@
 """Multi-rank parity on hardware (needs >= 2 GPUs; skipped on a single-GPU box): torchrun over NCCL, the distributed LLT and LU on
 2 (and 4 / 8 when visible) ranks against the single-GPU run of the same matrices — permutations / status bit-exact, factors to
-rounding, reconstruction probes —, the distributed QR (broadcast of the factored panel and its T block) against the same driver run
-locally, and the column-split GEMM against the single-GPU product (tools/dist_parity.py). The world-size-2 logic of the layout is covered on CPU by
+rounding, reconstruction probes (tools/dist_parity.py; the distributed QR and the column-split GEMM: test_gpu_zzzzzzzz_dist_multi_qr_gemm.py). The world-size-2 logic of the layout is covered on CPU by
 tests/test_dist_cpu.py (gloo)."""
 import os
 import subprocess
@@ -22,4 +21,4 @@ def test_distributed_factorizations_match_single_gpu(cuda_dev, world):
            "--master-port", str(29540 + world), os.path.join(ROOT, "tools", "dist_parity.py"), "3072", "256"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("-> OK") == 4, out.stdout[-2000:]  # llt, lu, qr, gemm
+    assert out.stdout.count("-> OK") == 2, out.stdout[-2000:]

@@ -1,7 +1,8 @@
 """Multi-rank parity check (run under torchrun, one rank per GPU): the distributed LLT and LU on P ranks against the SAME
 factorizations on one GPU (rank 0, communicator ignored): permutations and status bit-exact, factors to rounding (different GEMM
 kernels may serve different local widths), plus the reconstruction probes. Prints one line per check and exits non-zero on failure.
-usage: torchrun --nproc-per-node P tools/dist_parity.py [n] [nb]"""
+With `qr-gemm` as third argument the run checks the distributed QR and the column-split GEMM instead (same exit convention).
+usage: torchrun --nproc-per-node P tools/dist_parity.py [n] [nb] [qr-gemm]"""
 import os
 import sys
 
@@ -14,6 +15,8 @@ import faer_b200  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 nb = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+what = sys.argv[3] if len(sys.argv) > 3 else "llt-lu"
+assert what in ("llt-lu", "qr-gemm", "all")
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local_rank)
@@ -46,7 +49,7 @@ torch.manual_seed(0)
 G = torch.randn((n, n), dtype=torch.float64, device=dev)
 S = torch.addmm(n * torch.eye(n, dtype=torch.float64, device=dev), G, G.T)
 cols = torch.as_tensor(lay.global_col_indices(n, nb, world, rank), device=dev)
-for name in ("llt", "lu"):
+for name in (("llt", "lu") if what in ("llt-lu", "all") else ()):
     A = S if name == "llt" else G
     loc = A[:, cols].T.contiguous().T
     if name == "llt":
@@ -83,71 +86,72 @@ for name in ("llt", "lu"):
         ok = ok and good
         print(f"[dist_parity] {name} world={world} n={n} nb={nb}: status/perm identical {same_status}, "
               f"max |factor(P) - factor(1)| = {diff:.3e} (scale {scale:.1f}), probe residual {resid:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
-# ---- distributed QR (broadcast (V panel, T)): P ranks against the same driver run locally on rank 0 and against the
-# reconstruction probe A x = Q (R x) through the library's own block-Householder sequence ----
-mq, nq = n + n // 2, n
-bsq = int(faer_b200.linalg.qr_recommended_block_size(mq, nq))
-torch.manual_seed(2)
-Aq = torch.randn((mq, nq), dtype=torch.float64, device=dev)
-colsq = torch.as_tensor(lay.global_col_indices(nq, bsq, world, rank), device=dev)
-locq = Aq[:, colsq].T.contiguous().T
-Hq = lay.qr_in_place(locq, mq, nq, bsq)
-if world > 1:
-    fullq = torch.zeros((mq, nq), dtype=torch.float64, device=dev) if rank == 0 else None
-    for r in range(world):
-        w = lay.local_cols(nq, bsq, world, r)
-        buf = locq.T.contiguous() if r == rank else torch.empty((w, mq), dtype=torch.float64, device=dev)
-        dist.broadcast(buf, src=r)
-        if rank == 0:
-            fullq[:, torch.as_tensor(lay.global_col_indices(nq, bsq, world, r), device=dev)] = buf.T
-else:
-    fullq = locq
-if rank == 0:
-    oneq = Aq.T.contiguous().T.clone(memory_format=torch.preserve_format)
-    H1 = lay.qr_in_place(oneq, mq, nq, bsq, local_only=True)
-    diff = float((fullq - oneq).abs().max()); scale = float(oneq.abs().max())
-    hdiff = max(float((torch.triu(Hq[:min(bsq, nq - j), j:j + bsq]) - torch.triu(H1[:min(bsq, nq - j), j:j + bsq])).abs().max())
-                for j in range(0, nq, bsq))
-    x = torch.randn((nq, 3), dtype=torch.float64, device=dev)
-    y = torch.zeros((mq, 3), dtype=torch.float64, device=dev).T.contiguous().T
-    y[:nq] = torch.triu(fullq[:nq]) @ x
-    yc = y.T.contiguous().T
-    faer_b200.linalg.apply_block_householder_sequence_on_the_left_in_place(fullq.T.contiguous().T, Hq, yc)
-    resid = float((Aq @ x - yc).abs().max()) / (float(Aq.abs().max()) * mq)
-    good = diff <= 1e-9 * scale and hdiff <= 1e-9 and resid < 1e-12
-    ok = ok and good
-    print(f"[dist_parity] qr world={world} {mq}x{nq} bs={bsq}: max |factor(P) - factor(1)| = {diff:.3e} (scale {scale:.1f}), "
-          f"max |T(P) - T(1)| = {hdiff:.3e}, probe residual {resid:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+if what in ("qr-gemm", "all"):
+    # ---- distributed QR (broadcast (V panel, T)): P ranks against the same driver run locally on rank 0 and against the
+    # reconstruction probe A x = Q (R x) through the library's own block-Householder sequence ----
+    mq, nq = n + n // 2, n
+    bsq = int(faer_b200.linalg.qr_recommended_block_size(mq, nq))
+    torch.manual_seed(2)
+    Aq = torch.randn((mq, nq), dtype=torch.float64, device=dev)
+    colsq = torch.as_tensor(lay.global_col_indices(nq, bsq, world, rank), device=dev)
+    locq = Aq[:, colsq].T.contiguous().T
+    Hq = lay.qr_in_place(locq, mq, nq, bsq)
+    if world > 1:
+        fullq = torch.zeros((mq, nq), dtype=torch.float64, device=dev) if rank == 0 else None
+        for r in range(world):
+            w = lay.local_cols(nq, bsq, world, r)
+            buf = locq.T.contiguous() if r == rank else torch.empty((w, mq), dtype=torch.float64, device=dev)
+            dist.broadcast(buf, src=r)
+            if rank == 0:
+                fullq[:, torch.as_tensor(lay.global_col_indices(nq, bsq, world, r), device=dev)] = buf.T
+    else:
+        fullq = locq
+    if rank == 0:
+        oneq = Aq.T.contiguous().T.clone(memory_format=torch.preserve_format)
+        H1 = lay.qr_in_place(oneq, mq, nq, bsq, local_only=True)
+        diff = float((fullq - oneq).abs().max()); scale = float(oneq.abs().max())
+        hdiff = max(float((torch.triu(Hq[:min(bsq, nq - j), j:j + bsq]) - torch.triu(H1[:min(bsq, nq - j), j:j + bsq])).abs().max())
+                    for j in range(0, nq, bsq))
+        x = torch.randn((nq, 3), dtype=torch.float64, device=dev)
+        y = torch.zeros((mq, 3), dtype=torch.float64, device=dev).T.contiguous().T
+        y[:nq] = torch.triu(fullq[:nq]) @ x
+        yc = y.T.contiguous().T
+        faer_b200.linalg.apply_block_householder_sequence_on_the_left_in_place(fullq.T.contiguous().T, Hq, yc)
+        resid = float((Aq @ x - yc).abs().max()) / (float(Aq.abs().max()) * mq)
+        good = diff <= 1e-9 * scale and hdiff <= 1e-9 and resid < 1e-12
+        ok = ok and good
+        print(f"[dist_parity] qr world={world} {mq}x{nq} bs={bsq}: max |factor(P) - factor(1)| = {diff:.3e} (scale {scale:.1f}), "
+              f"max |T(P) - T(1)| = {hdiff:.3e}, probe residual {resid:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
 
-# ---- column-split GEMM: every rank forms its slab of C = C0 + alpha A B with A broadcast from the last rank; the
-# slabs are compared with the same product done on one GPU (rank 0). Different local widths may pick different kernels, so the
-# comparison is to the forward bound 2 k u sum|a||b|, not bitwise ----
-m2 = k2 = n
-torch.manual_seed(1)
-Af = torch.randn((m2, k2), dtype=torch.float64, device=dev); Bf = torch.randn((k2, n), dtype=torch.float64, device=dev)
-C0 = torch.randn((m2, n), dtype=torch.float64, device=dev)
-a0, a1 = lay.column_slab(n, world, rank)
-A_in = Af.T.contiguous().T if rank == world - 1 else torch.zeros((k2, m2), dtype=torch.float64, device=dev).T
-Cl = C0[:, a0:a1].T.contiguous().T
-lay.matmul(Cl, faer_b200.linalg.Accum.Add, A_in, Bf[:, a0:a1].T.contiguous().T, 0.75, src_rank=world - 1)
-if world > 1:
-    pieces = []
-    for r in range(world):
-        b0, b1 = lay.column_slab(n, world, r)
-        buf = Cl.T.contiguous() if r == rank else torch.empty((b1 - b0, m2), dtype=torch.float64, device=dev)
-        dist.broadcast(buf, src=r)
-        pieces.append(buf.T)
-    Cfull = torch.cat(pieces, dim=1)
-else:
-    Cfull = Cl
-if rank == 0:
-    one = C0.T.contiguous().T.clone(memory_format=torch.preserve_format)
-    faer_b200.linalg.matmul(one, faer_b200.linalg.Accum.Add, Af.T.contiguous().T, Bf.T.contiguous().T, 0.75)
-    bound = 2 * k2 * 2.0 ** -53 * 0.75 * (Af.abs() @ Bf.abs()) + 4 * 2.0 ** -53 * C0.abs()
-    worst = float(((Cfull - one).abs() / bound).max())
-    good = worst <= 1.0
-    ok = ok and good
-    print(f"[dist_parity] gemm world={world} n={n}: max |C(P) - C(1)| / (2 k u |A||B|) = {worst:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+    # ---- column-split GEMM: every rank forms its slab of C = C0 + alpha A B with A broadcast from the last rank; the
+    # slabs are compared with the same product done on one GPU (rank 0). Different local widths may pick different kernels, so the
+    # comparison is to the forward bound 2 k u sum|a||b|, not bitwise ----
+    m2 = k2 = n
+    torch.manual_seed(1)
+    Af = torch.randn((m2, k2), dtype=torch.float64, device=dev); Bf = torch.randn((k2, n), dtype=torch.float64, device=dev)
+    C0 = torch.randn((m2, n), dtype=torch.float64, device=dev)
+    a0, a1 = lay.column_slab(n, world, rank)
+    A_in = Af.T.contiguous().T if rank == world - 1 else torch.zeros((k2, m2), dtype=torch.float64, device=dev).T
+    Cl = C0[:, a0:a1].T.contiguous().T
+    lay.matmul(Cl, faer_b200.linalg.Accum.Add, A_in, Bf[:, a0:a1].T.contiguous().T, 0.75, src_rank=world - 1)
+    if world > 1:
+        pieces = []
+        for r in range(world):
+            b0, b1 = lay.column_slab(n, world, r)
+            buf = Cl.T.contiguous() if r == rank else torch.empty((b1 - b0, m2), dtype=torch.float64, device=dev)
+            dist.broadcast(buf, src=r)
+            pieces.append(buf.T)
+        Cfull = torch.cat(pieces, dim=1)
+    else:
+        Cfull = Cl
+    if rank == 0:
+        one = C0.T.contiguous().T.clone(memory_format=torch.preserve_format)
+        faer_b200.linalg.matmul(one, faer_b200.linalg.Accum.Add, Af.T.contiguous().T, Bf.T.contiguous().T, 0.75)
+        bound = 2 * k2 * 2.0 ** -53 * 0.75 * (Af.abs() @ Bf.abs()) + 4 * 2.0 ** -53 * C0.abs()
+        worst = float(((Cfull - one).abs() / bound).max())
+        good = worst <= 1.0
+        ok = ok and good
+        print(f"[dist_parity] gemm world={world} n={n}: max |C(P) - C(1)| / (2 k u |A||B|) = {worst:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
 if world > 1:
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(t, src=0)
