@@ -1,5 +1,6 @@
-// c64 / c32 (complex<f64> / complex<f32>) triangular solves, Cholesky LLT and partial-pivoting LU: faer's recursions on the
-// complex GEMMs (gemm_c64.cu, gemm_c32.cu) with small scalar complex leaf kernels, one source templated over the real type R.
+// c64 / c32 (complex<f64> / complex<f32>) triangular solves, Cholesky LLT, partial-pivoting LU and Householder QR (+ block-Householder
+// sequences): faer's recursions on the complex GEMMs (gemm_c64.cu, gemm_c32.cu) with small scalar complex leaf kernels, one source
+// templated over the real type R. (The comment blocks at the LU and QR sections cite their reference lines.)
 //
 // Reference:
 //   triangular_solve::solve_[unit_]{lower,upper}_triangular_in_place_with_conj   faer/src/linalg/triangular_solve.rs:220-604
@@ -10,8 +11,8 @@
 //       a_ij <- a_ij - conj(a_jk) a_ik, d = Re(a_jj), [regularise], fail if !(d > 0), l = sqrt(d), column j (diagonal included)
 //       multiplied by recip(l)  (ldlt/factor.rs:7-177, 299-366)
 //
-// All views are in COMPLEX element units (pointer to the first complex element as double*, strides in complex elements), as in
-// gemm_c64.cu. The leaves are plain scalar kernels (a 32 x 32 block per CTA / one thread per right-hand-side column): O(n^2 leaf)
+// All views are in COMPLEX element units (pointer to the first complex element as R*, strides in complex elements), as in
+// gemm_c64.cu / gemm_c32.cu. The leaves are plain scalar kernels (a 32 x 32 block per CTA / one thread per right-hand-side column): O(n^2 leaf)
 // work next to the O(n^3) that runs on the DMMA GEMM.
 #include <algorithm>
 #include <vector>
