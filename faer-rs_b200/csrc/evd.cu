@@ -3,10 +3,11 @@
 // come from one bisection thread per value (tridiag_ev.cuh).
 // Reference: faer/src/linalg/evd/mod.rs:270-353 (`self_adjoint_evd` with u = None: copy_from_triangular_lower, tridiag_in_place,
 // tridiag_evd::qr_algorithm on (diag, offdiag); nondecreasing order), as `MatRef::self_adjoint_eigenvalues` (solvers.rs:417-456).
-// Eigenvectors (divide and conquer + the Householder back-transform) are not built yet: the entry point refuses them.
-// Limit inherited from tridiag.cu: n <= 8192.
-// STATUS: written after round 1's last GPU session; tridiag.cu is validated, tridiag_ev.cuh is checked on the CPU (same
-// header compiled for the host), the small kernels below have not run yet.
+// This file is the VALUES-ONLY path (U passed with no columns); with eigenvectors the entry point goes to svd_vectors.cu
+// (divide and conquer of the tridiagonal, tridiag_dc.cu, + the Householder back-transform). Any n (tridiag.cu keeps its
+// per-CTA vectors in global memory above n = 8192).
+// STATUS: validated on hardware (tests/test_gpu_zz8_self_adjoint_eigenvalues.py, tests/test_gpu_zz11_evd_svd_vectors.py); tridiag_ev.cuh is also
+// checked on the CPU (the same header compiled for the host, tests/test_tridiag_ev_cpu.py).
 #include "runtime.cuh"
 #include "tensor_ops.cuh"
 #include "tridiag_ev.cuh"

@@ -1,6 +1,6 @@
 // LDLT without pivoting, f64: leaf kernel + recursive driver + the solve on the factors.
-// STATUS: written after round 1's last GPU session — compiled, checked against the reference recurrence only on paper.
-// The GPU tests (tests/test_gpu_zz6_ldlt.py) are its first run on hardware.
+// STATUS: validated on hardware against the oracle's LDLT (tests/test_gpu_zz6_ldlt.py; the leaf recurrence is also emulated on
+// the CPU in tests/test_ldlf2_emulation_cpu.py).
 //
 // Reference: faer/src/linalg/cholesky/ldlt/factor.rs
 //   cholesky_in_place 725-767 -> cholesky_recursion_right_looking(is_llt = false) 367-498:

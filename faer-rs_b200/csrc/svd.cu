@@ -5,10 +5,10 @@
 // Like the reference, a QR factorization comes first when nrows / ncols exceeds params.qr_ratio_threshold (11/6) and R is
 // bidiagonalised instead. Differences, both documented in DESIGN.md: (1) the reference reaches the values of the bidiagonal
 // through bidiag_svd (QR iteration / divide and conquer); here they are located by Sturm counts — same values to
-// n * eps * sigma_max, the small ones to high relative accuracy; (2) singular VECTORS are not built yet (the D&C merges and back-transforms are
-// the next row): the entry point refuses them instead of returning something else.
-// STATUS: driver written after round 1's last GPU session; bidiag.cu is validated, bidiag_sv.cuh is checked on the CPU
-// (the same header compiled for the host), the three small kernels below have not run yet.
+// n * eps * sigma_max, the small ones to high relative accuracy; (2) this file is the VALUES-ONLY path (U and V passed with no
+// columns); with vectors the entry point goes to svd_vectors.cu (divide and conquer + back-transforms).
+// STATUS: validated on hardware (tests/test_gpu_zz7_singular_values.py and the fixture files of tests/test_gpu_zz11_evd_svd_vectors.py);
+// bidiag_sv.cuh is also checked on the CPU (the same header compiled for the host, tests/test_bidiag_sv_cpu.py).
 #include "bidiag_sv.cuh"
 #include "runtime.cuh"
 #include "tensor_ops.cuh"

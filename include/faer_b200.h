@@ -219,9 +219,9 @@ struct FaerV0_24_LltStatus libfaer_v0_23_llt_factor_in_place_f64(struct FaerV0_2
                                                                  struct FaerV0_24_LltParams params);
 
 /* SVD (BASELINE.json configs[4]): lib.rs:2326-2366, faer.h:504 (BidiagParams), 708 (SvdParams), 6230-6268 (svd, svd_scratch);
- * semantics faer/src/linalg/svd/mod.rs:530-648. SINGULAR VALUES ONLY for now: U and V must be passed with ncols == 0 (the
- * reference's "None"); S receives min(nrows, ncols) values in non-increasing order. See csrc/svd.cu for the algorithm and
- * its status (written after round 1's last GPU session). */
+ * semantics faer/src/linalg/svd/mod.rs:530-672. U / V passed with ncols == 0 are the reference's "None" (values only: csrc/svd.cu,
+ * bisection on the bidiagonal); otherwise thin (min(nrows, ncols) columns) or full vectors (csrc/svd_vectors.cu: divide and
+ * conquer + back-transforms). S receives min(nrows, ncols) values in non-increasing order. Non-finite input: NoConvergence. */
 struct FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_f64(void);
 struct FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_f32(void);
 struct FaerV0_24_SvdParams libfaer_v0_23_SvdParams_f64(void);
@@ -232,8 +232,8 @@ struct FaerV0_24_SvdStatus libfaer_v0_23_svd_f64(struct FaerV0_24_MatRef A, stru
 struct FaerV0_24_SvdStatus libfaer_v0_23_svd_f32(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_MatMut V, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SvdParams params);
 
 /* Self-adjoint EVD: lib.rs:2367-2400, faer.h:696, 720, 6064, 6098; semantics faer/src/linalg/evd/mod.rs:270-353 (the LOWER triangle
- * of A is read; eigenvalues in nondecreasing order). EIGENVALUES ONLY for now: U must be passed with ncols == 0; n <= 8192.
- * See csrc/evd.cu for the algorithm and its status (written after round 1's last GPU session). */
+ * of A is read; eigenvalues in nondecreasing order). U passed with ncols == 0: eigenvalues only (csrc/evd.cu); otherwise the
+ * eigenvectors too (csrc/svd_vectors.cu, tridiag_dc.cu). Any n. Non-finite input: NoConvergence. */
 struct FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_f64(void);
 struct FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_f32(void);
 struct FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_f64(void);
@@ -247,7 +247,7 @@ struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_f32(struct FaerV0_24_M
  * semantics: cholesky/llt/reconstruct.rs:12-33 and inverse.rs:10-39 (only the LOWER triangle of the output is written),
  * lu/partial_pivoting/reconstruct.rs and inverse.rs, qr/no_pivoting/reconstruct.rs:13-39 and inverse.rs. L / U may be the packed
  * LU matrix or the split factors (the excluded parts are never read). The LU and QR inverses are the solves applied to the
- * identity. Written after round 1's last GPU session (csrc/reconstruct.cu). */
+ * identity (csrc/reconstruct.cu). */
 struct FaerV0_24_Layout libfaer_v0_23_llt_reconstruct_scratch_f64(size_t dim, struct FaerV0_24_Par par);
 void libfaer_v0_23_llt_reconstruct_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 struct FaerV0_24_Layout libfaer_v0_23_llt_inverse_scratch_f64(size_t dim, struct FaerV0_24_Par par);
@@ -279,7 +279,7 @@ void libfaer_v0_23_llt_solve_in_place_f32(struct FaerV0_24_MatRef L, enum FaerV0
  * LdltRegularization);  params: lib.rs:660;  factor: lib.rs:1190-1217, faer.h:3802, 3830;  solve: lib.rs:1218-1246, faer.h:3974,
  * 4004.  Semantics: faer/src/linalg/cholesky/ldlt/factor.rs:725-767 (D on the diagonal of A, unit-lower L strictly below, strict
  * upper triangle untouched; ZeroPivot { index }), solve.rs:11-49.  dynamic_regularization_signs: i8 slice or null ptr.
- * Written after round 1's last GPU session: see csrc/ldlt_f64.cu for its status. */
+ * Kernels: csrc/ldlt_f64.cu (trailing updates through spicy_matmul_f64). */
 struct FaerV0_24_LdltParams libfaer_v0_23_LdltParams_f64(void);
 struct FaerV0_24_Layout libfaer_v0_23_ldlt_factor_in_place_scratch_f64(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LdltParams params);
 struct FaerV0_24_LdltStatus libfaer_v0_23_ldlt_factor_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_LdltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LdltParams params);
