@@ -1,5 +1,5 @@
 // LDLT without pivoting, f64: leaf kernel + recursive driver + the solve on the factors.
-// STATUS: validated on hardware against the oracle's LDLT (tests/test_gpu_zz6_ldlt.py; the leaf recurrence is also emulated on
+// STATUS: validated on hardware against the CPU checker's LDLT (tests/test_gpu_zz6_ldlt.py; the leaf recurrence is also emulated on
 // the CPU in tests/test_ldlf2_emulation_cpu.py).
 //
 // Reference: faer/src/linalg/cholesky/ldlt/factor.rs
