@@ -249,35 +249,37 @@ def load() -> C.CDLL:
         f = getattr(lib, f"libfaer_v0_23_self_adjoint_evd_{suf}")
         f.argtypes = [MatRef, MatMut, VecMut, P, MemAlloc, SelfAdjointEvdParams]
         f.restype = EvdStatus
-    for name in ("llt_reconstruct", "llt_inverse"):
-        f = getattr(lib, f"libfaer_v0_23_{name}_scratch_f64")
-        f.argtypes = [C.c_size_t, P]
-        f.restype = Layout
-        f = getattr(lib, f"libfaer_v0_23_{name}_f64")
-        f.argtypes = [MatMut, MatRef, P, MemAlloc]
-        f.restype = None
-    for it in ("u32", "u64"):
-        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_reconstruct_scratch_{it}_f64")
-        f.argtypes = [C.c_size_t, C.c_size_t, P]
-        f.restype = Layout
-        f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_inverse_scratch_{it}_f64")
-        f.argtypes = [C.c_size_t, P]
-        f.restype = Layout
-        for name in ("partial_piv_lu_reconstruct", "partial_piv_lu_inverse"):
-            f = getattr(lib, f"libfaer_v0_23_{name}_{it}_f64")
-            f.argtypes = [MatMut, MatRef, MatRef, SliceMut, SliceMut, P, MemAlloc]
+    for suf in ("f64", "f32", "c64", "c32"):
+        for name in ("llt_reconstruct", "llt_inverse"):
+            f = getattr(lib, f"libfaer_v0_23_{name}_scratch_{suf}")
+            f.argtypes = [C.c_size_t, P]
+            f.restype = Layout
+            f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
+            f.argtypes = [MatMut, MatRef, P, MemAlloc]
             f.restype = None
-    for suf in ("f64", "f32"):
+        for it in ("u32", "u64"):
+            f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_reconstruct_scratch_{it}_{suf}")
+            f.argtypes = [C.c_size_t, C.c_size_t, P]
+            f.restype = Layout
+            f = getattr(lib, f"libfaer_v0_23_partial_piv_lu_inverse_scratch_{it}_{suf}")
+            f.argtypes = [C.c_size_t, P]
+            f.restype = Layout
+            for name in ("partial_piv_lu_reconstruct", "partial_piv_lu_inverse"):
+                f = getattr(lib, f"libfaer_v0_23_{name}_{it}_{suf}")
+                f.argtypes = [MatMut, MatRef, MatRef, SliceMut, SliceMut, P, MemAlloc]
+                f.restype = None
         f = getattr(lib, f"libfaer_v0_23_qr_reconstruct_scratch_{suf}")
         f.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, P]
         f.restype = Layout
         f = getattr(lib, f"libfaer_v0_23_qr_reconstruct_{suf}")
         f.argtypes = [MatMut, MatRef, MatRef, MatRef, P, MemAlloc]
         f.restype = None
-    lib.libfaer_v0_23_qr_inverse_scratch_f64.argtypes = [C.c_size_t, C.c_size_t, P]
-    lib.libfaer_v0_23_qr_inverse_scratch_f64.restype = Layout
-    lib.libfaer_v0_23_qr_inverse_f64.argtypes = [MatMut, MatRef, MatRef, MatRef, P, MemAlloc]
-    lib.libfaer_v0_23_qr_inverse_f64.restype = None
+        f = getattr(lib, f"libfaer_v0_23_qr_inverse_scratch_{suf}")
+        f.argtypes = [C.c_size_t, C.c_size_t, P]
+        f.restype = Layout
+        f = getattr(lib, f"libfaer_v0_23_qr_inverse_{suf}")
+        f.argtypes = [MatMut, MatRef, MatRef, MatRef, P, MemAlloc]
+        f.restype = None
     for suf in ("f32", "c64", "c32"):
         getattr(lib, f"libfaer_v0_23_LltParams_{suf}").argtypes = []
         getattr(lib, f"libfaer_v0_23_LltParams_{suf}").restype = LltParams

@@ -438,6 +438,49 @@ void qr_solve_entry_cplx(FaerV0_24_MatRef Qb, FaerV0_24_MatRef Qc, FaerV0_24_Mat
   if (rr) rr->finish();
 }
 
+// ---- reconstruct / inverse on the factors for f32 / c64 / c32 (reconstruct_types.cu; scalar kind <R, CX>) ----
+template <class R, bool CX>
+void llt_recon_entry_t(FaerV0_24_MatMut A, FaerV0_24_MatRef L, bool inverse) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t es = (CX ? 2 : 1) * sizeof(R);
+  // only the lower triangle is written: the rest of A must survive the round trip
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, es, true, true, st);
+  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, es, true, false, st);
+  if (inverse) llt_inverse_t<R, CX>(st, a.view<R>(), l.view<const R>());
+  else llt_reconstruct_t<R, CX>(st, a.view<R>(), l.view<const R>());
+  finish_all(st, {&a, &l});
+}
+template <class R, bool CX>
+void lu_recon_entry_t(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_MatRef U, FaerV0_24_SliceRef perm, int idx_bytes,
+                      bool inverse) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t es = (CX ? 2 : 1) * sizeof(R);
+  const size_t m = L.nrows;
+  std::vector<long long> p = read_perm(perm.ptr, m, idx_bytes);
+  for (size_t i = 0; i < m; ++i) FB_ASSERT(p[i] >= 0 && (size_t)p[i] < m, "invalid permutation entry");
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, es, false, true, st);
+  StagedMat l(L.ptr, (i64)L.nrows, (i64)L.ncols, (i64)L.row_stride, (i64)L.col_stride, es, true, false, st);
+  StagedMat u(U.ptr, (i64)U.nrows, (i64)U.ncols, (i64)U.row_stride, (i64)U.col_stride, es, true, false, st);
+  if (inverse) lu_inverse_t<R, CX>(st, a.view<R>(), l.view<const R>(), u.view<const R>(), p.data());
+  else lu_reconstruct_t<R, CX>(st, a.view<R>(), l.view<const R>(), u.view<const R>(), p.data());
+  finish_all(st, {&a, &l, &u});
+}
+template <class R, bool CX>
+void qr_recon_entry_t(FaerV0_24_MatMut A, FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff, FaerV0_24_MatRef Rm, bool inverse) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t es = (CX ? 2 : 1) * sizeof(R);
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, es, false, true, st);
+  StagedMat b(Q_basis.ptr, (i64)Q_basis.nrows, (i64)Q_basis.ncols, (i64)Q_basis.row_stride, (i64)Q_basis.col_stride, es, true, false, st);
+  StagedMat f(Q_coeff.ptr, (i64)Q_coeff.nrows, (i64)Q_coeff.ncols, (i64)Q_coeff.row_stride, (i64)Q_coeff.col_stride, es, true, false, st);
+  StagedMat r(Rm.ptr, (i64)Rm.nrows, (i64)Rm.ncols, (i64)Rm.row_stride, (i64)Rm.col_stride, es, true, false, st);
+  if (inverse) qr_inverse_t<R, CX>(st, a.view<R>(), b.view<const R>(), f.view<const R>(), r.view<const R>());
+  else qr_reconstruct_t<R, CX>(st, a.view<R>(), b.view<const R>(), f.view<const R>(), r.view<const R>());
+  finish_all(st, {&a, &b, &f, &r});
+}
+
 extern "C" {
 
 void libfaer_v0_23_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
@@ -1445,6 +1488,79 @@ void libfaer_v0_23_qr_inverse_f64(FaerV0_24_MatMut A, FaerV0_24_MatRef Q_basis, 
   qr_inverse_f64(st, a.s.view<double>(), b.s.view<const double>(), f.s.view<const double>(), r.s.view<const double>());
   finish_all(st, {&a.s, &b.s, &f.s, &r.s});
 }
+
+// ---- reconstruct / inverse for f32 / c64 / c32 (scratch sizes: the f64 formulas above with the element size of T) ----
+#define FB_RECON_TYPES_FFI(SUF, R, CX, ES)                                                                                       \
+  FaerV0_24_Layout libfaer_v0_23_llt_reconstruct_scratch_##SUF(size_t dim, FaerV0_24_Par par) {                                 \
+    (void)dim; (void)par;                                                                                                       \
+    return FaerV0_24_Layout{0, 1};                                                                                              \
+  }                                                                                                                             \
+  void libfaer_v0_23_llt_reconstruct_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) { \
+    (void)par; (void)mem;                                                                                                       \
+    llt_recon_entry_t<R, CX>(A, L, false);                                                                                      \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_llt_inverse_scratch_##SUF(size_t dim, FaerV0_24_Par par) {                                     \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{dim * dim * (ES), 64};                                                                              \
+  }                                                                                                                             \
+  void libfaer_v0_23_llt_inverse_##SUF(FaerV0_24_MatMut A_inv, FaerV0_24_MatRef L, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) { \
+    (void)par; (void)mem;                                                                                                       \
+    llt_recon_entry_t<R, CX>(A_inv, L, true);                                                                                   \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_qr_inverse_scratch_##SUF(size_t dim, size_t block_size, FaerV0_24_Par par) {                   \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{block_size * dim * (ES), 64};                                                                       \
+  }                                                                                                                             \
+  void libfaer_v0_23_qr_inverse_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff, FaerV0_24_MatRef R_, \
+                                      FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                                              \
+    (void)par; (void)mem;                                                                                                       \
+    qr_recon_entry_t<R, CX>(A, Q_basis, Q_coeff, R_, true);                                                                     \
+  }
+#define FB_QR_RECON_TYPES_FFI(SUF, R, CX, ES)                                                                                    \
+  FaerV0_24_Layout libfaer_v0_23_qr_reconstruct_scratch_##SUF(size_t nrows, size_t ncols, size_t block_size, FaerV0_24_Par par) { \
+    (void)nrows; (void)par;                                                                                                     \
+    return FaerV0_24_Layout{block_size * ncols * (ES), 64};                                                                     \
+  }                                                                                                                             \
+  void libfaer_v0_23_qr_reconstruct_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatRef Q_basis, FaerV0_24_MatRef Q_coeff,               \
+                                          FaerV0_24_MatRef R_, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                     \
+    (void)par; (void)mem;                                                                                                       \
+    qr_recon_entry_t<R, CX>(A, Q_basis, Q_coeff, R_, false);                                                                    \
+  }
+#define FB_LU_RECON_TYPES_FFI(IT, BYTES, SUF, R, CX, ES)                                                                         \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_reconstruct_scratch_##IT##_##SUF(size_t nrows, size_t ncols, FaerV0_24_Par par) { \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{nrows * ncols * (ES), 64};                                                                          \
+  }                                                                                                                             \
+  void libfaer_v0_23_partial_piv_lu_reconstruct_##IT##_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_MatRef U,        \
+                                                             FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,          \
+                                                             FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                       \
+    (void)perm_fwd; (void)par; (void)mem;                                                                                       \
+    lu_recon_entry_t<R, CX>(A, L, U, perm_bwd, BYTES, false);                                                                   \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_inverse_scratch_##IT##_##SUF(size_t dim, FaerV0_24_Par par) {                   \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{dim * dim * (ES), 64};                                                                              \
+  }                                                                                                                             \
+  void libfaer_v0_23_partial_piv_lu_inverse_##IT##_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_MatRef U,            \
+                                                         FaerV0_24_SliceRef perm_fwd, FaerV0_24_SliceRef perm_bwd,              \
+                                                         FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {                           \
+    (void)perm_bwd; (void)par; (void)mem;                                                                                       \
+    lu_recon_entry_t<R, CX>(A, L, U, perm_fwd, BYTES, true);                                                                    \
+  }
+FB_RECON_TYPES_FFI(f32, float, false, sizeof(float))
+FB_RECON_TYPES_FFI(c64, double, true, 2 * sizeof(double))
+FB_RECON_TYPES_FFI(c32, float, true, 2 * sizeof(float))
+FB_QR_RECON_TYPES_FFI(c64, double, true, 2 * sizeof(double))
+FB_QR_RECON_TYPES_FFI(c32, float, true, 2 * sizeof(float))
+FB_LU_RECON_TYPES_FFI(u32, 4, f32, float, false, sizeof(float))
+FB_LU_RECON_TYPES_FFI(u64, 8, f32, float, false, sizeof(float))
+FB_LU_RECON_TYPES_FFI(u32, 4, c64, double, true, 2 * sizeof(double))
+FB_LU_RECON_TYPES_FFI(u64, 8, c64, double, true, 2 * sizeof(double))
+FB_LU_RECON_TYPES_FFI(u32, 4, c32, float, true, 2 * sizeof(float))
+FB_LU_RECON_TYPES_FFI(u64, 8, c32, float, true, 2 * sizeof(float))
+#undef FB_RECON_TYPES_FFI
+#undef FB_QR_RECON_TYPES_FFI
+#undef FB_LU_RECON_TYPES_FFI
 
 // ---- global par / alloc ----
 FaerV0_24_Par libfaer_v0_23_get_global_par(void) {

@@ -80,4 +80,19 @@ bool tridiag_dc_f64(cudaStream_t st, const double* d, const double* e, i64 n, do
 template <class T>
 void tridiag_in_place(cudaStream_t st, View<T> A, View<T> H);
 
+// ---- reconstruct_types.cu: `*_reconstruct` / `*_inverse` on the factors for the scalar kinds <float, false> (f32),
+// <double, true> (c64), <float, true> (c32); complex views in COMPLEX element units on an R* base; perm arrays HOST int64 ----
+template <class R, bool CX>
+void llt_reconstruct_t(cudaStream_t st, View<R> out, View<const R> L);
+template <class R, bool CX>
+void llt_inverse_t(cudaStream_t st, View<R> out, View<const R> L);
+template <class R, bool CX>
+void lu_reconstruct_t(cudaStream_t st, View<R> out, View<const R> L, View<const R> U, const long long* perm_bwd_host);
+template <class R, bool CX>
+void lu_inverse_t(cudaStream_t st, View<R> out, View<const R> L, View<const R> U, const long long* perm_fwd_host);
+template <class R, bool CX>
+void qr_reconstruct_t(cudaStream_t st, View<R> out, View<const R> Q_basis, View<const R> Q_coeff, View<const R> Rm);
+template <class R, bool CX>
+void qr_inverse_t(cudaStream_t st, View<R> out, View<const R> Q_basis, View<const R> Q_coeff, View<const R> Rm);
+
 }  // namespace fb

@@ -409,28 +409,35 @@ def qr_solve_transpose_in_place(Q_basis, Q_coeff, R, rhs, conj: int = CONJ_NO, p
     _qr_solve("qr_solve_transpose_in_place", Q_basis, Q_coeff, R, rhs, conj, par)
 
 
-# ---- reconstruct / inverse on the factors (f64; qr_reconstruct also f32) --------------------------------
+# ---- reconstruct / inverse on the factors (f64 / f32 / c64 / c32) ---------------------------------------
+def _same_suffix(*xs) -> str:
+    sufs = {_suf_lu(x) for x in xs}
+    if len(sufs) != 1:
+        raise TypeError(f"mixed scalar types: {sorted(sufs)}")
+    return sufs.pop()
+
+
 def llt_reconstruct(out, L, par=None) -> None:
     """cholesky::llt::reconstruct (llt/reconstruct.rs:12-33): the LOWER triangle of out <- L L^H."""
-    _check_f64(out, L)
-    capi.load().libfaer_v0_23_llt_reconstruct_f64(capi.mat_mut(out), capi.mat_ref(L), par or capi.par_default(),
-                                                  capi.MemAlloc(None, 0))
+    suf = _same_suffix(out, L)
+    getattr(capi.load(), f"libfaer_v0_23_llt_reconstruct_{suf}")(capi.mat_mut(out), capi.mat_ref(L), par or capi.par_default(),
+                                                                 capi.MemAlloc(None, 0))
 
 
 def llt_inverse(out, L, par=None) -> None:
     """cholesky::llt::inverse (llt/inverse.rs:10-39): the LOWER triangle of out <- (L L^H)^-1."""
-    _check_f64(out, L)
-    capi.load().libfaer_v0_23_llt_inverse_f64(capi.mat_mut(out), capi.mat_ref(L), par or capi.par_default(),
-                                              capi.MemAlloc(None, 0))
+    suf = _same_suffix(out, L)
+    getattr(capi.load(), f"libfaer_v0_23_llt_inverse_{suf}")(capi.mat_mut(out), capi.mat_ref(L), par or capi.par_default(),
+                                                             capi.MemAlloc(None, 0))
 
 
 def _lu_recon(name, out, L, U, perm, perm_inv, par):
-    _check_f64(out, L, U)
+    suf = _same_suffix(out, L, U)
     isz = perm.element_size() if capi._is_torch(perm) else perm.itemsize
     it = {4: "u32", 8: "u64"}[isz]
-    getattr(capi.load(), f"libfaer_v0_23_{name}_{it}_f64")(capi.mat_mut(out), capi.mat_ref(L), capi.mat_ref(U),
-                                                          capi.slice_mut(perm), capi.slice_mut(perm_inv),
-                                                          par or capi.par_default(), capi.MemAlloc(None, 0))
+    getattr(capi.load(), f"libfaer_v0_23_{name}_{it}_{suf}")(capi.mat_mut(out), capi.mat_ref(L), capi.mat_ref(U),
+                                                            capi.slice_mut(perm), capi.slice_mut(perm_inv),
+                                                            par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def lu_reconstruct(out, L, U, perm, perm_inv, par=None) -> None:
@@ -445,17 +452,17 @@ def lu_inverse(out, L, U, perm, perm_inv, par=None) -> None:
 
 def qr_reconstruct(out, Q_basis, Q_coeff, R, par=None) -> None:
     """qr::no_pivoting::reconstruct (reconstruct.rs:13-39): out <- Q [R; 0]. R: min(m, n) x n (its strict lower part is not
-    read). f64 or f32."""
-    suf = _suf(out)
+    read)."""
+    suf = _same_suffix(out, Q_basis, Q_coeff, R)
     getattr(capi.load(), f"libfaer_v0_23_qr_reconstruct_{suf}")(capi.mat_mut(out), capi.mat_ref(Q_basis), capi.mat_ref(Q_coeff),
                                                                 capi.mat_ref(R), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def qr_inverse(out, Q_basis, Q_coeff, R, par=None) -> None:
-    """qr::no_pivoting::inverse: out <- A^-1 = R^-1 Q^H (square, f64)."""
-    _check_f64(out, Q_basis, Q_coeff, R)
-    capi.load().libfaer_v0_23_qr_inverse_f64(capi.mat_mut(out), capi.mat_ref(Q_basis), capi.mat_ref(Q_coeff), capi.mat_ref(R),
-                                             par or capi.par_default(), capi.MemAlloc(None, 0))
+    """qr::no_pivoting::inverse: out <- A^-1 = R^-1 Q^H (square)."""
+    suf = _same_suffix(out, Q_basis, Q_coeff, R)
+    getattr(capi.load(), f"libfaer_v0_23_qr_inverse_{suf}")(capi.mat_mut(out), capi.mat_ref(Q_basis), capi.mat_ref(Q_coeff),
+                                                            capi.mat_ref(R), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def singular_values(A, par=None, params=None):

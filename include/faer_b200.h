@@ -266,6 +266,54 @@ void libfaer_v0_23_qr_reconstruct_f64(struct FaerV0_24_MatMut A, struct FaerV0_2
 void libfaer_v0_23_qr_reconstruct_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 struct FaerV0_24_Layout libfaer_v0_23_qr_inverse_scratch_f64(size_t dim, size_t block_size, struct FaerV0_24_Par par);
 void libfaer_v0_23_qr_inverse_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+/* the same entry points for f32 / c64 / c32 (faer-ffi stamps them for every dtype, lib.rs:313-369; csrc/reconstruct_types.cu:
+ * the compositions above on the products, solves and Householder sequences of each scalar kind) */
+struct FaerV0_24_Layout libfaer_v0_23_llt_reconstruct_scratch_f32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_reconstruct_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_llt_inverse_scratch_f32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_inverse_f32(struct FaerV0_24_MatMut A_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_reconstruct_scratch_u32_f32(size_t nrows, size_t ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_reconstruct_u32_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_inverse_scratch_u32_f32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_inverse_u32_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_reconstruct_scratch_u64_f32(size_t nrows, size_t ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_reconstruct_u64_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_inverse_scratch_u64_f32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_inverse_u64_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_qr_inverse_scratch_f32(size_t dim, size_t block_size, struct FaerV0_24_Par par);
+void libfaer_v0_23_qr_inverse_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_llt_reconstruct_scratch_c64(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_reconstruct_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_llt_inverse_scratch_c64(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_inverse_c64(struct FaerV0_24_MatMut A_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_reconstruct_scratch_u32_c64(size_t nrows, size_t ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_reconstruct_u32_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_inverse_scratch_u32_c64(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_inverse_u32_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_reconstruct_scratch_u64_c64(size_t nrows, size_t ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_reconstruct_u64_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_inverse_scratch_u64_c64(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_inverse_u64_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_qr_reconstruct_scratch_c64(size_t nrows, size_t ncols, size_t block_size, struct FaerV0_24_Par par);
+void libfaer_v0_23_qr_reconstruct_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_qr_inverse_scratch_c64(size_t dim, size_t block_size, struct FaerV0_24_Par par);
+void libfaer_v0_23_qr_inverse_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_llt_reconstruct_scratch_c32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_reconstruct_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_llt_inverse_scratch_c32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_llt_inverse_c32(struct FaerV0_24_MatMut A_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_reconstruct_scratch_u32_c32(size_t nrows, size_t ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_reconstruct_u32_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_inverse_scratch_u32_c32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_inverse_u32_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_reconstruct_scratch_u64_c32(size_t nrows, size_t ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_reconstruct_u64_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_partial_piv_lu_inverse_scratch_u64_c32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_partial_piv_lu_inverse_u64_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_MatRef U, struct FaerV0_24_SliceRef perm_fwd, struct FaerV0_24_SliceRef perm_bwd, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_qr_reconstruct_scratch_c32(size_t nrows, size_t ncols, size_t block_size, struct FaerV0_24_Par par);
+void libfaer_v0_23_qr_reconstruct_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_qr_inverse_scratch_c32(size_t dim, size_t block_size, struct FaerV0_24_Par par);
+void libfaer_v0_23_qr_inverse_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef Q_basis, struct FaerV0_24_MatRef Q_coeff, struct FaerV0_24_MatRef R, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
 /* f32 LLT: faer.h:636 (LltParams_f32), 4036-4048 (factor), 4180-4216 (solve); same semantics as the f64 entry points.
  * The templated leaf kernel and recursive driver of csrc/llt.cu instantiated for float. */

@@ -96,6 +96,23 @@ def test_qr_solve_scratch_queries(fb):
             assert lay.len_bytes == 16 * 5 * sz
 
 
+def test_reconstruct_inverse_scratch_queries_every_dtype(fb):
+    """`*_reconstruct_scratch` / `*_inverse_scratch` for f64 / f32 / c64 / c32: the reference's formulas with the element size
+    of T (llt/reconstruct.rs:3-6 EMPTY, llt/inverse.rs:3-8 temp_mat(dim, dim), lu/partial_pivoting/reconstruct.rs
+    temp_mat(nrows, ncols), inverse.rs:3-10 temp_mat(dim, dim), qr/no_pivoting/reconstruct.rs:3-12 and inverse.rs:3-10: the
+    block-Householder sequence scratch temp_mat(block_size, ncols))."""
+    lib = fb.load()
+    par = fb.capi.par_default()
+    for suf, sz in (("f64", 8), ("f32", 4), ("c64", 16), ("c32", 8)):
+        assert getattr(lib, f"libfaer_v0_23_llt_reconstruct_scratch_{suf}")(100, par).len_bytes == 0
+        assert getattr(lib, f"libfaer_v0_23_llt_inverse_scratch_{suf}")(100, par).len_bytes == 100 * 100 * sz
+        for it in ("u32", "u64"):
+            assert getattr(lib, f"libfaer_v0_23_partial_piv_lu_reconstruct_scratch_{it}_{suf}")(30, 70, par).len_bytes == 30 * 70 * sz
+            assert getattr(lib, f"libfaer_v0_23_partial_piv_lu_inverse_scratch_{it}_{suf}")(50, par).len_bytes == 50 * 50 * sz
+        assert getattr(lib, f"libfaer_v0_23_qr_reconstruct_scratch_{suf}")(300, 120, 32, par).len_bytes == 32 * 120 * sz
+        assert getattr(lib, f"libfaer_v0_23_qr_inverse_scratch_{suf}")(90, 16, par).len_bytes == 16 * 90 * sz
+
+
 def test_state_touching_entry_points_are_serialised(fb):
     """The entry points that touch per-process state take the library's entry lock (runtime.cuh: FB_ENTRY); hammer the
     ones that need no GPU from several threads (ctypes drops the GIL during the calls)."""
