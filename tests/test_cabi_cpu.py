@@ -96,6 +96,24 @@ def test_qr_solve_scratch_queries(fb):
             assert lay.len_bytes == 16 * 5 * sz
 
 
+def test_prototypes_match_the_reference_header():
+    """Every `libfaer_v0_23_*` prototype of include/faer_b200.h has the return type and parameter types that the reference's
+    shipped header declares for the same symbol (tests/golden/faer_ffi_prototypes.json, extracted from faer-ffi/faer.h by
+    tests/golden/make_ffi_prototypes.py with the same parser), and nothing is declared that the reference does not have."""
+    import importlib.util
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "faer_ffi_prototypes.json")))
+    spec = importlib.util.spec_from_file_location("make_ffi_prototypes", os.path.join(ROOT, "tests", "golden", "make_ffi_prototypes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ours = mod.prototypes(open(os.path.join(ROOT, "include", "faer_b200.h")).read())
+    assert len(ours) >= 250
+    for name, proto in ours.items():
+        assert name in gold["prototypes"], f"{name} is not a faer-ffi symbol"
+        assert gold["prototypes"][name] == proto, (name, gold["prototypes"][name], proto)
+    assert set(ours) <= set(gold["reference_symbols_f32_f64_c32_c64"])
+
+
 def test_reconstruct_inverse_scratch_queries_every_dtype(fb):
     """`*_reconstruct_scratch` / `*_inverse_scratch` for f64 / f32 / c64 / c32: the reference's formulas with the element size
     of T (llt/reconstruct.rs:3-6 EMPTY, llt/inverse.rs:3-8 temp_mat(dim, dim), lu/partial_pivoting/reconstruct.rs
