@@ -228,7 +228,7 @@ def load() -> C.CDLL:
             f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
             f.argtypes = [MatRef, MatRef, MatRef, C.c_int, MatMut, P, MemAlloc]
             f.restype = None
-    for suf in ("f64", "f32"):
+    for suf in ("f64", "f32", "c64", "c32"):
         getattr(lib, f"libfaer_v0_23_BidiagParams_{suf}").argtypes = []
         getattr(lib, f"libfaer_v0_23_BidiagParams_{suf}").restype = BidiagParams
         getattr(lib, f"libfaer_v0_23_SvdParams_{suf}").argtypes = []

@@ -1,0 +1,215 @@
+// `svd` and `self_adjoint_evd` for complex T (c64; c32 is computed in c64 like the f32 entry points are computed in f64).
+//
+// Reference:
+//   svd::svd / svd_imp      faer/src/linalg/svd/mod.rs:530-672, 326-431   (wide inputs through the adjoint, bidiagonalize, phase
+//                                                                          normalisation 171-273, real bidiagonal SVD, back-transforms
+//                                                                          403-429: left sequence Conj::No, right sequence Conj::Yes on
+//                                                                          the transposed rows)
+//   evd::self_adjoint_evd   evd/mod.rs:270-418                             (tridiagonalize, real tridiagonal EVD of the phase-normalised
+//                                                                          form, back-transform 411-418)
+// Arrangement: the reductions to condensed form are the unblocked launch sequences of cplx_condensed_core.cuh (flat maps, one thread
+// per row / element; the same source runs thread by thread on the host in tests/test_cplx_condensed_emul_cpu.py). The condensed
+// REAL problems go to the solvers the real entry points use (tridiag_dc.cu; the Golub-Kahan / QR-stabilised bidiagonal solver of
+// svd_vectors.cu), the back-transforms to the complex block-Householder sequence of cplx.cu with block size 1 (the taus are the
+// 1 x 1 T blocks). Functional, not tuned: O(n) launches per column and n-thread matrix-vector products — meant for the moderate
+// sizes complex users of the C ABI bring, not for the BASELINE sizes of the real path.
+// The values-only calls (U / V not wanted) run the same path and skip the back-transforms.
+#include <algorithm>
+
+#include "cplx_condensed_core.cuh"
+#include "runtime.cuh"
+#include "tensor_ops.cuh"
+
+namespace fb {
+
+namespace {
+
+template <class B>
+__global__ void __launch_bounds__(256) cc_map_kernel(B body, cc::i64 y0) {
+  body((cc::i64)blockIdx.x * blockDim.x + threadIdx.x, y0 + (cc::i64)blockIdx.y);
+}
+
+// the launcher of cplx_condensed_core.cuh on a stream: body(i, j) for i < nx (rounded up to whole blocks), j < ny
+struct DevRun {
+  cudaStream_t st;
+  template <class B>
+  void operator()(const B& body, i64 nx, i64 ny) const {
+    if (nx <= 0 || ny <= 0) return;
+    for (i64 y0 = 0; y0 < ny; y0 += 65535) {
+      const unsigned nc = (unsigned)std::min<i64>(65535, ny - y0);
+      cc_map_kernel<B><<<dim3((unsigned)((nx + 255) / 256), nc), 256, 0, st>>>(body, y0);
+      FB_CUDA_CHECK(cudaGetLastError());
+      note_launch();
+    }
+  }
+};
+
+struct DevWork {
+  cc::Work ws;
+  void* blocks[5];
+  explicit DevWork(i64 len) {
+    ws.v = (cc::Cx*)(blocks[0] = ws_alloc((size_t)(len + 1) * sizeof(cc::Cx)));
+    ws.p = (cc::Cx*)(blocks[1] = ws_alloc((size_t)(len + 1) * sizeof(cc::Cx)));
+    ws.w = (cc::Cx*)(blocks[2] = ws_alloc((size_t)(len + 1) * sizeof(cc::Cx)));
+    ws.part = (double*)(blocks[3] = ws_alloc((size_t)3 * cc::NP * sizeof(double)));
+    ws.sc = (double*)(blocks[4] = ws_alloc((size_t)cc::SC_COUNT * sizeof(double)));
+  }
+  void release() {
+    for (void* b : blocks) ws_free(b);
+  }
+};
+
+// c64 view of the input: the view itself (TO = double) or a compact widened copy (TO = float; *owned receives the block)
+inline View<const double> as_c64(cudaStream_t st, View<const double> A, void** owned) {
+  (void)st;
+  *owned = nullptr;
+  return A;
+}
+inline View<const double> as_c64(cudaStream_t st, View<const float> A, void** owned) {
+  const i64 m = A.nrows, n = A.ncols;
+  cc::Cx* W = (cc::Cx*)ws_alloc((size_t)std::max<i64>(1, m * n) * sizeof(cc::Cx));
+  DevRun run{st};
+  run(cc::WidenC32{A.ptr, A.rs, A.cs, W, m, m, n}, m, n);
+  *owned = W;
+  return View<const double>{(const double*)W, m, n, 1, m};
+}
+
+}  // namespace
+
+template <class TO>
+bool self_adjoint_evd_cx(cudaStream_t st, View<const TO> A_in, View<TO> U, TO* S, i64 sstride) {
+  const i64 n = A_in.nrows;
+  FB_ASSERT(A_in.ncols == n, "self_adjoint_evd: square matrix required");
+  if (n == 0) return true;
+  const bool want_u = U.ptr != nullptr && U.ncols > 0;
+  DevRun run{st};
+  void* owned = nullptr;
+  const View<const double> A = as_c64(st, A_in, &owned);
+  cc::Cx* W = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
+  run(cc::BuildHermitian{A.ptr, A.rs, A.cs, W, n, n}, n, n);
+  DevWork work(n);
+  // tau | d | e | lam (n doubles each), then ph | tauc (n complex each)
+  double* reals = (double*)ws_alloc((size_t)(4 * n + 4) * sizeof(double));
+  double *tau = reals, *d = reals + n, *e = reals + 2 * n, *lam = reals + 3 * n;
+  cc::Cx* cplx = (cc::Cx*)ws_alloc((size_t)(2 * n + 2) * sizeof(cc::Cx));
+  cc::Cx *ph = cplx, *tauc = cplx + n;
+  FB_CUDA_CHECK(cudaMemsetAsync(reals, 0, (size_t)(4 * n + 4) * sizeof(double), st));
+  cc::tridiag_unblocked(run, W, n, n, tau, work.ws);
+  run(cc::TridiagPhases{W, n, n, tau, d, e, ph, tauc}, 1, 1);
+  bool ok = device_all_finite<double>(st, d, n) && (n < 2 || device_all_finite<double>(st, e, n - 1));
+  double* Q = nullptr;
+  if (ok) {
+    Q = (double*)ws_alloc((size_t)n * (size_t)n * sizeof(double));
+    ok = tridiag_dc_f64(st, d, e, n, lam, Q, n);
+  }
+  if (ok) {
+    if (want_u) {
+      FB_ASSERT(U.nrows == n && U.ncols == n, "self_adjoint_evd: U must be n x n");
+      cc::Cx* Uw = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
+      run(cc::ScaleRowsEmbed{Q, n, n, ph, Uw, n, n, n}, n, n);  // diag(ph) Q
+      if (n > 1)  // rows 1.. <- H_0 H_1 ... H_{n-2} rows 1.. (evd/mod.rs:411-418); reflector k: column k of W below the subdiagonal
+        apply_householder_sequence_left_c64(st, VCD{(const double*)(W + 1), n - 1, n - 1, 1, n}, VCD{(const double*)tauc, 1, n - 1, 1, 1},
+                                            false, VD{(double*)(Uw + 1), n - 1, n, 1, n}, false);
+      run(cc::CopyOut<TO>{U.ptr, U.rs, U.cs, Uw, n, n, n}, n, n);
+      FB_CUDA_CHECK(cudaStreamSynchronize(st));
+      ws_free(Uw);
+    }
+    run(cc::CopyValues<TO>{S, sstride, lam, n}, n, 1);
+  }
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (Q) ws_free(Q);
+  ws_free(cplx);
+  ws_free(reals);
+  work.release();
+  ws_free(W);
+  if (owned) ws_free(owned);
+  return ok;
+}
+
+template <class TO>
+bool svd_cx(cudaStream_t st, View<const TO> A_in, View<TO> U, TO* S, i64 sstride, View<TO> V) {
+  const bool transpose = A_in.ncols > A_in.nrows;
+  const i64 m = transpose ? A_in.ncols : A_in.nrows, n = transpose ? A_in.nrows : A_in.ncols;  // the work matrix M (= A or A^H) is m x n
+  // A = U S V^H; for a wide A: A^H = U' S V'^H, so U = V' and V = U' (svd/mod.rs:560-583, 661-669)
+  View<TO> Um = transpose ? V : U, Vm = transpose ? U : V;
+  const bool want_u = Um.ptr != nullptr && Um.ncols > 0, want_v = Vm.ptr != nullptr && Vm.ncols > 0;
+  DevRun run{st};
+  if (n == 0) {
+    if (want_u) {  // no singular values: the full left factor is the identity
+      const i64 ku = Um.ncols;
+      cc::Cx* Uw = (cc::Cx*)ws_alloc((size_t)std::max<i64>(1, m * ku) * sizeof(cc::Cx));
+      run(cc::ScaleRowsEmbed{nullptr, 1, 0, nullptr, Uw, m, m, ku}, m, ku);
+      run(cc::CopyOut<TO>{Um.ptr, Um.rs, Um.cs, Uw, m, m, ku}, m, ku);
+      FB_CUDA_CHECK(cudaStreamSynchronize(st));
+      ws_free(Uw);
+    }
+    return true;
+  }
+  void* owned = nullptr;
+  const View<const double> A = as_c64(st, A_in, &owned);
+  cc::Cx* W = (cc::Cx*)ws_alloc((size_t)m * (size_t)n * sizeof(cc::Cx));
+  run(cc::CopyIn{A.ptr, A.rs, A.cs, W, m, m, n, transpose ? 1 : 0}, m, n);
+  DevWork work(m);
+  // tl | tr | d | f | s_sorted (n doubles each), then l | r | tlc | trc (n complex each)
+  double* reals = (double*)ws_alloc((size_t)(5 * n + 4) * sizeof(double));
+  double *tl = reals, *tr = reals + n, *d = reals + 2 * n, *f = reals + 3 * n, *s_sorted = reals + 4 * n;
+  cc::Cx* cplx = (cc::Cx*)ws_alloc((size_t)(4 * n + 4) * sizeof(cc::Cx));
+  cc::Cx *l = cplx, *r = cplx + n, *tlc = cplx + 2 * n, *trc = cplx + 3 * n;
+  FB_CUDA_CHECK(cudaMemsetAsync(reals, 0, (size_t)(5 * n + 4) * sizeof(double), st));
+  cc::bidiag_unblocked(run, W, m, m, n, tl, tr, work.ws);
+  run(cc::BidiagPhases{W, m, n, tl, tr, d, f, l, r, tlc, trc}, 1, 1);
+  bool ok = device_all_finite<double>(st, d, n) && (n < 2 || device_all_finite<double>(st, f, n - 1));
+  double *UB = nullptr, *VB = nullptr;
+  if (ok) {
+    UB = (double*)ws_alloc((size_t)n * (size_t)n * sizeof(double));
+    VB = (double*)ws_alloc((size_t)n * (size_t)n * sizeof(double));
+    ok = bidiag_svd_vectors_f64(st, d, f, n, s_sorted, UB, VB);  // B_real = UB diag(S) VB^T
+  }
+  if (ok && want_u) {
+    const i64 ku = Um.ncols;  // n (thin) or m (full)
+    FB_ASSERT(Um.nrows == m && (ku == n || ku == m), "svd: the left factor must be nrows x {size, nrows}");
+    cc::Cx* Uw = (cc::Cx*)ws_alloc((size_t)m * (size_t)ku * sizeof(cc::Cx));
+    run(cc::ScaleRowsEmbed{UB, n, n, l, Uw, m, m, ku}, m, ku);  // [diag(l) UB, 0; 0, I]
+    // U = H_0 ... H_{n-1} [.]: left reflector k is column k of W below the diagonal (svd/mod.rs:403-412, Conj::No)
+    apply_householder_sequence_left_c64(st, VCD{(const double*)W, m, n, 1, m}, VCD{(const double*)tlc, 1, n, 1, 1}, false,
+                                        VD{(double*)Uw, m, ku, 1, m}, false);
+    run(cc::CopyOut<TO>{Um.ptr, Um.rs, Um.cs, Uw, m, m, ku}, m, ku);
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    ws_free(Uw);
+  }
+  if (ok && want_v) {
+    FB_ASSERT(Vm.nrows == n && Vm.ncols == n, "svd: the right factor must be ncols x ncols");
+    cc::Cx* Vw = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
+    run(cc::ScaleRowsEmbed{VB, n, n, r, Vw, n, n, n}, n, n);  // diag(r) VB
+    cc::Cx* T = nullptr;
+    if (n > 1) {
+      // the right reflectors are the rows of W right of the superdiagonal: transposed copy, sequence with Conj::Yes on rows 1..
+      // (svd/mod.rs:413-428)
+      T = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
+      run(cc::TransposeCorner{W, m, T, n, n}, n, n);
+      apply_householder_sequence_left_c64(st, VCD{(const double*)(T + 1), n - 1, n - 1, 1, n}, VCD{(const double*)trc, 1, n - 1, 1, 1}, true,
+                                          VD{(double*)(Vw + 1), n - 1, n, 1, n}, false);
+    }
+    run(cc::CopyOut<TO>{Vm.ptr, Vm.rs, Vm.cs, Vw, n, n, n}, n, n);
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (T) ws_free(T);
+    ws_free(Vw);
+  }
+  if (ok) run(cc::CopyValues<TO>{S, sstride, s_sorted, n}, n, 1);
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (VB) ws_free(VB);
+  if (UB) ws_free(UB);
+  ws_free(cplx);
+  ws_free(reals);
+  work.release();
+  ws_free(W);
+  if (owned) ws_free(owned);
+  return ok;
+}
+
+template bool svd_cx<double>(cudaStream_t, View<const double>, View<double>, double*, i64, View<double>);
+template bool svd_cx<float>(cudaStream_t, View<const float>, View<float>, float*, i64, View<float>);
+template bool self_adjoint_evd_cx<double>(cudaStream_t, View<const double>, View<double>, double*, i64);
+template bool self_adjoint_evd_cx<float>(cudaStream_t, View<const float>, View<float>, float*, i64);
+
+}  // namespace fb

@@ -481,6 +481,70 @@ void qr_recon_entry_t(FaerV0_24_MatMut A, FaerV0_24_MatRef Q_basis, FaerV0_24_Ma
   finish_all(st, {&a, &b, &f, &r});
 }
 
+// ---- `svd` / `self_adjoint_evd` for complex T (cplx_condensed.cu); S holds T-typed entries (value, 0), strides in complex units ----
+template <class R>
+FaerV0_24_EvdStatus self_adjoint_evd_entry_cplx(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t n = A.nrows, es = 2 * sizeof(R);
+  FB_ASSERT(A.ncols == n && S.len == n && (n == 0 || S.stride >= 1), "self_adjoint_evd: square A, S of length n, positive stride");
+  const bool want_u = U.ncols != 0;
+  if (want_u) FB_ASSERT(U.nrows == n && U.ncols == n, "self_adjoint_evd: U must be n x n (or have no columns)");
+  FaerV0_24_EvdStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_EvdStatus_Ok;
+  if (n == 0) return out;
+  StagedMat a(A.ptr, (i64)n, (i64)n, (i64)A.row_stride, (i64)A.col_stride, es, true, false, st);
+  R* s_dev = (R*)ws_alloc(n * es);
+  bool ok;
+  if (want_u) {
+    StagedMat u(U.ptr, (i64)n, (i64)n, (i64)U.row_stride, (i64)U.col_stride, es, false, true, st);
+    ok = self_adjoint_evd_cx<R>(st, a.view<const R>(), u.view<R>(), s_dev, 1);
+    if (ok) FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * es, s_dev, es, es, n, cudaMemcpyDefault, st));
+    finish_all(st, {&a, &u});
+  } else {
+    ok = self_adjoint_evd_cx<R>(st, a.view<const R>(), View<R>{nullptr, 0, 0, 1, 1}, s_dev, 1);
+    if (ok) FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * es, s_dev, es, es, n, cudaMemcpyDefault, st));
+    finish_all(st, {&a});
+  }
+  ws_free(s_dev);
+  if (!ok) out.tag = FaerV0_24_EvdStatus_NoConvergence;
+  return out;
+}
+template <class R>
+FaerV0_24_SvdStatus svd_entry_cplx(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t size = A.nrows < A.ncols ? A.nrows : A.ncols, es = 2 * sizeof(R);
+  FB_ASSERT(S.len == size && (size == 0 || S.stride >= 1), "svd: S must have min(nrows, ncols) entries and a positive stride");
+  const bool want_u = U.ncols != 0, want_v = V.ncols != 0;
+  if (want_u) FB_ASSERT(U.nrows == A.nrows && (U.ncols == A.nrows || U.ncols == size), "svd: U must be nrows x {size, nrows}");
+  if (want_v) FB_ASSERT(V.nrows == A.ncols && (V.ncols == A.ncols || V.ncols == size), "svd: V must be ncols x {size, ncols}");
+  FaerV0_24_SvdStatus out;
+  memset(&out, 0, sizeof(out));
+  out.tag = FaerV0_24_SvdStatus_Ok;
+  if (size == 0 && !want_u && !want_v) return out;
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, es, true, false, st);
+  R* s_dev = (R*)ws_alloc((size + 1) * es);
+  bool ok;
+  if (want_u || want_v) {
+    StagedMat u(U.ptr, (i64)U.nrows, (i64)U.ncols, (i64)U.row_stride, (i64)U.col_stride, es, false, true, st);
+    StagedMat v(V.ptr, (i64)V.nrows, (i64)V.ncols, (i64)V.row_stride, (i64)V.col_stride, es, false, true, st);
+    View<R> uv = want_u ? u.view<R>() : View<R>{nullptr, 0, 0, 1, 1};
+    View<R> vv = want_v ? v.view<R>() : View<R>{nullptr, 0, 0, 1, 1};
+    ok = svd_cx<R>(st, a.view<const R>(), uv, s_dev, 1, vv);
+    if (ok && size) FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * es, s_dev, es, es, size, cudaMemcpyDefault, st));
+    finish_all(st, {&a, &u, &v});
+  } else {
+    ok = svd_cx<R>(st, a.view<const R>(), View<R>{nullptr, 0, 0, 1, 1}, s_dev, 1, View<R>{nullptr, 0, 0, 1, 1});
+    if (ok && size) FB_CUDA_CHECK(cudaMemcpy2DAsync(S.ptr, (size_t)S.stride * es, s_dev, es, es, size, cudaMemcpyDefault, st));
+    finish_all(st, {&a});
+  }
+  ws_free(s_dev);
+  if (!ok) out.tag = FaerV0_24_SvdStatus_NoConvergence;
+  return out;
+}
+
 extern "C" {
 
 void libfaer_v0_23_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
@@ -1389,6 +1453,42 @@ FB_SVD_FFI(f32, float)
 FB_EVD_FFI(f64, double)
 FB_EVD_FFI(f32, float)
 #undef FB_EVD_FFI
+
+// ---- complex `svd` / `self_adjoint_evd` (cplx_condensed.cu: c32 computes in c64) ----
+#define FB_SVD_EVD_CPLX_FFI(SUF, R)                                                                                             \
+  FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_##SUF(void) { return FaerV0_24_BidiagParams{192 * 256}; }                  \
+  FaerV0_24_SvdParams libfaer_v0_23_SvdParams_##SUF(void) {                                                                    \
+    return FaerV0_24_SvdParams{FaerV0_24_BidiagParams{192 * 256}, FaerV0_24_QrParams{48 * 48, 192 * 256}, 128, 11.0 / 6.0};    \
+  }                                                                                                                            \
+  FaerV0_24_Layout libfaer_v0_23_svd_scratch_##SUF(size_t nrows, size_t ncols, FaerV0_24_ComputeSvdVectors compute_U,          \
+                                                   FaerV0_24_ComputeSvdVectors compute_V, FaerV0_24_Par par,                   \
+                                                   FaerV0_24_SvdParams params) {                                               \
+    (void)compute_U; (void)compute_V; (void)par; (void)params;                                                                 \
+    return FaerV0_24_Layout{nrows * ncols * 2 * sizeof(R), 64}; /* the copy of A (kept in the device pool here) */             \
+  }                                                                                                                            \
+  FaerV0_24_SvdStatus libfaer_v0_23_svd_##SUF(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S, FaerV0_24_MatMut V,  \
+                                              FaerV0_24_Par par, FaerV0_24_MemAlloc mem, FaerV0_24_SvdParams params) {         \
+    (void)par; (void)mem; (void)params;                                                                                        \
+    return svd_entry_cplx<R>(A, U, S, V);                                                                                      \
+  }                                                                                                                            \
+  FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_##SUF(void) { return FaerV0_24_TridiagParams{192 * 256}; }               \
+  FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_##SUF(void) {                                              \
+    return FaerV0_24_SelfAdjointEvdParams{FaerV0_24_TridiagParams{192 * 256}, 128};                                            \
+  }                                                                                                                            \
+  FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_##SUF(size_t dim, FaerV0_24_ComputeEigenvectors compute_U,           \
+                                                                FaerV0_24_Par par, FaerV0_24_SelfAdjointEvdParams params) {    \
+    (void)compute_U; (void)par; (void)params;                                                                                  \
+    return FaerV0_24_Layout{dim * dim * 2 * sizeof(R), 64};                                                                    \
+  }                                                                                                                            \
+  FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_##SUF(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV0_24_VecMut S,         \
+                                                           FaerV0_24_Par par, FaerV0_24_MemAlloc mem,                          \
+                                                           FaerV0_24_SelfAdjointEvdParams params) {                            \
+    (void)par; (void)mem; (void)params;                                                                                        \
+    return self_adjoint_evd_entry_cplx<R>(A, U, S);                                                                            \
+  }
+FB_SVD_EVD_CPLX_FFI(c64, double)
+FB_SVD_EVD_CPLX_FFI(c32, float)
+#undef FB_SVD_EVD_CPLX_FFI
 
 // ---- reconstruct / inverse on the factors (reconstruct.cu; f64, qr_reconstruct also f32) ----
 FaerV0_24_Layout libfaer_v0_23_llt_reconstruct_scratch_f64(size_t dim, FaerV0_24_Par par) {

@@ -233,6 +233,11 @@ bool bidiag_svd_vectors(cudaStream_t st, const double* d, const double* e, i64 n
 
 }  // namespace
 
+// the real bidiagonal solver for the complex driver (cplx_condensed.cu)
+bool bidiag_svd_vectors_f64(cudaStream_t st, const double* d, const double* e, i64 n, double* S_sorted, double* UB, double* VB) {
+  return bidiag_svd_vectors(st, d, e, n, S_sorted, UB, VB);
+}
+
 // Full driver. A: device view (any strides) of element type TA (float / double); U, V: device views or ncols == 0 / ptr == null
 // ("do not compute"); U is nrows x {size, nrows}, V is ncols x {size, ncols}; S: device, `sstride` elements apart.
 // Returns false on non-finite input (SvdError::NoConvergence, svd/mod.rs:282-286).

@@ -73,6 +73,16 @@ template <class TA>
 bool self_adjoint_evd_with_vectors(cudaStream_t st, View<const TA> A, View<TA> U, TA* S, i64 sstride);
 template <class T>
 bool device_all_finite(cudaStream_t st, const T* x, i64 n);
+// SVD of the real upper-bidiagonal (d, e) of order n (device arrays; e has n entries, the last one unused): S_sorted
+// non-increasing, UB / VB n x n column-major (ld n) with B = UB diag(S) VB^T. False on non-finite input.
+bool bidiag_svd_vectors_f64(cudaStream_t st, const double* d, const double* e, i64 n, double* S_sorted, double* UB, double* VB);
+// ---- cplx_condensed.cu: `svd` / `self_adjoint_evd` for complex T (TO = double: c64, float: c32 computed in c64); views in
+// COMPLEX element units on a TO* base; U / V with ptr == nullptr or ncols == 0: not computed; S: (value, 0) pairs `sstride`
+// complex elements apart (device). False on non-finite input. ----
+template <class TO>
+bool svd_cx(cudaStream_t st, View<const TO> A, View<TO> U, TO* S, i64 sstride, View<TO> V);
+template <class TO>
+bool self_adjoint_evd_cx(cudaStream_t st, View<const TO> A, View<TO> U, TO* S, i64 sstride);
 // ---- tridiag_dc.cu: divide-and-conquer eigensolver of a symmetric tridiagonal matrix (device arrays) ----
 bool tridiag_dc_f64(cudaStream_t st, const double* d, const double* e, i64 n, double* lam, double* Q, i64 ldq);
 // ---- tridiag.cu ----

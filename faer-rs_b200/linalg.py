@@ -465,12 +465,19 @@ def qr_inverse(out, Q_basis, Q_coeff, R, par=None) -> None:
                                                             capi.mat_ref(R), par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
+def _real_values(S):
+    """The ABI's S is T-typed: for complex T the values come back as (value, 0) pairs; the mirror returns them real."""
+    if capi._is_torch(S):
+        return S.real.contiguous() if S.is_complex() else S
+    return np.ascontiguousarray(S.real) if np.iscomplexobj(S) else S
+
+
 def singular_values(A, par=None, params=None):
     """`svd` with u = v = None (svd/mod.rs:530-648), as `MatRef::singular_values` (solvers.rs:457-487): the
     min(nrows, ncols) singular values of A in non-increasing order, as a numpy vector (host input) or a CUDA tensor (device
-    input). f64 or f32."""
+    input). f64 / f32 / c64 / c32 (real values for complex A)."""
     lib = capi.load()
-    suf = _suf(A)
+    suf = _suf_lu(A)
     m, n = A.shape
     size = min(m, n)
     if capi._is_torch(A):
@@ -486,15 +493,15 @@ def singular_values(A, par=None, params=None):
                                                   capi.MemAlloc(None, 0), params)
     if st.tag != 0:
         raise RuntimeError("SvdError::NoConvergence")
-    return S
+    return _real_values(S)
 
 
 def self_adjoint_eigenvalues(A, par=None, params=None):
     """`self_adjoint_evd` with u = None (evd/mod.rs:270-353), as `MatRef::self_adjoint_eigenvalues(Side::Lower)`
     (solvers.rs:417-456): the eigenvalues of the self-adjoint matrix whose LOWER triangle is in A, nondecreasing, as a numpy
-    vector (host input) or a CUDA tensor (device input). f64 or f32, n <= 8192."""
+    vector (host input) or a CUDA tensor (device input). f64 / f32 / c64 / c32 (real values for complex A)."""
     lib = capi.load()
-    suf = _suf(A)
+    suf = _suf_lu(A)
     n = A.shape[0]
     assert A.shape[1] == n
     if capi._is_torch(A):
@@ -509,7 +516,7 @@ def self_adjoint_eigenvalues(A, par=None, params=None):
                                                                par or capi.par_default(), capi.MemAlloc(None, 0), params)
     if st.tag != 0:
         raise RuntimeError("EvdError::NoConvergence")
-    return S
+    return _real_values(S)
 
 
 def spicy_matmul(C, C_block: int, row_idx, col_idx, accum: int, A, B, D, alpha: float) -> None:
@@ -571,15 +578,29 @@ def _new_mat(like, nrows, ncols):
     return np.zeros((nrows, ncols), dtype=like.dtype, order="F")
 
 
+def _values_vec(A, S, n):
+    """The VecMut for the values of `svd` / `self_adjoint_evd`. The reference's S holds T-typed entries; for complex A a REAL numpy
+    S is accepted too (filled through a complex temporary). Returns (VecMut, temporary or None)."""
+    if capi._is_torch(S):
+        assert S.dtype == A.dtype, "device S must have A's dtype (complex for complex A: the ABI's S is T-typed)"
+        return capi.VecMut(S.data_ptr(), n, 1), None
+    if np.iscomplexobj(A) and not np.iscomplexobj(S):
+        tmp = np.zeros(n, dtype=A.dtype)
+        return capi.VecMut(tmp.ctypes.data, n, 1), tmp
+    assert S.dtype == A.dtype
+    return capi.VecMut(S.ctypes.data, n, 1), None
+
+
 def svd(A, S, U=None, V=None, par=None, params=None) -> None:
     """svd::svd (svd/mod.rs:530-672) through `libfaer_v0_23_svd_<T>` (faer-ffi/src/lib.rs:2345-2366): A = U diag(S) V^H with S
     (length min(nrows, ncols)) non-increasing. U: None, nrows x size (thin) or nrows x nrows (full); V likewise with ncols.
-    f64 or f32 (f32 computes in f64). Raises RuntimeError("SvdError::NoConvergence") on non-finite input."""
+    f64 / f32 (f32 computes in f64), c64 / c32 (c32 computes in c64; S: A's dtype as in the ABI, or a real array).
+    Raises RuntimeError("SvdError::NoConvergence") on non-finite input."""
     lib = capi.load()
-    suf = _suf(A)
+    suf = _suf_lu(A)
     size = min(A.shape)
     assert S.shape == (size,)
-    sv = capi.VecMut(S.data_ptr() if capi._is_torch(S) else S.ctypes.data, size, 1)
+    sv, tmp = _values_vec(A, S, size)
     none = capi.MatMut(None, 0, 0, 0, 0)
     params = params or getattr(lib, f"libfaer_v0_23_SvdParams_{suf}")()
     st = getattr(lib, f"libfaer_v0_23_svd_{suf}")(capi.mat_ref(A), capi.mat_mut(U) if U is not None else none, sv,
@@ -587,22 +608,27 @@ def svd(A, S, U=None, V=None, par=None, params=None) -> None:
                                                   capi.MemAlloc(None, 0), params)
     if st.tag != 0:
         raise RuntimeError("SvdError::NoConvergence")
+    if tmp is not None:
+        S[...] = tmp.real
 
 
 def self_adjoint_evd(A, S, U=None, par=None, params=None) -> None:
     """evd::self_adjoint_evd (evd/mod.rs:270-418) through `libfaer_v0_23_self_adjoint_evd_<T>`: the LOWER triangle of A is
-    read; S nondecreasing; U (n x n or None) the eigenvectors. Raises RuntimeError("EvdError::NoConvergence") on non-finite input."""
+    read; S nondecreasing; U (n x n or None) the eigenvectors. f64 / f32 / c64 / c32 (S: A's dtype as in the ABI, or a real array
+    for complex A). Raises RuntimeError("EvdError::NoConvergence") on non-finite input."""
     lib = capi.load()
-    suf = _suf(A)
+    suf = _suf_lu(A)
     n = A.shape[0]
     assert A.shape[1] == n and S.shape == (n,)
-    sv = capi.VecMut(S.data_ptr() if capi._is_torch(S) else S.ctypes.data, n, 1)
+    sv, tmp = _values_vec(A, S, n)
     params = params or getattr(lib, f"libfaer_v0_23_SelfAdjointEvdParams_{suf}")()
     st = getattr(lib, f"libfaer_v0_23_self_adjoint_evd_{suf}")(capi.mat_ref(A), capi.mat_mut(U) if U is not None else
                                                                capi.MatMut(None, 0, 0, 0, 0), sv, par or capi.par_default(),
                                                                capi.MemAlloc(None, 0), params)
     if st.tag != 0:
         raise RuntimeError("EvdError::NoConvergence")
+    if tmp is not None:
+        S[...] = tmp.real
 
 
 def bidiag_in_place(A, H_left, H_right, par=None, params=None) -> None:

@@ -243,6 +243,24 @@ struct FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_f32(size_t dim, e
 struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_f64(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SelfAdjointEvdParams params);
 struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_f32(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SelfAdjointEvdParams params);
 
+/* `svd` / `self_adjoint_evd` for complex T (faer.h:6238-6268, 6043-6060; csrc/cplx_condensed.cu): same semantics as the real entry
+ * points; S holds T-typed entries (value, 0), its stride counts complex elements; c32 computes in c64. */
+struct FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_c64(void);
+struct FaerV0_24_BidiagParams libfaer_v0_23_BidiagParams_c32(void);
+struct FaerV0_24_SvdParams libfaer_v0_23_SvdParams_c64(void);
+struct FaerV0_24_SvdParams libfaer_v0_23_SvdParams_c32(void);
+struct FaerV0_24_Layout libfaer_v0_23_svd_scratch_c64(size_t nrows, size_t ncols, enum FaerV0_24_ComputeSvdVectors compute_U, enum FaerV0_24_ComputeSvdVectors compute_V, struct FaerV0_24_Par par, struct FaerV0_24_SvdParams params);
+struct FaerV0_24_Layout libfaer_v0_23_svd_scratch_c32(size_t nrows, size_t ncols, enum FaerV0_24_ComputeSvdVectors compute_U, enum FaerV0_24_ComputeSvdVectors compute_V, struct FaerV0_24_Par par, struct FaerV0_24_SvdParams params);
+struct FaerV0_24_SvdStatus libfaer_v0_23_svd_c64(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_MatMut V, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SvdParams params);
+struct FaerV0_24_SvdStatus libfaer_v0_23_svd_c32(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_MatMut V, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SvdParams params);
+struct FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_c64(void);
+struct FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_c32(void);
+struct FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_c64(void);
+struct FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_c32(void);
+struct FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_c64(size_t dim, enum FaerV0_24_ComputeEigenvectors compute_U, struct FaerV0_24_Par par, struct FaerV0_24_SelfAdjointEvdParams params);
+struct FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_c32(size_t dim, enum FaerV0_24_ComputeEigenvectors compute_U, struct FaerV0_24_Par par, struct FaerV0_24_SelfAdjointEvdParams params);
+struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_c64(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SelfAdjointEvdParams params);
+struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_c32(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SelfAdjointEvdParams params);
 /* reconstruct / inverse on the factors ("next" row): lib.rs:1039-1075 (llt), 1661-1720 (qr), 2059-2124 (lu);
  * semantics: cholesky/llt/reconstruct.rs:12-33 and inverse.rs:10-39 (only the LOWER triangle of the output is written),
  * lu/partial_pivoting/reconstruct.rs and inverse.rs, qr/no_pivoting/reconstruct.rs:13-39 and inverse.rs. L / U may be the packed
