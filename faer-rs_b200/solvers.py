@@ -506,7 +506,7 @@ class Svd:
         else:
             S = np.zeros(size, dtype=A.dtype)
         la.svd(A, S, U, V)
-        return cls(U, S, V)
+        return cls(U, la._real_values(S), V)  # the ABI's S is T-typed; the singular values are kept real
 
     @classmethod
     def new(cls, A):
@@ -541,7 +541,7 @@ class Svd:
         inv[~mask] = 0
         Vt = self._V[:, :size] * inv[None, :]
         out = la._new_mat(self._U, self._V.shape[0], self._U.shape[0])
-        la.matmul(out, la.Accum.Replace, Vt, self._U[:, :size].T, 1.0)
+        la.matmul(out, la.Accum.Replace, Vt, _conj(self._U[:, :size]).T, 1.0)
         return out
 
 
@@ -560,8 +560,8 @@ class SelfAdjointEigen:
             S = torch.zeros(n, dtype=A.dtype, device=A.device)
         else:
             S = np.zeros(n, dtype=A.dtype)
-        la.self_adjoint_evd(A if side == Side.Lower else A.T, S, U)
-        return cls(U, S)
+        la.self_adjoint_evd(A if side == Side.Lower else _conj(A).T, S, U)  # Upper: the lower triangle of the adjoint
+        return cls(U, la._real_values(S))
 
     def U(self):
         return self._U

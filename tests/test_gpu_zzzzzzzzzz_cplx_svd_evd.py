@@ -154,3 +154,25 @@ def test_cplx_svd_evd_device_resident(fb, cuda_dev):
     tol = np.finfo(float).eps * 128 * np.sqrt(8 * n) * max(1.0, float(H.abs().max()))
     assert float((Q.conj().T @ Q - eye).abs().max()) <= tol
     assert float(((Q * E[None, :]) @ Q.conj().T - H).abs().max()) <= tol
+
+
+def test_cplx_solvers_svd_and_eigen(fb, cuda_dev):
+    """`Svd::new` / `new_thin`, `SelfAdjointEigen::new` (both sides) and the pseudo-inverse on complex matrices
+    (solvers.rs:1324-1520; test_pinv svd/mod.rs:1055-...)."""
+    sv = fb.solvers
+    rng = np.random.default_rng(323)
+    A = crandn(rng, (6, 36), np.complex128)
+    d = sv.Svd.new(A)
+    assert d.U().shape == (6, 6) and d.V().shape == (36, 36) and d.S().shape == (6,) and not np.iscomplexobj(d.S())
+    t = sv.Svd.new_thin(A)
+    assert t.U().shape == (6, 6) and t.V().shape == (36, 6)
+    assert np.abs((t.U() * t.S()[None, :]) @ t.V().conj().T - A).max() <= 1e-13
+    pinv = t.pseudoinverse()
+    assert np.abs(pinv - np.linalg.pinv(A)).max() <= 1e-12
+    assert np.abs(A @ pinv @ A - A).max() <= 1e-12
+    G = crandn(rng, (30, 30), np.complex128); H = np.asfortranarray(G + G.conj().T)
+    for side, tri in ((sv.Side.Lower, np.tril), (sv.Side.Upper, np.triu)):
+        P = np.asfortranarray(tri(H))                      # only the chosen triangle is given
+        e = sv.SelfAdjointEigen.new(P, side)
+        assert not np.iscomplexobj(e.S())
+        assert np.abs((e.U() * e.S()[None, :]) @ e.U().conj().T - H).max() <= 1e-12
