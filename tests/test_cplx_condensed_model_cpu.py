@@ -91,3 +91,31 @@ def test_svd_model_identities(shape, full):
     assert np.abs(Um.conj().T @ Um - np.eye(Um.shape[1])).max() <= tol
     assert np.abs(Vm.conj().T @ Vm - np.eye(Vm.shape[1])).max() <= tol
     assert np.abs(S - np.linalg.svd(A, compute_uv=False)).max() <= tol
+
+
+@pytest.mark.parametrize("conj", [False, True])
+def test_back_transform_convention_matches_the_block_householder_sequence(oracle, conj):
+    """The drivers hand the back-transforms to `apply_block_householder_sequence_on_the_left_in_place_with_conj`
+    (householder.rs:724-765) with block size 1 — basis = the reduced matrix, factor = the row of taus, Conj::No for U and for the
+    eigenvectors, Conj::Yes on the transposed rows for V (svd/mod.rs:403-429). The model's `apply_sequence` is that call: checked
+    here against the oracle's restatement of the sequence (which the GPU's complex sequence is tested against on hardware)."""
+    rng = np.random.default_rng(1400 + int(conj))
+    m, n, k = 23, 9, 5
+    A = crandn(rng, (m, n))
+    W, tl, tr = cm.bidiag_unblocked(A)
+    M = crandn(rng, (m, k))
+    want = M.copy(order="F")
+    H = np.asfortranarray(tl.astype(np.complex128)[None, :])           # 1 x n factor: the taus are the 1 x 1 T blocks
+    oracle.apply_q_sequence(np.asfortranarray(W), H, want, conj_lhs=conj)
+    got = M.copy()
+    cm.apply_sequence(W, tl, got, conj=conj)
+    assert np.abs(got - want).max() <= 64 * m * U * np.abs(M).max()
+    # the right reflectors through the transposed corner, rows 1.. (the V back-transform)
+    Wt = np.asfortranarray(W[:n, :].T)
+    Mv = crandn(rng, (n, n))
+    want = Mv.copy(order="F")
+    Hr = np.asfortranarray(tr.astype(np.complex128)[None, :])
+    oracle.apply_q_sequence(np.asfortranarray(Wt[1:, :n - 1]), Hr, want[1:, :], conj_lhs=conj)
+    got = Mv.copy()
+    cm.apply_sequence(Wt[1:, :n - 1], tr, got[1:, :], conj=conj)
+    assert np.abs(got - want).max() <= 64 * n * U * np.abs(Mv).max()
