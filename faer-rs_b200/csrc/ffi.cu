@@ -95,6 +95,30 @@ void householder_seq_entry(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, Faer
   finish_all(st, {&b, &f, &r});
 }
 // ---- reductions to condensed form (svd/bidiag.rs:47-256) ----
+template <class TD, class TS>
+void ffi_cast(cudaStream_t st, TD* dst, i64 drs, i64 dcs, const TS* src, i64 srs, i64 scs, i64 m, i64 n);  // defined below
+// The condensed-form kernels want a column-major matrix (row stride 1). Any other layout (a row-major or strided HOST view keeps
+// its layout in the device mirror; a device view is whatever the caller has) goes through a compact column-major copy.
+template <class T>
+struct ColMajorWork {
+  cudaStream_t st;
+  View<T> orig, work;
+  T* buf = nullptr;
+  ColMajorWork(cudaStream_t st_, View<T> v) : st(st_), orig(v), work(v) {
+    if (v.rs != 1 && v.nrows > 0 && v.ncols > 0) {
+      buf = (T*)ws_alloc((size_t)v.nrows * (size_t)v.ncols * sizeof(T));
+      ffi_cast<T, T>(st, buf, 1, v.nrows, v.ptr, v.rs, v.cs, v.nrows, v.ncols);
+      work = View<T>{buf, v.nrows, v.ncols, 1, v.nrows};
+    }
+  }
+  void finish() {
+    if (!buf) return;
+    ffi_cast<T, T>(st, orig.ptr, orig.rs, orig.cs, buf, 1, orig.nrows, orig.nrows, orig.ncols);
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    ws_free(buf);
+    buf = nullptr;
+  }
+};
 template <class T>
 void bidiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Hl, FaerV0_24_MatMut Hr) {
   FB_ENTRY();
@@ -102,7 +126,9 @@ void bidiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Hl, FaerV0_24_MatMut Hr) 
   StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
   StagedMat hl(Hl.ptr, (i64)Hl.nrows, (i64)Hl.ncols, (i64)Hl.row_stride, (i64)Hl.col_stride, sizeof(T), true, true, st);
   StagedMat hr(Hr.ptr, (i64)Hr.nrows, (i64)Hr.ncols, (i64)Hr.row_stride, (i64)Hr.col_stride, sizeof(T), true, true, st);
-  bidiag_in_place<T>(st, a.view<T>(), hl.view<T>(), hr.view<T>());
+  ColMajorWork<T> w(st, a.view<T>());
+  bidiag_in_place<T>(st, w.work, hl.view<T>(), hr.view<T>());
+  w.finish();
   finish_all(st, {&a, &hl, &hr});
 }
 // evd/tridiag.rs:274-529
@@ -112,7 +138,9 @@ void tridiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
   cudaStream_t st = current_stream();
   StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
   StagedMat h(H.ptr, (i64)H.nrows, (i64)H.ncols, (i64)H.row_stride, (i64)H.col_stride, sizeof(T), true, true, st);
-  tridiag_in_place<T>(st, a.view<T>(), h.view<T>());
+  ColMajorWork<T> w(st, a.view<T>());
+  tridiag_in_place<T>(st, w.work, h.view<T>());
+  w.finish();
   finish_all(st, {&a, &h});
 }
 // ---- solves on the QR factors (qr/no_pivoting/solve.rs) ----
