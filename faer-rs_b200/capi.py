@@ -291,16 +291,28 @@ def load() -> C.CDLL:
         getattr(lib, f"libfaer_v0_23_llt_solve_in_place_scratch_{suf}").restype = Layout
         getattr(lib, f"libfaer_v0_23_llt_solve_in_place_{suf}").argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]
         getattr(lib, f"libfaer_v0_23_llt_solve_in_place_{suf}").restype = None
-    lib.libfaer_v0_23_LdltParams_f64.argtypes = []
-    lib.libfaer_v0_23_LdltParams_f64.restype = LdltParams
-    lib.libfaer_v0_23_ldlt_factor_in_place_scratch_f64.argtypes = [C.c_size_t, P, LdltParams]
-    lib.libfaer_v0_23_ldlt_factor_in_place_scratch_f64.restype = Layout
-    lib.libfaer_v0_23_ldlt_factor_in_place_f64.argtypes = [MatMut, LdltRegularization, P, MemAlloc, LdltParams]
-    lib.libfaer_v0_23_ldlt_factor_in_place_f64.restype = LdltStatus
-    lib.libfaer_v0_23_ldlt_solve_in_place_scratch_f64.argtypes = [C.c_size_t, C.c_size_t, P]
-    lib.libfaer_v0_23_ldlt_solve_in_place_scratch_f64.restype = Layout
-    lib.libfaer_v0_23_ldlt_solve_in_place_f64.argtypes = [MatRef, VecMut, C.c_int, MatMut, P, MemAlloc]
-    lib.libfaer_v0_23_ldlt_solve_in_place_f64.restype = None
+    for suf in ("f64", "f32", "c64", "c32"):
+        getattr(lib, f"libfaer_v0_23_LdltParams_{suf}").argtypes = []
+        getattr(lib, f"libfaer_v0_23_LdltParams_{suf}").restype = LdltParams
+        f = getattr(lib, f"libfaer_v0_23_ldlt_factor_in_place_scratch_{suf}")
+        f.argtypes = [C.c_size_t, P, LdltParams]
+        f.restype = Layout
+        f = getattr(lib, f"libfaer_v0_23_ldlt_factor_in_place_{suf}")
+        f.argtypes = [MatMut, LdltRegularization, P, MemAlloc, LdltParams]
+        f.restype = LdltStatus
+        f = getattr(lib, f"libfaer_v0_23_ldlt_solve_in_place_scratch_{suf}")
+        f.argtypes = [C.c_size_t, C.c_size_t, P]
+        f.restype = Layout
+        f = getattr(lib, f"libfaer_v0_23_ldlt_solve_in_place_{suf}")
+        f.argtypes = [MatRef, VecMut, C.c_int, MatMut, P, MemAlloc]
+        f.restype = None
+        for name in ("ldlt_reconstruct", "ldlt_inverse"):
+            f = getattr(lib, f"libfaer_v0_23_{name}_scratch_{suf}")
+            f.argtypes = [C.c_size_t, P]
+            f.restype = Layout
+            f = getattr(lib, f"libfaer_v0_23_{name}_{suf}")
+            f.argtypes = [MatMut, MatRef, VecMut, P, MemAlloc]
+            f.restype = None
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.argtypes = [C.c_size_t, C.c_size_t, P]
     lib.libfaer_v0_23_llt_solve_in_place_scratch_f64.restype = Layout
     lib.libfaer_v0_23_llt_solve_in_place_f64.argtypes = [MatRef, C.c_int, MatMut, P, MemAlloc]

@@ -17,32 +17,13 @@
 #include <algorithm>
 
 #include "cplx_condensed_core.cuh"
+#include "flat_map.cuh"
 #include "runtime.cuh"
 #include "tensor_ops.cuh"
 
 namespace fb {
 
 namespace {
-
-template <class B>
-__global__ void __launch_bounds__(256) cc_map_kernel(B body, cc::i64 y0) {
-  body((cc::i64)blockIdx.x * blockDim.x + threadIdx.x, y0 + (cc::i64)blockIdx.y);
-}
-
-// the launcher of cplx_condensed_core.cuh on a stream: body(i, j) for i < nx (rounded up to whole blocks), j < ny
-struct DevRun {
-  cudaStream_t st;
-  template <class B>
-  void operator()(const B& body, i64 nx, i64 ny) const {
-    if (nx <= 0 || ny <= 0) return;
-    for (i64 y0 = 0; y0 < ny; y0 += 65535) {
-      const unsigned nc = (unsigned)std::min<i64>(65535, ny - y0);
-      cc_map_kernel<B><<<dim3((unsigned)((nx + 255) / 256), nc), 256, 0, st>>>(body, y0);
-      FB_CUDA_CHECK(cudaGetLastError());
-      note_launch();
-    }
-  }
-};
 
 struct DevWork {
   cc::Work ws;

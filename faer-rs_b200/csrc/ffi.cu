@@ -573,6 +573,98 @@ FaerV0_24_SvdStatus svd_entry_cplx(FaerV0_24_MatRef A, FaerV0_24_MatMut U, FaerV
   return out;
 }
 
+// ---- LDLT for the other scalar kinds (ldlt_types.cu); D arrives as a VecRef of T-typed entries ----
+// the D argument on the device: a device vector is used in place, a host vector is gathered into a compact device copy
+template <class R, bool CX>
+struct DiagArg {
+  const R* ptr;
+  i64 stride;
+  R* mirror = nullptr;
+  DiagArg(FaerV0_24_VecRef D, size_t n, cudaStream_t st) {
+    const size_t w = CX ? 2 : 1;
+    ptr = (const R*)D.ptr;
+    stride = (i64)D.stride;
+    if (n > 0 && !is_device_pointer(D.ptr)) {
+      std::vector<R> h(n * w);
+      for (size_t i = 0; i < n; ++i)
+        for (size_t c = 0; c < w; ++c) h[i * w + c] = ((const R*)D.ptr)[((ptrdiff_t)i * D.stride) * (ptrdiff_t)w + (ptrdiff_t)c];
+      mirror = (R*)ws_alloc(n * w * sizeof(R));
+      FB_CUDA_CHECK(cudaMemcpyAsync(mirror, h.data(), n * w * sizeof(R), cudaMemcpyHostToDevice, st));
+      FB_CUDA_CHECK(cudaStreamSynchronize(st));  // `h` is pageable and local
+      ptr = mirror;
+      stride = 1;
+    }
+  }
+  ~DiagArg() {
+    if (mirror) ws_free(mirror);
+  }
+};
+template <class R, bool CX>
+FaerV0_24_LdltStatus ldlt_factor_entry_t(FaerV0_24_MatMut A, FaerV0_24_LdltRegularization regularization) {
+  FB_ENTRY();
+  FB_ASSERT(A.nrows == A.ncols, "LDLT needs a square matrix");
+  cudaStream_t st = current_stream();
+  const size_t es = (CX ? 2 : 1) * sizeof(R);
+  R delta = 0, eps = 0;  // the regularisation parameters are T::Real
+  if (regularization.dynamic_regularization_delta) delta = read_real(regularization.dynamic_regularization_delta, R());
+  if (regularization.dynamic_regularization_epsilon) eps = read_real(regularization.dynamic_regularization_epsilon, R());
+  const signed char* d_signs = nullptr;
+  signed char* signs_mirror = nullptr;
+  const FaerV0_24_SliceMut sg = regularization.dynamic_regularization_signs;
+  if (sg.ptr != nullptr && A.nrows > 0) {
+    FB_ASSERT(sg.len >= A.nrows, "dynamic_regularization_signs is shorter than the matrix dimension");
+    if (is_device_pointer(sg.ptr)) {
+      d_signs = (const signed char*)sg.ptr;
+    } else {
+      signs_mirror = (signed char*)ws_alloc(A.nrows);
+      FB_CUDA_CHECK(cudaMemcpyAsync(signs_mirror, sg.ptr, A.nrows, cudaMemcpyHostToDevice, st));
+      d_signs = signs_mirror;
+    }
+  }
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, es, true, true, st);
+  const LdltResult r = ldlt_in_place_t<R, CX>(st, a.view<R>(), delta, eps, d_signs);
+  finish_all(st, {&a});
+  if (signs_mirror) ws_free(signs_mirror);
+  FaerV0_24_LdltStatus out;
+  memset(&out, 0, sizeof(out));
+  if (r.ok) {
+    out.tag = FaerV0_24_LdltStatus_Ok;
+    out.ok.dynamic_regularization_count = r.dynamic_regularization_count;
+  } else {
+    out.tag = FaerV0_24_LdltStatus_ZeroPivot;
+    out.zero_pivot.index = r.zero_pivot_index;
+  }
+  return out;
+}
+template <class R, bool CX>
+void ldlt_solve_entry_t(FaerV0_24_MatRef L, FaerV0_24_VecRef D, FaerV0_24_Conj A_conj, FaerV0_24_MatMut rhs) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t n = L.nrows, es = (CX ? 2 : 1) * sizeof(R);
+  FB_ASSERT(L.ncols == n && D.len == n && rhs.nrows == n, "LDLT solve shape mismatch");
+  if (n == 0 || rhs.ncols == 0) return;
+  StagedMat l(L.ptr, (i64)n, (i64)n, (i64)L.row_stride, (i64)L.col_stride, es, true, false, st);
+  StagedMat r(rhs.ptr, (i64)rhs.nrows, (i64)rhs.ncols, (i64)rhs.row_stride, (i64)rhs.col_stride, es, true, true, st);
+  DiagArg<R, CX> d(D, n, st);
+  ldlt_solve_in_place_t<R, CX>(st, l.view<const R>(), d.ptr, d.stride, A_conj == FaerV0_24_Conj_Yes, r.view<R>());
+  finish_all(st, {&l, &r});
+}
+template <class R, bool CX>
+void ldlt_recon_entry_t(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_VecRef D, bool inverse) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t n = L.nrows, es = (CX ? 2 : 1) * sizeof(R);
+  FB_ASSERT(L.ncols == n && D.len == n && A.nrows == n && A.ncols == n, "LDLT reconstruct / inverse shape mismatch");
+  if (n == 0) return;
+  // only the lower triangle is written: the rest of A must survive the round trip
+  StagedMat a(A.ptr, (i64)n, (i64)n, (i64)A.row_stride, (i64)A.col_stride, es, true, true, st);
+  StagedMat l(L.ptr, (i64)n, (i64)n, (i64)L.row_stride, (i64)L.col_stride, es, true, false, st);
+  DiagArg<R, CX> d(D, n, st);
+  if (inverse) ldlt_inverse_t<R, CX>(st, a.view<R>(), l.view<const R>(), d.ptr, d.stride);
+  else ldlt_reconstruct_t<R, CX>(st, a.view<R>(), l.view<const R>(), d.ptr, d.stride);
+  finish_all(st, {&a, &l});
+}
+
 extern "C" {
 
 void libfaer_v0_23_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Accum accum, FaerV0_24_MatRef A, FaerV0_24_MatRef B,
@@ -1689,6 +1781,57 @@ FB_LU_RECON_TYPES_FFI(u64, 8, c32, float, true, 2 * sizeof(float))
 #undef FB_RECON_TYPES_FFI
 #undef FB_QR_RECON_TYPES_FFI
 #undef FB_LU_RECON_TYPES_FFI
+
+// ---- LDLT: factor / solve for f32 / c64 / c32, reconstruct / inverse for every dtype (ldlt_types.cu) ----
+#define FB_LDLT_FS_FFI(SUF, R, CX, ES)                                                                                          \
+  FaerV0_24_LdltParams libfaer_v0_23_LdltParams_##SUF(void) { return FaerV0_24_LdltParams{64, 128}; }                           \
+  FaerV0_24_Layout libfaer_v0_23_ldlt_factor_in_place_scratch_##SUF(size_t dim, FaerV0_24_Par par, FaerV0_24_LdltParams params) { \
+    (void)par; (void)params;                                                                                                    \
+    return FaerV0_24_Layout{dim * (ES), 64}; /* temp_mat_scratch::<T>(dim, 1), ldlt/factor.rs:715-724 */                        \
+  }                                                                                                                             \
+  FaerV0_24_LdltStatus libfaer_v0_23_ldlt_factor_in_place_##SUF(FaerV0_24_MatMut A, FaerV0_24_LdltRegularization regularization, \
+                                                                FaerV0_24_Par par, FaerV0_24_MemAlloc mem,                      \
+                                                                FaerV0_24_LdltParams params) {                                  \
+    (void)par; (void)mem; (void)params;                                                                                         \
+    return ldlt_factor_entry_t<R, CX>(A, regularization);                                                                       \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_ldlt_solve_in_place_scratch_##SUF(size_t dim, size_t rhs_ncols, FaerV0_24_Par par) {           \
+    (void)dim; (void)rhs_ncols; (void)par;                                                                                      \
+    return FaerV0_24_Layout{0, 1};                                                                                              \
+  }                                                                                                                             \
+  void libfaer_v0_23_ldlt_solve_in_place_##SUF(FaerV0_24_MatRef L, FaerV0_24_VecRef D, FaerV0_24_Conj A_conj,                   \
+                                               FaerV0_24_MatMut rhs, FaerV0_24_Par par, FaerV0_24_MemAlloc mem) {               \
+    (void)par; (void)mem;                                                                                                       \
+    ldlt_solve_entry_t<R, CX>(L, D, A_conj, rhs);                                                                               \
+  }
+#define FB_LDLT_RI_FFI(SUF, R, CX, ES)                                                                                          \
+  FaerV0_24_Layout libfaer_v0_23_ldlt_reconstruct_scratch_##SUF(size_t dim, FaerV0_24_Par par) {                                \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{dim * dim * (ES), 64}; /* temp_mat_scratch(dim, dim), ldlt/reconstruct.rs:4-7 */                    \
+  }                                                                                                                             \
+  void libfaer_v0_23_ldlt_reconstruct_##SUF(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_VecRef D, FaerV0_24_Par par,      \
+                                            FaerV0_24_MemAlloc mem) {                                                           \
+    (void)par; (void)mem;                                                                                                       \
+    ldlt_recon_entry_t<R, CX>(A, L, D, false);                                                                                  \
+  }                                                                                                                             \
+  FaerV0_24_Layout libfaer_v0_23_ldlt_inverse_scratch_##SUF(size_t dim, FaerV0_24_Par par) {                                    \
+    (void)par;                                                                                                                  \
+    return FaerV0_24_Layout{dim * dim * (ES), 64}; /* temp_mat_scratch(dim, dim), ldlt/inverse.rs:4-7 */                        \
+  }                                                                                                                             \
+  void libfaer_v0_23_ldlt_inverse_##SUF(FaerV0_24_MatMut A_inv, FaerV0_24_MatRef L, FaerV0_24_VecRef D, FaerV0_24_Par par,      \
+                                        FaerV0_24_MemAlloc mem) {                                                               \
+    (void)par; (void)mem;                                                                                                       \
+    ldlt_recon_entry_t<R, CX>(A_inv, L, D, true);                                                                               \
+  }
+FB_LDLT_FS_FFI(f32, float, false, sizeof(float))
+FB_LDLT_FS_FFI(c64, double, true, 2 * sizeof(double))
+FB_LDLT_FS_FFI(c32, float, true, 2 * sizeof(float))
+FB_LDLT_RI_FFI(f64, double, false, sizeof(double))
+FB_LDLT_RI_FFI(f32, float, false, sizeof(float))
+FB_LDLT_RI_FFI(c64, double, true, 2 * sizeof(double))
+FB_LDLT_RI_FFI(c32, float, true, 2 * sizeof(float))
+#undef FB_LDLT_FS_FFI
+#undef FB_LDLT_RI_FFI
 
 // ---- global par / alloc ----
 FaerV0_24_Par libfaer_v0_23_get_global_par(void) {

@@ -105,4 +105,16 @@ void qr_reconstruct_t(cudaStream_t st, View<R> out, View<const R> Q_basis, View<
 template <class R, bool CX>
 void qr_inverse_t(cudaStream_t st, View<R> out, View<const R> Q_basis, View<const R> Q_coeff, View<const R> Rm);
 
+// ---- ldlt_types.cu: LDLT beyond the f64 factorization, over the scalar kind <R, complex?> (complex views in COMPLEX element units
+// on an R* base). Factor / solve: <float, false>, <double, true>, <float, true>; reconstruct / inverse: also <double, false>.
+// D: DEVICE pointer to T-typed entries `dstride` elements apart; d_signs: device int8[n] or null ----
+template <class R, bool CX>
+LdltResult ldlt_in_place_t(cudaStream_t st, View<R> A, R delta, R eps, const signed char* d_signs);
+template <class R, bool CX>
+void ldlt_solve_in_place_t(cudaStream_t st, View<const R> L, const R* D, i64 dstride, bool conj, View<R> rhs);
+template <class R, bool CX>
+void ldlt_reconstruct_t(cudaStream_t st, View<R> out, View<const R> L, const R* D, i64 dstride);
+template <class R, bool CX>
+void ldlt_inverse_t(cudaStream_t st, View<R> out, View<const R> L, const R* D, i64 dstride);
+
 }  // namespace fb

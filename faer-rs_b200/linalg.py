@@ -233,13 +233,15 @@ class LdltError(Exception):
 def ldlt_in_place(A, regularization=(0.0, 0.0), signs=None, par=None, params=None) -> LdltInfo:
     """cholesky::ldlt::factor::cholesky_in_place (ldlt/factor.rs:725-767): in-place LDLT of the lower triangle, D on the
     diagonal and the unit-lower L strictly below it. regularization = (delta, epsilon); signs: optional int8 array (numpy)
-    or int8 CUDA tensor of expected pivot signs. Raises LdltError."""
-    _check_f64(A)
+    or int8 CUDA tensor of expected pivot signs. f64 (tuned kernels), f32 / c64 / c32 (the functional path of ldlt_types.cu).
+    Raises LdltError."""
+    suf = _suf_lu(A)
+    real = C.c_double if suf in ("f64", "c64") else C.c_float
     lib = capi.load()
-    params = params or lib.libfaer_v0_23_LdltParams_f64()
+    params = params or getattr(lib, f"libfaer_v0_23_LdltParams_{suf}")()
     par = par or capi.par_default()
-    delta = C.c_double(float(regularization[0]))
-    eps = C.c_double(float(regularization[1]))
+    delta = real(float(regularization[0]))
+    eps = real(float(regularization[1]))
     sl = capi.SliceMut(None, 0)
     if signs is not None:
         if not capi._is_torch(signs):
@@ -247,7 +249,7 @@ def ldlt_in_place(A, regularization=(0.0, 0.0), signs=None, par=None, params=Non
         sl = capi.slice_mut(signs)
         assert sl.len == A.shape[0]
     reg = capi.LdltRegularization(C.cast(C.pointer(delta), C.c_void_p), C.cast(C.pointer(eps), C.c_void_p), sl)
-    st = lib.libfaer_v0_23_ldlt_factor_in_place_f64(capi.mat_mut(A), reg, par, capi.MemAlloc(None, 0), params)
+    st = getattr(lib, f"libfaer_v0_23_ldlt_factor_in_place_{suf}")(capi.mat_mut(A), reg, par, capi.MemAlloc(None, 0), params)
     if st.tag == 0:
         return LdltInfo(int(st.value))
     if st.tag == 1:
@@ -255,24 +257,41 @@ def ldlt_in_place(A, regularization=(0.0, 0.0), signs=None, par=None, params=Non
     raise RuntimeError("LdltStatus::Unknown")
 
 
-def ldlt_solve_in_place(LD, rhs, conj: int = CONJ_NO, par=None, D=None) -> None:
-    """cholesky::ldlt::solve::solve_in_place_with_conj (ldlt/solve.rs:11-49): rhs <- (L D L^T)^-1 rhs with L the unit-lower
-    part of LD. D defaults to the diagonal of LD (passed as a strided vector over the same storage, as `L.diagonal()` in
-    the reference); a separate contiguous vector can be given instead, as `Ldlt::D()`."""
-    _check_f64(LD, rhs)
-    lib = capi.load()
+def _ldlt_diag(LD, D):
+    """The `D: VecRef` argument: the diagonal of LD as a strided vector over the same storage (`L.diagonal()` in the reference), or a
+    separate contiguous vector of LD's dtype (`Ldlt::D()`)."""
     p, m, n, rs, cs = capi._fields(LD)
     assert m == n
     if D is None:
-        dv = capi.VecMut(p, n, rs + cs)
-    elif capi._is_torch(D):
-        assert D.dim() == 1 and D.numel() == n and D.is_contiguous()
-        dv = capi.VecMut(D.data_ptr(), n, 1)
-    else:
-        assert D.ndim == 1 and D.size == n and D.dtype == np.float64 and D.flags.c_contiguous
-        dv = capi.VecMut(D.ctypes.data, n, 1)
-    lib.libfaer_v0_23_ldlt_solve_in_place_f64(capi.mat_ref(LD), dv, conj, capi.mat_mut(rhs),
-                                              par or capi.par_default(), capi.MemAlloc(None, 0))
+        return capi.VecMut(p, n, rs + cs)
+    if capi._is_torch(D):
+        assert D.dim() == 1 and D.numel() == n and D.is_contiguous() and D.dtype == LD.dtype
+        return capi.VecMut(D.data_ptr(), n, 1)
+    assert D.ndim == 1 and D.size == n and D.dtype == LD.dtype and D.flags.c_contiguous
+    return capi.VecMut(D.ctypes.data, n, 1)
+
+
+def ldlt_solve_in_place(LD, rhs, conj: int = CONJ_NO, par=None, D=None) -> None:
+    """cholesky::ldlt::solve::solve_in_place_with_conj (ldlt/solve.rs:11-49): rhs <- conj?(L D L^H)^-1 rhs with L the unit-lower
+    part of LD. D defaults to the diagonal of LD; a separate contiguous vector of LD's dtype can be given instead. f64 / f32 /
+    c64 / c32."""
+    suf = _same_suffix(LD, rhs)
+    getattr(capi.load(), f"libfaer_v0_23_ldlt_solve_in_place_{suf}")(capi.mat_ref(LD), _ldlt_diag(LD, D), conj, capi.mat_mut(rhs),
+                                                                     par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
+def ldlt_reconstruct(out, LD, par=None, D=None) -> None:
+    """cholesky::ldlt::reconstruct (ldlt/reconstruct.rs:9-55): the LOWER triangle of out <- L D L^H."""
+    suf = _same_suffix(out, LD)
+    getattr(capi.load(), f"libfaer_v0_23_ldlt_reconstruct_{suf}")(capi.mat_mut(out), capi.mat_ref(LD), _ldlt_diag(LD, D),
+                                                                  par or capi.par_default(), capi.MemAlloc(None, 0))
+
+
+def ldlt_inverse(out, LD, par=None, D=None) -> None:
+    """cholesky::ldlt::inverse (ldlt/inverse.rs:9-60): the LOWER triangle of out <- (L D L^H)^-1."""
+    suf = _same_suffix(out, LD)
+    getattr(capi.load(), f"libfaer_v0_23_ldlt_inverse_{suf}")(capi.mat_mut(out), capi.mat_ref(LD), _ldlt_diag(LD, D),
+                                                              par or capi.par_default(), capi.MemAlloc(None, 0))
 
 
 def llt_solve_in_place(L, rhs, conj: int = CONJ_NO, par=None) -> None:

@@ -351,6 +351,41 @@ struct FaerV0_24_Layout libfaer_v0_23_ldlt_factor_in_place_scratch_f64(size_t di
 struct FaerV0_24_LdltStatus libfaer_v0_23_ldlt_factor_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_LdltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LdltParams params);
 struct FaerV0_24_Layout libfaer_v0_23_ldlt_solve_in_place_scratch_f64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
 void libfaer_v0_23_ldlt_solve_in_place_f64(struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+/* LDLT for the other dtypes and `ldlt_reconstruct` / `ldlt_inverse` (faer.h:3802-4030 stamped per dtype; lib.rs:1190-1300;
+ * csrc/ldlt_types.cu: the unblocked flat-map factorization of ldlt_core.cuh for f32 / c64 / c32, compositions for the rest). The
+ * regularisation scalars are T::Real, D holds T-typed entries (the real parts are used), A_conj is honoured for complex T,
+ * only the LOWER triangle of the reconstruct / inverse output is written (ldlt/reconstruct.rs:9-55, inverse.rs:9-60). */
+struct FaerV0_24_LdltParams libfaer_v0_23_LdltParams_f32(void);
+struct FaerV0_24_LdltParams libfaer_v0_23_LdltParams_c64(void);
+struct FaerV0_24_LdltParams libfaer_v0_23_LdltParams_c32(void);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_factor_in_place_scratch_f32(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LdltParams params);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_factor_in_place_scratch_c64(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LdltParams params);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_factor_in_place_scratch_c32(size_t dim, struct FaerV0_24_Par par, struct FaerV0_24_LdltParams params);
+struct FaerV0_24_LdltStatus libfaer_v0_23_ldlt_factor_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_LdltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LdltParams params);
+struct FaerV0_24_LdltStatus libfaer_v0_23_ldlt_factor_in_place_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_LdltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LdltParams params);
+struct FaerV0_24_LdltStatus libfaer_v0_23_ldlt_factor_in_place_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_LdltRegularization regularization, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_LdltParams params);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_solve_in_place_scratch_f32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_solve_in_place_scratch_c64(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_solve_in_place_scratch_c32(size_t dim, size_t rhs_ncols, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_solve_in_place_f32(struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_ldlt_solve_in_place_c64(struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+void libfaer_v0_23_ldlt_solve_in_place_c32(struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, enum FaerV0_24_Conj A_conj, struct FaerV0_24_MatMut rhs, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_reconstruct_scratch_f64(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_reconstruct_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_inverse_scratch_f64(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_inverse_f64(struct FaerV0_24_MatMut A_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_reconstruct_scratch_f32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_reconstruct_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_inverse_scratch_f32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_inverse_f32(struct FaerV0_24_MatMut A_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_reconstruct_scratch_c64(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_reconstruct_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_inverse_scratch_c64(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_inverse_c64(struct FaerV0_24_MatMut A_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_reconstruct_scratch_c32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_reconstruct_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
+struct FaerV0_24_Layout libfaer_v0_23_ldlt_inverse_scratch_c32(size_t dim, struct FaerV0_24_Par par);
+void libfaer_v0_23_ldlt_inverse_c32(struct FaerV0_24_MatMut A_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_VecRef D, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem);
 
 /* partial-pivoting LU.   params: lib.rs:679-684, faer.h:648; scratch: lib.rs:1952-1965; factor: lib.rs:1966-1983, faer.h:4456-4461 */
 /* c64 (complex<f64>, interleaved) triangular solves and LLT: faer.h:6130-6143, 636, 4036-4048 / lib.rs:896-937, 984-1038 stamped
