@@ -279,7 +279,7 @@ class Llt(_Solve):
 
 
 class Ldlt(_Solve):
-    """A = L D L^T without pivoting (solvers.rs:818-872): unit-lower L (explicit unit diagonal, zero strict upper part) and
+    """A = L D L^H without pivoting (solvers.rs:818-872): unit-lower L (explicit unit diagonal, zero strict upper part) and
     the diagonal D as a vector. `Ldlt.new(A, side)` raises LdltError(index) on a zero pivot."""
 
     def __init__(self, L, D):
@@ -288,10 +288,9 @@ class Ldlt(_Solve):
     @classmethod
     def new(cls, A, side: int = Side.Lower) -> "Ldlt":
         assert A.ndim == 2 and A.shape[0] == A.shape[1]
-        assert not _is_cplx(A), "Ldlt: real scalars only on this backend"
         n = A.shape[0]
         L = _zeros(A, n, n)
-        _assign(L, _tri(A if side == Side.Lower else A.T, lower=True))
+        _assign(L, _tri(A if side == Side.Lower else _adjoint(A), lower=True))  # Upper: the lower triangle of the adjoint
         la.ldlt_in_place(L)  # default regularization and params; LdltError propagates
         if _t(L):
             D = L.diagonal().clone()
@@ -316,9 +315,11 @@ class Ldlt(_Solve):
         return self._L
 
     def _solve_core(self, rhs, conj: int) -> None:
-        la.ldlt_solve_in_place(self._L, rhs, D=self._D)  # real scalars: conj(A) = A
+        la.ldlt_solve_in_place(self._L, rhs, conj, D=self._D)
 
-    _solve_transpose_core = _solve_core  # real scalars: A^T = A
+    def _solve_transpose_core(self, rhs, conj: int) -> None:
+        # A^T = conj(A) for a self-adjoint A: conj composed with Yes (as Llt above)
+        la.ldlt_solve_in_place(self._L, rhs, la.CONJ_NO if conj == la.CONJ_YES else la.CONJ_YES, D=self._D)
 
     def reconstruct(self):
         """ldlt/reconstruct.rs: L D L^H."""
@@ -327,7 +328,7 @@ class Ldlt(_Solve):
             LDm.mul_(self._D.unsqueeze(0))
         else:
             LDm *= self._D[None, :]
-        return mul(LDm, self._L.T)
+        return mul(LDm, _adjoint(self._L))
 
 
 class PartialPivLu(_Solve):

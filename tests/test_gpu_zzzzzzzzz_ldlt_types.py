@@ -130,3 +130,30 @@ def test_ldlt_reconstruct_and_inverse(fb, cuda_dev, dtype):
         Lsep = np.asfortranarray(np.tril(LD, -1) + np.eye(n, dtype=dtype))
         la.ldlt_reconstruct(out2, Lsep, D=np.ascontiguousarray(np.diagonal(LD)))
         assert np.array_equal(np.tril(out2), np.tril(out)), n
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float32])
+def test_ldlt_solver_class_other_dtypes(fb, cuda_dev, dtype):
+    """`Ldlt::new` and the Solve family (solvers.rs:818-872, 93-282) on complex / f32 matrices: L / D contracts, both sides, the four
+    solves (A x, conj(A) x, A^T x, A^H x)."""
+    sv = fb.solvers
+    rng = np.random.default_rng(474)
+    n = 50
+    u = float(np.finfo(rdt(dtype)).eps)
+    A = indefinite(rng, n, dtype)
+    dec = sv.Ldlt.new(A, sv.Side.Lower)
+    L, D = wide(np.asarray(dec.L())), wide(np.asarray(dec.D()))
+    assert np.all(np.diag(L) == 1) and np.all(np.triu(L, 1) == 0) and D.shape == (n,) and np.all(D.imag == 0)
+    Aw = wide(A)
+    assert np.abs(L @ np.diag(D) @ L.conj().T - Aw).max() <= 64 * n * u * np.abs(A).max()
+    assert (D.real < 0).sum() == (np.linalg.eigvalsh(Aw) < 0).sum()
+    assert np.abs(wide(np.asarray(dec.reconstruct())) - Aw).max() <= 128 * n * u * np.abs(A).max()
+    B = crand(rng, (n, 4), dtype)
+    tol = 256 * n * u * np.linalg.cond(Aw) * np.abs(B).max()
+    assert np.abs(Aw @ wide(np.asarray(dec.solve(B))) - wide(B)).max() <= tol
+    assert np.abs(Aw.conj() @ wide(np.asarray(dec.solve_conjugate(B))) - wide(B)).max() <= tol
+    assert np.abs(Aw.T @ wide(np.asarray(dec.solve_transpose(B))) - wide(B)).max() <= tol
+    assert np.abs(Aw.conj().T @ wide(np.asarray(dec.solve_adjoint(B))) - wide(B)).max() <= tol
+    poisoned = A.copy(order="F"); poisoned[np.tril_indices(n, -1)] = np.nan
+    up = sv.Ldlt.new(poisoned, sv.Side.Upper)
+    assert np.allclose(np.asarray(up.L()), np.asarray(dec.L()), rtol=1e3 * u, atol=1e3 * u)
