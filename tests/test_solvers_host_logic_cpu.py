@@ -34,7 +34,7 @@ def oracle_backed_la(fb, oracle):
         packed = np.array(LD, order="F", copy=True)
         if D is not None:
             np.fill_diagonal(packed, D)
-        oracle.ldlt_solve(packed, rhs)
+        oracle.ldlt_solve(packed, rhs, conj_lhs=bool(conj))
 
     def lu_in_place(A, perm, perm_inv, par=None, params=None):
         p, pi, _ = oracle.lu(A)
@@ -98,6 +98,17 @@ def test_solvers_host_logic_against_oracle_backend(fb, oracle, monkeypatch):
     run_all(sv)
     run_all(sv, cplx=True)  # the reference's test_all_solvers runs on c64 (solvers.rs:2919-2977)
     run_ldlt(sv)
+
+
+def test_ldlt_class_on_complex_and_f32(fb, oracle, monkeypatch):
+    """The host logic of `solvers.Ldlt` beyond f64 (conjugation flags of the four solves, the adjoint side, L D L^H): the GPU
+    test's own function against the oracle-backed stand-in."""
+    import importlib
+    sv = fb.solvers
+    monkeypatch.setattr(sv, "la", oracle_backed_la(fb, oracle))
+    gpu_case = importlib.import_module("test_gpu_zzzzzzzzz_ldlt_types").test_ldlt_solver_class_other_dtypes
+    for dtype in (np.complex128, np.float32):
+        gpu_case(fb, None, dtype)
 
 
 def test_split_lu_contract(fb):
