@@ -75,7 +75,9 @@ inline VCD cv(const VD& v) { return VCD{v.ptr, v.nrows, v.ncols, v.rs, v.cs}; }
 extern unsigned long long g_launch_count;
 inline void note_launch() { ++g_launch_count; }
 
-// ---- PTX helpers -----------------------------------------------------------
+// ---- PTX helpers (device compilation only; the host build of the flat-map drivers, tools/emul/drivers_host.cpp, includes this
+// header through a plain C++ compiler) -----------------------------------------------------------
+#if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // cp.async with zero-fill: copies `src_bytes` (<= CP) bytes and zero-fills the rest.
@@ -104,5 +106,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+#endif  // __CUDACC__
 
 }  // namespace fb

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <type_traits>
 
+#include "flat_map.cuh"
 #include "runtime.cuh"
 #include "tensor_ops.cuh"
 
@@ -21,62 +22,58 @@ namespace fb {
 
 namespace {
 
-// W = 1 (real) or 2 (interleaved complex) R values per element; strides in elements
+// Flat-map bodies (flat_map.cuh). W = 1 (real) or 2 (interleaved complex) R values per element; strides in elements.
+#if defined(__CUDACC__)
+#define RT_HD __host__ __device__ __forceinline__
+#else
+#define RT_HD inline
+#endif
 template <class R, int W>
-__global__ void rt_set_identity_kernel(R* __restrict__ A, i64 rs, i64 cs, i64 n, i64 c0) {
-  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  const i64 j = c0 + blockIdx.y;
-  if (i < n && j < n) {
+struct RtSetIdentity {
+  R* A; i64 rs, cs, n;
+  RT_HD void operator()(i64 i, i64 j) const {
+    if (i >= n || j >= n) return;
     R* p = A + W * (i * rs + j * cs);
     p[0] = i == j ? R(1) : R(0);
     if (W == 2) p[W - 1] = R(0);
   }
-}
+};
 // out (m x n) <- upper trapezoid of Rm (size x n) in its first `size` rows, zero elsewhere
 template <class R, int W>
-__global__ void rt_set_upper_trapezoid_kernel(R* __restrict__ out, i64 o_rs, i64 o_cs, i64 m, i64 n, const R* __restrict__ Rm,
-                                              i64 r_rs, i64 r_cs, i64 size, i64 c0) {
-  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  const i64 j = c0 + blockIdx.y;
-  if (i < m && j < n) {
+struct RtSetUpperTrapezoid {
+  R* out; i64 o_rs, o_cs, m, n; const R* Rm; i64 r_rs, r_cs, size;
+  RT_HD void operator()(i64 i, i64 j) const {
+    if (i >= m || j >= n) return;
     R* p = out + W * (i * o_rs + j * o_cs);
     const bool take = i < size && i <= j;
     const R* q = Rm + W * (i * r_rs + j * r_cs);
     p[0] = take ? q[0] : R(0);
     if (W == 2) p[W - 1] = take ? q[W - 1] : R(0);
   }
-}
+};
 // tmp (compact column-major, ld = nrows) [i, c] = src[perm[i], c]
 template <class R, int W>
-__global__ void rt_gather_rows_kernel(R* __restrict__ tmp, const R* __restrict__ src, i64 rs, i64 cs, i64 nrows, i64 ncols,
-                                      const long long* __restrict__ perm, i64 c0) {
-  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  const i64 c = c0 + blockIdx.y;
-  if (i < nrows && c < ncols) {
+struct RtGatherRows {
+  R* tmp; const R* src; i64 rs, cs, nrows, ncols; const long long* perm;
+  RT_HD void operator()(i64 i, i64 c) const {
+    if (i >= nrows || c >= ncols) return;
     const R* q = src + W * (perm[i] * rs + c * cs);
     R* p = tmp + W * (c * nrows + i);
     p[0] = q[0];
     if (W == 2) p[W - 1] = q[W - 1];
   }
-}
+};
 template <class R, int W>
-__global__ void rt_scatter_back_kernel(R* __restrict__ dst, i64 rs, i64 cs, const R* __restrict__ tmp, i64 nrows, i64 ncols,
-                                       i64 c0) {
-  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  const i64 c = c0 + blockIdx.y;
-  if (i < nrows && c < ncols) {
+struct RtScatterBack {
+  R* dst; i64 rs, cs; const R* tmp; i64 nrows, ncols;
+  RT_HD void operator()(i64 i, i64 c) const {
+    if (i >= nrows || c >= ncols) return;
     const R* q = tmp + W * (c * nrows + i);
     R* p = dst + W * (i * rs + c * cs);
     p[0] = q[0];
     if (W == 2) p[W - 1] = q[W - 1];
   }
-}
-
-// launches over (rows in blocks of 256) x (columns in chunks of <= 65535: the grid.y limit)
-template <class F>
-void over_column_chunks(i64 ncols, F&& f) {
-  for (i64 c0 = 0; c0 < ncols; c0 += 65535) f(c0, (unsigned)std::min<i64>(65535, ncols - c0));
-}
+};
 
 template <class R, bool CX>
 struct Kind {
@@ -90,12 +87,8 @@ struct Kind {
 
   static void set_identity(cudaStream_t st, V A) {
     const i64 n = A.nrows;
-    if (n == 0) return;
-    over_column_chunks(n, [&](i64 c0, unsigned nc) {
-      rt_set_identity_kernel<R, W><<<dim3((unsigned)((n + 255) / 256), nc), 256, 0, st>>>(A.ptr, A.rs, A.cs, n, c0);
-      FB_CUDA_CHECK(cudaGetLastError());
-      note_launch();
-    });
+    DevRun run{st};
+    run(RtSetIdentity<R, W>{A.ptr, A.rs, A.cs, n}, n, n);
   }
   // rhs[i, :] <- rhs[perm[i], :]; perm: HOST int64 of rhs.nrows entries
   static void permute_rows(cudaStream_t st, V rhs, const long long* perm) {
@@ -104,16 +97,9 @@ struct Kind {
     long long* d_perm = (long long*)ws_alloc((size_t)n * 8);
     R* tmp = (R*)ws_alloc((size_t)n * (size_t)k * W * sizeof(R));
     FB_CUDA_CHECK(cudaMemcpyAsync(d_perm, perm, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    over_column_chunks(k, [&](i64 c0, unsigned nc) {
-      rt_gather_rows_kernel<R, W><<<dim3((unsigned)((n + 255) / 256), nc), 256, 0, st>>>(tmp, rhs.ptr, rhs.rs, rhs.cs, n, k, d_perm, c0);
-      FB_CUDA_CHECK(cudaGetLastError());
-      note_launch();
-    });
-    over_column_chunks(k, [&](i64 c0, unsigned nc) {
-      rt_scatter_back_kernel<R, W><<<dim3((unsigned)((n + 255) / 256), nc), 256, 0, st>>>(rhs.ptr, rhs.rs, rhs.cs, tmp, n, k, c0);
-      FB_CUDA_CHECK(cudaGetLastError());
-      note_launch();
-    });
+    DevRun run{st};
+    run(RtGatherRows<R, W>{tmp, rhs.ptr, rhs.rs, rhs.cs, n, k, d_perm}, n, k);
+    run(RtScatterBack<R, W>{rhs.ptr, rhs.rs, rhs.cs, tmp, n, k}, n, k);
     FB_CUDA_CHECK(cudaStreamSynchronize(st));  // perm (host, pageable) and the pool buffers are released below
     ws_free(tmp);
     ws_free(d_perm);
@@ -219,12 +205,8 @@ void qr_reconstruct_t(cudaStream_t st, View<R> out, View<const R> Qb, View<const
   FB_ASSERT(out.nrows == m && out.ncols == n && Qb.ncols == size && Qc.nrows > 0 && Qc.ncols == size && Rm.nrows == size,
             "qr_reconstruct shape mismatch");
   if (m == 0 || n == 0) return;
-  over_column_chunks(n, [&](i64 c0, unsigned nc) {
-    rt_set_upper_trapezoid_kernel<R, K::W><<<dim3((unsigned)((m + 255) / 256), nc), 256, 0, st>>>(
-        out.ptr, out.rs, out.cs, m, n, Rm.ptr, Rm.rs, Rm.cs, size, c0);
-    FB_CUDA_CHECK(cudaGetLastError());
-    note_launch();
-  });
+  DevRun run{st};
+  run(RtSetUpperTrapezoid<R, K::W>{out.ptr, out.rs, out.cs, m, n, Rm.ptr, Rm.rs, Rm.cs, size}, m, n);
   if (size > 0) rt_hh_seq(st, Qb, Qc, out, false, Tag());
 }
 
