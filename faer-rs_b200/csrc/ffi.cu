@@ -78,55 +78,6 @@ void householder_seq_entry(FaerV0_24_MatRef basis, FaerV0_24_MatRef factor, Faer
   else apply_block_householder_sequence_on_the_left<T>(st, b.view<const T>(), f.view<const T>(), r.view<T>());
   finish_all(st, {&b, &f, &r});
 }
-// ---- reductions to condensed form (svd/bidiag.rs:47-256) ----
-template <class TD, class TS>
-void ffi_cast(cudaStream_t st, TD* dst, i64 drs, i64 dcs, const TS* src, i64 srs, i64 scs, i64 m, i64 n);  // defined below
-// The condensed-form kernels want a column-major matrix (row stride 1). Any other layout (a row-major or strided HOST view keeps
-// its layout in the device mirror; a device view is whatever the caller has) goes through a compact column-major copy.
-template <class T>
-struct ColMajorWork {
-  cudaStream_t st;
-  View<T> orig, work;
-  T* buf = nullptr;
-  ColMajorWork(cudaStream_t st_, View<T> v) : st(st_), orig(v), work(v) {
-    if (v.rs != 1 && v.nrows > 0 && v.ncols > 0) {
-      buf = (T*)ws_alloc((size_t)v.nrows * (size_t)v.ncols * sizeof(T));
-      ffi_cast<T, T>(st, buf, 1, v.nrows, v.ptr, v.rs, v.cs, v.nrows, v.ncols);
-      work = View<T>{buf, v.nrows, v.ncols, 1, v.nrows};
-    }
-  }
-  void finish() {
-    if (!buf) return;
-    ffi_cast<T, T>(st, orig.ptr, orig.rs, orig.cs, buf, 1, orig.nrows, orig.nrows, orig.ncols);
-    FB_CUDA_CHECK(cudaStreamSynchronize(st));
-    ws_free(buf);
-    buf = nullptr;
-  }
-};
-template <class T>
-void bidiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Hl, FaerV0_24_MatMut Hr) {
-  FB_ENTRY();
-  cudaStream_t st = current_stream();
-  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
-  StagedMat hl(Hl.ptr, (i64)Hl.nrows, (i64)Hl.ncols, (i64)Hl.row_stride, (i64)Hl.col_stride, sizeof(T), true, true, st);
-  StagedMat hr(Hr.ptr, (i64)Hr.nrows, (i64)Hr.ncols, (i64)Hr.row_stride, (i64)Hr.col_stride, sizeof(T), true, true, st);
-  ColMajorWork<T> w(st, a.view<T>());
-  bidiag_in_place<T>(st, w.work, hl.view<T>(), hr.view<T>());
-  w.finish();
-  finish_all(st, {&a, &hl, &hr});
-}
-// evd/tridiag.rs:274-529
-template <class T>
-void tridiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
-  FB_ENTRY();
-  cudaStream_t st = current_stream();
-  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
-  StagedMat h(H.ptr, (i64)H.nrows, (i64)H.ncols, (i64)H.row_stride, (i64)H.col_stride, sizeof(T), true, true, st);
-  ColMajorWork<T> w(st, a.view<T>());
-  tridiag_in_place<T>(st, w.work, h.view<T>());
-  w.finish();
-  finish_all(st, {&a, &h});
-}
 // ---- solves on the QR factors (qr/no_pivoting/solve.rs) ----
 // mode 0: solve_lstsq_in_place_with_conj (solve.rs:38-76): rhs <- Q^H rhs, then R[..size, ..] x = rhs[..size, ..]
 // mode 1: solve_in_place_with_conj (solve.rs:96-119): the same on a square factorization
@@ -1513,15 +1464,6 @@ long long faer_b200_dist_qr_factor_in_place_f32(void* A_local, size_t ld, size_t
   return dist_qr_f32((float*)A_local, (i64)ld, (i64)nrows, (i64)ncols, (i64)block_size, (float*)Q_coeff, flags);
 }
 
-void faer_b200_bidiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) {
-  bidiag_entry<double>(A, H_left, H_right);
-}
-void faer_b200_bidiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) {
-  bidiag_entry<float>(A, H_left, H_right);
-}
-
-void faer_b200_tridiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<double>(A, householder); }
-void faer_b200_tridiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<float>(A, householder); }
 
 void faer_b200_spicy_matmul_f64(FaerV0_24_MatMut C, FaerV0_24_Block C_block, const unsigned long long* row_idx, size_t nrow_idx,
                                 const unsigned long long* col_idx, size_t ncol_idx, FaerV0_24_Accum accum, FaerV0_24_MatRef A,

@@ -4,6 +4,7 @@
 // violations, host buffers staged, device buffers used in place). Kept apart from ffi.cu so that this unit, runtime.cu and the
 // three drivers also build for the host (tools/emul/ffi_types_host.cpp: the staging layer and the drivers end to end on the CPU).
 #include "ffi_common.cuh"
+#include "flat_map.cuh"
 #include "gemm_f32.cuh"
 #include "runtime.cuh"
 #include "tensor_ops.cuh"
@@ -213,9 +214,81 @@ void ldlt_recon_entry_t(FaerV0_24_MatMut A, FaerV0_24_MatRef L, FaerV0_24_VecRef
   finish_all(st, {&a, &l});
 }
 
+// ---- reductions to condensed form as extension entry points (svd/bidiag.rs:47-256, evd/tridiag.rs:274-529) ----
+// The condensed-form kernels want a column-major matrix (row stride 1). Any other layout (a row-major or strided HOST view keeps
+// its layout in the device mirror; a device view is whatever the caller has) goes through a compact column-major copy.
+#if defined(__CUDACC__)
+#define FT_HD __host__ __device__ __forceinline__
+#else
+#define FT_HD inline
+#endif
+template <class T>
+struct CopyStrided {
+  T* dst; i64 drs, dcs; const T* src; i64 srs, scs, m, n;
+  FT_HD void operator()(i64 i, i64 j) const {
+    if (i < m && j < n) dst[i * drs + j * dcs] = src[i * srs + j * scs];
+  }
+};
+template <class T>
+struct ColMajorWork {
+  cudaStream_t st;
+  View<T> orig, work;
+  T* buf = nullptr;
+  ColMajorWork(cudaStream_t st_, View<T> v) : st(st_), orig(v), work(v) {
+    if (v.rs != 1 && v.nrows > 0 && v.ncols > 0) {
+      buf = (T*)ws_alloc((size_t)v.nrows * (size_t)v.ncols * sizeof(T));
+      DevRun run{st};
+      run(CopyStrided<T>{buf, 1, v.nrows, v.ptr, v.rs, v.cs, v.nrows, v.ncols}, v.nrows, v.ncols);
+      work = View<T>{buf, v.nrows, v.ncols, 1, v.nrows};
+    }
+  }
+  void finish() {
+    if (!buf) return;
+    DevRun run{st};
+    run(CopyStrided<T>{orig.ptr, orig.rs, orig.cs, buf, 1, orig.nrows, orig.nrows, orig.ncols}, orig.nrows, orig.ncols);
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    ws_free(buf);
+    buf = nullptr;
+  }
+};
+template <class T>
+void bidiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut Hl, FaerV0_24_MatMut Hr) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
+  StagedMat hl(Hl.ptr, (i64)Hl.nrows, (i64)Hl.ncols, (i64)Hl.row_stride, (i64)Hl.col_stride, sizeof(T), true, true, st);
+  StagedMat hr(Hr.ptr, (i64)Hr.nrows, (i64)Hr.ncols, (i64)Hr.row_stride, (i64)Hr.col_stride, sizeof(T), true, true, st);
+  ColMajorWork<T> w(st, a.view<T>());
+  bidiag_in_place<T>(st, w.work, hl.view<T>(), hr.view<T>());
+  w.finish();
+  finish_all(st, {&a, &hl, &hr});
+}
+template <class T>
+void tridiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, sizeof(T), true, true, st);
+  StagedMat h(H.ptr, (i64)H.nrows, (i64)H.ncols, (i64)H.row_stride, (i64)H.col_stride, sizeof(T), true, true, st);
+  ColMajorWork<T> w(st, a.view<T>());
+  tridiag_in_place<T>(st, w.work, h.view<T>());
+  w.finish();
+  finish_all(st, {&a, &h});
+}
+
 }  // namespace
 
 extern "C" {
+
+// ---- extensions: reductions to condensed form ----
+void faer_b200_bidiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) {
+  bidiag_entry<double>(A, H_left, H_right);
+}
+void faer_b200_bidiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) {
+  bidiag_entry<float>(A, H_left, H_right);
+}
+
+void faer_b200_tridiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<double>(A, householder); }
+void faer_b200_tridiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<float>(A, householder); }
 
 // ---- complex `svd` / `self_adjoint_evd` (cplx_condensed.cu: c32 computes in c64) ----
 #define FB_SVD_EVD_CPLX_FFI(SUF, R)                                                                                             \

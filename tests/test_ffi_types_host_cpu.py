@@ -49,6 +49,13 @@ def hostlib(tmp_path_factory, fb, oracle):
             n = d.shape[0]
             u, s, vt = np.linalg.svd(np.diag(d[:, 0]) + np.diag(e[:n - 1, 0], 1))
             S[:, 0] = s; UB[...] = u; VB[...] = vt.T; c.ret = 1
+        elif c.op == 6:
+            A, Hl, Hr = view(c.m[0]), view(c.m[1]), view(c.m[2])
+            hl, hr = oracle.bidiag(A, Hl.shape[0], Hr.shape[0])
+            Hl[...] = hl; Hr[...] = hr
+        elif c.op == 7:
+            A, H = view(c.m[0]), view(c.m[1])
+            H[...] = oracle.tridiag(A, H.shape[0])
 
     cb = CB(callback)
     lib.drivers_set_callback(cb)
@@ -80,6 +87,9 @@ def hostlib(tmp_path_factory, fb, oracle):
         g(f"ldlt_factor_in_place_{suf}").argtypes = [MatMut, capi.LdltRegularization, P, MemAlloc, capi.LdltParams]
         g(f"ldlt_factor_in_place_{suf}").restype = capi.LdltStatus
         g(f"ldlt_solve_in_place_{suf}").argtypes = [MatRef, VecMut, C.c_int, MatMut, P, MemAlloc]; g(f"ldlt_solve_in_place_{suf}").restype = None
+    for suf in ("f64", "f32"):
+        getattr(lib, f"faer_b200_bidiag_in_place_{suf}").argtypes = [MatMut, MatMut, MatMut]; getattr(lib, f"faer_b200_bidiag_in_place_{suf}").restype = None
+        getattr(lib, f"faer_b200_tridiag_in_place_{suf}").argtypes = [MatMut, MatMut]; getattr(lib, f"faer_b200_tridiag_in_place_{suf}").restype = None
     yield lib
     assert lib.drivers_guard_errors() == 0 and lib.drivers_live_blocks() == 0
 
@@ -163,3 +173,10 @@ def test_cplx_svd_evd_through_the_abi(host_fb):
         T.test_cplx_self_adjoint_evd(host_fb, None, dtype)
     T.test_cplx_non_finite_input_is_no_convergence(host_fb, None)
     T.test_cplx_solvers_svd_and_eigen(host_fb, None)
+
+
+def test_condensed_extension_layouts_through_the_abi(host_fb):
+    T = importlib.import_module("test_gpu_zzzzzzzzz_condensed_layouts")
+    for dtype in (np.float64, np.float32):
+        T.test_bidiag_row_major_and_strided_host_views(host_fb, None, dtype)
+        T.test_tridiag_row_major_and_strided_host_views(host_fb, None, dtype)

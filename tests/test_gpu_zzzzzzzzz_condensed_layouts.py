@@ -21,7 +21,7 @@ def test_bidiag_row_major_and_strided_host_views(fb, cuda_dev, dtype):
         A = rng.standard_normal((m, n)).astype(dtype)
         ref = np.asfortranarray(A); Hl0 = np.zeros((bl, n), dtype=dtype, order="F"); Hr0 = np.zeros((br, n - 1), dtype=dtype, order="F")
         la.bidiag_in_place(ref, Hl0, Hr0)
-        rm = np.ascontiguousarray(A); Hl = np.zeros_like(Hl0); Hr = np.zeros_like(Hr0)
+        rm = np.array(A, order="C", copy=True); Hl = np.zeros_like(Hl0); Hr = np.zeros_like(Hr0)
         la.bidiag_in_place(rm, Hl, Hr)
         sc = max(m, n) * max(1.0, float(np.abs(A).max()))
         assert same(rm, ref, dtype, sc) and same(Hl, Hl0, dtype, sc) and same(Hr, Hr0, dtype, sc), (m, n)
@@ -43,7 +43,7 @@ def test_tridiag_row_major_and_strided_host_views(fb, cuda_dev, dtype):
         ref = np.asfortranarray(A); H0 = np.zeros((b, n - 1), dtype=dtype, order="F")
         la.tridiag_in_place(ref, H0)
         assert np.all(ref[np.triu_indices(n, 1)] == 123.0)
-        rm = np.ascontiguousarray(A); H = np.zeros_like(H0)
+        rm = np.array(A, order="C", copy=True); H = np.zeros_like(H0)
         la.tridiag_in_place(rm, H)
         sc = n * max(1.0, float(np.abs(A).max()))
         assert same(rm, ref, dtype, sc) and same(H, H0, dtype, sc), n

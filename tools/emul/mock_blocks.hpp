@@ -102,6 +102,27 @@ bool bidiag_svd_vectors_f64(cudaStream_t, const double* d, const double* e, i64 
   g_cb(&c);
   return c.ret != 0;
 }
+// the HBM-bound reductions of bidiag.cu / tridiag.cu: op 6 / 7
+template <class T>
+void bidiag_in_place(cudaStream_t, View<T> A, View<T> Hl, View<T> Hr) {
+  FB_ASSERT(A.rs == 1, "bidiag_in_place: column-major (row stride 1) matrix required");  // the kernels' own precondition
+  MockCall c{};
+  c.op = 6;
+  c.m[0] = mm(A, false); c.m[1] = mm(Hl, false); c.m[2] = mm(Hr, false);
+  g_cb(&c);
+}
+template <class T>
+void tridiag_in_place(cudaStream_t, View<T> A, View<T> H) {
+  FB_ASSERT(A.rs == 1, "tridiag_in_place: column-major (row stride 1) matrix required");
+  MockCall c{};
+  c.op = 7;
+  c.m[0] = mm(A, false); c.m[1] = mm(H, false);
+  g_cb(&c);
+}
+template void bidiag_in_place<double>(cudaStream_t, View<double>, View<double>, View<double>);
+template void bidiag_in_place<float>(cudaStream_t, View<float>, View<float>, View<float>);
+template void tridiag_in_place<double>(cudaStream_t, View<double>, View<double>);
+template void tridiag_in_place<float>(cudaStream_t, View<float>, View<float>);
 template <class T>
 bool device_all_finite(cudaStream_t, const T* x, i64 n) {
   for (i64 i = 0; i < n; ++i)
