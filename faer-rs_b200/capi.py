@@ -250,6 +250,10 @@ def load() -> C.CDLL:
         f.argtypes = [MatRef, MatMut, VecMut, P, MemAlloc, SelfAdjointEvdParams]
         f.restype = EvdStatus
     for suf in ("f64", "f32", "c64", "c32"):
+        for name in ("inverse_triangular_lower", "inverse_triangular_upper", "inverse_unit_triangular_lower", "inverse_unit_triangular_upper"):
+            f = getattr(lib, f"libfaer_v0_23_{name}_in_place_{suf}")
+            f.argtypes = [MatMut, MatRef, P]
+            f.restype = None
         for name in ("llt_reconstruct", "llt_inverse"):
             f = getattr(lib, f"libfaer_v0_23_{name}_scratch_{suf}")
             f.argtypes = [C.c_size_t, P]

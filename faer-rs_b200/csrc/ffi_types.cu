@@ -275,6 +275,21 @@ void tridiag_entry(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
   finish_all(st, {&a, &h});
 }
 
+// ---- triangular inverses (triangular_inverse.rs; faer-ffi/src/lib.rs:938-980) ----
+template <class R, bool CX>
+void inverse_triangular_entry_t(FaerV0_24_MatMut dst, FaerV0_24_MatRef src, bool lower, bool unit) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t es = (CX ? 2 : 1) * sizeof(R);
+  FB_ASSERT(dst.nrows == dst.ncols && src.nrows == dst.nrows && src.ncols == dst.ncols, "inverse_triangular shape mismatch");
+  if (dst.nrows == 0) return;
+  // only the triangle is written: the rest of dst must survive the round trip
+  StagedMat d(dst.ptr, (i64)dst.nrows, (i64)dst.ncols, (i64)dst.row_stride, (i64)dst.col_stride, es, true, true, st);
+  StagedMat s(src.ptr, (i64)src.nrows, (i64)src.ncols, (i64)src.row_stride, (i64)src.col_stride, es, true, false, st);
+  inverse_triangular_t<R, CX>(st, d.view<R>(), s.view<const R>(), lower, unit);
+  finish_all(st, {&d, &s});
+}
+
 }  // namespace
 
 extern "C" {
@@ -449,5 +464,29 @@ FB_LDLT_RI_FFI(c64, double, true, 2 * sizeof(double))
 FB_LDLT_RI_FFI(c32, float, true, 2 * sizeof(float))
 #undef FB_LDLT_FS_FFI
 #undef FB_LDLT_RI_FFI
+
+// ---- triangular inverses, every dtype ----
+#define FB_TRI_INV_FFI(SUF, R, CX)                                                                                              \
+  void libfaer_v0_23_inverse_triangular_lower_in_place_##SUF(FaerV0_24_MatMut L_inv, FaerV0_24_MatRef L, FaerV0_24_Par par) {    \
+    (void)par;                                                                                                                  \
+    inverse_triangular_entry_t<R, CX>(L_inv, L, true, false);                                                                   \
+  }                                                                                                                             \
+  void libfaer_v0_23_inverse_triangular_upper_in_place_##SUF(FaerV0_24_MatMut L_inv, FaerV0_24_MatRef L, FaerV0_24_Par par) {    \
+    (void)par;                                                                                                                  \
+    inverse_triangular_entry_t<R, CX>(L_inv, L, false, false);                                                                  \
+  }                                                                                                                             \
+  void libfaer_v0_23_inverse_unit_triangular_lower_in_place_##SUF(FaerV0_24_MatMut L_inv, FaerV0_24_MatRef L, FaerV0_24_Par par) { \
+    (void)par;                                                                                                                  \
+    inverse_triangular_entry_t<R, CX>(L_inv, L, true, true);                                                                    \
+  }                                                                                                                             \
+  void libfaer_v0_23_inverse_unit_triangular_upper_in_place_##SUF(FaerV0_24_MatMut L_inv, FaerV0_24_MatRef L, FaerV0_24_Par par) { \
+    (void)par;                                                                                                                  \
+    inverse_triangular_entry_t<R, CX>(L_inv, L, false, true);                                                                   \
+  }
+FB_TRI_INV_FFI(f64, double, false)
+FB_TRI_INV_FFI(f32, float, false)
+FB_TRI_INV_FFI(c64, double, true)
+FB_TRI_INV_FFI(c32, float, true)
+#undef FB_TRI_INV_FFI
 
 }  // extern "C"

@@ -75,6 +75,21 @@ struct RtScatterBack {
   }
 };
 
+// dst(i, j) = src(i, j) on the triangle `lower` selects — diagonal included unless `unit` — and nothing elsewhere
+template <class R, int W>
+struct RtCopyTriangle {
+  R* dst; i64 d_rs, d_cs; const R* src; i64 s_rs, s_cs, n; int lower, unit;
+  RT_HD void operator()(i64 i, i64 j) const {
+    if (i >= n || j >= n) return;
+    const bool in = lower ? (unit ? i > j : i >= j) : (unit ? i < j : i <= j);
+    if (!in) return;
+    const R* q = src + W * (i * s_rs + j * s_cs);
+    R* p = dst + W * (i * d_rs + j * d_cs);
+    p[0] = q[0];
+    if (W == 2) p[W - 1] = q[W - 1];
+  }
+};
+
 template <class R, bool CX>
 struct Kind {
   static constexpr int W = CX ? 2 : 1;
@@ -222,6 +237,32 @@ void qr_inverse_t(cudaStream_t st, View<R> out, View<const R> Qb, View<const R> 
   rt_hh_seq(st, Qb, Qc, out, true, Tag());     // Q^H
   rt_solve_upper(st, Rm, false, out, Tag());  // R^-1 Q^H
 }
+
+// linalg::triangular_inverse::invert_[unit_]{lower,upper}_triangular (triangular_inverse.rs): dst(triangle) <- src(triangle)^-1;
+// only the triangle is written (the diagonal too unless `unit`). Here as the triangular solve applied to the identity.
+inline void rt_solve_lower(cudaStream_t st, VCD t, bool unit, VD rhs, std::false_type) { solve_lower_triangular_in_place_f64(st, t, unit, rhs); }
+inline void rt_solve_upper(cudaStream_t st, VCD t, bool unit, VD rhs, std::false_type) { solve_upper_triangular_in_place_f64(st, t, unit, rhs); }
+template <class R, bool CX>
+void inverse_triangular_t(cudaStream_t st, View<R> dst, View<const R> src, bool lower, bool unit) {
+  typedef Kind<R, CX> K;
+  typedef std::integral_constant<bool, CX> Tag;
+  const i64 n = dst.nrows;
+  FB_ASSERT(dst.ncols == n && src.nrows == n && src.ncols == n, "inverse_triangular shape mismatch");
+  if (n == 0) return;
+  R* buf = (R*)ws_alloc((size_t)n * (size_t)n * K::W * sizeof(R));
+  View<R> X{buf, n, n, 1, n};
+  K::set_identity(st, X);
+  if (lower) rt_solve_lower(st, src, unit, X, Tag());
+  else rt_solve_upper(st, src, unit, X, Tag());
+  DevRun run{st};
+  run(RtCopyTriangle<R, K::W>{dst.ptr, dst.rs, dst.cs, buf, 1, n, n, lower ? 1 : 0, unit ? 1 : 0}, n, n);
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  ws_free(buf);
+}
+template void inverse_triangular_t<double, false>(cudaStream_t, View<double>, View<const double>, bool, bool);
+template void inverse_triangular_t<float, false>(cudaStream_t, View<float>, View<const float>, bool, bool);
+template void inverse_triangular_t<double, true>(cudaStream_t, View<double>, View<const double>, bool, bool);
+template void inverse_triangular_t<float, true>(cudaStream_t, View<float>, View<const float>, bool, bool);
 
 #define FB_RECON_INST(R, CX)                                                                                                     \
   template void llt_reconstruct_t<R, CX>(cudaStream_t, View<R>, View<const R>);                                                  \

@@ -105,6 +105,9 @@ void qr_reconstruct_t(cudaStream_t st, View<R> out, View<const R> Q_basis, View<
 template <class R, bool CX>
 void qr_inverse_t(cudaStream_t st, View<R> out, View<const R> Q_basis, View<const R> Q_coeff, View<const R> Rm);
 
+// dst(triangle) <- src(triangle)^-1 (triangular_inverse.rs), every scalar kind; only the triangle is written (not the diagonal if unit)
+template <class R, bool CX>
+void inverse_triangular_t(cudaStream_t st, View<R> dst, View<const R> src, bool lower, bool unit);
 // ---- ldlt_types.cu: LDLT beyond the f64 factorization, over the scalar kind <R, complex?> (complex views in COMPLEX element units
 // on an R* base). Factor / solve: <float, false>, <double, true>, <float, true>; reconstruct / inverse: also <double, false>.
 // D: DEVICE pointer to T-typed entries `dstride` elements apart; d_signs: device int8[n] or null ----

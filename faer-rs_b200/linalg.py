@@ -436,6 +436,14 @@ def _same_suffix(*xs) -> str:
     return sufs.pop()
 
 
+def invert_triangular(dst, src, lower: bool, unit: bool = False, par=None) -> None:
+    """linalg::triangular_inverse::invert_[unit_]{lower,upper}_triangular (triangular_inverse.rs): the chosen triangle of dst <- the
+    inverse of the same triangle of src; nothing else of dst is written (not its diagonal for the unit variants)."""
+    suf = _same_suffix(dst, src)
+    name = f"inverse_{'unit_' if unit else ''}triangular_{'lower' if lower else 'upper'}_in_place"
+    getattr(capi.load(), f"libfaer_v0_23_{name}_{suf}")(capi.mat_mut(dst), capi.mat_ref(src), par or capi.par_default())
+
+
 def llt_reconstruct(out, L, par=None) -> None:
     """cholesky::llt::reconstruct (llt/reconstruct.rs:12-33): the LOWER triangle of out <- L L^H."""
     suf = _same_suffix(out, L)

@@ -261,6 +261,24 @@ struct FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_c64(size_t dim, e
 struct FaerV0_24_Layout libfaer_v0_23_self_adjoint_evd_scratch_c32(size_t dim, enum FaerV0_24_ComputeEigenvectors compute_U, struct FaerV0_24_Par par, struct FaerV0_24_SelfAdjointEvdParams params);
 struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_c64(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SelfAdjointEvdParams params);
 struct FaerV0_24_EvdStatus libfaer_v0_23_self_adjoint_evd_c32(struct FaerV0_24_MatRef A, struct FaerV0_24_MatMut U, struct FaerV0_24_VecMut S, struct FaerV0_24_Par par, struct FaerV0_24_MemAlloc mem, struct FaerV0_24_SelfAdjointEvdParams params);
+/* triangular inverses (faer.h:3080-3170; faer-ffi/src/lib.rs:938-980; linalg/triangular_inverse.rs): the triangle of L_inv <- the
+ * inverse of the triangle of L; nothing else of L_inv is written (not its diagonal for the unit variants). csrc/reconstruct_types.cu. */
+void libfaer_v0_23_inverse_triangular_lower_in_place_f64(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_triangular_lower_in_place_f32(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_triangular_lower_in_place_c64(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_triangular_lower_in_place_c32(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_triangular_upper_in_place_f64(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_triangular_upper_in_place_f32(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_triangular_upper_in_place_c64(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_triangular_upper_in_place_c32(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_unit_triangular_lower_in_place_f64(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_unit_triangular_lower_in_place_f32(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_unit_triangular_lower_in_place_c64(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_unit_triangular_lower_in_place_c32(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_unit_triangular_upper_in_place_f64(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_unit_triangular_upper_in_place_f32(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_unit_triangular_upper_in_place_c64(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
+void libfaer_v0_23_inverse_unit_triangular_upper_in_place_c32(struct FaerV0_24_MatMut L_inv, struct FaerV0_24_MatRef L, struct FaerV0_24_Par par);
 /* reconstruct / inverse on the factors ("next" row): lib.rs:1039-1075 (llt), 1661-1720 (qr), 2059-2124 (lu);
  * semantics: cholesky/llt/reconstruct.rs:12-33 and inverse.rs:10-39 (only the LOWER triangle of the output is written),
  * lu/partial_pivoting/reconstruct.rs and inverse.rs, qr/no_pivoting/reconstruct.rs:13-39 and inverse.rs. L / U may be the packed

@@ -87,6 +87,9 @@ def hostlib(tmp_path_factory, fb, oracle):
         g(f"ldlt_factor_in_place_{suf}").argtypes = [MatMut, capi.LdltRegularization, P, MemAlloc, capi.LdltParams]
         g(f"ldlt_factor_in_place_{suf}").restype = capi.LdltStatus
         g(f"ldlt_solve_in_place_{suf}").argtypes = [MatRef, VecMut, C.c_int, MatMut, P, MemAlloc]; g(f"ldlt_solve_in_place_{suf}").restype = None
+    for suf in ("f64", "f32", "c64", "c32"):
+        for name in ("inverse_triangular_lower", "inverse_triangular_upper", "inverse_unit_triangular_lower", "inverse_unit_triangular_upper"):
+            g(f"{name}_in_place_{suf}").argtypes = [MatMut, MatRef, P]; g(f"{name}_in_place_{suf}").restype = None
     for suf in ("f64", "f32"):
         getattr(lib, f"faer_b200_bidiag_in_place_{suf}").argtypes = [MatMut, MatMut, MatMut]; getattr(lib, f"faer_b200_bidiag_in_place_{suf}").restype = None
         getattr(lib, f"faer_b200_tridiag_in_place_{suf}").argtypes = [MatMut, MatMut]; getattr(lib, f"faer_b200_tridiag_in_place_{suf}").restype = None
@@ -180,3 +183,9 @@ def test_condensed_extension_layouts_through_the_abi(host_fb):
     for dtype in (np.float64, np.float32):
         T.test_bidiag_row_major_and_strided_host_views(host_fb, None, dtype)
         T.test_tridiag_row_major_and_strided_host_views(host_fb, None, dtype)
+
+
+def test_invert_triangular_through_the_abi(host_fb):
+    T = importlib.import_module("test_gpu_zzzzzzzzz_inverse_triangular")
+    for dtype in T.DTYPES:
+        T.test_invert_triangular(host_fb, None, dtype)
