@@ -1,4 +1,5 @@
-// extern "C" boundary: the symbols declared in include/faer_b200.h.
+// extern "C" boundary: the symbols declared in include/faer_b200.h (second translation unit: ffi_types.cu, the entry points whose
+// drivers are the flat-map files; helpers shared by both: ffi_common.cuh).
 // Each entry point mirrors the faer-ffi function of the same name (faer-ffi/src/lib.rs, cited per function in the
 // header): same argument order and meaning, by-value PODs, synchronous on return, abort() on precondition
 // violations. Host buffers are staged; device buffers are used in place.
@@ -631,7 +632,7 @@ void libfaer_v0_23_llt_solve_in_place_f32(FaerV0_24_MatRef L, FaerV0_24_Conj A_c
   finish_all(st, {&l, &r});
 }
 
-// ---- LDLT (no pivoting); DRAFT, see ldlt_f64.cu ----
+// ---- LDLT (no pivoting), f64: ldlt_f64.cu (the other dtypes, reconstruct and inverse: ffi_types.cu / ldlt_types.cu) ----
 FaerV0_24_LdltParams libfaer_v0_23_LdltParams_f64(void) {
   return FaerV0_24_LdltParams{64, 128};  // reference defaults: ldlt/factor.rs:705-714
 }
