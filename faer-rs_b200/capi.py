@@ -361,6 +361,10 @@ def load() -> C.CDLL:
         f = getattr(lib, f"faer_b200_tridiag_in_place_{suf}")
         f.argtypes = [MatMut, MatMut]
         f.restype = None
+    for suf in ("f64", "f32", "c64", "c32"):
+        f = getattr(lib, f"faer_b200_hessenberg_in_place_{suf}")
+        f.argtypes = [MatMut, MatMut]
+        f.restype = None
     lib.faer_b200_spicy_matmul_f64.argtypes = [MatMut, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, MatRef,
                                                MatRef, C.c_void_p, C.c_void_p]
     lib.faer_b200_spicy_matmul_f64.restype = None

@@ -188,6 +188,56 @@ bool svd_cx(cudaStream_t st, View<const TO> A_in, View<TO> U, TO* S, i64 sstride
   return ok;
 }
 
+// evd::hessenberg::hessenberg_in_place (evd/hessenberg.rs:549-567) as an extension (the reference does not export it through its C
+// ABI): A <- its upper Hessenberg form H = Q^H A Q in the entries (i, j) with i <= j + 1 and the reflectors of Q = H_0 ... H_{n-2} below
+// the subdiagonal; Hf (bs x (n - 1)) <- their T blocks (diag tau, V^H V above it inside each block), the layout the block-Householder
+// sequences take. Every dtype runs the c64 launch sequence of cplx_condensed_core.cuh (real input as (x, 0): stays exactly real).
+template <class TO, bool CX>
+void hessenberg_in_place_t(cudaStream_t st, View<TO> A, View<TO> Hf) {
+  const i64 n = A.nrows, bs = Hf.nrows, s = n > 0 ? n - 1 : 0;
+  FB_ASSERT(A.ncols == n && Hf.ncols == s && (s == 0 || bs > 0), "hessenberg_in_place: square A, householder factor bs x (n - 1)");
+  if (n == 0) return;
+  DevRun run{st};
+  cc::Cx* W = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
+  if (CX) {
+    void* owned = nullptr;
+    const View<const double> Ac = as_c64(st, View<const TO>{A.ptr, n, n, A.rs, A.cs}, &owned);
+    run(cc::CopyIn{Ac.ptr, Ac.rs, Ac.cs, W, n, n, n, 0}, n, n);
+    if (owned) {
+      FB_CUDA_CHECK(cudaStreamSynchronize(st));
+      ws_free(owned);
+    }
+  } else {
+    run(cc::RealToCx<TO>{A.ptr, A.rs, A.cs, W, n, n, n}, n, n);
+  }
+  DevWork work(n);
+  double* tau = (double*)ws_alloc((size_t)(n + 1) * sizeof(double));
+  FB_CUDA_CHECK(cudaMemsetAsync(tau, 0, (size_t)(n + 1) * sizeof(double), st));
+  cc::hessenberg_unblocked(run, W, n, n, tau, work.ws);
+  cc::Cx* Tf = nullptr;
+  if (s > 0) {
+    Tf = (cc::Cx*)ws_alloc((size_t)bs * (size_t)s * sizeof(cc::Cx));
+    FB_CUDA_CHECK(cudaMemsetAsync(Tf, 0, (size_t)bs * (size_t)s * sizeof(cc::Cx), st));
+    run(cc::BuildTBlocks{W + 1, n, n - 1, s, tau, Tf, bs, bs}, bs, s);
+  }
+  if (CX) {
+    run(cc::CopyOut<TO>{A.ptr, A.rs, A.cs, W, n, n, n}, n, n);
+    if (s > 0) run(cc::CopyOut<TO>{Hf.ptr, Hf.rs, Hf.cs, Tf, bs, bs, s}, bs, s);
+  } else {
+    run(cc::CxToReal<TO>{A.ptr, A.rs, A.cs, W, n, n, n}, n, n);
+    if (s > 0) run(cc::CxToReal<TO>{Hf.ptr, Hf.rs, Hf.cs, Tf, bs, bs, s}, bs, s);
+  }
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (Tf) ws_free(Tf);
+  ws_free(tau);
+  work.release();
+  ws_free(W);
+}
+template void hessenberg_in_place_t<double, false>(cudaStream_t, View<double>, View<double>);
+template void hessenberg_in_place_t<float, false>(cudaStream_t, View<float>, View<float>);
+template void hessenberg_in_place_t<double, true>(cudaStream_t, View<double>, View<double>);
+template void hessenberg_in_place_t<float, true>(cudaStream_t, View<float>, View<float>);
+
 template bool svd_cx<double>(cudaStream_t, View<const double>, View<double>, double*, i64, View<double>);
 template bool svd_cx<float>(cudaStream_t, View<const float>, View<float>, float*, i64, View<float>);
 template bool self_adjoint_evd_cx<double>(cudaStream_t, View<const double>, View<double>, double*, i64);

@@ -318,6 +318,44 @@ struct WidenC32 {
   }
 };
 
+// T blocks of the reflectors stored in the columns of V (m x s, unit-lower trapezoid, leading dimension ld): for block j0 = (c / bs) bs
+// the b x b upper-triangular T with diag = tau and T(a, c) = v_a^H v_c above it (upgrade_householder_factor, householder.rs:132-272),
+// written to Tf(a - j0, c) of the bs x s factor (column-major, leading dimension ldt). One thread per (a, c) with a <= c in one block.
+struct BuildTBlocks {
+  const Cx* V; i64 ld, m, s; const double* tau; Cx* Tf; i64 ldt, bs;
+  CC_HD void operator()(i64 r, i64 c) const {
+    if (c >= s || r >= bs) return;
+    const i64 j0 = (c / bs) * bs, a = j0 + r;
+    if (a > c) return;
+    if (a == c) { Tf[r + c * ldt] = cx(tau[c], 0.0); return; }
+    // v_a = [0.., 1 (row a), V(a+1.., a)], v_c likewise; the product runs over rows >= c
+    const Cx vac = V[c + a * ld];  // row c of v_a (c > a: an essential), times the implicit 1 of v_c
+    double ar = vac.re, ai = -vac.im;
+    for (i64 i = c + 1; i < m; ++i) {
+      const Cx x = V[i + a * ld], y = V[i + c * ld];
+      ar += fma(x.re, y.re, x.im * y.im);  // conj(x) * y
+      ai += fma(x.re, y.im, -x.im * y.re);
+    }
+    Tf[r + c * ldt] = cx(ar, ai);
+  }
+};
+// real view (any strides) -> compact complex, and back (the real dtypes run the complex sequences on (x, 0): every product with a
+// zero imaginary part stays exactly real)
+template <class TR>
+struct RealToCx {
+  const TR* A; i64 rs, cs; Cx* W; i64 ld, m, n;
+  CC_HD void operator()(i64 i, i64 j) const {
+    if (i < m && j < n) W[i + j * ld] = cx((double)A[i * rs + j * cs], 0.0);
+  }
+};
+template <class TR>
+struct CxToReal {
+  TR* A; i64 rs, cs; const Cx* W; i64 ld, m, n;
+  CC_HD void operator()(i64 i, i64 j) const {
+    if (i < m && j < n) A[i * rs + j * cs] = (TR)W[i + j * ld].re;
+  }
+};
+
 // workspace of the reductions (device pointers on the GPU, plain arrays in the host build)
 struct Work {
   Cx *v, *p, *w;       // max(m, n) entries each
@@ -362,6 +400,24 @@ void bidiag_unblocked(L& run, Cx* W, i64 ld, i64 m, i64 n, double* tl, double* t
     run(ScaleTail{r, ld, cols, ws.sc, ws.v, 1, ws.w}, cols, 1);                      //     v = conj([1, essential]), w = [1, essential]
     run(MatVec{W, ld, k + 1, k + 1, rows - 1, cols, ws.v, ws.sc, ws.p}, rows - 1, 1);  // (5) z = M conj(v) / tau
     run(Rank1{W, ld, k + 1, k + 1, rows - 1, cols, ws.p, ws.w, ws.sc}, rows - 1, cols);  // (6) M -= z v^T
+  }
+}
+
+// W: n x n general matrix (ld), tau: n - 1 entries. On return the upper Hessenberg form H = Q^H A Q is in the entries (i, j) with
+// i <= j + 1, reflector k (Q = H_0 H_1 ... H_{n-2}) below the subdiagonal of column k (evd/hessenberg.rs:549-567; the reference's
+// unblocked variant defers and fuses the updates, here every column applies its similarity transform at once).
+template <class L>
+void hessenberg_unblocked(L& run, Cx* W, i64 ld, i64 n, double* tau, const Work& ws) {
+  for (i64 k = 0; k + 1 < n; ++k) {
+    const i64 len = n - k - 1;
+    Cx* x = W + (k + 1) + k * ld;
+    run(NormPartial{x, 1, len, ws.part}, NP, 1);
+    run(HouseFinal{x, ws.part, tau + k, ws.sc}, 1, 1);
+    run(ScaleTail{x, 1, len, ws.sc, ws.w, 1, ws.v}, len, 1);                          // v = [1, essential], w = conj(v)
+    run(VecHMat{W, ld, k + 1, k + 1, len, len, ws.v, ws.sc, ws.p}, len, 1);           // y = v^H M / tau, M = W[k+1.., k+1..]
+    run(Rank1{W, ld, k + 1, k + 1, len, len, ws.v, ws.p, ws.sc}, len, len);           // M -= v y            (H M)
+    run(MatVec{W, ld, 0, k + 1, n, len, ws.v, ws.sc, ws.p}, n, 1);                    // z = N v / tau, N = W[.., k+1..]
+    run(Rank1{W, ld, 0, k + 1, n, len, ws.p, ws.w, ws.sc}, n, len);                   // N -= z v^H          (N H)
   }
 }
 

@@ -290,6 +290,19 @@ void inverse_triangular_entry_t(FaerV0_24_MatMut dst, FaerV0_24_MatRef src, bool
   finish_all(st, {&d, &s});
 }
 
+// ---- Hessenberg reduction (extension; evd/hessenberg.rs:549-567) ----
+template <class R, bool CX>
+void hessenberg_entry_t(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t es = (CX ? 2 : 1) * sizeof(R);
+  FB_ASSERT(A.nrows == A.ncols && H.ncols == (A.nrows > 0 ? A.nrows - 1 : 0), "hessenberg_in_place: square A, householder factor bs x (n - 1)");
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, es, true, true, st);
+  StagedMat h(H.ptr, (i64)H.nrows, (i64)H.ncols, (i64)H.row_stride, (i64)H.col_stride, es, false, true, st);
+  hessenberg_in_place_t<R, CX>(st, a.view<R>(), h.view<R>());
+  finish_all(st, {&a, &h});
+}
+
 }  // namespace
 
 extern "C" {
@@ -488,5 +501,14 @@ FB_TRI_INV_FFI(f32, float, false)
 FB_TRI_INV_FFI(c64, double, true)
 FB_TRI_INV_FFI(c32, float, true)
 #undef FB_TRI_INV_FFI
+
+FaerV0_24_HessenbergParams libfaer_v0_23_HessenbergParams_f64(void) { return FaerV0_24_HessenbergParams{192 * 256, 256 * 256}; }
+FaerV0_24_HessenbergParams libfaer_v0_23_HessenbergParams_f32(void) { return FaerV0_24_HessenbergParams{192 * 256, 256 * 256}; }
+FaerV0_24_HessenbergParams libfaer_v0_23_HessenbergParams_c64(void) { return FaerV0_24_HessenbergParams{192 * 256, 256 * 256}; }
+FaerV0_24_HessenbergParams libfaer_v0_23_HessenbergParams_c32(void) { return FaerV0_24_HessenbergParams{192 * 256, 256 * 256}; }
+void faer_b200_hessenberg_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { hessenberg_entry_t<double, false>(A, householder); }
+void faer_b200_hessenberg_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { hessenberg_entry_t<float, false>(A, householder); }
+void faer_b200_hessenberg_in_place_c64(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { hessenberg_entry_t<double, true>(A, householder); }
+void faer_b200_hessenberg_in_place_c32(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { hessenberg_entry_t<float, true>(A, householder); }
 
 }  // extern "C"

@@ -83,6 +83,10 @@ template <class TO>
 bool svd_cx(cudaStream_t st, View<const TO> A, View<TO> U, TO* S, i64 sstride, View<TO> V);
 template <class TO>
 bool self_adjoint_evd_cx(cudaStream_t st, View<const TO> A, View<TO> U, TO* S, i64 sstride);
+// A <- upper Hessenberg form + reflectors, Hf (bs x (n - 1)) <- T blocks (evd/hessenberg.rs:549-567); <TO, complex?>: <double, false> f64,
+// <float, false> f32, <double, true> c64, <float, true> c32 (complex views in complex units)
+template <class TO, bool CX>
+void hessenberg_in_place_t(cudaStream_t st, View<TO> A, View<TO> Hf);
 // ---- tridiag_dc.cu: divide-and-conquer eigensolver of a symmetric tridiagonal matrix (device arrays) ----
 bool tridiag_dc_f64(cudaStream_t st, const double* d, const double* e, i64 n, double* lam, double* Q, i64 ldq);
 // ---- tridiag.cu ----

@@ -668,6 +668,14 @@ def bidiag_in_place(A, H_left, H_right, par=None, params=None) -> None:
     getattr(lib, f"faer_b200_bidiag_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(H_left), capi.mat_mut(H_right))
 
 
+def hessenberg_in_place(A, householder, par=None, params=None) -> None:
+    """evd::hessenberg::hessenberg_in_place (evd/hessenberg.rs:549-567): A = Q H Q^H for a general square A; H ends up in the entries
+    (i, j) with i <= j + 1, the reflectors of Q below the subdiagonal, their T blocks in `householder` (b x (n - 1)).
+    f64 / f32 / c64 / c32; functional (unblocked)."""
+    suf = _same_suffix(A, householder)
+    getattr(capi.load(), f"faer_b200_hessenberg_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(householder))
+
+
 def tridiag_in_place(A, householder, par=None, params=None) -> None:
     """evd::tridiag::tridiag_in_place (evd/tridiag.rs:274-529): A = Q T Q^H for a self-adjoint A (only the lower triangle
     is read / written), f64 or f32. T ends up on A's diagonal / subdiagonal, the reflectors below the subdiagonal, their

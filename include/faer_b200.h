@@ -234,6 +234,16 @@ struct FaerV0_24_SvdStatus libfaer_v0_23_svd_f32(struct FaerV0_24_MatRef A, stru
 /* Self-adjoint EVD: lib.rs:2367-2400, faer.h:696, 720, 6064, 6098; semantics faer/src/linalg/evd/mod.rs:270-353 (the LOWER triangle
  * of A is read; eigenvalues in nondecreasing order). U passed with ncols == 0: eigenvalues only (csrc/evd.cu); otherwise the
  * eigenvectors too (csrc/svd_vectors.cu, tridiag_dc.cu). Any n. Non-finite input: NoConvergence. */
+/* evd/hessenberg.rs:17-25 (faer.h:110-113, 600): parameters of the Hessenberg reduction (the reduction itself is reached in the
+ * reference through the general EVD; here as the extension faer_b200_hessenberg_in_place_<T> below) */
+typedef struct FaerV0_24_HessenbergParams {
+  size_t par_threshold;
+  size_t blocking_threshold;
+} FaerV0_24_HessenbergParams;
+struct FaerV0_24_HessenbergParams libfaer_v0_23_HessenbergParams_f64(void);
+struct FaerV0_24_HessenbergParams libfaer_v0_23_HessenbergParams_f32(void);
+struct FaerV0_24_HessenbergParams libfaer_v0_23_HessenbergParams_c64(void);
+struct FaerV0_24_HessenbergParams libfaer_v0_23_HessenbergParams_c32(void);
 struct FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_f64(void);
 struct FaerV0_24_TridiagParams libfaer_v0_23_TridiagParams_f32(void);
 struct FaerV0_24_SelfAdjointEvdParams libfaer_v0_23_SelfAdjointEvdParams_f64(void);
@@ -593,12 +603,19 @@ long long faer_b200_dist_qr_factor_in_place_f32(void *A_local, size_t ld, size_t
  * right reflectors right of the superdiagonal with H_right (br x (ncols-1)). Device matrices must be column-major. */
 void faer_b200_bidiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
 void faer_b200_bidiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
-/* ---- reduction to tridiagonal form A = Q T Q^H of a self-adjoint matrix (lower triangle read and written; n <= 8192 in
- * this version). Reached in the reference through libfaer_v0_23_self_adjoint_evd_* (faer-ffi/src/lib.rs:2382-2400 ->
+/* ---- reduction to tridiagonal form A = Q T Q^H of a self-adjoint matrix (lower triangle read and written). Reached in the reference through libfaer_v0_23_self_adjoint_evd_* (faer-ffi/src/lib.rs:2382-2400 ->
  * faer/src/linalg/evd/mod.rs); mirrors faer::linalg::evd::tridiag::tridiag_in_place (faer/src/linalg/evd/tridiag.rs:274-280):
  * T on A's diagonal / subdiagonal, reflectors below the subdiagonal, `householder` (b x (n-1)) holds their T blocks. */
 void faer_b200_tridiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
 void faer_b200_tridiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+/* ---- reduction to upper Hessenberg form A = Q H Q^H (general square matrix). faer-ffi exports only the parameter structs of this
+ * stage (FaerV0_24_HessenbergParams, faer.h:110-113); the entry mirrors faer::linalg::evd::hessenberg::hessenberg_in_place (faer/src/linalg/evd/hessenberg.rs:549-567):
+ * H in the entries (i, j) with i <= j + 1, the reflectors of Q = H_0 ... H_{n-2} below the subdiagonal, `householder` (b x (n-1))
+ * holds their T blocks. Functional (the unblocked flat-map sequence of csrc/cplx_condensed_core.cuh; real dtypes run it on (x, 0)). */
+void faer_b200_hessenberg_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+void faer_b200_hessenberg_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+void faer_b200_hessenberg_in_place_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+void faer_b200_hessenberg_in_place_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
 /* "spicy" matmul: C[row_idx[i], col_idx[j]] (+)= alpha * (A diag(D) B)[i, j] for the (i, j) that C_block keeps (block structure
  * of the PRODUCT). Mirrors faer::linalg::matmul::internal::spicy_matmul (faer/src/linalg/matmul/internal/mod.rs:45-58), which
  * faer-ffi does not export (it is an internal of LDLT and of the sparse supernodal Cholesky): row_idx / col_idx may be NULL

@@ -170,3 +170,35 @@ def svd(A, full=False):
     if transpose:
         U, V = V, U
     return S, U, V
+
+
+def hessenberg_unblocked(A):
+    """Step list of cc::hessenberg_unblocked: H = Q^H A Q, Q = H_0 ... H_{n-2}; reflector k below the subdiagonal of column k."""
+    W = np.array(A, dtype=np.complex128)
+    n = W.shape[0]
+    taus = np.full(max(n - 1, 0), np.inf)
+    for k in range(n - 1):
+        beta, ess, tau = make_householder(W[k + 1:, k])
+        W[k + 1, k] = beta
+        W[k + 2:, k] = ess
+        taus[k] = tau
+        if not np.isfinite(tau):
+            continue
+        v = np.concatenate([[1.0], ess])
+        M = W[k + 1:, k + 1:]
+        M -= np.outer(v, (v.conj() @ M) / tau)
+        N = W[:, k + 1:]
+        N -= np.outer((N @ v) / tau, v.conj())
+    return W, taus
+
+
+def t_blocks(V, taus, bs):
+    """The bs x s factor of T blocks (diag tau, strict upper part of V^H V inside each block) — householder.rs:132-272."""
+    m, s = V.shape
+    Tf = np.zeros((bs, s), dtype=np.complex128)
+    for j0 in range(0, s, bs):
+        b = min(bs, s - j0)
+        Vb = np.tril(V[j0:, j0:j0 + b], -1) + np.eye(m - j0, b)
+        G = Vb.conj().T @ Vb
+        Tf[:b, j0:j0 + b] = np.triu(G, 1) + np.diag(taus[j0:j0 + b])
+    return Tf

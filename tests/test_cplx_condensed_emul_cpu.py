@@ -245,3 +245,34 @@ def test_non_finite_input_reaches_the_condensed_form(emul):
         G = crandn(rng, (25, 25)); H = np.asfortranarray(G + G.conj().T); H[9, 2] = bad
         _, _, d, e, _, _ = run_tridiag(emul, H)
         assert not (np.all(np.isfinite(d)) and np.all(np.isfinite(e)))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 8, 16, 45, 130])
+def test_hessenberg_emulation(emul, oracle, n):
+    """evd/hessenberg.rs tests (test_hessenberg_cplx: n in {1..16}, block size 3): the emulated launch sequence against the model,
+    and the reference's own check — Q^H A Q through the block-Householder sequences with the T blocks equals the Hessenberg part."""
+    emul.cc_emul_hessenberg.argtypes = [P, I64, I64, I64, P, P, P, I64, C.c_int]
+    rng = np.random.default_rng(1800 + n)
+    A = crandn(rng, (n, n))
+    bs = 3
+    outs = []
+    for rev in (0, 1):
+        W = np.zeros((n, n), dtype=np.complex128, order="F"); tau = np.zeros(max(n - 1, 1)); Tf = np.zeros((bs, max(n - 1, 1)), dtype=np.complex128, order="F")
+        rs, cs = strides(A)
+        emul.cc_emul_hessenberg(A.ctypes.data, rs, cs, n, W.ctypes.data, tau.ctypes.data, Tf.ctypes.data, bs, rev)
+        outs.append((W, tau[:n - 1], Tf[:, :n - 1]))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    W, tau, Tf = outs[0]
+    Wm, taum = cm.hessenberg_unblocked(A)
+    scale = np.abs(A).max() * n
+    assert np.abs(np.triu(W, -1) - np.triu(Wm, -1)).max() <= 4096 * U * scale
+    assert np.abs(np.tril(W, -2) - np.tril(Wm, -2)).max(initial=0.0) <= 4096 * n * U
+    if n > 1:
+        assert np.allclose(tau[np.isfinite(tau)], taum[np.isfinite(taum)], rtol=4096 * n * U) and np.array_equal(np.isfinite(tau), np.isfinite(taum))
+        V = np.asfortranarray(W[1:, :n - 1])
+        assert np.allclose(Tf, cm.t_blocks(V, tau, bs), rtol=1e-12, atol=1e-12 * n)
+        B = A.copy(order="F")
+        oracle.apply_q_transpose_sequence(V, np.asfortranarray(Tf), B[1:, :], conj_lhs=True)          # Q^H A
+        oracle.apply_q_transpose_sequence(V, np.asfortranarray(Tf), B.T[1:, :], conj_lhs=False)       # (Q^H A) Q
+        assert np.abs(B - np.triu(W, -1)).max() <= 256 * n * U * np.abs(A).max()

@@ -90,6 +90,8 @@ def hostlib(tmp_path_factory, fb, oracle):
     for suf in ("f64", "f32", "c64", "c32"):
         for name in ("inverse_triangular_lower", "inverse_triangular_upper", "inverse_unit_triangular_lower", "inverse_unit_triangular_upper"):
             g(f"{name}_in_place_{suf}").argtypes = [MatMut, MatRef, P]; g(f"{name}_in_place_{suf}").restype = None
+    for suf in ("f64", "f32", "c64", "c32"):
+        getattr(lib, f"faer_b200_hessenberg_in_place_{suf}").argtypes = [MatMut, MatMut]; getattr(lib, f"faer_b200_hessenberg_in_place_{suf}").restype = None
     for suf in ("f64", "f32"):
         getattr(lib, f"faer_b200_bidiag_in_place_{suf}").argtypes = [MatMut, MatMut, MatMut]; getattr(lib, f"faer_b200_bidiag_in_place_{suf}").restype = None
         getattr(lib, f"faer_b200_tridiag_in_place_{suf}").argtypes = [MatMut, MatMut]; getattr(lib, f"faer_b200_tridiag_in_place_{suf}").restype = None
@@ -189,3 +191,9 @@ def test_invert_triangular_through_the_abi(host_fb):
     T = importlib.import_module("test_gpu_zzzzzzzzz_inverse_triangular")
     for dtype in T.DTYPES:
         T.test_invert_triangular(host_fb, None, dtype)
+
+
+def test_hessenberg_through_the_abi(host_fb, oracle):
+    T = importlib.import_module("test_gpu_zzzzzzzzz_hessenberg")
+    for dtype in T.DTYPES:
+        T.test_hessenberg(host_fb, oracle, None, dtype)

@@ -90,4 +90,15 @@ void cc_emul_widen_c32(const float* A, i64 rs, i64 cs, double* W, i64 m, i64 n) 
   run(WidenC32{A, rs, cs, (Cx*)W, m, m, n}, m, n);
 }
 
+
+// A: n x n interleaved complex (rs, cs). Outputs: W (n x n column-major: H + reflectors), tau (n - 1), Tf (bs x (n - 1) T blocks).
+long long cc_emul_hessenberg(const double* A, i64 rs, i64 cs, i64 n, double* W_, double* tau, double* Tf, i64 bs, int reverse) {
+  Cx* W = (Cx*)W_;
+  HostRun run{reverse != 0};
+  HostWork hw(n);
+  run(CopyIn{A, rs, cs, W, n, n, n, 0}, n, n);
+  hessenberg_unblocked(run, W, n, n, tau, hw.ws);
+  if (n > 1) run(BuildTBlocks{W + 1, n, n - 1, n - 1, tau, (Cx*)Tf, bs, bs}, bs, n - 1);
+  return run.launches;
+}
 }  // extern "C"
