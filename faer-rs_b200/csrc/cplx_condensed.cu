@@ -10,8 +10,8 @@
 // Arrangement: the reductions to condensed form are the unblocked launch sequences of cplx_condensed_core.cuh (flat maps, one thread
 // per row / element; the same source runs thread by thread on the host in tests/test_cplx_condensed_emul_cpu.py). The condensed
 // REAL problems go to the solvers the real entry points use (tridiag_dc.cu; the Golub-Kahan / QR-stabilised bidiagonal solver of
-// svd_vectors.cu), the back-transforms to the complex block-Householder sequence of cplx.cu with block size 1 (the taus are the
-// 1 x 1 T blocks). Functional, not tuned: O(n) launches per column and n-thread matrix-vector products — meant for the moderate
+// svd_vectors.cu), the back-transforms to the complex block-Householder sequence of cplx.cu with blocks of 32 reflectors (T blocks
+// from the BuildTBlocks body). Functional, not tuned: O(n) launches per column and n-thread matrix-vector products — meant for the moderate
 // sizes complex users of the C ABI bring, not for the BASELINE sizes of the real path.
 // The values-only calls (U / V not wanted) run the same path and skip the back-transforms.
 #include <algorithm>
@@ -39,6 +39,17 @@ struct DevWork {
     for (void* b : blocks) ws_free(b);
   }
 };
+
+// block size of the back-transforms and the T blocks of a reflector set (householder.rs:132-272): V = the m x s unit-lower trapezoid at
+// `V` (leading dimension ld), tau its s scalars; returns a zero-initialised bs x s factor (pool block) with the blocks filled in
+constexpr i64 BT_BS = 32;
+inline cc::Cx* build_t_blocks(cudaStream_t st, const cc::Cx* V, i64 ld, i64 m, i64 s, const double* tau, i64 bs) {
+  cc::Cx* Tf = (cc::Cx*)ws_alloc((size_t)bs * (size_t)s * sizeof(cc::Cx));
+  FB_CUDA_CHECK(cudaMemsetAsync(Tf, 0, (size_t)bs * (size_t)s * sizeof(cc::Cx), st));
+  DevRun run{st};
+  run(cc::BuildTBlocks{V, ld, m, s, tau, Tf, bs, bs}, bs, s);
+  return Tf;
+}
 
 // c64 view of the input: the view itself (TO = double) or a compact widened copy (TO = float; *owned receives the block)
 inline View<const double> as_c64(cudaStream_t st, View<const double> A, void** owned) {
@@ -88,11 +99,16 @@ bool self_adjoint_evd_cx(cudaStream_t st, View<const TO> A_in, View<TO> U, TO* S
       FB_ASSERT(U.nrows == n && U.ncols == n, "self_adjoint_evd: U must be n x n");
       cc::Cx* Uw = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
       run(cc::ScaleRowsEmbed{Q, n, n, ph, Uw, n, n, n}, n, n);  // diag(ph) Q
-      if (n > 1)  // rows 1.. <- H_0 H_1 ... H_{n-2} rows 1.. (evd/mod.rs:411-418); reflector k: column k of W below the subdiagonal
-        apply_householder_sequence_left_c64(st, VCD{(const double*)(W + 1), n - 1, n - 1, 1, n}, VCD{(const double*)tauc, 1, n - 1, 1, 1},
+      cc::Cx* Tf = nullptr;
+      if (n > 1) {  // rows 1.. <- H_0 H_1 ... H_{n-2} rows 1.. (evd/mod.rs:411-418); reflector k: column k of W below the subdiagonal
+        const i64 bs = std::min<i64>(BT_BS, n - 1);
+        Tf = build_t_blocks(st, W + 1, n, n - 1, n - 1, tau, bs);
+        apply_householder_sequence_left_c64(st, VCD{(const double*)(W + 1), n - 1, n - 1, 1, n}, VCD{(const double*)Tf, bs, n - 1, 1, bs},
                                             false, VD{(double*)(Uw + 1), n - 1, n, 1, n}, false);
+      }
       run(cc::CopyOut<TO>{U.ptr, U.rs, U.cs, Uw, n, n, n}, n, n);
       FB_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (Tf) ws_free(Tf);
       ws_free(Uw);
     }
     run(cc::CopyValues<TO>{S, sstride, lam, n}, n, 1);
@@ -152,27 +168,33 @@ bool svd_cx(cudaStream_t st, View<const TO> A_in, View<TO> U, TO* S, i64 sstride
     cc::Cx* Uw = (cc::Cx*)ws_alloc((size_t)m * (size_t)ku * sizeof(cc::Cx));
     run(cc::ScaleRowsEmbed{UB, n, n, l, Uw, m, m, ku}, m, ku);  // [diag(l) UB, 0; 0, I]
     // U = H_0 ... H_{n-1} [.]: left reflector k is column k of W below the diagonal (svd/mod.rs:403-412, Conj::No)
-    apply_householder_sequence_left_c64(st, VCD{(const double*)W, m, n, 1, m}, VCD{(const double*)tlc, 1, n, 1, 1}, false,
+    const i64 bs = std::min<i64>(BT_BS, n);
+    cc::Cx* Tf = build_t_blocks(st, W, m, m, n, tl, bs);
+    apply_householder_sequence_left_c64(st, VCD{(const double*)W, m, n, 1, m}, VCD{(const double*)Tf, bs, n, 1, bs}, false,
                                         VD{(double*)Uw, m, ku, 1, m}, false);
     run(cc::CopyOut<TO>{Um.ptr, Um.rs, Um.cs, Uw, m, m, ku}, m, ku);
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    ws_free(Tf);
     ws_free(Uw);
   }
   if (ok && want_v) {
     FB_ASSERT(Vm.nrows == n && Vm.ncols == n, "svd: the right factor must be ncols x ncols");
     cc::Cx* Vw = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
     run(cc::ScaleRowsEmbed{VB, n, n, r, Vw, n, n, n}, n, n);  // diag(r) VB
-    cc::Cx* T = nullptr;
+    cc::Cx *T = nullptr, *Tfr = nullptr;
     if (n > 1) {
       // the right reflectors are the rows of W right of the superdiagonal: transposed copy, sequence with Conj::Yes on rows 1..
       // (svd/mod.rs:413-428)
       T = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
       run(cc::TransposeCorner{W, m, T, n, n}, n, n);
-      apply_householder_sequence_left_c64(st, VCD{(const double*)(T + 1), n - 1, n - 1, 1, n}, VCD{(const double*)trc, 1, n - 1, 1, 1}, true,
+      const i64 bs = std::min<i64>(BT_BS, n - 1);
+      Tfr = build_t_blocks(st, T + 1, n, n - 1, n - 1, tr, bs);
+      apply_householder_sequence_left_c64(st, VCD{(const double*)(T + 1), n - 1, n - 1, 1, n}, VCD{(const double*)Tfr, bs, n - 1, 1, bs}, true,
                                           VD{(double*)(Vw + 1), n - 1, n, 1, n}, false);
     }
     run(cc::CopyOut<TO>{Vm.ptr, Vm.rs, Vm.cs, Vw, n, n, n}, n, n);
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (Tfr) ws_free(Tfr);
     if (T) ws_free(T);
     ws_free(Vw);
   }
