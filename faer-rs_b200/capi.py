@@ -354,7 +354,7 @@ def load() -> C.CDLL:
     lib.faer_b200_profile_begin.restype = None
     lib.faer_b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
     lib.faer_b200_profile_end.restype = None
-    for suf in ("f64", "f32"):
+    for suf in ("f64", "f32", "c64", "c32"):
         f = getattr(lib, f"faer_b200_bidiag_in_place_{suf}")
         f.argtypes = [MatMut, MatMut, MatMut]
         f.restype = None

@@ -210,6 +210,73 @@ bool svd_cx(cudaStream_t st, View<const TO> A_in, View<TO> U, TO* S, i64 sstride
   return ok;
 }
 
+// svd::bidiag::bidiag_in_place (svd/bidiag.rs:47-256) and evd::tridiag::tridiag_in_place (evd/tridiag.rs:274-529) for complex T as
+// extensions (the real dtypes have their HBM-bound kernels in bidiag.cu / tridiag.cu): the unblocked sequences of
+// cplx_condensed_core.cuh and the T blocks of the reflectors in the layout the reference returns.
+template <class TO>
+void bidiag_in_place_cx(cudaStream_t st, View<TO> A, View<TO> Hl, View<TO> Hr) {
+  const i64 m = A.nrows, n = A.ncols, bl = Hl.nrows, br = Hr.nrows;
+  FB_ASSERT(m >= n, "bidiag_in_place: nrows >= ncols required (the SVD driver works on the adjoint of wide inputs)");
+  FB_ASSERT(Hl.ncols == n && Hr.ncols == (n > 0 ? n - 1 : 0) && (n == 0 || bl > 0) && (n <= 1 || br > 0), "bidiag_in_place: Householder factor shapes");
+  if (n == 0) return;
+  DevRun run{st};
+  void* owned = nullptr;
+  const View<const double> Ac = as_c64(st, View<const TO>{A.ptr, m, n, A.rs, A.cs}, &owned);
+  cc::Cx* W = (cc::Cx*)ws_alloc((size_t)m * (size_t)n * sizeof(cc::Cx));
+  run(cc::CopyIn{Ac.ptr, Ac.rs, Ac.cs, W, m, m, n, 0}, m, n);
+  DevWork work(m);
+  double* taus = (double*)ws_alloc((size_t)(2 * n + 2) * sizeof(double));
+  double *tl = taus, *tr = taus + n;
+  FB_CUDA_CHECK(cudaMemsetAsync(taus, 0, (size_t)(2 * n + 2) * sizeof(double), st));
+  cc::bidiag_unblocked(run, W, m, m, n, tl, tr, work.ws);
+  cc::Cx* Tl = build_t_blocks(st, W, m, m, n, tl, bl);
+  cc::Cx *T = nullptr, *Tr = nullptr;
+  if (n > 1) {  // the right reflectors as columns (svd/bidiag.rs:239-255: the factor of the transposed rows)
+    T = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
+    run(cc::TransposeCorner{W, m, T, n, n}, n, n);
+    Tr = build_t_blocks(st, T + 1, n, n - 1, n - 1, tr, br);
+  }
+  run(cc::CopyOut<TO>{A.ptr, A.rs, A.cs, W, m, m, n}, m, n);
+  run(cc::CopyOut<TO>{Hl.ptr, Hl.rs, Hl.cs, Tl, bl, bl, n}, bl, n);
+  if (n > 1) run(cc::CopyOut<TO>{Hr.ptr, Hr.rs, Hr.cs, Tr, br, br, n - 1}, br, n - 1);
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (Tr) ws_free(Tr);
+  if (T) ws_free(T);
+  ws_free(Tl);
+  ws_free(taus);
+  work.release();
+  ws_free(W);
+  if (owned) ws_free(owned);
+}
+template <class TO>
+void tridiag_in_place_cx(cudaStream_t st, View<TO> A, View<TO> H) {
+  const i64 n = A.nrows, b = H.nrows;
+  FB_ASSERT(A.ncols == n && H.ncols == (n > 0 ? n - 1 : 0) && (n <= 1 || b > 0), "tridiag_in_place: square A, householder factor b x (n - 1)");
+  if (n == 0) return;
+  DevRun run{st};
+  void* owned = nullptr;
+  const View<const double> Ac = as_c64(st, View<const TO>{A.ptr, n, n, A.rs, A.cs}, &owned);
+  cc::Cx* W = (cc::Cx*)ws_alloc((size_t)n * (size_t)n * sizeof(cc::Cx));
+  run(cc::BuildHermitian{Ac.ptr, Ac.rs, Ac.cs, W, n, n}, n, n);
+  DevWork work(n);
+  double* tau = (double*)ws_alloc((size_t)(n + 1) * sizeof(double));
+  FB_CUDA_CHECK(cudaMemsetAsync(tau, 0, (size_t)(n + 1) * sizeof(double), st));
+  cc::tridiag_unblocked(run, W, n, n, tau, work.ws);
+  cc::Cx* Tf = n > 1 ? build_t_blocks(st, W + 1, n, n - 1, n - 1, tau, b) : nullptr;
+  run(cc::CopyOutLower<TO>{A.ptr, A.rs, A.cs, W, n, n}, n, n);  // only the lower triangle is written (tridiag.rs:274-280)
+  if (n > 1) run(cc::CopyOut<TO>{H.ptr, H.rs, H.cs, Tf, b, b, n - 1}, b, n - 1);
+  FB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (Tf) ws_free(Tf);
+  ws_free(tau);
+  work.release();
+  ws_free(W);
+  if (owned) ws_free(owned);
+}
+template void bidiag_in_place_cx<double>(cudaStream_t, View<double>, View<double>, View<double>);
+template void bidiag_in_place_cx<float>(cudaStream_t, View<float>, View<float>, View<float>);
+template void tridiag_in_place_cx<double>(cudaStream_t, View<double>, View<double>);
+template void tridiag_in_place_cx<float>(cudaStream_t, View<float>, View<float>);
+
 // evd::hessenberg::hessenberg_in_place (evd/hessenberg.rs:549-567) as an extension (the reference does not export it through its C
 // ABI): A <- its upper Hessenberg form H = Q^H A Q in the entries (i, j) with i <= j + 1 and the reflectors of Q = H_0 ... H_{n-2} below
 // the subdiagonal; Hf (bs x (n - 1)) <- their T blocks (diag tau, V^H V above it inside each block), the layout the block-Householder

@@ -213,7 +213,8 @@ struct Rank2 {
   CC_HD void operator()(i64 i, i64 j) const {
     if (i >= len || j >= len || sc[SC_SKIP] != 0.0) return;
     Cx* a = W + (r0 + i) + (r0 + j) * ld;
-    const Cx t = cadd(cmul(v[i], cconj(w[j])), cmul(w[i], cconj(v[j])));
+    Cx t = cadd(cmul(v[i], cconj(w[j])), cmul(w[i], cconj(v[j])));
+    if (i == j) t.im = 0.0;  // v conj(w) + w conj(v) is real: the diagonal of a self-adjoint matrix stays exactly real
     *a = csub(*a, t);
   }
 };
@@ -293,6 +294,17 @@ struct CopyOut {
   TO* out; i64 rs, cs; const Cx* src; i64 lds, rows, cols;
   CC_HD void operator()(i64 i, i64 j) const {
     if (i >= rows || j >= cols) return;
+    const Cx v = src[i + j * lds];
+    TO* p = out + 2 * (i * rs + j * cs);
+    p[0] = (TO)v.re; p[1] = (TO)v.im;
+  }
+};
+// the LOWER triangle of the out view <- the lower triangle of src (n x n); nothing above the diagonal is written
+template <class TO>
+struct CopyOutLower {
+  TO* out; i64 rs, cs; const Cx* src; i64 lds, n;
+  CC_HD void operator()(i64 i, i64 j) const {
+    if (i >= n || j >= n || i < j) return;
     const Cx v = src[i + j * lds];
     TO* p = out + 2 * (i * rs + j * cs);
     p[0] = (TO)v.re; p[1] = (TO)v.im;

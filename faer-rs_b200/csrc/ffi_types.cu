@@ -303,6 +303,29 @@ void hessenberg_entry_t(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
   finish_all(st, {&a, &h});
 }
 
+// complex reductions to condensed form (extensions; cplx_condensed.cu)
+template <class R>
+void bidiag_entry_cx(FaerV0_24_MatMut A, FaerV0_24_MatMut Hl, FaerV0_24_MatMut Hr) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t es = 2 * sizeof(R);
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, es, true, true, st);
+  StagedMat hl(Hl.ptr, (i64)Hl.nrows, (i64)Hl.ncols, (i64)Hl.row_stride, (i64)Hl.col_stride, es, false, true, st);
+  StagedMat hr(Hr.ptr, (i64)Hr.nrows, (i64)Hr.ncols, (i64)Hr.row_stride, (i64)Hr.col_stride, es, false, true, st);
+  bidiag_in_place_cx<R>(st, a.view<R>(), hl.view<R>(), hr.view<R>());
+  finish_all(st, {&a, &hl, &hr});
+}
+template <class R>
+void tridiag_entry_cx(FaerV0_24_MatMut A, FaerV0_24_MatMut H) {
+  FB_ENTRY();
+  cudaStream_t st = current_stream();
+  const size_t es = 2 * sizeof(R);
+  StagedMat a(A.ptr, (i64)A.nrows, (i64)A.ncols, (i64)A.row_stride, (i64)A.col_stride, es, true, true, st);
+  StagedMat h(H.ptr, (i64)H.nrows, (i64)H.ncols, (i64)H.row_stride, (i64)H.col_stride, es, false, true, st);
+  tridiag_in_place_cx<R>(st, a.view<R>(), h.view<R>());
+  finish_all(st, {&a, &h});
+}
+
 }  // namespace
 
 extern "C" {
@@ -315,6 +338,10 @@ void faer_b200_bidiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, 
   bidiag_entry<float>(A, H_left, H_right);
 }
 
+void faer_b200_bidiag_in_place_c64(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) { bidiag_entry_cx<double>(A, H_left, H_right); }
+void faer_b200_bidiag_in_place_c32(FaerV0_24_MatMut A, FaerV0_24_MatMut H_left, FaerV0_24_MatMut H_right) { bidiag_entry_cx<float>(A, H_left, H_right); }
+void faer_b200_tridiag_in_place_c64(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry_cx<double>(A, householder); }
+void faer_b200_tridiag_in_place_c32(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry_cx<float>(A, householder); }
 void faer_b200_tridiag_in_place_f64(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<double>(A, householder); }
 void faer_b200_tridiag_in_place_f32(FaerV0_24_MatMut A, FaerV0_24_MatMut householder) { tridiag_entry<float>(A, householder); }
 

@@ -83,6 +83,11 @@ template <class TO>
 bool svd_cx(cudaStream_t st, View<const TO> A, View<TO> U, TO* S, i64 sstride, View<TO> V);
 template <class TO>
 bool self_adjoint_evd_cx(cudaStream_t st, View<const TO> A, View<TO> U, TO* S, i64 sstride);
+// complex bidiagonalization / tridiagonalization with T blocks (TO = double: c64, float: c32 computed in c64; complex-unit views)
+template <class TO>
+void bidiag_in_place_cx(cudaStream_t st, View<TO> A, View<TO> Hl, View<TO> Hr);
+template <class TO>
+void tridiag_in_place_cx(cudaStream_t st, View<TO> A, View<TO> H);
 // A <- upper Hessenberg form + reflectors, Hf (bs x (n - 1)) <- T blocks (evd/hessenberg.rs:549-567); <TO, complex?>: <double, false> f64,
 // <float, false> f32, <double, true> c64, <float, true> c32 (complex views in complex units)
 template <class TO, bool CX>

@@ -659,12 +659,11 @@ def self_adjoint_evd(A, S, U=None, par=None, params=None) -> None:
 
 
 def bidiag_in_place(A, H_left, H_right, par=None, params=None) -> None:
-    """svd::bidiag::bidiag_in_place (svd/bidiag.rs:47-256): A = U B V^H for nrows >= ncols, f64 or f32. B ends up on A's
+    """svd::bidiag::bidiag_in_place (svd/bidiag.rs:47-256): A = U B V^H for nrows >= ncols, f64 / f32 (HBM-bound kernels) or c64 / c32 (functional). B ends up on A's
     diagonal / superdiagonal, the left reflectors below the diagonal (T blocks in H_left, bl x ncols), the right
     reflectors to the right of the superdiagonal (T blocks in H_right, br x (ncols - 1))."""
     lib = capi.load()
-    suf = _suf(A)
-    assert _suf(H_left) == suf and _suf(H_right) == suf
+    suf = _same_suffix(A, H_left, H_right)
     getattr(lib, f"faer_b200_bidiag_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(H_left), capi.mat_mut(H_right))
 
 
@@ -678,11 +677,10 @@ def hessenberg_in_place(A, householder, par=None, params=None) -> None:
 
 def tridiag_in_place(A, householder, par=None, params=None) -> None:
     """evd::tridiag::tridiag_in_place (evd/tridiag.rs:274-529): A = Q T Q^H for a self-adjoint A (only the lower triangle
-    is read / written), f64 or f32. T ends up on A's diagonal / subdiagonal, the reflectors below the subdiagonal, their
-    T blocks in `householder` (b x (n - 1))."""
+    is read / written), f64 / f32 (HBM-bound kernel) or c64 / c32 (functional). T ends up on A's diagonal / subdiagonal, the
+    reflectors below the subdiagonal, their T blocks in `householder` (b x (n - 1))."""
     lib = capi.load()
-    suf = _suf(A)
-    assert _suf(householder) == suf
+    suf = _same_suffix(A, householder)
     getattr(lib, f"faer_b200_tridiag_in_place_{suf}")(capi.mat_mut(A), capi.mat_mut(householder))
 
 

@@ -603,11 +603,16 @@ long long faer_b200_dist_qr_factor_in_place_f32(void *A_local, size_t ld, size_t
  * right reflectors right of the superdiagonal with H_right (br x (ncols-1)). Device matrices must be column-major. */
 void faer_b200_bidiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
 void faer_b200_bidiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
+/* complex T: the functional unblocked sequences of csrc/cplx_condensed_core.cuh (any layout) */
+void faer_b200_bidiag_in_place_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
+void faer_b200_bidiag_in_place_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
 /* ---- reduction to tridiagonal form A = Q T Q^H of a self-adjoint matrix (lower triangle read and written). Reached in the reference through libfaer_v0_23_self_adjoint_evd_* (faer-ffi/src/lib.rs:2382-2400 ->
  * faer/src/linalg/evd/mod.rs); mirrors faer::linalg::evd::tridiag::tridiag_in_place (faer/src/linalg/evd/tridiag.rs:274-280):
  * T on A's diagonal / subdiagonal, reflectors below the subdiagonal, `householder` (b x (n-1)) holds their T blocks. */
 void faer_b200_tridiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
 void faer_b200_tridiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+void faer_b200_tridiag_in_place_c64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
+void faer_b200_tridiag_in_place_c32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut householder);
 /* ---- reduction to upper Hessenberg form A = Q H Q^H (general square matrix). faer-ffi exports only the parameter structs of this
  * stage (FaerV0_24_HessenbergParams, faer.h:110-113); the entry mirrors faer::linalg::evd::hessenberg::hessenberg_in_place (faer/src/linalg/evd/hessenberg.rs:549-567):
  * H in the entries (i, j) with i <= j + 1, the reflectors of Q = H_0 ... H_{n-2} below the subdiagonal, `householder` (b x (n-1))

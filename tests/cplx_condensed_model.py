@@ -61,6 +61,7 @@ def tridiag_unblocked(A):
         K = np.vdot(v, p) / (2.0 * tau)
         w = p - K * v
         A22 -= np.outer(v, w.conj()) + np.outer(w, v.conj())
+        A22[np.diag_indices(A22.shape[0])] = A22[np.diag_indices(A22.shape[0])].real  # the diagonal stays exactly real
     return W, taus
 
 

@@ -92,7 +92,7 @@ def hostlib(tmp_path_factory, fb, oracle):
             g(f"{name}_in_place_{suf}").argtypes = [MatMut, MatRef, P]; g(f"{name}_in_place_{suf}").restype = None
     for suf in ("f64", "f32", "c64", "c32"):
         getattr(lib, f"faer_b200_hessenberg_in_place_{suf}").argtypes = [MatMut, MatMut]; getattr(lib, f"faer_b200_hessenberg_in_place_{suf}").restype = None
-    for suf in ("f64", "f32"):
+    for suf in ("f64", "f32", "c64", "c32"):
         getattr(lib, f"faer_b200_bidiag_in_place_{suf}").argtypes = [MatMut, MatMut, MatMut]; getattr(lib, f"faer_b200_bidiag_in_place_{suf}").restype = None
         getattr(lib, f"faer_b200_tridiag_in_place_{suf}").argtypes = [MatMut, MatMut]; getattr(lib, f"faer_b200_tridiag_in_place_{suf}").restype = None
     yield lib
@@ -197,3 +197,10 @@ def test_hessenberg_through_the_abi(host_fb, oracle):
     T = importlib.import_module("test_gpu_zzzzzzzzz_hessenberg")
     for dtype in T.DTYPES:
         T.test_hessenberg(host_fb, oracle, None, dtype)
+
+
+def test_cplx_condensed_forms_through_the_abi(host_fb, oracle):
+    T = importlib.import_module("test_gpu_zzzzzzzzz_cplx_condensed_forms")
+    for dtype in T.CDTYPES:
+        T.test_cplx_bidiag_vs_oracle(host_fb, oracle, None, dtype)
+        T.test_cplx_tridiag_vs_oracle(host_fb, oracle, None, dtype)
