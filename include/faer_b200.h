@@ -600,7 +600,8 @@ long long faer_b200_dist_qr_factor_in_place_f32(void *A_local, size_t ld, size_t
  * reached through libfaer_v0_23_svd_*, faer-ffi/src/lib.rs:2345-2366 -> faer/src/linalg/svd/mod.rs:326-431); the entry
  * mirrors the Rust function it replaces, faer::linalg::svd::bidiag::bidiag_in_place (faer/src/linalg/svd/bidiag.rs:47-54):
  * B on A's diagonal / superdiagonal, left reflectors below the diagonal with H_left (bl x ncols) holding their T blocks,
- * right reflectors right of the superdiagonal with H_right (br x (ncols-1)). Device matrices must be column-major. */
+ * right reflectors right of the superdiagonal with H_right (br x (ncols-1)). Any layout (views that are not column-major go through a
+ * compact column-major copy). */
 void faer_b200_bidiag_in_place_f64(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
 void faer_b200_bidiag_in_place_f32(struct FaerV0_24_MatMut A, struct FaerV0_24_MatMut H_left, struct FaerV0_24_MatMut H_right);
 /* complex T: the functional unblocked sequences of csrc/cplx_condensed_core.cuh (any layout) */
