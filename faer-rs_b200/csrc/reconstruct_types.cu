@@ -10,7 +10,7 @@
 //   lu/partial_pivoting/inverse.rs:11-49       A^-1 from the factors; here as the LU solve applied to the identity
 //   qr/no_pivoting/reconstruct.rs:13-39 out = [R; 0], then out <- Q out (sequence on the left, Conj::No)
 //   qr/no_pivoting/inverse.rs:11-43     A^-1 = R^-1 Q^H; here as the QR solve applied to the identity (Q^H first, then R^-1)
-// Tests: tests/test_gpu_zzzzzzzzz_reconstruct_types.py.
+// Tests: tests/test_gpu_zzzzzzzzz_2_reconstruct_types.py.
 #include <algorithm>
 #include <type_traits>
 

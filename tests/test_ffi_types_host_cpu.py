@@ -152,7 +152,7 @@ def host_fb(fb, oracle, hostlib, monkeypatch):
 
 
 def test_reconstruct_types_through_the_abi(host_fb):
-    T = importlib.import_module("test_gpu_zzzzzzzzz_reconstruct_types")
+    T = importlib.import_module("test_gpu_zzzzzzzzz_2_reconstruct_types")
     for dtype in T.DTYPES:
         T.test_llt_reconstruct_and_inverse_types(host_fb, None, dtype)
         T.test_qr_reconstruct_and_inverse_types(host_fb, None, dtype)
@@ -161,7 +161,7 @@ def test_reconstruct_types_through_the_abi(host_fb):
 
 
 def test_ldlt_types_through_the_abi(host_fb, oracle):
-    T = importlib.import_module("test_gpu_zzzzzzzzz_ldlt_types")
+    T = importlib.import_module("test_gpu_zzzzzzzzz_3_ldlt_types")
     for dtype in T.FS_DTYPES:
         T.test_ldlt_types_vs_oracle(host_fb, oracle, None, dtype)
         T.test_ldlt_types_zero_pivot_and_regularisation(host_fb, oracle, None, dtype)
@@ -181,26 +181,26 @@ def test_cplx_svd_evd_through_the_abi(host_fb):
 
 
 def test_condensed_extension_layouts_through_the_abi(host_fb):
-    T = importlib.import_module("test_gpu_zzzzzzzzz_condensed_layouts")
+    T = importlib.import_module("test_gpu_zzzzzzzzz_4_condensed_layouts")
     for dtype in (np.float64, np.float32):
         T.test_bidiag_row_major_and_strided_host_views(host_fb, None, dtype)
         T.test_tridiag_row_major_and_strided_host_views(host_fb, None, dtype)
 
 
 def test_invert_triangular_through_the_abi(host_fb):
-    T = importlib.import_module("test_gpu_zzzzzzzzz_inverse_triangular")
+    T = importlib.import_module("test_gpu_zzzzzzzzz_1_inverse_triangular")
     for dtype in T.DTYPES:
         T.test_invert_triangular(host_fb, None, dtype)
 
 
 def test_hessenberg_through_the_abi(host_fb, oracle):
-    T = importlib.import_module("test_gpu_zzzzzzzzz_hessenberg")
+    T = importlib.import_module("test_gpu_zzzzzzzzz_5_hessenberg")
     for dtype in T.DTYPES:
         T.test_hessenberg(host_fb, oracle, None, dtype)
 
 
 def test_cplx_condensed_forms_through_the_abi(host_fb, oracle):
-    T = importlib.import_module("test_gpu_zzzzzzzzz_cplx_condensed_forms")
+    T = importlib.import_module("test_gpu_zzzzzzzzz_6_cplx_condensed_forms")
     for dtype in T.CDTYPES:
         T.test_cplx_bidiag_vs_oracle(host_fb, oracle, None, dtype)
         T.test_cplx_tridiag_vs_oracle(host_fb, oracle, None, dtype)

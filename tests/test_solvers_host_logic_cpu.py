@@ -106,7 +106,7 @@ def test_ldlt_class_on_complex_and_f32(fb, oracle, monkeypatch):
     import importlib
     sv = fb.solvers
     monkeypatch.setattr(sv, "la", oracle_backed_la(fb, oracle))
-    gpu_case = importlib.import_module("test_gpu_zzzzzzzzz_ldlt_types").test_ldlt_solver_class_other_dtypes
+    gpu_case = importlib.import_module("test_gpu_zzzzzzzzz_3_ldlt_types").test_ldlt_solver_class_other_dtypes
     for dtype in (np.complex128, np.float32):
         gpu_case(fb, None, dtype)
 

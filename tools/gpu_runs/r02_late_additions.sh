@@ -6,7 +6,7 @@
 set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/late_build.log 2>&1
-for f in test_gpu_zzzzzzzzz_condensed_layouts test_gpu_zzzzzzzzz_cplx_condensed_forms test_gpu_zzzzzzzzz_hessenberg test_gpu_zzzzzzzzz_inverse_triangular test_gpu_zzzzzzzzz_ldlt_types test_gpu_zzzzzzzzz_reconstruct_types test_gpu_zzzzzzzzzz_cplx_svd_evd; do
+for f in test_gpu_zzzzzzzzz_1_inverse_triangular test_gpu_zzzzzzzzz_2_reconstruct_types test_gpu_zzzzzzzzz_3_ldlt_types test_gpu_zzzzzzzzz_4_condensed_layouts test_gpu_zzzzzzzzz_5_hessenberg test_gpu_zzzzzzzzz_6_cplx_condensed_forms test_gpu_zzzzzzzzzz_cplx_svd_evd; do
   timeout 800 python -m pytest tests/$f.py -q -m gpu -x > gpurun_out/late_$f.log 2>&1
   echo "$f: exit $?" | tee -a gpurun_out/late_summary.log
   tail -3 gpurun_out/late_$f.log | tee -a gpurun_out/late_summary.log
